@@ -1,0 +1,338 @@
+"""TEST INFRASTRUCTURE — ctypes bindings for the CPU oracle (oracle/librisk_oracle.so, the C
+restatement in risk_oracle.c) and, when it has been built, for the compiled reference
+(oracle/_ref/libref_oracle.so, see oracle/ref/build_ref.sh).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package alphazero_risk_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "librisk_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libref_oracle.so")
+
+LANDS, MOVES, SKIP, NONE = 42, 43, 42, 43
+DATA_BYTES, INPUT_FLOATS = 160, 546
+STREAM_REAL, STREAM_DEAL = 0xFFFFFFFF, 0xFFFFFFFE
+PHASES = ("SETUP", "SETUP_NEUTRAL", "REINFORCEMENT", "ATTACK", "ATTACK_MOBILIZATION", "FORTIFY")
+
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", HERE, "librisk_oracle.so"])
+
+
+def build_ref():
+    subprocess.check_call(["bash", os.path.join(HERE, "ref", "build_ref.sh")])
+
+
+class RoState(C.Structure):
+    _fields_ = [("land", C.c_uint8 * 42), ("cards", C.c_uint8 * 2), ("round", C.c_uint16), ("cur", C.c_int8),
+                ("card_sets", C.c_uint8), ("reinf", C.c_uint8), ("phase", C.c_uint8), ("mob_from", C.c_uint8),
+                ("mob_to", C.c_uint8), ("allow_draw", C.c_uint8), ("attacks", C.c_uint8)]
+
+
+class RoRules(C.Structure):
+    _fields_ = [("allow_yield", C.c_int), ("limit_reinforcement", C.c_int), ("limit_attack", C.c_int),
+                ("max_game_rounds", C.c_int), ("min_unit_move", C.c_int), ("mcts_simulations", C.c_int),
+                ("threads_per_mcts", C.c_int), ("cpuct", C.c_float), ("dir_noise_value", C.c_float),
+                ("dir_noise_epsi", C.c_float), ("temperature_threshold", C.c_int)]
+
+
+class RoDice(C.Structure):
+    _fields_ = [("use_tape", C.c_int), ("seed", C.c_uint64), ("game", C.c_uint32), ("ply", C.c_uint32),
+                ("sim", C.c_uint32), ("j", C.c_uint32), ("tape", C.POINTER(C.c_int32)), ("tape_len", C.c_int),
+                ("tape_pos", C.c_int)]
+
+
+class BenchOut(C.Structure):
+    _fields_ = [("steps", C.c_uint64), ("games", C.c_uint64), ("sims", C.c_uint64), ("evals", C.c_uint64),
+                ("moves", C.c_uint64), ("seconds", C.c_double)]
+
+
+_oracle = None
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        L = C.CDLL(ORACLE_SO)
+        sp, rp, dp = C.POINTER(RoState), C.POINTER(RoRules), C.POINTER(RoDice)
+        L.ro_default_rules.argtypes = [rp]
+        L.ro_dice_philox.argtypes = [dp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.ro_export_data.argtypes = [sp, u8p]
+        L.ro_import_data.argtypes = [sp, u8p]
+        L.ro_data_byte_mask.argtypes = [u8p]
+        L.ro_new_game.argtypes = [sp, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.ro_new_game_tape.argtypes = [sp, i32p]
+        L.ro_valid_moves.argtypes = [sp, rp]
+        L.ro_valid_moves.restype = C.c_uint64
+        L.ro_game_status.argtypes = [sp, rp]
+        L.ro_reinforcement_value.argtypes = [C.c_uint64]
+        L.ro_make_move.argtypes = [sp, C.c_int, rp, dp]
+        L.ro_random_action.argtypes = [sp, rp, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.ro_encode.argtypes = [sp, f32p]
+        L.ro_normalize_policy.argtypes = [f32p, C.c_uint64]
+        L.ro_mcts_new.restype = C.c_void_p
+        L.ro_mcts_new.argtypes = [C.c_void_p, C.c_void_p]
+        for fn in ("ro_mcts_free", "ro_mcts_clear", "ro_mcts_trim", "ro_mcts_table_size"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+        L.ro_mcts_search.argtypes = [C.c_void_p, sp, rp, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p, f32p, f32p,
+                                     C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        L.ro_pick_move.argtypes = [f32p, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.ro_bench_env.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(BenchOut)]
+        _oracle = L
+    return _oracle
+
+
+def data_byte_mask():
+    m = np.zeros(DATA_BYTES, np.uint8)
+    oracle_lib().ro_data_byte_mask(m)
+    return m.astype(bool)
+
+
+def default_rules(**kw):
+    r = RoRules()
+    oracle_lib().ro_default_rules(C.byref(r))
+    for k, v in kw.items():
+        setattr(r, k, v)
+    return r
+
+
+class OracleGame:
+    """One game driven through the C restatement."""
+
+    def __init__(self, rules=None):
+        self.L = oracle_lib()
+        self.s = RoState()
+        self.rules = rules if rules is not None else default_rules()
+
+    def new_game(self, seed, game, ply=0):
+        self.L.ro_new_game(C.byref(self.s), seed, game, ply)
+
+    def new_game_tape(self, draws):
+        self.L.ro_new_game_tape(C.byref(self.s), np.ascontiguousarray(draws, np.int32))
+
+    def data(self):
+        out = np.zeros(DATA_BYTES, np.uint8)
+        self.L.ro_export_data(C.byref(self.s), out)
+        return out
+
+    def set_data(self, data):
+        return self.L.ro_import_data(C.byref(self.s), np.ascontiguousarray(data, np.uint8))
+
+    def valid(self):
+        return int(self.L.ro_valid_moves(C.byref(self.s), C.byref(self.rules)))
+
+    def status(self):
+        return int(self.L.ro_game_status(C.byref(self.s), C.byref(self.rules)))
+
+    def random_action(self, seed, game, ply):
+        return int(self.L.ro_random_action(C.byref(self.s), C.byref(self.rules), seed, game, ply))
+
+    def move(self, action, seed, game, ply, sim=STREAM_REAL):
+        d = RoDice()
+        self.L.ro_dice_philox(C.byref(d), seed, game, ply, sim)
+        return int(self.L.ro_make_move(C.byref(self.s), action, C.byref(self.rules), C.byref(d)))
+
+    def move_tape(self, action, dice):
+        tape = np.ascontiguousarray(dice, np.int32)
+        d = RoDice()
+        d.use_tape = 1
+        d.tape = tape.ctypes.data_as(C.POINTER(C.c_int32))
+        d.tape_len = len(tape)
+        rc = int(self.L.ro_make_move(C.byref(self.s), action, C.byref(self.rules), C.byref(d)))
+        return rc, int(d.tape_pos)
+
+    def encode(self):
+        x = np.zeros(INPUT_FLOATS, np.float32)
+        self.L.ro_encode(C.byref(self.s), x)
+        return x
+
+
+class OracleMcts:
+    def __init__(self, rules=None, evaluator="pseudo"):
+        self.L = oracle_lib()
+        self.rules = rules if rules is not None else default_rules()
+        fn = {"pseudo": self.L.ro_eval_pseudo, "uniform": self.L.ro_eval_uniform}[evaluator]
+        self.h = self.L.ro_mcts_new(C.cast(fn, C.c_void_p), None)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ro_mcts_free(self.h)
+            self.h = None
+
+    def clear(self):
+        self.L.ro_mcts_clear(self.h)
+
+    def trim(self):
+        self.L.ro_mcts_trim(self.h)
+
+    def table_size(self):
+        return int(self.L.ro_mcts_table_size(self.h))
+
+    def search(self, game_obj, seed, game, ply):
+        N = np.zeros(MOVES, np.uint32)
+        Q = np.zeros(MOVES, np.float32)
+        P = np.zeros(MOVES, np.float32)
+        pi = np.zeros(MOVES, np.float32)
+        sumN, val = C.c_uint32(0), C.c_float(0)
+        rc = self.L.ro_mcts_search(self.h, C.byref(game_obj.s), C.byref(self.rules), seed, game, ply, N, Q, P, pi,
+                                   C.byref(sumN), C.byref(val))
+        assert rc == 0, rc
+        return dict(N=N, Q=Q, P=P, pi=pi, sumN=int(sumN.value), value=float(val.value))
+
+    def pick(self, pi, sample, seed, game, ply):
+        return int(self.L.ro_pick_move(np.ascontiguousarray(pi, np.float32), int(sample), seed, game, ply))
+
+
+# --------------------------------------------------------------------------- compiled reference
+_ref = None
+
+
+def ref_available():
+    return os.path.exists(REF_SO)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_SO)
+        vp = C.c_void_p
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_state_new.restype = vp
+        L.ref_state_free.argtypes = [vp]
+        L.ref_state_get.argtypes = [vp, u8p]
+        L.ref_state_set.argtypes = [vp, u8p]
+        L.ref_state_newgame_philox.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.ref_state_newgame_tape.argtypes = [vp, i32p, C.c_int]
+        L.ref_valid_moves.argtypes = [vp]
+        L.ref_valid_moves.restype = C.c_uint64
+        L.ref_game_status.argtypes = [vp]
+        L.ref_make_move_philox.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.ref_make_move_tape.argtypes = [vp, C.c_int, i32p, C.c_int]
+        L.ref_random_action_philox.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.ref_encode.argtypes = [vp, f32p]
+        L.ref_normalize_policy.argtypes = [f32p, C.c_uint64]
+        L.ref_consistency_violations.argtypes = [vp]
+        L.ref_get_map.argtypes = [np.ctypeslib.ndpointer(np.uint64), np.ctypeslib.ndpointer(np.int8),
+                                  np.ctypeslib.ndpointer(np.uint64), i32p]
+        L.ref_get_default_settings.argtypes = [f32p]
+        L.ref_set_settings.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int]
+        L.ref_mcts_new.restype = vp
+        L.ref_mcts_new.argtypes = [vp, vp]
+        for fn in ("ref_mcts_free", "ref_mcts_clear", "ref_mcts_trim", "ref_mcts_table_size"):
+            getattr(L, fn).argtypes = [vp]
+        L.ref_mcts_evals.argtypes = [vp]
+        L.ref_mcts_evals.restype = C.c_uint64
+        L.ref_mcts_search.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p, f32p, f32p,
+                                      C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        L.ref_pick_move.argtypes = [vp, f32p, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.ref_bench_env.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.POINTER(BenchOut)]
+        L.ref_bench_selfplay.argtypes = [C.c_int, C.c_uint64, C.c_uint32, vp, vp, C.POINTER(BenchOut)]
+        _ref = L
+    return _ref
+
+
+def ref_apply_rules(rules):
+    ref_lib().ref_set_settings(rules.mcts_simulations, rules.threads_per_mcts, rules.cpuct, rules.dir_noise_value,
+                               rules.dir_noise_epsi, rules.allow_yield, rules.limit_reinforcement, rules.limit_attack,
+                               rules.temperature_threshold, rules.max_game_rounds, rules.min_unit_move)
+
+
+class RefGame:
+    """One game driven through the UNMODIFIED reference classes (State / UtilityNN)."""
+
+    def __init__(self):
+        self.L = ref_lib()
+        self.s = self.L.ref_state_new()
+
+    def __del__(self):
+        if getattr(self, "s", None):
+            self.L.ref_state_free(self.s)
+            self.s = None
+
+    def new_game(self, seed, game, ply=0):
+        assert self.L.ref_state_newgame_philox(self.s, seed, game, ply) == 0
+
+    def new_game_tape(self, draws):
+        t = np.ascontiguousarray(draws, np.int32)
+        assert self.L.ref_state_newgame_tape(self.s, t, len(t)) == 42
+
+    def data(self):
+        out = np.zeros(DATA_BYTES, np.uint8)
+        self.L.ref_state_get(self.s, out)
+        return out
+
+    def set_data(self, data):
+        self.L.ref_state_set(self.s, np.ascontiguousarray(data, np.uint8))
+
+    def valid(self):
+        return int(self.L.ref_valid_moves(self.s))
+
+    def status(self):
+        return int(self.L.ref_game_status(self.s))
+
+    def random_action(self, seed, game, ply):
+        return int(self.L.ref_random_action_philox(self.s, seed, game, ply))
+
+    def move(self, action, seed, game, ply):
+        return int(self.L.ref_make_move_philox(self.s, action, seed, game, ply))
+
+    def move_tape(self, action, dice):
+        t = np.ascontiguousarray(dice, np.int32)
+        n = int(self.L.ref_make_move_tape(self.s, action, t, len(t)))
+        return (0, n) if n >= 0 else (-1, 0)
+
+    def encode(self):
+        x = np.zeros(INPUT_FLOATS, np.float32)
+        self.L.ref_encode(self.s, x)
+        return x
+
+    def violations(self):
+        return int(self.L.ref_consistency_violations(self.s))
+
+
+class RefMcts:
+    def __init__(self, evaluator="pseudo"):
+        self.L = ref_lib()
+        fn = {"pseudo": self.L.ref_eval_pseudo, "uniform": self.L.ref_eval_uniform}[evaluator]
+        self.h = self.L.ref_mcts_new(C.cast(fn, C.c_void_p), None)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_mcts_free(self.h)
+            self.h = None
+
+    def clear(self):
+        self.L.ref_mcts_clear(self.h)
+
+    def trim(self):
+        self.L.ref_mcts_trim(self.h)
+
+    def table_size(self):
+        return int(self.L.ref_mcts_table_size(self.h))
+
+    def search(self, game_obj, seed, game, ply):
+        N = np.zeros(MOVES, np.uint32)
+        Q = np.zeros(MOVES, np.float32)
+        P = np.zeros(MOVES, np.float32)
+        pi = np.zeros(MOVES, np.float32)
+        sumN, val = C.c_uint32(0), C.c_float(0)
+        rc = self.L.ref_mcts_search(self.h, game_obj.s, seed, game, ply, N, Q, P, pi, C.byref(sumN), C.byref(val))
+        assert rc == 0, self.L.ref_last_error()
+        return dict(N=N, Q=Q, P=P, pi=pi, sumN=int(sumN.value), value=float(val.value))
+
+    def pick(self, pi, sample, seed, game, ply):
+        return int(self.L.ref_pick_move(self.h, np.ascontiguousarray(pi, np.float32), int(sample), seed, game, ply))

@@ -1,0 +1,3 @@
+#pragma once
+/* TEST INFRASTRUCTURE: see tensorflow/tf_stub.h */
+#include "tensorflow/tf_stub.h"

@@ -1,0 +1,87 @@
+"""CPU suite: the C oracle against the compiled reference run LIVE (oracle/_ref, built from
+/root/reference by oracle/ref/build_ref.sh).  Skipped where the library is absent."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref/libref_oracle.so not built")
+
+
+def test_reference_struct_sizes_and_defaults():
+    L = po.ref_lib()
+    assert (L.ref_sizeof_data(), L.ref_sizeof_player_status(), L.ref_sizeof_nn_input()) == (160, 48, 88)
+    d = np.zeros(11, np.float32)
+    L.ref_get_default_settings(d)
+    r = po.default_rules()
+    assert list(d) == [r.mcts_simulations, r.threads_per_mcts, np.float32(r.cpuct), np.float32(r.dir_noise_value),
+                       np.float32(r.dir_noise_epsi), r.allow_yield, r.limit_reinforcement, r.limit_attack,
+                       r.temperature_threshold, r.max_game_rounds, r.min_unit_move]
+
+
+def test_map_tables_match_reference():
+    import ctypes as C
+    nm, nl = np.zeros(42, np.uint64), np.zeros(42 * 6, np.int8)
+    cm, cb = np.zeros(6, np.uint64), np.zeros(6, np.int32)
+    po.ref_lib().ref_get_map(nm, nl, cm, cb)
+    L = po.oracle_lib()
+    assert list((C.c_uint64 * 42).in_dll(L, "RO_NBR_MASK")) == list(nm)
+    assert list((C.c_int8 * 252).in_dll(L, "RO_NBR_LIST")) == list(nl)
+    assert list((C.c_uint64 * 6).in_dll(L, "RO_CONTINENT_MASK")) == list(cm)
+    assert list((C.c_int * 6).in_dll(L, "RO_CONTINENT_BONUS")) == list(cb)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(allow_yield=0), dict(limit_reinforcement=0), dict(limit_attack=1)])
+def test_random_games_lockstep(kw):
+    seed = 0xC0FFEE
+    rules = po.default_rules(**kw)
+    po.ref_apply_rules(rules)
+    mask = po.data_byte_mask()
+    o, r = po.OracleGame(rules), po.RefGame()
+    steps = 0
+    for g in range(40):
+        o.new_game(seed, g)
+        r.new_game(seed, g)
+        ply = 0
+        while True:
+            assert (o.data()[mask] == r.data()[mask]).all()
+            assert o.valid() == r.valid() and o.status() == r.status()
+            if ply % 11 == 0:
+                assert (o.encode().view(np.uint32) == r.encode().view(np.uint32)).all()
+            if o.status() != -1:
+                break
+            a = o.random_action(seed, g, ply)
+            assert a == r.random_action(seed, g, ply)
+            assert o.move(a, seed, g, ply) == 0 and r.move(a, seed, g, ply) == 0
+            assert r.violations() == 0
+            ply += 1
+        steps += ply
+    po.ref_apply_rules(po.default_rules())
+    assert steps > 5000
+
+
+@pytest.mark.parametrize("sims,T,play_mode", [(16, 1, False), (48, 1, False), (33, 2, True)])
+def test_mcts_lockstep(sims, T, play_mode):
+    seed = 0xFACADE
+    rules = po.default_rules(mcts_simulations=sims, threads_per_mcts=T)
+    po.ref_apply_rules(rules)
+    mask = po.data_byte_mask()
+    o, r, om, rm = po.OracleGame(rules), po.RefGame(), po.OracleMcts(rules), po.RefMcts()
+    o.new_game(seed, 3)
+    r.new_game(seed, 3)
+    ply, last = 0, None
+    while o.status() == -1:
+        if play_mode and o.s.cur != last:
+            om.trim(); rm.trim(); last = o.s.cur
+        a, b = om.search(o, seed, 3, ply), rm.search(r, seed, 3, ply)
+        for k in ("N", "Q", "P", "pi"):
+            assert (a[k].view(np.uint32) == b[k].view(np.uint32)).all(), (ply, k)
+        assert a["sumN"] == b["sumN"] and a["value"] == b["value"] and om.table_size() == rm.table_size()
+        sample = (not play_mode) and o.s.round <= rules.temperature_threshold
+        mv = om.pick(a["pi"], sample, seed, 3, ply)
+        assert mv == rm.pick(b["pi"], sample, seed, 3, ply)
+        assert o.move(mv, seed, 3, ply) == 0 and r.move(mv, seed, 3, ply) == 0
+        assert (o.data()[mask] == r.data()[mask]).all()
+        ply += 1
+    po.ref_apply_rules(po.default_rules())
+    assert ply > 100
