@@ -1,0 +1,167 @@
+"""Host-side Python binding of libaz_b200.so (ctypes over the C ABI of include/az_b200.h).
+
+This is plumbing for tests, bench.py and torch.distributed launches; the product is the
+CUDA library.  There is NO CPU fallback: importing works anywhere (so the CPU test-suite
+can check that the library loads and exports its symbols), but creating any handle without
+a CUDA device raises AzError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libaz_b200.so")
+
+LANDS, MOVES, SKIP, NONE = 42, 43, 42, 43
+DATA_BYTES, INPUT_FLOATS = 160, 546
+STATUS_RUNNING, STATUS_DRAW, STATUS_ILLEGAL, STATUS_OVER = -1, -2, -3, -4
+
+
+class AzError(RuntimeError):
+    pass
+
+
+class AzRules(C.Structure):
+    """mirror of az_rules / SETTINGS.* (reference src/settings.h:40-62)"""
+    _fields_ = [("allow_yield", C.c_int32), ("limit_reinforcement", C.c_int32), ("limit_attack", C.c_int32),
+                ("max_game_rounds", C.c_int32), ("min_unit_move", C.c_int32), ("mcts_simulations", C.c_int32),
+                ("threads_per_mcts", C.c_int32), ("cpuct", C.c_float), ("dir_noise_value", C.c_float),
+                ("dir_noise_epsi", C.c_float), ("temperature_threshold", C.c_int32)]
+
+
+class AzCounters(C.Structure):
+    _fields_ = [("steps", C.c_uint64), ("games", C.c_uint64), ("wins", C.c_uint64 * 2), ("draws", C.c_uint64),
+                ("illegal", C.c_uint64), ("sims", C.c_uint64), ("evals", C.c_uint64)]
+
+    def as_dict(self):
+        return dict(steps=int(self.steps), games=int(self.games), wins=[int(self.wins[0]), int(self.wins[1])],
+                    draws=int(self.draws), illegal=int(self.illegal), sims=int(self.sims), evals=int(self.evals))
+
+
+_lib = None
+
+
+def lib():
+    """loads libaz_b200.so; raises AzError (never falls back) when it has not been built"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AzError("libaz_b200.so is missing: run `python -m alphazero_risk_b200.build` (nvcc, sm_100a)")
+        L = C.CDLL(LIB_PATH)
+        vp, u8, i8, u64, f32 = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_int8), C.POINTER(C.c_uint64), C.POINTER(C.c_float)
+        L.az_last_error.restype = C.c_char_p
+        L.az_default_rules.argtypes = [C.POINTER(AzRules)]
+        L.az_env_create.argtypes = [C.c_int, C.POINTER(AzRules), C.c_int, C.c_uint32, C.POINTER(vp)]
+        L.az_env_destroy.argtypes = [vp]
+        L.az_env_size.argtypes = [vp]
+        L.az_env_reset.argtypes = [vp, C.c_uint64, vp]
+        L.az_env_import_aos.argtypes = [vp, vp, vp]
+        L.az_env_export_aos.argtypes = [vp, vp, vp]
+        L.az_env_valid_moves.argtypes = [vp, vp, vp]
+        L.az_env_status.argtypes = [vp, vp, vp]
+        L.az_env_step.argtypes = [vp, vp, vp, vp, vp]
+        L.az_env_step_dev.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.az_env_encode.argtypes = [vp, vp, vp]
+        L.az_env_encode_dev.argtypes = [vp, vp, vp]
+        L.az_env_rollout.argtypes = [vp, C.c_int, vp]
+        L.az_env_counters.argtypes = [vp, C.POINTER(AzCounters), C.c_int, vp]
+        L.az_env_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise AzError("libaz_b200 error %d: %s" % (rc, lib().az_last_error().decode()))
+
+
+def default_rules(**kw):
+    r = AzRules()
+    lib().az_default_rules(C.byref(r))
+    for k, v in kw.items():
+        setattr(r, k, v)
+    return r
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Env:
+    """n lockstep Risk games resident in HBM (az_env_*)."""
+
+    def __init__(self, n_games, rules=None, device=0, first_game_id=0):
+        self.L = lib()
+        self.n = int(n_games)
+        self.rules = rules if rules is not None else default_rules()
+        self.device = device
+        h = C.c_void_p()
+        check(self.L.az_env_create(self.n, C.byref(self.rules), device, first_game_id, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.az_env_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self, seed, stream=None):
+        check(self.L.az_env_reset(self.h, int(seed), stream))
+
+    def import_aos(self, data, stream=None):
+        a = np.ascontiguousarray(data, np.uint8)
+        assert a.shape == (self.n, DATA_BYTES)
+        check(self.L.az_env_import_aos(self.h, _ptr(a), stream))
+
+    def export_aos(self, out=None, stream=None):
+        a = out if out is not None else np.empty((self.n, DATA_BYTES), np.uint8)
+        check(self.L.az_env_export_aos(self.h, _ptr(a), stream))
+        return a
+
+    def valid_moves(self, stream=None):
+        a = np.empty(self.n, np.uint64)
+        check(self.L.az_env_valid_moves(self.h, _ptr(a), stream))
+        return a
+
+    def status(self, stream=None):
+        a = np.empty(self.n, np.int8)
+        check(self.L.az_env_status(self.h, _ptr(a), stream))
+        return a
+
+    def step(self, action, dice=None, out=None, stream=None):
+        act = np.ascontiguousarray(action, np.uint8)
+        assert act.shape == (self.n,)
+        st = out if out is not None else np.empty(self.n, np.int8)
+        d = None
+        if dice is not None:
+            d = np.ascontiguousarray(dice, np.uint8)
+            assert d.shape == (self.n, 5)
+        check(self.L.az_env_step(self.h, _ptr(act), _ptr(d) if d is not None else None, _ptr(st), stream))
+        return st
+
+    def step_dev(self, d_action, d_dice, d_status, d_valid_after=None, stream=None):
+        """raw device pointers (ints), e.g. torch tensors' data_ptr()"""
+        check(self.L.az_env_step_dev(self.h, d_action, d_dice, d_status, d_valid_after, stream))
+
+    def encode(self, stream=None):
+        a = np.empty((self.n, 7, 6, 13), np.float32)
+        check(self.L.az_env_encode(self.h, _ptr(a), stream))
+        return a
+
+    def encode_dev(self, d_x, stream=None):
+        check(self.L.az_env_encode_dev(self.h, d_x, stream))
+
+    def rollout(self, n_steps, stream=None):
+        check(self.L.az_env_rollout(self.h, int(n_steps), stream))
+
+    def counters(self, reset=False, stream=None):
+        c = AzCounters()
+        check(self.L.az_env_counters(self.h, C.byref(c), int(reset), stream))
+        return c.as_dict()
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        check(self.L.az_env_last_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)

@@ -1,0 +1,573 @@
+// az_env.cu — lockstep Risk environment kernels for sm_100a and the az_env_* C ABI.
+//
+// One thread per game.  Game state lives in HBM as a structure of arrays of 32-bit words
+// (word w of game g at state[w * n + g]) so every load/store of a warp is one coalesced
+// 128-byte line; inside a kernel the 42 land bytes of a thread sit in a shared-memory
+// COLUMN (word w of thread t at smem[w * blockDim + t]) which makes the divergent,
+// data-dependent byte indexing of the rules bank-conflict free, and the map tables are
+// staged in shared memory once per block.
+//
+// Replaces (reference, /root/reference/src/risk_game): State::newGame state/state.cpp:137-167,
+// UtilityNN::getValidMoves / makeMove player/alpha_zero/alphazero_moves.cpp:3-233,
+// State::gameStatus state/state.cpp:518-565, NNInputData + setInStateTensor
+// neural_network/alphazero_nn_data.cpp:165-196 + alphazero_nn.cpp:31-67.
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "az_common.cuh"
+#include "az_game.cuh"
+#include "az_tables_gen.h"
+
+// ---------------------------------------------------------------- error string
+static thread_local char g_az_err[512] = "";
+void az_set_error(const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_az_err, sizeof g_az_err, fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* az_last_error(void) { return g_az_err; }
+extern "C" int az_version(void) { return 100; }
+extern "C" int az_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" void az_default_rules(az_rules* r)
+{   // /root/reference/src/settings.h:40-62
+    r->allow_yield = 1; r->limit_reinforcement = 1; r->limit_attack = 0; r->max_game_rounds = 58; r->min_unit_move = 3;
+    r->mcts_simulations = 32; r->threads_per_mcts = 2; r->cpuct = 1.1f; r->dir_noise_value = 0.3f; r->dir_noise_epsi = 0.25f;
+    r->temperature_threshold = 43;
+}
+
+// ---------------------------------------------------------------- tables in HBM (one copy per device)
+static uint64_t* g_tables_dev[64] = { nullptr };
+static std::mutex g_tables_mu;
+
+int az_upload_tables()
+{
+    int dev = 0;
+    AZ_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tables_mu);
+    if (dev < 0 || dev >= 64) { az_set_error("device index %d out of range", dev); return AZ_ERR_INVALID_ARG; }
+    if (g_tables_dev[dev]) return AZ_OK;
+    uint64_t h[AZ_TABLE_U64];
+    memcpy(h, AZ_NBR_UNION_LUT_H, sizeof AZ_NBR_UNION_LUT_H);
+    memcpy(h + 7 * 64, AZ_NBR_MASK_H, sizeof AZ_NBR_MASK_H);
+    memcpy(h + 7 * 64 + 42, AZ_NBR_LIST6_H, sizeof AZ_NBR_LIST6_H);
+    uint64_t* d = nullptr;
+    AZ_CUDA(cudaMalloc(&d, sizeof h));
+    AZ_CUDA(cudaMemcpy(d, h, sizeof h, cudaMemcpyHostToDevice));
+    g_tables_dev[dev] = d;
+    return AZ_OK;
+}
+const uint64_t* az_device_tables()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < 64) ? g_tables_dev[dev] : nullptr;
+}
+
+// ---------------------------------------------------------------- per-thread game context
+#define ENV_BLOCK 128
+#define ENV_COL_WORDS 22     // 11 land words + 11 fortify-DFS parent words per thread
+
+struct EnvSmem {
+    uint64_t tab[AZ_TABLE_U64];
+    uint32_t col[ENV_COL_WORDS * ENV_BLOCK];
+};
+
+__device__ __forceinline__ AzTables env_stage_tables(EnvSmem& sm, const uint64_t* __restrict__ g_tab)
+{
+    for (int i = threadIdx.x; i < AZ_TABLE_U64; i += blockDim.x) sm.tab[i] = g_tab[i];
+    __syncthreads();
+    return az_tables_from_smem(sm.tab);
+}
+
+struct EnvCtx {
+    AzGame g;
+    AzLandColumn land, scratch;
+    uint32_t ply;
+};
+
+__device__ __forceinline__ void env_bind(EnvCtx& c, EnvSmem& sm)
+{
+    c.land.base = (uint8_t*)(sm.col) + 4 * threadIdx.x;
+    c.land.stride_bytes = 4 * ENV_BLOCK;
+    c.scratch.base = (uint8_t*)(sm.col + 11 * ENV_BLOCK) + 4 * threadIdx.x;
+    c.scratch.stride_bytes = 4 * ENV_BLOCK;
+}
+
+__device__ __forceinline__ void env_load(EnvCtx& c, EnvSmem& sm, const uint32_t* __restrict__ st, int n, int gi)
+{
+    env_bind(c, sm);
+    c.g.own0 = c.g.own1 = c.g.gt1 = c.g.full = 0;
+    uint32_t w10 = 0;
+#pragma unroll
+    for (int w = 0; w < 11; ++w) {
+        uint32_t v = st[(size_t)w * n + gi];
+        sm.col[w * ENV_BLOCK + threadIdx.x] = v;
+        az_masks_add_word(c.g, v, w);
+        if (w == 10) w10 = v;
+    }
+    az_unpack_scalars(c.g, w10, st[(size_t)11 * n + gi], st[(size_t)12 * n + gi], st[(size_t)13 * n + gi]);
+    c.ply = st[(size_t)AZ_W_PLY * n + gi];
+}
+
+__device__ __forceinline__ void env_store(const EnvCtx& c, EnvSmem& sm, uint32_t* __restrict__ st, int n, int gi)
+{
+#pragma unroll
+    for (int w = 0; w < 10; ++w) st[(size_t)w * n + gi] = sm.col[w * ENV_BLOCK + threadIdx.x];
+    uint32_t w10 = (sm.col[10 * ENV_BLOCK + threadIdx.x] & 0xffffu) | (c.g.cards0 << 16) | (c.g.cards1 << 24);
+    st[(size_t)10 * n + gi] = w10;
+    st[(size_t)11 * n + gi] = az_pack_w11(c.g);
+    st[(size_t)12 * n + gi] = az_pack_w12(c.g);
+    st[(size_t)13 * n + gi] = az_pack_w13(c.g);
+    st[(size_t)AZ_W_PLY * n + gi] = c.ply;
+}
+
+// ---------------------------------------------------------------- kernels
+__global__ void __launch_bounds__(ENV_BLOCK) k_env_reset(uint32_t* __restrict__ st, int n, uint64_t seed, uint32_t first_game)
+{
+    __shared__ EnvSmem sm;
+    int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    EnvCtx c; env_bind(c, sm);
+#pragma unroll
+    for (int w = 0; w < 11; ++w) sm.col[w * ENV_BLOCK + threadIdx.x] = 0;
+    az_new_game(c.g, c.land, seed, first_game + (uint32_t)gi, 0u);
+    c.ply = 0;
+    env_store(c, sm, st, n, gi);
+    st[(size_t)15 * n + gi] = 0;
+}
+
+// one makeMove per game with externally supplied actions (the vector-env API)
+__global__ void __launch_bounds__(ENV_BLOCK) k_env_step(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
+                                                         const uint8_t* __restrict__ action, const uint8_t* __restrict__ dice5,
+                                                         int8_t* __restrict__ status, uint64_t* __restrict__ valid_after,
+                                                         uint64_t seed, uint32_t first_game, AzRulesDev rules)
+{
+    __shared__ EnvSmem sm;
+    AzTables T = env_stage_tables(sm, g_tab);
+    int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    EnvCtx c; env_load(c, sm, st, n, gi);
+    int stt = az_game_status(c.g, rules);
+    int out;
+    if (stt != AZ_STATUS_RUNNING) out = AZ_STATUS_OVER;
+    else {
+        uint64_t valid = az_valid_moves(c.g, T, rules);
+        int rc;
+        if (dice5) {
+            AzDiceTape d; d.t = dice5 + (size_t)gi * 5; d.j = 0;
+            rc = az_make_move(c.g, c.land, c.scratch, T, rules, valid, (int)action[gi], d);
+        } else {
+            AzDicePhilox d; d.init(seed, first_game + (uint32_t)gi, c.ply, AZ_STREAM_REAL);
+            rc = az_make_move(c.g, c.land, c.scratch, T, rules, valid, (int)action[gi], d);
+        }
+        if (rc == 0) { c.ply++; env_store(c, sm, st, n, gi); out = az_game_status(c.g, rules); }
+        else out = rc;
+    }
+    status[gi] = (int8_t)out;
+    if (valid_after) valid_after[gi] = az_valid_moves(c.g, T, rules);
+}
+
+__global__ void __launch_bounds__(ENV_BLOCK) k_env_query(const uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
+                                                          uint64_t* __restrict__ valid, int8_t* __restrict__ status, AzRulesDev rules)
+{
+    __shared__ EnvSmem sm;
+    AzTables T = env_stage_tables(sm, g_tab);
+    int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    EnvCtx c; env_load(c, sm, st, n, gi);
+    if (valid) valid[gi] = az_valid_moves(c.g, T, rules);
+    if (status) status[gi] = (int8_t)az_game_status(c.g, rules);
+}
+
+// BASELINE config 2: n_steps uniform-random legal moves per game inside one launch; the state
+// stays in registers / shared memory between steps, finished games are re-dealt in place.
+__global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
+                                                            int n_steps, uint64_t seed, uint32_t first_game, AzRulesDev rules,
+                                                            unsigned long long* __restrict__ counters)
+{
+    __shared__ EnvSmem sm;
+    AzTables T = env_stage_tables(sm, g_tab);
+    int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
+    unsigned steps = 0, games = 0, w0 = 0, w1 = 0, dr = 0;
+    if (gi < n) {
+        EnvCtx c; env_load(c, sm, st, n, gi);
+        const uint32_t game = first_game + (uint32_t)gi;
+        for (int s = 0; s < n_steps; ++s) {
+            int stt = az_game_status(c.g, rules);
+            if (stt != AZ_STATUS_RUNNING) {
+                games++; w0 += stt == 0; w1 += stt == 1; dr += stt == AZ_STATUS_DRAW;
+                az_new_game(c.g, c.land, seed, game, c.ply);
+            }
+            uint64_t valid = az_valid_moves(c.g, T, rules);
+            az_u32x4 blk = az_rng_block(seed, game, c.ply, AZ_STREAM_REAL, 0);
+            int action = az_nth_set_bit(valid, az_mulhi32(blk.y, (uint32_t)__popcll(valid)));
+            AzDicePhilox d; d.init_with_block0(seed, game, c.ply, AZ_STREAM_REAL, blk);
+            az_make_move(c.g, c.land, c.scratch, T, rules, valid, action, d);
+            c.ply++; steps++;
+        }
+        env_store(c, sm, st, n, gi);
+    }
+    // warp-reduce, one atomic per warp and counter
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        steps += __shfl_xor_sync(0xffffffffu, steps, o); games += __shfl_xor_sync(0xffffffffu, games, o);
+        w0 += __shfl_xor_sync(0xffffffffu, w0, o); w1 += __shfl_xor_sync(0xffffffffu, w1, o); dr += __shfl_xor_sync(0xffffffffu, dr, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&counters[0], (unsigned long long)steps);
+        if (games) atomicAdd(&counters[1], (unsigned long long)games);
+        if (w0) atomicAdd(&counters[2], (unsigned long long)w0);
+        if (w1) atomicAdd(&counters[3], (unsigned long long)w1);
+        if (dr) atomicAdd(&counters[4], (unsigned long long)dr);
+    }
+}
+
+// AoS Data image (state/state.h:86-105, g++ x86-64 layout) <-> device SoA
+__device__ __forceinline__ void put48(uint8_t* p, uint64_t v) { for (int i = 0; i < 6; ++i) p[i] = (uint8_t)(v >> (8 * i)); }
+__device__ __forceinline__ uint64_t get48(const uint8_t* p) { uint64_t v = 0; for (int i = 0; i < 6; ++i) v |= (uint64_t)p[i] << (8 * i); return v; }
+
+__global__ void __launch_bounds__(ENV_BLOCK) k_env_export(const uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
+                                                           uint8_t* __restrict__ aos)
+{
+    __shared__ EnvSmem sm;
+    AzTables T = env_stage_tables(sm, g_tab);
+    int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    EnvCtx c; env_load(c, sm, st, n, gi);
+    uint8_t* d = aos + (size_t)gi * AZ_DATA_BYTES;
+    for (int i = 0; i < AZ_DATA_BYTES; ++i) d[i] = 0;
+    int total[2] = { 0, 0 };
+    for (int i = 0; i < AZ_LANDS; ++i) {
+        uint32_t v = c.land.get(i); d[i] = (uint8_t)v;
+        if ((v >> 6) < 2) total[v >> 6] += (int)(v & 63u);
+    }
+    for (uint32_t p = 0; p < 2; ++p) {
+        uint8_t* ps = d + 48 + 48 * p;
+        uint64_t o = c.g.own(p);
+        put48(ps + 0, o); put48(ps + 8, o & c.g.gt1); put48(ps + 16, o & c.g.full);
+        put48(ps + 24, az_nbr_union(T, o) & ~o); put48(ps + 32, az_attack_army(c.g, T, p));
+        ps[38] = (uint8_t)(total[p] & 0xff); ps[39] = (uint8_t)((total[p] >> 8) & 0xff);
+        ps[40] = (uint8_t)(p ? c.g.cards1 : c.g.cards0);
+    }
+    d[144] = (uint8_t)(c.g.round & 0xff); d[145] = (uint8_t)(c.g.round >> 8);
+    d[146] = (uint8_t)c.g.cur; d[147] = (uint8_t)c.g.card_sets; d[148] = (uint8_t)c.g.reinf; d[149] = (uint8_t)c.g.phase;
+    d[150] = (uint8_t)c.g.mob_from; d[151] = (uint8_t)c.g.mob_to; d[152] = (uint8_t)c.g.allow_draw; d[153] = (uint8_t)c.g.attacks;
+}
+
+__global__ void __launch_bounds__(ENV_BLOCK) k_env_import(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
+                                                           const uint8_t* __restrict__ aos, int* __restrict__ bad)
+{
+    __shared__ EnvSmem sm;
+    AzTables T = env_stage_tables(sm, g_tab);
+    int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    const uint8_t* d = aos + (size_t)gi * AZ_DATA_BYTES;
+    EnvCtx c; env_bind(c, sm);
+    c.g.own0 = c.g.own1 = c.g.gt1 = c.g.full = 0;
+    int total[2] = { 0, 0 };
+    for (int w = 0; w < 11; ++w) {
+        uint32_t v = 0;
+        for (int b = 0; b < 4; ++b) { int i = 4 * w + b; if (i < AZ_LANDS) v |= (uint32_t)d[i] << (8 * b); }
+        sm.col[w * ENV_BLOCK + threadIdx.x] = v;
+        az_masks_add_word(c.g, v, w);
+    }
+    for (int i = 0; i < AZ_LANDS; ++i) { uint32_t v = d[i]; if ((v >> 6) < 2) total[v >> 6] += (int)(v & 63u); if ((v >> 6) == 3) atomicAdd(bad, 1); }
+    c.g.cards0 = d[48 + 40]; c.g.cards1 = d[96 + 40];
+    c.g.round = (uint32_t)d[144] | ((uint32_t)d[145] << 8); c.g.cur = d[146]; c.g.card_sets = d[147]; c.g.reinf = d[148]; c.g.phase = d[149];
+    c.g.mob_from = d[150]; c.g.mob_to = d[151]; c.g.allow_draw = d[152]; c.g.attacks = d[153];
+    // the derived fields of the image must agree with landArmy[] (State::consistencyCheck, state.cpp:1209-1429)
+    int wrong = 0;
+    for (uint32_t p = 0; p < 2; ++p) {
+        const uint8_t* ps = d + 48 + 48 * p;
+        uint64_t o = c.g.own(p);
+        wrong += get48(ps) != o; wrong += get48(ps + 8) != (o & c.g.gt1); wrong += get48(ps + 16) != (o & c.g.full);
+        wrong += get48(ps + 24) != (az_nbr_union(T, o) & ~o); wrong += get48(ps + 32) != az_attack_army(c.g, T, p);
+        wrong += (int)(int16_t)((uint16_t)ps[38] | ((uint16_t)ps[39] << 8)) != total[p];
+    }
+    wrong += c.g.cur > 1; wrong += c.g.phase > AZ_PH_FORTIFY;
+    if (wrong) atomicAdd(bad, 1);
+    c.ply = 0;
+    env_store(c, sm, st, n, gi);
+    st[(size_t)15 * n + gi] = 0;
+}
+
+// NNInputData(State) + setInStateTensor -> fp32 [n][7][6][13]; one warp per game, coalesced stores
+__global__ void __launch_bounds__(128) k_env_encode(const uint32_t* __restrict__ st, int n, float* __restrict__ x)
+{
+    __shared__ uint32_t s_words[4][16];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int gi = blockIdx.x * 4 + warp;
+    if (gi >= n) return;
+    if (lane < 14) s_words[warp][lane] = st[(size_t)lane * n + gi];
+    __syncwarp();
+    const uint8_t* land = (const uint8_t*)s_words[warp];
+    AzGame g;
+    az_unpack_scalars(g, s_words[warp][10], s_words[warp][11], s_words[warp][12], s_words[warp][13]);
+    // lanes 0..31 hold lands 0..31, lanes 0..9 also lands 32..41
+    uint32_t b0 = land[lane], b1 = lane < 10 ? land[32 + lane] : (3u << 6);
+    uint32_t m0a = __ballot_sync(0xffffffffu, (b0 >> 6) == 0), m0b = __ballot_sync(0xffffffffu, (b1 >> 6) == 0);
+    uint32_t m1a = __ballot_sync(0xffffffffu, (b0 >> 6) == 1), m1b = __ballot_sync(0xffffffffu, (b1 >> 6) == 1);
+    g.own0 = (uint64_t)m0a | ((uint64_t)m0b << 32); g.own1 = (uint64_t)m1a | ((uint64_t)m1b << 32);
+    int t0 = ((b0 >> 6) == 0 ? (int)(b0 & 63u) : 0) + ((b1 >> 6) == 0 ? (int)(b1 & 63u) : 0);
+    int t1 = ((b0 >> 6) == 1 ? (int)(b0 & 63u) : 0) + ((b1 >> 6) == 1 ? (int)(b1 & 63u) : 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
+    const uint32_t cur = g.cur, enemy = cur ^ 1u;
+    float ref = (float)az_reinforcement_value(g.own(cur)), eref = (float)az_reinforcement_value(g.own(enemy));
+    float reinf_share = __fdiv_rn(ref, __fadd_rn(ref, eref));
+    float att = __fdiv_rn((float)g.attacks, 8.0f); att = att < 1.0f ? att : 1.0f;
+    float ta = (float)(cur ? t1 : t0), eta = (float)(cur ? t0 : t1);
+    float army_share = __fdiv_rn(ta, __fadd_rn(ta, eta));
+    float* out = x + (size_t)gi * AZ_INPUT_FLOATS;
+    for (int idx = lane; idx < AZ_INPUT_FLOATS; idx += 32) {
+        int l = idx / 13, ch = idx - l * 13;
+        uint32_t v = land[l], o = v >> 6;
+        float fa = __fdiv_rn((float)(v & 63u), 32.0f);
+        float val;
+        if (ch == 0) val = o == cur ? fa : 0.0f;
+        else if (ch == 1) val = o == enemy ? fa : 0.0f;
+        else if (ch == 2) val = o == AZ_NEUTRAL ? fa : 0.0f;
+        else if (ch == 3) val = army_share;
+        else if (ch == 4) val = reinf_share;
+        else if (ch == 5) val = att;
+        else if (ch == 6) val = g.allow_draw ? 1.0f : 0.0f;
+        else val = (g.phase == (uint32_t)(ch - 7)) ? 1.0f : 0.0f;
+        out[idx] = val;
+    }
+}
+
+// ---------------------------------------------------------------- host side
+struct az_env {
+    int n = 0, device = 0;
+    uint32_t first_game = 0;
+    uint64_t seed = 0;
+    az_rules rules;
+    uint32_t* d_state = nullptr;
+    unsigned long long* d_counters = nullptr;   // 8 x u64
+    // staging for the host-buffer entry points
+    uint8_t* d_action = nullptr; uint8_t* d_dice = nullptr; int8_t* d_status = nullptr; uint64_t* d_valid = nullptr;
+    uint8_t* d_aos = nullptr; float* d_x = nullptr; int* d_bad = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+static AzRulesDev dev_rules(const az_rules& r)
+{
+    AzRulesDev d; d.allow_yield = r.allow_yield; d.limit_reinforcement = r.limit_reinforcement; d.limit_attack = r.limit_attack;
+    d.max_game_rounds = r.max_game_rounds; d.min_unit_move = r.min_unit_move; return d;
+}
+static inline int env_grid(int n) { return (n + ENV_BLOCK - 1) / ENV_BLOCK; }
+
+extern "C" int az_env_create(int n_games, const az_rules* rules, int device, uint32_t first_game_id, az_env** out)
+{
+    AZ_REQUIRE(out != nullptr, "out is NULL");
+    AZ_REQUIRE(n_games > 0, "n_games must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); az_set_error("no CUDA device: libaz_b200 has no CPU fallback"); return AZ_ERR_NO_DEVICE; }
+    AZ_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    AzDeviceGuard guard(device);
+    int rc = az_upload_tables();
+    if (rc != AZ_OK) return rc;
+    az_env* e = new (std::nothrow) az_env();
+    AZ_REQUIRE(e != nullptr, "out of host memory");
+    e->n = n_games; e->device = device; e->first_game = first_game_id;
+    if (rules) e->rules = *rules; else az_default_rules(&e->rules);
+    AZ_CUDA(cudaMalloc(&e->d_state, sizeof(uint32_t) * AZ_STATE_WORDS * (size_t)n_games));
+    AZ_CUDA(cudaMemset(e->d_state, 0, sizeof(uint32_t) * AZ_STATE_WORDS * (size_t)n_games));
+    AZ_CUDA(cudaMalloc(&e->d_counters, 8 * sizeof(unsigned long long)));
+    AZ_CUDA(cudaMemset(e->d_counters, 0, 8 * sizeof(unsigned long long)));
+    AZ_CUDA(cudaMalloc(&e->d_bad, sizeof(int)));
+    AZ_CUDA(cudaEventCreate(&e->ev0));
+    AZ_CUDA(cudaEventCreate(&e->ev1));
+    *out = e;
+    return AZ_OK;
+}
+
+extern "C" int az_env_destroy(az_env* e)
+{
+    if (!e) return AZ_OK;
+    AzDeviceGuard guard(e->device);
+    cudaFree(e->d_state); cudaFree(e->d_counters); cudaFree(e->d_action); cudaFree(e->d_dice); cudaFree(e->d_status);
+    cudaFree(e->d_valid); cudaFree(e->d_aos); cudaFree(e->d_x); cudaFree(e->d_bad);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    delete e;
+    return AZ_OK;
+}
+
+extern "C" int az_env_size(const az_env* e) { return e ? e->n : 0; }
+
+template <class T> static int ensure(T** p, size_t count)
+{
+    if (*p) return AZ_OK;
+    AZ_CUDA(cudaMalloc(p, sizeof(T) * count));
+    return AZ_OK;
+}
+
+extern "C" int az_env_reset(az_env* e, uint64_t seed, void* stream)
+{
+    AZ_REQUIRE(e != nullptr, "env is NULL");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    e->seed = seed;
+    k_env_reset<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, seed, e->first_game);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+extern "C" int az_env_import_aos(az_env* e, const uint8_t* h_data, void* stream)
+{
+    AZ_REQUIRE(e && h_data, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure(&e->d_aos, (size_t)e->n * AZ_DATA_BYTES); if (rc) return rc;
+    AZ_CUDA(cudaMemcpyAsync(e->d_aos, h_data, (size_t)e->n * AZ_DATA_BYTES, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaMemsetAsync(e->d_bad, 0, sizeof(int), s));
+    k_env_import<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), e->d_aos, e->d_bad);
+    AZ_CUDA(cudaGetLastError());
+    int bad = 0;
+    AZ_CUDA(cudaMemcpyAsync(&bad, e->d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    if (bad) { az_set_error("az_env_import_aos: %d game image(s) whose masks/totals disagree with landArmy[]", bad); return AZ_ERR_BAD_STATE; }
+    return AZ_OK;
+}
+
+extern "C" int az_env_export_aos(az_env* e, uint8_t* h_data, void* stream)
+{
+    AZ_REQUIRE(e && h_data, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure(&e->d_aos, (size_t)e->n * AZ_DATA_BYTES); if (rc) return rc;
+    k_env_export<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), e->d_aos);
+    AZ_CUDA(cudaGetLastError());
+    AZ_CUDA(cudaMemcpyAsync(h_data, e->d_aos, (size_t)e->n * AZ_DATA_BYTES, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+extern "C" int az_env_valid_moves(az_env* e, uint64_t* h_mask, void* stream)
+{
+    AZ_REQUIRE(e && h_mask, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure(&e->d_valid, (size_t)e->n); if (rc) return rc;
+    k_env_query<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), e->d_valid, nullptr, dev_rules(e->rules));
+    AZ_CUDA(cudaGetLastError());
+    AZ_CUDA(cudaMemcpyAsync(h_mask, e->d_valid, sizeof(uint64_t) * (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+extern "C" int az_env_status(az_env* e, int8_t* h_status, void* stream)
+{
+    AZ_REQUIRE(e && h_status, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure(&e->d_status, (size_t)e->n); if (rc) return rc;
+    k_env_query<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), nullptr, e->d_status, dev_rules(e->rules));
+    AZ_CUDA(cudaGetLastError());
+    AZ_CUDA(cudaMemcpyAsync(h_status, e->d_status, (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+extern "C" int az_env_step_dev(az_env* e, const uint8_t* d_action, const uint8_t* d_dice, int8_t* d_status,
+                               uint64_t* d_valid_after, void* stream)
+{
+    AZ_REQUIRE(e && d_action && d_status, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AZ_CUDA(cudaEventRecord(e->ev0, s));
+    k_env_step<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), d_action, d_dice, d_status, d_valid_after,
+                                                     e->seed, e->first_game, dev_rules(e->rules));
+    AZ_CUDA(cudaGetLastError());
+    AZ_CUDA(cudaEventRecord(e->ev1, s));
+    e->timed = true;
+    return AZ_OK;
+}
+
+extern "C" int az_env_step(az_env* e, const uint8_t* h_action, const uint8_t* h_dice, int8_t* h_status, void* stream)
+{
+    AZ_REQUIRE(e && h_action && h_status, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure(&e->d_action, (size_t)e->n); if (rc) return rc;
+    rc = ensure(&e->d_status, (size_t)e->n); if (rc) return rc;
+    AZ_CUDA(cudaMemcpyAsync(e->d_action, h_action, (size_t)e->n, cudaMemcpyHostToDevice, s));
+    if (h_dice) {
+        rc = ensure(&e->d_dice, (size_t)e->n * 5); if (rc) return rc;
+        AZ_CUDA(cudaMemcpyAsync(e->d_dice, h_dice, (size_t)e->n * 5, cudaMemcpyHostToDevice, s));
+    }
+    rc = az_env_step_dev(e, e->d_action, h_dice ? e->d_dice : nullptr, e->d_status, nullptr, stream);
+    if (rc) return rc;
+    AZ_CUDA(cudaMemcpyAsync(h_status, e->d_status, (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+extern "C" int az_env_encode_dev(az_env* e, float* d_x, void* stream)
+{
+    AZ_REQUIRE(e && d_x, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    k_env_encode<<<(e->n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(e->d_state, e->n, d_x);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+extern "C" int az_env_encode(az_env* e, float* h_x, void* stream)
+{
+    AZ_REQUIRE(e && h_x, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure(&e->d_x, (size_t)e->n * AZ_INPUT_FLOATS); if (rc) return rc;
+    rc = az_env_encode_dev(e, e->d_x, stream); if (rc) return rc;
+    AZ_CUDA(cudaMemcpyAsync(h_x, e->d_x, sizeof(float) * (size_t)e->n * AZ_INPUT_FLOATS, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+extern "C" int az_env_rollout(az_env* e, int n_steps, void* stream)
+{
+    AZ_REQUIRE(e != nullptr, "env is NULL");
+    AZ_REQUIRE(n_steps >= 0, "n_steps must be >= 0");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AZ_CUDA(cudaEventRecord(e->ev0, s));
+    k_env_rollout<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
+                                                        dev_rules(e->rules), e->d_counters);
+    AZ_CUDA(cudaGetLastError());
+    AZ_CUDA(cudaEventRecord(e->ev1, s));
+    e->timed = true;
+    return AZ_OK;
+}
+
+extern "C" int az_env_counters(az_env* e, az_counters* h_out, int reset, void* stream)
+{
+    AZ_REQUIRE(e && h_out, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long h[8];
+    AZ_CUDA(cudaMemcpyAsync(h, e->d_counters, sizeof h, cudaMemcpyDeviceToHost, s));
+    if (reset) AZ_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof h, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    h_out->steps = h[0]; h_out->games = h[1]; h_out->wins[0] = h[2]; h_out->wins[1] = h[3]; h_out->draws = h[4];
+    h_out->illegal = h[5]; h_out->sims = h[6]; h_out->evals = h[7];
+    return AZ_OK;
+}
+
+extern "C" int az_env_last_kernel_ms(az_env* e, float* ms)
+{
+    AZ_REQUIRE(e && ms, "NULL argument");
+    if (!e->timed) { az_set_error("no timed launch yet"); return AZ_ERR_NOT_READY; }
+    AzDeviceGuard guard(e->device);
+    AZ_CUDA(cudaEventSynchronize(e->ev1));
+    AZ_CUDA(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return AZ_OK;
+}

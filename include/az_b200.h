@@ -1,0 +1,139 @@
+/*
+ * az_b200.h — C ABI of libaz_b200.so, the B200 (sm_100a) implementation of
+ * JGasp/alphazero-risk's self-play hot path.
+ *
+ * The reference has no FFI: its plugin seams are C++ classes.  Each entry
+ * point below names the reference interface it replaces (paths relative to
+ * /root/reference/src/risk_game); the C++ adapters that present those interfaces on top of
+ * this ABI live in alphazero_risk_b200/host/, the binding a reference maintainer would add
+ * is shown in INTEGRATION.md.
+ *
+ * Conventions: every call returns AZ_OK (0) or a negative az_error; the message of the last
+ * failure on the calling thread is az_last_error().  No exception crosses the boundary: where
+ * the reference throws for one game (illegal action, move on a finished game) the per-game
+ * status byte carries the code and the game's state is left untouched.  Handles are opaque,
+ * the library owns all device memory, the caller owns host buffers.  `stream` is a
+ * cudaStream_t passed as void* (NULL = the legacy default stream).  Calls on different
+ * handles are thread-safe; calls on one handle must be serialised by the caller.
+ * Pointers named h_* are HOST buffers (copied inside the call), d_* are DEVICE buffers.
+ */
+#ifndef AZ_B200_H
+#define AZ_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AZ_API __attribute__((visibility("default")))
+#else
+#define AZ_API
+#endif
+
+#define AZ_LANDS 42
+#define AZ_MOVES 43            /* 42 lands + skip; ALL_MOVES, player/alpha_zero/alphazero_mcts.h:13 */
+#define AZ_SKIP 42             /* Land::SKIP_MOVE, land/land.cpp:312 */
+#define AZ_NONE 43             /* LandIndex::None */
+#define AZ_DATA_BYTES 160      /* sizeof(Data), state/state.h:86-105 */
+#define AZ_INPUT_FLOATS 546    /* [7][6][13], neural_network/alphazero_nn_data.h:66 (INPUT_VECTOR_TYPE_2) */
+#define AZ_STATE_WORDS 16      /* device SoA: 32-bit words per game */
+
+typedef enum az_error {
+    AZ_OK = 0,
+    AZ_ERR_INVALID_ARG = -1,
+    AZ_ERR_CUDA = -2,
+    AZ_ERR_NO_DEVICE = -3,
+    AZ_ERR_BAD_STATE = -4,     /* az_env_import_aos: masks / totals disagree with landArmy[] */
+    AZ_ERR_CAPACITY = -5,      /* MCTS node pool exhausted */
+    AZ_ERR_NOT_READY = -6
+} az_error;
+
+/* per-game status byte written by the step calls */
+#define AZ_STATUS_RUNNING (-1) /* State::NOT_ENDED, state/state.h:124 */
+#define AZ_STATUS_DRAW (-2)    /* State::DRAW, state/state.h:123; 0 / 1 = winner */
+#define AZ_STATUS_ILLEGAL (-3) /* action not in the legal-move mask (reference: std::invalid_argument / logic_error) */
+#define AZ_STATUS_OVER (-4)    /* game had already ended before the step */
+
+/* runtime options of /root/reference/src/settings.h:40-62 that change the path's results;
+   field names follow SETTINGS.* */
+typedef struct az_rules {
+    int32_t allow_yield;             /* ALLOW_YIELD               --allow-yield           default 1 */
+    int32_t limit_reinforcement;     /* LIMIT_REINFORCEMENT_MOVES --limit-reinforcement   default 1 */
+    int32_t limit_attack;            /* LIMIT_ATTACK_MOVES        --limit-attack          default 0 */
+    int32_t max_game_rounds;         /* MAX_GAME_ROUNDS                                   default 58 */
+    int32_t min_unit_move;           /* MIN_UNIT_MOVE                                     default 3 */
+    int32_t mcts_simulations;        /* MCTS_SIMULATIONS          --mcts                  default 32 */
+    int32_t threads_per_mcts;        /* THREADS_PER_MCTS          -t   (sims - sims % t)  default 2 */
+    float cpuct;                     /* HP_EXPLORATION            --hp                    default 1.1 */
+    float dir_noise_value;           /* DIR_NOISE_VALUE           --dnv                   default 0.3 */
+    float dir_noise_epsi;            /* DIR_NOISE_EPSI            --dne                   default 0.25 */
+    int32_t temperature_threshold;   /* TEMPERATURE_TRESHOLD      --temp                  default 43 */
+} az_rules;
+
+typedef struct az_env az_env;
+
+/* counters accumulated on the device by az_env_rollout / az_selfplay_* (GameResults, game/game.h:17-29) */
+typedef struct az_counters {
+    uint64_t steps;        /* env steps applied                         */
+    uint64_t games;        /* games that reached a terminal status      */
+    uint64_t wins[2];      /* GameResults::players[i].win               */
+    uint64_t draws;        /* GameResults::draw                         */
+    uint64_t illegal;      /* rejected actions (always 0 for rollouts)  */
+    uint64_t sims;         /* MCTS simulations                          */
+    uint64_t evals;        /* network evaluations                       */
+} az_counters;
+
+AZ_API const char* az_last_error(void);
+AZ_API int az_version(void);
+AZ_API int az_device_count(void);
+AZ_API void az_default_rules(az_rules* r);                     /* settings.h:40-62 defaults */
+
+/* ---------------------------------------------------------------- environment (State + UtilityNN) */
+/* n_games lockstep games resident in HBM on `device`; first_game_id = global id of game 0
+   (games shard over GPUs by contiguous id range; the RNG contract is keyed by global id) */
+AZ_API int az_env_create(int n_games, const az_rules* rules, int device, uint32_t first_game_id, az_env** out);
+AZ_API int az_env_destroy(az_env* env);
+AZ_API int az_env_size(const az_env* env);
+
+/* State::newGame (state/state.cpp:137-167) for every game: Philox(seed, game, ply=0, AZ_STREAM_DEAL) */
+AZ_API int az_env_reset(az_env* env, uint64_t seed, void* stream);
+
+/* State::getData() images, n_games x 160 bytes (padding bytes are written as zero / ignored) */
+AZ_API int az_env_import_aos(az_env* env, const uint8_t* h_data, void* stream);
+AZ_API int az_env_export_aos(az_env* env, uint8_t* h_data, void* stream);
+
+/* UtilityNN::getValidMoves (player/alpha_zero/alphazero_moves.cpp:3-70): 43-bit mask per game */
+AZ_API int az_env_valid_moves(az_env* env, uint64_t* h_mask, void* stream);
+/* State::gameStatus (state/state.cpp:518-565) */
+AZ_API int az_env_status(az_env* env, int8_t* h_status, void* stream);
+
+/* UtilityNN::makeMove (alphazero_moves.cpp:72-233) on every game + gameStatus afterwards.
+   h_action[n]: 0..41 land, 42 skip.  h_dice: NULL = dice from the Philox contract
+   (seed of the last az_env_reset, game, ply), else n x 5 bytes consumed in the reference's
+   order (attacker dice, then defender dice).  h_status[n] receives the status byte. */
+AZ_API int az_env_step(az_env* env, const uint8_t* h_action, const uint8_t* h_dice, int8_t* h_status, void* stream);
+/* same with every buffer already resident in HBM; d_valid_after may be NULL */
+AZ_API int az_env_step_dev(az_env* env, const uint8_t* d_action, const uint8_t* d_dice, int8_t* d_status,
+                    uint64_t* d_valid_after, void* stream);
+
+/* NNInputData(State) + setInStateTensor (neural_network/alphazero_nn_data.cpp:165-196,
+   alphazero_nn.cpp:31-67): fp32 [n][7][6][13] */
+AZ_API int az_env_encode(az_env* env, float* h_x, void* stream);
+AZ_API int az_env_encode_dev(az_env* env, float* d_x, void* stream);
+
+/* BASELINE config 2: n_steps lockstep steps of uniform-random legal play on every game
+   (action = k-th set bit of the mask, k = mulhi(word1, popcount), dice = word0 of the
+   real-move Philox block); finished games are re-dealt in place.  Counters accumulate in
+   HBM; az_env_counters copies them to the host. */
+AZ_API int az_env_rollout(az_env* env, int n_steps, void* stream);
+AZ_API int az_env_counters(az_env* env, az_counters* h_out, int reset, void* stream);
+/* seconds spent by the last rollout / step launch on the device (CUDA events on `stream`) */
+AZ_API int az_env_last_kernel_ms(az_env* env, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZ_B200_H */
