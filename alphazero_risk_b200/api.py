@@ -67,6 +67,21 @@ def lib():
         L.az_env_rollout.argtypes = [vp, C.c_int, vp]
         L.az_env_counters.argtypes = [vp, C.POINTER(AzCounters), C.c_int, vp]
         L.az_env_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.az_nn_create.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+        L.az_nn_destroy.argtypes = [vp]
+        L.az_nn_blocks.argtypes = [vp]
+        L.az_nn_num_vars.argtypes = [vp]
+        L.az_nn_num_params.argtypes = [vp]
+        L.az_nn_num_params.restype = C.c_size_t
+        L.az_nn_var_info.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int * 4)]
+        L.az_nn_load_weights.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+        L.az_nn_get_weights.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+        L.az_nn_export_blob.argtypes = [vp, vp, C.c_size_t]
+        L.az_nn_import_blob.argtypes = [vp, vp, C.c_size_t]
+        L.az_nn_init_random.argtypes = [vp, C.c_uint64]
+        L.az_nn_finalize.argtypes = [vp]
+        L.az_nn_forward.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp]
+        L.az_nn_forward_dev.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp]
         _lib = L
     return _lib
 
@@ -165,3 +180,73 @@ class Env:
         ms = C.c_float(0)
         check(self.L.az_env_last_kernel_ms(self.h, C.byref(ms)))
         return float(ms.value)
+
+
+FP32, BF16 = 0, 1
+
+
+class Net:
+    """the policy/value conv ResNet (az_nn_*); weights keyed by the reference graph's TF variable names"""
+
+    def __init__(self, blocks=5, device=0, seed=None):
+        self.L = lib()
+        h = C.c_void_p()
+        check(self.L.az_nn_create(int(blocks), device, C.byref(h)))
+        self.h, self.blocks, self.device = h, int(blocks), device
+        if seed is not None:
+            self.init_random(seed)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.az_nn_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def variables(self):
+        out = []
+        for i in range(self.L.az_nn_num_vars(self.h)):
+            name, cnt, rank, shp = C.c_char_p(), C.c_size_t(), C.c_int(), (C.c_int * 4)()
+            check(self.L.az_nn_var_info(self.h, i, C.byref(name), C.byref(cnt), C.byref(rank), C.byref(shp)))
+            out.append((name.value.decode(), tuple(shp[k] for k in range(rank.value))))
+        return out
+
+    def num_params(self):
+        return int(self.L.az_nn_num_params(self.h))
+
+    def init_random(self, seed):
+        check(self.L.az_nn_init_random(self.h, int(seed)))
+
+    def load(self, name, array):
+        a = np.ascontiguousarray(array, np.float32)
+        check(self.L.az_nn_load_weights(self.h, name.encode(), _ptr(a), a.size))
+
+    def get(self, name, shape):
+        a = np.empty(shape, np.float32)
+        check(self.L.az_nn_get_weights(self.h, name.encode(), _ptr(a), a.size))
+        return a
+
+    def weights(self):
+        return {n: self.get(n, s) for n, s in self.variables()}
+
+    def export_blob(self):
+        a = np.empty(self.num_params(), np.float32)
+        check(self.L.az_nn_export_blob(self.h, _ptr(a), a.size))
+        return a
+
+    def import_blob(self, blob):
+        a = np.ascontiguousarray(blob, np.float32)
+        check(self.L.az_nn_import_blob(self.h, _ptr(a), a.size))
+
+    def finalize(self):
+        check(self.L.az_nn_finalize(self.h))
+
+    def forward(self, x, precision=FP32, stream=None):
+        a = np.ascontiguousarray(x, np.float32).reshape(-1, INPUT_FLOATS)
+        n = a.shape[0]
+        pol, val = np.empty((n, MOVES), np.float32), np.empty(n, np.float32)
+        check(self.L.az_nn_forward(self.h, _ptr(a), n, _ptr(pol), _ptr(val), precision, stream))
+        return pol, val
+
+    def forward_dev(self, d_x, n, d_policy, d_value, precision=FP32, stream=None):
+        check(self.L.az_nn_forward_dev(self.h, d_x, int(n), d_policy, d_value, precision, stream))

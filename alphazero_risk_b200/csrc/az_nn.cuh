@@ -1,0 +1,51 @@
+// az_nn.cuh — internal declarations shared by az_nn.cu (weights, fp32 forward, ABI),
+// az_nn_tc.cu (bf16 tcgen05 tower) and az_mcts.cu (leaf evaluation).
+#pragma once
+
+#include <map>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "az_b200.h"
+
+#define AZ_NN_CH 256          // FILTERS, python/src/build_graph.py:32
+#define AZ_NN_IN_CH 13        // FEATURES (INPUT_VECTOR_TYPE_2), build_graph.py:18
+#define AZ_NN_BN_EPS 0.001f   // tf.layers.batch_normalization default epsilon (GraphDef: 0.0010000000474974513)
+
+struct AzVar {
+    std::string name;
+    std::vector<int> shape;
+    size_t count = 0, offset = 0;
+    float glorot_limit = 0.0f, init_const = 0.0f;
+};
+
+struct AzHeadParams {
+    const float *pi_w, *bn_pi, *dense_w, *dense_b, *v_w, *bn_v, *dense1_w, *dense1_b, *dense2_w, *dense2_b;
+};
+
+struct AzTcState;   // az_nn_tc.cu
+
+struct az_nn {
+    int blocks = 5, device = 0;
+    std::vector<AzVar> vars;
+    std::map<std::string, int> index;
+    std::vector<float> blob;          // every variable, fp32, TF layouts (HWIO kernels), inventory order
+    bool finalized = false;
+    float* d_blob = nullptr;          // device copy of blob
+    int cap = 0;                      // positions the work buffers are sized for
+    float* d_act[3] = { nullptr, nullptr, nullptr };   // fp32 activations [cap][42][256]
+    float* d_x = nullptr; float* d_policy = nullptr; float* d_value = nullptr;   // staging for host-buffer calls
+    AzTcState* tc = nullptr;
+};
+
+const float* az_nn_host_var(const az_nn* nn, const std::string& name);
+const float* az_nn_dev_var(const az_nn* nn, const std::string& name);
+AzHeadParams az_nn_head_params(const az_nn* nn);
+int az_nn_reserve(az_nn* nn, int n);
+
+// bf16 tensor-core path (az_nn_tc.cu)
+int az_nn_tc_prepare(az_nn* nn);            // fold BN, pack bf16 weight tiles; called by finalize
+void az_nn_tc_release(az_nn* nn);
+// x: fp32 [n][7][6][13] (or NULL when env_state is given: encode fused into the stem)
+int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, int n, float* d_policy, float* d_value, cudaStream_t s);

@@ -133,6 +133,34 @@ AZ_API int az_env_counters(az_env* env, az_counters* h_out, int reset, void* str
 /* seconds spent by the last rollout / step launch on the device (CUDA events on `stream`) */
 AZ_API int az_env_last_kernel_ms(az_env* env, float* ms);
 
+/* ---------------------------------------------------------------- network (AlphaZeroNN / AlphaZeroNNId forward) */
+typedef struct az_nn az_nn;
+#define AZ_NN_FP32 0   /* fp32 CUDA-core validation path: agrees with an fp32 restatement of the graph to <= 1e-5 */
+#define AZ_NN_BF16 1   /* bf16 tcgen05 tensor-core path, fp32 accumulate / BN / heads */
+
+/* the conv ResNet of /root/reference/python/src/build_graph.py:54-90 with `blocks` residual blocks
+   (BLOCKS: 5 = shipped GraphDefs python/model/model_*_5.pb, 20 = CMake default) */
+AZ_API int az_nn_create(int blocks, int device, az_nn** out);
+AZ_API int az_nn_destroy(az_nn* nn);
+AZ_API int az_nn_blocks(const az_nn* nn);
+AZ_API int az_nn_num_vars(const az_nn* nn);
+AZ_API size_t az_nn_num_params(const az_nn* nn);
+/* i-th variable: TF variable name (e.g. "res0a_branch2a/kernel"), element count, rank, shape (HWIO kernels) */
+AZ_API int az_nn_var_info(const az_nn* nn, int i, const char** name, size_t* count, int* rank, int* shape4);
+/* weights by TF variable name, fp32, TF layout (replaces save/restore_all, neural_network/alphazero_nn.cpp:189-204) */
+AZ_API int az_nn_load_weights(az_nn* nn, const char* name, const float* h_ptr, size_t count);
+AZ_API int az_nn_get_weights(const az_nn* nn, const char* name, float* h_ptr, size_t count);
+/* all variables as one flat fp32 blob in inventory order (what gets broadcast between GPUs) */
+AZ_API int az_nn_export_blob(const az_nn* nn, float* h_out, size_t count);
+AZ_API int az_nn_import_blob(az_nn* nn, const float* h_in, size_t count);
+/* the graph's "init" op (alphazero_nn.cpp:185): Glorot-uniform kernels, zero biases, BN identity */
+AZ_API int az_nn_init_random(az_nn* nn, uint64_t seed);
+AZ_API int az_nn_finalize(az_nn* nn);
+/* AlphaZeroNN::predict / processBatchPrediction (alphazero_nn.cpp:236-267, 333-349):
+   x fp32 [n][7][6][13] -> policy [n][43] (softmax), value [n] (tanh) */
+AZ_API int az_nn_forward(az_nn* nn, const float* h_x, int n, float* h_policy, float* h_value, int precision, void* stream);
+AZ_API int az_nn_forward_dev(az_nn* nn, const float* d_x, int n, float* d_policy, float* d_value, int precision, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

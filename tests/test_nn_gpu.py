@@ -1,0 +1,91 @@
+"""GPU suite: the policy/value network forward through the C ABI against the PyTorch CPU
+restatement of the reference graph (oracle/nn_oracle.py), random-init weights (the graph's own
+init op: Glorot-uniform kernels, BN identity) and perturbed BN statistics."""
+import numpy as np
+import pytest
+
+from oracle import nn_oracle as no
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5       # north_star: network outputs within 1e-5 (fp32)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from alphazero_risk_b200 import api as a
+    if a.lib().az_device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu suite must run on a B200")
+    return a
+
+
+def game_inputs(n, seed=0xBEEF):
+    """encoded positions from seeded random play (the network's real input distribution)"""
+    xs, o, g = [], po.OracleGame(), 0
+    while len(xs) < n:
+        o.new_game(seed, g, 0)
+        ply = 0
+        while o.status() == -1 and len(xs) < n:
+            if ply % 9 == 0:
+                xs.append(o.encode())
+            o.move(o.random_action(seed, g, ply), seed, g, ply)
+            ply += 1
+        g += 1
+    return np.array(xs, np.float32).reshape(n, 7, 6, 13)
+
+
+def test_variable_inventory_matches_graph(api):
+    net = api.Net(blocks=5)
+    names = [n for n, _ in net.variables()]
+    assert names == no.variable_names(5)
+    shapes = dict(net.variables())
+    assert shapes["conv/kernel"] == (3, 3, 13, 256) and shapes["conv_bn/gamma"] == (7,)
+    assert shapes["res4e_branch2b/kernel"] == (3, 3, 256, 256) and shapes["dense/kernel"] == (84, 43)
+    assert shapes["dense_1/kernel"] == (42, 256) and shapes["dense_2/kernel"] == (256, 1) and shapes["pi/kernel"] == (1, 1, 256, 2)
+    # trainable parameters of the shipped 5-block graph: 5 949 022
+    trainable = sum(int(np.prod(s)) for n, s in net.variables() if "moving_" not in n)
+    assert trainable == 5949022
+    net.close()
+
+
+@pytest.mark.parametrize("blocks,n", [(5, 37), (2, 1), (5, 130)])
+def test_fp32_forward_matches_torch(api, blocks, n):
+    net = api.Net(blocks=blocks, seed=1234)
+    rng = np.random.default_rng(7)
+    # make BN non-trivial: the random-init identity statistics would hide indexing mistakes
+    for name, shape in net.variables():
+        if name.endswith("/gamma"):
+            net.load(name, rng.uniform(0.8, 1.2, shape))
+        elif name.endswith("/beta") or name.endswith("/moving_mean") or name.endswith("/bias"):
+            net.load(name, rng.uniform(-0.1, 0.1, shape))
+        elif name.endswith("/moving_variance"):
+            net.load(name, rng.uniform(0.7, 1.3, shape))
+    w = net.weights()
+    x = game_inputs(n)
+    pol, val = net.forward(x, api.FP32)
+    rp, rv = no.forward(w, x, blocks)
+    assert np.abs(pol.sum(1) - 1).max() < 1e-5
+    assert np.abs(pol - rp).max() <= FP32_TOL, np.abs(pol - rp).max()
+    assert np.abs(val - rv).max() <= FP32_TOL, np.abs(val - rv).max()
+    # batch invariance (the reference's commented-out testBatchNormalization, alphazero_risk.cpp:114-158)
+    p1, v1 = net.forward(x[:1], api.FP32)
+    assert (p1[0] == pol[0]).all() and v1[0] == val[0]
+    net.close()
+
+
+def test_random_init_is_the_graph_init(api):
+    net = api.Net(blocks=5, seed=42)
+    w = net.weights()
+    lim = {"conv/kernel": 0.049783, "res0a_branch2a/kernel": 0.036084, "pi/kernel": 0.152499, "dense/kernel": 0.217357,
+           "v/kernel": 0.152795, "dense_1/kernel": 0.141895, "dense_2/kernel": 0.152795}
+    for k, l in lim.items():
+        assert abs(np.abs(w[k]).max() - l) < 2e-3 * l + 1e-6 and abs(w[k].mean()) < 0.02 * l + 1e-3
+    assert (w["conv_bn/gamma"] == 1).all() and (w["bn_pi/moving_variance"] == 1).all() and (w["dense/bias"] == 0).all()
+    blob = net.export_blob()
+    net2 = api.Net(blocks=5)
+    net2.import_blob(blob)
+    x = game_inputs(5)
+    a, b = net.forward(x), net2.forward(x)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    net.close(); net2.close()
