@@ -82,6 +82,14 @@ def lib():
         L.az_nn_finalize.argtypes = [vp]
         L.az_nn_forward.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp]
         L.az_nn_forward_dev.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp]
+        L.az_mcts_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+        L.az_mcts_destroy.argtypes = [vp]
+        L.az_mcts_simulations.argtypes = [vp]
+        L.az_mcts_clear.argtypes = [vp, vp]
+        L.az_mcts_search.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+        L.az_mcts_root_stats.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+        L.az_selfplay_run.argtypes = [vp, C.c_int, vp]
+        L.az_mcts_counters.argtypes = [vp, C.POINTER(AzCounters), C.POINTER(C.c_uint64), C.c_int, vp]
         _lib = L
     return _lib
 
@@ -250,3 +258,57 @@ class Net:
 
     def forward_dev(self, d_x, n, d_policy, d_value, precision=FP32, stream=None):
         check(self.L.az_nn_forward_dev(self.h, d_x, int(n), d_policy, d_value, precision, stream))
+
+
+EVAL_NN, EVAL_PSEUDO, EVAL_UNIFORM = 0, 1, 2
+PICK_ARGMAX, PICK_SELFPLAY = 0, 1
+
+
+class Mcts:
+    """one search tree per game of `env` (az_mcts_*); hyper-parameters come from env.rules"""
+
+    def __init__(self, env, net=None, evaluator=EVAL_NN, precision=FP32):
+        self.L = lib()
+        self.env, self.net = env, net
+        h = C.c_void_p()
+        check(self.L.az_mcts_create(env.h, net.h if net is not None else None, evaluator, precision, C.byref(h)))
+        self.h, self.n = h, env.n
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.az_mcts_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def simulations(self):
+        return int(self.L.az_mcts_simulations(self.h))
+
+    def clear(self, stream=None):
+        check(self.L.az_mcts_clear(self.h, stream))
+
+    def search(self, pick_mode=PICK_ARGMAX, apply_move=False, extra_trim=None, stream=None):
+        n = self.n
+        N, pi = np.empty((n, MOVES), np.uint32), np.empty((n, MOVES), np.float32)
+        mv, st = np.empty(n, np.uint8), np.empty(n, np.int8)
+        et = None if extra_trim is None else np.ascontiguousarray(extra_trim, np.uint8)
+        check(self.L.az_mcts_search(self.h, _ptr(et) if et is not None else None, pick_mode, int(apply_move),
+                                    _ptr(N), _ptr(pi), _ptr(mv), _ptr(st), stream))
+        return dict(N=N, pi=pi, move=mv, status=st)
+
+    def root_stats(self, stream=None):
+        n = self.n
+        q, p = np.empty((n, MOVES), np.float32), np.empty((n, MOVES), np.float32)
+        sumn, val, tab = np.empty(n, np.uint32), np.empty(n, np.float32), np.empty(n, np.int32)
+        check(self.L.az_mcts_root_stats(self.h, _ptr(q), _ptr(p), _ptr(sumn), _ptr(val), _ptr(tab), stream))
+        return dict(Q=q, P=p, sumN=sumn, value=val, table=tab)
+
+    def selfplay(self, n_moves, stream=None):
+        check(self.L.az_selfplay_run(self.h, int(n_moves), stream))
+
+    def counters(self, reset=False, stream=None):
+        c, err = AzCounters(), C.c_uint64(0)
+        check(self.L.az_mcts_counters(self.h, C.byref(c), C.byref(err), int(reset), stream))
+        d = c.as_dict()
+        d["errors"] = int(err.value)
+        return d

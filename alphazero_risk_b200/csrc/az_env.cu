@@ -533,6 +533,20 @@ extern "C" int az_env_encode(az_env* e, float* h_x, void* stream)
     return AZ_OK;
 }
 
+// accessors for the other translation units of the library (az_mcts.cu)
+int az_launch_encode(const uint32_t* d_state, int n, float* d_x, cudaStream_t s)
+{
+    k_env_encode<<<(n + 3) / 4, 128, 0, s>>>(d_state, n, d_x);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+uint32_t* az_env_state_ptr(az_env* e) { return e->d_state; }
+int az_env_n(const az_env* e) { return e->n; }
+int az_env_device(const az_env* e) { return e->device; }
+uint64_t az_env_seed(const az_env* e) { return e->seed; }
+uint32_t az_env_first_game(const az_env* e) { return e->first_game; }
+const az_rules* az_env_rules(const az_env* e) { return &e->rules; }
+
 extern "C" int az_env_rollout(az_env* e, int n_steps, void* stream)
 {
     AZ_REQUIRE(e != nullptr, "env is NULL");

@@ -1,0 +1,646 @@
+// az_mcts.cu — lockstep MCTS over thousands of games for sm_100a, and the az_mcts_* / az_selfplay_* C ABI.
+//
+// Reference behaviour (player/alpha_zero/alphazero_mcts.cpp): a transposition table keyed by the
+// FULL game state (StateSimulationsStorage, :189-245), PUCT selection with a constant "noise"
+// prior mix (:67-119), recursive search with chance nodes re-sampled on every descent (:322-377),
+// backup Q = (N*Q + v)/(N+1) (:8-21), trim of nodes not visited since the previous search
+// (:229-245), root policy from visit counts (:121-148) and move choice (:379-412).
+//
+// B200 design: one WARP per game, THREADS_PER_MCTS = 1 semantics (one leaf in flight per game, so a
+// leaf batch is "all games").  Every game owns two node pools + two hash indices in HBM that
+// ping-pong per search: nodes created or visited during search k live in pool k&1 (a node found in
+// the previous pool is migrated on first touch), so "trimNodes" is an epoch bump + clearing one
+// small index, and a node is alive exactly when the reference would still hold it.  A node is one
+// 640-byte record (56-byte state key, legal mask, sumN, value, P[43], Q[43], N[43]) read and
+// written by the 32 lanes as coalesced rows; PUCT argmax and hash-window probing are warp
+// reductions; the float operations use explicit _rn intrinsics (and the TU is built with
+// -fmad=false) so every rounding matches the reference's x86 build bit for bit.
+#include <cstring>
+#include <new>
+
+#include "az_common.cuh"
+#include "az_game.cuh"
+#include "az_nn.cuh"
+#include "az_pseudo_net.h"
+
+#define NODE_WORDS 160
+#define NW_VALID 14
+#define NW_SUMN 16
+#define NW_VALUE 17
+#define NW_P 20
+#define NW_Q 64
+#define NW_N 108
+#define MCTS_WARPS 4
+#define FULL 0xffffffffu
+
+enum { EVAL_NN = 0, EVAL_PSEUDO = 1, EVAL_UNIFORM = 2 };
+enum { CNT_SIMS = 0, CNT_EVALS = 1, CNT_POOL_OVERFLOW = 2, CNT_DEPTH_OVERFLOW = 3, CNT_STEPS = 4, CNT_GAMES = 5, CNT_W0 = 6, CNT_W1 = 7, CNT_DRAW = 8, CNT_ILLEGAL = 9, CNT_N = 12 };
+
+struct MctsDev {
+    int n, cap, H, dmax;
+    uint32_t* nodes;        // [n][2][cap][NODE_WORDS]
+    uint32_t* index;        // [n][2][H]     0 = empty, else tag16 << 16 | (node + 1)
+    uint32_t* count;        // [n][2]
+    uint32_t* epoch;        // [n]
+    uint32_t* migrated;     // [n]
+    uint32_t* path;         // [n][dmax]     node | move << 16 | flip << 22
+    uint32_t* path_len;     // [n]
+    uint32_t* leaf_state;   // [16][n]
+    uint64_t* leaf_valid;   // [n]
+    int32_t* pending;       // [n]
+    float* term_value;      // [n]
+    float* nn_policy;       // [n][43]
+    float* nn_value;        // [n]
+    uint32_t* root_state;   // env state [16][n]
+    uint8_t* extra_trim;    // [n] trims to add before the next search (play-mode turn start / new game)
+    uint32_t* out_visits; float* out_pi; float* out_q; float* out_p; uint8_t* out_move; float* out_value; uint32_t* out_sumn; int32_t* out_table; int8_t* out_status;
+    unsigned long long* counters;
+    float c1, c2, cpuct;
+    uint64_t seed; uint32_t first_game;
+    AzRulesDev rules;
+    int eval_mode, temp_threshold;
+};
+
+struct WarpSmem {
+    uint32_t row[MCTS_WARPS][16];       // packed state of the game a warp is working on (land bytes + scalars)
+    uint32_t scratch[MCTS_WARPS][12];   // fortify DFS parent bytes
+};
+
+struct WG {                // warp-uniform game context: every lane holds the same values
+    AzGame g;
+    AzLandRow land, scratch;
+    uint32_t* row;
+};
+
+__device__ __forceinline__ void wg_bind(WG& w, WarpSmem& sm, int warp)
+{
+    w.row = sm.row[warp];
+    w.land.base = (uint8_t*)sm.row[warp];
+    w.scratch.base = (uint8_t*)sm.scratch[warp];
+}
+
+// state words (SoA [16][n]) -> warp context
+__device__ __forceinline__ void wg_load(WG& w, const uint32_t* __restrict__ st, int n, int gi, int lane)
+{
+    __syncwarp();
+    if (lane < 16) w.row[lane] = st[(size_t)lane * n + gi];
+    __syncwarp();
+    w.g.own0 = w.g.own1 = w.g.gt1 = w.g.full = 0;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) az_masks_add_word(w.g, w.row[k], k);
+    az_unpack_scalars(w.g, w.row[10], w.row[11], w.row[12], w.row[13]);
+}
+
+// registers -> packed words 10..13 of the row (land bytes are already there)
+__device__ __forceinline__ void wg_flush(WG& w, int lane)
+{
+    __syncwarp();
+    if (lane == 0) {
+        w.row[10] = (w.row[10] & 0xffffu) | (w.g.cards0 << 16) | (w.g.cards1 << 24);
+        w.row[11] = az_pack_w11(w.g); w.row[12] = az_pack_w12(w.g); w.row[13] = az_pack_w13(w.g);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint64_t warp_hash(uint32_t kw, int lane)
+{
+    uint64_t h = ((uint64_t)kw + 0x9E3779B97F4A7C15ull * (uint64_t)(lane + 1)) * 0xD6E8FEB86659FD93ull;
+    h ^= h >> 29;
+    if (lane >= 14) h = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        uint32_t lo = __shfl_xor_sync(FULL, (uint32_t)h, o), hi = __shfl_xor_sync(FULL, (uint32_t)(h >> 32), o);
+        h += ((uint64_t)hi << 32) | lo;
+    }
+    return az_pn_mix(h);
+}
+
+__device__ __forceinline__ uint32_t* node_ptr(const MctsDev& m, int gi, uint32_t pool, uint32_t idx)
+{
+    return m.nodes + (((size_t)gi * 2 + pool) * (size_t)m.cap + idx) * NODE_WORDS;
+}
+
+// probe one pool's index for the key held in lanes 0..13 (kw).  Returns node index or -1;
+// empty_slot = first empty slot of the probe sequence (where an insert would go).
+__device__ __forceinline__ int pool_lookup(const MctsDev& m, int gi, uint32_t pool, uint64_t h, uint32_t kw, int lane, int& empty_slot)
+{
+    const uint32_t* base = m.index + ((size_t)gi * 2 + pool) * (size_t)m.H;
+    const uint32_t tag = (uint32_t)(h >> 48) & 0xffffu;
+    const uint32_t start = (uint32_t)h & (uint32_t)(m.H - 1);
+    empty_slot = -1;
+    for (int win = 0; win < m.H; win += 32) {
+        uint32_t slot = (start + (uint32_t)win + (uint32_t)lane) & (uint32_t)(m.H - 1);
+        uint32_t e = base[slot];
+        uint32_t empties = __ballot_sync(FULL, e == 0);
+        uint32_t matches = __ballot_sync(FULL, e != 0 && (e >> 16) == tag);
+        int first_empty = empties ? (__ffs((int)empties) - 1) : 32;
+        if (first_empty < 32) matches &= (1u << first_empty) - 1u;
+        while (matches) {
+            int l = __ffs((int)matches) - 1; matches &= matches - 1;
+            uint32_t idx = (__shfl_sync(FULL, e, l) & 0xffffu) - 1u;
+            const uint32_t* nd = node_ptr(m, gi, pool, idx);
+            uint32_t w = lane < 14 ? nd[lane] : 0u;
+            if (__ballot_sync(FULL, w == kw) == FULL) return (int)idx;
+        }
+        if (first_empty < 32) { empty_slot = (int)((start + (uint32_t)win + (uint32_t)first_empty) & (uint32_t)(m.H - 1)); return -1; }
+    }
+    return -1;
+}
+
+__device__ __forceinline__ void index_insert(const MctsDev& m, int gi, uint32_t pool, int slot, uint64_t h, uint32_t idx, int lane)
+{
+    if (lane == 0) m.index[((size_t)gi * 2 + pool) * (size_t)m.H + slot] = (((uint32_t)(h >> 48) & 0xffffu) << 16) | (idx + 1u);
+    __syncwarp();
+}
+
+// find the node of the state in w.row: current pool first, then the previous one (migrating it).
+// Returns node index in the CURRENT pool or -1 (then ins_slot = where to insert in the current index).
+__device__ __forceinline__ int find_node(const MctsDev& m, int gi, uint32_t cur, const WG& w, int lane, uint64_t& h, int& ins_slot)
+{
+    uint32_t kw = lane < 14 ? w.row[lane] : 0u;
+    h = warp_hash(kw, lane);
+    int idx = pool_lookup(m, gi, cur, h, kw, lane, ins_slot);
+    if (idx >= 0) return idx;
+    int dummy;
+    int old = pool_lookup(m, gi, cur ^ 1u, h, kw, lane, dummy);
+    if (old < 0) return -1;
+    uint32_t cnt = m.count[gi * 2 + cur];
+    if ((int)cnt >= m.cap || ins_slot < 0) { if (lane == 0) atomicAdd(&m.counters[CNT_POOL_OVERFLOW], 1ull); return -2; }
+    const uint32_t* src = node_ptr(m, gi, cur ^ 1u, (uint32_t)old);
+    uint32_t* dst = node_ptr(m, gi, cur, cnt);
+#pragma unroll
+    for (int k = 0; k < NODE_WORDS / 32; ++k) dst[k * 32 + lane] = src[k * 32 + lane];
+    __syncwarp();
+    if (lane == 0) { m.count[gi * 2 + cur] = cnt + 1; m.migrated[gi] += 1; }
+    index_insert(m, gi, cur, ins_slot, h, cnt, lane);
+    return (int)cnt;
+}
+
+// StateSimulations::getNextBestMoveAndSetVisited, alphazero_mcts.cpp:67-119 (ascending-index
+// iteration = the contract; active_N never blocks at THREADS_PER_MCTS = 1)
+__device__ __forceinline__ int puct_select(const MctsDev& m, const uint32_t* nd, int lane)
+{
+    const uint64_t valid = (uint64_t)nd[NW_VALID] | ((uint64_t)nd[NW_VALID + 1] << 32);
+    const float sq = __fsqrt_rn(__fadd_rn(1.0f, (float)nd[NW_SUMN]));
+    float bu = -INFINITY; int bi = 64;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        int i = lane + 32 * k;
+        if (i < AZ_MOVES && ((valid >> i) & 1ull)) {
+            float P = __uint_as_float(nd[NW_P + i]), Q = __uint_as_float(nd[NW_Q + i]);
+            float noiseP = __fadd_rn(__fmul_rn(m.c1, P), m.c2);
+            float v = __fmul_rn(__fmul_rn(noiseP, m.cpuct), sq);
+            float nn = __fadd_rn(1.0f, (float)nd[NW_N + i]);
+            float u = __fadd_rn(Q, __fdiv_rn(v, nn));
+            if (u > bu) { bu = u; bi = i; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ou = __shfl_xor_sync(FULL, bu, o); int oi = __shfl_xor_sync(FULL, bi, o);
+        if (ou > bu || (ou == bu && oi < bi)) { bu = ou; bi = oi; }
+    }
+    return bi;
+}
+
+// part 1 of a simulation step: expand the pending leaf with the evaluator's output
+// (StateSimulations ctor :26-42 after NNOutputData::normalize, alphazero_nn_data.cpp:3-27)
+// and back the value up the recorded path (AlphaZeroMCTS::search :363-372, addValue :8-21)
+__device__ __forceinline__ void expand_and_backup(const MctsDev& m, int gi, uint32_t cur, WG& w, int lane)
+{
+    const uint32_t len = m.path_len[gi];
+    float v = m.term_value[gi];
+    if (m.pending[gi]) {
+        wg_load(w, m.leaf_state, m.n, gi, lane);
+        const uint64_t valid = m.leaf_valid[gi];
+        float p0 = 0.0f, p1 = 0.0f, value;
+        if (m.eval_mode == EVAL_NN) {
+            p0 = m.nn_policy[(size_t)gi * AZ_MOVES + lane];
+            if (lane + 32 < AZ_MOVES) p1 = m.nn_policy[(size_t)gi * AZ_MOVES + 32 + lane];
+            value = m.nn_value[gi];
+        } else if (m.eval_mode == EVAL_PSEUDO) {
+            uint64_t key = az_pn_key((const uint8_t*)w.row, (int)w.g.cur, (int)w.g.round, (int)w.g.phase);
+            p0 = az_pn_policy(key, lane);
+            if (lane + 32 < AZ_MOVES) p1 = az_pn_policy(key, lane + 32);
+            value = az_pn_value(key);
+        } else { p0 = 1.0f / 43.0f; p1 = lane + 32 < AZ_MOVES ? 1.0f / 43.0f : 0.0f; value = 0.0f; }
+        if (!((valid >> lane) & 1ull)) p0 = 0.0f;
+        if (lane + 32 >= AZ_MOVES || !((valid >> (lane + 32)) & 1ull)) p1 = 0.0f;
+        float sum = 0.0f;                                   // ascending-order fp32 sum, like the reference loop
+        for (int i = 0; i < AZ_MOVES; ++i) {
+            float pi = __shfl_sync(FULL, i < 32 ? p0 : p1, i & 31);
+            if ((valid >> i) & 1ull) sum = __fadd_rn(sum, pi);
+        }
+        if (p0 > 0.0f) p0 = __fdiv_rn(p0, sum);
+        if (p1 > 0.0f) p1 = __fdiv_rn(p1, sum);
+        uint64_t h; int ins;
+        uint32_t kw = lane < 14 ? w.row[lane] : 0u;
+        h = warp_hash(kw, lane);
+        int found = pool_lookup(m, gi, cur, h, kw, lane, ins);
+        uint32_t cnt = m.count[gi * 2 + cur];
+        if (found < 0 && (int)cnt < m.cap && ins >= 0) {
+            uint32_t* nd = node_ptr(m, gi, cur, cnt);
+            if (lane < 14) nd[lane] = kw;
+            if (lane == 14) nd[NW_VALID] = (uint32_t)valid;
+            if (lane == 15) nd[NW_VALID + 1] = (uint32_t)(valid >> 32);
+            if (lane == 16) nd[NW_SUMN] = 0u;
+            if (lane == 17) nd[NW_VALUE] = __float_as_uint(value);
+            nd[NW_P + lane] = __float_as_uint(p0); nd[NW_Q + lane] = 0u; nd[NW_N + lane] = 0u;
+            if (lane < 12) { nd[NW_P + 32 + lane] = __float_as_uint(p1); nd[NW_Q + 32 + lane] = 0u; nd[NW_N + 32 + lane] = 0u; }
+            __syncwarp();
+            if (lane == 0) { m.count[gi * 2 + cur] = cnt + 1; atomicAdd(&m.counters[CNT_EVALS], 1ull); }
+            index_insert(m, gi, cur, ins, h, cnt, lane);
+        } else if (found < 0 && lane == 0) atomicAdd(&m.counters[CNT_POOL_OVERFLOW], 1ull);
+        v = value;
+        if (lane == 0) m.pending[gi] = 0;
+    }
+    if (len > 0 && lane == 0) {
+        for (int d = (int)len - 1; d >= 0; --d) {
+            uint32_t e = m.path[(size_t)gi * m.dmax + d];
+            uint32_t idx = e & 0xffffu, mv = (e >> 16) & 63u;
+            if ((e >> 22) & 1u) v = -v;
+            uint32_t* nd = node_ptr(m, gi, cur, idx);
+            uint32_t N = nd[NW_N + mv];
+            float Q = __uint_as_float(nd[NW_Q + mv]);
+            float q = N == 0 ? v : __fdiv_rn(__fadd_rn(__fmul_rn((float)N, Q), v), (float)(N + 1u));
+            nd[NW_Q + mv] = __float_as_uint(q);
+            nd[NW_N + mv] = N + 1u;
+            nd[NW_SUMN] += 1u;
+        }
+        m.path_len[gi] = 0;
+        atomicAdd(&m.counters[CNT_SIMS], 1ull);
+    }
+    __syncwarp();
+}
+
+// part 2: one descent from the root (AlphaZeroMCTS::search :322-377 unrolled into a loop).
+// sim < 0: only the root lookup of setRootState (:289-307).
+__device__ __forceinline__ void descend(const MctsDev& m, int gi, uint32_t cur, WG& w, const AzTables& T, int sim, int lane)
+{
+    wg_load(w, m.root_state, m.n, gi, lane);
+    const uint32_t ply = w.row[AZ_W_PLY];
+    if (az_game_status(w.g, m.rules) != AZ_STATUS_RUNNING) { if (lane == 0) { m.pending[gi] = 0; m.path_len[gi] = 0; m.term_value[gi] = 0.0f; } return; }
+    AzDicePhilox dice; dice.init(m.seed, m.first_game + (uint32_t)gi, ply, (uint32_t)(sim < 0 ? 0 : sim));
+    uint32_t depth = 0;
+    for (;;) {
+        __syncwarp();
+        int st = az_game_status(w.g, m.rules);
+        if (st != AZ_STATUS_RUNNING) {
+            if (lane == 0) { m.term_value[gi] = st == AZ_STATUS_DRAW ? 0.0f : ((uint32_t)st == w.g.cur ? 1.0f : -1.0f); m.pending[gi] = 0; }
+            break;
+        }
+        uint64_t valid = az_valid_moves(w.g, T, m.rules);
+        uint64_t h; int ins;
+        int idx = find_node(m, gi, cur, w, lane, h, ins);
+        if (idx < 0) {                                      // unseen state: queue it for evaluation
+            if (lane < 14) m.leaf_state[(size_t)lane * m.n + gi] = w.row[lane];
+            if (lane == 0) { m.leaf_valid[gi] = valid; m.pending[gi] = idx == -1 ? 1 : 0; m.term_value[gi] = 0.0f; }
+            break;
+        }
+        if (sim < 0) { if (lane == 0) m.pending[gi] = 0; break; }       // setRootState: root already known
+        if ((int)depth >= m.dmax) { if (lane == 0) { atomicAdd(&m.counters[CNT_DEPTH_OVERFLOW], 1ull); m.pending[gi] = 0; m.term_value[gi] = 0.0f; } break; }
+        const uint32_t* nd = node_ptr(m, gi, cur, (uint32_t)idx);
+        int mv = puct_select(m, nd, lane);
+        uint32_t before = w.g.cur;
+        __syncwarp();      // every lane runs the (identical) transition on the shared row: keep them converged
+        az_make_move(w.g, w.land, w.scratch, T, m.rules, valid, mv, dice);
+        wg_flush(w, lane);
+        uint32_t flip = w.g.cur != before ? 1u : 0u;
+        if (lane == 0) m.path[(size_t)gi * m.dmax + depth] = (uint32_t)idx | ((uint32_t)mv << 16) | (flip << 22);
+        depth++;
+    }
+    if (lane == 0) m.path_len[gi] = depth;
+    __syncwarp();
+}
+
+// StateSimulationsStorage::trimNodes (:229-245) as an epoch bump; `extra` additional trims
+// (AlphaZeroPlayer::takeTurn's turn-start trim, alphazero_player.cpp:5; clearNodes on newGame :31-34)
+__global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_begin(MctsDev m, int extra_all)
+{
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int gi = blockIdx.x * MCTS_WARPS + warp;
+    if (gi >= m.n) return;
+    uint32_t trims = 1u + (uint32_t)extra_all + (uint32_t)m.extra_trim[gi];
+    uint32_t e = m.epoch[gi] + trims;
+    for (uint32_t t = 0; t < (trims > 2 ? 2u : trims); ++t) {
+        uint32_t pool = (e - t) & 1u;
+        uint32_t* ix = m.index + ((size_t)gi * 2 + pool) * (size_t)m.H;
+        for (int i = lane; i < m.H; i += 32) ix[i] = 0u;
+        if (lane == 0) m.count[gi * 2 + pool] = 0u;
+    }
+    if (lane == 0) { m.epoch[gi] = e; m.extra_trim[gi] = 0; m.migrated[gi] = 0; m.pending[gi] = 0; m.path_len[gi] = 0; }
+}
+
+__global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_sim(MctsDev m, const uint64_t* __restrict__ g_tab, int sim, int do_descent)
+{
+    __shared__ uint64_t s_tab[AZ_TABLE_U64];
+    __shared__ WarpSmem s_w;
+    for (int i = threadIdx.x; i < AZ_TABLE_U64; i += blockDim.x) s_tab[i] = g_tab[i];
+    __syncthreads();
+    AzTables T = az_tables_from_smem(s_tab);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int gi = blockIdx.x * MCTS_WARPS + warp;
+    if (gi >= m.n) return;
+    WG w; wg_bind(w, s_w, warp);
+    const uint32_t cur = m.epoch[gi] & 1u;
+    expand_and_backup(m, gi, cur, w, lane);
+    if (do_descent) descend(m, gi, cur, w, T, sim, lane);
+}
+
+// after the last simulation: root statistics (calculateMoveProbability :121-148), move choice
+// (pickHigestWeightedMove :397-412 / pickRandomWeightedMove :379-395 under the self-play
+// temperature rule, alphazero_trainer.cpp:98-106) and optionally the real move on the env state.
+__global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_finish(MctsDev m, const uint64_t* __restrict__ g_tab, int pick_mode, int apply_move, int auto_reset)
+{
+    __shared__ uint64_t s_tab[AZ_TABLE_U64];
+    __shared__ WarpSmem s_w;
+    for (int i = threadIdx.x; i < AZ_TABLE_U64; i += blockDim.x) s_tab[i] = g_tab[i];
+    __syncthreads();
+    AzTables T = az_tables_from_smem(s_tab);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int gi = blockIdx.x * MCTS_WARPS + warp;
+    if (gi >= m.n) return;
+    WG w; wg_bind(w, s_w, warp);
+    const uint32_t cur = m.epoch[gi] & 1u;
+    expand_and_backup(m, gi, cur, w, lane);
+    wg_load(w, m.root_state, m.n, gi, lane);
+    uint32_t ply = w.row[AZ_W_PLY];
+    const uint32_t game = m.first_game + (uint32_t)gi;
+    int status = az_game_status(w.g, m.rules);
+    int move = AZ_NONE;
+    if (status == AZ_STATUS_RUNNING) {
+        uint64_t h; int ins;
+        uint32_t kw = lane < 14 ? w.row[lane] : 0u;
+        h = warp_hash(kw, lane);
+        int idx = pool_lookup(m, gi, cur, h, kw, lane, ins);
+        uint32_t n0 = 0, n1 = 0; float q0 = 0.0f, q1 = 0.0f, pr0 = 0.0f, pr1 = 0.0f, value = 0.0f; uint32_t sumn = 0; uint64_t valid = 0;
+        if (idx >= 0) {
+            const uint32_t* nd = node_ptr(m, gi, cur, (uint32_t)idx);
+            valid = (uint64_t)nd[NW_VALID] | ((uint64_t)nd[NW_VALID + 1] << 32);
+            sumn = nd[NW_SUMN]; value = __uint_as_float(nd[NW_VALUE]);
+            if ((valid >> lane) & 1ull) { n0 = nd[NW_N + lane]; q0 = __uint_as_float(nd[NW_Q + lane]); pr0 = __uint_as_float(nd[NW_P + lane]); }
+            if (lane + 32 < AZ_MOVES && ((valid >> (lane + 32)) & 1ull)) { n1 = nd[NW_N + 32 + lane]; q1 = __uint_as_float(nd[NW_Q + 32 + lane]); pr1 = __uint_as_float(nd[NW_P + 32 + lane]); }
+        }
+        float f0 = (float)n0, f1 = (float)n1, sum = 0.0f;
+        for (int i = 0; i < AZ_MOVES; ++i) {
+            float fi = __shfl_sync(FULL, i < 32 ? f0 : f1, i & 31);
+            if ((valid >> i) & 1ull) sum = __fadd_rn(sum, fi);
+        }
+        float pi0 = __fdiv_rn(f0, sum), pi1 = __fdiv_rn(f1, sum);
+        if (!((valid >> lane) & 1ull)) pi0 = __fdiv_rn(0.0f, sum);
+        if (lane + 32 >= AZ_MOVES) pi1 = 0.0f;
+        bool sample = pick_mode == 1 && (int)w.g.round <= m.temp_threshold;
+        az_u32x4 blk = az_rng_block(m.seed, game, ply, AZ_STREAM_REAL, 0);
+        if (!sample) {
+            float best = 0.0f; int bi = AZ_NONE;
+            for (int i = 0; i < AZ_MOVES; ++i) {
+                float p = __shfl_sync(FULL, i < 32 ? pi0 : pi1, i & 31);
+                if (p > best) { best = p; bi = i; }
+            }
+            move = bi;
+        } else {
+            float tot = 0.0f;
+            for (int i = 0; i < AZ_MOVES; ++i) tot = __fadd_rn(tot, __shfl_sync(FULL, i < 32 ? pi0 : pi1, i & 31));
+            float a = __fmul_rn(tot, az_rng_unit_float(blk.z)), it = 0.0f;
+            for (int i = 0; i < AZ_MOVES; ++i) {
+                it = __fadd_rn(it, __shfl_sync(FULL, i < 32 ? pi0 : pi1, i & 31));
+                if (move == AZ_NONE && it >= a) move = i;
+            }
+        }
+        if (m.out_visits) {
+            size_t o = (size_t)gi * AZ_MOVES;
+            m.out_visits[o + lane] = n0; m.out_pi[o + lane] = pi0; m.out_q[o + lane] = q0; m.out_p[o + lane] = pr0;
+            if (lane + 32 < AZ_MOVES) { m.out_visits[o + 32 + lane] = n1; m.out_pi[o + 32 + lane] = pi1; m.out_q[o + 32 + lane] = q1; m.out_p[o + 32 + lane] = pr1; }
+            if (lane == 0) {
+                m.out_move[gi] = (uint8_t)move; m.out_value[gi] = value; m.out_sumn[gi] = sumn;
+                m.out_table[gi] = (int32_t)(m.count[gi * 2 + cur] + m.count[gi * 2 + (cur ^ 1u)] - m.migrated[gi]);
+            }
+        }
+        if (apply_move) {
+            uint64_t vm = az_valid_moves(w.g, T, m.rules);
+            AzDicePhilox dice; dice.init_with_block0(m.seed, game, ply, AZ_STREAM_REAL, blk);
+            __syncwarp();
+            int rc = az_make_move(w.g, w.land, w.scratch, T, m.rules, vm, move, dice);
+            if (rc == 0) { ply++; if (lane == 0) atomicAdd(&m.counters[CNT_STEPS], 1ull); }
+            else if (lane == 0) atomicAdd(&m.counters[CNT_ILLEGAL], 1ull);
+            status = az_game_status(w.g, m.rules);
+            if (status != AZ_STATUS_RUNNING && lane == 0) {
+                atomicAdd(&m.counters[CNT_GAMES], 1ull);
+                atomicAdd(&m.counters[status == 0 ? CNT_W0 : (status == 1 ? CNT_W1 : CNT_DRAW)], 1ull);
+            }
+            if (status != AZ_STATUS_RUNNING && auto_reset) {
+                __syncwarp();
+                az_new_game(w.g, w.land, m.seed, game, ply);      // threadExecuteTrainingGame starts the next game with a fresh AlphaZeroMCTS
+                if (lane == 0) m.extra_trim[gi] = 2;
+                status = AZ_STATUS_RUNNING;
+            }
+            wg_flush(w, lane);
+            if (lane < 14) m.root_state[(size_t)lane * m.n + gi] = w.row[lane];
+            if (lane == 14) m.root_state[(size_t)AZ_W_PLY * m.n + gi] = ply;
+        }
+    } else if (m.out_visits) {
+        size_t o = (size_t)gi * AZ_MOVES;
+        m.out_visits[o + lane] = 0; m.out_pi[o + lane] = 0.0f; m.out_q[o + lane] = 0.0f; m.out_p[o + lane] = 0.0f;
+        if (lane + 32 < AZ_MOVES) { m.out_visits[o + 32 + lane] = 0; m.out_pi[o + 32 + lane] = 0.0f; m.out_q[o + 32 + lane] = 0.0f; m.out_p[o + 32 + lane] = 0.0f; }
+        if (lane == 0) { m.out_move[gi] = AZ_NONE; m.out_value[gi] = 0.0f; m.out_sumn[gi] = 0; m.out_table[gi] = 0; }
+    }
+    if (m.out_status && lane == 0) m.out_status[gi] = (int8_t)status;
+}
+
+// ---------------------------------------------------------------- host side
+int az_launch_encode(const uint32_t* d_state, int n, float* d_x, cudaStream_t s);   // az_env.cu
+uint32_t* az_env_state_ptr(az_env* e); int az_env_n(const az_env* e); int az_env_device(const az_env* e);
+uint64_t az_env_seed(const az_env* e); uint32_t az_env_first_game(const az_env* e); const az_rules* az_env_rules(const az_env* e);
+
+struct az_mcts {
+    az_env* env = nullptr; az_nn* nn = nullptr;
+    int evaluator = EVAL_NN, precision = AZ_NN_FP32, device = 0;
+    MctsDev d;
+    float* d_x = nullptr;
+    std::vector<void*> allocs;
+};
+
+template <class T> static int dalloc(az_mcts* mc, T** p, size_t count, bool zero = true)
+{
+    AZ_CUDA(cudaMalloc(p, sizeof(T) * count));
+    if (zero) AZ_CUDA(cudaMemset(*p, 0, sizeof(T) * count));
+    mc->allocs.push_back(*p);
+    return AZ_OK;
+}
+
+static int next_pow2(int v) { int p = 64; while (p < v) p <<= 1; return p; }
+
+extern "C" int az_mcts_create(az_env* env, az_nn* nn, int evaluator, int precision, az_mcts** out)
+{
+    AZ_REQUIRE(env && out, "NULL argument");
+    AZ_REQUIRE(evaluator >= EVAL_NN && evaluator <= EVAL_UNIFORM, "unknown evaluator");
+    AZ_REQUIRE(evaluator != EVAL_NN || nn != nullptr, "evaluator AZ_EVAL_NN needs a network");
+    AZ_REQUIRE(precision == AZ_NN_FP32 || precision == AZ_NN_BF16, "unknown precision");
+    const az_rules* r = az_env_rules(env);
+    int T = r->threads_per_mcts < 1 ? 1 : r->threads_per_mcts;
+    int sims = r->mcts_simulations - (r->mcts_simulations % T);          // alphazero_mcts.cpp:265
+    AZ_REQUIRE(sims >= 1, "mcts_simulations - mcts_simulations % threads_per_mcts must be >= 1");
+    AzDeviceGuard guard(az_env_device(env));
+    az_mcts* mc = new (std::nothrow) az_mcts();
+    AZ_REQUIRE(mc != nullptr, "out of host memory");
+    mc->env = env; mc->nn = nn; mc->evaluator = evaluator; mc->precision = precision; mc->device = az_env_device(env);
+    MctsDev& d = mc->d;
+    memset(&d, 0, sizeof d);
+    d.n = az_env_n(env);
+    d.cap = 3 * (sims + 1) + 64; if (d.cap > 65000) d.cap = 65000;
+    d.H = next_pow2(2 * d.cap);
+    d.dmax = 192;
+    size_t n = (size_t)d.n;
+    int rc = 0;
+    rc |= dalloc(mc, &d.nodes, n * 2 * d.cap * NODE_WORDS, false);
+    rc |= dalloc(mc, &d.index, n * 2 * d.H);
+    rc |= dalloc(mc, &d.count, n * 2); rc |= dalloc(mc, &d.epoch, n); rc |= dalloc(mc, &d.migrated, n);
+    rc |= dalloc(mc, &d.path, n * d.dmax); rc |= dalloc(mc, &d.path_len, n);
+    rc |= dalloc(mc, &d.leaf_state, n * 16); rc |= dalloc(mc, &d.leaf_valid, n); rc |= dalloc(mc, &d.pending, n);
+    rc |= dalloc(mc, &d.term_value, n); rc |= dalloc(mc, &d.nn_policy, n * AZ_MOVES); rc |= dalloc(mc, &d.nn_value, n);
+    rc |= dalloc(mc, &d.extra_trim, n);
+    rc |= dalloc(mc, &d.out_visits, n * AZ_MOVES); rc |= dalloc(mc, &d.out_pi, n * AZ_MOVES); rc |= dalloc(mc, &d.out_q, n * AZ_MOVES);
+    rc |= dalloc(mc, &d.out_p, n * AZ_MOVES); rc |= dalloc(mc, &d.out_move, n); rc |= dalloc(mc, &d.out_value, n);
+    rc |= dalloc(mc, &d.out_sumn, n); rc |= dalloc(mc, &d.out_table, n); rc |= dalloc(mc, &d.out_status, n);
+    rc |= dalloc(mc, &d.counters, (size_t)CNT_N);
+    if (evaluator == EVAL_NN) rc |= dalloc(mc, &mc->d_x, n * AZ_INPUT_FLOATS);
+    if (rc) { for (void* p : mc->allocs) cudaFree(p); delete mc; return AZ_ERR_CUDA; }
+    d.root_state = az_env_state_ptr(env);
+    d.c1 = 1.0f - r->dir_noise_epsi;                 // (1 - SETTINGS.DIR_NOISE_EPSI), alphazero_mcts.cpp:81
+    d.c2 = r->dir_noise_epsi * r->dir_noise_value;   // SETTINGS.DIR_NOISE_EPSI * SETTINGS.DIR_NOISE_VALUE
+    d.cpuct = r->cpuct;
+    d.rules.allow_yield = r->allow_yield; d.rules.limit_reinforcement = r->limit_reinforcement; d.rules.limit_attack = r->limit_attack;
+    d.rules.max_game_rounds = r->max_game_rounds; d.rules.min_unit_move = r->min_unit_move;
+    d.eval_mode = evaluator; d.temp_threshold = r->temperature_threshold;
+    *out = mc;
+    return AZ_OK;
+}
+
+extern "C" int az_mcts_destroy(az_mcts* mc)
+{
+    if (!mc) return AZ_OK;
+    AzDeviceGuard guard(mc->device);
+    for (void* p : mc->allocs) cudaFree(p);
+    delete mc;
+    return AZ_OK;
+}
+
+extern "C" int az_mcts_simulations(const az_mcts* mc)
+{
+    if (!mc) return 0;
+    const az_rules* r = az_env_rules(mc->env);
+    int T = r->threads_per_mcts < 1 ? 1 : r->threads_per_mcts;
+    return r->mcts_simulations - (r->mcts_simulations % T);
+}
+
+// StateSimulationsStorage::clearNodes for every game (AlphaZeroPlayer::newGame, alphazero_player.cpp:31-34)
+extern "C" int az_mcts_clear(az_mcts* mc, void* stream)
+{
+    AZ_REQUIRE(mc != nullptr, "mcts is NULL");
+    AzDeviceGuard guard(mc->device);
+    AZ_CUDA(cudaMemsetAsync(mc->d.extra_trim, 2, (size_t)mc->d.n, (cudaStream_t)stream));
+    return AZ_OK;
+}
+
+static int evaluate_leaves(az_mcts* mc, cudaStream_t s)
+{
+    if (mc->evaluator != EVAL_NN) return AZ_OK;
+    MctsDev& d = mc->d;
+    if (mc->precision == AZ_NN_BF16) {
+        int rc = az_nn_reserve(mc->nn, d.n); if (rc) return rc;
+        return az_nn_tc_forward(mc->nn, nullptr, d.leaf_state, d.n, d.nn_policy, d.nn_value, s);
+    }
+    int rc = az_launch_encode(d.leaf_state, d.n, mc->d_x, s); if (rc) return rc;
+    return az_nn_forward_dev(mc->nn, mc->d_x, d.n, d.nn_policy, d.nn_value, AZ_NN_FP32, s);
+}
+
+// one AlphaZeroMCTS::simulate (alphazero_mcts.cpp:255-287) for every game, then the move choice
+static int search_once(az_mcts* mc, int extra_all, int pick_mode, int apply_move, int auto_reset, cudaStream_t s)
+{
+    MctsDev& d = mc->d;
+    d.seed = az_env_seed(mc->env); d.first_game = az_env_first_game(mc->env);
+    const uint64_t* tab = az_device_tables();
+    int grid = (d.n + MCTS_WARPS - 1) / MCTS_WARPS, sims = az_mcts_simulations(mc);
+    k_mcts_begin<<<grid, MCTS_WARPS * 32, 0, s>>>(d, extra_all);
+    k_mcts_sim<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, -1, 1);             // setRootState
+    AZ_CUDA(cudaGetLastError());
+    int rc = evaluate_leaves(mc, s); if (rc) return rc;
+    for (int i = 0; i < sims; ++i) {
+        k_mcts_sim<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, i, 1);
+        AZ_CUDA(cudaGetLastError());
+        rc = evaluate_leaves(mc, s); if (rc) return rc;
+    }
+    k_mcts_finish<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, pick_mode, apply_move, auto_reset);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+extern "C" int az_mcts_search(az_mcts* mc, const uint8_t* h_extra_trim, int pick_mode, int apply_move,
+                              uint32_t* h_visits, float* h_pi, uint8_t* h_move, int8_t* h_status, void* stream)
+{
+    AZ_REQUIRE(mc != nullptr, "mcts is NULL");
+    AZ_REQUIRE(pick_mode == 0 || pick_mode == 1, "pick_mode: 0 = argmax (play), 1 = self-play temperature rule");
+    AzDeviceGuard guard(mc->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    MctsDev& d = mc->d;
+    if (h_extra_trim) {
+        // added to (not replacing) trims already scheduled on the device, e.g. by az_mcts_clear
+        std::vector<uint8_t> cur(d.n);
+        AZ_CUDA(cudaMemcpyAsync(cur.data(), d.extra_trim, (size_t)d.n, cudaMemcpyDeviceToHost, s));
+        AZ_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i < d.n; ++i) cur[i] = (uint8_t)(cur[i] + h_extra_trim[i]);
+        AZ_CUDA(cudaMemcpyAsync(d.extra_trim, cur.data(), (size_t)d.n, cudaMemcpyHostToDevice, s));
+        AZ_CUDA(cudaStreamSynchronize(s));
+    }
+    int rc = search_once(mc, 0, pick_mode, apply_move, 0, s); if (rc) return rc;
+    size_t n = (size_t)d.n;
+    if (h_visits) AZ_CUDA(cudaMemcpyAsync(h_visits, d.out_visits, sizeof(uint32_t) * n * AZ_MOVES, cudaMemcpyDeviceToHost, s));
+    if (h_pi) AZ_CUDA(cudaMemcpyAsync(h_pi, d.out_pi, sizeof(float) * n * AZ_MOVES, cudaMemcpyDeviceToHost, s));
+    if (h_move) AZ_CUDA(cudaMemcpyAsync(h_move, d.out_move, n, cudaMemcpyDeviceToHost, s));
+    if (h_status) AZ_CUDA(cudaMemcpyAsync(h_status, d.out_status, n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+extern "C" int az_mcts_root_stats(az_mcts* mc, float* h_q, float* h_p, uint32_t* h_sumn, float* h_value, int32_t* h_table, void* stream)
+{
+    AZ_REQUIRE(mc != nullptr, "mcts is NULL");
+    AzDeviceGuard guard(mc->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    MctsDev& d = mc->d; size_t n = (size_t)d.n;
+    if (h_q) AZ_CUDA(cudaMemcpyAsync(h_q, d.out_q, sizeof(float) * n * AZ_MOVES, cudaMemcpyDeviceToHost, s));
+    if (h_p) AZ_CUDA(cudaMemcpyAsync(h_p, d.out_p, sizeof(float) * n * AZ_MOVES, cudaMemcpyDeviceToHost, s));
+    if (h_sumn) AZ_CUDA(cudaMemcpyAsync(h_sumn, d.out_sumn, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
+    if (h_value) AZ_CUDA(cudaMemcpyAsync(h_value, d.out_value, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+    if (h_table) AZ_CUDA(cudaMemcpyAsync(h_table, d.out_table, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+// n_moves lockstep self-play moves (threadExecuteTrainingGame, alphazero_trainer.cpp:80-119) with no
+// host synchronisation: search, temperature-rule move choice, real move, finished games re-dealt.
+extern "C" int az_selfplay_run(az_mcts* mc, int n_moves, void* stream)
+{
+    AZ_REQUIRE(mc != nullptr && n_moves >= 0, "bad argument");
+    AzDeviceGuard guard(mc->device);
+    for (int i = 0; i < n_moves; ++i) {
+        int rc = search_once(mc, 0, 1, 1, 1, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return AZ_OK;
+}
+
+extern "C" int az_mcts_counters(az_mcts* mc, az_counters* h_out, uint64_t* h_errors, int reset, void* stream)
+{
+    AZ_REQUIRE(mc && h_out, "NULL argument");
+    AzDeviceGuard guard(mc->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long h[CNT_N];
+    AZ_CUDA(cudaMemcpyAsync(h, mc->d.counters, sizeof h, cudaMemcpyDeviceToHost, s));
+    if (reset) AZ_CUDA(cudaMemsetAsync(mc->d.counters, 0, sizeof h, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    h_out->sims = h[CNT_SIMS]; h_out->evals = h[CNT_EVALS]; h_out->steps = h[CNT_STEPS]; h_out->games = h[CNT_GAMES];
+    h_out->wins[0] = h[CNT_W0]; h_out->wins[1] = h[CNT_W1]; h_out->draws = h[CNT_DRAW]; h_out->illegal = h[CNT_ILLEGAL];
+    if (h_errors) *h_errors = h[CNT_POOL_OVERFLOW] + h[CNT_DEPTH_OVERFLOW];
+    return AZ_OK;
+}

@@ -161,6 +161,38 @@ AZ_API int az_nn_finalize(az_nn* nn);
 AZ_API int az_nn_forward(az_nn* nn, const float* h_x, int n, float* h_policy, float* h_value, int precision, void* stream);
 AZ_API int az_nn_forward_dev(az_nn* nn, const float* d_x, int n, float* d_policy, float* d_value, int precision, void* stream);
 
+/* ---------------------------------------------------------------- MCTS (AlphaZeroMCTS) and self-play */
+typedef struct az_mcts az_mcts;
+#define AZ_EVAL_NN 0        /* leaf evaluation by the network (az_nn) */
+#define AZ_EVAL_PSEUDO 1    /* include/az_pseudo_net.h: exactly representable outputs, for bit-exact search parity tests */
+#define AZ_EVAL_UNIFORM 2   /* uniform prior, value 0 ("null evaluator": tree + env cost only) */
+
+/* one search tree (transposition table) per game of `env`; hyper-parameters come from the env's az_rules
+   (mcts_simulations, threads_per_mcts -> sims - sims % t, cpuct, dir_noise_*, temperature_threshold).
+   Replaces AlphaZeroMCTS (player/alpha_zero/alphazero_mcts.h:75-94) with THREADS_PER_MCTS = 1 semantics. */
+AZ_API int az_mcts_create(az_env* env, az_nn* nn, int evaluator, int precision, az_mcts** out);
+AZ_API int az_mcts_destroy(az_mcts* mcts);
+AZ_API int az_mcts_simulations(const az_mcts* mcts);
+/* StateSimulationsStorage::clearNodes for every game (AlphaZeroPlayer::newGame, alphazero_player.cpp:31-34) */
+AZ_API int az_mcts_clear(az_mcts* mcts, void* stream);
+/* AlphaZeroMCTS::simulate (alphazero_mcts.cpp:255-287) on the current state of every running game, then
+   calculateMoveProbability(1.0) (:121-148) and the move choice: pick_mode 0 = pickHigestWeightedMove (play,
+   alphazero_player.cpp:12), 1 = the self-play rule of alphazero_trainer.cpp:98-106 (sample while
+   round <= TEMPERATURE_TRESHOLD).  h_extra_trim (NULL or [n]): additional trimNodes before the search —
+   1 at the first search of a player's turn in play mode (alphazero_player.cpp:5).  apply_move != 0 also
+   plays the chosen move on the env (UtilityNN::makeMove, dice from the Philox contract).
+   Outputs (each may be NULL): visit counts N [n][43], pi [n][43], chosen move [n], status after [n]. */
+AZ_API int az_mcts_search(az_mcts* mcts, const uint8_t* h_extra_trim, int pick_mode, int apply_move,
+                          uint32_t* h_visits, float* h_pi, uint8_t* h_move, int8_t* h_status, void* stream);
+/* root statistics of the last search (test introspection): Q [n][43], P [n][43], sumN [n], root value [n],
+   number of live nodes in the table [n] */
+AZ_API int az_mcts_root_stats(az_mcts* mcts, float* h_q, float* h_p, uint32_t* h_sumn, float* h_value, int32_t* h_table, void* stream);
+/* n_moves lockstep self-play moves with no host synchronisation (threadExecuteTrainingGame,
+   alphazero_trainer.cpp:80-119): search, temperature-rule move, real move, finished games re-dealt */
+AZ_API int az_selfplay_run(az_mcts* mcts, int n_moves, void* stream);
+/* counters since the last reset; *h_errors = node-pool + path-depth overflows (must be 0) */
+AZ_API int az_mcts_counters(az_mcts* mcts, az_counters* h_out, uint64_t* h_errors, int reset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,177 @@
+"""GPU suite: the CUDA MCTS through the C ABI against the CPU oracle (itself pinned bit-for-bit to the
+compiled reference's AlphaZeroMCTS) and the reference's golden search traces.  Visit counts, Q, P, pi,
+table sizes and chosen moves are compared as BIT PATTERNS given identical evaluator outputs."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+SEED = 0x5EED0001
+
+
+@pytest.fixture(scope="module")
+def api():
+    from alphazero_risk_b200 import api as a
+    if a.lib().az_device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu suite must run on a B200")
+    return a
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def run_lockstep(api, n, first, sims, T, play_mode, max_moves, evaluator="pseudo", net=None, oracle_eval=None):
+    rules_o = po.default_rules(mcts_simulations=sims, threads_per_mcts=T)
+    rules_d = api.default_rules(mcts_simulations=sims, threads_per_mcts=T)
+    env = api.Env(n, rules=rules_d, first_game_id=first)
+    env.reset(SEED)
+    ev = {"pseudo": api.EVAL_PSEUDO, "uniform": api.EVAL_UNIFORM, "nn": api.EVAL_NN}[evaluator]
+    mc = api.Mcts(env, net=net, evaluator=ev)
+    assert mc.simulations() == sims - sims % T
+    games = [po.OracleGame(rules_o) for _ in range(n)]
+    trees = []
+    for g, o in enumerate(games):
+        o.new_game(SEED, first + g, 0)
+        t = po.OracleMcts(rules_o, "pseudo" if evaluator == "nn" else evaluator)
+        if oracle_eval is not None:
+            t.L.ro_mcts_free(t.h)
+            t.h = t.L.ro_mcts_new(C.cast(oracle_eval, C.c_void_p), None)
+        trees.append(t)
+    ply = np.zeros(n, int)
+    last_cur = [None] * n
+    moves_done = 0
+    for step in range(max_moves):
+        extra = np.zeros(n, np.uint8)
+        if play_mode:
+            for g, o in enumerate(games):
+                if o.status() == -1 and o.s.cur != last_cur[g]:
+                    extra[g] = 1
+        res = mc.search(pick_mode=api.PICK_ARGMAX if play_mode else api.PICK_SELFPLAY, apply_move=True,
+                        extra_trim=extra if play_mode else None)
+        rs = mc.root_stats()
+        for g, o in enumerate(games):
+            if o.status() != -1:
+                assert res["move"][g] == 43 and res["status"][g] == o.status()
+                continue
+            if play_mode and extra[g]:
+                trees[g].trim(); last_cur[g] = o.s.cur
+            a = trees[g].search(o, SEED, first + g, int(ply[g]))
+            assert (res["N"][g] == a["N"]).all(), (step, g, res["N"][g], a["N"])
+            assert (bits(rs["Q"][g]) == bits(a["Q"])).all(), (step, g)
+            assert (bits(rs["P"][g]) == bits(a["P"])).all(), (step, g)
+            assert (bits(res["pi"][g]) == bits(a["pi"])).all(), (step, g)
+            assert rs["sumN"][g] == a["sumN"] and bits(rs["value"][g:g + 1])[0] == bits(np.float32([a["value"]]))[0]
+            assert rs["table"][g] == trees[g].table_size(), (step, g, rs["table"][g], trees[g].table_size())
+            sample = (not play_mode) and o.s.round <= rules_o.temperature_threshold
+            mv = trees[g].pick(a["pi"], sample, SEED, first + g, int(ply[g]))
+            assert res["move"][g] == mv, (step, g)
+            assert o.move(mv, SEED, first + g, int(ply[g])) == 0
+            ply[g] += 1
+            moves_done += 1
+            assert res["status"][g] == o.status()
+        if step % 16 == 0 or step == max_moves - 1:
+            dev = env.export_aos()
+            for g, o in enumerate(games):
+                assert (dev[g] == o.data()).all(), (step, g)
+        if all(o.status() != -1 for o in games):
+            break
+    cnt = mc.counters()
+    assert cnt["errors"] == 0 and cnt["illegal"] == 0
+    assert cnt["sims"] == moves_done * (sims - sims % T)
+    mc.close(); env.close()
+    return moves_done
+
+
+def test_selfplay_pseudo_net_16_sims(api):
+    assert run_lockstep(api, n=24, first=500, sims=16, T=1, play_mode=False, max_moves=130) > 2500
+
+
+def test_selfplay_full_games_64_sims(api):
+    assert run_lockstep(api, n=3, first=9000, sims=64, T=1, play_mode=False, max_moves=400) > 500
+
+
+def test_play_mode_turn_start_trim_and_thread_rounding(api):
+    # MCTS_SIMULATIONS = 33 with THREADS_PER_MCTS = 2 -> 32 simulations (alphazero_mcts.cpp:265)
+    assert run_lockstep(api, n=6, first=77, sims=33, T=2, play_mode=True, max_moves=150) > 500
+
+
+def test_uniform_evaluator(api):
+    assert run_lockstep(api, n=4, first=31, sims=24, T=1, play_mode=False, max_moves=60, evaluator="uniform") > 200
+
+
+@pytest.mark.parametrize("name", ["selfplay16", "selfplay64", "play32t2"])
+def test_reference_golden_search_traces(api, golden_dir, name):
+    """the compiled reference's own search traces (tests/golden/mcts_trace.npz), one game each"""
+    t = np.load(os.path.join(golden_dir, "mcts_trace.npz"))
+    sims, T, play_mode, g = [int(v) for v in t[name + "_cfg"]]
+    seed = int(t["seed"])
+    env = api.Env(1, rules=api.default_rules(mcts_simulations=sims, threads_per_mcts=T), first_game_id=g)
+    env.reset(seed)
+    mc = api.Mcts(env, evaluator=api.EVAL_PSEUDO)
+    n = len(t[name + "_move"])
+    for ply in range(n):
+        assert (env.export_aos()[0] == t[name + "_root"][ply]).all(), ply
+        extra = np.array([1 if t[name + "_trimmed"][ply] else 0], np.uint8)
+        res = mc.search(pick_mode=api.PICK_ARGMAX if play_mode else api.PICK_SELFPLAY, apply_move=True, extra_trim=extra)
+        rs = mc.root_stats()
+        assert (res["N"][0] == t[name + "_N"][ply]).all(), ply
+        assert (bits(rs["Q"][0]) == t[name + "_Q"][ply]).all() and (bits(rs["P"][0]) == t[name + "_P"][ply]).all()
+        assert (bits(res["pi"][0]) == t[name + "_pi"][ply]).all()
+        assert rs["sumN"][0] == t[name + "_sumN"][ply] and bits(rs["value"])[0] == t[name + "_value"][ply]
+        assert rs["table"][0] == t[name + "_table"][ply]
+        assert res["move"][0] == t[name + "_move"][ply]
+    assert (env.export_aos()[0] == t[name + "_final"]).all()
+    assert env.status()[0] == int(t[name + "_status"])
+    assert mc.counters()["errors"] == 0
+    mc.close(); env.close()
+
+
+def test_search_with_network_matches_oracle_given_same_outputs(api):
+    """evaluator = the fp32 network.  The oracle search calls the SAME network (batch of one, the
+    kernels are batch-invariant) for its leaf evaluations, so both sides see identical outputs."""
+    net = api.Net(blocks=2, seed=1234)
+    L = po.oracle_lib()
+
+    @C.CFUNCTYPE(None, C.POINTER(po.RoState), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p)
+    def evaluator(sp, policy, value, user):
+        x = np.zeros(po.INPUT_FLOATS, np.float32)
+        L.ro_encode(sp, x)
+        p, v = net.forward(x.reshape(1, -1), api.FP32)
+        for i in range(43):
+            policy[i] = float(p[0, i])
+        value[0] = float(v[0])
+
+    assert run_lockstep(api, n=5, first=4242, sims=12, T=1, play_mode=False, max_moves=70, evaluator="nn", net=net,
+                        oracle_eval=evaluator) > 300
+    net.close()
+
+
+def test_selfplay_run_device_loop(api):
+    """az_selfplay_run: many moves with no host synchronisation, finished games re-dealt, trees cleared"""
+    n, moves = 64, 500
+    env = api.Env(n, rules=api.default_rules(mcts_simulations=8, threads_per_mcts=1), first_game_id=0)
+    env.reset(SEED)
+    mc = api.Mcts(env, evaluator=api.EVAL_PSEUDO)
+    mc.selfplay(moves)
+    cnt = mc.counters()
+    assert cnt["errors"] == 0 and cnt["illegal"] == 0
+    assert cnt["steps"] == n * moves and cnt["sims"] == n * moves * 8
+    assert cnt["games"] == cnt["wins"][0] + cnt["wins"][1] + cnt["draws"] and cnt["games"] > n // 2
+    # replay game 0 on the oracle, including the re-deals and the table clears
+    rules = po.default_rules(mcts_simulations=8, threads_per_mcts=1)
+    o, t = po.OracleGame(rules), po.OracleMcts(rules, "pseudo")
+    o.new_game(SEED, 0, 0)
+    for ply in range(moves):
+        a = t.search(o, SEED, 0, ply)
+        mv = t.pick(a["pi"], o.s.round <= rules.temperature_threshold, SEED, 0, ply)
+        assert o.move(mv, SEED, 0, ply) == 0
+        if o.status() != -1:
+            o.new_game(SEED, 0, ply + 1)
+            t.clear()
+    assert (env.export_aos()[0] == o.data()).all()
+    mc.close(); env.close()

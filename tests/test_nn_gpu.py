@@ -43,9 +43,10 @@ def test_variable_inventory_matches_graph(api):
     assert shapes["conv/kernel"] == (3, 3, 13, 256) and shapes["conv_bn/gamma"] == (7,)
     assert shapes["res4e_branch2b/kernel"] == (3, 3, 256, 256) and shapes["dense/kernel"] == (84, 43)
     assert shapes["dense_1/kernel"] == (42, 256) and shapes["dense_2/kernel"] == (256, 1) and shapes["pi/kernel"] == (1, 1, 256, 2)
-    # trainable parameters of the shipped 5-block graph: 5 949 022
+    # VarHandleOp inventory of the shipped 5-block GraphDef (python/model/model_txt_V2_5.pb):
+    # 5 954 160 elements, 5 949 020 of them trainable (everything but the BN moving statistics)
     trainable = sum(int(np.prod(s)) for n, s in net.variables() if "moving_" not in n)
-    assert trainable == 5949022
+    assert trainable == 5949020 and net.num_params() == 5954160
     net.close()
 
 
