@@ -1,11 +1,449 @@
-// az_nn_tc.cu — bf16 tcgen05 tensor-core tower (placeholder until the kernel lands in this round).
+// az_nn_tc.cu — the residual tower of the policy/value network on 5th-generation tensor cores
+// (tcgen05.mma, accumulators in TMEM, operands streamed into shared memory by bulk async copies).
+//
+// The network is a 3x3 conv ResNet on a 7x6 board (python/src/build_graph.py:54-90); each tower
+// convolution is the only dense contraction on the self-play path: an implicit GEMM with
+// M = positions, N = 256 output channels, K = 9 taps x 256 input channels.
+//
+// Layout that makes the implicit GEMM a set of PLAIN shifted views (no im2col, no gather):
+//   * every board is stored as 8 x 7 = 56 "padded rows": cell (y, x) -> row y*7 + x, column x = 6
+//     and row-group y = 7 are zeros.  The one zero column is at the same time the right border of
+//     board row y and the left border of row y+1, the zero row-group is the bottom border of the
+//     board and the top border of the next one, so tap (ky, kx) of output row r reads input row
+//     r + (ky-1)*7 + (kx-1) with no masking at all (42 of 56 rows carry data).
+//   * activations are bf16, stored [channel chunk of 8][row][8 channels] (16-byte row cells), i.e.
+//     the canonical K-major SWIZZLE_NONE UMMA operand layout with an 8-row core-matrix stride of
+//     128 B: a row shift is just a different 16-byte-aligned start address in the smem descriptor.
+//   * weights are pre-packed per (layer, tap, 32-channel K block) as [chunk][256 out channels][8]
+//     = 16 KB contiguous, exactly one pipeline stage, fetched with one cp.async.bulk.
+//
+// One CTA = 256 padded rows (two 128-row UMMA tiles sharing every weight stage, 2 x 256 TMEM
+// columns).  Warp 0 streams operands (one elected lane), warp 1 issues tcgen05.mma (one elected
+// lane) and owns the TMEM allocation, warps 2-5 run the epilogue: tcgen05.ld -> folded BatchNorm
+// -> (+ skip) -> ReLU -> zero the padding rows -> bf16 -> 16-byte coalesced stores.
+#include <cstring>
+#include <vector>
+#include <cuda_bf16.h>
+
 #include "az_common.cuh"
+#include "az_game.cuh"
 #include "az_nn.cuh"
 
-int az_nn_tc_prepare(az_nn*) { return AZ_OK; }
-void az_nn_tc_release(az_nn*) {}
-int az_nn_tc_forward(az_nn*, const float*, const uint32_t*, int, float*, float*, cudaStream_t)
+#define TC_ROWS_PER_BOARD 56
+#define TC_TILE_ROWS 256
+#define TC_HALO 8
+#define TC_A_ROWS (TC_TILE_ROWS + 2 * TC_HALO)              // 272
+#define TC_CHUNKS 32                                         // 256 channels / 8
+#define TC_A_BYTES (TC_CHUNKS * TC_A_ROWS * 16)              // 139264
+#define TC_STAGE_BYTES (4 * 256 * 16)                        // 16384: 32 input channels x 256 output channels
+#define TC_STAGES 4
+#define TC_ITERS 72                                          // 9 taps x 8 K blocks
+#define TC_LAYER_BYTES (TC_ITERS * TC_STAGE_BYTES)           // 1179648
+#define TC_THREADS 192
+#define TC_SMEM_BYTES (TC_A_BYTES + TC_STAGES * TC_STAGE_BYTES + 2 * 256 * 4 + 16 * 8 + 16)
+
+struct AzTcState {
+    int cap_boards = 0, n_tiles = 0, r_alloc = 0;
+    __nv_bfloat16* d_act[3] = { nullptr, nullptr, nullptr };   // [32][r_alloc][8]
+    uint8_t* d_wpacked = nullptr;                              // [2*blocks][72][16 KB]
+    float* d_scale = nullptr; float* d_shift = nullptr;        // [2*blocks][256]
+    float* d_x = nullptr;                                      // fp32 encode of the leaf states
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
-    az_set_error("bf16 tensor-core path not built yet");
-    return AZ_ERR_NOT_READY;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address [0,14) >> 4, leading-dimension byte offset [16,30) >> 4 (distance between the two
+// 8-element K chunks of one K=16 MMA), stride byte offset [32,46) >> 4 (distance between 8-row core
+// matrices), descriptor version [46,48) = 1 on Blackwell, layout type [61,64) = 0.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 [4,6) = 1, A = B = bf16 [7,10) = [10,13) = 1,
+// both K-major (bits 15,16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
+#define TC_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24))
+
+__device__ __forceinline__ bool tc_row_valid(int r, int n_boards)
+{
+    int b = r / TC_ROWS_PER_BOARD, p = r - b * TC_ROWS_PER_BOARD;
+    return b < n_boards && p < 49 && (p % 7) != 6;
+}
+
+// ---------------------------------------------------------------- tower convolution
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ wpacked, const float* __restrict__ scale,
+             const float* __restrict__ shift, const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
+             int n_boards, int r_alloc)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TC_A_BYTES;
+    float* s_scale = reinterpret_cast<float*>(sB + TC_STAGES * TC_STAGE_BYTES);
+    float* s_shift = s_scale + 256;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+    uint64_t* bar_a = bars;                 // A tile landed
+    uint64_t* bar_full = bars + 1;          // [TC_STAGES] weight stage landed
+    uint64_t* bar_empty = bars + 1 + TC_STAGES;   // [TC_STAGES] weight stage consumed
+    uint64_t* bar_acc = bars + 1 + 2 * TC_STAGES; // accumulators complete
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+
+    for (int i = threadIdx.x; i < 256; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 1);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- operand streamer
+            mbar_expect_tx(bar_a, TC_A_BYTES);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(in);
+            for (int c = 0; c < TC_CHUNKS; ++c)
+                bulk_g2s(sA + (size_t)c * TC_A_ROWS * 16, src + ((size_t)c * r_alloc + (size_t)tile * TC_TILE_ROWS) * 16, TC_A_ROWS * 16, bar_a);
+            for (int it = 0; it < TC_ITERS; ++it) {
+                int s = it % TC_STAGES, k = it / TC_STAGES;
+                if (k > 0) mbar_wait(bar_empty + s, (uint32_t)((k - 1) & 1));
+                mbar_expect_tx(bar_full + s, TC_STAGE_BYTES);
+                bulk_g2s(sB + (size_t)s * TC_STAGE_BYTES, wpacked + (size_t)it * TC_STAGE_BYTES, TC_STAGE_BYTES, bar_full + s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer
+            mbar_wait(bar_a, 0);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            for (int it = 0; it < TC_ITERS; ++it) {
+                int s = it % TC_STAGES, k = it / TC_STAGES;
+                mbar_wait(bar_full + s, (uint32_t)(k & 1));
+                tc_fence_after();
+                int tap = it >> 3, kb = it & 7;
+                int sh = (tap / 3 - 1) * 7 + (tap % 3 - 1);
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    uint64_t bdesc = umma_desc(b_base + (uint32_t)(s * TC_STAGE_BYTES + kk * 2 * 256 * 16), 256 * 16, 128);
+                    int chunk0 = kb * 4 + kk * 2;
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        uint64_t adesc = umma_desc(a_base + (uint32_t)((chunk0 * TC_A_ROWS + TC_HALO + t * 128 + sh) * 16), TC_A_ROWS * 16, 128);
+                        tc_mma_bf16(tmem_base + (uint32_t)(t * 256), adesc, bdesc, TC_IDESC, (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(bar_empty + s);        // frees the weight stage when these MMAs retire
+            }
+            tc_commit(bar_acc);
+        }
+    } else {
+        // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31
+        const int q = warp & 3;
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+            const int r = tile * TC_TILE_ROWS + t * 128 + q * 32 + lane;       // padded row of this thread
+            const bool valid = tc_row_valid(r, n_boards);
+#pragma unroll 2
+            for (int c = 0; c < TC_CHUNKS; ++c) {
+                uint32_t v[8];
+                tc_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + c * 8), v);
+                tc_ld_wait();
+                const size_t cell = ((size_t)c * r_alloc + TC_HALO + r) * 8;       // element index of this 16-byte cell
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[e]), s_scale[c * 8 + e], s_shift[c * 8 + e]);
+                if (skip) {
+                    uint4 sk = *reinterpret_cast<const uint4*>(skip + cell);
+                    const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sk);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(s2[e]); f[2 * e] += x.x; f[2 * e + 1] += x.y; }
+                }
+                uint4 o;
+                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float a = valid ? fmaxf(f[2 * e], 0.0f) : 0.0f, b = valid ? fmaxf(f[2 * e + 1], 0.0f) : 0.0f;
+                    o2[e] = __floats2bfloat162_rn(a, b);
+                }
+                *reinterpret_cast<uint4*>(out + cell) = o;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- stem + heads on the padded bf16 layout
+__constant__ int8_t c_nb_tc[42 * 9];
+
+// conv3x3 13->256 + row-indexed BN + ReLU (fp32 math), output in the tower's layout.  Block = board.
+__global__ void __launch_bounds__(256) k_nn_stem_tc(const float* __restrict__ x, int n, const float* __restrict__ w, const float* __restrict__ bn,
+                                                     __nv_bfloat16* __restrict__ out, int r_alloc)
+{
+    __shared__ float s_in[43 * AZ_NN_IN_CH];
+    __shared__ __align__(16) __nv_bfloat16 s_out[42][256];
+    const int b = blockIdx.x, co = threadIdx.x;
+    for (int i = threadIdx.x; i < 42 * AZ_NN_IN_CH; i += 256) s_in[i] = x[(size_t)b * 42 * AZ_NN_IN_CH + i];
+    if (threadIdx.x < AZ_NN_IN_CH) s_in[42 * AZ_NN_IN_CH + threadIdx.x] = 0.0f;
+    __syncthreads();
+    float wr[9 * AZ_NN_IN_CH];
+#pragma unroll
+    for (int i = 0; i < 9 * AZ_NN_IN_CH; ++i) wr[i] = w[i * AZ_NN_CH + co];
+    for (int p = 0; p < 42; ++p) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            int qn = c_nb_tc[p * 9 + t]; qn = qn < 0 ? 42 : qn;
+#pragma unroll
+            for (int ci = 0; ci < AZ_NN_IN_CH; ++ci) acc = fmaf(s_in[qn * AZ_NN_IN_CH + ci], wr[t * AZ_NN_IN_CH + ci], acc);
+        }
+        int y = p / 6;
+        float sc = bn[y] * rsqrtf(bn[21 + y] + AZ_NN_BN_EPS);
+        float v = (acc - bn[14 + y]) * sc + bn[7 + y];
+        s_out[p][co] = __float2bfloat16_rn(fmaxf(v, 0.0f));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 42 * TC_CHUNKS; i += 256) {
+        int p = i / TC_CHUNKS, c = i - p * TC_CHUNKS;
+        int row = b * TC_ROWS_PER_BOARD + (p / 6) * 7 + (p % 6);
+        *reinterpret_cast<uint4*>(out + ((size_t)c * r_alloc + TC_HALO + row) * 8) = *reinterpret_cast<const uint4*>(&s_out[p][c * 8]);
+    }
+}
+
+__device__ __forceinline__ float warp_sum_tc(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __restrict__ act, int n, int r_alloc, AzHeadParams hp,
+                                                      float* __restrict__ policy, float* __restrict__ value)
+{
+    __shared__ float s_pi[84], s_v[42], s_h[256], s_logit[43], s_red[8];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = warp; p < 42; p += 8) {
+        int row = b * TC_ROWS_PER_BOARD + (p / 6) * 7 + (p % 6);
+        uint4 cell = *reinterpret_cast<const uint4*>(act + ((size_t)lane * r_alloc + TC_HALO + row) * 8);   // lane = channel chunk
+        const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cell);
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float2 xv = __bfloat1622float2(c2[e]);
+            int c = lane * 8 + 2 * e;
+            s0 = fmaf(xv.x, hp.pi_w[c * 2 + 0], s0); s1 = fmaf(xv.x, hp.pi_w[c * 2 + 1], s1); s2 = fmaf(xv.x, hp.v_w[c], s2);
+            s0 = fmaf(xv.y, hp.pi_w[(c + 1) * 2 + 0], s0); s1 = fmaf(xv.y, hp.pi_w[(c + 1) * 2 + 1], s1); s2 = fmaf(xv.y, hp.v_w[c + 1], s2);
+        }
+        s0 = warp_sum_tc(s0); s1 = warp_sum_tc(s1); s2 = warp_sum_tc(s2);
+        if (lane == 0) {
+            float y0 = (s0 - hp.bn_pi[4]) * (hp.bn_pi[0] * rsqrtf(hp.bn_pi[6] + AZ_NN_BN_EPS)) + hp.bn_pi[2];
+            float y1 = (s1 - hp.bn_pi[5]) * (hp.bn_pi[1] * rsqrtf(hp.bn_pi[7] + AZ_NN_BN_EPS)) + hp.bn_pi[3];
+            float yv = (s2 - hp.bn_v[2]) * (hp.bn_v[0] * rsqrtf(hp.bn_v[3] + AZ_NN_BN_EPS)) + hp.bn_v[1];
+            s_pi[p * 2 + 0] = fmaxf(y0, 0.0f); s_pi[p * 2 + 1] = fmaxf(y1, 0.0f); s_v[p] = fmaxf(yv, 0.0f);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 43) {
+        float s = hp.dense_b[threadIdx.x];
+        for (int k = 0; k < 84; ++k) s = fmaf(s_pi[k], hp.dense_w[k * 43 + threadIdx.x], s);
+        s_logit[threadIdx.x] = s;
+    }
+    {
+        float s = hp.dense1_b[threadIdx.x];
+        for (int k = 0; k < 42; ++k) s = fmaf(s_v[k], hp.dense1_w[k * 256 + threadIdx.x], s);
+        s_h[threadIdx.x] = fmaxf(s, 0.0f);
+    }
+    __syncthreads();
+    float part = warp_sum_tc(s_h[threadIdx.x] * hp.dense2_w[threadIdx.x]);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = hp.dense2_b[0];
+        for (int i = 0; i < 8; ++i) s += s_red[i];
+        value[b] = tanhf(s);
+    }
+    if (warp == 0) {
+        float l0 = s_logit[lane], l1 = lane < 11 ? s_logit[32 + lane] : -INFINITY;
+        float mx = fmaxf(l0, l1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float e0 = expf(l0 - mx), e1 = lane < 11 ? expf(l1 - mx) : 0.0f;
+        float sum = warp_sum_tc(e0 + e1);
+        policy[(size_t)b * 43 + lane] = e0 / sum;
+        if (lane < 11) policy[(size_t)b * 43 + 32 + lane] = e1 / sum;
+    }
+}
+
+// ---------------------------------------------------------------- host side
+int az_launch_encode(const uint32_t* d_state, int n, float* d_x, cudaStream_t s);   // az_env.cu
+
+static std::string tc_block_name(int i) { return std::to_string(i) + std::string(1, (char)('a' + i)); }
+
+int az_nn_tc_prepare(az_nn* nn)
+{
+    if (!nn->tc) nn->tc = new AzTcState();
+    AzTcState* tc = nn->tc;
+    const int layers = 2 * nn->blocks;
+    std::vector<uint8_t> packed((size_t)layers * TC_LAYER_BYTES);
+    std::vector<float> scale((size_t)layers * 256), shift((size_t)layers * 256);
+    for (int L = 0; L < layers; ++L) {
+        std::string sfx = tc_block_name(L / 2) + ((L & 1) ? "_branch2b" : "_branch2a");
+        const float* w = az_nn_host_var(nn, "res" + sfx + "/kernel");           // HWIO [3][3][256][256]
+        const float* g = az_nn_host_var(nn, "bn" + sfx + "/gamma");
+        const float* be = az_nn_host_var(nn, "bn" + sfx + "/beta");
+        const float* mu = az_nn_host_var(nn, "bn" + sfx + "/moving_mean");
+        const float* var = az_nn_host_var(nn, "bn" + sfx + "/moving_variance");
+        if (!w || !g || !be || !mu || !var) { az_set_error("missing tower variable for layer %d", L); return AZ_ERR_INVALID_ARG; }
+        for (int c = 0; c < 256; ++c) {
+            float sc = g[c] / sqrtf(var[c] + AZ_NN_BN_EPS);
+            scale[(size_t)L * 256 + c] = sc; shift[(size_t)L * 256 + c] = be[c] - mu[c] * sc;
+        }
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(packed.data() + (size_t)L * TC_LAYER_BYTES);
+        for (int tap = 0; tap < 9; ++tap)
+            for (int kb = 0; kb < 8; ++kb)
+                for (int ch = 0; ch < 4; ++ch)
+                    for (int n = 0; n < 256; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            int ci = kb * 32 + ch * 8 + e;
+                            dst[((((size_t)tap * 8 + kb) * 4 + ch) * 256 + n) * 8 + e] = __float2bfloat16_rn(w[((size_t)tap * 256 + ci) * 256 + n]);
+                        }
+    }
+    if (!tc->d_wpacked) {
+        AZ_CUDA(cudaMalloc(&tc->d_wpacked, packed.size()));
+        AZ_CUDA(cudaMalloc(&tc->d_scale, scale.size() * sizeof(float)));
+        AZ_CUDA(cudaMalloc(&tc->d_shift, shift.size() * sizeof(float)));
+        int8_t nb[42 * 9];
+        for (int p = 0; p < 42; ++p)
+            for (int t = 0; t < 9; ++t) {
+                int y = p / 6 + t / 3 - 1, x = p % 6 + t % 3 - 1;
+                nb[p * 9 + t] = (y < 0 || y >= 7 || x < 0 || x >= 6) ? (int8_t)-1 : (int8_t)(y * 6 + x);
+            }
+        AZ_CUDA(cudaMemcpyToSymbol(c_nb_tc, nb, sizeof nb));
+        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    }
+    AZ_CUDA(cudaMemcpy(tc->d_wpacked, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+    AZ_CUDA(cudaMemcpy(tc->d_scale, scale.data(), scale.size() * sizeof(float), cudaMemcpyHostToDevice));
+    AZ_CUDA(cudaMemcpy(tc->d_shift, shift.data(), shift.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return AZ_OK;
+}
+
+void az_nn_tc_release(az_nn* nn)
+{
+    if (!nn->tc) return;
+    AzTcState* tc = nn->tc;
+    for (int i = 0; i < 3; ++i) cudaFree(tc->d_act[i]);
+    cudaFree(tc->d_wpacked); cudaFree(tc->d_scale); cudaFree(tc->d_shift); cudaFree(tc->d_x);
+    delete tc;
+    nn->tc = nullptr;
+}
+
+static int tc_reserve(AzTcState* tc, int n)
+{
+    if (n <= tc->cap_boards) return AZ_OK;
+    for (int i = 0; i < 3; ++i) { cudaFree(tc->d_act[i]); tc->d_act[i] = nullptr; }
+    cudaFree(tc->d_x); tc->d_x = nullptr;
+    int tiles = (n * TC_ROWS_PER_BOARD + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    int r_alloc = tiles * TC_TILE_ROWS + 2 * TC_HALO;
+    size_t bytes = (size_t)TC_CHUNKS * r_alloc * 16;
+    for (int i = 0; i < 3; ++i) {
+        AZ_CUDA(cudaMalloc(&tc->d_act[i], bytes));
+        AZ_CUDA(cudaMemset(tc->d_act[i], 0, bytes));          // padding rows and halos must read as zero
+    }
+    AZ_CUDA(cudaMalloc(&tc->d_x, sizeof(float) * (size_t)n * AZ_INPUT_FLOATS));
+    tc->cap_boards = n; tc->n_tiles = tiles; tc->r_alloc = r_alloc;
+    return AZ_OK;
+}
+
+int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, int n, float* d_policy, float* d_value, cudaStream_t s)
+{
+    AzTcState* tc = nn->tc;
+    if (!tc || !tc->d_wpacked) { az_set_error("network not finalized"); return AZ_ERR_NOT_READY; }
+    int rc = tc_reserve(tc, n); if (rc) return rc;
+    if (!d_x) {
+        rc = az_launch_encode(d_env_state, n, tc->d_x, s); if (rc) return rc;
+        d_x = tc->d_x;
+    }
+    // the buffers were sized for cap_boards; tiles beyond the boards of this call only produce zeros
+    const int tiles = (n * TC_ROWS_PER_BOARD + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    int cur = 0, tmp = 1, nxt = 2;
+    k_nn_stem_tc<<<n, 256, 0, s>>>(d_x, n, az_nn_dev_var(nn, "conv/kernel"), az_nn_dev_var(nn, "conv_bn/gamma"), tc->d_act[cur], tc->r_alloc);
+    AZ_CUDA(cudaGetLastError());
+    for (int i = 0; i < nn->blocks; ++i) {
+        const int L0 = 2 * i, L1 = 2 * i + 1;
+        k_nn_conv_tc<<<tiles, TC_THREADS, TC_SMEM_BYTES, s>>>(tc->d_act[cur], tc->d_wpacked + (size_t)L0 * TC_LAYER_BYTES, tc->d_scale + L0 * 256,
+                                                              tc->d_shift + L0 * 256, nullptr, tc->d_act[tmp], n, tc->r_alloc);
+        AZ_CUDA(cudaGetLastError());
+        k_nn_conv_tc<<<tiles, TC_THREADS, TC_SMEM_BYTES, s>>>(tc->d_act[tmp], tc->d_wpacked + (size_t)L1 * TC_LAYER_BYTES, tc->d_scale + L1 * 256,
+                                                              tc->d_shift + L1 * 256, tc->d_act[cur], tc->d_act[nxt], n, tc->r_alloc);
+        AZ_CUDA(cudaGetLastError());
+        int o = cur; cur = nxt; nxt = o;
+    }
+    k_nn_heads_tc<<<n, 256, 0, s>>>(tc->d_act[cur], n, tc->r_alloc, az_nn_head_params(nn), d_policy, d_value);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
 }

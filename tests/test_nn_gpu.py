@@ -91,3 +91,33 @@ def test_random_init_is_the_graph_init(api):
     a, b = net.forward(x), net2.forward(x)
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
     net.close(); net2.close()
+
+
+BF16_POLICY_TOL = 2e-3   # stated bf16 tolerance: |softmax prob| difference vs the fp32 path
+BF16_VALUE_TOL = 1e-2    # |tanh value| difference vs the fp32 path
+
+
+@pytest.mark.parametrize("blocks,n", [(1, 5), (5, 3), (5, 600), (3, 147)])
+def test_bf16_tcgen05_forward_close_to_fp32(api, blocks, n):
+    """the tensor-core tower (bf16 operands, fp32 TMEM accumulation, fp32 BN/heads) against the fp32
+    validation path on the same weights; also exercises tiles that end inside / beyond the batch"""
+    net = api.Net(blocks=blocks, seed=99)
+    rng = np.random.default_rng(3)
+    for name, shape in net.variables():
+        if name.endswith("/gamma"):
+            net.load(name, rng.uniform(0.8, 1.2, shape))
+        elif name.endswith("/beta") or name.endswith("/moving_mean") or name.endswith("/bias"):
+            net.load(name, rng.uniform(-0.1, 0.1, shape))
+        elif name.endswith("/moving_variance"):
+            net.load(name, rng.uniform(0.7, 1.3, shape))
+    x = game_inputs(n)
+    p32, v32 = net.forward(x, api.FP32)
+    p16, v16 = net.forward(x, api.BF16)
+    assert np.isfinite(p16).all() and np.isfinite(v16).all()
+    assert np.abs(p16.sum(1) - 1).max() < 1e-5
+    assert np.abs(p32 - p16).max() <= BF16_POLICY_TOL, np.abs(p32 - p16).max()
+    assert np.abs(v32 - v16).max() <= BF16_VALUE_TOL, np.abs(v32 - v16).max()
+    # a smaller batch after a larger one reuses the (now dirty) activation buffers
+    p16b, v16b = net.forward(x[:2], api.BF16)
+    assert (p16b == p16[:2]).all() and (v16b == v16[:2]).all()
+    net.close()
