@@ -119,6 +119,26 @@ def cpu_env_baseline(seconds_target):
                 sample="1 thread x %d random-play env steps through oracle/risk_oracle.c, %.1f s" % (n, out.seconds)), out
 
 
+def cpu_selfplay_baseline(sims, seconds_target):
+    """reference MCTS + env on all host threads with a NULL evaluator (uniform prior, value 0): tree + env cost only.
+    TensorFlow is not installable, so the network is left out of this baseline and that is stated."""
+    import ctypes as C
+    from oracle import pyoracle as po
+    threads = host_threads()
+    if not po.ref_available():
+        return {"value": None, "unit": "sims/s", "cores": 0, "kind": "port", "sample": "oracle/_ref not built"}
+    L = po.ref_lib()
+    po.ref_apply_rules(po.default_rules(mcts_simulations=sims, threads_per_mcts=1))
+    out = po.BenchOut()
+    L.ref_bench_selfplay(threads, 20, 1, None, None, C.byref(out))
+    per_thread = int(max(20, out.moves / max(out.seconds, 1e-9) / threads * seconds_target))
+    L.ref_bench_selfplay(threads, per_thread, 2, None, None, C.byref(out))
+    po.ref_apply_rules(po.default_rules())
+    return dict(value=out.sims / out.seconds, unit="sims/s", cores=threads, kind="reference",
+                sample="%d threads x %d self-play moves x %d sims through the compiled reference (AlphaZeroMCTS::simulate, T=1, "
+                       "null evaluator: no network cost), %.1f s" % (threads, per_thread, sims, out.seconds))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -139,6 +159,81 @@ def run_reference(args):
                 cpu_baseline=cb, e2e={"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 wall_s=time.time() - t0)
     print(json.dumps(line))
+
+
+def nn_flops_per_position(blocks):
+    """SURVEY.md §8d conventional count (padded taps included): 0.4981 GFLOP (5 blocks), 1.9844 GFLOP (20 blocks)"""
+    return 2 * 42 * (9 * 13 * 256 + 2 * blocks * 9 * 256 * 256 + 256 * 2 + 256 * 1) + 2 * (84 * 43 + 42 * 256 + 256)
+
+
+def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
+    """BASELINE configs[2]: batched self-play, 4096 games x 64 MCTS sims/move per GPU, leaf-batched bf16
+    tcgen05 network forward (5-block graph = the only GraphDef the reference ships, random-init weights)."""
+    import numpy as np
+    n, sims, blocks = args.sp_games, args.sp_sims, args.blocks
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    rules = api.default_rules(mcts_simulations=sims, threads_per_mcts=1)
+    env = api.Env(n, rules=rules, device=local, first_game_id=rank * n)
+    env.reset(SEED, stream=sptr)
+    net = api.Net(blocks=blocks, device=local)
+    if rank == 0:
+        net.init_random(1234)
+    if dist is not None:      # weight broadcast (replaces the checkpoint-file hand-off of alphazero_gpu_cluster.cpp:221-231)
+        blob = torch.from_numpy(net.export_blob() if rank == 0 else np.zeros(net.num_params(), np.float32)).cuda()
+        dist.broadcast(blob, src=0)
+        net.import_blob(blob.cpu().numpy())
+    net.finalize()
+    mc = api.Mcts(env, net=net, evaluator=api.EVAL_NN, precision=api.BF16)
+    moves_per_step = args.sp_moves
+    for _ in range(max(1, args.warmup // 2)):
+        mc.selfplay(moves_per_step, stream=sptr)
+    torch.cuda.synchronize()
+    mc.counters(reset=True, stream=sptr)
+    steps = max(2, min(args.steps, args.sp_steps))
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for i in range(steps):
+        ev[i][0].record(stream)
+        mc.selfplay(moves_per_step, stream=sptr)      # working set (node pools + activations) is far larger than L2
+        ev[i][1].record(stream)
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    cnt = mc.counters(stream=sptr)
+    # e2e: one az_mcts_search call per move through the host-buffer ABI (visit counts, pi, moves, status copied back)
+    e2e_moves = max(2, moves_per_step)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_moves):
+        mc.search(pick_mode=api.PICK_SELFPLAY, apply_move=True, stream=sptr)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    c = torch.tensor([cnt["sims"], cnt["evals"], cnt["steps"], cnt["games"], cnt["errors"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)          # stats gather (replaces GameResults::add, game.cpp:298-309)
+    dev_ms, e2e_ms = [float(v) for v in t.tolist()]
+    tot_sims, tot_evals, tot_steps, tot_games, errors = [float(v) for v in c.tolist()]
+    mc.close(); net.close(); env.close()
+    if rank != 0:
+        return None
+    _, tf_peak, src = measured_peaks()
+    nn_launch_positions = n * (sims + 1) * moves_per_step * steps          # positions pushed through the tower per rank
+    achieved_tf = nn_launch_positions * nn_flops_per_position(blocks) / (dev_ms * 1e-3) / 1e12
+    return dict(metric="mcts_sims_per_sec", value=tot_sims / (dev_ms * 1e-3), unit="sims/s", ms_per_step=dev_ms / steps, steps=steps,
+                nn_evals_per_sec=tot_evals / (dev_ms * 1e-3), selfplay_env_steps_per_sec=tot_steps / (dev_ms * 1e-3),
+                config={"workload": "configs[2]: batched self-play, %d games x %d MCTS sims/move per GPU, T=1 semantics (one leaf per game "
+                                    "per batch), %d-block graph, random-init weights (seed 1234), bf16 tcgen05 forward, %d moves per step"
+                                    % (n, sims, blocks, moves_per_step), "games_per_gpu": n, "sims_per_move": sims, "blocks": blocks},
+                roofline={"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
+                          "traffic": None, "peak_source": src + " (sustained cuBLAS bf16)",
+                          "note": "conventional FLOPs/position (0.4981 G for 5 blocks) x positions pushed through the tower / whole-step device "
+                                  "time (tree kernels, encode and heads included in the time)"},
+                e2e={"value": n * sims * e2e_moves * world / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": 0,
+                     "d2h_bytes_per_step": n * (43 * 8 + 2), "steps": e2e_moves},
+                gpu_launches=steps * moves_per_step * (2 + (sims + 1) * (2 + 1 + 2 * blocks + 1 + 1)),
+                dtype="bf16 tower / fp32 tree", results={"games_finished": tot_games, "table_errors": errors})
 
 
 def run_ours(args):
@@ -215,6 +310,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, wall_ms = [float(v) for v in t.tolist()]
 
+    mcts_line = None
+    if not args.no_selfplay:
+        mcts_line = run_selfplay(args, api, torch, dist, rank, world, local, barrier)
+
     if rank == 0:
         hbm_peak, _, src = measured_peaks()
         total_steps = n * S * args.steps * world
@@ -235,9 +334,14 @@ def run_ours(args):
                          "d2h_bytes_per_step": n * 160 + 64, "steps": e2e_steps},
                     gpu_launches=args.steps, wall_ms_timed_region=wall_ms, clocks=clocks,
                     results={"games_finished": cnt["games"], "wins": cnt["wins"], "draws": cnt["draws"]})
+        if mcts_line is not None:
+            line["mcts"] = mcts_line
+            line["gpu_launches"] += mcts_line["gpu_launches"]
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_env_baseline(12.0)
             line["cpu_baseline"] = cb
+            if mcts_line is not None:
+                mcts_line["cpu_baseline"] = cpu_selfplay_baseline(args.sp_sims, 10.0)
         print(json.dumps(line))
     env.close()
     if dist is not None:
@@ -253,6 +357,12 @@ def main():
     ap.add_argument("--games", type=int, default=65536)
     ap.add_argument("--lockstep", type=int, default=512, help="lockstep moves per launch (one bench step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-selfplay", action="store_true", help="skip the configs[2] self-play measurement")
+    ap.add_argument("--sp-games", type=int, default=4096)
+    ap.add_argument("--sp-sims", type=int, default=64)
+    ap.add_argument("--sp-moves", type=int, default=2, help="self-play moves per timed step")
+    ap.add_argument("--sp-steps", type=int, default=4, help="max timed self-play steps")
+    ap.add_argument("--blocks", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
