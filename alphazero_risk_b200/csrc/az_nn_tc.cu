@@ -17,10 +17,13 @@
 //   * weights are pre-packed per (layer, tap, 32-channel K block) as [chunk][256 out channels][8]
 //     = 16 KB contiguous, exactly one pipeline stage, fetched with one cp.async.bulk.
 //
-// One CTA = 256 padded rows (two 128-row UMMA tiles sharing every weight stage, 2 x 256 TMEM
-// columns).  Warp 0 streams operands (one elected lane), warp 1 issues tcgen05.mma (one elected
-// lane) and owns the TMEM allocation, warps 2-5 run the epilogue: tcgen05.ld -> folded BatchNorm
-// -> (+ skip) -> ReLU -> zero the padding rows -> bf16 -> 16-byte coalesced stores.
+// Persistent kernel, one CTA per SM, output tile = 128 padded rows x 256 channels.  Warp 0 streams
+// operands (one elected lane: the next tile's A operand is prefetched into the second A buffer while
+// the current tile is multiplied), warp 1 issues tcgen05.mma (one elected lane) into one of two
+// 256-column TMEM accumulators and owns the TMEM allocation, warps 2-5 run the epilogue of the
+// PREVIOUS tile concurrently: tcgen05.ld -> folded BatchNorm -> (+ skip) -> ReLU -> zero the padding
+// rows -> bf16 -> 16-byte coalesced stores.  The stem (13 -> 256 channels, BatchNorm indexed by board
+// row) is the same kernel instantiated with 2 input chunks (13 channels padded to 16).
 #include <cstring>
 #include <vector>
 #include <cuda_bf16.h>
@@ -30,23 +33,32 @@
 #include "az_nn.cuh"
 
 #define TC_ROWS_PER_BOARD 56
-#define TC_TILE_ROWS 256
+#define TC_TILE_ROWS 128
 #define TC_HALO 8
-#define TC_A_ROWS (TC_TILE_ROWS + 2 * TC_HALO)              // 272
+#define TC_A_ROWS (TC_TILE_ROWS + 2 * TC_HALO)              // 144
 #define TC_CHUNKS 32                                         // 256 channels / 8
-#define TC_A_BYTES (TC_CHUNKS * TC_A_ROWS * 16)              // 139264
-#define TC_STAGE_BYTES (4 * 256 * 16)                        // 16384: 32 input channels x 256 output channels
 #define TC_STAGES 4
-#define TC_ITERS 72                                          // 9 taps x 8 K blocks
-#define TC_LAYER_BYTES (TC_ITERS * TC_STAGE_BYTES)           // 1179648
 #define TC_THREADS 192
-#define TC_SMEM_BYTES (TC_A_BYTES + TC_STAGES * TC_STAGE_BYTES + 2 * 256 * 4 + 16 * 8 + 16)
+#define TC_LAYER_BYTES (9 * 256 * 256 * 2)                   // 1179648 packed bf16 weights of one tower conv
+#define TC_STEM_BYTES (9 * 16 * 256 * 2)                     // 73728: stem weights, 13 input channels padded to 16
+
+// compile-time shape of one conv flavour: KCH = input channel chunks (32 for the tower, 2 for the stem)
+template <int KCH> struct TcShape {
+    static constexpr int CH_PER_STAGE = KCH >= 4 ? 4 : 2;            // chunks per weight stage
+    static constexpr int KSTEPS = CH_PER_STAGE / 2;                   // K=16 MMAs per stage
+    static constexpr int KBLOCKS = KCH / CH_PER_STAGE;
+    static constexpr int ITERS = 9 * KBLOCKS;                         // weight stages per output tile
+    static constexpr int STAGE_BYTES = CH_PER_STAGE * 256 * 16;
+    static constexpr int A_BYTES = KCH * TC_A_ROWS * 16;              // one A buffer
+    static constexpr int SMEM_BYTES = 2 * A_BYTES + TC_STAGES * STAGE_BYTES + 2 * 256 * 4 + 32 * 8 + 16;
+};
 
 struct AzTcState {
-    int cap_boards = 0, n_tiles = 0, r_alloc = 0;
+    int cap_boards = 0, n_tiles = 0, r_alloc = 0, n_sm = 148;
     __nv_bfloat16* d_act[3] = { nullptr, nullptr, nullptr };   // [32][r_alloc][8]
-    uint8_t* d_wpacked = nullptr;                              // [2*blocks][72][16 KB]
-    float* d_scale = nullptr; float* d_shift = nullptr;        // [2*blocks][256]
+    __nv_bfloat16* d_in = nullptr;                             // [2][r_alloc][8]: encoded input, 13 channels padded to 16
+    uint8_t* d_wpacked = nullptr;                              // [2*blocks] x 1.18 MB tower weights, then the 72 KB stem weights
+    float* d_scale = nullptr; float* d_shift = nullptr;        // [2*blocks][256] folded BN, then [256] (7 used) for the stem's row BN
     float* d_x = nullptr;                                      // fp32 encode of the leaf states
 };
 
@@ -77,6 +89,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -119,32 +135,34 @@ __device__ __forceinline__ bool tc_row_valid(int r, int n_boards)
     return b < n_boards && p < 49 && (p % 7) != 6;
 }
 
-// ---------------------------------------------------------------- tower convolution
+// ---------------------------------------------------------------- conv3x3 on tensor cores (tower and stem)
+template <int KCH, bool ROW_BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ wpacked, const float* __restrict__ scale,
              const float* __restrict__ shift, const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
-             int n_boards, int r_alloc)
+             int n_boards, int r_alloc, int n_tiles)
 {
+    using S = TcShape<KCH>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + TC_A_BYTES;
-    float* s_scale = reinterpret_cast<float*>(sB + TC_STAGES * TC_STAGE_BYTES);
+    uint8_t* sA = smem;                                   // 2 x A_BYTES
+    uint8_t* sB = smem + 2 * S::A_BYTES;                  // TC_STAGES x STAGE_BYTES
+    float* s_scale = reinterpret_cast<float*>(sB + TC_STAGES * S::STAGE_BYTES);
     float* s_shift = s_scale + 256;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
-    uint64_t* bar_a = bars;                 // A tile landed
-    uint64_t* bar_full = bars + 1;          // [TC_STAGES] weight stage landed
-    uint64_t* bar_empty = bars + 1 + TC_STAGES;   // [TC_STAGES] weight stage consumed
-    uint64_t* bar_acc = bars + 1 + 2 * TC_STAGES; // accumulators complete
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* bar_a_full = bars;                          // [2] A operand of a tile landed
+    uint64_t* bar_a_empty = bars + 2;                     // [2] all MMAs reading that A buffer retired
+    uint64_t* bar_w_full = bars + 4;                      // [TC_STAGES]
+    uint64_t* bar_w_empty = bars + 4 + TC_STAGES;         // [TC_STAGES]
+    uint64_t* bar_acc_full = bars + 4 + 2 * TC_STAGES;    // [2] accumulator complete
+    uint64_t* bar_acc_empty = bars + 6 + 2 * TC_STAGES;   // [2] accumulator drained by the 4 epilogue warps
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
 
     for (int i = threadIdx.x; i < 256; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
     if (threadIdx.x == 0) {
-        mbar_init(bar_a, 1);
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
-        mbar_init(bar_acc, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_a_full + b, 1); mbar_init(bar_a_empty + b, 1); mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, 4); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_w_full + s, 1); mbar_init(bar_w_empty + s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -159,61 +177,82 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
     if (warp == 0) {
         if (lane == 0) {
             // ---- operand streamer
-            mbar_expect_tx(bar_a, TC_A_BYTES);
             const uint8_t* src = reinterpret_cast<const uint8_t*>(in);
-            for (int c = 0; c < TC_CHUNKS; ++c)
-                bulk_g2s(sA + (size_t)c * TC_A_ROWS * 16, src + ((size_t)c * r_alloc + (size_t)tile * TC_TILE_ROWS) * 16, TC_A_ROWS * 16, bar_a);
-            for (int it = 0; it < TC_ITERS; ++it) {
-                int s = it % TC_STAGES, k = it / TC_STAGES;
-                if (k > 0) mbar_wait(bar_empty + s, (uint32_t)((k - 1) & 1));
-                mbar_expect_tx(bar_full + s, TC_STAGE_BYTES);
-                bulk_g2s(sB + (size_t)s * TC_STAGE_BYTES, wpacked + (size_t)it * TC_STAGE_BYTES, TC_STAGE_BYTES, bar_full + s);
+            auto load_a = [&](int j, int tile) {
+                const int b = j & 1;
+                if (j >= 2) mbar_wait(bar_a_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
+                mbar_expect_tx(bar_a_full + b, S::A_BYTES);
+                for (int c = 0; c < KCH; ++c)
+                    bulk_g2s(sA + (size_t)b * S::A_BYTES + (size_t)c * TC_A_ROWS * 16,
+                             src + ((size_t)c * r_alloc + (size_t)tile * TC_TILE_ROWS) * 16, TC_A_ROWS * 16, bar_a_full + b);
+            };
+            uint32_t wit = 0;
+            int j = 0;
+            if ((int)blockIdx.x < n_tiles) load_a(0, blockIdx.x);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+                for (int it = 0; it < S::ITERS; ++it, ++wit) {
+                    const uint32_t s = wit % TC_STAGES, k = wit / TC_STAGES;
+                    if (k > 0) mbar_wait(bar_w_empty + s, (k - 1) & 1u);
+                    mbar_expect_tx(bar_w_full + s, S::STAGE_BYTES);
+                    bulk_g2s(sB + (size_t)s * S::STAGE_BYTES, wpacked + (size_t)it * S::STAGE_BYTES, S::STAGE_BYTES, bar_w_full + s);
+                    // prefetch the next tile's A operand early in this tile (its buffer is released by the previous tile's MMAs)
+                    if (it == (S::ITERS > 8 ? 8 : S::ITERS - 1) && tile + (int)gridDim.x < n_tiles) load_a(j + 1, tile + gridDim.x);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ---- MMA issuer
-            mbar_wait(bar_a, 0);
-            tc_fence_after();
             const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-            for (int it = 0; it < TC_ITERS; ++it) {
-                int s = it % TC_STAGES, k = it / TC_STAGES;
-                mbar_wait(bar_full + s, (uint32_t)(k & 1));
+            uint32_t wit = 0;
+            int j = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+                const int b = j & 1;
+                mbar_wait(bar_a_full + b, (uint32_t)((j >> 1) & 1));
+                if (j >= 2) mbar_wait(bar_acc_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
                 tc_fence_after();
-                int tap = it >> 3, kb = it & 7;
-                int sh = (tap / 3 - 1) * 7 + (tap % 3 - 1);
+                for (int it = 0; it < S::ITERS; ++it, ++wit) {
+                    const uint32_t s = wit % TC_STAGES, k = wit / TC_STAGES;
+                    mbar_wait(bar_w_full + s, k & 1u);
+                    tc_fence_after();
+                    const int tap = it / S::KBLOCKS, kb = it - tap * S::KBLOCKS;
+                    const int sh = (tap / 3 - 1) * 7 + (tap % 3 - 1);
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    uint64_t bdesc = umma_desc(b_base + (uint32_t)(s * TC_STAGE_BYTES + kk * 2 * 256 * 16), 256 * 16, 128);
-                    int chunk0 = kb * 4 + kk * 2;
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        uint64_t adesc = umma_desc(a_base + (uint32_t)((chunk0 * TC_A_ROWS + TC_HALO + t * 128 + sh) * 16), TC_A_ROWS * 16, 128);
-                        tc_mma_bf16(tmem_base + (uint32_t)(t * 256), adesc, bdesc, TC_IDESC, (it > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < S::KSTEPS; ++kk) {
+                        const uint64_t bdesc = umma_desc(b_base + (uint32_t)(s * S::STAGE_BYTES + kk * 2 * 256 * 16), 256 * 16, 128);
+                        const int chunk0 = kb * S::CH_PER_STAGE + kk * 2;
+                        const uint64_t adesc = umma_desc(a_base + (uint32_t)(b * S::A_BYTES + (chunk0 * TC_A_ROWS + TC_HALO + sh) * 16), TC_A_ROWS * 16, 128);
+                        tc_mma_bf16(tmem_base + (uint32_t)(b * 256), adesc, bdesc, TC_IDESC, (it > 0 || kk > 0) ? 1u : 0u);
                     }
+                    tc_commit(bar_w_empty + s);          // frees the weight stage when these MMAs retire
                 }
-                tc_commit(bar_empty + s);        // frees the weight stage when these MMAs retire
+                tc_commit(bar_a_empty + b);
+                tc_commit(bar_acc_full + b);
             }
-            tc_commit(bar_acc);
         }
     } else {
         // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31
         const int q = warp & 3;
-        mbar_wait(bar_acc, 0);
-        tc_fence_after();
-#pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-            const int r = tile * TC_TILE_ROWS + t * 128 + q * 32 + lane;       // padded row of this thread
+        int j = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            const int b = j & 1;
+            mbar_wait(bar_acc_full + b, (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            const int r = tile * TC_TILE_ROWS + q * 32 + lane;                 // padded row of this thread
             const bool valid = tc_row_valid(r, n_boards);
+            const int yrow = (r % TC_ROWS_PER_BOARD) / 7;                      // board row (stem BatchNorm index)
 #pragma unroll 2
             for (int c = 0; c < TC_CHUNKS; ++c) {
                 uint32_t v[8];
-                tc_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + c * 8), v);
+                tc_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c * 8), v);
                 tc_ld_wait();
-                const size_t cell = ((size_t)c * r_alloc + TC_HALO + r) * 8;       // element index of this 16-byte cell
+                const size_t cell = ((size_t)c * r_alloc + TC_HALO + r) * 8;   // element index of this 16-byte cell
                 float f[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[e]), s_scale[c * 8 + e], s_shift[c * 8 + e]);
+                for (int e = 0; e < 8; ++e) {
+                    const int bi = ROW_BN ? (yrow < 7 ? yrow : 0) : c * 8 + e;
+                    f[e] = fmaf(__uint_as_float(v[e]), s_scale[bi], s_shift[bi]);
+                }
                 if (skip) {
                     uint4 sk = *reinterpret_cast<const uint4*>(skip + cell);
                     const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sk);
@@ -224,11 +263,14 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
                 __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    float a = valid ? fmaxf(f[2 * e], 0.0f) : 0.0f, b = valid ? fmaxf(f[2 * e + 1], 0.0f) : 0.0f;
-                    o2[e] = __floats2bfloat162_rn(a, b);
+                    float x0 = valid ? fmaxf(f[2 * e], 0.0f) : 0.0f, x1 = valid ? fmaxf(f[2 * e + 1], 0.0f) : 0.0f;
+                    o2[e] = __floats2bfloat162_rn(x0, x1);
                 }
                 *reinterpret_cast<uint4*>(out + cell) = o;
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty + b);
         }
     }
     tc_fence_before();
@@ -238,40 +280,26 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
     }
 }
 
-// ---------------------------------------------------------------- stem + heads on the padded bf16 layout
-__constant__ int8_t c_nb_tc[42 * 9];
-
-// conv3x3 13->256 + row-indexed BN + ReLU (fp32 math), output in the tower's layout.  Block = board.
-__global__ void __launch_bounds__(256) k_nn_stem_tc(const float* __restrict__ x, int n, const float* __restrict__ w, const float* __restrict__ bn,
-                                                     __nv_bfloat16* __restrict__ out, int r_alloc)
+// ---------------------------------------------------------------- input packing + heads on the padded bf16 layout
+// fp32 [n][42][13] -> bf16 [2 chunks][r_alloc][8] (channels 13..15 = 0); thread = board cell
+__global__ void __launch_bounds__(256) k_nn_pack_input_tc(const float* __restrict__ x, int n, __nv_bfloat16* __restrict__ out, int r_alloc)
 {
-    __shared__ float s_in[43 * AZ_NN_IN_CH];
-    __shared__ __align__(16) __nv_bfloat16 s_out[42][256];
-    const int b = blockIdx.x, co = threadIdx.x;
-    for (int i = threadIdx.x; i < 42 * AZ_NN_IN_CH; i += 256) s_in[i] = x[(size_t)b * 42 * AZ_NN_IN_CH + i];
-    if (threadIdx.x < AZ_NN_IN_CH) s_in[42 * AZ_NN_IN_CH + threadIdx.x] = 0.0f;
-    __syncthreads();
-    float wr[9 * AZ_NN_IN_CH];
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n * 42) return;
+    int b = i / 42, p = i - b * 42;
+    const float* src = x + (size_t)i * AZ_NN_IN_CH;
+    int row = b * TC_ROWS_PER_BOARD + (p / 6) * 7 + (p % 6);
 #pragma unroll
-    for (int i = 0; i < 9 * AZ_NN_IN_CH; ++i) wr[i] = w[i * AZ_NN_CH + co];
-    for (int p = 0; p < 42; ++p) {
-        float acc = 0.0f;
+    for (int c = 0; c < 2; ++c) {
+        uint4 o;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            int qn = c_nb_tc[p * 9 + t]; qn = qn < 0 ? 42 : qn;
-#pragma unroll
-            for (int ci = 0; ci < AZ_NN_IN_CH; ++ci) acc = fmaf(s_in[qn * AZ_NN_IN_CH + ci], wr[t * AZ_NN_IN_CH + ci], acc);
+        for (int e = 0; e < 4; ++e) {
+            int c0 = c * 8 + 2 * e;
+            float a = c0 < AZ_NN_IN_CH ? src[c0] : 0.0f, bb = c0 + 1 < AZ_NN_IN_CH ? src[c0 + 1] : 0.0f;
+            o2[e] = __floats2bfloat162_rn(a, bb);
         }
-        int y = p / 6;
-        float sc = bn[y] * rsqrtf(bn[21 + y] + AZ_NN_BN_EPS);
-        float v = (acc - bn[14 + y]) * sc + bn[7 + y];
-        s_out[p][co] = __float2bfloat16_rn(fmaxf(v, 0.0f));
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 42 * TC_CHUNKS; i += 256) {
-        int p = i / TC_CHUNKS, c = i - p * TC_CHUNKS;
-        int row = b * TC_ROWS_PER_BOARD + (p / 6) * 7 + (p % 6);
-        *reinterpret_cast<uint4*>(out + ((size_t)c * r_alloc + TC_HALO + row) * 8) = *reinterpret_cast<const uint4*>(&s_out[p][c * 8]);
+        *reinterpret_cast<uint4*>(out + ((size_t)c * r_alloc + TC_HALO + row) * 8) = o;
     }
 }
 
@@ -344,13 +372,28 @@ int az_launch_encode(const uint32_t* d_state, int n, float* d_x, cudaStream_t s)
 
 static std::string tc_block_name(int i) { return std::to_string(i) + std::string(1, (char)('a' + i)); }
 
+// HWIO fp32 [3][3][cin][256] -> bf16 [tap][K block][chunk][256 out][8], cin padded to a multiple of 16
+static void pack_conv(const float* w, int cin, int kch, __nv_bfloat16* dst)
+{
+    const int ch_per_stage = kch >= 4 ? 4 : 2, kblocks = kch / ch_per_stage;
+    for (int tap = 0; tap < 9; ++tap)
+        for (int kb = 0; kb < kblocks; ++kb)
+            for (int ch = 0; ch < ch_per_stage; ++ch)
+                for (int n = 0; n < 256; ++n)
+                    for (int e = 0; e < 8; ++e) {
+                        int ci = (kb * ch_per_stage + ch) * 8 + e;
+                        float v = ci < cin ? w[((size_t)tap * cin + ci) * 256 + n] : 0.0f;
+                        dst[((((size_t)tap * kblocks + kb) * ch_per_stage + ch) * 256 + n) * 8 + e] = __float2bfloat16_rn(v);
+                    }
+}
+
 int az_nn_tc_prepare(az_nn* nn)
 {
     if (!nn->tc) nn->tc = new AzTcState();
     AzTcState* tc = nn->tc;
     const int layers = 2 * nn->blocks;
-    std::vector<uint8_t> packed((size_t)layers * TC_LAYER_BYTES);
-    std::vector<float> scale((size_t)layers * 256), shift((size_t)layers * 256);
+    std::vector<uint8_t> packed((size_t)layers * TC_LAYER_BYTES + TC_STEM_BYTES);
+    std::vector<float> scale((size_t)(layers + 1) * 256, 0.0f), shift((size_t)(layers + 1) * 256, 0.0f);
     for (int L = 0; L < layers; ++L) {
         std::string sfx = tc_block_name(L / 2) + ((L & 1) ? "_branch2b" : "_branch2a");
         const float* w = az_nn_host_var(nn, "res" + sfx + "/kernel");           // HWIO [3][3][256][256]
@@ -363,28 +406,31 @@ int az_nn_tc_prepare(az_nn* nn)
             float sc = g[c] / sqrtf(var[c] + AZ_NN_BN_EPS);
             scale[(size_t)L * 256 + c] = sc; shift[(size_t)L * 256 + c] = be[c] - mu[c] * sc;
         }
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(packed.data() + (size_t)L * TC_LAYER_BYTES);
-        for (int tap = 0; tap < 9; ++tap)
-            for (int kb = 0; kb < 8; ++kb)
-                for (int ch = 0; ch < 4; ++ch)
-                    for (int n = 0; n < 256; ++n)
-                        for (int e = 0; e < 8; ++e) {
-                            int ci = kb * 32 + ch * 8 + e;
-                            dst[((((size_t)tap * 8 + kb) * 4 + ch) * 256 + n) * 8 + e] = __float2bfloat16_rn(w[((size_t)tap * 256 + ci) * 256 + n]);
-                        }
+        pack_conv(w, 256, 32, reinterpret_cast<__nv_bfloat16*>(packed.data() + (size_t)L * TC_LAYER_BYTES));
+    }
+    {   // stem: conv/kernel [3][3][13][256], BatchNorm over the 7 board rows
+        const float* w = az_nn_host_var(nn, "conv/kernel");
+        const float* g = az_nn_host_var(nn, "conv_bn/gamma");
+        const float* be = az_nn_host_var(nn, "conv_bn/beta");
+        const float* mu = az_nn_host_var(nn, "conv_bn/moving_mean");
+        const float* var = az_nn_host_var(nn, "conv_bn/moving_variance");
+        if (!w || !g || !be || !mu || !var) { az_set_error("missing stem variable"); return AZ_ERR_INVALID_ARG; }
+        for (int y = 0; y < 7; ++y) {
+            float sc = g[y] / sqrtf(var[y] + AZ_NN_BN_EPS);
+            scale[(size_t)layers * 256 + y] = sc; shift[(size_t)layers * 256 + y] = be[y] - mu[y] * sc;
+        }
+        pack_conv(w, AZ_NN_IN_CH, 2, reinterpret_cast<__nv_bfloat16*>(packed.data() + (size_t)layers * TC_LAYER_BYTES));
     }
     if (!tc->d_wpacked) {
         AZ_CUDA(cudaMalloc(&tc->d_wpacked, packed.size()));
         AZ_CUDA(cudaMalloc(&tc->d_scale, scale.size() * sizeof(float)));
         AZ_CUDA(cudaMalloc(&tc->d_shift, shift.size() * sizeof(float)));
-        int8_t nb[42 * 9];
-        for (int p = 0; p < 42; ++p)
-            for (int t = 0; t < 9; ++t) {
-                int y = p / 6 + t / 3 - 1, x = p % 6 + t % 3 - 1;
-                nb[p * 9 + t] = (y < 0 || y >= 7 || x < 0 || x >= 6) ? (int8_t)-1 : (int8_t)(y * 6 + x);
-            }
-        AZ_CUDA(cudaMemcpyToSymbol(c_nb_tc, nb, sizeof nb));
-        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<32>::SMEM_BYTES));
+        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::SMEM_BYTES));
+        int dev = 0, sms = 148;
+        AZ_CUDA(cudaGetDevice(&dev));
+        AZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        tc->n_sm = sms;
     }
     AZ_CUDA(cudaMemcpy(tc->d_wpacked, packed.data(), packed.size(), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_scale, scale.data(), scale.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -397,7 +443,7 @@ void az_nn_tc_release(az_nn* nn)
     if (!nn->tc) return;
     AzTcState* tc = nn->tc;
     for (int i = 0; i < 3; ++i) cudaFree(tc->d_act[i]);
-    cudaFree(tc->d_wpacked); cudaFree(tc->d_scale); cudaFree(tc->d_shift); cudaFree(tc->d_x);
+    cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_scale); cudaFree(tc->d_shift); cudaFree(tc->d_x);
     delete tc;
     nn->tc = nullptr;
 }
@@ -406,7 +452,7 @@ static int tc_reserve(AzTcState* tc, int n)
 {
     if (n <= tc->cap_boards) return AZ_OK;
     for (int i = 0; i < 3; ++i) { cudaFree(tc->d_act[i]); tc->d_act[i] = nullptr; }
-    cudaFree(tc->d_x); tc->d_x = nullptr;
+    cudaFree(tc->d_x); tc->d_x = nullptr; cudaFree(tc->d_in); tc->d_in = nullptr;
     int tiles = (n * TC_ROWS_PER_BOARD + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     int r_alloc = tiles * TC_TILE_ROWS + 2 * TC_HALO;
     size_t bytes = (size_t)TC_CHUNKS * r_alloc * 16;
@@ -414,6 +460,8 @@ static int tc_reserve(AzTcState* tc, int n)
         AZ_CUDA(cudaMalloc(&tc->d_act[i], bytes));
         AZ_CUDA(cudaMemset(tc->d_act[i], 0, bytes));          // padding rows and halos must read as zero
     }
+    AZ_CUDA(cudaMalloc(&tc->d_in, (size_t)2 * r_alloc * 16));
+    AZ_CUDA(cudaMemset(tc->d_in, 0, (size_t)2 * r_alloc * 16));
     AZ_CUDA(cudaMalloc(&tc->d_x, sizeof(float) * (size_t)n * AZ_INPUT_FLOATS));
     tc->cap_boards = n; tc->n_tiles = tiles; tc->r_alloc = r_alloc;
     return AZ_OK;
@@ -428,18 +476,23 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
         rc = az_launch_encode(d_env_state, n, tc->d_x, s); if (rc) return rc;
         d_x = tc->d_x;
     }
-    // the buffers were sized for cap_boards; tiles beyond the boards of this call only produce zeros
+    // buffers are sized for cap_boards; only the tiles that hold boards of this call are computed
     const int tiles = (n * TC_ROWS_PER_BOARD + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    const int grid = tiles < tc->n_sm ? tiles : tc->n_sm;
+    const int layers = 2 * nn->blocks;
     int cur = 0, tmp = 1, nxt = 2;
-    k_nn_stem_tc<<<n, 256, 0, s>>>(d_x, n, az_nn_dev_var(nn, "conv/kernel"), az_nn_dev_var(nn, "conv_bn/gamma"), tc->d_act[cur], tc->r_alloc);
+    k_nn_pack_input_tc<<<(n * 42 + 255) / 256, 256, 0, s>>>(d_x, n, tc->d_in, tc->r_alloc);
+    AZ_CUDA(cudaGetLastError());
+    k_nn_conv_tc<2, true><<<grid, TC_THREADS, TcShape<2>::SMEM_BYTES, s>>>(tc->d_in, tc->d_wpacked + (size_t)layers * TC_LAYER_BYTES,
+        tc->d_scale + layers * 256, tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n, tc->r_alloc, tiles);
     AZ_CUDA(cudaGetLastError());
     for (int i = 0; i < nn->blocks; ++i) {
         const int L0 = 2 * i, L1 = 2 * i + 1;
-        k_nn_conv_tc<<<tiles, TC_THREADS, TC_SMEM_BYTES, s>>>(tc->d_act[cur], tc->d_wpacked + (size_t)L0 * TC_LAYER_BYTES, tc->d_scale + L0 * 256,
-                                                              tc->d_shift + L0 * 256, nullptr, tc->d_act[tmp], n, tc->r_alloc);
+        k_nn_conv_tc<32, false><<<grid, TC_THREADS, TcShape<32>::SMEM_BYTES, s>>>(tc->d_act[cur], tc->d_wpacked + (size_t)L0 * TC_LAYER_BYTES,
+            tc->d_scale + L0 * 256, tc->d_shift + L0 * 256, nullptr, tc->d_act[tmp], n, tc->r_alloc, tiles);
         AZ_CUDA(cudaGetLastError());
-        k_nn_conv_tc<<<tiles, TC_THREADS, TC_SMEM_BYTES, s>>>(tc->d_act[tmp], tc->d_wpacked + (size_t)L1 * TC_LAYER_BYTES, tc->d_scale + L1 * 256,
-                                                              tc->d_shift + L1 * 256, tc->d_act[cur], tc->d_act[nxt], n, tc->r_alloc);
+        k_nn_conv_tc<32, false><<<grid, TC_THREADS, TcShape<32>::SMEM_BYTES, s>>>(tc->d_act[tmp], tc->d_wpacked + (size_t)L1 * TC_LAYER_BYTES,
+            tc->d_scale + L1 * 256, tc->d_shift + L1 * 256, tc->d_act[cur], tc->d_act[nxt], n, tc->r_alloc, tiles);
         AZ_CUDA(cudaGetLastError());
         int o = cur; cur = nxt; nxt = o;
     }
