@@ -49,5 +49,25 @@ g++ $CXXFLAGS -fno-access-control -c "$HERE/ref_shim.cpp" -o "$B/obj/91_ref_shim
 gcc -O3 -w -fPIC -c "$B/libs/xxhash/xxhash.c" -o "$B/obj/92_xxhash.o" & pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 g++ -shared -pthread -o "$OUT/libref_oracle.so" "${OBJS[@]}" "$B/obj/90_alphazero_nn.o" "$B/obj/91_ref_shim.o" "$B/obj/92_xxhash.o"
-rm -rf "$B"
 echo "built $OUT/libref_oracle.so"
+
+# ---- second variant: the same UNMODIFIED reference search / player / game loop, NN facade bound to the B200
+# library through alphazero_risk_b200/host/az_nn_service.hpp (drop-in test, tests/test_dropin_gpu.py)
+AZLIB="$REPO/alphazero_risk_b200/libaz_b200.so"
+if [ -f "$AZLIB" ]; then
+  cp "$HERE/overlay_gpu_cluster_b200.h" "$AZ/neural_network/alphazero_gpu_cluster.h"
+  GFLAGS="$CXXFLAGS -I$REPO/alphazero_risk_b200/host"
+  pids=()
+  g++ $GFLAGS -c "$AZ/alphazero_mcts.cpp" -o "$B/obj/g_mcts.o" & pids+=($!)
+  g++ $GFLAGS -c "$AZ/alphazero_player.cpp" -o "$B/obj/g_player.o" & pids+=($!)
+  g++ $GFLAGS -fno-access-control -c "$HERE/ref_shim_gpu.cpp" -o "$B/obj/g_shim.o" & pids+=($!)
+  for p in "${pids[@]}"; do wait "$p"; done
+  GOBJS=()
+  for o in "${OBJS[@]}"; do case "$o" in *alphazero_mcts.o) ;; *) GOBJS+=("$o");; esac; done
+  g++ -shared -pthread -o "$OUT/libref_gpusvc.so" "${GOBJS[@]}" "$B/obj/g_mcts.o" "$B/obj/g_player.o" "$B/obj/g_shim.o" "$B/obj/92_xxhash.o" \
+      -L"$REPO/alphazero_risk_b200" -laz_b200 -Wl,-rpath,'$ORIGIN/../../alphazero_risk_b200'
+  echo "built $OUT/libref_gpusvc.so"
+else
+  echo "libaz_b200.so not built yet: skipping libref_gpusvc.so" >&2
+fi
+rm -rf "$B"

@@ -1,0 +1,38 @@
+"""The C++ host adapter that mirrors the reference's NN facade (alphazero_risk_b200/host/az_nn_service.hpp).
+CPU part: it compiles standalone against include/az_b200.h and fails loudly without a GPU.
+GPU part (marked gpu): concurrent predictFuture batching equals direct evaluation."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "host", "test_nn_service")
+
+
+def build_exe():
+    from alphazero_risk_b200 import build
+    build.build()
+    src = os.path.join(ROOT, "tests", "host", "test_nn_service.cpp")
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(build.LIB)):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + os.path.join(ROOT, "include"),
+                               "-I" + os.path.join(ROOT, "alphazero_risk_b200", "host"), src, "-o", EXE,
+                               "-L" + os.path.join(ROOT, "alphazero_risk_b200"), "-laz_b200",
+                               "-Wl,-rpath," + os.path.join(ROOT, "alphazero_risk_b200"), "-Wl,-rpath,$ORIGIN/../../alphazero_risk_b200"])
+    return EXE
+
+
+def test_adapter_compiles_and_has_no_cpu_fallback():
+    exe = build_exe()
+    from alphazero_risk_b200 import api
+    if api.lib().az_device_count() > 0:
+        pytest.skip("a GPU is present")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "NO_DEVICE_OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_adapter_batches_concurrent_requests():
+    exe = build_exe() if os.path.exists("/usr/bin/g++") or os.path.exists("/opt/gcc/bin/g++") else EXE
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "SERVICE_OK" in out.stdout, out.stdout + out.stderr
