@@ -134,9 +134,40 @@ def cpu_selfplay_baseline(sims, seconds_target):
     per_thread = int(max(20, out.moves / max(out.seconds, 1e-9) / threads * seconds_target))
     L.ref_bench_selfplay(threads, per_thread, 2, None, None, C.byref(out))
     po.ref_apply_rules(po.default_rules())
-    return dict(value=out.sims / out.seconds, unit="sims/s", cores=threads, kind="reference",
-                sample="%d threads x %d self-play moves x %d sims through the compiled reference (AlphaZeroMCTS::simulate, T=1, "
-                       "null evaluator: no network cost), %.1f s" % (threads, per_thread, sims, out.seconds))
+    res = dict(value=out.sims / out.seconds, unit="sims/s", cores=threads, kind="reference",
+               sample="%d threads x %d self-play moves x %d sims through the compiled reference (AlphaZeroMCTS::simulate, T=1, "
+                      "NULL evaluator: tree + env cost only, no network), %.1f s" % (threads, per_thread, sims, out.seconds))
+    # the reference's network runs in TensorFlow (absent); time the PyTorch-CPU restatement of the same graph instead
+    try:
+        import numpy as np
+        import torch
+        from oracle import nn_oracle as no
+        torch.set_num_threads(threads)
+        rng = np.random.default_rng(0)
+        shapes = {"conv/kernel": (3, 3, 13, 256), "pi/kernel": (1, 1, 256, 2), "v/kernel": (1, 1, 256, 1), "dense/kernel": (84, 43),
+                  "dense/bias": (43,), "dense_1/kernel": (42, 256), "dense_1/bias": (256,), "dense_2/kernel": (256, 1), "dense_2/bias": (1,)}
+        w = {}
+        for name in no.variable_names(5):
+            if name in shapes:
+                shp = shapes[name]
+            elif name.endswith("/kernel"):
+                shp = (3, 3, 256, 256)
+            else:
+                shp = (7,) if name.startswith("conv_bn") else (2,) if name.startswith("bn_pi") else (1,) if name.startswith("bn_v") else (256,)
+            w[name] = (rng.standard_normal(shp) * 0.05 + (1.0 if name.endswith(("gamma", "variance")) else 0.0)).astype(np.float32)
+        x = rng.random((256, 7, 6, 13), dtype=np.float32)
+        no.forward(w, x[:32], 5)
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < 4.0:
+            no.forward(w, x, 5); reps += 1
+        nn_rate = reps * 256 / (time.perf_counter() - t0)
+        res["nn_positions_per_sec_torch_cpu"] = nn_rate
+        res["with_network_estimate_sims_per_sec"] = 1.0 / (1.0 / res["value"] + 1.0 / nn_rate)
+        res["sample"] += "; 5-block network on the same cores via the PyTorch-CPU restatement (batch 256): %.0f positions/s" % nn_rate
+    except Exception as e:   # noqa: BLE001
+        res["nn_positions_per_sec_torch_cpu"] = None
+        res["sample"] += "; torch CPU network timing failed: %s" % e
+    return res
 
 
 def run_reference(args):
