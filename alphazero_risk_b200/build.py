@@ -46,7 +46,8 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
         objs.append(obj)
         if force or _newer([src] + headers, obj):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [nvcc] + ARCH + COMMON + extra + os.environ.get("AZ_B200_NVCC_FLAGS", "").split() + \
+                  (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             procs.append((unit, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for unit, p in procs:

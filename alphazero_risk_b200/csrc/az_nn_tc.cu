@@ -37,8 +37,11 @@
 #define TC_HALO 8
 #define TC_A_ROWS (TC_TILE_ROWS + 2 * TC_HALO)              // 144
 #define TC_CHUNKS 32                                         // 256 channels / 8
+#ifndef TC_STAGES
 #define TC_STAGES 4
+#endif
 #define TC_THREADS 192
+#define TC_SKIP_AHEAD 4                                      // residual-input prefetch distance in the epilogue (chunks); the loop is unrolled by the same 4
 #define TC_LAYER_BYTES (9 * 256 * 256 * 2)                   // 1179648 packed bf16 weights of one tower conv
 #define TC_STEM_BYTES (9 * 16 * 256 * 2)                     // 73728: stem weights, 13 input channels padded to 16
 
@@ -55,6 +58,7 @@ template <int KCH> struct TcShape {
 
 struct AzTcState {
     int cap_boards = 0, n_tiles = 0, r_alloc = 0, n_sm = 148;
+    int cluster = 1, max_clusters = 148;                       // thread-block cluster size of the tower kernel, co-resident clusters
     __nv_bfloat16* d_act[3] = { nullptr, nullptr, nullptr };   // [32][r_alloc][8]
     __nv_bfloat16* d_in = nullptr;                             // [2][r_alloc][8]: encoded input, 13 channels padded to 16
     uint8_t* d_wpacked = nullptr;                              // [2*blocks] x 1.18 MB tower weights, then the 72 KB stem weights
@@ -90,6 +94,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// one slice of a weight stage fetched once from L2 and delivered to the same shared-memory offset (and the same
+// mbarrier offset) of every CTA of the cluster named in cta_mask
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -99,6 +115,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
 {
@@ -158,11 +180,21 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // thread-block cluster: the CTAs of a cluster walk the same weight stream in step, each fetches 1/csz of every
+    // weight stage and multicasts it to all of them, so L2 -> SM weight traffic drops by csz (the kernel is bound by
+    // L2 delivery, not by the tensor pipe, when every CTA streams all 1.18 MB of a layer per 128-row tile)
+    uint32_t crank, csz;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csz));
+    const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
+    const int n_clusters = (int)(gridDim.x / csz), cid = (int)(blockIdx.x / csz);
+    const int n_items = (n_tiles + (int)csz - 1) / (int)csz;      // one item = csz consecutive tiles, one per CTA of the cluster
+    const uint32_t slice = (uint32_t)S::STAGE_BYTES / csz;
 
     for (int i = threadIdx.x; i < 256; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b) { mbar_init(bar_a_full + b, 1); mbar_init(bar_a_empty + b, 1); mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, 4); }
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_w_full + s, 1); mbar_init(bar_w_empty + s, 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_w_full + s, 1); mbar_init(bar_w_empty + s, csz); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -171,6 +203,7 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
     }
     tc_fence_before();
     __syncthreads();
+    if (csz > 1) cluster_sync_all();        // nobody multicasts into a CTA whose barriers are not initialised yet
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
@@ -178,7 +211,9 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
         if (lane == 0) {
             // ---- operand streamer
             const uint8_t* src = reinterpret_cast<const uint8_t*>(in);
-            auto load_a = [&](int j, int tile) {
+            auto load_a = [&](int j, int item) {
+                int tile = item * (int)csz + (int)crank;
+                if (tile >= n_tiles) tile = n_tiles - 1;          // padding tile of the last item: multiplied, never stored
                 const int b = j & 1;
                 if (j >= 2) mbar_wait(bar_a_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
                 mbar_expect_tx(bar_a_full + b, S::A_BYTES);
@@ -188,15 +223,19 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
             };
             uint32_t wit = 0;
             int j = 0;
-            if ((int)blockIdx.x < n_tiles) load_a(0, blockIdx.x);
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            if (cid < n_items) load_a(0, cid);
+            for (int item = cid; item < n_items; item += n_clusters, ++j) {
                 for (int it = 0; it < S::ITERS; ++it, ++wit) {
                     const uint32_t s = wit % TC_STAGES, k = wit / TC_STAGES;
-                    if (k > 0) mbar_wait(bar_w_empty + s, (k - 1) & 1u);
+                    if (k > 0) mbar_wait(bar_w_empty + s, (k - 1) & 1u);     // every CTA of the cluster is done with this stage
                     mbar_expect_tx(bar_w_full + s, S::STAGE_BYTES);
-                    bulk_g2s(sB + (size_t)s * S::STAGE_BYTES, wpacked + (size_t)it * S::STAGE_BYTES, S::STAGE_BYTES, bar_w_full + s);
+                    if (csz == 1)
+                        bulk_g2s(sB + (size_t)s * S::STAGE_BYTES, wpacked + (size_t)it * S::STAGE_BYTES, S::STAGE_BYTES, bar_w_full + s);
+                    else
+                        bulk_g2s_multicast(sB + (size_t)s * S::STAGE_BYTES + (size_t)crank * slice,
+                                           wpacked + (size_t)it * S::STAGE_BYTES + (size_t)crank * slice, slice, bar_w_full + s, cmask);
                     // prefetch the next tile's A operand early in this tile (its buffer is released by the previous tile's MMAs)
-                    if (it == (S::ITERS > 8 ? 8 : S::ITERS - 1) && tile + (int)gridDim.x < n_tiles) load_a(j + 1, tile + gridDim.x);
+                    if (it == (S::ITERS > 8 ? 8 : S::ITERS - 1) && item + n_clusters < n_items) load_a(j + 1, item + n_clusters);
                 }
             }
         }
@@ -206,7 +245,7 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
             const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
             uint32_t wit = 0;
             int j = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+            for (int item = cid; item < n_items; item += n_clusters, ++j) {
                 const int b = j & 1;
                 mbar_wait(bar_a_full + b, (uint32_t)((j >> 1) & 1));
                 if (j >= 2) mbar_wait(bar_acc_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
@@ -224,7 +263,9 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
                         const uint64_t adesc = umma_desc(a_base + (uint32_t)(b * S::A_BYTES + (chunk0 * TC_A_ROWS + TC_HALO + sh) * 16), TC_A_ROWS * 16, 128);
                         tc_mma_bf16(tmem_base + (uint32_t)(b * 256), adesc, bdesc, TC_IDESC, (it > 0 || kk > 0) ? 1u : 0u);
                     }
-                    tc_commit(bar_w_empty + s);          // frees the weight stage when these MMAs retire
+                    // frees the weight stage when these MMAs retire — in every CTA of the cluster, since each of them
+                    // writes a slice of the next round into this CTA's copy of the stage
+                    if (csz == 1) tc_commit(bar_w_empty + s); else tc_commit_multicast(bar_w_empty + s, cmask);
                 }
                 tc_commit(bar_a_empty + b);
                 tc_commit(bar_acc_full + b);
@@ -234,19 +275,36 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
         // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31
         const int q = warp & 3;
         int j = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
+        for (int item = cid; item < n_items; item += n_clusters, ++j) {
             const int b = j & 1;
+            const int tile = item * (int)csz + (int)crank;
             mbar_wait(bar_acc_full + b, (uint32_t)((j >> 1) & 1));
             tc_fence_after();
+            if (tile < n_tiles) {
             const int r = tile * TC_TILE_ROWS + q * 32 + lane;                 // padded row of this thread
             const bool valid = tc_row_valid(r, n_boards);
             const int yrow = (r % TC_ROWS_PER_BOARD) / 7;                      // board row (stem BatchNorm index)
-#pragma unroll 2
+            // the residual input is prefetched TC_SKIP_AHEAD chunks ahead (ncu, round 1: with a load-then-use skip read the
+            // branch2b layers ran 285 us against 220 us for the branch2a layers — the epilogue, not the MMA, set the tile time)
+            const size_t cell0 = ((size_t)TC_HALO + r) * 8;
+            const size_t cstride = (size_t)r_alloc * 8;
+            uint4 skq[TC_SKIP_AHEAD];
+            if (skip) {
+#pragma unroll
+                for (int p = 0; p < TC_SKIP_AHEAD; ++p) skq[p] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)p * cstride));
+            }
+#pragma unroll 4
             for (int c = 0; c < TC_CHUNKS; ++c) {
                 uint32_t v[8];
                 tc_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c * 8), v);
+                uint4 sk = make_uint4(0u, 0u, 0u, 0u);
+                if (skip) {
+                    sk = skq[c % TC_SKIP_AHEAD];
+                    if (c + TC_SKIP_AHEAD < TC_CHUNKS)
+                        skq[c % TC_SKIP_AHEAD] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)(c + TC_SKIP_AHEAD) * cstride));
+                }
                 tc_ld_wait();
-                const size_t cell = ((size_t)c * r_alloc + TC_HALO + r) * 8;   // element index of this 16-byte cell
+                const size_t cell = cell0 + (size_t)c * cstride;               // element index of this 16-byte cell
                 float f[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -254,7 +312,6 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
                     f[e] = fmaf(__uint_as_float(v[e]), s_scale[bi], s_shift[bi]);
                 }
                 if (skip) {
-                    uint4 sk = *reinterpret_cast<const uint4*>(skip + cell);
                     const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sk);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(s2[e]); f[2 * e] += x.x; f[2 * e + 1] += x.y; }
@@ -268,6 +325,7 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
                 }
                 *reinterpret_cast<uint4*>(out + cell) = o;
             }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acc_empty + b);
@@ -275,6 +333,7 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
     }
     tc_fence_before();
     __syncthreads();
+    if (csz > 1) cluster_sync_all();        // peers may still be signalling this CTA's barriers until they are done too
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -387,6 +446,20 @@ static void pack_conv(const float* w, int cin, int kch, __nv_bfloat16* dst)
                     }
 }
 
+// persistent launch of one tower / stem convolution; csz > 1 = thread-block clusters with multicast weight streaming
+template <int KCH, bool ROW_BN>
+static cudaError_t launch_conv(int grid, int csz, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w, const float* scale, const float* shift,
+                               const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcShape<KCH>::SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = csz > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc<KCH, ROW_BN>, in, w, scale, shift, skip, out, n_boards, r_alloc, n_tiles);
+}
+
 int az_nn_tc_prepare(az_nn* nn)
 {
     if (!nn->tc) nn->tc = new AzTcState();
@@ -431,6 +504,27 @@ int az_nn_tc_prepare(az_nn* nn)
         AZ_CUDA(cudaGetDevice(&dev));
         AZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         tc->n_sm = sms;
+        if (const char* eg = getenv("AZ_TC_GRID")) { int g = atoi(eg); if (g >= 1 && g < sms) tc->n_sm = sms = g; }   // experiment knob: fewer persistent CTAs
+        // cluster size of the tower kernel: AZ_TC_CLUSTER = 1 (default) | 2 | 4; the grid is the number of clusters the
+        // device can hold at once (GPC sizes need not be multiples of the cluster size) times the cluster size.
+        // Measured on B200 (batch 4096, 5 blocks): 2.75 / 2.74 / 2.91 ms per forward for 1 / 2 / 4 — multicast weight
+        // streaming buys nothing, the kernel is bound by the MMA's own shared-memory operand reads (profiles/README.md)
+        const char* ev = getenv("AZ_TC_CLUSTER");
+        int csz = ev ? atoi(ev) : 1;
+        if (csz != 1 && csz != 2 && csz != 4) csz = 1;
+        tc->cluster = csz; tc->max_clusters = sms / csz;
+        if (csz > 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(sms / csz * csz)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcShape<32>::SMEM_BYTES;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nc = 0;
+            AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc<32, false>, &cfg));
+            if (nc < 1) { tc->cluster = 1; tc->max_clusters = sms; }
+            else tc->max_clusters = nc < sms / csz ? nc : sms / csz;
+        }
     }
     AZ_CUDA(cudaMemcpy(tc->d_wpacked, packed.data(), packed.size(), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_scale, scale.data(), scale.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -479,21 +573,21 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
     // buffers are sized for cap_boards; only the tiles that hold boards of this call are computed
     const int tiles = (n * TC_ROWS_PER_BOARD + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     const int grid = tiles < tc->n_sm ? tiles : tc->n_sm;
+    const int csz = tc->cluster;
+    const int items = (tiles + csz - 1) / csz;
+    const int tgrid = (items < tc->max_clusters ? items : tc->max_clusters) * csz;     // tower: whole clusters, all co-resident
     const int layers = 2 * nn->blocks;
     int cur = 0, tmp = 1, nxt = 2;
     k_nn_pack_input_tc<<<(n * 42 + 255) / 256, 256, 0, s>>>(d_x, n, tc->d_in, tc->r_alloc);
     AZ_CUDA(cudaGetLastError());
-    k_nn_conv_tc<2, true><<<grid, TC_THREADS, TcShape<2>::SMEM_BYTES, s>>>(tc->d_in, tc->d_wpacked + (size_t)layers * TC_LAYER_BYTES,
-        tc->d_scale + layers * 256, tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n, tc->r_alloc, tiles);
-    AZ_CUDA(cudaGetLastError());
+    AZ_CUDA((launch_conv<2, true>(grid, 1, s, tc->d_in, tc->d_wpacked + (size_t)layers * TC_LAYER_BYTES, tc->d_scale + layers * 256,
+                                  tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n, tc->r_alloc, tiles)));
     for (int i = 0; i < nn->blocks; ++i) {
         const int L0 = 2 * i, L1 = 2 * i + 1;
-        k_nn_conv_tc<32, false><<<grid, TC_THREADS, TcShape<32>::SMEM_BYTES, s>>>(tc->d_act[cur], tc->d_wpacked + (size_t)L0 * TC_LAYER_BYTES,
-            tc->d_scale + L0 * 256, tc->d_shift + L0 * 256, nullptr, tc->d_act[tmp], n, tc->r_alloc, tiles);
-        AZ_CUDA(cudaGetLastError());
-        k_nn_conv_tc<32, false><<<grid, TC_THREADS, TcShape<32>::SMEM_BYTES, s>>>(tc->d_act[tmp], tc->d_wpacked + (size_t)L1 * TC_LAYER_BYTES,
-            tc->d_scale + L1 * 256, tc->d_shift + L1 * 256, tc->d_act[cur], tc->d_act[nxt], n, tc->r_alloc, tiles);
-        AZ_CUDA(cudaGetLastError());
+        AZ_CUDA((launch_conv<32, false>(tgrid, csz, s, tc->d_act[cur], tc->d_wpacked + (size_t)L0 * TC_LAYER_BYTES, tc->d_scale + L0 * 256,
+                                        tc->d_shift + L0 * 256, nullptr, tc->d_act[tmp], n, tc->r_alloc, tiles)));
+        AZ_CUDA((launch_conv<32, false>(tgrid, csz, s, tc->d_act[tmp], tc->d_wpacked + (size_t)L1 * TC_LAYER_BYTES, tc->d_scale + L1 * 256,
+                                        tc->d_shift + L1 * 256, tc->d_act[cur], tc->d_act[nxt], n, tc->r_alloc, tiles)));
         int o = cur; cur = nxt; nxt = o;
     }
     k_nn_heads_tc<<<n, 256, 0, s>>>(tc->d_act[cur], n, tc->r_alloc, az_nn_head_params(nn), d_policy, d_value);
