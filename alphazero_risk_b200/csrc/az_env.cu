@@ -187,9 +187,10 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_query(const uint32_t* __restr
     if (status) status[gi] = (int8_t)az_game_status(c.g, rules);
 }
 
-// BASELINE config 2: n_steps uniform-random legal moves per game inside one launch; the state
-// stays in registers / shared memory between steps, finished games are re-dealt in place.
-__global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
+// BASELINE config 2, first version (kept as the A/B reference, AZ_ENV_ROLLOUT=v1): every lane runs az_valid_moves /
+// az_make_move as written for the single-step kernel; the six phase paths, the fortify component search and the re-deal
+// serialise inside a warp (ncu round 1: 4.5 of 32 lanes active, 3200 warp instructions per move).
+__global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout_v1(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
                                                             int n_steps, uint64_t seed, uint32_t first_game, AzRulesDev rules,
                                                             unsigned long long* __restrict__ counters)
 {
@@ -230,136 +231,66 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout(uint32_t* __restrict_
     }
 }
 
-// Phase-coherent rollout.  Same results as k_env_rollout, different thread <-> game assignment: before
-// every move the 128 games of a block are counting-sorted by (needs re-deal, roundPhase) so that a warp
-// executes one phase's code path instead of the union of all six (ncu on the plain kernel: 4.5 of 32
-// threads active per instruction).  All game state (land bytes, register masks, packed scalars, ply)
-// lives in shared-memory columns between moves so any thread can pick up any game.
-#define SRT_REG_WORDS 13     // own0, own1, gt1, full (2 words each), word10 (cards), words 11..13, ply
-struct EnvSortSmem {
-    uint64_t tab[AZ_TABLE_U64];
-    uint32_t col[ENV_COL_WORDS * ENV_BLOCK];
-    uint32_t reg[SRT_REG_WORDS * ENV_BLOCK];
-    uint32_t wcount[4][8];
-    uint8_t bucket[ENV_BLOCK];
-    uint8_t perm[ENV_BLOCK];
-};
 
-__device__ __forceinline__ void srt_save(const AzGame& g, uint32_t ply, EnvSortSmem& sm, int u)
+// BASELINE config 2: n_steps uniform-random legal moves per game inside one launch; the state stays in registers /
+// shared memory between moves, finished games are re-dealt in place.  Same results as k_env_rollout_v1, restructured
+// around what ncu showed (profiles/README.md): ~60 % of the v1 instructions were the fortify component search and the
+// re-deal executing with 1-2 active lanes.  Here
+//   * the common work of a move (status, legal mask with ONE neighbour union, Philox block, action pick, land writes,
+//     attack-army check) is one instruction stream for all lanes (az_valid_moves_flat / az_move_flat);
+//   * a lane whose move needs the component search, or whose game ended, PARKS; parked lanes are served together once
+//     `park_f` / `park_r` of them have accumulated (or nothing else in the warp can run), so the long serial paths run
+//     with many lanes active instead of one.  A parked lane simply finishes its n_steps a little later: games are
+//     independent and their random streams are keyed by (game, ply), so the interleaving does not change any result.
+__global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
+                                                            int n_steps, uint64_t seed, uint32_t first_game, AzRulesDev rules,
+                                                            unsigned long long* __restrict__ counters, int park_f, int park_r)
 {
-    uint32_t* r = sm.reg + u;
-    r[0 * ENV_BLOCK] = (uint32_t)g.own0; r[1 * ENV_BLOCK] = (uint32_t)(g.own0 >> 32);
-    r[2 * ENV_BLOCK] = (uint32_t)g.own1; r[3 * ENV_BLOCK] = (uint32_t)(g.own1 >> 32);
-    r[4 * ENV_BLOCK] = (uint32_t)g.gt1; r[5 * ENV_BLOCK] = (uint32_t)(g.gt1 >> 32);
-    r[6 * ENV_BLOCK] = (uint32_t)g.full; r[7 * ENV_BLOCK] = (uint32_t)(g.full >> 32);
-    r[8 * ENV_BLOCK] = (g.cards0 << 16) | (g.cards1 << 24);
-    r[9 * ENV_BLOCK] = az_pack_w11(g); r[10 * ENV_BLOCK] = az_pack_w12(g); r[11 * ENV_BLOCK] = az_pack_w13(g);
-    r[12 * ENV_BLOCK] = ply;
-}
-__device__ __forceinline__ void srt_load(AzGame& g, uint32_t& ply, const EnvSortSmem& sm, int u)
-{
-    const uint32_t* r = sm.reg + u;
-    g.own0 = (uint64_t)r[0 * ENV_BLOCK] | ((uint64_t)r[1 * ENV_BLOCK] << 32);
-    g.own1 = (uint64_t)r[2 * ENV_BLOCK] | ((uint64_t)r[3 * ENV_BLOCK] << 32);
-    g.gt1 = (uint64_t)r[4 * ENV_BLOCK] | ((uint64_t)r[5 * ENV_BLOCK] << 32);
-    g.full = (uint64_t)r[6 * ENV_BLOCK] | ((uint64_t)r[7 * ENV_BLOCK] << 32);
-    az_unpack_scalars(g, r[8 * ENV_BLOCK], r[9 * ENV_BLOCK], r[10 * ENV_BLOCK], r[11 * ENV_BLOCK]);
-    ply = r[12 * ENV_BLOCK];
-}
-
-__global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout_sorted(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
-                                                                   int n_steps, uint64_t seed, uint32_t first_game, AzRulesDev rules,
-                                                                   unsigned long long* __restrict__ counters)
-{
-    __shared__ EnvSortSmem sm;
-    for (int i = threadIdx.x; i < AZ_TABLE_U64; i += blockDim.x) sm.tab[i] = g_tab[i];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g0 = blockIdx.x * ENV_BLOCK;
-    const int gi = g0 + tid;
-    // load game `tid` into the shared columns
-    {
-        AzGame g; g.own0 = g.own1 = g.gt1 = g.full = 0;
-        uint32_t ply = 0;
-        if (gi < n) {
-            uint32_t w10 = 0;
-#pragma unroll
-            for (int w = 0; w < 11; ++w) {
-                uint32_t v = st[(size_t)w * n + gi];
-                sm.col[w * ENV_BLOCK + tid] = v;
-                az_masks_add_word(g, v, w);
-                if (w == 10) w10 = v;
-            }
-            az_unpack_scalars(g, w10, st[(size_t)11 * n + gi], st[(size_t)12 * n + gi], st[(size_t)13 * n + gi]);
-            ply = st[(size_t)AZ_W_PLY * n + gi];
-            srt_save(g, ply, sm, tid);
-            sm.bucket[tid] = az_game_status(g, rules) != AZ_STATUS_RUNNING ? 6 : (uint8_t)g.phase;
-        } else sm.bucket[tid] = 7;
-    }
-    __syncthreads();
-    AzTables T = az_tables_from_smem(sm.tab);
-    unsigned steps = 0, games = 0, w0 = 0, w1 = 0, dr = 0;
-    for (int s = 0; s < n_steps; ++s) {
-        // ---- counting sort of the block's games by bucket
-        const uint32_t b = sm.bucket[tid];
-        uint32_t mine = 0, rank = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) {
-            uint32_t m = __ballot_sync(0xffffffffu, b == k);
-            if (lane == (int)k) sm.wcount[warp][k] = (uint32_t)__popc(m);
-            if (b == k) { mine = m; }
+    __shared__ EnvSmem sm;
+    AzTables T = env_stage_tables(sm, g_tab);
+    const int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
+    const bool live = gi < n;
+    unsigned games = 0, w0 = 0, w1 = 0, dr = 0;
+    int done = 0;
+    EnvCtx c;
+    if (live) env_load(c, sm, st, n, gi); else { env_bind(c, sm); c.g = AzGame(); c.ply = 0; }
+    const uint32_t game = first_game + (uint32_t)gi;
+    int parked = 0, park_li = 0;                       // 0 = running, 1 = waiting for a re-deal, 2 = waiting for the component search
+    for (;;) {
+        const bool active = live && done < n_steps;
+        const unsigned m_active = __ballot_sync(0xffffffffu, active);
+        if (!m_active) break;
+        const unsigned m_r = __ballot_sync(0xffffffffu, active && parked == 1);
+        const unsigned m_f = __ballot_sync(0xffffffffu, active && parked == 2);
+        const bool nobody_runs = (m_active & ~(m_r | m_f)) == 0;
+        if (m_r && (__popc(m_r) >= park_r || nobody_runs)) {
+            if (active && parked == 1) { az_new_game(c.g, c.land, seed, game, c.ply); parked = 0; }
         }
-        rank = (uint32_t)__popc(mine & ((1u << lane) - 1u));
-        __syncthreads();
-        uint32_t base = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < 8; ++k)
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                uint32_t c = sm.wcount[w][k];
-                if (k < b || (k == b && w < warp)) base += c;
-            }
-        sm.perm[base + rank] = (uint8_t)tid;
-        __syncthreads();
-        // ---- one move of game perm[tid]
-        const int u = sm.perm[tid];
-        if (sm.bucket[u] != 7) {
-            EnvCtx c;
-            c.land.base = (uint8_t*)(sm.col) + 4 * u; c.land.stride_bytes = 4 * ENV_BLOCK;
-            c.scratch.base = (uint8_t*)(sm.col + 11 * ENV_BLOCK) + 4 * u; c.scratch.stride_bytes = 4 * ENV_BLOCK;
-            srt_load(c.g, c.ply, sm, u);
-            const uint32_t game = first_game + (uint32_t)(g0 + u);
-            int stt = az_game_status(c.g, rules);
+        if (m_f && (__popc(m_f) >= park_f || nobody_runs)) {
+            if (active && parked == 2) { az_fortify_finish(c.g, c.land, c.scratch, T, park_li); parked = 0; c.ply++; done++; }
+        }
+        if (live && done < n_steps && parked == 0) {
+            const int stt = az_game_status(c.g, rules);
             if (stt != AZ_STATUS_RUNNING) {
                 games++; w0 += stt == 0; w1 += stt == 1; dr += stt == AZ_STATUS_DRAW;
-                az_new_game(c.g, c.land, seed, game, c.ply);
+                parked = 1;
+            } else {
+                const uint64_t valid = az_valid_moves_flat(c.g, T, rules);
+                const az_u32x4 blk = az_rng_block(seed, game, c.ply, AZ_STREAM_REAL, 0);
+                const int action = az_nth_set_bit(valid, az_mulhi32(blk.y, (uint32_t)__popcll(valid)));
+                if (az_move_flat(c.g, c.land, T, rules, action, blk.x)) { parked = 2; park_li = action; }
+                else { c.ply++; done++; }
             }
-            uint64_t valid = az_valid_moves(c.g, T, rules);
-            az_u32x4 blk = az_rng_block(seed, game, c.ply, AZ_STREAM_REAL, 0);
-            int action = az_nth_set_bit(valid, az_mulhi32(blk.y, (uint32_t)__popcll(valid)));
-            AzDicePhilox d; d.init_with_block0(seed, game, c.ply, AZ_STREAM_REAL, blk);
-            az_make_move(c.g, c.land, c.scratch, T, rules, valid, action, d);
-            c.ply++; steps++;
-            srt_save(c.g, c.ply, sm, u);
-            sm.bucket[u] = az_game_status(c.g, rules) != AZ_STATUS_RUNNING ? 6 : (uint8_t)c.g.phase;
         }
-        __syncthreads();
     }
-    // write game `tid` back
-    if (gi < n) {
-#pragma unroll
-        for (int w = 0; w < 10; ++w) st[(size_t)w * n + gi] = sm.col[w * ENV_BLOCK + tid];
-        st[(size_t)10 * n + gi] = (sm.col[10 * ENV_BLOCK + tid] & 0xffffu) | sm.reg[8 * ENV_BLOCK + tid];
-        st[(size_t)11 * n + gi] = sm.reg[9 * ENV_BLOCK + tid];
-        st[(size_t)12 * n + gi] = sm.reg[10 * ENV_BLOCK + tid];
-        st[(size_t)13 * n + gi] = sm.reg[11 * ENV_BLOCK + tid];
-        st[(size_t)AZ_W_PLY * n + gi] = sm.reg[12 * ENV_BLOCK + tid];
-    }
+    if (live) env_store(c, sm, st, n, gi);
+    unsigned steps = live ? (unsigned)done : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         steps += __shfl_xor_sync(0xffffffffu, steps, o); games += __shfl_xor_sync(0xffffffffu, games, o);
         w0 += __shfl_xor_sync(0xffffffffu, w0, o); w1 += __shfl_xor_sync(0xffffffffu, w1, o); dr += __shfl_xor_sync(0xffffffffu, dr, o);
     }
-    if (lane == 0) {
+    if ((threadIdx.x & 31) == 0) {
         atomicAdd(&counters[0], (unsigned long long)steps);
         if (games) atomicAdd(&counters[1], (unsigned long long)games);
         if (w0) atomicAdd(&counters[2], (unsigned long long)w0);
@@ -693,15 +624,17 @@ extern "C" int az_env_rollout(az_env* e, int n_steps, void* stream)
     AzDeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     AZ_CUDA(cudaEventRecord(e->ev0, s));
-    // A/B switch: the phase-sorted variant is bit-identical but measured SLOWER on B200 (4.06 vs 5.78 G steps/s,
-    // profiles/README.md): its three block barriers per move make every warp wait for the slowest code path
-    static const bool plain = getenv("AZ_ENV_ROLLOUT_SORTED") == nullptr;
-    if (plain)
-        k_env_rollout<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
-                                                            dev_rules(e->rules), e->d_counters);
+    // AZ_ENV_ROLLOUT=v1 selects the first version of the kernel (A/B reference); AZ_ENV_PARK_F / AZ_ENV_PARK_R tune how many
+    // parked lanes a warp collects before it runs the component search / the re-deal for them
+    static const bool v1 = getenv("AZ_ENV_ROLLOUT") != nullptr && strcmp(getenv("AZ_ENV_ROLLOUT"), "v1") == 0;
+    static const int park_f = getenv("AZ_ENV_PARK_F") ? atoi(getenv("AZ_ENV_PARK_F")) : 8;
+    static const int park_r = getenv("AZ_ENV_PARK_R") ? atoi(getenv("AZ_ENV_PARK_R")) : 2;
+    if (v1)
+        k_env_rollout_v1<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
+                                                               dev_rules(e->rules), e->d_counters);
     else
-        k_env_rollout_sorted<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
-                                                                   dev_rules(e->rules), e->d_counters);
+        k_env_rollout<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
+                                                            dev_rules(e->rules), e->d_counters, park_f, park_r);
     AZ_CUDA(cudaGetLastError());
     AZ_CUDA(cudaEventRecord(e->ev1, s));
     e->timed = true;

@@ -35,12 +35,24 @@ enum { AZ_PH_SETUP = 0, AZ_PH_SETUP_NEUTRAL = 1, AZ_PH_REINFORCEMENT = 2, AZ_PH_
 #define AZ_PRIMARY_WORDS 14
 #define AZ_W_PLY 14
 
-// n-th (0-based) set bit of a 42/43-bit mask
+// n-th (0-based) set bit of a 42/43-bit mask, n < popcount(m): a 5-step binary search on popcounts
+// (__fns is a software loop on sm_100 — it was 13 % of the rollout kernel's instructions)
 __device__ __forceinline__ int az_nth_set_bit(uint64_t m, uint32_t n)
 {
-    uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
-    uint32_t pl = (uint32_t)__popc(lo);
-    return n < pl ? (int)__fns(lo, 0, (int)n + 1) : 32 + (int)__fns(hi, 0, (int)(n - pl) + 1);
+    uint32_t w = (uint32_t)m;
+    const uint32_t pl = (uint32_t)__popc(w);
+    int base = 0;
+    if (n >= pl) { n -= pl; w = (uint32_t)(m >> 32); base = 32; }
+    uint32_t c = (uint32_t)__popc(w & 0xffffu);
+    if (n >= c) { n -= c; w >>= 16; base += 16; }
+    c = (uint32_t)__popc(w & 0xffu);
+    if (n >= c) { n -= c; w >>= 8; base += 8; }
+    c = (uint32_t)__popc(w & 0xfu);
+    if (n >= c) { n -= c; w >>= 4; base += 4; }
+    c = (uint32_t)__popc(w & 0x3u);
+    if (n >= c) { n -= c; w >>= 2; base += 2; }
+    if (n >= (w & 1u)) base += 1;
+    return base;
 }
 
 // ---------------------------------------------------------------- constant tables
@@ -248,8 +260,15 @@ struct AzDiceTape {                   // explicit dice (golden vectors)
 // fortify source selection: UtilityNN::makeMove FORTIFY branch (alphazero_moves.cpp:172-231) over the
 // owned connected component of `li` listed in the DFS PRE-ORDER of GameHelper::LandSetMovement::add
 // (game_helper.cpp:51-82; seed = lowest owned index of the component, children in neighbour-list
-// order).  The recursion is replaced by a parent-pointer walk: after returning to a node, rescanning
-// its list from the start finds the same next child because everything before it is already seen.
+// order): the source is the land (!= li) with the most movable armies, interior lands (all neighbours
+// owned) before border lands, FIRST in pre-order among equals.
+//
+// The pre-order only matters for ties, so the maximum is found first with mask arithmetic: candidates =
+// component lands with army >= 2, restricted to interior ones if any exist; if a single land holds the
+// maximum it is the answer and no walk is needed.  Otherwise the DFS runs until it first visits one of the
+// tied lands.  (The walk replaces the reference's recursion by parent pointers: after returning to a
+// node, rescanning its list from the start finds the same next child because everything before it is
+// already seen.)
 template <class LandT, class ScratchT>
 __device__ __forceinline__ void az_fortify_source(const AzGame& g, const LandT& land, ScratchT& parent, const AzTables& T,
                                                   int li, int& from_out, int& amount_out)
@@ -257,36 +276,40 @@ __device__ __forceinline__ void az_fortify_source(const AzGame& g, const LandT& 
     const uint64_t owned = g.own(g.cur);
     uint64_t comp = 1ull << li;
     for (;;) { uint64_t n = (comp | az_nbr_union(T, comp)) & owned; if (n == comp) break; comp = n; }
-    const int seed = __ffsll((long long)comp) - 1;
-    int best_i = 0, from_i = -1, best_b = 0, from_b = -1;
+    from_out = -1; amount_out = 0;
+    uint64_t cand = comp & ~(1ull << li) & g.gt1;                       // army - 1 > 0
+    if (cand == 0) return;
+    const uint64_t inter = cand & ~az_nbr_union(T, AZ_ALL_LANDS & ~owned);   // not adjacent to any land the mover does not own
+    if (inter) cand = inter;
+    int best = 0;
+    uint64_t tie = 0;
+    for (uint64_t k = cand; k; k &= k - 1) {
+        const int v = __ffsll((long long)k) - 1;
+        const int a = (int)(land.get(v) & 63u);
+        if (a > best) { best = a; tie = 0; }
+        if (a == best) tie |= 1ull << v;
+    }
+    amount_out = best - 1;
+    if ((tie & (tie - 1)) == 0) { from_out = __ffsll((long long)tie) - 1; return; }
+    // several lands hold the maximum: the first one in DFS pre-order wins
     uint64_t seen = 0;
-    int v = seed;
+    int v = __ffsll((long long)comp) - 1;
     for (;;) {
-        // visit v (pre-order position)
+        if ((tie >> v) & 1ull) { from_out = v; return; }
         seen |= 1ull << v;
-        if (v != li) {
-            int val = (int)(land.get(v) & 63u) - 1;
-            uint64_t nb = T.nbr[v];
-            if ((nb & owned) == nb) { if (val > best_i) { best_i = val; from_i = v; } }
-            else                    { if (val > best_b) { best_b = val; from_b = v; } }
-        }
-        if (seen == comp) break;
-        // next unvisited owned land in DFS order
-        for (;;) {
-            uint64_t cand = T.nbr[v] & owned & ~seen;
-            if (cand) {
+        for (;;) {                                                       // next unvisited owned land in DFS order
+            const uint64_t nxt = T.nbr[v] & owned & ~seen;
+            if (nxt) {
                 uint64_t lst = T.list6[v];
                 int u = (int)(lst & 63u);
-                while (!((cand >> u) & 1ull)) { lst >>= 6; u = (int)(lst & 63u); }
+                while (!((nxt >> u) & 1ull)) { lst >>= 6; u = (int)(lst & 63u); }
                 parent.set(u, (uint32_t)v);
                 v = u;
                 break;
             }
-            v = (int)parent.get(v);   // backtrack (never past the seed: seen != comp guarantees a candidate upstream)
+            v = (int)parent.get(v);   // backtrack (never past the seed: an unvisited tied land guarantees a candidate upstream)
         }
     }
-    if (from_i >= 0) { from_b = from_i; best_b = best_i; }
-    from_out = from_b; amount_out = best_b;
 }
 
 // UtilityNN::makeMove, player/alpha_zero/alphazero_moves.cpp:72-233.  `valid` = az_valid_moves(g).
@@ -418,6 +441,165 @@ __device__ __forceinline__ int az_make_move(AzGame& g, LandT& land, ScratchT& sc
     }
     }
     return 0;
+}
+
+// ---------------------------------------------------------------- one-instruction-stream variants for the thread-per-game rollout
+// A warp of the rollout kernel holds 32 games in (up to) six different phases.  az_valid_moves / az_make_move branch per
+// phase, so the warp executes the SUM of the phase paths with ~4 of 32 lanes active (ncu, round 1).  The two functions
+// below compute the same results with the expensive parts (neighbour-union table walks, land writes, the attack-army
+// check) hoisted into code every lane runs once; only short phase-specific arithmetic stays under branches.
+
+// == az_valid_moves (UtilityNN::getValidMoves, alphazero_moves.cpp:3-70) with a single neighbour union
+__device__ __forceinline__ uint64_t az_valid_moves_flat(const AzGame& g, const AzTables& T, const AzRulesDev& r)
+{
+    const uint64_t oc = g.own(g.cur), oe = g.own(g.cur ^ 1u);
+    const uint32_t ph = g.phase;
+    const uint64_t s_in = ph == AZ_PH_ATTACK ? (oc & g.gt1) : (ph == AZ_PH_FORTIFY ? oe : (AZ_ALL_LANDS & ~oc));
+    const uint64_t u = az_nbr_union(T, s_in);
+    const uint64_t o = oc & ~g.full;
+    uint64_t place = o;                                           // SETUP / REINFORCEMENT
+    if (r.limit_reinforcement && (o & u)) place = o & u;
+    if (o == 0) place = AZ_SKIP_MASK;
+    const uint64_t aa = u & ~oc;                                  // ATTACK
+    const uint64_t att = r.limit_attack ? (aa ? aa : AZ_SKIP_MASK) : (aa | AZ_SKIP_MASK);
+    const uint64_t fort = (r.limit_reinforcement ? (oc & u) : oc) | AZ_SKIP_MASK;
+    const uint64_t mob = (1ull << (g.mob_from & 63u)) | (1ull << (g.mob_to & 63u));
+    uint64_t v = place;
+    v = ph == AZ_PH_SETUP_NEUTRAL ? (AZ_ALL_LANDS & ~oc & ~oe) : v;
+    v = ph == AZ_PH_ATTACK ? att : v;
+    v = ph == AZ_PH_MOBILIZATION ? mob : v;
+    v = ph == AZ_PH_FORTIFY ? fort : v;
+    return v;
+}
+
+// == az_make_move for a LEGAL action (UtilityNN::makeMove, alphazero_moves.cpp:72-233), dice = the base-6 digits of
+// `dice_word` (word 0 of the real-move Philox block: at most 5 dice per move, include/az_philox.h).
+// Returns 1 WITHOUT touching the state when the move is a FORTIFY onto a non-full land: that one needs the owned
+// component search (az_fortify_source), which the rollout kernel batches over several lanes; returns 0 otherwise.
+template <class LandT>
+__device__ __forceinline__ int az_move_flat(AzGame& g, LandT& land, const AzTables& T, const AzRulesDev& r, int action, uint32_t dice_word)
+{
+    const uint32_t cur = g.cur, ph = g.phase;
+    const bool skip = action == AZ_SKIP;
+    const int li = skip ? 0 : action;
+    const uint32_t tob = land.get(li);
+    const int at = (int)(tob & 63u);
+    if (ph == AZ_PH_FORTIFY && !skip && at != AZ_ARMY_MAX) return 1;
+
+    bool ga = false, et = false;                 // State::gotoAttack / nextPlayerGameTurn after the land writes
+    int ia = li, ib = li;
+    uint32_t va = 0, vb = 0, oa = cur, ob = cur;
+    bool wa = false, wb = false;
+    if (skip) {                                                    // alphazero_moves.cpp:79-92
+        ga = ph == AZ_PH_REINFORCEMENT;
+        et = ph == AZ_PH_FORTIFY;
+        if (ph == AZ_PH_ATTACK) g.phase = AZ_PH_FORTIFY;
+    } else if (ph == AZ_PH_ATTACK) {                               // alphazero_moves.cpp:122-145, State::attackMove state.cpp:769-918
+        int best = 0, from = li;
+        uint64_t lst = T.list6[li];
+        const uint64_t cand = g.own(cur) & g.gt1;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int n = (int)(lst & 63u); lst >>= 6;
+            const bool ok = n != 63 && ((cand >> n) & 1ull);
+            const int v = ok ? (int)(land.get(ok ? n : li) & 63u) - 1 : 0;
+            if (v > best) { best = v; from = n; }
+        }
+        g.attacks = (g.attacks + 1) & 0xff;
+        int a = best + 1, d = at, units = 1;
+        const uint32_t defender = tob >> 6;
+        if (d > 0) {
+            const int na = a >= 4 ? 3 : (a == 3 ? 2 : 1);
+            const int nd = d >= 2 ? 2 : 1;
+            units = na;
+            uint32_t w = dice_word;
+            uint64_t p;
+            p = (uint64_t)w * 6u; w = (uint32_t)p; const int a0 = (int)(p >> 32) + 1;
+            int a1 = 0, a2 = 0, d1 = 0;
+            if (na > 1) { p = (uint64_t)w * 6u; w = (uint32_t)p; a1 = (int)(p >> 32) + 1; }
+            if (na > 2) { p = (uint64_t)w * 6u; w = (uint32_t)p; a2 = (int)(p >> 32) + 1; }
+            p = (uint64_t)w * 6u; w = (uint32_t)p; const int d0 = (int)(p >> 32) + 1;
+            if (nd > 1) { p = (uint64_t)w * 6u; w = (uint32_t)p; d1 = (int)(p >> 32) + 1; }
+            const int hi = max(a0, max(a1, a2));
+            int lo = min(a0, max(a1, a2)); lo = max(lo, min(a1, a2));
+            const int dh = max(d0, d1), dl = min(d0, d1);
+            if (hi > dh) d--; else { a--; units--; }
+            if (na >= 2 && nd == 2) { if (lo > dl) d--; else { a--; units--; } }
+        }
+        ia = from; ib = li; wa = wb = true;
+        if (d == 0) {
+            a -= units;
+            if (a > 1) { g.phase = AZ_PH_MOBILIZATION; g.mob_from = (uint32_t)from; g.mob_to = (uint32_t)li; }
+            g.allow_draw = 1;
+            va = (uint32_t)a; vb = (uint32_t)units;
+        } else { va = (uint32_t)a; vb = (uint32_t)d; ob = defender; }
+    } else if (ph == AZ_PH_MOBILIZATION) {                         // alphazero_moves.cpp:146-171, State::attackReinforcementMove
+        if ((uint32_t)li == g.mob_from) ga = true;
+        else {
+            const int from = (int)g.mob_from;
+            const int af = (int)(land.get(from) & 63u);
+            const int v = af - 1;
+            int rf = v / 2;
+            if (rf < r.min_unit_move) rf = r.min_unit_move < v ? r.min_unit_move : v;
+            ia = from; va = (uint32_t)(af - rf); ib = li; vb = (uint32_t)(at + rf); wa = wb = true;
+            ga = af - rf == 1;
+        }
+    } else if (ph == AZ_PH_FORTIFY) {                              // target already full: nothing moves, the turn ends
+        et = true;
+    } else {                                                       // SETUP / SETUP_NEUTRAL / REINFORCEMENT: one land gains armies
+        int gain;
+        if (ph == AZ_PH_SETUP) {                                   // State::setupReinforcementMove, state.cpp:1009-1030
+            g.reinf = (g.reinf - 2) & 0xff; gain = 2; g.phase = AZ_PH_SETUP_NEUTRAL;
+        } else if (ph == AZ_PH_SETUP_NEUTRAL) {                    // setupReinforcementNeutralMove + nextPlayerSetupTurn
+            gain = 1; ob = AZ_NEUTRAL;
+            g.phase = AZ_PH_SETUP; g.round = (g.round + 1) & 0xffff; g.cur ^= 1u;
+            if (g.reinf == 0) { g.phase = AZ_PH_REINFORCEMENT; g.reinf = (uint32_t)az_reinforcement_value(g.own(g.cur)); }
+        } else {                                                   // alphazero_moves.cpp:104-121, playCards, State::reinforcementMove
+            uint32_t cards = cur ? g.cards1 : g.cards0;
+            if (cards >= 3) {
+                cards -= 3;
+                if (cur) g.cards1 = cards; else g.cards0 = cards;
+                g.card_sets = (g.card_sets + 1) & 0xff;
+                const int cs = (int)g.card_sets;
+                g.reinf = (g.reinf + (uint32_t)(cs <= 5 ? 2 + 2 * cs : 15 + (cs - 6) * 5)) & 0xff;
+            }
+            int rf = (int)g.reinf / 2;
+            if (rf < r.min_unit_move) rf = r.min_unit_move < (int)g.reinf ? r.min_unit_move : (int)g.reinf;
+            const int space = AZ_ARMY_MAX - at;
+            if (space < rf) rf = space;
+            g.reinf = (g.reinf - (uint32_t)rf) & 0xff;
+            gain = rf;
+            ga = g.reinf == 0;
+        }
+        vb = (uint32_t)(at + gain); wb = true;
+    }
+    if (wa) az_set_land(g, land, ia, va, oa);
+    if (wb) az_set_land(g, land, ib, vb, ob);
+    if (ga) { g.phase = AZ_PH_ATTACK; g.mob_from = AZ_NONE; g.mob_to = AZ_NONE; g.reinf = 0; }
+    // gotoAttack (state.cpp:20-40) and the end of attackMove (:909-912) share one test, run once for every lane:
+    // the ATTACK phase is only entered / kept while the mover still has a land that can attack
+    const uint64_t aa = az_attack_army(g, T, cur);
+    if (g.phase == AZ_PH_ATTACK && aa == 0) g.phase = AZ_PH_FORTIFY;
+    if (et) az_end_turn(g);
+    return 0;
+}
+
+// the deferred half of a FORTIFY move (alphazero_moves.cpp:172-231 + State::fortifyMove state.cpp:949-974 + nextPlayerGameTurn)
+template <class LandT, class ScratchT>
+__device__ __forceinline__ void az_fortify_finish(AzGame& g, LandT& land, ScratchT& scratch, const AzTables& T, int li)
+{
+    const uint32_t cur = g.cur;
+    const int at = (int)(land.get(li) & 63u);
+    int from, amount;
+    az_fortify_source(g, land, scratch, T, li, from, amount);
+    if (from >= 0) {
+        const int space = AZ_ARMY_MAX - at;
+        const int mv = space < amount ? space : amount;
+        const int af = (int)(land.get(from) & 63u);
+        az_set_land(g, land, from, (uint32_t)(af - mv), cur);
+        az_set_land(g, land, li, (uint32_t)(at + mv), cur);
+    }
+    az_end_turn(g);
 }
 
 // State::newGame, state/state.cpp:137-167 (Utility::randomMask, land/land.cpp:100-112):
