@@ -58,10 +58,11 @@ template <int KCH> struct TcShape {
 
 struct AzTcState {
     int cap_boards = 0, n_tiles = 0, r_alloc = 0, n_sm = 148;
-    int cluster = 1, max_clusters = 148;                       // thread-block cluster size of the tower kernel, co-resident clusters
     __nv_bfloat16* d_act[3] = { nullptr, nullptr, nullptr };   // [32][r_alloc][8]
     __nv_bfloat16* d_in = nullptr;                             // [2][r_alloc][8]: encoded input, 13 channels padded to 16
     uint8_t* d_wpacked = nullptr;                              // [2*blocks] x 1.18 MB tower weights, then the 72 KB stem weights
+    uint8_t* d_wpacked2 = nullptr;                             // tower weights in the CTA-pair layout (output channels split in two halves per stage)
+    int pair_mode = 1, max_pairs = 74;                         // tower on CTA pairs (k_nn_conv_tc2) unless AZ_TC_MODE=single
     float* d_scale = nullptr; float* d_shift = nullptr;        // [2*blocks][256] folded BN, then [256] (7 used) for the stem's row BN
     float* d_x = nullptr;                                      // fp32 encode of the leaf states
 };
@@ -94,13 +95,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-// one slice of a weight stage fetched once from L2 and delivered to the same shared-memory offset (and the same
-// mbarrier offset) of every CTA of the cluster named in cta_mask
-__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t cta_mask)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -116,11 +110,45 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// same, arriving on the barrier at this offset in every CTA of cta_mask
-__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t cta_mask)
+// ---- CTA-pair (cta_group::2) variants
+// Barriers signalled by the other CTA of the pair.  Default (.cta) semantics on purpose: everything ordered through them is
+// async-proxy traffic (bulk copies, tcgen05.mma / ld, ordered by complete_tx, tcgen05.commit and the tcgen05 fences) — no
+// generic-proxy data crosses the pair.  With .acquire/.release.cluster ptxas emits MEMBAR.ALL.GPU + CCTL.IVALL per call and
+// the kernel ran 2.3x slower (measured).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity)
 {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITC_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAITC_DONE;\n\t"
+        "bra WAITC_LOOP;\n\t"
+        "WAITC_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank)   // arrive on `bar` of CTA cta_rank of the cluster
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(cta_rank) : "memory");
+}
+__device__ __forceinline__ void tc2_commit(uint64_t* bar)                              // both CTAs of the pair get the arrive
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
 {
@@ -150,6 +178,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 [4,6) = 1, A = B = bf16 [7,10) = [10,13) = 1,
 // both K-major (bits 15,16 = 0), N >> 3 at [17,23), M >> 4 at [24,29)
 #define TC_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24))
+#define TC2_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24))   // M = 256 over the CTA pair
 
 __device__ __forceinline__ bool tc_row_valid(int r, int n_boards)
 {
@@ -180,21 +209,10 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // thread-block cluster: the CTAs of a cluster walk the same weight stream in step, each fetches 1/csz of every
-    // weight stage and multicasts it to all of them, so L2 -> SM weight traffic drops by csz (the kernel is bound by
-    // L2 delivery, not by the tensor pipe, when every CTA streams all 1.18 MB of a layer per 128-row tile)
-    uint32_t crank, csz;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csz));
-    const uint16_t cmask = (uint16_t)((1u << csz) - 1u);
-    const int n_clusters = (int)(gridDim.x / csz), cid = (int)(blockIdx.x / csz);
-    const int n_items = (n_tiles + (int)csz - 1) / (int)csz;      // one item = csz consecutive tiles, one per CTA of the cluster
-    const uint32_t slice = (uint32_t)S::STAGE_BYTES / csz;
-
     for (int i = threadIdx.x; i < 256; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b) { mbar_init(bar_a_full + b, 1); mbar_init(bar_a_empty + b, 1); mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, 4); }
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_w_full + s, 1); mbar_init(bar_w_empty + s, csz); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(bar_w_full + s, 1); mbar_init(bar_w_empty + s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -203,7 +221,6 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
     }
     tc_fence_before();
     __syncthreads();
-    if (csz > 1) cluster_sync_all();        // nobody multicasts into a CTA whose barriers are not initialised yet
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
@@ -211,9 +228,7 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
         if (lane == 0) {
             // ---- operand streamer
             const uint8_t* src = reinterpret_cast<const uint8_t*>(in);
-            auto load_a = [&](int j, int item) {
-                int tile = item * (int)csz + (int)crank;
-                if (tile >= n_tiles) tile = n_tiles - 1;          // padding tile of the last item: multiplied, never stored
+            auto load_a = [&](int j, int tile) {
                 const int b = j & 1;
                 if (j >= 2) mbar_wait(bar_a_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
                 mbar_expect_tx(bar_a_full + b, S::A_BYTES);
@@ -223,19 +238,15 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
             };
             uint32_t wit = 0;
             int j = 0;
-            if (cid < n_items) load_a(0, cid);
-            for (int item = cid; item < n_items; item += n_clusters, ++j) {
+            if ((int)blockIdx.x < n_tiles) load_a(0, blockIdx.x);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
                 for (int it = 0; it < S::ITERS; ++it, ++wit) {
                     const uint32_t s = wit % TC_STAGES, k = wit / TC_STAGES;
-                    if (k > 0) mbar_wait(bar_w_empty + s, (k - 1) & 1u);     // every CTA of the cluster is done with this stage
+                    if (k > 0) mbar_wait(bar_w_empty + s, (k - 1) & 1u);
                     mbar_expect_tx(bar_w_full + s, S::STAGE_BYTES);
-                    if (csz == 1)
-                        bulk_g2s(sB + (size_t)s * S::STAGE_BYTES, wpacked + (size_t)it * S::STAGE_BYTES, S::STAGE_BYTES, bar_w_full + s);
-                    else
-                        bulk_g2s_multicast(sB + (size_t)s * S::STAGE_BYTES + (size_t)crank * slice,
-                                           wpacked + (size_t)it * S::STAGE_BYTES + (size_t)crank * slice, slice, bar_w_full + s, cmask);
+                    bulk_g2s(sB + (size_t)s * S::STAGE_BYTES, wpacked + (size_t)it * S::STAGE_BYTES, S::STAGE_BYTES, bar_w_full + s);
                     // prefetch the next tile's A operand early in this tile (its buffer is released by the previous tile's MMAs)
-                    if (it == (S::ITERS > 8 ? 8 : S::ITERS - 1) && item + n_clusters < n_items) load_a(j + 1, item + n_clusters);
+                    if (it == (S::ITERS > 8 ? 8 : S::ITERS - 1) && tile + (int)gridDim.x < n_tiles) load_a(j + 1, tile + gridDim.x);
                 }
             }
         }
@@ -245,7 +256,7 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
             const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
             uint32_t wit = 0;
             int j = 0;
-            for (int item = cid; item < n_items; item += n_clusters, ++j) {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
                 const int b = j & 1;
                 mbar_wait(bar_a_full + b, (uint32_t)((j >> 1) & 1));
                 if (j >= 2) mbar_wait(bar_acc_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
@@ -263,9 +274,7 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
                         const uint64_t adesc = umma_desc(a_base + (uint32_t)(b * S::A_BYTES + (chunk0 * TC_A_ROWS + TC_HALO + sh) * 16), TC_A_ROWS * 16, 128);
                         tc_mma_bf16(tmem_base + (uint32_t)(b * 256), adesc, bdesc, TC_IDESC, (it > 0 || kk > 0) ? 1u : 0u);
                     }
-                    // frees the weight stage when these MMAs retire — in every CTA of the cluster, since each of them
-                    // writes a slice of the next round into this CTA's copy of the stage
-                    if (csz == 1) tc_commit(bar_w_empty + s); else tc_commit_multicast(bar_w_empty + s, cmask);
+                    tc_commit(bar_w_empty + s);          // frees the weight stage when these MMAs retire
                 }
                 tc_commit(bar_a_empty + b);
                 tc_commit(bar_acc_full + b);
@@ -275,12 +284,11 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
         // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31
         const int q = warp & 3;
         int j = 0;
-        for (int item = cid; item < n_items; item += n_clusters, ++j) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++j) {
             const int b = j & 1;
-            const int tile = item * (int)csz + (int)crank;
             mbar_wait(bar_acc_full + b, (uint32_t)((j >> 1) & 1));
             tc_fence_after();
-            if (tile < n_tiles) {
+            {
             const int r = tile * TC_TILE_ROWS + q * 32 + lane;                 // padded row of this thread
             const bool valid = tc_row_valid(r, n_boards);
             const int yrow = (r % TC_ROWS_PER_BOARD) / 7;                      // board row (stem BatchNorm index)
@@ -333,9 +341,207 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
     }
     tc_fence_before();
     __syncthreads();
-    if (csz > 1) cluster_sync_all();        // peers may still be signalling this CTA's barriers until they are done too
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
+// ---------------------------------------------------------------- tower conv3x3 on a CTA PAIR (tcgen05 cta_group::2)
+// ncu on the one-CTA kernel: every M128 N256 K16 MMA reads 4 KB of A and 8 KB of B from shared memory; at 128 B/clk that is
+// 96 clk for an instruction the tensor pipe finishes in 64, and the kernel ran exactly at that bound (65 % pipe active).
+// Here two CTAs on the two SMs of a TPC compute one 256-row x 256-channel tile pair: each CTA keeps its own 128 rows of A and
+// only HALF of the weights (128 output channels, 8 KB per K=32 stage), the pair's tensor cores exchange the B halves, so
+// every SM reads 8 KB per MMA and streams half the weight bytes from L2.
+//   warp 0 (both CTAs): operand streamer — own A tile (double buffered) and own half of every weight stage (TC2_STAGES ring)
+//   warp 1, leader CTA: issues tcgen05.mma.cta_group::2 (M = 256); its commits arrive on the barriers of BOTH CTAs
+//   warp 1, peer CTA  : relay — forwards "my A tile / my weight half has landed" to the leader's barriers
+//   warps 2-5 (both)  : epilogue of the CTA's own 128 accumulator rows (TMEM double buffered), as in k_nn_conv_tc
+#define TC2_STAGES 8
+#define TC2_STAGE_BYTES (4 * 128 * 16)                       // K = 32 (4 chunks) x 128 output channels
+#define TC2_ITERS (9 * 8)
+#define TC2_A_BYTES (TC_CHUNKS * TC_A_ROWS * 16)
+#define TC2_SMEM_BYTES (2 * TC2_A_BYTES + TC2_STAGES * TC2_STAGE_BYTES + 2 * 256 * 4 + 64 * 8 + 16)
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_nn_conv_tc2(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ wpacked2, const float* __restrict__ scale,
+              const float* __restrict__ shift, const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
+              int n_boards, int r_alloc, int n_tiles)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;                                   // 2 x TC2_A_BYTES
+    uint8_t* sB = smem + 2 * TC2_A_BYTES;                 // TC2_STAGES x TC2_STAGE_BYTES
+    float* s_scale = reinterpret_cast<float*>(sB + TC2_STAGES * TC2_STAGE_BYTES);
+    float* s_shift = s_scale + 256;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+    uint64_t* bar_a_full = bars;                          // [2] own A tile landed
+    uint64_t* bar_a_empty = bars + 2;                     // [2] MMAs reading that A buffer retired (leader commit, both CTAs)
+    uint64_t* bar_pa_full = bars + 4;                     // [2] leader only: the peer's A tile landed
+    uint64_t* bar_acc_full = bars + 6;                    // [2] accumulator complete (leader commit, both CTAs)
+    uint64_t* bar_acc_empty = bars + 8;                   // [2] leader only: drained by the 8 epilogue warps of the pair
+    uint64_t* bar_w_full = bars + 10;                     // [TC2_STAGES] own weight half landed
+    uint64_t* bar_w_empty = bars + 10 + TC2_STAGES;       // [TC2_STAGES] (leader commit, both CTAs)
+    uint64_t* bar_pw_full = bars + 10 + 2 * TC2_STAGES;   // [TC2_STAGES] leader only: the peer's weight half landed
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 64);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const bool leader = crank == 0;
+    const int n_pairs = (int)(gridDim.x >> 1), pid = (int)(blockIdx.x >> 1);
+    const int n_items = (n_tiles + 1) >> 1;               // one item = two consecutive 128-row tiles
+
+    for (int i = threadIdx.x; i < 256; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_a_full + b, 1); mbar_init(bar_a_empty + b, 1); mbar_init(bar_pa_full + b, 1);
+            mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, 8);
+        }
+        for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(bar_w_full + s, 1); mbar_init(bar_w_empty + s, 1); mbar_init(bar_pw_full + s, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- operand streamer (both CTAs)
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(in);
+            auto load_a = [&](int j, int item) {
+                int tile = 2 * item + (int)crank;
+                if (tile >= n_tiles) tile = n_tiles - 1;          // odd tile count: the peer's last tile is multiplied, never stored
+                const int b = j & 1;
+                if (j >= 2) mbar_wait_cluster(bar_a_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
+                mbar_expect_tx(bar_a_full + b, TC2_A_BYTES);
+                for (int c = 0; c < TC_CHUNKS; ++c)
+                    bulk_g2s(sA + (size_t)b * TC2_A_BYTES + (size_t)c * TC_A_ROWS * 16,
+                             src + ((size_t)c * r_alloc + (size_t)tile * TC_TILE_ROWS) * 16, TC_A_ROWS * 16, bar_a_full + b);
+            };
+            uint32_t wit = 0;
+            int j = 0;
+            if (pid < n_items) load_a(0, pid);
+            for (int item = pid; item < n_items; item += n_pairs, ++j) {
+                for (int it = 0; it < TC2_ITERS; ++it, ++wit) {
+                    const uint32_t s = wit % TC2_STAGES, k = wit / TC2_STAGES;
+                    if (k > 0) mbar_wait_cluster(bar_w_empty + s, (k - 1) & 1u);
+                    mbar_expect_tx(bar_w_full + s, TC2_STAGE_BYTES);
+                    bulk_g2s(sB + (size_t)s * TC2_STAGE_BYTES, wpacked2 + ((size_t)it * 2 + crank) * TC2_STAGE_BYTES, TC2_STAGE_BYTES, bar_w_full + s);
+                    if (it == 8 && item + n_pairs < n_items) load_a(j + 1, item + n_pairs);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ---- MMA issuer (leader CTA)
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            uint32_t wit = 0;
+            int j = 0;
+            for (int item = pid; item < n_items; item += n_pairs, ++j) {
+                const int b = j & 1;
+                mbar_wait(bar_a_full + b, (uint32_t)((j >> 1) & 1));
+                mbar_wait_cluster(bar_pa_full + b, (uint32_t)((j >> 1) & 1));
+                if (j >= 2) mbar_wait_cluster(bar_acc_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
+                tc_fence_after();
+                for (int it = 0; it < TC2_ITERS; ++it, ++wit) {
+                    const uint32_t s = wit % TC2_STAGES, k = wit / TC2_STAGES;
+                    mbar_wait(bar_w_full + s, k & 1u);
+                    mbar_wait_cluster(bar_pw_full + s, k & 1u);
+                    tc_fence_after();
+                    const int tap = it >> 3, kb = it & 7;
+                    const int sh = (tap / 3 - 1) * 7 + (tap % 3 - 1);
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const uint64_t bdesc = umma_desc(b_base + (uint32_t)(s * TC2_STAGE_BYTES + kk * 2 * 128 * 16), 128 * 16, 128);
+                        const int chunk0 = kb * 4 + kk * 2;
+                        const uint64_t adesc = umma_desc(a_base + (uint32_t)(b * TC2_A_BYTES + (chunk0 * TC_A_ROWS + TC_HALO + sh) * 16), TC_A_ROWS * 16, 128);
+                        tc2_mma_bf16(tmem_base + (uint32_t)(b * 256), adesc, bdesc, TC2_IDESC, (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    tc2_commit(bar_w_empty + s);
+                }
+                tc2_commit(bar_a_empty + b);
+                tc2_commit(bar_acc_full + b);
+            }
+        } else if (lane == 0) {
+            // ---- relay (peer CTA): tell the leader when this CTA's operands have landed
+            uint32_t wit = 0;
+            int j = 0;
+            for (int item = pid; item < n_items; item += n_pairs, ++j) {
+                const int b = j & 1;
+                mbar_wait(bar_a_full + b, (uint32_t)((j >> 1) & 1));
+                mbar_arrive_remote(bar_pa_full + b, 0u);
+                for (int it = 0; it < TC2_ITERS; ++it, ++wit) {
+                    const uint32_t s = wit % TC2_STAGES, k = wit / TC2_STAGES;
+                    mbar_wait(bar_w_full + s, k & 1u);
+                    mbar_arrive_remote(bar_pw_full + s, 0u);
+                }
+            }
+        }
+    } else {
+        // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 of this CTA's half of the pair's accumulator
+        const int q = warp & 3;
+        int j = 0;
+        for (int item = pid; item < n_items; item += n_pairs, ++j) {
+            const int b = j & 1;
+            const int tile = 2 * item + (int)crank;
+            mbar_wait_cluster(bar_acc_full + b, (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            if (tile < n_tiles) {
+                const int r = tile * TC_TILE_ROWS + q * 32 + lane;
+                const bool valid = tc_row_valid(r, n_boards);
+                const size_t cell0 = ((size_t)TC_HALO + r) * 8;
+                const size_t cstride = (size_t)r_alloc * 8;
+                uint4 skq[TC_SKIP_AHEAD];
+                if (skip) {
+#pragma unroll
+                    for (int p = 0; p < TC_SKIP_AHEAD; ++p) skq[p] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)p * cstride));
+                }
+#pragma unroll 4
+                for (int c = 0; c < TC_CHUNKS; ++c) {
+                    uint32_t v[8];
+                    tc_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c * 8), v);
+                    uint4 sk = make_uint4(0u, 0u, 0u, 0u);
+                    if (skip) {
+                        sk = skq[c % TC_SKIP_AHEAD];
+                        if (c + TC_SKIP_AHEAD < TC_CHUNKS)
+                            skq[c % TC_SKIP_AHEAD] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)(c + TC_SKIP_AHEAD) * cstride));
+                    }
+                    tc_ld_wait();
+                    const size_t cell = cell0 + (size_t)c * cstride;
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[e]), s_scale[c * 8 + e], s_shift[c * 8 + e]);
+                    if (skip) {
+                        const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sk);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(s2[e]); f[2 * e] += x.x; f[2 * e + 1] += x.y; }
+                    }
+                    uint4 o;
+                    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float x0 = valid ? fmaxf(f[2 * e], 0.0f) : 0.0f, x1 = valid ? fmaxf(f[2 * e + 1], 0.0f) : 0.0f;
+                        o2[e] = __floats2bfloat162_rn(x0, x1);
+                    }
+                    *reinterpret_cast<uint4*>(out + cell) = o;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (leader) mbar_arrive(bar_acc_empty + b); else mbar_arrive_remote(bar_acc_empty + b, 0u); }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                     // nobody leaves while the other CTA may still signal its barriers or read its operands
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -369,60 +575,86 @@ __device__ __forceinline__ float warp_sum_tc(float v)
     return v;
 }
 
+// policy + value heads for HB boards per block (the head weights, 60 KB, are read once per block instead of once per board)
+#define HB 8
 __global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __restrict__ act, int n, int r_alloc, AzHeadParams hp,
                                                       float* __restrict__ policy, float* __restrict__ value)
 {
-    __shared__ float s_pi[84], s_v[42], s_h[256], s_logit[43], s_red[8];
-    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int p = warp; p < 42; p += 8) {
-        int row = b * TC_ROWS_PER_BOARD + (p / 6) * 7 + (p % 6);
-        uint4 cell = *reinterpret_cast<const uint4*>(act + ((size_t)lane * r_alloc + TC_HALO + row) * 8);   // lane = channel chunk
+    __shared__ float s_pi[HB][84], s_v[HB][42], s_logit[HB][44], s_red[HB][8];
+    const int b0 = blockIdx.x * HB, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nb = n - b0 < HB ? n - b0 : HB;
+    // 1x1 convolutions (pi: 2 channels, v: 1 channel) + BatchNorm + ReLU; one warp per board cell, lane = channel chunk
+    float wp0[8], wp1[8], wv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const int c = lane * 8 + e; wp0[e] = hp.pi_w[c * 2]; wp1[e] = hp.pi_w[c * 2 + 1]; wv[e] = hp.v_w[c]; }
+    const float sc0 = hp.bn_pi[0] * rsqrtf(hp.bn_pi[6] + AZ_NN_BN_EPS), sc1 = hp.bn_pi[1] * rsqrtf(hp.bn_pi[7] + AZ_NN_BN_EPS);
+    const float scv = hp.bn_v[0] * rsqrtf(hp.bn_v[3] + AZ_NN_BN_EPS);
+    for (int i = warp; i < nb * 42; i += 8) {
+        const int bl = i / 42, p = i - bl * 42;
+        const int row = (b0 + bl) * TC_ROWS_PER_BOARD + (p / 6) * 7 + (p % 6);
+        const uint4 cell = *reinterpret_cast<const uint4*>(act + ((size_t)lane * r_alloc + TC_HALO + row) * 8);
         const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cell);
         float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            float2 xv = __bfloat1622float2(c2[e]);
-            int c = lane * 8 + 2 * e;
-            s0 = fmaf(xv.x, hp.pi_w[c * 2 + 0], s0); s1 = fmaf(xv.x, hp.pi_w[c * 2 + 1], s1); s2 = fmaf(xv.x, hp.v_w[c], s2);
-            s0 = fmaf(xv.y, hp.pi_w[(c + 1) * 2 + 0], s0); s1 = fmaf(xv.y, hp.pi_w[(c + 1) * 2 + 1], s1); s2 = fmaf(xv.y, hp.v_w[c + 1], s2);
+            const float2 xv = __bfloat1622float2(c2[e]);
+            s0 = fmaf(xv.x, wp0[2 * e], s0); s1 = fmaf(xv.x, wp1[2 * e], s1); s2 = fmaf(xv.x, wv[2 * e], s2);
+            s0 = fmaf(xv.y, wp0[2 * e + 1], s0); s1 = fmaf(xv.y, wp1[2 * e + 1], s1); s2 = fmaf(xv.y, wv[2 * e + 1], s2);
         }
         s0 = warp_sum_tc(s0); s1 = warp_sum_tc(s1); s2 = warp_sum_tc(s2);
         if (lane == 0) {
-            float y0 = (s0 - hp.bn_pi[4]) * (hp.bn_pi[0] * rsqrtf(hp.bn_pi[6] + AZ_NN_BN_EPS)) + hp.bn_pi[2];
-            float y1 = (s1 - hp.bn_pi[5]) * (hp.bn_pi[1] * rsqrtf(hp.bn_pi[7] + AZ_NN_BN_EPS)) + hp.bn_pi[3];
-            float yv = (s2 - hp.bn_v[2]) * (hp.bn_v[0] * rsqrtf(hp.bn_v[3] + AZ_NN_BN_EPS)) + hp.bn_v[1];
-            s_pi[p * 2 + 0] = fmaxf(y0, 0.0f); s_pi[p * 2 + 1] = fmaxf(y1, 0.0f); s_v[p] = fmaxf(yv, 0.0f);
+            s_pi[bl][p * 2 + 0] = fmaxf((s0 - hp.bn_pi[4]) * sc0 + hp.bn_pi[2], 0.0f);
+            s_pi[bl][p * 2 + 1] = fmaxf((s1 - hp.bn_pi[5]) * sc1 + hp.bn_pi[3], 0.0f);
+            s_v[bl][p] = fmaxf((s2 - hp.bn_v[2]) * scv + hp.bn_v[1], 0.0f);
         }
     }
     __syncthreads();
+    // dense 84 -> 43 (policy logits): thread = output, weights reused over the block's boards
     if (threadIdx.x < 43) {
-        float s = hp.dense_b[threadIdx.x];
-        for (int k = 0; k < 84; ++k) s = fmaf(s_pi[k], hp.dense_w[k * 43 + threadIdx.x], s);
-        s_logit[threadIdx.x] = s;
+        float acc[HB];
+#pragma unroll
+        for (int bl = 0; bl < HB; ++bl) acc[bl] = hp.dense_b[threadIdx.x];
+        for (int k = 0; k < 84; ++k) {
+            const float w = hp.dense_w[k * 43 + threadIdx.x];
+#pragma unroll
+            for (int bl = 0; bl < HB; ++bl) acc[bl] = fmaf(s_pi[bl][k], w, acc[bl]);
+        }
+#pragma unroll
+        for (int bl = 0; bl < HB; ++bl) s_logit[bl][threadIdx.x] = acc[bl];
     }
+    // dense 42 -> 256 + ReLU, then 256 -> 1 (value)
     {
-        float s = hp.dense1_b[threadIdx.x];
-        for (int k = 0; k < 42; ++k) s = fmaf(s_v[k], hp.dense1_w[k * 256 + threadIdx.x], s);
-        s_h[threadIdx.x] = fmaxf(s, 0.0f);
+        float acc[HB];
+#pragma unroll
+        for (int bl = 0; bl < HB; ++bl) acc[bl] = hp.dense1_b[threadIdx.x];
+        for (int k = 0; k < 42; ++k) {
+            const float w = hp.dense1_w[k * 256 + threadIdx.x];
+#pragma unroll
+            for (int bl = 0; bl < HB; ++bl) acc[bl] = fmaf(s_v[bl][k], w, acc[bl]);
+        }
+        const float w2 = hp.dense2_w[threadIdx.x];
+#pragma unroll
+        for (int bl = 0; bl < HB; ++bl) {
+            const float part = warp_sum_tc(fmaxf(acc[bl], 0.0f) * w2);
+            if (lane == 0) s_red[bl][warp] = part;
+        }
     }
     __syncthreads();
-    float part = warp_sum_tc(s_h[threadIdx.x] * hp.dense2_w[threadIdx.x]);
-    if (lane == 0) s_red[warp] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = hp.dense2_b[0];
-        for (int i = 0; i < 8; ++i) s += s_red[i];
-        value[b] = tanhf(s);
+    if (threadIdx.x < nb) {
+        float sum = hp.dense2_b[0];
+        for (int i = 0; i < 8; ++i) sum += s_red[threadIdx.x][i];
+        value[b0 + threadIdx.x] = tanhf(sum);
     }
-    if (warp == 0) {
-        float l0 = s_logit[lane], l1 = lane < 11 ? s_logit[32 + lane] : -INFINITY;
+    // softmax: one warp per board
+    for (int bl = warp; bl < nb; bl += 8) {
+        const float l0 = s_logit[bl][lane], l1 = lane < 11 ? s_logit[bl][32 + lane] : -INFINITY;
         float mx = fmaxf(l0, l1);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float e0 = expf(l0 - mx), e1 = lane < 11 ? expf(l1 - mx) : 0.0f;
-        float sum = warp_sum_tc(e0 + e1);
-        policy[(size_t)b * 43 + lane] = e0 / sum;
-        if (lane < 11) policy[(size_t)b * 43 + 32 + lane] = e1 / sum;
+        const float e0 = expf(l0 - mx), e1 = lane < 11 ? expf(l1 - mx) : 0.0f;
+        const float sum = warp_sum_tc(e0 + e1);
+        policy[(size_t)(b0 + bl) * 43 + lane] = e0 / sum;
+        if (lane < 11) policy[(size_t)(b0 + bl) * 43 + 32 + lane] = e1 / sum;
     }
 }
 
@@ -446,18 +678,39 @@ static void pack_conv(const float* w, int cin, int kch, __nv_bfloat16* dst)
                     }
 }
 
-// persistent launch of one tower / stem convolution; csz > 1 = thread-block clusters with multicast weight streaming
-template <int KCH, bool ROW_BN>
-static cudaError_t launch_conv(int grid, int csz, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w, const float* scale, const float* shift,
-                               const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles)
+// HWIO fp32 [3][3][256][256] -> bf16 [tap][K block of 32][half of the output channels][chunk 4][128 out][8]: one 8 KB stage per CTA of a pair
+static void pack_conv_pair(const float* w, __nv_bfloat16* dst)
+{
+    for (int tap = 0; tap < 9; ++tap)
+        for (int kb = 0; kb < 8; ++kb)
+            for (int h = 0; h < 2; ++h)
+                for (int ch = 0; ch < 4; ++ch)
+                    for (int n = 0; n < 128; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            const int ci = (kb * 4 + ch) * 8 + e, co = h * 128 + n;
+                            dst[(((((size_t)tap * 8 + kb) * 2 + h) * 4 + ch) * 128 + n) * 8 + e] = __float2bfloat16_rn(w[((size_t)tap * 256 + ci) * 256 + co]);
+                        }
+}
+
+static cudaError_t launch_conv_pair(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w2, const float* scale, const float* shift,
+                                    const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles)
 {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcShape<KCH>::SMEM_BYTES; cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC2_SMEM_BYTES; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = csz > 1 ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc<KCH, ROW_BN>, in, w, scale, shift, skip, out, n_boards, r_alloc, n_tiles);
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc2, in, w2, scale, shift, skip, out, n_boards, r_alloc, n_tiles);
+}
+
+// persistent launch of one stem / one-CTA tower convolution
+template <int KCH, bool ROW_BN>
+static cudaError_t launch_conv(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w, const float* scale, const float* shift,
+                               const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles)
+{
+    k_nn_conv_tc<KCH, ROW_BN><<<grid, TC_THREADS, TcShape<KCH>::SMEM_BYTES, s>>>(in, w, scale, shift, skip, out, n_boards, r_alloc, n_tiles);
+    return cudaGetLastError();
 }
 
 int az_nn_tc_prepare(az_nn* nn)
@@ -466,6 +719,7 @@ int az_nn_tc_prepare(az_nn* nn)
     AzTcState* tc = nn->tc;
     const int layers = 2 * nn->blocks;
     std::vector<uint8_t> packed((size_t)layers * TC_LAYER_BYTES + TC_STEM_BYTES);
+    std::vector<uint8_t> packed2((size_t)layers * TC_LAYER_BYTES);
     std::vector<float> scale((size_t)(layers + 1) * 256, 0.0f), shift((size_t)(layers + 1) * 256, 0.0f);
     for (int L = 0; L < layers; ++L) {
         std::string sfx = tc_block_name(L / 2) + ((L & 1) ? "_branch2b" : "_branch2a");
@@ -480,6 +734,7 @@ int az_nn_tc_prepare(az_nn* nn)
             scale[(size_t)L * 256 + c] = sc; shift[(size_t)L * 256 + c] = be[c] - mu[c] * sc;
         }
         pack_conv(w, 256, 32, reinterpret_cast<__nv_bfloat16*>(packed.data() + (size_t)L * TC_LAYER_BYTES));
+        pack_conv_pair(w, reinterpret_cast<__nv_bfloat16*>(packed2.data() + (size_t)L * TC_LAYER_BYTES));
     }
     {   // stem: conv/kernel [3][3][13][256], BatchNorm over the 7 board rows
         const float* w = az_nn_host_var(nn, "conv/kernel");
@@ -496,37 +751,34 @@ int az_nn_tc_prepare(az_nn* nn)
     }
     if (!tc->d_wpacked) {
         AZ_CUDA(cudaMalloc(&tc->d_wpacked, packed.size()));
+        AZ_CUDA(cudaMalloc(&tc->d_wpacked2, packed2.size()));
         AZ_CUDA(cudaMalloc(&tc->d_scale, scale.size() * sizeof(float)));
         AZ_CUDA(cudaMalloc(&tc->d_shift, shift.size() * sizeof(float)));
         AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<32>::SMEM_BYTES));
         AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::SMEM_BYTES));
+        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
         int dev = 0, sms = 148;
         AZ_CUDA(cudaGetDevice(&dev));
         AZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         tc->n_sm = sms;
         if (const char* eg = getenv("AZ_TC_GRID")) { int g = atoi(eg); if (g >= 1 && g < sms) tc->n_sm = sms = g; }   // experiment knob: fewer persistent CTAs
-        // cluster size of the tower kernel: AZ_TC_CLUSTER = 1 (default) | 2 | 4; the grid is the number of clusters the
-        // device can hold at once (GPC sizes need not be multiples of the cluster size) times the cluster size.
-        // Measured on B200 (batch 4096, 5 blocks): 2.75 / 2.74 / 2.91 ms per forward for 1 / 2 / 4 — multicast weight
-        // streaming buys nothing, the kernel is bound by the MMA's own shared-memory operand reads (profiles/README.md)
-        const char* ev = getenv("AZ_TC_CLUSTER");
-        int csz = ev ? atoi(ev) : 1;
-        if (csz != 1 && csz != 2 && csz != 4) csz = 1;
-        tc->cluster = csz; tc->max_clusters = sms / csz;
-        if (csz > 1) {
+        {   // CTA pairs the device can hold at once
+            const char* em = getenv("AZ_TC_MODE");
+            tc->pair_mode = !(em && strcmp(em, "single") == 0);
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(sms / csz * csz)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TcShape<32>::SMEM_BYTES;
+            cfg.gridDim = dim3((unsigned)(sms / 2 * 2)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC2_SMEM_BYTES;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = (unsigned)csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             int nc = 0;
-            AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc<32, false>, &cfg));
-            if (nc < 1) { tc->cluster = 1; tc->max_clusters = sms; }
-            else tc->max_clusters = nc < sms / csz ? nc : sms / csz;
+            AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc2, &cfg));
+            tc->max_pairs = nc < sms / 2 ? nc : sms / 2;
+            if (tc->max_pairs < 1) tc->pair_mode = 0;
         }
     }
     AZ_CUDA(cudaMemcpy(tc->d_wpacked, packed.data(), packed.size(), cudaMemcpyHostToDevice));
+    AZ_CUDA(cudaMemcpy(tc->d_wpacked2, packed2.data(), packed2.size(), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_scale, scale.data(), scale.size() * sizeof(float), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_shift, shift.data(), shift.size() * sizeof(float), cudaMemcpyHostToDevice));
     return AZ_OK;
@@ -537,7 +789,7 @@ void az_nn_tc_release(az_nn* nn)
     if (!nn->tc) return;
     AzTcState* tc = nn->tc;
     for (int i = 0; i < 3; ++i) cudaFree(tc->d_act[i]);
-    cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_scale); cudaFree(tc->d_shift); cudaFree(tc->d_x);
+    cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_wpacked2); cudaFree(tc->d_scale); cudaFree(tc->d_shift); cudaFree(tc->d_x);
     delete tc;
     nn->tc = nullptr;
 }
@@ -573,24 +825,30 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
     // buffers are sized for cap_boards; only the tiles that hold boards of this call are computed
     const int tiles = (n * TC_ROWS_PER_BOARD + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     const int grid = tiles < tc->n_sm ? tiles : tc->n_sm;
-    const int csz = tc->cluster;
-    const int items = (tiles + csz - 1) / csz;
-    const int tgrid = (items < tc->max_clusters ? items : tc->max_clusters) * csz;     // tower: whole clusters, all co-resident
     const int layers = 2 * nn->blocks;
     int cur = 0, tmp = 1, nxt = 2;
     k_nn_pack_input_tc<<<(n * 42 + 255) / 256, 256, 0, s>>>(d_x, n, tc->d_in, tc->r_alloc);
     AZ_CUDA(cudaGetLastError());
-    AZ_CUDA((launch_conv<2, true>(grid, 1, s, tc->d_in, tc->d_wpacked + (size_t)layers * TC_LAYER_BYTES, tc->d_scale + layers * 256,
+    AZ_CUDA((launch_conv<2, true>(grid, s, tc->d_in, tc->d_wpacked + (size_t)layers * TC_LAYER_BYTES, tc->d_scale + layers * 256,
                                   tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n, tc->r_alloc, tiles)));
+    const int pitems = (tiles + 1) / 2;
+    const int pgrid = 2 * (pitems < tc->max_pairs ? pitems : tc->max_pairs);
     for (int i = 0; i < nn->blocks; ++i) {
         const int L0 = 2 * i, L1 = 2 * i + 1;
-        AZ_CUDA((launch_conv<32, false>(tgrid, csz, s, tc->d_act[cur], tc->d_wpacked + (size_t)L0 * TC_LAYER_BYTES, tc->d_scale + L0 * 256,
-                                        tc->d_shift + L0 * 256, nullptr, tc->d_act[tmp], n, tc->r_alloc, tiles)));
-        AZ_CUDA((launch_conv<32, false>(tgrid, csz, s, tc->d_act[tmp], tc->d_wpacked + (size_t)L1 * TC_LAYER_BYTES, tc->d_scale + L1 * 256,
-                                        tc->d_shift + L1 * 256, tc->d_act[cur], tc->d_act[nxt], n, tc->r_alloc, tiles)));
+        if (tc->pair_mode) {
+            AZ_CUDA(launch_conv_pair(pgrid, s, tc->d_act[cur], tc->d_wpacked2 + (size_t)L0 * TC_LAYER_BYTES, tc->d_scale + L0 * 256,
+                                     tc->d_shift + L0 * 256, nullptr, tc->d_act[tmp], n, tc->r_alloc, tiles));
+            AZ_CUDA(launch_conv_pair(pgrid, s, tc->d_act[tmp], tc->d_wpacked2 + (size_t)L1 * TC_LAYER_BYTES, tc->d_scale + L1 * 256,
+                                     tc->d_shift + L1 * 256, tc->d_act[cur], tc->d_act[nxt], n, tc->r_alloc, tiles));
+        } else {
+            AZ_CUDA((launch_conv<32, false>(grid, s, tc->d_act[cur], tc->d_wpacked + (size_t)L0 * TC_LAYER_BYTES, tc->d_scale + L0 * 256,
+                                            tc->d_shift + L0 * 256, nullptr, tc->d_act[tmp], n, tc->r_alloc, tiles)));
+            AZ_CUDA((launch_conv<32, false>(grid, s, tc->d_act[tmp], tc->d_wpacked + (size_t)L1 * TC_LAYER_BYTES, tc->d_scale + L1 * 256,
+                                            tc->d_shift + L1 * 256, tc->d_act[cur], tc->d_act[nxt], n, tc->r_alloc, tiles)));
+        }
         int o = cur; cur = nxt; nxt = o;
     }
-    k_nn_heads_tc<<<n, 256, 0, s>>>(tc->d_act[cur], n, tc->r_alloc, az_nn_head_params(nn), d_policy, d_value);
+    k_nn_heads_tc<<<(n + HB - 1) / HB, 256, 0, s>>>(tc->d_act[cur], n, tc->r_alloc, az_nn_head_params(nn), d_policy, d_value);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
