@@ -39,6 +39,16 @@ def measured_peaks():
     return 6650.0, 1400.0, "fallback"
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        d = json.load(open(p)).get(kernel)
+        return None if d is None else float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 class ClockSampler:
     """samples nvidia-smi clocks / throttle reasons of one GPU during the timed region"""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -223,12 +233,16 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
     mc.counters(reset=True, stream=sptr)
     steps = max(2, min(args.steps, args.sp_steps))
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     barrier()
     for i in range(steps):
         ev[i][0].record(stream)
         mc.selfplay(moves_per_step, stream=sptr)      # working set (node pools + activations) is far larger than L2
         ev[i][1].record(stream)
     barrier()
+    sp_clocks = sampler.stop() if rank == 0 else None
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     cnt = mc.counters(stream=sptr)
     # e2e: one az_mcts_search call per move through the host-buffer ABI (visit counts, pi, moves, status copied back)
@@ -258,9 +272,13 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
                                     "per batch), %d-block graph, random-init weights (seed 1234), bf16 tcgen05 forward, %d moves per step"
                                     % (n, sims, blocks, moves_per_step), "games_per_gpu": n, "sims_per_move": sims, "blocks": blocks},
                 roofline={"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
-                          "traffic": None, "peak_source": src + " (sustained cuBLAS bf16)",
+                          "traffic": ncu_traffic("k_nn_conv_tc2"), "peak_source": src + " (sustained cuBLAS bf16)",
+                          "executed_frac": achieved_tf * 56.0 / 42.0 / tf_peak,
                           "note": "conventional FLOPs/position (0.4981 G for 5 blocks) x positions pushed through the tower / whole-step device "
-                                  "time (tree kernels, encode and heads included in the time)"},
+                                  "time (tree kernels, encode and heads included in the time); the padded board layout executes 56/42 of "
+                                  "that (executed_frac); the forward runs at the board's 1 kW power cap (clocks.reasons: sw_power_cap), "
+                                  "like the cuBLAS run the peak comes from; traffic = DRAM bytes of one tower-layer launch (ncu)"},
+                clocks=sp_clocks,
                 e2e={"value": n * sims * e2e_moves * world / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": 0,
                      "d2h_bytes_per_step": n * (43 * 8 + 2), "steps": e2e_moves},
                 gpu_launches=steps * moves_per_step * (2 + (sims + 1) * (2 + 1 + 2 * blocks + 1 + 1)),
@@ -324,8 +342,9 @@ def run_ours(args):
     h_out = torch.empty((n, 160), dtype=torch.uint8).pin_memory()
     env.reset(SEED, stream=sptr)
     env.export_aos(out=h_in.numpy(), stream=sptr)
-    for _ in range(2):
+    for _ in range(2):        # every step continues from the images the previous step exported (host buffers swap roles)
         env.import_aos(h_in.numpy(), stream=sptr); env.rollout(S, stream=sptr); env.export_aos(out=h_out.numpy(), stream=sptr)
+        h_in, h_out = h_out, h_in
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -333,6 +352,7 @@ def run_ours(args):
         env.rollout(S, stream=sptr)
         env.export_aos(out=h_out.numpy(), stream=sptr)
         env.counters(stream=sptr)
+        h_in, h_out = h_out, h_in
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -358,9 +378,10 @@ def run_ours(args):
                             "games_per_gpu": n, "lockstep_moves_per_step": S, "l2": "256 MiB flush between timed iterations",
                             "sharding": "games by contiguous global id, no data-path collective"},
                     roofline={"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                              "traffic": None, "peak_source": src,
+                              "traffic": ncu_traffic("k_env_rollout"), "peak_source": src,
                               "note": "algorithmic 330 B/step x games x moves per launch / CUDA-event time of k_env_rollout; the state "
-                                      "stays on chip between the moves of one launch, so this is not DRAM traffic"},
+                                      "stays on chip between the moves of one launch (traffic = the ncu DRAM bytes of one launch: the "
+                                      "64 B/game SoA state read once), so this is an issue-bound kernel, not a DRAM-bound one"},
                     e2e={"value": n * S * e2e_steps * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": n * 160,
                          "d2h_bytes_per_step": n * 160 + 64, "steps": e2e_steps},
                     gpu_launches=args.steps, wall_ms_timed_region=wall_ms, clocks=clocks,
