@@ -90,6 +90,9 @@ def lib():
         L.az_mcts_root_stats.argtypes = [vp, vp, vp, vp, vp, vp, vp]
         L.az_selfplay_run.argtypes = [vp, C.c_int, vp]
         L.az_mcts_counters.argtypes = [vp, C.POINTER(AzCounters), C.POINTER(C.c_uint64), C.c_int, vp]
+        L.az_selfplay_record.argtypes = [vp, C.c_size_t, C.c_int]
+        L.az_selfplay_samples.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), vp]
+        L.az_samples_write_file.argtypes = [C.c_char_p, vp, C.c_size_t]
         _lib = L
     return _lib
 
@@ -261,6 +264,14 @@ class Net:
 
 
 EVAL_NN, EVAL_PSEUDO, EVAL_UNIFORM = 0, 1, 2
+SAMPLE_BYTES = 265
+
+
+def write_samples_file(path, records):
+    """NNTrainDataStorage::saveTrainingSamples file (az_samples_write_file)"""
+    a = np.ascontiguousarray(records, np.uint8).reshape(-1, SAMPLE_BYTES)
+    check(lib().az_samples_write_file(path.encode(), _ptr(a) if len(a) else None, C.c_size_t(len(a))))
+
 PICK_ARGMAX, PICK_SELFPLAY = 0, 1
 
 
@@ -305,6 +316,18 @@ class Mcts:
 
     def selfplay(self, n_moves, stream=None):
         check(self.L.az_selfplay_run(self.h, int(n_moves), stream))
+
+    def record(self, capacity_samples, max_moves_per_game=1024):
+        """enable training-sample recording (az_selfplay_record)"""
+        check(self.L.az_selfplay_record(self.h, C.c_size_t(int(capacity_samples)), int(max_moves_per_game)))
+
+    def samples(self, stream=None):
+        """finished-game samples as a [k, 265] uint8 array (reference file layout per record) and the dropped count"""
+        n, dropped = C.c_size_t(0), C.c_uint64(0)
+        check(self.L.az_selfplay_samples(self.h, None, C.c_size_t(0), C.byref(n), C.byref(dropped), stream))
+        out = np.empty((n.value, SAMPLE_BYTES), np.uint8)
+        check(self.L.az_selfplay_samples(self.h, _ptr(out) if n.value else None, C.c_size_t(n.value), C.byref(n), C.byref(dropped), stream))
+        return out[:n.value], int(dropped.value)
 
     def counters(self, reset=False, stream=None):
         c, err = AzCounters(), C.c_uint64(0)

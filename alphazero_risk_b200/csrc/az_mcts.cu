@@ -15,6 +15,7 @@
 // written by the 32 lanes as coalesced rows; PUCT argmax and hash-window probing are warp
 // reductions; the float operations use explicit _rn intrinsics (and the TU is built with
 // -fmad=false) so every rounding matches the reference's x86 build bit for bit.
+#include <cstdio>
 #include <cstring>
 #include <new>
 
@@ -34,6 +35,7 @@
 #define FULL 0xffffffffu
 
 enum { EVAL_NN = 0, EVAL_PSEUDO = 1, EVAL_UNIFORM = 2 };
+#define REC_BYTES AZ_SAMPLE_BYTES
 enum { CNT_SIMS = 0, CNT_EVALS = 1, CNT_POOL_OVERFLOW = 2, CNT_DEPTH_OVERFLOW = 3, CNT_STEPS = 4, CNT_GAMES = 5, CNT_W0 = 6, CNT_W1 = 7, CNT_DRAW = 8, CNT_ILLEGAL = 9, CNT_N = 12 };
 
 struct MctsDev {
@@ -55,6 +57,13 @@ struct MctsDev {
     uint8_t* extra_trim;    // [n] trims to add before the next search (play-mode turn start / new game)
     uint32_t* out_visits; float* out_pi; float* out_q; float* out_p; uint8_t* out_move; float* out_value; uint32_t* out_sumn; int32_t* out_table; int8_t* out_status;
     unsigned long long* counters;
+    // self-play sample recording (NNTrainData, alphazero_nn_data.h:112-121): per-game staging until the game ends
+    uint32_t* rec_state;    // [n][rec_moves][14]   root state before the move
+    float* rec_pi;          // [n][rec_moves][43]   policy target
+    uint32_t* rec_len;      // [n]                  staged samples of the running game (> rec_moves = overflowed)
+    uint8_t* rec_out;       // [rec_cap][265]       finished games, packed records in the reference's file layout
+    unsigned long long* rec_count;   // [2]         records in rec_out, samples dropped (staging or output full)
+    int rec_moves; unsigned long long rec_cap;
     float c1, c2, cpuct;
     uint64_t seed; uint32_t first_game;
     AzRulesDev rules;
@@ -313,6 +322,89 @@ __device__ __forceinline__ void descend(const MctsDev& m, int gi, uint32_t cur, 
     __syncwarp();
 }
 
+
+// ---------------------------------------------------------------- self-play samples
+// One record = what NNTrainDataStorage::saveTrainingSamples writes per sample (alphazero_nn_data.cpp:115-138):
+//   int8 playerIndex | NNInputData (88 B, alphazero_nn_data.h:73-101, g++ x86-64 layout) | float value | float policy[43]
+// NNInputData: land[42] @0, playerIndex @42, round u16 @44, then 10 floats @48: reinforcementShare, attackFrequency, canDrawCard,
+// phase one-hot x 6, armyShare (alphazero_nn_data.cpp:165-196); the three padding bytes (43, 46, 47) are written as zero.
+// Called by the game's warp when the game has ended with `status` (NNTrainDataStorage::updateValues, alphazero_nn_data.cpp:51-65).
+__device__ __noinline__ void rec_flush(const MctsDev& m, int gi, int status, uint8_t* s_rec, int lane)
+{
+    const uint32_t len = m.rec_len[gi];
+    if (len == 0) return;
+    unsigned long long base = 0;
+    bool ok = len <= (uint32_t)m.rec_moves;
+    if (lane == 0) {
+        if (ok) { base = atomicAdd(&m.rec_count[0], (unsigned long long)len); if (base + len > m.rec_cap) ok = false; }
+        if (!ok) atomicAdd(&m.rec_count[1], (unsigned long long)len);
+    }
+    ok = __shfl_sync(FULL, (int)ok, 0) != 0;
+    base = ((unsigned long long)__shfl_sync(FULL, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(FULL, (uint32_t)base, 0);
+    if (ok) {
+        for (uint32_t i = 0; i < len; ++i) {
+            const uint32_t* st = m.rec_state + ((size_t)gi * m.rec_moves + i) * 14;
+            const float* pi = m.rec_pi + ((size_t)gi * m.rec_moves + i) * AZ_MOVES;
+            __syncwarp();
+            uint32_t w = lane < 14 ? st[lane] : 0u;
+            // land bytes: lanes 0..10 hold words 0..10
+            const uint32_t w10 = __shfl_sync(FULL, w, 10), w11 = __shfl_sync(FULL, w, 11), w12 = __shfl_sync(FULL, w, 12), w13 = __shfl_sync(FULL, w, 13);
+            AzGame g; g.own0 = g.own1 = g.gt1 = g.full = 0;
+            az_unpack_scalars(g, w10, w11, w12, w13);
+            int t0 = 0, t1 = 0;
+            uint64_t o0 = 0, o1 = 0;
+            if (lane < 11) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int l = lane * 4 + b;
+                    if (l < AZ_LANDS) {
+                        const uint32_t v = (w >> (8 * b)) & 0xffu;
+                        if ((v >> 6) == 0) { t0 += (int)(v & 63u); o0 |= 1ull << l; }
+                        if ((v >> 6) == 1) { t1 += (int)(v & 63u); o1 |= 1ull << l; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                t0 += __shfl_xor_sync(FULL, t0, o); t1 += __shfl_xor_sync(FULL, t1, o);
+                o0 |= ((uint64_t)__shfl_xor_sync(FULL, (uint32_t)(o0 >> 32), o) << 32) | __shfl_xor_sync(FULL, (uint32_t)o0, o);
+                o1 |= ((uint64_t)__shfl_xor_sync(FULL, (uint32_t)(o1 >> 32), o) << 32) | __shfl_xor_sync(FULL, (uint32_t)o1, o);
+            }
+            const uint32_t cur = g.cur;
+            const float ref = (float)az_reinforcement_value(cur ? o1 : o0), eref = (float)az_reinforcement_value(cur ? o0 : o1);
+            const float ta = (float)(cur ? t1 : t0), eta = (float)(cur ? t0 : t1);
+            float att = __fdiv_rn((float)g.attacks, 8.0f); att = att < 1.0f ? att : 1.0f;
+            // assemble the 265 bytes in shared memory (4-byte fields of the record are not 4-byte aligned in the file)
+            if (lane < 11) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) { const int l = lane * 4 + b; if (l < AZ_LANDS) s_rec[1 + l] = (uint8_t)(w >> (8 * b)); }
+            }
+            if (lane == 11) {
+                s_rec[0] = (uint8_t)cur;
+                s_rec[1 + 42] = (uint8_t)cur; s_rec[1 + 43] = 0;
+                s_rec[1 + 44] = (uint8_t)(g.round & 0xffu); s_rec[1 + 45] = (uint8_t)(g.round >> 8); s_rec[1 + 46] = 0; s_rec[1 + 47] = 0;
+            }
+            float f = 0.0f; int foff = -1;
+            if (lane == 12) { f = __fdiv_rn(ref, __fadd_rn(ref, eref)); foff = 1 + 48; }
+            if (lane == 13) { f = att; foff = 1 + 52; }
+            if (lane == 14) { f = g.allow_draw ? 1.0f : 0.0f; foff = 1 + 56; }
+            if (lane >= 15 && lane <= 20) { f = g.phase == (uint32_t)(lane - 15) ? 1.0f : 0.0f; foff = 1 + 60 + 4 * (lane - 15); }
+            if (lane == 21) { f = __fdiv_rn(ta, __fadd_rn(ta, eta)); foff = 1 + 84; }
+            if (lane == 22) { f = status == AZ_STATUS_DRAW ? 0.0f : ((uint32_t)status == cur ? 1.0f : -1.0f); foff = 1 + 88; }
+            if (foff >= 0) { const uint32_t u = __float_as_uint(f); for (int b = 0; b < 4; ++b) s_rec[foff + b] = (uint8_t)(u >> (8 * b)); }
+            for (int k = lane; k < AZ_MOVES; k += 32) {
+                const uint32_t u = __float_as_uint(pi[k]);
+                for (int b = 0; b < 4; ++b) s_rec[93 + 4 * k + b] = (uint8_t)(u >> (8 * b));
+            }
+            __syncwarp();
+            uint8_t* dst = m.rec_out + (base + i) * REC_BYTES;
+            for (int k = lane; k < REC_BYTES; k += 32) dst[k] = s_rec[k];
+        }
+    }
+    __syncwarp();
+    if (lane == 0) m.rec_len[gi] = 0;
+}
+
 // StateSimulationsStorage::trimNodes (:229-245) as an epoch bump; `extra` additional trims
 // (AlphaZeroPlayer::takeTurn's turn-start trim, alphazero_player.cpp:5; clearNodes on newGame :31-34)
 __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_begin(MctsDev m, int extra_all)
@@ -354,6 +446,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_finish(MctsDev m, cons
 {
     __shared__ uint64_t s_tab[AZ_TABLE_U64];
     __shared__ WarpSmem s_w;
+    __shared__ uint8_t s_rec[MCTS_WARPS][272];
     for (int i = threadIdx.x; i < AZ_TABLE_U64; i += blockDim.x) s_tab[i] = g_tab[i];
     __syncthreads();
     AzTables T = az_tables_from_smem(s_tab);
@@ -416,6 +509,17 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_finish(MctsDev m, cons
                 m.out_table[gi] = (int32_t)(m.count[gi * 2 + cur] + m.count[gi * 2 + (cur ^ 1u)] - m.migrated[gi]);
             }
         }
+        if (apply_move && m.rec_out) {
+            // threadExecuteTrainingGame pushes (player, NNInputData(rootState), policy) before the move, alphazero_trainer.cpp:108
+            const uint32_t k = m.rec_len[gi];
+            if (k < (uint32_t)m.rec_moves) {
+                if (lane < 14) m.rec_state[((size_t)gi * m.rec_moves + k) * 14 + lane] = w.row[lane];
+                float* rp = m.rec_pi + ((size_t)gi * m.rec_moves + k) * AZ_MOVES;
+                rp[lane] = pi0; if (lane + 32 < AZ_MOVES) rp[lane + 32] = pi1;
+            }
+            __syncwarp();
+            if (lane == 0) m.rec_len[gi] = k + 1;          // > rec_moves marks the game's samples as overflowed (dropped at the end)
+        }
         if (apply_move) {
             uint64_t vm = az_valid_moves(w.g, T, m.rules);
             AzDicePhilox dice; dice.init_with_block0(m.seed, game, ply, AZ_STREAM_REAL, blk);
@@ -428,6 +532,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_finish(MctsDev m, cons
                 atomicAdd(&m.counters[CNT_GAMES], 1ull);
                 atomicAdd(&m.counters[status == 0 ? CNT_W0 : (status == 1 ? CNT_W1 : CNT_DRAW)], 1ull);
             }
+            if (status != AZ_STATUS_RUNNING && m.rec_out) rec_flush(m, gi, status, s_rec[warp], lane);
             if (status != AZ_STATUS_RUNNING && auto_reset) {
                 __syncwarp();
                 az_new_game(w.g, w.land, m.seed, game, ply);      // threadExecuteTrainingGame starts the next game with a fresh AlphaZeroMCTS
@@ -627,6 +732,61 @@ extern "C" int az_selfplay_run(az_mcts* mc, int n_moves, void* stream)
         int rc = search_once(mc, 0, 1, 1, 1, (cudaStream_t)stream);
         if (rc) return rc;
     }
+    return AZ_OK;
+}
+
+// ---- self-play samples
+extern "C" int az_selfplay_record(az_mcts* mc, size_t capacity_samples, int max_moves_per_game)
+{
+    AZ_REQUIRE(mc != nullptr, "mcts is NULL");
+    AZ_REQUIRE(capacity_samples > 0 && max_moves_per_game > 0, "capacity_samples and max_moves_per_game must be positive");
+    AZ_REQUIRE(mc->d.rec_out == nullptr, "recording is already enabled on this handle");
+    AzDeviceGuard guard(mc->device);
+    MctsDev& d = mc->d;
+    size_t n = (size_t)d.n;
+    int rc = 0;
+    rc |= dalloc(mc, &d.rec_state, n * (size_t)max_moves_per_game * 14, false);
+    rc |= dalloc(mc, &d.rec_pi, n * (size_t)max_moves_per_game * AZ_MOVES, false);
+    rc |= dalloc(mc, &d.rec_len, n);
+    rc |= dalloc(mc, &d.rec_count, (size_t)2);
+    uint8_t* out = nullptr;
+    rc |= dalloc(mc, &out, capacity_samples * (size_t)REC_BYTES, false);
+    if (rc) { d.rec_out = nullptr; return AZ_ERR_CUDA; }
+    d.rec_moves = max_moves_per_game; d.rec_cap = capacity_samples;
+    d.rec_out = out;                                   // set last: the kernels record iff rec_out != NULL
+    return AZ_OK;
+}
+
+extern "C" int az_selfplay_samples(az_mcts* mc, uint8_t* h_records, size_t max_records, size_t* n_out, uint64_t* h_dropped, void* stream)
+{
+    AZ_REQUIRE(mc && n_out, "NULL argument");
+    AZ_REQUIRE(mc->d.rec_out != nullptr, "az_selfplay_record has not been called");
+    AzDeviceGuard guard(mc->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long h[2];
+    AZ_CUDA(cudaMemcpyAsync(h, mc->d.rec_count, sizeof h, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    size_t have = (size_t)(h[0] < mc->d.rec_cap ? h[0] : mc->d.rec_cap);   // reservations past the capacity were dropped (and counted)
+    if (h_dropped) *h_dropped = h[1];
+    *n_out = have;
+    if (!h_records) return AZ_OK;                      // size query
+    AZ_REQUIRE(max_records >= have, "h_records is too small: query the size with h_records = NULL first");
+    if (have) AZ_CUDA(cudaMemcpyAsync(h_records, mc->d.rec_out, have * (size_t)REC_BYTES, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemsetAsync(mc->d.rec_count, 0, sizeof h, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+// NNTrainDataStorage::saveTrainingSamples (alphazero_nn_data.cpp:115-138): size_t count, then the packed records
+extern "C" int az_samples_write_file(const char* path, const uint8_t* h_records, size_t n)
+{
+    AZ_REQUIRE(path && (h_records || n == 0), "NULL argument");
+    FILE* f = fopen(path, "wb");
+    if (!f) { az_set_error("cannot open %s for writing", path); return AZ_ERR_INVALID_ARG; }
+    uint64_t count = (uint64_t)n;                      // sizeof(size_t) == 8 on the reference's platform
+    bool ok = fwrite(&count, sizeof count, 1, f) == 1 && (n == 0 || fwrite(h_records, REC_BYTES, n, f) == n);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { az_set_error("short write to %s", path); return AZ_ERR_INVALID_ARG; }
     return AZ_OK;
 }
 

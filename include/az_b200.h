@@ -190,6 +190,19 @@ AZ_API int az_mcts_root_stats(az_mcts* mcts, float* h_q, float* h_p, uint32_t* h
 /* n_moves lockstep self-play moves with no host synchronisation (threadExecuteTrainingGame,
    alphazero_trainer.cpp:80-119): search, temperature-rule move, real move, finished games re-dealt */
 AZ_API int az_selfplay_run(az_mcts* mcts, int n_moves, void* stream);
+/* ---- self-play training samples.  threadExecuteTrainingGame pushes NNTrainData(player, NNInputData(rootState),
+   policy) before every real move (alphazero_trainer.cpp:108) and NNTrainDataStorage::updateValues fills the values when the game
+   ends (neural_network/alphazero_nn_data.cpp:51-65).  One record = what saveTrainingSamples writes per sample (:115-138):
+   int8 playerIndex | NNInputData (88 B, alphazero_nn_data.h:73-101; padding bytes 43, 46, 47 written as 0) | float value |
+   float policy[43], packed, 265 bytes. */
+#define AZ_SAMPLE_BYTES 265
+/* enable recording in az_selfplay_run / az_mcts_search(apply_move): device staging of max_moves_per_game samples per running game
+   and an output queue of capacity_samples records of FINISHED games (samples that do not fit are counted as dropped) */
+AZ_API int az_selfplay_record(az_mcts* mcts, size_t capacity_samples, int max_moves_per_game);
+/* copies the queued records to h_records (NULL = only report the count in *n_out) and empties the queue */
+AZ_API int az_selfplay_samples(az_mcts* mcts, uint8_t* h_records, size_t max_records, size_t* n_out, uint64_t* h_dropped, void* stream);
+/* NNTrainDataStorage::saveTrainingSamples file: size_t count, then the records (readable by the reference's trainer) */
+AZ_API int az_samples_write_file(const char* path, const uint8_t* h_records, size_t n);
 /* counters since the last reset; *h_errors = node-pool + path-depth overflows (must be 0) */
 AZ_API int az_mcts_counters(az_mcts* mcts, az_counters* h_out, uint64_t* h_errors, int reset, void* stream);
 

@@ -83,6 +83,8 @@ def oracle_lib():
         L.ro_random_action.argtypes = [sp, rp, C.c_uint64, C.c_uint32, C.c_uint32]
         L.ro_encode.argtypes = [sp, f32p]
         L.ro_normalize_policy.argtypes = [f32p, C.c_uint64]
+        L.ro_nn_input.argtypes = [sp, u8p]
+        L.ro_sample_record.argtypes = [sp, f32p, C.c_int, u8p]
         L.ro_mcts_new.restype = C.c_void_p
         L.ro_mcts_new.argtypes = [C.c_void_p, C.c_void_p]
         for fn in ("ro_mcts_free", "ro_mcts_clear", "ro_mcts_trim", "ro_mcts_table_size"):
@@ -159,6 +161,18 @@ class OracleGame:
         self.L.ro_encode(C.byref(self.s), x)
         return x
 
+    def nn_input(self):
+        """NNInputData(const State&) as its 88-byte image"""
+        out = np.zeros(88, np.uint8)
+        self.L.ro_nn_input(C.byref(self.s), out)
+        return out
+
+    def sample_record(self, pi, status):
+        """one 265-byte training sample of the reference's file format for the current state, policy `pi`, final `status`"""
+        out = np.zeros(265, np.uint8)
+        self.L.ro_sample_record(C.byref(self.s), np.ascontiguousarray(pi, np.float32), int(status), out)
+        return out
+
 
 class OracleMcts:
     def __init__(self, rules=None, evaluator="pseudo"):
@@ -224,6 +238,8 @@ def ref_lib():
         L.ref_random_action_philox.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32]
         L.ref_encode.argtypes = [vp, f32p]
         L.ref_normalize_policy.argtypes = [f32p, C.c_uint64]
+        L.ref_nn_input.argtypes = [vp, u8p]
+        L.ref_save_samples.argtypes = [C.c_char_p, C.c_int, np.ctypeslib.ndpointer(np.int8), u8p, f32p, C.c_int, C.c_int]
         L.ref_consistency_violations.argtypes = [vp]
         L.ref_get_map.argtypes = [np.ctypeslib.ndpointer(np.uint64), np.ctypeslib.ndpointer(np.int8),
                                   np.ctypeslib.ndpointer(np.uint64), i32p]
@@ -300,6 +316,11 @@ class RefGame:
         self.L.ref_encode(self.s, x)
         return x
 
+    def nn_input(self):
+        out = np.zeros(88, np.uint8)
+        self.L.ref_nn_input(self.s, out)
+        return out
+
     def violations(self):
         return int(self.L.ref_consistency_violations(self.s))
 
@@ -336,3 +357,12 @@ class RefMcts:
 
     def pick(self, pi, sample, seed, game, ply):
         return int(self.L.ref_pick_move(self.h, np.ascontiguousarray(pi, np.float32), int(sample), seed, game, ply))
+
+
+def ref_save_samples(path, players, nn_inputs, policies, status, rounds):
+    """the reference's own NNTrainDataStorage: push the samples, updateValues(status), saveTrainingSamples(path)"""
+    p = np.ascontiguousarray(players, np.int8)
+    rc = ref_lib().ref_save_samples(path.encode(), len(p), p, np.ascontiguousarray(nn_inputs, np.uint8).reshape(-1),
+                                    np.ascontiguousarray(policies, np.float32).reshape(-1), int(status), int(rounds))
+    if rc != 0:
+        raise RuntimeError(ref_lib().ref_last_error().decode())

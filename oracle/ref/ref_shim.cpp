@@ -194,6 +194,24 @@ REF_API void ref_encode(void* s, float* x546)
 
 REF_API void ref_nn_input(void* s, uint8_t* out) { NNInputData in(*(State*)s); memcpy(out, &in, sizeof in); }
 
+/* the reference's own sample store: push n samples (player, NNInputData image, policy), let updateValues(status) fill the values,
+   saveTrainingSamples(path).  alphazero_trainer.cpp:108-114, alphazero_nn_data.cpp:51-65, 115-138 */
+REF_API int ref_save_samples(const char* path, int n, const int8_t* players, const uint8_t* nn_inputs88, const float* policies43, int status, int rounds)
+{
+	try {
+		NNTrainDataStorage st;
+		for (int i = 0; i < n; i++) {
+			NNInputData in;
+			memcpy((void*)&in, nn_inputs88 + (size_t)i * sizeof(NNInputData), sizeof in);
+			std::vector<float> pol(policies43 + (size_t)i * TF_OUTPUT_POLICY_TENSOR_SIZE, policies43 + (size_t)(i + 1) * TF_OUTPUT_POLICY_TENSOR_SIZE);
+			st.data.push_back(NNTrainData((uint8_t)players[i], std::move(in), NNOutputData(std::move(pol))));
+		}
+		st.updateValues(status, rounds);
+		st.saveTrainingSamples(path);
+		return 0;
+	} catch (std::exception& e) { snprintf(g_err, sizeof g_err, "%s", e.what()); return -1; }
+}
+
 REF_API void ref_normalize_policy(float* policy43, uint64_t valid)
 {
 	NNOutputData o;

@@ -505,6 +505,39 @@ void ro_encode(const ro_state* s, float x[RO_INPUT_FLOATS])
     }
 }
 
+/* NNInputData(const State&), neural_network/alphazero_nn_data.cpp:165-196, as the 88-byte g++ x86-64 image of the class
+   (alphazero_nn_data.h:73-101): land[42] @0, playerIndex @42, round u16 @44, floats @48: reinforcementShare, attackFrequency,
+   canDrawCard, phase one-hot x 6, armyShare.  Padding bytes 43, 46, 47 are zero. */
+void ro_nn_input(const ro_state* s, uint8_t out[RO_NN_INPUT_BYTES])
+{
+    derived d; derive(s, &d);
+    int c = s->cur, e = c ^ 1;
+    float ref = (float)(int8_t)ro_reinforcement_value(d.owned[c]);
+    float eref = (float)(int8_t)ro_reinforcement_value(d.owned[e]);
+    float att = (float)s->attacks / 8.0f; if (!(att < 1.0f)) att = 1.0f;
+    float ta = (float)d.total_army[c], eta = (float)d.total_army[e];
+    float f[10];
+    f[0] = ref / (ref + eref); f[1] = att; f[2] = s->allow_draw ? 1.0f : 0.0f;
+    for (int p = 0; p < 6; ++p) f[3 + p] = s->phase == p ? 1.0f : 0.0f;
+    f[9] = ta / (ta + eta);
+    memset(out, 0, RO_NN_INPUT_BYTES);
+    memcpy(out, s->land, RO_LANDS);
+    out[42] = (uint8_t)c;
+    out[44] = (uint8_t)(s->round & 0xff); out[45] = (uint8_t)(s->round >> 8);
+    memcpy(out + 48, f, sizeof f);
+}
+
+/* one training sample as NNTrainDataStorage::saveTrainingSamples writes it (alphazero_nn_data.cpp:115-138):
+   int8 playerIndex | NNInputData | float value | float policy[43]; value per updateValues (:51-65) for final status `status` */
+void ro_sample_record(const ro_state* s, const float pi[RO_MOVES], int status, uint8_t out[RO_SAMPLE_BYTES])
+{
+    float z = status == RO_DRAW ? 0.0f : (status == s->cur ? 1.0f : -1.0f);
+    out[0] = (uint8_t)s->cur;
+    ro_nn_input(s, out + 1);
+    memcpy(out + 1 + RO_NN_INPUT_BYTES, &z, 4);
+    memcpy(out + 1 + RO_NN_INPUT_BYTES + 4, pi, 4 * RO_MOVES);
+}
+
 /* NNOutputData::normalize, neural_network/alphazero_nn_data.cpp:3-27 */
 void ro_normalize_policy(float policy[RO_MOVES], uint64_t valid)
 {

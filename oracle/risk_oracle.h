@@ -101,6 +101,10 @@ int ro_make_move(ro_state* s, int action, const ro_rules* r, ro_dice* dice);    
 int ro_random_action(const ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply);
 void ro_encode(const ro_state* s, float x[RO_INPUT_FLOATS]);                     /* NNInputData + setInStateTensor */
 void ro_normalize_policy(float policy[RO_MOVES], uint64_t valid);                /* NNOutputData::normalize */
+#define RO_NN_INPUT_BYTES 88   /* sizeof(NNInputData), alphazero_nn_data.h:73-101 */
+#define RO_SAMPLE_BYTES 265    /* 1 + 88 + 4 + 43 * 4, alphazero_nn_data.cpp:115-138 */
+void ro_nn_input(const ro_state* s, uint8_t out[RO_NN_INPUT_BYTES]);             /* NNInputData(const State&) image */
+void ro_sample_record(const ro_state* s, const float pi[RO_MOVES], int status, uint8_t out[RO_SAMPLE_BYTES]);
 
 /* ---- MCTS (alphazero_mcts.cpp) ---- */
 typedef void (*ro_eval_fn)(const ro_state* s, float policy[RO_MOVES], float* value, void* user);

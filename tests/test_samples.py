@@ -1,0 +1,111 @@
+"""Self-play training samples: record layout and file format against the reference's own
+NNInputData / NNTrainDataStorage, then the device-side recording against an oracle replay of the same games."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+SEED = 0x5EED0001
+NEED_REF = pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+
+
+def random_positions(game_cls, n_games, steps):
+    """(game object after k random-play steps) snapshots, reproducible"""
+    out = []
+    for g in range(n_games):
+        o = game_cls()
+        o.new_game(SEED, g, 0)
+        for ply in range(steps):
+            if o.status() != -1:
+                break
+            if ply % 7 == 3:
+                out.append((g, ply, o.data().copy()))
+            assert o.move(o.random_action(SEED, g, ply), SEED, g, ply) == 0
+    return out
+
+
+@NEED_REF
+def test_nn_input_image_matches_reference():
+    """ro_nn_input == the bytes of the reference's NNInputData(const State&) (padding bytes 43, 46, 47 excluded)"""
+    snaps = random_positions(po.RefGame, 6, 400)
+    assert len(snaps) > 200
+    ref, orc = po.RefGame(), po.OracleGame()
+    keep = np.ones(88, bool); keep[[43, 46, 47]] = False
+    for _, _, data in snaps:
+        ref.set_data(data); assert orc.set_data(data) == 0
+        assert (ref.nn_input()[keep] == orc.nn_input()[keep]).all()
+        assert (orc.nn_input()[~keep] == 0).all()
+
+
+@NEED_REF
+def test_samples_file_is_the_reference_format(tmp_path):
+    """az_samples_write_file writes byte for byte what NNTrainDataStorage::saveTrainingSamples writes"""
+    from alphazero_risk_b200 import api
+    rng = np.random.default_rng(5)
+    snaps = random_positions(po.OracleGame, 3, 300)[:64]
+    orc = po.OracleGame()
+    for status in (0, 1, -2):
+        players, inputs, pols, recs = [], [], [], []
+        for _, _, data in snaps:
+            assert orc.set_data(data) == 0
+            pi = rng.random(43, dtype=np.float32); pi /= pi.sum()
+            players.append(orc.s.cur); inputs.append(orc.nn_input()); pols.append(pi)
+            recs.append(orc.sample_record(pi, status))
+        ref_path, our_path = str(tmp_path / ("ref%d.bin" % status)), str(tmp_path / ("ours%d.bin" % status))
+        po.ref_save_samples(ref_path, players, np.stack(inputs), np.stack(pols), status, 40)
+        api.write_samples_file(our_path, np.stack(recs))
+        a, b = open(ref_path, "rb").read(), open(our_path, "rb").read()
+        assert len(a) == 8 + 265 * len(snaps) and a == b
+
+
+@pytest.mark.gpu
+def test_device_recording_matches_oracle_replay():
+    """az_selfplay_run with recording: every finished game's samples (state image, policy target, outcome) equal an oracle replay"""
+    from alphazero_risk_b200 import api
+    if api.lib().az_device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu suite must run on a B200")
+    n, moves, sims = 12, 900, 4
+    env = api.Env(n, rules=api.default_rules(mcts_simulations=sims, threads_per_mcts=1), first_game_id=3)
+    env.reset(SEED)
+    mc = api.Mcts(env, evaluator=api.EVAL_PSEUDO)
+    mc.record(capacity_samples=n * moves, max_moves_per_game=1024)
+    mc.selfplay(moves)
+    recs, dropped = mc.samples()
+    assert dropped == 0 and mc.counters()["errors"] == 0
+    # oracle replay: the expected records of every game that finished, grouped per game
+    rules = po.default_rules(mcts_simulations=sims, threads_per_mcts=1)
+    expected = []
+    for g in range(n):
+        o, t = po.OracleGame(rules), po.OracleMcts(rules, "pseudo")
+        o.new_game(SEED, 3 + g, 0)
+        cur = []
+        for ply in range(moves):
+            a = t.search(o, SEED, 3 + g, ply)
+            cur.append((po.RoState.from_buffer_copy(o.s), a["pi"].copy()))
+            mv = t.pick(a["pi"], o.s.round <= rules.temperature_threshold, SEED, 3 + g, ply)
+            assert o.move(mv, SEED, 3 + g, ply) == 0
+            st = o.status()
+            if st != -1:
+                game = []
+                for s, pi in cur:
+                    o2 = po.OracleGame(rules); o2.s = s
+                    game.append(o2.sample_record(pi, st))
+                expected.append(np.stack(game).tobytes())
+                cur = []
+                o.new_game(SEED, 3 + g, ply + 1)
+                t.clear()
+    assert len(expected) >= n // 2, "too few finished games for a meaningful check"
+    assert sum(len(e) for e in expected) == recs.size
+    # games finish in a data-dependent order; each game's records are contiguous in the queue
+    blob, left, pos = recs.tobytes(), sorted(expected, key=len, reverse=True), 0
+    while pos < len(blob):
+        hit = [e for e in left if blob.startswith(e, pos)]
+        assert hit, "record stream at byte %d matches no expected game" % pos
+        left.remove(hit[0]); pos += len(hit[0])
+    assert not left
+    # a second drain is empty; the staged samples of the running games are untouched
+    again, _ = mc.samples()
+    assert len(again) == 0
+    mc.close(); env.close()
