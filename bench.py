@@ -208,6 +208,7 @@ def nn_flops_per_position(blocks):
 
 
 def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
+    from alphazero_risk_b200 import dist as azdist
     """BASELINE configs[2]: batched self-play, 4096 games x 64 MCTS sims/move per GPU, leaf-batched bf16
     tcgen05 network forward (5-block graph = the only GraphDef the reference ships, random-init weights)."""
     import numpy as np
@@ -221,9 +222,7 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
     if rank == 0:
         net.init_random(1234)
     if dist is not None:      # weight broadcast (replaces the checkpoint-file hand-off of alphazero_gpu_cluster.cpp:221-231)
-        blob = torch.from_numpy(net.export_blob() if rank == 0 else np.zeros(net.num_params(), np.float32)).cuda()
-        dist.broadcast(blob, src=0)
-        net.import_blob(blob.cpu().numpy())
+        azdist.broadcast_weights(net, dist, src=0)
     net.finalize()
     mc = api.Mcts(env, net=net, evaluator=api.EVAL_NN, precision=api.BF16)
     moves_per_step = args.sp_moves
@@ -253,13 +252,11 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
         mc.search(pick_mode=api.PICK_SELFPLAY, apply_move=True, stream=sptr)
     barrier()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    c = torch.tensor([cnt["sims"], cnt["evals"], cnt["steps"], cnt["games"], cnt["errors"]], dtype=torch.float64, device="cuda")
+    dev_ms, e2e_ms = dev_ms, e2e_s * 1e3
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)          # stats gather (replaces GameResults::add, game.cpp:298-309)
-    dev_ms, e2e_ms = [float(v) for v in t.tolist()]
-    tot_sims, tot_evals, tot_steps, tot_games, errors = [float(v) for v in c.tolist()]
+        dev_ms, e2e_ms = azdist.max_over_ranks([dev_ms, e2e_ms], dist)
+        cnt = azdist.reduce_counters(cnt, dist)           # stats gather (replaces GameResults::add, game.cpp:298-309)
+    tot_sims, tot_evals, tot_steps, tot_games, errors = [float(cnt[k]) for k in ("sims", "evals", "steps", "games", "errors")]
     mc.close(); net.close(); env.close()
     if rank != 0:
         return None
@@ -309,7 +306,7 @@ def run_ours(args):
     n, S = args.games, args.lockstep
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
-    env = api.Env(n, device=local, first_game_id=rank * n)
+    env = api.Env(n, device=local, first_game_id=rank * n)       # weak scaling: every rank owns n games, global ids rank*n ..
     env.reset(SEED, stream=sptr)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
@@ -356,10 +353,11 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, t_wall * 1e3], dtype=torch.float64, device="cuda")
+    dev_ms, e2e_ms, wall_ms = dev_ms, e2e_s * 1e3, t_wall * 1e3
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_ms = [float(v) for v in t.tolist()]
+        from alphazero_risk_b200 import dist as azdist
+        dev_ms, e2e_ms, wall_ms = azdist.max_over_ranks([dev_ms, e2e_ms, wall_ms], dist)
+        cnt = azdist.reduce_counters(dict(cnt, errors=0), dist)
 
     mcts_line = None
     if not args.no_selfplay:
