@@ -34,6 +34,12 @@
  * rInt() % remaining) uses sim = AZ_STREAM_DEAL: draw i = mulhi(word(i%4) of
  * block (i/4), 42 - i).
  *
+ * A scripted opponent (ScriptPlayer::takeTurn, player/script/script_player.cpp:162-227) plays a WHOLE turn in one call
+ * and draws an unbounded number of dice: they are consumed sequentially from the stream sim = AZ_STREAM_OPP of the
+ * (game, ply) at which the turn starts (one ply per opponent turn), exactly like the reference consumes its engine.
+ * Its rInt() draws (Utility::randomMask in the setup phase, land/land.cpp:100-112: rInt() % count) come from
+ * sim = AZ_STREAM_OPP_INT: draw i = word (i % 4) of block (i / 4), shifted right by one (a non-negative int).
+ *
  * Plain C99 / CUDA; no dependencies.
  */
 #ifndef AZ_PHILOX_H
@@ -49,6 +55,8 @@
 
 #define AZ_STREAM_REAL 0xFFFFFFFFu /* dice / action / sampling float of a real move */
 #define AZ_STREAM_DEAL 0xFFFFFFFEu /* initial deal of a (re)started game             */
+#define AZ_STREAM_OPP 0xFFFFFFFDu  /* dice of one scripted-opponent turn               */
+#define AZ_STREAM_OPP_INT 0xFFFFFFFCu /* rInt() draws of one scripted-opponent turn   */
 
 typedef struct az_u32x4 { uint32_t x, y, z, w; } az_u32x4;
 
@@ -115,6 +123,13 @@ AZ_HD uint32_t az_rng_deal_draw(uint64_t seed, uint32_t game, uint32_t ply, uint
 {
     az_u32x4 blk = az_rng_block(seed, game, ply, AZ_STREAM_DEAL, i >> 2);
     return az_mulhi32(az_u32x4_word(blk, (int)(i & 3u)), 42u - i);
+}
+
+/* i-th rInt() of a scripted opponent's turn */
+AZ_HD uint32_t az_rng_opp_int(uint64_t seed, uint32_t game, uint32_t ply, uint32_t i)
+{
+    az_u32x4 blk = az_rng_block(seed, game, ply, AZ_STREAM_OPP_INT, i >> 2);
+    return az_u32x4_word(blk, (int)(i & 3u)) >> 1;
 }
 
 AZ_HD float az_rng_unit_float(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }

@@ -47,6 +47,10 @@ class RoRules(C.Structure):
                 ("dir_noise_epsi", C.c_float), ("temperature_threshold", C.c_int)]
 
 
+class RoScript(C.Structure):
+    _fields_ = [("set", C.c_int8), ("to", C.c_int8), ("from_", C.c_int8), ("from_army", C.c_uint8)]
+
+
 class RoDice(C.Structure):
     _fields_ = [("use_tape", C.c_int), ("seed", C.c_uint64), ("game", C.c_uint32), ("ply", C.c_uint32),
                 ("sim", C.c_uint32), ("j", C.c_uint32), ("tape", C.POINTER(C.c_int32)), ("tape_len", C.c_int),
@@ -84,6 +88,9 @@ def oracle_lib():
         L.ro_encode.argtypes = [sp, f32p]
         L.ro_normalize_policy.argtypes = [f32p, C.c_uint64]
         L.ro_nn_input.argtypes = [sp, u8p]
+        L.ro_script_init.argtypes = [C.POINTER(RoScript)]
+        L.ro_script_turn.argtypes = [sp, C.POINTER(RoScript), rp, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.ro_invert_players.argtypes = [sp]
         L.ro_sample_record.argtypes = [sp, f32p, C.c_int, u8p]
         L.ro_mcts_new.restype = C.c_void_p
         L.ro_mcts_new.argtypes = [C.c_void_p, C.c_void_p]
@@ -160,6 +167,13 @@ class OracleGame:
         x = np.zeros(INPUT_FLOATS, np.float32)
         self.L.ro_encode(C.byref(self.s), x)
         return x
+
+    def script_turn(self, script, seed, game, ply):
+        """ScriptPlayer::takeTurn on this game; `script` = RoScript carrying the player's members between turns"""
+        return int(self.L.ro_script_turn(C.byref(self.s), C.byref(script), C.byref(self.rules), seed, game, ply))
+
+    def invert_players(self):
+        self.L.ro_invert_players(C.byref(self.s))
 
     def nn_input(self):
         """NNInputData(const State&) as its 88-byte image"""
@@ -239,6 +253,11 @@ def ref_lib():
         L.ref_encode.argtypes = [vp, f32p]
         L.ref_normalize_policy.argtypes = [f32p, C.c_uint64]
         L.ref_nn_input.argtypes = [vp, u8p]
+        L.ref_script_new.restype = vp
+        L.ref_script_free.argtypes = [vp]
+        L.ref_script_turn.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.ref_state_invert_players.argtypes = [vp]
+        L.ref_state_set_current_player.argtypes = [vp, C.c_int]
         L.ref_save_samples.argtypes = [C.c_char_p, C.c_int, np.ctypeslib.ndpointer(np.int8), u8p, f32p, C.c_int, C.c_int]
         L.ref_consistency_violations.argtypes = [vp]
         L.ref_get_map.argtypes = [np.ctypeslib.ndpointer(np.uint64), np.ctypeslib.ndpointer(np.int8),
@@ -321,6 +340,16 @@ class RefGame:
         self.L.ref_nn_input(self.s, out)
         return out
 
+    def script_turn(self, script, seed, game, ply):
+        """`script` = handle from ref_lib().ref_script_new() (a reference ScriptPlayer object)"""
+        return int(self.L.ref_script_turn(script, self.s, seed, game, ply))
+
+    def invert_players(self):
+        self.L.ref_state_invert_players(self.s)
+
+    def set_current_player(self, p):
+        self.L.ref_state_set_current_player(self.s, int(p))
+
     def violations(self):
         return int(self.L.ref_consistency_violations(self.s))
 
@@ -357,6 +386,12 @@ class RefMcts:
 
     def pick(self, pi, sample, seed, game, ply):
         return int(self.L.ref_pick_move(self.h, np.ascontiguousarray(pi, np.float32), int(sample), seed, game, ply))
+
+
+def new_script():
+    sp = RoScript()
+    oracle_lib().ro_script_init(C.byref(sp))
+    return sp
 
 
 def ref_save_samples(path, players, nn_inputs, policies, status, rounds):

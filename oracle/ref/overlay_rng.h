@@ -38,6 +38,7 @@ struct RefRngCtx
 	uint32_t game = 0, ply = 0, sim = AZ_STREAM_REAL;
 	uint32_t die_j = 0;   /* dice drawn so far in this (game, ply, sim) stream */
 	uint32_t deal_i = 0;  /* rInt() draws so far in this deal                  */
+	uint32_t int_j = 0;   /* rInt() draws so far in this scripted-opponent turn */
 	/* tape */
 	const int32_t* tape = nullptr;
 	size_t tape_len = 0, tape_pos = 0;
@@ -80,6 +81,7 @@ public:
 		{
 			/* only the initial deal draws ints on the hot path: Utility::randomMask,
 			   land.cpp:100-112 computes rInt() % remaining; remaining = 42 - i */
+			if (c.sim == AZ_STREAM_OPP) return (int)az_rng_opp_int(c.seed, c.game, c.ply, c.int_j++);
 			if (c.deal_i >= 42) { fprintf(stderr, "ref overlay rng: rInt outside a deal\n"); abort(); }
 			uint32_t k = az_rng_deal_draw(c.seed, c.game, c.ply, c.deal_i);
 			c.deal_i++;

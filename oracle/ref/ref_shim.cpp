@@ -194,6 +194,23 @@ REF_API void ref_encode(void* s, float* x546)
 
 REF_API void ref_nn_input(void* s, uint8_t* out) { NNInputData in(*(State*)s); memcpy(out, &in, sizeof in); }
 
+/* ---- ScriptPlayer (player/script/script_player.cpp): one object per (game slot, side), like GameGroup::threadPlayGame keeps them */
+REF_API void* ref_script_new() { return new ScriptPlayer(); }
+REF_API void ref_script_free(void* p) { delete (ScriptPlayer*)p; }
+/* ScriptPlayer::takeTurn(state) with dice / ints from the scripted-opponent streams of (seed, game, ply) */
+REF_API int ref_script_turn(void* p, void* s, uint64_t seed, uint32_t game, uint32_t ply)
+{
+	RefRngCtx& c = ref_rng_ctx();
+	c.mode = REF_RNG_PHILOX; c.seed = seed; c.game = game; c.ply = ply; c.sim = AZ_STREAM_OPP; c.die_j = 0; c.int_j = 0;
+	try { ((ScriptPlayer*)p)->takeTurn(*(State*)s); }
+	catch (std::exception& e) { snprintf(g_err, sizeof g_err, "%s", e.what()); c.mode = REF_RNG_ENGINE; c.sim = AZ_STREAM_REAL; return -1; }
+	c.mode = REF_RNG_ENGINE; c.sim = AZ_STREAM_REAL;
+	return 0;
+}
+/* Game::newGame's mirror game (game/game.cpp:170-179): previous start state with the sides swapped */
+REF_API void ref_state_invert_players(void* s) { ((State*)s)->invertPlayers(); }
+REF_API void ref_state_set_current_player(void* s, int p) { ((State*)s)->setCurrentPlayerTurn(p); }
+
 /* the reference's own sample store: push n samples (player, NNInputData image, policy), let updateValues(status) fill the values,
    saveTrainingSamples(path).  alphazero_trainer.cpp:108-114, alphazero_nn_data.cpp:51-65, 115-138 */
 REF_API int ref_save_samples(const char* path, int n, const int8_t* players, const uint8_t* nn_inputs88, const float* policies43, int status, int rounds)

@@ -505,6 +505,237 @@ void ro_encode(const ro_state* s, float x[RO_INPUT_FLOATS])
     }
 }
 
+
+/* ------------------------------------------------------------------ scripted opponent
+   ScriptPlayer::takeTurn, player/script/script_player.cpp:162-227 (and :19-160), GameHelper::PlayerMovement /
+   LandSetMovement::add, player/game_helper.cpp:51-109.  One call plays the WHOLE turn (or, in the setup phase, the
+   player's placement and the neutral placement).  Dice come from the sequential stream AZ_STREAM_OPP of (game, ply), the
+   rInt() of Utility::randomMask from AZ_STREAM_OPP_INT (include/az_philox.h). */
+
+/* land/land_set.cpp:12-24: member lands of each continent IN DECLARATION ORDER (first attackable one is attacked);
+   continent ids here: 0 NA, 1 SA, 2 EU, 3 AF, 4 AS, 5 AU as in RO_CONTINENT_MASK */
+static const int8_t RO_CONTINENT_LANDS[6][13] = {
+    { 0, 1, 2, 3, 4, 5, 6, 7, 8, -1 },
+    { 9, 10, 11, 12, -1 },
+    { 13, 14, 15, 16, 17, 19, 18, -1 },
+    { 20, 21, 22, 24, 25, 23, -1 },
+    { 26, 33, 35, 36, 27, 28, 29, 30, 31, 32, 34, 37, -1 },
+    { 38, 39, 40, 41, -1 },
+};
+
+void ro_script_init(ro_script* sp) { sp->set = -1; sp->to = -1; sp->from = -1; sp->from_army = 0; }
+
+typedef struct script_ctx {
+    ro_state* s; ro_script* sp; const ro_rules* r;
+    uint64_t seed; uint32_t game, ply, die_j, int_j;
+    uint64_t owned_attack_mask, attack_mask;     /* ScriptPlayer::ownedAttackLandBitMask / attackLandBitMask */
+} script_ctx;
+
+static int script_die(script_ctx* c) { return az_rng_die(c->seed, c->game, c->ply, AZ_STREAM_OPP, c->die_j++); }
+
+/* GameHelper::sortLandSet, game_helper.cpp:19-39: fewer lands still to conquer first, then more attackable ones, then the
+   larger continent mask — a strict total order, so the previous order of ScriptPlayer::attackLandSetPriority is irrelevant */
+static int set_before(int a, int na, int aa, int b, int nb, int ab)
+{
+    if (na != nb) return na < nb;
+    if (aa != ab) return aa > ab;
+    return RO_CONTINENT_MASK[a] > RO_CONTINENT_MASK[b];
+}
+
+/* updateAttackLandSetPriority / updateAttackLandSet / updateAttackLandTo / updateAttackLandFrom, script_player.cpp:19-70;
+   members that find no candidate keep their previous value, like the reference's */
+static void script_pick_target(script_ctx* c)
+{
+    derived d; derive(c->s, &d);
+    int me = c->s->cur;
+    int not_owned[6], not_owned_attack[6], order[6];
+    for (int k = 0; k < 6; ++k) {
+        uint64_t m = RO_CONTINENT_MASK[k] & ~d.owned[me];
+        not_owned[k] = popc(m); not_owned_attack[k] = popc(m & c->attack_mask);
+        order[k] = k;
+    }
+    for (int i = 1; i < 6; ++i)          /* any sort gives the same result for a strict total order */
+        for (int j = i; j > 0 && set_before(order[j], not_owned[order[j]], not_owned_attack[order[j]],
+                                            order[j - 1], not_owned[order[j - 1]], not_owned_attack[order[j - 1]]); --j) {
+            int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
+        }
+    for (int i = 0; i < 6; ++i) if (not_owned_attack[order[i]] > 0) { c->sp->set = (int8_t)order[i]; break; }
+    if (c->sp->set >= 0)
+        for (int i = 0; RO_CONTINENT_LANDS[c->sp->set][i] >= 0; ++i) {
+            int l = RO_CONTINENT_LANDS[c->sp->set][i];
+            if ((1ull << l) & c->attack_mask) { c->sp->to = (int8_t)l; break; }
+        }
+    c->sp->from_army = 0;
+    if (c->sp->to >= 0)
+        for (int k = 0; k < 6 && RO_NBR_LIST[c->sp->to][k] >= 0; ++k) {
+            int n = RO_NBR_LIST[c->sp->to][k];
+            if (((1ull << n) & c->owned_attack_mask) && army_of(c->s, n) > c->sp->from_army) {
+                c->sp->from_army = (uint8_t)army_of(c->s, n); c->sp->from = (int8_t)n;
+            }
+        }
+}
+
+/* State::attackMove, state/state.cpp:769-918; returns 1 when the land was captured */
+static int script_attack(script_ctx* c, int from, int to)
+{
+    ro_state* s = c->s;
+    int cur = s->cur;
+    s->attacks = (uint8_t)(s->attacks + 1);
+    int a = army_of(s, from), dd = army_of(s, to), defender = owner_of(s, to), units = 1;
+    if (dd > 0) {
+        int na = a >= 4 ? 3 : (a == 3 ? 2 : 1), nd = dd >= 2 ? 2 : 1;
+        units = na;
+        int ad[3] = { 0, 0, 0 }, df[2] = { 0, 0 };
+        for (int i = 0; i < na; ++i) ad[i] = script_die(c);
+        for (int i = 0; i < nd; ++i) df[i] = script_die(c);
+        sort_dice_desc(ad, 3); sort_dice_desc(df, 2);
+        if (ad[0] > df[0]) dd--; else { a--; units--; }
+        if (na >= 2 && nd == 2) { if (ad[1] > df[1]) dd--; else { a--; units--; } }
+    }
+    int captured = 0;
+    if (dd == 0) {
+        a -= units;
+        if (a > 1) { s->phase = RO_ATTACK_MOBILIZATION; s->mob_from = (uint8_t)from; s->mob_to = (uint8_t)to; }
+        s->allow_draw = 1;
+        set_land(s, from, a, cur); set_land(s, to, units, cur);
+        captured = 1;
+    } else { set_land(s, from, a, cur); set_land(s, to, dd, defender); }
+    if (s->phase == RO_ATTACK && attack_army_mask(s, cur) == 0) s->phase = RO_FORTIFY;
+    return captured;
+}
+
+/* ScriptPlayer::attackLand, script_player.cpp:71-136 */
+static void script_attack_land(script_ctx* c)
+{
+    ro_state* s = c->s; ro_script* sp = c->sp;
+    int me = s->cur;
+    while (s->reinf > 0) {
+        derived d; derive(s, &d);
+        uint64_t not_full = d.owned[me] & ~d.full[me];
+        int to = sp->from;
+        if (((1ull << sp->from) & not_full) == 0) {
+            uint64_t nb = RO_NBR_MASK[sp->to] & not_full;
+            if (nb) to = ctz(nb);
+            else {
+                uint64_t neutral_attack = nbr_union(d.neutral) & ~d.neutral;
+                nb = not_full & (d.attack[me ^ 1] | neutral_attack);
+                to = nb ? ctz(nb) : ctz(not_full);
+            }
+        }
+        int amount = RO_ARMY_MAX - army_of(s, to);
+        if (s->reinf < amount) amount = s->reinf;
+        while (amount > 0) {                       /* State::reinforcementMove, state.cpp:976-998 */
+            int step = amount < c->r->min_unit_move ? amount : c->r->min_unit_move;
+            s->reinf = (uint8_t)(s->reinf - step);
+            set_land(s, to, army_of(s, to) + step, me);
+            if (s->reinf == 0) goto_attack(s);
+            amount -= step;
+        }
+    }
+    sp->from_army = (uint8_t)army_of(s, sp->from);
+    while (sp->from_army > 1) {
+        int captured = script_attack(c, sp->from, sp->to);
+        sp->from_army = (uint8_t)army_of(s, sp->from);
+        if (captured && sp->from_army > 1) {       /* move everything but one army into the new land, MIN_UNIT_MOVE at a time */
+            int left = sp->from_army - 1;
+            while (left > 0) {                     /* State::attackReinforcementMove, state.cpp:920-947 */
+                int step = left < c->r->min_unit_move ? left : c->r->min_unit_move;
+                left -= step;
+                set_land(s, s->mob_from, army_of(s, s->mob_from) - step, me);
+                set_land(s, s->mob_to, army_of(s, s->mob_to) + step, me);
+                if (army_of(s, s->mob_from) == 1) goto_attack(s);
+            }
+            break;
+        }
+    }
+}
+
+/* ScriptPlayer::fortify, script_player.cpp:138-160 over GameHelper::PlayerMovement, game_helper.cpp:84-109: the owned components in
+   ascending seed order, each listed in DFS pre-order; per component the interior land with the largest army (first strict
+   maximum) is the source, the border land with the most foreign neighbours (first strict maximum) the target; the component
+   with the largest source army is used (std::sort on <= 16 elements is libstdc++'s stable insertion sort: first maximum). */
+static void script_fortify(script_ctx* c)
+{
+    ro_state* s = c->s;
+    int me = s->cur;
+    derived d; derive(s, &d);
+    if (d.owned_army[me] == 0) return;
+    uint64_t owned = d.owned[me], seen = 0;
+    int best_from = -1, best_to = -1, best_amount = -1;
+    for (int i = 0; i < RO_LANDS; ++i) {
+        if (!((1ull << i) & owned & ~seen)) continue;
+        int order[RO_LANDS], n = 0;
+        dfs(i, owned, &seen, order, &n);
+        int from = -1, from_amount = 0, to = -1, to_nbrs = 0;
+        for (int k = 0; k < n; ++k) {
+            int l = order[k];
+            uint64_t foreign = ~owned & RO_NBR_MASK[l];
+            if (foreign == 0) { if (army_of(s, l) > from_amount) { from = l; from_amount = army_of(s, l); } }
+            else if (popc(foreign) > to_nbrs) { to_nbrs = popc(foreign); to = l; }
+        }
+        if (from_amount > best_amount) { best_amount = from_amount; best_from = from; best_to = to; }
+    }
+    if (best_amount > 0 && best_to >= 0) {          /* State::fortifyMove, state.cpp:949-974 */
+        int amount = army_of(s, best_from) - 1, space = RO_ARMY_MAX - army_of(s, best_to);
+        if (space < amount) amount = space;
+        set_land(s, best_from, army_of(s, best_from) - amount, me);
+        set_land(s, best_to, army_of(s, best_to) + amount, me);
+    }
+}
+
+int ro_script_turn(ro_state* s, ro_script* sp, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply)
+{
+    if (ro_game_status(s, r) != RO_NOT_ENDED) return RO_ERR_GAME_OVER;
+    script_ctx c; memset(&c, 0, sizeof c);
+    c.s = s; c.sp = sp; c.r = r; c.seed = seed; c.game = game; c.ply = ply;
+    int me = s->cur;
+    derived d; derive(s, &d);
+    c.owned_attack_mask = d.owned[me]; c.attack_mask = d.attack[me];
+    if (s->phase == RO_SETUP) {
+        script_pick_target(&c);
+        s->reinf = (uint8_t)(s->reinf - 2);                       /* setupReinforcementMove, state.cpp:1009-1030 */
+        set_land(s, sp->from, army_of(s, sp->from) + 2, me);
+        s->phase = RO_SETUP_NEUTRAL;
+        uint64_t neutral = ALL_LANDS & ~d.owned[0] & ~d.owned[1];
+        uint64_t near_enemy = neutral & d.attack[me ^ 1] & ~d.attack[me];
+        if (near_enemy == 0) near_enemy = neutral & d.attack[me ^ 1];
+        uint64_t pool = near_enemy ? near_enemy : neutral;
+        int k = (int)(az_rng_opp_int(seed, game, ply, c.int_j++) % (uint32_t)popc(pool));   /* Utility::randomMask */
+        while (k--) pool &= pool - 1;
+        int land = ctz(pool);
+        set_land(s, land, army_of(s, land) + 1, RO_NEUTRAL);      /* setupReinforcementNeutralMove + nextPlayerSetupTurn */
+        s->phase = RO_SETUP; s->round++; s->cur ^= 1;
+        if (s->reinf == 0) {
+            derive(s, &d);
+            s->phase = RO_REINFORCEMENT; s->reinf = (uint8_t)ro_reinforcement_value(d.owned[s->cur]);
+        }
+        return RO_OK;
+    }
+    if (s->phase != RO_REINFORCEMENT) return RO_ERR_ILLEGAL_ACTION;   /* the script only ever starts a turn */
+    if (s->cards[me] >= 3) {                                      /* GameHelper::playCards + State::playCards, state.cpp:1091-1117 */
+        s->cards[me] = (uint8_t)(s->cards[me] - 3);
+        s->card_sets = (uint8_t)(s->card_sets + 1);
+        int cs = s->card_sets;
+        s->reinf = (uint8_t)(s->reinf + (cs <= 5 ? 2 + 2 * cs : 15 + (cs - 6) * 5));
+    }
+    while (c.attack_mask > 0 || s->reinf > 0) {
+        script_pick_target(&c);
+        script_attack_land(&c);
+        derive(s, &d);
+        c.owned_attack_mask = d.owned_army[me]; c.attack_mask = d.attack_army[me];
+    }
+    script_fortify(&c);
+    end_turn(s);
+    return RO_OK;
+}
+
+/* Game::newGame's mirror game, game/game.cpp:170-179: State::invertPlayers (state.cpp:493-516) + setCurrentPlayerTurn */
+void ro_invert_players(ro_state* s)
+{
+    for (int i = 0; i < RO_LANDS; ++i) { int o = owner_of(s, i); if (o < 2) set_land(s, i, army_of(s, i), o ^ 1); }
+    uint8_t t = s->cards[0]; s->cards[0] = s->cards[1]; s->cards[1] = t;
+}
+
 /* NNInputData(const State&), neural_network/alphazero_nn_data.cpp:165-196, as the 88-byte g++ x86-64 image of the class
    (alphazero_nn_data.h:73-101): land[42] @0, playerIndex @42, round u16 @44, floats @48: reinforcementShare, attackFrequency,
    canDrawCard, phase one-hot x 6, armyShare.  Padding bytes 43, 46, 47 are zero. */

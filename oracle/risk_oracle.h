@@ -101,6 +101,11 @@ int ro_make_move(ro_state* s, int action, const ro_rules* r, ro_dice* dice);    
 int ro_random_action(const ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply);
 void ro_encode(const ro_state* s, float x[RO_INPUT_FLOATS]);                     /* NNInputData + setInStateTensor */
 void ro_normalize_policy(float policy[RO_MOVES], uint64_t valid);                /* NNOutputData::normalize */
+/* ---- scripted opponent (ScriptPlayer, player/script/script_player.cpp) ---- */
+typedef struct ro_script { int8_t set, to, from; uint8_t from_army; } ro_script;   /* attackingLandSet / landAttackTo / landAttackFrom / attackFromArmy */
+void ro_script_init(ro_script* sp);
+int ro_script_turn(ro_state* s, ro_script* sp, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply);  /* ScriptPlayer::takeTurn */
+void ro_invert_players(ro_state* s);                                             /* State::invertPlayers */
 #define RO_NN_INPUT_BYTES 88   /* sizeof(NNInputData), alphazero_nn_data.h:73-101 */
 #define RO_SAMPLE_BYTES 265    /* 1 + 88 + 4 + 43 * 4, alphazero_nn_data.cpp:115-138 */
 void ro_nn_input(const ro_state* s, uint8_t out[RO_NN_INPUT_BYTES]);             /* NNInputData(const State&) image */

@@ -6,6 +6,7 @@ import pytest
 from oracle import pyoracle as po
 
 pytestmark = pytest.mark.skipif(not po.ref_available(), reason="oracle/_ref/libref_oracle.so not built")
+SEED = 0x5EED0001
 
 
 def test_reference_struct_sizes_and_defaults():
@@ -85,3 +86,37 @@ def test_mcts_lockstep(sims, T, play_mode):
         ply += 1
     po.ref_apply_rules(po.default_rules())
     assert ply > 100
+
+
+@pytest.mark.parametrize("mode", ["script_vs_script", "script_vs_random_mover", "mirror_pair"])
+def test_script_player_lockstep(mode):
+    """ro_script_turn == the UNMODIFIED ScriptPlayer::takeTurn (player/script/script_player.cpp:162-227): every Data field
+    after every turn, with the scripted-opponent RNG streams of include/az_philox.h; also State::invertPlayers for the mirror game"""
+    L = po.ref_lib()
+    po.ref_apply_rules(po.default_rules())
+    mask = po.data_byte_mask().astype(bool)
+    turns = 0
+    for g in range(18):
+        ref, orc = po.RefGame(), po.OracleGame()
+        ref.new_game(SEED, 100 + g, 0); orc.new_game(SEED, 100 + g, 0)
+        if mode == "mirror_pair":            # Game::newGame second game of a pair: same deal, sides swapped, player 1 starts
+            ref.invert_players(); ref.set_current_player(1)
+            orc.invert_players(); orc.s.cur = 1
+            assert (ref.data()[mask] == orc.data()[mask]).all()
+        rs, os_ = [L.ref_script_new(), L.ref_script_new()], [po.new_script(), po.new_script()]
+        ply = 0
+        while ref.status() == -1 and ply < 450:
+            cur = orc.s.cur
+            if mode != "script_vs_random_mover" or cur == 1:
+                assert ref.script_turn(rs[cur], SEED, 100 + g, ply) == 0, L.ref_last_error()
+                assert orc.script_turn(os_[cur], SEED, 100 + g, ply) == 0
+                turns += 1
+            else:
+                a = orc.random_action(SEED, 100 + g, ply)
+                assert ref.move(a, SEED, 100 + g, ply) == 0 and orc.move(a, SEED, 100 + g, ply) == 0
+            ply += 1
+            assert (ref.data()[mask] == orc.data()[mask]).all(), "game %d ply %d" % (g, ply)
+            assert ref.status() == orc.status() and ref.violations() == 0
+        for h in rs:
+            L.ref_script_free(h)
+    assert turns > 300
