@@ -91,6 +91,10 @@ def lib():
         L.az_selfplay_run.argtypes = [vp, C.c_int, vp]
         L.az_mcts_counters.argtypes = [vp, C.POINTER(AzCounters), C.POINTER(C.c_uint64), C.c_int, vp]
         L.az_selfplay_record.argtypes = [vp, C.c_size_t, C.c_int]
+        L.az_env_script_turn.argtypes = [vp, vp, vp, vp]
+        L.az_arena_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+        L.az_arena_destroy.argtypes = [vp]
+        L.az_arena_play.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(AzArenaResults), vp]
         L.az_selfplay_samples.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), vp]
         L.az_samples_write_file.argtypes = [C.c_char_p, vp, C.c_size_t]
         _lib = L
@@ -170,6 +174,12 @@ class Env:
     def step_dev(self, d_action, d_dice, d_status, d_valid_after=None, stream=None):
         """raw device pointers (ints), e.g. torch tensors' data_ptr()"""
         check(self.L.az_env_step_dev(self.h, d_action, d_dice, d_status, d_valid_after, stream))
+
+    def script_turn(self, script, stream=None):
+        """ScriptPlayer::takeTurn for the side to move of every running game; `script` = uint32 [n, 2] (in/out), SCRIPT_INIT at first"""
+        st = np.empty(self.n, np.int8)
+        check(self.L.az_env_script_turn(self.h, _ptr(script), _ptr(st), stream))
+        return st
 
     def encode(self, stream=None):
         a = np.empty((self.n, 7, 6, 13), np.float32)
@@ -264,6 +274,43 @@ class Net:
 
 
 EVAL_NN, EVAL_PSEUDO, EVAL_UNIFORM = 0, 1, 2
+OPPONENT_SCRIPT = 1
+SCRIPT_INIT = 0x00ffffff
+
+
+class AzArenaResults(C.Structure):
+    _fields_ = [("count", C.c_uint64), ("draw", C.c_uint64), ("win", C.c_uint64 * 2), ("win_and_started", C.c_uint64 * 2),
+                ("az_moves", C.c_uint64), ("az_sims", C.c_uint64), ("az_evals", C.c_uint64), ("opponent_turns", C.c_uint64),
+                ("ticks", C.c_uint64), ("errors", C.c_uint64)]
+
+    def as_dict(self):
+        return dict(count=int(self.count), draw=int(self.draw), win=[int(self.win[0]), int(self.win[1])],
+                    win_and_started=[int(self.win_and_started[0]), int(self.win_and_started[1])], az_moves=int(self.az_moves),
+                    az_sims=int(self.az_sims), az_evals=int(self.az_evals), opponent_turns=int(self.opponent_turns),
+                    ticks=int(self.ticks), errors=int(self.errors))
+
+
+class Arena:
+    """`-m play` on the device: the Mcts handle's games as AlphaZero (player 0) vs a device-side opponent (player 1)"""
+
+    def __init__(self, mcts, opponent=OPPONENT_SCRIPT, mirror_games=True):
+        self.L, self.mcts = lib(), mcts
+        h = C.c_void_p()
+        check(self.L.az_arena_create(mcts.h, opponent, int(mirror_games), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.az_arena_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def play(self, n_games, seed, stream=None):
+        r = AzArenaResults()
+        check(self.L.az_arena_play(self.h, int(n_games), int(seed), C.byref(r), stream))
+        return r.as_dict()
+
 SAMPLE_BYTES = 265
 
 

@@ -19,6 +19,8 @@
 #include "az_common.cuh"
 #include "az_game.cuh"
 #include "az_tables_gen.h"
+#include "az_script.cuh"
+#include "az_arena.cuh"
 
 // ---------------------------------------------------------------- error string
 static thread_local char g_az_err[512] = "";
@@ -299,6 +301,113 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout(uint32_t* __restrict_
     }
 }
 
+
+
+// ScriptPlayer::takeTurn for the side to move of every running game (one whole turn per call, one ply)
+__global__ void __launch_bounds__(ENV_BLOCK) k_env_script_turn(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
+                                                                uint32_t* __restrict__ script, int8_t* __restrict__ status,
+                                                                uint64_t seed, uint32_t first_game, AzRulesDev rules)
+{
+    __shared__ EnvSmem sm;
+    AzTables T = env_stage_tables(sm, g_tab);
+    int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    EnvCtx c; env_load(c, sm, st, n, gi);
+    int out = az_game_status(c.g, rules);
+    if (out != AZ_STATUS_RUNNING) out = AZ_STATUS_OVER;
+    else {
+        const uint32_t side = c.g.cur;
+        uint32_t spw = script[(size_t)gi * 2 + side];
+        const int rc = az_script_turn(c.g, c.land, c.scratch, T, rules, spw, seed, first_game + (uint32_t)gi, c.ply);
+        if (rc == 0) { script[(size_t)gi * 2 + side] = spw; c.ply++; env_store(c, sm, st, n, gi); out = az_game_status(c.g, rules); }
+        else out = rc;
+    }
+    status[gi] = (int8_t)out;
+}
+
+// ---------------------------------------------------------------- arena (-m play): everything between two AlphaZero moves
+// GameGroup::threadPlayGame / Game::playGames / Game::newGame / GameResults::addGame (game/game.cpp:153-254) for one game slot per
+// thread: tally a finished game, start the next one (fresh deal, or the mirror game = previous start state with the sides swapped
+// and player 1 to move, game.cpp:170-179), let the scripted opponent (player index 1) play its turns, and stop as soon as
+// player 0 (the AlphaZero side, searched by the MCTS kernels) is to move.  Pairs of games are claimed from a shared counter like
+// Counter::hasNext(2) (game.cpp:12-24).
+__global__ void __launch_bounds__(ENV_BLOCK) k_arena_advance(ArenaDev a, const uint64_t* __restrict__ g_tab, AzRulesDev rules)
+{
+    __shared__ EnvSmem sm;
+    AzTables T = env_stage_tables(sm, g_tab);
+    const int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
+    if (gi >= a.n) return;
+    if (!a.active[gi]) return;
+    EnvCtx c; env_load(c, sm, a.state, a.n, gi);
+    const uint32_t game = a.first_game + (uint32_t)gi;
+    uint32_t player_start = a.player_start[gi];
+    bool fresh = a.fresh[gi] != 0, active = true;
+    uint32_t last = a.last_mover[gi];
+    unsigned trim = 0;
+    for (int it = 0; it < 64; ++it) {
+        const int st = az_game_status(c.g, rules);
+        if (fresh || st != AZ_STATUS_RUNNING) {
+            if (!fresh) {                                             // GameResults::addGame, game.cpp:193-213
+                atomicAdd(&a.res[ARENA_COUNT], 1ull);
+                if (st == AZ_STATUS_DRAW) atomicAdd(&a.res[ARENA_DRAW], 1ull);
+                else {
+                    atomicAdd(&a.res[ARENA_WIN0 + st], 1ull);
+                    if ((uint32_t)st == player_start) atomicAdd(&a.res[ARENA_WAS0 + st], 1ull);
+                }
+                player_start ^= 1u;                                   // Game::incPlayerStart
+            }
+            if (!fresh && player_start == 1u) {
+                // second game of the claimed pair
+                if (a.mirror) {                                       // state = previousStartState; invertPlayers(); setCurrentPlayerTurn(1)
+#pragma unroll
+                    for (int w = 0; w < 11; ++w) {
+                        uint32_t v = a.start_state[(size_t)w * a.n + gi];
+                        uint32_t o = 0;                               // swap owners 0 <-> 1 (bit 6 of a byte whose bit 7 is clear)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) { uint32_t by = (v >> (8 * b)) & 0xffu; if (4 * w + b < AZ_LANDS && (by & 0x80u) == 0) by ^= 0x40u; o |= by << (8 * b); }
+                        sm.col[w * ENV_BLOCK + threadIdx.x] = o;
+                    }
+                    const uint32_t w10 = sm.col[10 * ENV_BLOCK + threadIdx.x];
+                    // cards travel with PlayerStatus (both 0 at a game start); scalars as dealt
+                    c.g.own0 = c.g.own1 = c.g.gt1 = c.g.full = 0;
+#pragma unroll
+                    for (int w = 0; w < 11; ++w) az_masks_add_word(c.g, sm.col[w * ENV_BLOCK + threadIdx.x], w);
+                    az_unpack_scalars(c.g, (w10 & 0xffffu) | ((w10 >> 24) << 16) | (((w10 >> 16) & 0xffu) << 24),
+                                      a.start_state[(size_t)11 * a.n + gi], a.start_state[(size_t)12 * a.n + gi], a.start_state[(size_t)13 * a.n + gi]);
+                } else az_new_game(c.g, c.land, a.seed, game, c.ply);
+                c.g.cur = 1u;
+            } else {
+                // claim the next pair (Counter::hasNext(2)); a slot that gets none is done
+                const unsigned long long before = atomicAdd(&a.res[ARENA_CLAIMED], 2ull);
+                if (before + 2ull > a.total_games) { atomicAdd(&a.res[ARENA_CLAIMED], (unsigned long long)-2ll); active = false; break; }
+                player_start = 0u;
+                az_new_game(c.g, c.land, a.seed, game, c.ply);        // State::newGame; setCurrentPlayerTurn(playerStart = 0)
+                env_store(c, sm, a.start_state, a.n, gi);             // previousStartState
+            }
+            fresh = false;
+            trim = 2; last = 0xffu;                                   // Player::newGame: AlphaZeroPlayer clears its table
+            continue;
+        }
+        if (c.g.cur == 1u) {                                          // the opponent's whole turn
+            uint32_t spw = a.script[(size_t)gi * 2 + 1];
+            if (a.opponent == AZ_OPPONENT_SCRIPT) az_script_turn(c.g, c.land, c.scratch, T, rules, spw, a.seed, game, c.ply);
+            a.script[(size_t)gi * 2 + 1] = spw;
+            c.ply++;
+            atomicAdd(&a.res[ARENA_OPP_TURNS], 1ull);
+            last = 1u;
+            continue;
+        }
+        // player 0 = AlphaZero is to move: AlphaZeroPlayer::takeTurn trims once when its turn starts (alphazero_player.cpp:5)
+        if (last != 0u && trim < 2) trim = 1;
+        last = 0u;
+        break;
+    }
+    env_store(c, sm, a.state, a.n, gi);
+    a.player_start[gi] = (uint8_t)player_start; a.fresh[gi] = 0; a.last_mover[gi] = (uint8_t)last;
+    a.active[gi] = active ? 1 : 0;
+    if (active) { a.extra_trim[gi] = (uint8_t)(a.extra_trim[gi] + trim); atomicAdd(&a.res[ARENA_ACTIVE], 1ull); }
+}
+
 // AoS Data image (state/state.h:86-105, g++ x86-64 layout) <-> device SoA
 __device__ __forceinline__ void put48(uint8_t* p, uint64_t v) { for (int i = 0; i < 6; ++i) p[i] = (uint8_t)(v >> (8 * i)); }
 __device__ __forceinline__ uint64_t get48(const uint8_t* p) { uint64_t v = 0; for (int i = 0; i < 6; ++i) v |= (uint64_t)p[i] << (8 * i); return v; }
@@ -423,7 +532,7 @@ struct az_env {
     unsigned long long* d_counters = nullptr;   // 8 x u64
     // staging for the host-buffer entry points
     uint8_t* d_action = nullptr; uint8_t* d_dice = nullptr; int8_t* d_status = nullptr; uint64_t* d_valid = nullptr;
-    uint8_t* d_aos = nullptr; float* d_x = nullptr; int* d_bad = nullptr;
+    uint8_t* d_aos = nullptr; float* d_x = nullptr; int* d_bad = nullptr; uint32_t* d_script = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
 };
@@ -434,6 +543,14 @@ static AzRulesDev dev_rules(const az_rules& r)
     d.max_game_rounds = r.max_game_rounds; d.min_unit_move = r.min_unit_move; return d;
 }
 static inline int env_grid(int n) { return (n + ENV_BLOCK - 1) / ENV_BLOCK; }
+
+int az_launch_arena_advance(const ArenaDev& a, const az_rules* rules, cudaStream_t s)
+{
+    k_arena_advance<<<env_grid(a.n), ENV_BLOCK, 0, s>>>(a, az_device_tables(), dev_rules(*rules));
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
 
 extern "C" int az_env_create(int n_games, const az_rules* rules, int device, uint32_t first_game_id, az_env** out)
 {
@@ -465,7 +582,7 @@ extern "C" int az_env_destroy(az_env* e)
     if (!e) return AZ_OK;
     AzDeviceGuard guard(e->device);
     cudaFree(e->d_state); cudaFree(e->d_counters); cudaFree(e->d_action); cudaFree(e->d_dice); cudaFree(e->d_status);
-    cudaFree(e->d_valid); cudaFree(e->d_aos); cudaFree(e->d_x); cudaFree(e->d_bad);
+    cudaFree(e->d_valid); cudaFree(e->d_aos); cudaFree(e->d_x); cudaFree(e->d_bad); cudaFree(e->d_script);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     delete e;
@@ -577,6 +694,23 @@ extern "C" int az_env_step(az_env* e, const uint8_t* h_action, const uint8_t* h_
     }
     rc = az_env_step_dev(e, e->d_action, h_dice ? e->d_dice : nullptr, e->d_status, nullptr, stream);
     if (rc) return rc;
+    AZ_CUDA(cudaMemcpyAsync(h_status, e->d_status, (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+extern "C" int az_env_script_turn(az_env* e, uint32_t* h_script, int8_t* h_status, void* stream)
+{
+    AZ_REQUIRE(e && h_script && h_status, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure(&e->d_script, (size_t)e->n * 2); if (rc) return rc;
+    rc = ensure(&e->d_status, (size_t)e->n); if (rc) return rc;
+    AZ_CUDA(cudaMemcpyAsync(e->d_script, h_script, sizeof(uint32_t) * 2 * (size_t)e->n, cudaMemcpyHostToDevice, s));
+    k_env_script_turn<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), e->d_script, e->d_status, e->seed,
+                                                            e->first_game, dev_rules(e->rules));
+    AZ_CUDA(cudaGetLastError());
+    AZ_CUDA(cudaMemcpyAsync(h_script, e->d_script, sizeof(uint32_t) * 2 * (size_t)e->n, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaMemcpyAsync(h_status, e->d_status, (size_t)e->n, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaStreamSynchronize(s));
     return AZ_OK;

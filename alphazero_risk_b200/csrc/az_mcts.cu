@@ -23,6 +23,7 @@
 #include "az_game.cuh"
 #include "az_nn.cuh"
 #include "az_pseudo_net.h"
+#include "az_arena.cuh"
 
 #define NODE_WORDS 160
 #define NW_VALID 14
@@ -802,5 +803,99 @@ extern "C" int az_mcts_counters(az_mcts* mc, az_counters* h_out, uint64_t* h_err
     h_out->sims = h[CNT_SIMS]; h_out->evals = h[CNT_EVALS]; h_out->steps = h[CNT_STEPS]; h_out->games = h[CNT_GAMES];
     h_out->wins[0] = h[CNT_W0]; h_out->wins[1] = h[CNT_W1]; h_out->draws = h[CNT_DRAW]; h_out->illegal = h[CNT_ILLEGAL];
     if (h_errors) *h_errors = h[CNT_POOL_OVERFLOW] + h[CNT_DEPTH_OVERFLOW];
+    return AZ_OK;
+}
+
+// ---------------------------------------------------------------- arena: -m play on the device (SURVEY §8f N1 + N2)
+// executePlay (src/alphazero_risk.cpp:4-47) -> GameGroup::playGames (game/game.cpp:277-312): every game slot is what one
+// threadPlayGame thread is in the reference — player index 0 = AlphaZeroPlayer (searched here by the lockstep MCTS in play mode:
+// argmax move, table trimmed when its turn starts, cleared at a new game), player index 1 = the opponent, games claimed in
+// mirror pairs, results tallied like GameResults.
+int az_env_reset(az_env* e, uint64_t seed, void* stream);
+
+struct az_arena {
+    az_mcts* mc = nullptr;
+    ArenaDev a;
+    std::vector<void*> allocs;
+};
+
+template <class T> static int aalloc(az_arena* ar, T** p, size_t count)
+{
+    AZ_CUDA(cudaMalloc(p, sizeof(T) * count));
+    AZ_CUDA(cudaMemset(*p, 0, sizeof(T) * count));
+    ar->allocs.push_back(*p);
+    return AZ_OK;
+}
+
+extern "C" int az_arena_create(az_mcts* mc, int opponent, int mirror_games, az_arena** out)
+{
+    AZ_REQUIRE(mc && out, "NULL argument");
+    AZ_REQUIRE(opponent == AZ_OPPONENT_SCRIPT, "unknown opponent kind");
+    AzDeviceGuard guard(mc->device);
+    az_arena* ar = new (std::nothrow) az_arena();
+    AZ_REQUIRE(ar != nullptr, "out of host memory");
+    ar->mc = mc;
+    ArenaDev& a = ar->a;
+    memset(&a, 0, sizeof a);
+    a.n = mc->d.n; a.opponent = opponent; a.mirror = mirror_games ? 1 : 0;
+    size_t n = (size_t)a.n;
+    int rc = 0;
+    rc |= aalloc(ar, &a.start_state, n * 16); rc |= aalloc(ar, &a.script, n * 2);
+    rc |= aalloc(ar, &a.player_start, n); rc |= aalloc(ar, &a.fresh, n); rc |= aalloc(ar, &a.active, n); rc |= aalloc(ar, &a.last_mover, n);
+    rc |= aalloc(ar, &a.res, (size_t)ARENA_N);
+    if (rc) { for (void* p : ar->allocs) cudaFree(p); delete ar; return AZ_ERR_CUDA; }
+    a.state = mc->d.root_state; a.extra_trim = mc->d.extra_trim;
+    *out = ar;
+    return AZ_OK;
+}
+
+extern "C" int az_arena_destroy(az_arena* ar)
+{
+    if (!ar) return AZ_OK;
+    AzDeviceGuard guard(ar->mc->device);
+    for (void* p : ar->allocs) cudaFree(p);
+    delete ar;
+    return AZ_OK;
+}
+
+extern "C" int az_arena_play(az_arena* ar, uint64_t n_games, uint64_t seed, az_arena_results* h_out, void* stream)
+{
+    AZ_REQUIRE(ar && h_out, "NULL argument");
+    az_mcts* mc = ar->mc;
+    AzDeviceGuard guard(mc->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    ArenaDev& a = ar->a;
+    size_t n = (size_t)a.n;
+    int rc = az_env_reset(mc->env, seed, stream); if (rc) return rc;           // fixes the seed of the Philox contract for this match
+    a.seed = seed; a.first_game = az_env_first_game(mc->env); a.total_games = n_games;
+    // ScriptPlayer objects live as long as the PlayerGroup: their members are NOT reset between matches in the reference either,
+    // but a match here starts from fresh players (AZ_SCRIPT_INIT = "never set")
+    std::vector<uint32_t> init(n * 2, 0x00ffffffu);
+    AZ_CUDA(cudaMemcpyAsync(a.script, init.data(), sizeof(uint32_t) * n * 2, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaMemsetAsync(a.player_start, 0, n, s)); AZ_CUDA(cudaMemsetAsync(a.fresh, 1, n, s));
+    AZ_CUDA(cudaMemsetAsync(a.active, 1, n, s)); AZ_CUDA(cudaMemsetAsync(a.last_mover, 0xff, n, s));
+    AZ_CUDA(cudaMemsetAsync(a.res, 0, sizeof(unsigned long long) * ARENA_N, s));
+    AZ_CUDA(cudaMemsetAsync(mc->d.counters, 0, sizeof(unsigned long long) * CNT_N, s));
+    AZ_CUDA(cudaStreamSynchronize(s));                                        // `init` goes out of scope below
+    unsigned long long active = 0;
+    uint64_t ticks = 0;
+    for (;;) {
+        AZ_CUDA(cudaMemsetAsync(a.res + ARENA_ACTIVE, 0, sizeof(unsigned long long), s));
+        rc = az_launch_arena_advance(a, az_env_rules(mc->env), s); if (rc) return rc;
+        AZ_CUDA(cudaMemcpyAsync(&active, a.res + ARENA_ACTIVE, sizeof active, cudaMemcpyDeviceToHost, s));
+        AZ_CUDA(cudaStreamSynchronize(s));
+        if (active == 0) break;
+        rc = search_once(mc, 0, 0, 1, 0, s); if (rc) return rc;               // one AlphaZero move on every slot that is waiting for one
+        ++ticks;
+    }
+    unsigned long long r[ARENA_N], c[CNT_N];
+    AZ_CUDA(cudaMemcpyAsync(r, a.res, sizeof r, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(c, mc->d.counters, sizeof c, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    h_out->count = r[ARENA_COUNT]; h_out->draw = r[ARENA_DRAW];
+    h_out->win[0] = r[ARENA_WIN0]; h_out->win[1] = r[ARENA_WIN1];
+    h_out->win_and_started[0] = r[ARENA_WAS0]; h_out->win_and_started[1] = r[ARENA_WAS1];
+    h_out->opponent_turns = r[ARENA_OPP_TURNS]; h_out->az_moves = c[CNT_STEPS]; h_out->az_sims = c[CNT_SIMS]; h_out->az_evals = c[CNT_EVALS];
+    h_out->ticks = ticks; h_out->errors = c[CNT_POOL_OVERFLOW] + c[CNT_DEPTH_OVERFLOW] + c[CNT_ILLEGAL];
     return AZ_OK;
 }

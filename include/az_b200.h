@@ -119,6 +119,13 @@ AZ_API int az_env_step(az_env* env, const uint8_t* h_action, const uint8_t* h_di
 AZ_API int az_env_step_dev(az_env* env, const uint8_t* d_action, const uint8_t* d_dice, int8_t* d_status,
                     uint64_t* d_valid_after, void* stream);
 
+/* ScriptPlayer::takeTurn (player/script/script_player.cpp:162-227) for the side to move of every running game: one WHOLE turn per
+   call (in the setup phase: the player's placement and the neutral placement), one ply.  h_script[n][2] carries the ScriptPlayer
+   members that survive between calls, one packed word per (game, side); initialise with AZ_SCRIPT_INIT.  Dice / ints come from the
+   scripted-opponent streams of the Philox contract (include/az_philox.h).  h_status as az_env_step. */
+#define AZ_SCRIPT_INIT 0x00ffffffu
+AZ_API int az_env_script_turn(az_env* env, uint32_t* h_script, int8_t* h_status, void* stream);
+
 /* NNInputData(State) + setInStateTensor (neural_network/alphazero_nn_data.cpp:165-196,
    alphazero_nn.cpp:31-67): fp32 [n][7][6][13] */
 AZ_API int az_env_encode(az_env* env, float* h_x, void* stream);
@@ -205,6 +212,26 @@ AZ_API int az_selfplay_samples(az_mcts* mcts, uint8_t* h_records, size_t max_rec
 AZ_API int az_samples_write_file(const char* path, const uint8_t* h_records, size_t n);
 /* counters since the last reset; *h_errors = node-pool + path-depth overflows (must be 0) */
 AZ_API int az_mcts_counters(az_mcts* mcts, az_counters* h_out, uint64_t* h_errors, int reset, void* stream);
+
+/* ---------------------------------------------------------------- arena: `-m play` on the device (SURVEY.md 8f N1 + N2)
+   executePlay (src/alphazero_risk.cpp:4-47) -> GameGroup::playGames(pg1, pg2, games) (game/game.cpp:277-312).  Every game slot of
+   the MCTS handle's env is one threadPlayGame: player index 0 = AlphaZeroPlayer (player/alpha_zero/alphazero_player.cpp:3-34: search,
+   argmax move, table trimmed when its turn starts and cleared at a new game), player index 1 = the opponent; slots claim games in
+   pairs like Counter::hasNext(2) (game.cpp:12-24) and play the second game of a pair as the mirror game when mirror_games != 0
+   (Game::newGame, game.cpp:170-191); results are GameResults (game/game.h:17-29). */
+#define AZ_OPPONENT_SCRIPT 1   /* ScriptPlayer, player/script/script_player.cpp:162-227, on the device */
+typedef struct az_arena az_arena;
+typedef struct az_arena_results {
+    uint64_t count;               /* GameResults::count */
+    uint64_t draw;                /* GameResults::draw */
+    uint64_t win[2];              /* GameResults::players[i].win (0 = AlphaZero, 1 = opponent) */
+    uint64_t win_and_started[2];  /* GameResults::players[i].winAndStartedGame */
+    uint64_t az_moves, az_sims, az_evals, opponent_turns, ticks, errors;
+} az_arena_results;
+AZ_API int az_arena_create(az_mcts* mcts, int opponent, int mirror_games, az_arena** out);
+AZ_API int az_arena_destroy(az_arena* arena);
+/* plays 2 * floor(n_games / 2) games (pairs, like the reference) over the env's slots; seed fixes the Philox contract */
+AZ_API int az_arena_play(az_arena* arena, uint64_t n_games, uint64_t seed, az_arena_results* h_out, void* stream);
 
 #ifdef __cplusplus
 }

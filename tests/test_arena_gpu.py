@@ -1,0 +1,127 @@
+"""GPU suite for SURVEY.md 8f N1 + N2: the device-side scripted opponent against the oracle's ScriptPlayer restatement (itself pinned
+to the compiled reference, tests/test_oracle_vs_ref.py) and the `-m play` arena (AlphaZero vs Script, mirror pairs, GameResults)
+against an oracle replay of the same match."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+SEED = 0x5EED0001
+
+
+@pytest.fixture(scope="module")
+def api():
+    from alphazero_risk_b200 import api as a
+    if a.lib().az_device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu suite must run on a B200")
+    return a
+
+
+def test_script_vs_script_lockstep(api):
+    """every game: both sides scripted, one whole turn per call, all 160 Data bytes equal to the oracle after every turn"""
+    n, first = 96, 7
+    env = api.Env(n, first_game_id=first)
+    env.reset(SEED)
+    script = np.full((n, 2), api.SCRIPT_INIT, np.uint32)
+    games = [po.OracleGame() for _ in range(n)]
+    sps = [[po.new_script(), po.new_script()] for _ in range(n)]
+    for g, o in enumerate(games):
+        o.new_game(SEED, first + g, 0)
+    turns = 0
+    for ply in range(120):
+        st = env.script_turn(script)
+        dev = env.export_aos()
+        for g, o in enumerate(games):
+            if o.status() != -1:
+                assert st[g] == -4
+                continue
+            assert o.script_turn(sps[g][o.s.cur], SEED, first + g, ply) == 0
+            turns += 1
+            assert st[g] == o.status()
+            assert (dev[g] == o.data()).all(), "game %d differs after turn %d" % (g, ply)
+    assert turns > n * 30 and all(o.status() != -1 for o in games)
+    env.close()
+
+
+def oracle_pair(slot_game, sims, ply0=0):
+    """one claimed pair on one slot, replayed on the oracle: AlphaZero (player 0, play mode, pseudo evaluator) vs Script (player 1),
+    fresh deal then the mirror game (Game::newGame, game/game.cpp:170-191); returns GameResults-style tallies, the final Data
+    image and the ply counter"""
+    rules = po.default_rules(mcts_simulations=sims, threads_per_mcts=1)
+    o, tree, sp = po.OracleGame(rules), po.OracleMcts(rules, "pseudo"), po.new_script()
+    res = dict(count=0, draw=0, win=[0, 0], was=[0, 0], az_moves=0, opp_turns=0)
+    ply = ply0
+    start = None
+    for player_start in (0, 1):
+        if player_start == 0:
+            o.new_game(SEED, slot_game, ply)
+            start = po.RoState.from_buffer_copy(o.s)
+        else:
+            o.s = po.RoState.from_buffer_copy(start)
+            o.invert_players()
+            o.s.cur = 1
+        tree.clear()
+        last = None
+        while o.status() == -1:
+            if o.s.cur == 1:
+                assert o.script_turn(sp, SEED, slot_game, ply) == 0
+                res["opp_turns"] += 1
+                last = 1
+            else:
+                if last != 0:
+                    tree.trim()            # AlphaZeroPlayer::takeTurn: trimNodes when its turn starts
+                a = tree.search(o, SEED, slot_game, ply)
+                mv = tree.pick(a["pi"], False, SEED, slot_game, ply)
+                assert o.move(mv, SEED, slot_game, ply) == 0
+                res["az_moves"] += 1
+                last = 0
+            ply += 1
+        st = o.status()
+        res["count"] += 1
+        if st == -2:
+            res["draw"] += 1
+        else:
+            res["win"][st] += 1
+            res["was"][st] += int(st == player_start)
+    return res, o.data(), ply
+
+
+def test_arena_one_pair_per_slot_matches_oracle(api):
+    """n slots, 2n games: every slot claims exactly one mirror pair, so the whole match is deterministic and must equal the oracle replay"""
+    n, first, sims = 10, 40, 8
+    env = api.Env(n, rules=api.default_rules(mcts_simulations=sims, threads_per_mcts=1), first_game_id=first)
+    mc = api.Mcts(env, evaluator=api.EVAL_PSEUDO)
+    arena = api.Arena(mc, api.OPPONENT_SCRIPT, mirror_games=True)
+    r = arena.play(2 * n, SEED)
+    assert r["errors"] == 0 and r["count"] == 2 * n
+    dev = env.export_aos()
+    tot = dict(count=0, draw=0, win=[0, 0], was=[0, 0], az_moves=0, opp_turns=0)
+    for g in range(n):
+        res, data, _ = oracle_pair(first + g, sims)
+        assert (dev[g] == data).all(), "slot %d: final position differs from the oracle replay" % g
+        for k in ("count", "draw", "az_moves", "opp_turns"):
+            tot[k] += res[k]
+        for i in range(2):
+            tot["win"][i] += res["win"][i]; tot["was"][i] += res["was"][i]
+    assert (r["count"], r["draw"], r["win"], r["win_and_started"]) == (tot["count"], tot["draw"], tot["win"], tot["was"])
+    assert r["az_moves"] == tot["az_moves"] and r["opponent_turns"] == tot["opp_turns"] and r["az_sims"] == tot["az_moves"] * sims
+    arena.close(); mc.close(); env.close()
+
+
+def test_arena_claims_pairs_like_the_counter(api):
+    """more games than slots, odd request: 2 * floor(n / 2) games are played (Counter::hasNext(2)), tallies are consistent"""
+    n, sims = 6, 4
+    env = api.Env(n, rules=api.default_rules(mcts_simulations=sims, threads_per_mcts=1), first_game_id=0)
+    mc = api.Mcts(env, evaluator=api.EVAL_UNIFORM)
+    arena = api.Arena(mc, api.OPPONENT_SCRIPT, mirror_games=True)
+    r = arena.play(27, SEED)
+    assert r["errors"] == 0 and r["count"] == 26
+    assert r["draw"] + r["win"][0] + r["win"][1] == 26
+    assert r["win_and_started"][0] <= r["win"][0] and r["win_and_started"][1] <= r["win"][1]
+    assert r["az_sims"] == r["az_moves"] * sims and r["opponent_turns"] > 26 * 13
+    r2 = arena.play(4, SEED + 1)          # the handle can be reused for another match
+    assert r2["count"] == 4 and r2["errors"] == 0
+    arena.close(); mc.close(); env.close()
