@@ -587,6 +587,7 @@ extern "C" int az_mcts_create(az_env* env, az_nn* nn, int evaluator, int precisi
     int sims = r->mcts_simulations - (r->mcts_simulations % T);          // alphazero_mcts.cpp:265
     AZ_REQUIRE(sims >= 1, "mcts_simulations - mcts_simulations % threads_per_mcts must be >= 1");
     AzDeviceGuard guard(az_env_device(env));
+    if (evaluator == EVAL_NN && !nn->finalized) { int frc = az_nn_finalize(nn); if (frc) return frc; }   // weights loaded but not yet folded / packed
     az_mcts* mc = new (std::nothrow) az_mcts();
     AZ_REQUIRE(mc != nullptr, "out of host memory");
     mc->env = env; mc->nn = nn; mc->evaluator = evaluator; mc->precision = precision; mc->device = az_env_device(env);

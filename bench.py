@@ -282,6 +282,34 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
                 dtype="bf16 tower / fp32 tree", results={"games_finished": tot_games, "table_errors": errors})
 
 
+def run_play(args, api, torch, rank, local):
+    """BASELINE configs[0] on the device: `-m play --mcts=16 --cg=1000` — AlphaZero (random-init 5-block net, bf16 tcgen05 forward,
+    16 simulations per move = MCTS_SIMULATIONS 16 with the default 2 search threads) against the scripted opponent, mirror pairs.
+    The reference runs 32 concurrent game threads; here every pair gets its own slot so the whole match is one lockstep batch."""
+    games = args.play_games - args.play_games % 2
+    slots = max(1, games // 2)
+    stream = torch.cuda.current_stream(); sptr = stream.cuda_stream
+    rules = api.default_rules(mcts_simulations=16, threads_per_mcts=2)
+    env = api.Env(slots, rules=rules, device=local, first_game_id=rank * slots)
+    net = api.Net(blocks=args.blocks, device=local, seed=1234)
+    mc = api.Mcts(env, net=net, evaluator=api.EVAL_NN, precision=api.BF16)
+    arena = api.Arena(mc, api.OPPONENT_SCRIPT, mirror_games=True)
+    arena.play(min(games, 2 * min(slots, 64)), SEED + 7, stream=sptr)          # warm-up match
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    r = arena.play(games, SEED, stream=sptr)
+    e1.record(stream); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    arena.close(); mc.close(); net.close(); env.close()
+    return dict(metric="play_games_per_sec", value=r["count"] / (ms * 1e-3), unit="games/s", ms=ms,
+                az_sims_per_sec=r["az_sims"] / (ms * 1e-3), az_moves=r["az_moves"], opponent_turns=r["opponent_turns"],
+                results={"count": r["count"], "draw": r["draw"], "win_az_script": r["win"], "win_and_started": r["win_and_started"],
+                         "errors": r["errors"]},
+                config={"workload": "configs[0]: -m play --mcts=16 --cg=%d, AlphaZero (random-init %d-block net, bf16) vs ScriptPlayer, both "
+                                    "on the device, %d lockstep slots x 1 mirror pair" % (games, args.blocks, slots)})
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -363,6 +391,10 @@ def run_ours(args):
     if not args.no_selfplay:
         mcts_line = run_selfplay(args, api, torch, dist, rank, world, local, barrier)
 
+    play_line = None
+    if args.play_games >= 2 and rank == 0 and world == 1:
+        play_line = run_play(args, api, torch, rank, local)
+
     if rank == 0:
         hbm_peak, _, src = measured_peaks()
         total_steps = n * S * args.steps * world
@@ -387,6 +419,8 @@ def run_ours(args):
         if mcts_line is not None:
             line["mcts"] = mcts_line
             line["gpu_launches"] += mcts_line["gpu_launches"]
+        if play_line is not None:
+            line["play"] = play_line
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_env_baseline(12.0)
             line["cpu_baseline"] = cb
@@ -413,6 +447,7 @@ def main():
     ap.add_argument("--sp-moves", type=int, default=2, help="self-play moves per timed step")
     ap.add_argument("--sp-steps", type=int, default=4, help="max timed self-play steps")
     ap.add_argument("--blocks", type=int, default=5)
+    ap.add_argument("--play-games", type=int, default=1000, help="configs[0] match size (--cg); 0 skips it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
