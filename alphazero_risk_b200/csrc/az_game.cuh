@@ -275,7 +275,7 @@ __device__ __forceinline__ void az_fortify_source(const AzGame& g, const LandT& 
 {
     const uint64_t owned = g.own(g.cur);
     uint64_t comp = 1ull << li;
-    for (;;) { uint64_t n = (comp | az_nbr_union(T, comp)) & owned; if (n == comp) break; comp = n; }
+    for (;;) { uint64_t n = (comp | az_nbr_union(T, comp)) & owned; if (n == comp) break; comp = n; }   // (a per-land BFS has fewer instructions but a longer dependent chain: measured 4 % slower)
     from_out = -1; amount_out = 0;
     uint64_t cand = comp & ~(1ull << li) & g.gt1;                       // army - 1 > 0
     if (cand == 0) return;

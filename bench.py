@@ -244,12 +244,17 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
     sp_clocks = sampler.stop() if rank == 0 else None
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     cnt = mc.counters(stream=sptr)
-    # e2e: one az_mcts_search call per move through the host-buffer ABI (visit counts, pi, moves, status copied back)
+    # e2e: the call a host-side game loop makes per move — State images in from pinned host memory (az_env_import_aos), one
+    # az_mcts_search through the host-buffer ABI (visit counts, pi, moves, status copied back), images out again
     e2e_moves = max(2, moves_per_step)
+    h_img = torch.empty((n, 160), dtype=torch.uint8).pin_memory()
+    env.export_aos(out=h_img.numpy(), stream=sptr)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_moves):
+        env.import_aos(h_img.numpy(), stream=sptr)
         mc.search(pick_mode=api.PICK_SELFPLAY, apply_move=True, stream=sptr)
+        env.export_aos(out=h_img.numpy(), stream=sptr)
     barrier()
     e2e_s = time.perf_counter() - t0
     dev_ms, e2e_ms = dev_ms, e2e_s * 1e3
@@ -276,8 +281,8 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
                                   "that (executed_frac); the forward runs at the board's 1 kW power cap (clocks.reasons: sw_power_cap), "
                                   "like the cuBLAS run the peak comes from; traffic = DRAM bytes of one tower-layer launch (ncu)"},
                 clocks=sp_clocks,
-                e2e={"value": n * sims * e2e_moves * world / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": 0,
-                     "d2h_bytes_per_step": n * (43 * 8 + 2), "steps": e2e_moves},
+                e2e={"value": n * sims * e2e_moves * world / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": n * 160,
+                     "d2h_bytes_per_step": n * (43 * 8 + 2 + 160), "steps": e2e_moves},
                 gpu_launches=steps * moves_per_step * (2 + (sims + 1) * (2 + 1 + 2 * blocks + 1 + 1)),
                 dtype="bf16 tower / fp32 tree", results={"games_finished": tot_games, "table_errors": errors})
 

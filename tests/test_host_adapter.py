@@ -10,16 +10,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "host", "test_nn_service")
 
 
-def build_exe():
+PLAY_EXE = os.path.join(ROOT, "tests", "host", "test_play")
+
+
+def build_exe(name="test_nn_service"):
     from alphazero_risk_b200 import build
     build.build()
-    src = os.path.join(ROOT, "tests", "host", "test_nn_service.cpp")
-    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(src), os.path.getmtime(build.LIB)):
+    src = os.path.join(ROOT, "tests", "host", name + ".cpp")
+    exe = os.path.join(ROOT, "tests", "host", name)
+    hdrs = [os.path.join(ROOT, "alphazero_risk_b200", "host", h) for h in ("az_nn_service.hpp", "az_play.hpp")]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max([os.path.getmtime(src), os.path.getmtime(build.LIB)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + os.path.join(ROOT, "include"),
-                               "-I" + os.path.join(ROOT, "alphazero_risk_b200", "host"), src, "-o", EXE,
+                               "-I" + os.path.join(ROOT, "alphazero_risk_b200", "host"), src, "-o", exe,
                                "-L" + os.path.join(ROOT, "alphazero_risk_b200"), "-laz_b200",
                                "-Wl,-rpath," + os.path.join(ROOT, "alphazero_risk_b200"), "-Wl,-rpath,$ORIGIN/../../alphazero_risk_b200"])
-    return EXE
+    return exe
 
 
 def test_adapter_compiles_and_has_no_cpu_fallback():
@@ -36,3 +41,20 @@ def test_adapter_batches_concurrent_requests():
     exe = build_exe() if os.path.exists("/usr/bin/g++") or os.path.exists("/opt/gcc/bin/g++") else EXE
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "SERVICE_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_play_adapter_compiles_and_has_no_cpu_fallback():
+    exe = build_exe("test_play")
+    from alphazero_risk_b200 import api
+    if api.lib().az_device_count() > 0:
+        pytest.skip("a GPU is present")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "NO_DEVICE_OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_play_adapter_runs_a_match():
+    """GameGroup::playGames(az group, script group, 41) through azb200::DevicePlay: 40 games, reproducible tallies"""
+    exe = build_exe("test_play") if os.path.exists("/usr/bin/g++") or os.path.exists("/opt/gcc/bin/g++") else PLAY_EXE
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "PLAY_OK" in out.stdout, out.stdout + out.stderr
