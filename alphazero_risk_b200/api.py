@@ -92,6 +92,7 @@ def lib():
         L.az_mcts_counters.argtypes = [vp, C.POINTER(AzCounters), C.POINTER(C.c_uint64), C.c_int, vp]
         L.az_selfplay_record.argtypes = [vp, C.c_size_t, C.c_int]
         L.az_env_script_turn.argtypes = [vp, vp, vp, vp]
+        L.az_env_random_turn.argtypes = [vp, vp, vp]
         L.az_arena_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
         L.az_arena_destroy.argtypes = [vp]
         L.az_arena_play.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(AzArenaResults), vp]
@@ -179,6 +180,12 @@ class Env:
         """ScriptPlayer::takeTurn for the side to move of every running game; `script` = uint32 [n, 2] (in/out), SCRIPT_INIT at first"""
         st = np.empty(self.n, np.int8)
         check(self.L.az_env_script_turn(self.h, _ptr(script), _ptr(st), stream))
+        return st
+
+    def random_turn(self, stream=None):
+        """RandomPlayer::takeTurn for the side to move of every running game"""
+        st = np.empty(self.n, np.int8)
+        check(self.L.az_env_random_turn(self.h, _ptr(st), stream))
         return st
 
     def encode(self, stream=None):
@@ -274,7 +281,7 @@ class Net:
 
 
 EVAL_NN, EVAL_PSEUDO, EVAL_UNIFORM = 0, 1, 2
-OPPONENT_SCRIPT = 1
+OPPONENT_SCRIPT, OPPONENT_RANDOM = 1, 2
 SCRIPT_INIT = 0x00ffffff
 
 

@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout(uint32_t* __restrict_
 // ScriptPlayer::takeTurn for the side to move of every running game (one whole turn per call, one ply)
 __global__ void __launch_bounds__(ENV_BLOCK) k_env_script_turn(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
                                                                 uint32_t* __restrict__ script, int8_t* __restrict__ status,
-                                                                uint64_t seed, uint32_t first_game, AzRulesDev rules)
+                                                                uint64_t seed, uint32_t first_game, AzRulesDev rules, int kind)
 {
     __shared__ EnvSmem sm;
     AzTables T = env_stage_tables(sm, g_tab);
@@ -317,9 +317,13 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_script_turn(uint32_t* __restr
     if (out != AZ_STATUS_RUNNING) out = AZ_STATUS_OVER;
     else {
         const uint32_t side = c.g.cur;
-        uint32_t spw = script[(size_t)gi * 2 + side];
-        const int rc = az_script_turn(c.g, c.land, c.scratch, T, rules, spw, seed, first_game + (uint32_t)gi, c.ply);
-        if (rc == 0) { script[(size_t)gi * 2 + side] = spw; c.ply++; env_store(c, sm, st, n, gi); out = az_game_status(c.g, rules); }
+        uint32_t spw = kind == AZ_OPPONENT_SCRIPT ? script[(size_t)gi * 2 + side] : 0u;
+        const int rc = kind == AZ_OPPONENT_SCRIPT ? az_script_turn(c.g, c.land, c.scratch, T, rules, spw, seed, first_game + (uint32_t)gi, c.ply)
+                                                  : az_random_turn(c.g, c.land, c.scratch, T, rules, seed, first_game + (uint32_t)gi, c.ply);
+        if (rc == 0) {
+            if (kind == AZ_OPPONENT_SCRIPT) script[(size_t)gi * 2 + side] = spw;
+            c.ply++; env_store(c, sm, st, n, gi); out = az_game_status(c.g, rules);
+        }
         else out = rc;
     }
     status[gi] = (int8_t)out;
@@ -391,6 +395,7 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_arena_advance(ArenaDev a, const u
         if (c.g.cur == 1u) {                                          // the opponent's whole turn
             uint32_t spw = a.script[(size_t)gi * 2 + 1];
             if (a.opponent == AZ_OPPONENT_SCRIPT) az_script_turn(c.g, c.land, c.scratch, T, rules, spw, a.seed, game, c.ply);
+            else az_random_turn(c.g, c.land, c.scratch, T, rules, a.seed, game, c.ply);
             a.script[(size_t)gi * 2 + 1] = spw;
             c.ply++;
             atomicAdd(&a.res[ARENA_OPP_TURNS], 1ull);
@@ -708,9 +713,23 @@ extern "C" int az_env_script_turn(az_env* e, uint32_t* h_script, int8_t* h_statu
     rc = ensure(&e->d_status, (size_t)e->n); if (rc) return rc;
     AZ_CUDA(cudaMemcpyAsync(e->d_script, h_script, sizeof(uint32_t) * 2 * (size_t)e->n, cudaMemcpyHostToDevice, s));
     k_env_script_turn<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), e->d_script, e->d_status, e->seed,
-                                                            e->first_game, dev_rules(e->rules));
+                                                            e->first_game, dev_rules(e->rules), AZ_OPPONENT_SCRIPT);
     AZ_CUDA(cudaGetLastError());
     AZ_CUDA(cudaMemcpyAsync(h_script, e->d_script, sizeof(uint32_t) * 2 * (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(h_status, e->d_status, (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+extern "C" int az_env_random_turn(az_env* e, int8_t* h_status, void* stream)
+{
+    AZ_REQUIRE(e && h_status, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = ensure(&e->d_status, (size_t)e->n); if (rc) return rc;
+    k_env_script_turn<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), nullptr, e->d_status, e->seed,
+                                                            e->first_game, dev_rules(e->rules), AZ_OPPONENT_RANDOM);
+    AZ_CUDA(cudaGetLastError());
     AZ_CUDA(cudaMemcpyAsync(h_status, e->d_status, (size_t)e->n, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaStreamSynchronize(s));
     return AZ_OK;

@@ -831,7 +831,7 @@ template <class T> static int aalloc(az_arena* ar, T** p, size_t count)
 extern "C" int az_arena_create(az_mcts* mc, int opponent, int mirror_games, az_arena** out)
 {
     AZ_REQUIRE(mc && out, "NULL argument");
-    AZ_REQUIRE(opponent == AZ_OPPONENT_SCRIPT, "unknown opponent kind");
+    AZ_REQUIRE(opponent == AZ_OPPONENT_SCRIPT || opponent == AZ_OPPONENT_RANDOM, "unknown opponent kind");
     AzDeviceGuard guard(mc->device);
     az_arena* ar = new (std::nothrow) az_arena();
     AZ_REQUIRE(ar != nullptr, "out of host memory");

@@ -266,3 +266,107 @@ __device__ __forceinline__ int az_script_turn(AzGame& g, LandT& land, ScratchT& 
     sp_word = c.sp.pack();
     return 0;
 }
+
+// ---------------------------------------------------------------- RandomPlayer
+// RandomPlayer::takeTurn, /root/reference/src/risk_game/player/random/random_player.cpp:22-111: uniformly random moves on the State
+// primitives (one army per reinforcement move, random attack-from land, coin-flip mobilisation, random fortify amount) until the
+// turn passes.  pickRandomMove = one rInt() (k-th lowest set bit, k = rInt() % count), the coin = one rFloat(); both advance the
+// opponent word sequence (az_rng_opp_word); dice from AZ_STREAM_OPP.
+template <class LandT>
+struct AzRandomCtx {
+    uint64_t seed; uint32_t game, ply, int_j;
+    __device__ __forceinline__ int pick(uint64_t mask)
+    {
+        const uint32_t k = az_rng_opp_int(seed, game, ply, int_j++) % (uint32_t)__popcll(mask);
+        return az_nth_set_bit(mask, k);
+    }
+};
+
+template <class LandT, class ScratchT>
+__device__ __forceinline__ int az_random_turn(AzGame& g, LandT& land, ScratchT& scratch, const AzTables& T, const AzRulesDev& r,
+                                              uint64_t seed, uint32_t game, uint32_t ply)
+{
+    AzScriptCtx<LandT> c(g, land, T, r);                 // only for az_script_attack (State::attackMove with sequential dice)
+    c.dice.init(seed, game, ply, AZ_STREAM_OPP);
+    AzRandomCtx<LandT> rc; rc.seed = seed; rc.game = game; rc.ply = ply; rc.int_j = 0;
+    const uint32_t me = g.cur;
+    int guard = 0;
+    while (az_game_status(g, r) == AZ_STATUS_RUNNING && g.cur == me && ++guard < 8192) {
+        const uint64_t owned = g.own(me);
+        switch (g.phase) {
+        case AZ_PH_SETUP: {
+            const int li = rc.pick(owned);
+            g.reinf = (g.reinf - 2) & 0xff;
+            az_set_land(g, land, li, (land.get(li) & 63u) + 2, me);
+            g.phase = AZ_PH_SETUP_NEUTRAL;
+            break;
+        }
+        case AZ_PH_SETUP_NEUTRAL: {
+            const int li = rc.pick(AZ_ALL_LANDS & ~g.own0 & ~g.own1);
+            az_set_land(g, land, li, (land.get(li) & 63u) + 1, AZ_NEUTRAL);
+            g.phase = AZ_PH_SETUP; g.round = (g.round + 1) & 0xffff; g.cur ^= 1u;
+            if (g.reinf == 0) { g.phase = AZ_PH_REINFORCEMENT; g.reinf = (uint32_t)az_reinforcement_value(g.own(g.cur)); }
+            break;
+        }
+        case AZ_PH_REINFORCEMENT: {
+            uint32_t cards = me ? g.cards1 : g.cards0;
+            if (cards >= 3) {
+                cards -= 3;
+                if (me) g.cards1 = cards; else g.cards0 = cards;
+                g.card_sets = (g.card_sets + 1) & 0xff;
+                const int cs = (int)g.card_sets;
+                g.reinf = (g.reinf + (uint32_t)(cs <= 5 ? 2 + 2 * cs : 15 + (cs - 6) * 5)) & 0xff;
+            }
+            const int li = rc.pick(owned & ~g.full);
+            g.reinf = (g.reinf - 1) & 0xff;
+            az_set_land(g, land, li, (land.get(li) & 63u) + 1, me);
+            if (g.reinf == 0) az_goto_attack(g, T);
+            break;
+        }
+        case AZ_PH_ATTACK: {
+            const int li = rc.pick(az_attack_army(g, T, me) | AZ_SKIP_MASK);
+            if (li == AZ_SKIP) g.phase = AZ_PH_FORTIFY;
+            else {
+                const int from = rc.pick(T.nbr[li] & owned & g.gt1);
+                az_script_attack(c, from, li);
+            }
+            break;
+        }
+        case AZ_PH_MOBILIZATION: {
+            const float f = az_rng_unit_float(az_rng_opp_word(seed, game, ply, rc.int_j++));
+            if (f > 0.5f) {
+                const int af = (int)(land.get(g.mob_from) & 63u), at = (int)(land.get(g.mob_to) & 63u);
+                int amount = af - 1;
+                if (r.min_unit_move < amount) amount = r.min_unit_move;
+                const uint32_t mf = g.mob_from, mt = g.mob_to;
+                az_set_land(g, land, (int)mf, (uint32_t)(af - amount), me);
+                az_set_land(g, land, (int)mt, (uint32_t)(at + amount), me);
+                if (af - amount == 1) az_goto_attack(g, T);
+            } else az_goto_attack(g, T);
+            break;
+        }
+        default: {
+            const int to = rc.pick((owned & ~g.full) | AZ_SKIP_MASK);
+            if (to != AZ_SKIP) {
+                uint64_t comp = 1ull << to;
+                for (;;) { const uint64_t n = (comp | az_nbr_union(T, comp)) & owned; if (n == comp) break; comp = n; }
+                const uint64_t pool = comp & ~(1ull << to) & g.gt1;
+                if (pool) {
+                    const int from = rc.pick(pool);
+                    const int af = (int)(land.get(from) & 63u), at = (int)(land.get(to) & 63u);
+                    int amount = af - 1;
+                    const int space = AZ_ARMY_MAX - at;
+                    if (space < amount) amount = space;
+                    const int moved = (int)(az_rng_opp_int(seed, game, ply, rc.int_j++) % (uint32_t)amount);
+                    az_set_land(g, land, from, (uint32_t)(af - moved), me);
+                    az_set_land(g, land, to, (uint32_t)(at + moved), me);
+                }
+            }
+            az_end_turn(g);
+            break;
+        }
+        }
+    }
+    (void)scratch;
+    return 0;
+}

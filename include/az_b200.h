@@ -125,6 +125,8 @@ AZ_API int az_env_step_dev(az_env* env, const uint8_t* d_action, const uint8_t* 
    scripted-opponent streams of the Philox contract (include/az_philox.h).  h_status as az_env_step. */
 #define AZ_SCRIPT_INIT 0x00ffffffu
 AZ_API int az_env_script_turn(az_env* env, uint32_t* h_script, int8_t* h_status, void* stream);
+/* RandomPlayer::takeTurn (player/random/random_player.cpp:22-111), same calling convention (the random player keeps no members) */
+AZ_API int az_env_random_turn(az_env* env, int8_t* h_status, void* stream);
 
 /* NNInputData(State) + setInStateTensor (neural_network/alphazero_nn_data.cpp:165-196,
    alphazero_nn.cpp:31-67): fp32 [n][7][6][13] */
@@ -220,6 +222,7 @@ AZ_API int az_mcts_counters(az_mcts* mcts, az_counters* h_out, uint64_t* h_error
    pairs like Counter::hasNext(2) (game.cpp:12-24) and play the second game of a pair as the mirror game when mirror_games != 0
    (Game::newGame, game.cpp:170-191); results are GameResults (game/game.h:17-29). */
 #define AZ_OPPONENT_SCRIPT 1   /* ScriptPlayer, player/script/script_player.cpp:162-227, on the device */
+#define AZ_OPPONENT_RANDOM 2   /* RandomPlayer, player/random/random_player.cpp:22-111, on the device */
 typedef struct az_arena az_arena;
 typedef struct az_arena_results {
     uint64_t count;               /* GameResults::count */

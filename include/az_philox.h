@@ -38,7 +38,8 @@
  * and draws an unbounded number of dice: they are consumed sequentially from the stream sim = AZ_STREAM_OPP of the
  * (game, ply) at which the turn starts (one ply per opponent turn), exactly like the reference consumes its engine.
  * Its rInt() draws (Utility::randomMask in the setup phase, land/land.cpp:100-112: rInt() % count) come from
- * sim = AZ_STREAM_OPP_INT: draw i = word (i % 4) of block (i / 4), shifted right by one (a non-negative int).
+ * sim = AZ_STREAM_OPP_INT: draw i = word (i % 4) of block (i / 4), shifted right by one (a non-negative int); RandomPlayer's
+ * rFloat() (player/random/random_player.cpp:66) takes the next word of the same sequence as (word >> 8) * 2^-24.
  *
  * Plain C99 / CUDA; no dependencies.
  */
@@ -125,11 +126,15 @@ AZ_HD uint32_t az_rng_deal_draw(uint64_t seed, uint32_t game, uint32_t ply, uint
     return az_mulhi32(az_u32x4_word(blk, (int)(i & 3u)), 42u - i);
 }
 
-/* i-th rInt() of a scripted opponent's turn */
-AZ_HD uint32_t az_rng_opp_int(uint64_t seed, uint32_t game, uint32_t ply, uint32_t i)
+/* i-th non-dice draw of a scripted opponent's turn: rInt() = word >> 1, rFloat() = az_rng_unit_float(word); both advance i */
+AZ_HD uint32_t az_rng_opp_word(uint64_t seed, uint32_t game, uint32_t ply, uint32_t i)
 {
     az_u32x4 blk = az_rng_block(seed, game, ply, AZ_STREAM_OPP_INT, i >> 2);
-    return az_u32x4_word(blk, (int)(i & 3u)) >> 1;
+    return az_u32x4_word(blk, (int)(i & 3u));
+}
+AZ_HD uint32_t az_rng_opp_int(uint64_t seed, uint32_t game, uint32_t ply, uint32_t i)
+{
+    return az_rng_opp_word(seed, game, ply, i) >> 1;
 }
 
 AZ_HD float az_rng_unit_float(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }

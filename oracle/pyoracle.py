@@ -91,6 +91,7 @@ def oracle_lib():
         L.ro_script_init.argtypes = [C.POINTER(RoScript)]
         L.ro_script_turn.argtypes = [sp, C.POINTER(RoScript), rp, C.c_uint64, C.c_uint32, C.c_uint32]
         L.ro_invert_players.argtypes = [sp]
+        L.ro_random_turn.argtypes = [sp, rp, C.c_uint64, C.c_uint32, C.c_uint32]
         L.ro_sample_record.argtypes = [sp, f32p, C.c_int, u8p]
         L.ro_mcts_new.restype = C.c_void_p
         L.ro_mcts_new.argtypes = [C.c_void_p, C.c_void_p]
@@ -171,6 +172,10 @@ class OracleGame:
     def script_turn(self, script, seed, game, ply):
         """ScriptPlayer::takeTurn on this game; `script` = RoScript carrying the player's members between turns"""
         return int(self.L.ro_script_turn(C.byref(self.s), C.byref(script), C.byref(self.rules), seed, game, ply))
+
+    def random_turn(self, seed, game, ply):
+        """RandomPlayer::takeTurn on this game"""
+        return int(self.L.ro_random_turn(C.byref(self.s), C.byref(self.rules), seed, game, ply))
 
     def invert_players(self):
         self.L.ro_invert_players(C.byref(self.s))
@@ -257,6 +262,10 @@ def ref_lib():
         L.ref_script_free.argtypes = [vp]
         L.ref_script_turn.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]
         L.ref_state_invert_players.argtypes = [vp]
+        L.ref_random_new.restype = vp
+        L.ref_random_new.argtypes = [C.c_int]
+        L.ref_random_free.argtypes = [vp]
+        L.ref_random_turn.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]
         L.ref_state_set_current_player.argtypes = [vp, C.c_int]
         L.ref_save_samples.argtypes = [C.c_char_p, C.c_int, np.ctypeslib.ndpointer(np.int8), u8p, f32p, C.c_int, C.c_int]
         L.ref_consistency_violations.argtypes = [vp]
@@ -343,6 +352,10 @@ class RefGame:
     def script_turn(self, script, seed, game, ply):
         """`script` = handle from ref_lib().ref_script_new() (a reference ScriptPlayer object)"""
         return int(self.L.ref_script_turn(script, self.s, seed, game, ply))
+
+    def random_turn(self, player, seed, game, ply):
+        """`player` = handle from ref_lib().ref_random_new(side)"""
+        return int(self.L.ref_random_turn(player, self.s, seed, game, ply))
 
     def invert_players(self):
         self.L.ref_state_invert_players(self.s)

@@ -112,6 +112,7 @@ public:
 		{
 		case REF_RNG_PHILOX:
 		{
+			if (c.sim == AZ_STREAM_OPP) return az_rng_unit_float(az_rng_opp_word(c.seed, c.game, c.ply, c.int_j++));
 			az_u32x4 b = az_rng_block(c.seed, c.game, c.ply, AZ_STREAM_REAL, 0);
 			return az_rng_unit_float(b.z);
 		}

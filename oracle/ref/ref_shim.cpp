@@ -29,6 +29,7 @@
 #include "risk_game/player/alpha_zero/alphazero_mcts.h"
 #include "risk_game/player/alpha_zero/neural_network/alphazero_nn.h"
 #include "risk_game/player/script/script_player.h"
+#include "risk_game/player/random/random_player.h"
 
 #include "az_philox.h"
 #include "az_pseudo_net.h"
@@ -203,6 +204,18 @@ REF_API int ref_script_turn(void* p, void* s, uint64_t seed, uint32_t game, uint
 	RefRngCtx& c = ref_rng_ctx();
 	c.mode = REF_RNG_PHILOX; c.seed = seed; c.game = game; c.ply = ply; c.sim = AZ_STREAM_OPP; c.die_j = 0; c.int_j = 0;
 	try { ((ScriptPlayer*)p)->takeTurn(*(State*)s); }
+	catch (std::exception& e) { snprintf(g_err, sizeof g_err, "%s", e.what()); c.mode = REF_RNG_ENGINE; c.sim = AZ_STREAM_REAL; return -1; }
+	c.mode = REF_RNG_ENGINE; c.sim = AZ_STREAM_REAL;
+	return 0;
+}
+/* ---- RandomPlayer (player/random/random_player.cpp:22-111); playerIndexTurn = the side it plays (Game::addPlayer, game.cpp:86-90) */
+REF_API void* ref_random_new(int side) { RandomPlayer* p = new RandomPlayer(); p->playerIndexTurn = (int8_t)side; return p; }
+REF_API void ref_random_free(void* p) { delete (RandomPlayer*)p; }
+REF_API int ref_random_turn(void* p, void* s, uint64_t seed, uint32_t game, uint32_t ply)
+{
+	RefRngCtx& c = ref_rng_ctx();
+	c.mode = REF_RNG_PHILOX; c.seed = seed; c.game = game; c.ply = ply; c.sim = AZ_STREAM_OPP; c.die_j = 0; c.int_j = 0;
+	try { ((RandomPlayer*)p)->takeTurn(*(State*)s); }
 	catch (std::exception& e) { snprintf(g_err, sizeof g_err, "%s", e.what()); c.mode = REF_RNG_ENGINE; c.sim = AZ_STREAM_REAL; return -1; }
 	c.mode = REF_RNG_ENGINE; c.sim = AZ_STREAM_REAL;
 	return 0;

@@ -729,6 +729,99 @@ int ro_script_turn(ro_state* s, ro_script* sp, const ro_rules* r, uint64_t seed,
     return RO_OK;
 }
 
+
+/* RandomPlayer::takeTurn, player/random/random_player.cpp:22-111: uniformly random moves on the State primitives until the turn
+   passes.  Every pickRandomMove is one rInt() (k-th lowest set bit, k = rInt() % count), the mobilisation coin is one rFloat(),
+   both from the opponent word sequence; dice from the opponent dice stream. */
+static int random_pick(script_ctx* c, uint64_t mask)
+{
+    int k = (int)(az_rng_opp_int(c->seed, c->game, c->ply, c->int_j++) % (uint32_t)popc(mask));
+    while (k--) mask &= mask - 1;
+    return ctz(mask);
+}
+
+int ro_random_turn(ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply)
+{
+    if (ro_game_status(s, r) != RO_NOT_ENDED) return RO_ERR_GAME_OVER;
+    script_ctx c; memset(&c, 0, sizeof c);
+    c.s = s; c.r = r; c.seed = seed; c.game = game; c.ply = ply;
+    const int me = s->cur;
+    while (ro_game_status(s, r) == RO_NOT_ENDED && s->cur == me) {
+        derived d; derive(s, &d);
+        switch (s->phase) {
+        case RO_SETUP: {
+            int li = random_pick(&c, d.owned[me]);
+            s->reinf = (uint8_t)(s->reinf - 2);
+            set_land(s, li, army_of(s, li) + 2, me);
+            s->phase = RO_SETUP_NEUTRAL;
+            break;
+        }
+        case RO_SETUP_NEUTRAL: {
+            int li = random_pick(&c, ALL_LANDS & ~d.owned[0] & ~d.owned[1]);
+            set_land(s, li, army_of(s, li) + 1, RO_NEUTRAL);
+            s->phase = RO_SETUP; s->round++; s->cur ^= 1;
+            if (s->reinf == 0) {
+                derive(s, &d);
+                s->phase = RO_REINFORCEMENT; s->reinf = (uint8_t)ro_reinforcement_value(d.owned[s->cur]);
+            }
+            break;
+        }
+        case RO_REINFORCEMENT: {
+            if (s->cards[me] >= 3) {
+                s->cards[me] = (uint8_t)(s->cards[me] - 3);
+                s->card_sets = (uint8_t)(s->card_sets + 1);
+                int cs = s->card_sets;
+                s->reinf = (uint8_t)(s->reinf + (cs <= 5 ? 2 + 2 * cs : 15 + (cs - 6) * 5));
+            }
+            int li = random_pick(&c, d.owned[me] & ~d.full[me]);
+            s->reinf = (uint8_t)(s->reinf - 1);                      /* reinforcementMove(1, li) */
+            set_land(s, li, army_of(s, li) + 1, me);
+            if (s->reinf == 0) goto_attack(s);
+            break;
+        }
+        case RO_ATTACK: {
+            int li = random_pick(&c, d.attack_army[me] | SKIP_MASK);
+            if (li == RO_SKIP) s->phase = RO_FORTIFY;                 /* gotoFortify */
+            else {
+                int from = random_pick(&c, RO_NBR_MASK[li] & d.owned_army[me]);
+                script_attack(&c, from, li);
+            }
+            break;
+        }
+        case RO_ATTACK_MOBILIZATION: {
+            float f = az_rng_unit_float(az_rng_opp_word(seed, game, ply, c.int_j++));
+            if (f > 0.5f) {
+                int amount = army_of(s, s->mob_from) - 1;
+                if (r->min_unit_move < amount) amount = r->min_unit_move;
+                set_land(s, s->mob_from, army_of(s, s->mob_from) - amount, me);
+                set_land(s, s->mob_to, army_of(s, s->mob_to) + amount, me);
+                if (army_of(s, s->mob_from) == 1) goto_attack(s);
+            } else goto_attack(s);
+            break;
+        }
+        default: { /* FORTIFY */
+            int to = random_pick(&c, (d.owned[me] & ~d.full[me]) | SKIP_MASK);
+            if (to != RO_SKIP) {
+                uint64_t seen = 0; int order[RO_LANDS], n = 0;
+                dfs(to, d.owned[me], &seen, order, &n);               /* the owned component that holds `to` */
+                uint64_t pool = seen & ~(1ull << to) & d.owned_army[me];
+                if (pool) {
+                    int from = random_pick(&c, pool);
+                    int amount = army_of(s, from) - 1, space = RO_ARMY_MAX - army_of(s, to);
+                    if (space < amount) amount = space;
+                    int moved = (int)(az_rng_opp_int(seed, game, ply, c.int_j++) % (uint32_t)amount);
+                    set_land(s, from, army_of(s, from) - moved, me);
+                    set_land(s, to, army_of(s, to) + moved, me);
+                }
+            }
+            end_turn(s);
+            break;
+        }
+        }
+    }
+    return RO_OK;
+}
+
 /* Game::newGame's mirror game, game/game.cpp:170-179: State::invertPlayers (state.cpp:493-516) + setCurrentPlayerTurn */
 void ro_invert_players(ro_state* s)
 {

@@ -105,6 +105,7 @@ void ro_normalize_policy(float policy[RO_MOVES], uint64_t valid);               
 typedef struct ro_script { int8_t set, to, from; uint8_t from_army; } ro_script;   /* attackingLandSet / landAttackTo / landAttackFrom / attackFromArmy */
 void ro_script_init(ro_script* sp);
 int ro_script_turn(ro_state* s, ro_script* sp, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply);  /* ScriptPlayer::takeTurn */
+int ro_random_turn(ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply);                 /* RandomPlayer::takeTurn */
 void ro_invert_players(ro_state* s);                                             /* State::invertPlayers */
 #define RO_NN_INPUT_BYTES 88   /* sizeof(NNInputData), alphazero_nn_data.h:73-101 */
 #define RO_SAMPLE_BYTES 265    /* 1 + 88 + 4 + 43 * 4, alphazero_nn_data.cpp:115-138 */

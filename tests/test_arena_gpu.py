@@ -46,7 +46,31 @@ def test_script_vs_script_lockstep(api):
     env.close()
 
 
-def oracle_pair(slot_game, sims, ply0=0):
+def test_random_vs_random_lockstep(api):
+    """RandomPlayer::takeTurn on the device, both sides, against the oracle restatement: all Data bytes after every turn"""
+    n, first = 64, 2000
+    env = api.Env(n, first_game_id=first)
+    env.reset(SEED)
+    games = [po.OracleGame() for _ in range(n)]
+    for g, o in enumerate(games):
+        o.new_game(SEED, first + g, 0)
+    turns = 0
+    for ply in range(110):
+        st = env.random_turn()
+        dev = env.export_aos()
+        for g, o in enumerate(games):
+            if o.status() != -1:
+                assert st[g] == -4
+                continue
+            assert o.random_turn(SEED, first + g, ply) == 0
+            turns += 1
+            assert st[g] == o.status()
+            assert (dev[g] == o.data()).all(), "game %d differs after turn %d" % (g, ply)
+    assert turns > n * 40
+    env.close()
+
+
+def oracle_pair(slot_game, sims, ply0=0, opponent="script"):
     """one claimed pair on one slot, replayed on the oracle: AlphaZero (player 0, play mode, pseudo evaluator) vs Script (player 1),
     fresh deal then the mirror game (Game::newGame, game/game.cpp:170-191); returns GameResults-style tallies, the final Data
     image and the ply counter"""
@@ -67,7 +91,7 @@ def oracle_pair(slot_game, sims, ply0=0):
         last = None
         while o.status() == -1:
             if o.s.cur == 1:
-                assert o.script_turn(sp, SEED, slot_game, ply) == 0
+                assert (o.script_turn(sp, SEED, slot_game, ply) if opponent == "script" else o.random_turn(SEED, slot_game, ply)) == 0
                 res["opp_turns"] += 1
                 last = 1
             else:
@@ -89,18 +113,19 @@ def oracle_pair(slot_game, sims, ply0=0):
     return res, o.data(), ply
 
 
-def test_arena_one_pair_per_slot_matches_oracle(api):
+@pytest.mark.parametrize("opponent", ["script", "random"])
+def test_arena_one_pair_per_slot_matches_oracle(api, opponent):
     """n slots, 2n games: every slot claims exactly one mirror pair, so the whole match is deterministic and must equal the oracle replay"""
-    n, first, sims = 10, 40, 8
+    n, first, sims = (10, 40, 8) if opponent == "script" else (6, 90, 8)
     env = api.Env(n, rules=api.default_rules(mcts_simulations=sims, threads_per_mcts=1), first_game_id=first)
     mc = api.Mcts(env, evaluator=api.EVAL_PSEUDO)
-    arena = api.Arena(mc, api.OPPONENT_SCRIPT, mirror_games=True)
+    arena = api.Arena(mc, api.OPPONENT_SCRIPT if opponent == "script" else api.OPPONENT_RANDOM, mirror_games=True)
     r = arena.play(2 * n, SEED)
     assert r["errors"] == 0 and r["count"] == 2 * n
     dev = env.export_aos()
     tot = dict(count=0, draw=0, win=[0, 0], was=[0, 0], az_moves=0, opp_turns=0)
     for g in range(n):
-        res, data, _ = oracle_pair(first + g, sims)
+        res, data, _ = oracle_pair(first + g, sims, opponent=opponent)
         assert (dev[g] == data).all(), "slot %d: final position differs from the oracle replay" % g
         for k in ("count", "draw", "az_moves", "opp_turns"):
             tot[k] += res[k]

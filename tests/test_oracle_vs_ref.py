@@ -120,3 +120,34 @@ def test_script_player_lockstep(mode):
         for h in rs:
             L.ref_script_free(h)
     assert turns > 300
+
+
+@pytest.mark.parametrize("opponent", ["random_vs_random", "random_vs_script"])
+def test_random_player_lockstep(opponent):
+    """ro_random_turn == the UNMODIFIED RandomPlayer::takeTurn (player/random/random_player.cpp:22-111), every Data field after
+    every turn, with the opponent RNG streams of include/az_philox.h"""
+    L = po.ref_lib()
+    po.ref_apply_rules(po.default_rules())
+    mask = po.data_byte_mask().astype(bool)
+    turns = 0
+    for g in range(14):
+        ref, orc = po.RefGame(), po.OracleGame()
+        ref.new_game(SEED, 300 + g, 0); orc.new_game(SEED, 300 + g, 0)
+        rp = [L.ref_random_new(0), L.ref_random_new(1)]
+        rs, os_ = L.ref_script_new(), po.new_script()
+        ply = 0
+        while ref.status() == -1 and ply < 500:
+            cur = orc.s.cur
+            if opponent == "random_vs_random" or cur == 0:
+                assert ref.random_turn(rp[cur], SEED, 300 + g, ply) == 0, L.ref_last_error()
+                assert orc.random_turn(SEED, 300 + g, ply) == 0
+                turns += 1
+            else:
+                assert ref.script_turn(rs, SEED, 300 + g, ply) == 0 and orc.script_turn(os_, SEED, 300 + g, ply) == 0
+            ply += 1
+            assert (ref.data()[mask] == orc.data()[mask]).all(), "game %d ply %d" % (g, ply)
+            assert ref.status() == orc.status() and ref.violations() == 0
+        for h in rp:
+            L.ref_random_free(h)
+        L.ref_script_free(rs)
+    assert turns > 250
