@@ -557,6 +557,8 @@ int az_launch_arena_advance(const ArenaDev& a, const az_rules* rules, cudaStream
 }
 
 
+extern "C" int az_env_destroy(az_env* e);
+
 extern "C" int az_env_create(int n_games, const az_rules* rules, int device, uint32_t first_game_id, az_env** out)
 {
     AZ_REQUIRE(out != nullptr, "out is NULL");
@@ -571,13 +573,21 @@ extern "C" int az_env_create(int n_games, const az_rules* rules, int device, uin
     AZ_REQUIRE(e != nullptr, "out of host memory");
     e->n = n_games; e->device = device; e->first_game = first_game_id;
     if (rules) e->rules = *rules; else az_default_rules(&e->rules);
-    AZ_CUDA(cudaMalloc(&e->d_state, sizeof(uint32_t) * AZ_STATE_WORDS * (size_t)n_games));
-    AZ_CUDA(cudaMemset(e->d_state, 0, sizeof(uint32_t) * AZ_STATE_WORDS * (size_t)n_games));
-    AZ_CUDA(cudaMalloc(&e->d_counters, 8 * sizeof(unsigned long long)));
-    AZ_CUDA(cudaMemset(e->d_counters, 0, 8 * sizeof(unsigned long long)));
-    AZ_CUDA(cudaMalloc(&e->d_bad, sizeof(int)));
-    AZ_CUDA(cudaEventCreate(&e->ev0));
-    AZ_CUDA(cudaEventCreate(&e->ev1));
+    // a failed allocation must not leak the handle or what was allocated before it
+    const size_t state_bytes = sizeof(uint32_t) * AZ_STATE_WORDS * (size_t)n_games;
+    cudaError_t ce = cudaMalloc(&e->d_state, state_bytes);
+    if (ce == cudaSuccess) ce = cudaMemset(e->d_state, 0, state_bytes);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_counters, 8 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMemset(e->d_counters, 0, 8 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_bad, sizeof(int));
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev1);
+    if (ce != cudaSuccess) {
+        az_set_error("az_env_create(%d games): %s", n_games, cudaGetErrorString(ce));
+        cudaGetLastError();
+        az_env_destroy(e);
+        return AZ_ERR_CUDA;
+    }
     *out = e;
     return AZ_OK;
 }

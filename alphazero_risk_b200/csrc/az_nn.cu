@@ -268,8 +268,9 @@ extern "C" int az_nn_create(int blocks, int device, az_nn** out)
             int y = p / 6 + t / 3 - 1, x = p % 6 + t % 3 - 1;
             nb[p * 9 + t] = (y < 0 || y >= 7 || x < 0 || x >= 6) ? (int8_t)-1 : (int8_t)(y * 6 + x);
         }
-    AZ_CUDA(cudaMemcpyToSymbol(c_nb, nb, sizeof nb));
-    AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(F32_SMEM_FLOATS * sizeof(float))));
+    cudaError_t ce = cudaMemcpyToSymbol(c_nb, nb, sizeof nb);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_nn_conv_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(F32_SMEM_FLOATS * sizeof(float)));
+    if (ce != cudaSuccess) { az_set_error("az_nn_create: %s", cudaGetErrorString(ce)); cudaGetLastError(); delete nn; return AZ_ERR_CUDA; }
     *out = nn;
     return AZ_OK;
 }
