@@ -74,7 +74,9 @@ const uint64_t* az_device_tables()
 }
 
 // ---------------------------------------------------------------- per-thread game context
-#define ENV_BLOCK 128
+#ifndef ENV_BLOCK
+#define ENV_BLOCK 256      // swept 32..256 on B200 (tools/env_block.sh): 13.7 / 13.8 / 13.8 / 14.2 G steps/s — the kernel is latency bound per warp
+#endif
 #define ENV_COL_WORDS 22     // 11 land words + 11 fortify-DFS parent words per thread
 
 struct EnvSmem {
