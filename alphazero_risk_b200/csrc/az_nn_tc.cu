@@ -54,6 +54,7 @@ template <int KCH> struct TcShape {
     static constexpr int STAGE_BYTES = CH_PER_STAGE * 256 * 16;
     static constexpr int A_BYTES = KCH * TC_A_ROWS * 16;              // one A buffer
     static constexpr int SMEM_BYTES = 2 * A_BYTES + TC_STAGES * STAGE_BYTES + 2 * 256 * 4 + 32 * 8 + 16;
+    static constexpr int smem_bytes(int nv) { return 2 * nv * A_BYTES + TC_STAGES * STAGE_BYTES + 2 * 256 * 4 + 32 * 8 + 16; }
 };
 
 struct AzTcState {
@@ -62,7 +63,10 @@ struct AzTcState {
     __nv_bfloat16* d_in = nullptr;                             // [2][r_alloc][8]: encoded input, 13 channels padded to 16
     uint8_t* d_wpacked = nullptr;                              // [2*blocks] x 1.18 MB tower weights, then the 72 KB stem weights
     uint8_t* d_wpacked2 = nullptr;                             // tower weights in the CTA-pair layout (output channels split in two halves per stage)
-    int pair_mode = 1, max_pairs = 74;                         // tower on CTA pairs (k_nn_conv_tc2) unless AZ_TC_MODE=single
+    int pair_mode = 1, max_pairs = 74;                         // tower on CTA pairs (k_nn_conv_tc2 / tc3) unless AZ_TC_MODE=single
+    int rpb = 49;                                              // rows per board: 49 (masked-copy layout, k_nn_conv_tc3) or 56 (AZ_TC_LAYOUT=56)
+    uint8_t* d_wpacked3 = nullptr;                             // tower weights for k_nn_conv_tc3: [K group][tap][half]
+    size_t in_var_stride = 0;                                  // elements between the three copies of the encoded input (49-row layout)
     float* d_scale = nullptr; float* d_shift = nullptr;        // [2*blocks][256] folded BN, then [256] (7 used) for the stem's row BN
     float* d_x = nullptr;                                      // fp32 encode of the leaf states
 };
@@ -180,23 +184,35 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
 #define TC_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24))
 #define TC2_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24))   // M = 256 over the CTA pair
 
-__device__ __forceinline__ bool tc_row_valid(int r, int n_boards)
+// Two board layouts (rows per board = rpb):
+//   56: cell (y, x) -> row y*7 + x, zero column x = 6 and zero row-group y = 7 (taps are plain shifts of ONE operand)
+//   49: cell (y, x) -> row y*6 + x, seven zero rows behind the 42 cells.  The zero rows still serve as top / bottom border; the
+//       left / right border comes from two masked copies of the operand: taps with kx = 0 read the copy whose x = 5 cells are
+//       zero, taps with kx = 2 the copy whose x = 0 cells are zero (what they would wrongly pick up from the neighbouring board
+//       row is exactly such a cell).  12.5 % fewer rows = 12.5 % fewer MMAs for a forward that runs at the board's power cap.
+__device__ __forceinline__ int tc_cell_row(int p, int rpb) { return rpb == 56 ? (p / 6) * 7 + (p % 6) : p; }
+__device__ __forceinline__ bool tc_row_valid(int r, int n_boards, int rpb)
 {
-    int b = r / TC_ROWS_PER_BOARD, p = r - b * TC_ROWS_PER_BOARD;
-    return b < n_boards && p < 49 && (p % 7) != 6;
+    int b = r / rpb, p = r - b * rpb;
+    return b < n_boards && (rpb == 56 ? (p < 49 && (p % 7) != 6) : p < 42);
 }
+__device__ __forceinline__ int tc_row_y(int r, int rpb) { int p = r % rpb; return rpb == 56 ? p / 7 : p / 6; }
+__device__ __forceinline__ int tc_tap_shift(int tap, int rpb) { return (tap / 3 - 1) * (rpb == 56 ? 7 : 6) + (tap % 3 - 1); }
+__device__ __forceinline__ int tc_tap_variant(int tap, int rpb) { return rpb == 56 ? 0 : (tap % 3 == 0 ? 1 : (tap % 3 == 2 ? 2 : 0)); }
 
 // ---------------------------------------------------------------- conv3x3 on tensor cores (tower and stem)
-template <int KCH, bool ROW_BN>
+// NV = operand copies per A buffer: 1 (56-row layout) or 3 (49-row layout: plain, x=5 zeroed, x=0 zeroed — read from three global
+// arrays var_stride_bytes apart; only used for the 2-chunk stem, the tower builds its copies in shared memory, k_nn_conv_tc3)
+template <int KCH, bool ROW_BN, int NV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ wpacked, const float* __restrict__ scale,
              const float* __restrict__ shift, const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
-             int n_boards, int r_alloc, int n_tiles)
+             int n_boards, int r_alloc, int n_tiles, int rpb, size_t var_stride_bytes)
 {
     using S = TcShape<KCH>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sA = smem;                                   // 2 x A_BYTES
-    uint8_t* sB = smem + 2 * S::A_BYTES;                  // TC_STAGES x STAGE_BYTES
+    uint8_t* sA = smem;                                   // 2 x NV x A_BYTES
+    uint8_t* sB = smem + 2 * NV * S::A_BYTES;             // TC_STAGES x STAGE_BYTES
     float* s_scale = reinterpret_cast<float*>(sB + TC_STAGES * S::STAGE_BYTES);
     float* s_shift = s_scale + 256;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
@@ -231,10 +247,11 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
             auto load_a = [&](int j, int tile) {
                 const int b = j & 1;
                 if (j >= 2) mbar_wait(bar_a_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
-                mbar_expect_tx(bar_a_full + b, S::A_BYTES);
-                for (int c = 0; c < KCH; ++c)
-                    bulk_g2s(sA + (size_t)b * S::A_BYTES + (size_t)c * TC_A_ROWS * 16,
-                             src + ((size_t)c * r_alloc + (size_t)tile * TC_TILE_ROWS) * 16, TC_A_ROWS * 16, bar_a_full + b);
+                mbar_expect_tx(bar_a_full + b, NV * S::A_BYTES);
+                for (int v = 0; v < NV; ++v)
+                    for (int c = 0; c < KCH; ++c)
+                        bulk_g2s(sA + (size_t)(b * NV + v) * S::A_BYTES + (size_t)c * TC_A_ROWS * 16,
+                                 src + (size_t)v * var_stride_bytes + ((size_t)c * r_alloc + (size_t)tile * TC_TILE_ROWS) * 16, TC_A_ROWS * 16, bar_a_full + b);
             };
             uint32_t wit = 0;
             int j = 0;
@@ -266,12 +283,12 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
                     mbar_wait(bar_w_full + s, k & 1u);
                     tc_fence_after();
                     const int tap = it / S::KBLOCKS, kb = it - tap * S::KBLOCKS;
-                    const int sh = (tap / 3 - 1) * 7 + (tap % 3 - 1);
+                    const int sh = tc_tap_shift(tap, rpb), var = NV > 1 ? tc_tap_variant(tap, rpb) : 0;
 #pragma unroll
                     for (int kk = 0; kk < S::KSTEPS; ++kk) {
                         const uint64_t bdesc = umma_desc(b_base + (uint32_t)(s * S::STAGE_BYTES + kk * 2 * 256 * 16), 256 * 16, 128);
                         const int chunk0 = kb * S::CH_PER_STAGE + kk * 2;
-                        const uint64_t adesc = umma_desc(a_base + (uint32_t)(b * S::A_BYTES + (chunk0 * TC_A_ROWS + TC_HALO + sh) * 16), TC_A_ROWS * 16, 128);
+                        const uint64_t adesc = umma_desc(a_base + (uint32_t)((b * NV + var) * S::A_BYTES + (chunk0 * TC_A_ROWS + TC_HALO + sh) * 16), TC_A_ROWS * 16, 128);
                         tc_mma_bf16(tmem_base + (uint32_t)(b * 256), adesc, bdesc, TC_IDESC, (it > 0 || kk > 0) ? 1u : 0u);
                     }
                     tc_commit(bar_w_empty + s);          // frees the weight stage when these MMAs retire
@@ -290,8 +307,8 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
             tc_fence_after();
             {
             const int r = tile * TC_TILE_ROWS + q * 32 + lane;                 // padded row of this thread
-            const bool valid = tc_row_valid(r, n_boards);
-            const int yrow = (r % TC_ROWS_PER_BOARD) / 7;                      // board row (stem BatchNorm index)
+            const bool valid = tc_row_valid(r, n_boards, rpb);
+            const int yrow = tc_row_y(r, rpb);                                 // board row (stem BatchNorm index)
             // the residual input is prefetched TC_SKIP_AHEAD chunks ahead (ncu, round 1: with a load-then-use skip read the
             // branch2b layers ran 285 us against 220 us for the branch2a layers — the epilogue, not the MMA, set the tile time)
             const size_t cell0 = ((size_t)TC_HALO + r) * 8;
@@ -494,7 +511,7 @@ k_nn_conv_tc2(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
             tc_fence_after();
             if (tile < n_tiles) {
                 const int r = tile * TC_TILE_ROWS + q * 32 + lane;
-                const bool valid = tc_row_valid(r, n_boards);
+                const bool valid = tc_row_valid(r, n_boards, 56);
                 const size_t cell0 = ((size_t)TC_HALO + r) * 8;
                 const size_t cstride = (size_t)r_alloc * 8;
                 uint4 skq[TC_SKIP_AHEAD];
@@ -545,15 +562,235 @@ k_nn_conv_tc2(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
     }
 }
 
+
+// ---------------------------------------------------------------- tower conv3x3 on a CTA pair, 49-row board layout
+// Same CTA-pair structure as k_nn_conv_tc2 (tcgen05 cta_group::2, half of the weights per CTA), on the 49-row layout: the A operand
+// exists in three copies in shared memory (plain / x=5 cells zeroed / x=0 cells zeroed, see tc_tap_variant), so it no longer fits
+// twice.  The K loop is therefore turned inside out — K group (32 channels) outer, the nine taps inner — and the operand lives in a
+// RING of K groups: a group's slot is refilled for the next tile as soon as its nine taps have retired.
+//   warp 0      : streams the plain copy of K groups T3_LA groups ahead (4 x 2.3 KB bulk copies) and the weight half-stages
+//   warp 6      : "masker" — when a group has landed, writes its two masked copies with ordinary shared-memory stores, makes them
+//                 visible to the tensor core (fence.proxy.async) and signals this CTA's and the leader's "group ready" barrier
+//   warp 1      : leader: MMA issue (kb outer, tap inner); peer: relays "weight half landed"
+//   warps 2..5  : epilogue, as before
+#define T3_THREADS 224
+#define T3_G 5                                               // ring slots
+#define T3_LA 3                                              // operand prefetch distance in K groups (<= T3_G - 2, see the streamer)
+#define T3_VAR_BYTES (4 * TC_A_ROWS * 16)                    // one copy of one K group: 4 chunks x 144 rows x 16 B = 9216
+#define T3_SLOT_BYTES (3 * T3_VAR_BYTES)
+#define T3_SMEM_BYTES (T3_G * T3_SLOT_BYTES + TC2_STAGES * TC2_STAGE_BYTES + 2 * 256 * 4 + 64 * 8 + 16)
+
+__global__ void __launch_bounds__(T3_THREADS, 1)
+k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ wpacked3, const float* __restrict__ scale,
+              const float* __restrict__ shift, const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
+              int n_boards, int r_alloc, int n_tiles)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;                                   // T3_G x T3_SLOT_BYTES
+    uint8_t* sB = smem + T3_G * T3_SLOT_BYTES;            // TC2_STAGES x TC2_STAGE_BYTES
+    float* s_scale = reinterpret_cast<float*>(sB + TC2_STAGES * TC2_STAGE_BYTES);
+    float* s_shift = s_scale + 256;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+    uint64_t* bar_a_full = bars;                          // [T3_G] plain copy of the group landed
+    uint64_t* bar_a_ready = bars + 8;                     // [T3_G] masked copies written (this CTA)
+    uint64_t* bar_pa_ready = bars + 16;                   // [T3_G] leader only: the peer's group is ready
+    uint64_t* bar_a_empty = bars + 24;                    // [T3_G] the group's MMAs retired (leader commit, both CTAs)
+    uint64_t* bar_acc_full = bars + 32;                   // [2]
+    uint64_t* bar_acc_empty = bars + 34;                  // [2] leader only, 8 epilogue warps of the pair
+    uint64_t* bar_w_full = bars + 36;                     // [TC2_STAGES]
+    uint64_t* bar_w_empty = bars + 36 + TC2_STAGES;
+    uint64_t* bar_pw_full = bars + 36 + 2 * TC2_STAGES;   // leader only
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 64);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const bool leader = crank == 0;
+    const int n_pairs = (int)(gridDim.x >> 1), pid = (int)(blockIdx.x >> 1);
+    const int n_items = (n_tiles + 1) >> 1;
+    const int my_items = pid < n_items ? (n_items - pid + n_pairs - 1) / n_pairs : 0;
+    const int total_groups = my_items * 8;
+    auto tile_of_group = [&](int q) {                     // the 128-row tile this CTA works on while consuming K group q
+        int tile = 2 * (pid + (q >> 3) * n_pairs) + (int)crank;
+        return tile < n_tiles ? tile : n_tiles - 1;       // odd tile count: the peer's last tile is multiplied, never stored
+    };
+
+    for (int i = threadIdx.x; i < 256; i += T3_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < T3_G; ++g) { mbar_init(bar_a_full + g, 1); mbar_init(bar_a_ready + g, 1); mbar_init(bar_pa_ready + g, 1); mbar_init(bar_a_empty + g, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, 8); }
+        for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(bar_w_full + s, 1); mbar_init(bar_w_empty + s, 1); mbar_init(bar_pw_full + s, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- operand streamer.  Group q + T3_LA is requested while group q's weights are being issued; its slot was last used
+            // by group q + T3_LA - T3_G <= q - 2, whose MMAs have retired by then (the weight ring keeps this thread less than
+            // one group ahead of the MMA issuer), so the wait below never stalls the weight stream.
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(in);
+            auto load_group = [&](int q) {
+                const int slot = q % T3_G, rnd = q / T3_G, kb = q & 7, tile = tile_of_group(q);
+                if (rnd > 0) mbar_wait_cluster(bar_a_empty + slot, (uint32_t)((rnd - 1) & 1));
+                mbar_expect_tx(bar_a_full + slot, T3_VAR_BYTES);
+                for (int c = 0; c < 4; ++c)
+                    bulk_g2s(sA + (size_t)slot * T3_SLOT_BYTES + (size_t)c * TC_A_ROWS * 16,
+                             src + ((size_t)(kb * 4 + c) * r_alloc + (size_t)tile * TC_TILE_ROWS) * 16, TC_A_ROWS * 16, bar_a_full + slot);
+            };
+            for (int q = 0; q < T3_LA && q < total_groups; ++q) load_group(q);
+            uint32_t wit = 0;
+            for (int q = 0; q < total_groups; ++q) {
+                if (q + T3_LA < total_groups) load_group(q + T3_LA);
+                const int kb = q & 7;
+                for (int tap = 0; tap < 9; ++tap, ++wit) {
+                    const uint32_t s = wit % TC2_STAGES, k = wit / TC2_STAGES;
+                    if (k > 0) mbar_wait_cluster(bar_w_empty + s, (k - 1) & 1u);
+                    mbar_expect_tx(bar_w_full + s, TC2_STAGE_BYTES);
+                    bulk_g2s(sB + (size_t)s * TC2_STAGE_BYTES, wpacked3 + ((size_t)(kb * 9 + tap) * 2 + crank) * TC2_STAGE_BYTES, TC2_STAGE_BYTES, bar_w_full + s);
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ---- masker: A_L (x = 5 cells zero) and A_R (x = 0 cells zero) of every landed group
+        for (int q = 0; q < total_groups; ++q) {
+            const int slot = q % T3_G, rnd = q / T3_G;
+            const int row0 = tile_of_group(q) * TC_TILE_ROWS - TC_HALO;          // board-layout row of the slot's first operand row (may be < 0: halo of tile 0)
+            mbar_wait(bar_a_full + slot, (uint32_t)(rnd & 1));
+            uint8_t* base = sA + (size_t)slot * T3_SLOT_BYTES;
+            for (int idx = lane; idx < 4 * TC_A_ROWS; idx += 32) {
+                const int row = idx % TC_A_ROWS;
+                const int p = (row0 + row + 49) % 49;                             // row0 + row >= -8
+                const int x = p < 42 ? p % 6 : -1;
+                const uint4 cell = *reinterpret_cast<const uint4*>(base + (size_t)idx * 16);
+                const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(base + T3_VAR_BYTES + (size_t)idx * 16) = x == 5 ? zero : cell;
+                *reinterpret_cast<uint4*>(base + 2 * T3_VAR_BYTES + (size_t)idx * 16) = x == 0 ? zero : cell;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar_a_ready + slot); if (!leader) mbar_arrive_remote(bar_pa_ready + slot, 0u); }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ---- MMA issuer (leader CTA): K group outer, taps inner
+            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+            uint32_t wit = 0;
+            for (int j = 0; j < my_items; ++j) {
+                const int b = j & 1;
+                if (j >= 2) mbar_wait_cluster(bar_acc_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
+                for (int kb = 0; kb < 8; ++kb) {
+                    const int q = j * 8 + kb, slot = q % T3_G, rnd = q / T3_G;
+                    mbar_wait(bar_a_ready + slot, (uint32_t)(rnd & 1));
+                    mbar_wait_cluster(bar_pa_ready + slot, (uint32_t)(rnd & 1));
+                    tc_fence_after();
+                    for (int tap = 0; tap < 9; ++tap, ++wit) {
+                        const uint32_t s = wit % TC2_STAGES, k = wit / TC2_STAGES;
+                        mbar_wait(bar_w_full + s, k & 1u);
+                        mbar_wait_cluster(bar_pw_full + s, k & 1u);
+                        tc_fence_after();
+                        const int sh = tc_tap_shift(tap, 49), var = tc_tap_variant(tap, 49);
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint64_t bdesc = umma_desc(b_base + (uint32_t)(s * TC2_STAGE_BYTES + kk * 2 * 128 * 16), 128 * 16, 128);
+                            const uint64_t adesc = umma_desc(a_base + (uint32_t)(slot * T3_SLOT_BYTES + var * T3_VAR_BYTES + (kk * 2 * TC_A_ROWS + TC_HALO + sh) * 16), TC_A_ROWS * 16, 128);
+                            tc2_mma_bf16(tmem_base + (uint32_t)(b * 256), adesc, bdesc, TC2_IDESC, (kb > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                        }
+                        tc2_commit(bar_w_empty + s);
+                    }
+                    tc2_commit(bar_a_empty + slot);
+                }
+                tc2_commit(bar_acc_full + b);
+            }
+        } else if (lane == 0) {
+            // ---- relay (peer CTA): this CTA's weight halves have landed
+            const uint32_t total_stages = (uint32_t)total_groups * 9u;
+            for (uint32_t wit = 0; wit < total_stages; ++wit) {
+                const uint32_t s = wit % TC2_STAGES, k = wit / TC2_STAGES;
+                mbar_wait(bar_w_full + s, k & 1u);
+                mbar_arrive_remote(bar_pw_full + s, 0u);
+            }
+        }
+    } else {
+        // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 of this CTA's half of the pair's accumulator
+        const int q4 = warp & 3;
+        for (int j = 0; j < my_items; ++j) {
+            const int b = j & 1;
+            const int tile = 2 * (pid + j * n_pairs) + (int)crank;
+            mbar_wait_cluster(bar_acc_full + b, (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            if (tile < n_tiles) {
+                const int r = tile * TC_TILE_ROWS + q4 * 32 + lane;
+                const bool valid = tc_row_valid(r, n_boards, 49);
+                const size_t cell0 = ((size_t)TC_HALO + r) * 8;
+                const size_t cstride = (size_t)r_alloc * 8;
+                uint4 skq[TC_SKIP_AHEAD];
+                if (skip) {
+#pragma unroll
+                    for (int p = 0; p < TC_SKIP_AHEAD; ++p) skq[p] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)p * cstride));
+                }
+#pragma unroll 4
+                for (int c = 0; c < TC_CHUNKS; ++c) {
+                    uint32_t v[8];
+                    tc_ld8(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * 256 + c * 8), v);
+                    uint4 sk = make_uint4(0u, 0u, 0u, 0u);
+                    if (skip) {
+                        sk = skq[c % TC_SKIP_AHEAD];
+                        if (c + TC_SKIP_AHEAD < TC_CHUNKS)
+                            skq[c % TC_SKIP_AHEAD] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)(c + TC_SKIP_AHEAD) * cstride));
+                    }
+                    tc_ld_wait();
+                    const size_t cell = cell0 + (size_t)c * cstride;
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[e]), s_scale[c * 8 + e], s_shift[c * 8 + e]);
+                    if (skip) {
+                        const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sk);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(s2[e]); f[2 * e] += x.x; f[2 * e + 1] += x.y; }
+                    }
+                    uint4 o;
+                    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float x0 = valid ? fmaxf(f[2 * e], 0.0f) : 0.0f, x1 = valid ? fmaxf(f[2 * e + 1], 0.0f) : 0.0f;
+                        o2[e] = __floats2bfloat162_rn(x0, x1);
+                    }
+                    *reinterpret_cast<uint4*>(out + cell) = o;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (leader) mbar_arrive(bar_acc_empty + b); else mbar_arrive_remote(bar_acc_empty + b, 0u); }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- input packing + heads on the padded bf16 layout
 // fp32 [n][42][13] -> bf16 [2 chunks][r_alloc][8] (channels 13..15 = 0); thread = board cell
-__global__ void __launch_bounds__(256) k_nn_pack_input_tc(const float* __restrict__ x, int n, __nv_bfloat16* __restrict__ out, int r_alloc)
+// (49-row layout: three copies var_stride elements apart — plain, x = 5 cells zeroed, x = 0 cells zeroed — for the stem's taps)
+__global__ void __launch_bounds__(256) k_nn_pack_input_tc(const float* __restrict__ x, int n, __nv_bfloat16* __restrict__ out, int r_alloc,
+                                                           int rpb, size_t var_stride)
 {
     int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n * 42) return;
     int b = i / 42, p = i - b * 42;
     const float* src = x + (size_t)i * AZ_NN_IN_CH;
-    int row = b * TC_ROWS_PER_BOARD + (p / 6) * 7 + (p % 6);
+    int row = b * rpb + tc_cell_row(p, rpb);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         uint4 o;
@@ -564,7 +801,13 @@ __global__ void __launch_bounds__(256) k_nn_pack_input_tc(const float* __restric
             float a = c0 < AZ_NN_IN_CH ? src[c0] : 0.0f, bb = c0 + 1 < AZ_NN_IN_CH ? src[c0 + 1] : 0.0f;
             o2[e] = __floats2bfloat162_rn(a, bb);
         }
-        *reinterpret_cast<uint4*>(out + ((size_t)c * r_alloc + TC_HALO + row) * 8) = o;
+        const size_t at = ((size_t)c * r_alloc + TC_HALO + row) * 8;
+        *reinterpret_cast<uint4*>(out + at) = o;
+        if (rpb == 49) {
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(out + var_stride + at) = (p % 6) == 5 ? zero : o;
+            *reinterpret_cast<uint4*>(out + 2 * var_stride + at) = (p % 6) == 0 ? zero : o;
+        }
     }
 }
 
@@ -577,7 +820,7 @@ __device__ __forceinline__ float warp_sum_tc(float v)
 
 // policy + value heads for HB boards per block (the head weights, 60 KB, are read once per block instead of once per board)
 #define HB 8
-__global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __restrict__ act, int n, int r_alloc, AzHeadParams hp,
+__global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __restrict__ act, int n, int r_alloc, int rpb, AzHeadParams hp,
                                                       float* __restrict__ policy, float* __restrict__ value)
 {
     __shared__ float s_pi[HB][84], s_v[HB][42], s_logit[HB][44], s_red[HB][8];
@@ -591,7 +834,7 @@ __global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __rest
     const float scv = hp.bn_v[0] * rsqrtf(hp.bn_v[3] + AZ_NN_BN_EPS);
     for (int i = warp; i < nb * 42; i += 8) {
         const int bl = i / 42, p = i - bl * 42;
-        const int row = (b0 + bl) * TC_ROWS_PER_BOARD + (p / 6) * 7 + (p % 6);
+        const int row = (b0 + bl) * rpb + tc_cell_row(p, rpb);
         const uint4 cell = *reinterpret_cast<const uint4*>(act + ((size_t)lane * r_alloc + TC_HALO + row) * 8);
         const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cell);
         float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
@@ -679,7 +922,8 @@ static void pack_conv(const float* w, int cin, int kch, __nv_bfloat16* dst)
 }
 
 // HWIO fp32 [3][3][256][256] -> bf16 [tap][K block of 32][half of the output channels][chunk 4][128 out][8]: one 8 KB stage per CTA of a pair
-static void pack_conv_pair(const float* w, __nv_bfloat16* dst)
+// (kb_outer: stages ordered [K block][tap] for k_nn_conv_tc3 instead of [tap][K block])
+static void pack_conv_pair(const float* w, __nv_bfloat16* dst, bool kb_outer)
 {
     for (int tap = 0; tap < 9; ++tap)
         for (int kb = 0; kb < 8; ++kb)
@@ -688,8 +932,21 @@ static void pack_conv_pair(const float* w, __nv_bfloat16* dst)
                     for (int n = 0; n < 128; ++n)
                         for (int e = 0; e < 8; ++e) {
                             const int ci = (kb * 4 + ch) * 8 + e, co = h * 128 + n;
-                            dst[(((((size_t)tap * 8 + kb) * 2 + h) * 4 + ch) * 128 + n) * 8 + e] = __float2bfloat16_rn(w[((size_t)tap * 256 + ci) * 256 + co]);
+                            const size_t stage = kb_outer ? (size_t)kb * 9 + tap : (size_t)tap * 8 + kb;
+                            dst[((((stage * 2 + h) * 4 + ch) * 128 + n) * 8) + e] = __float2bfloat16_rn(w[((size_t)tap * 256 + ci) * 256 + co]);
                         }
+}
+
+static cudaError_t launch_conv_pair3(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w3, const float* scale, const float* shift,
+                                     const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles);
 }
 
 static cudaError_t launch_conv_pair(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w2, const float* scale, const float* shift,
@@ -705,11 +962,12 @@ static cudaError_t launch_conv_pair(int grid, cudaStream_t s, const __nv_bfloat1
 }
 
 // persistent launch of one stem / one-CTA tower convolution
-template <int KCH, bool ROW_BN>
+template <int KCH, bool ROW_BN, int NV>
 static cudaError_t launch_conv(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w, const float* scale, const float* shift,
-                               const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles)
+                               const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles, int rpb, size_t var_stride_bytes)
 {
-    k_nn_conv_tc<KCH, ROW_BN><<<grid, TC_THREADS, TcShape<KCH>::SMEM_BYTES, s>>>(in, w, scale, shift, skip, out, n_boards, r_alloc, n_tiles);
+    k_nn_conv_tc<KCH, ROW_BN, NV><<<grid, TC_THREADS, TcShape<KCH>::smem_bytes(NV), s>>>(in, w, scale, shift, skip, out, n_boards, r_alloc, n_tiles,
+                                                                                        rpb, var_stride_bytes);
     return cudaGetLastError();
 }
 
@@ -719,7 +977,7 @@ int az_nn_tc_prepare(az_nn* nn)
     AzTcState* tc = nn->tc;
     const int layers = 2 * nn->blocks;
     std::vector<uint8_t> packed((size_t)layers * TC_LAYER_BYTES + TC_STEM_BYTES);
-    std::vector<uint8_t> packed2((size_t)layers * TC_LAYER_BYTES);
+    std::vector<uint8_t> packed2((size_t)layers * TC_LAYER_BYTES), packed3((size_t)layers * TC_LAYER_BYTES);
     std::vector<float> scale((size_t)(layers + 1) * 256, 0.0f), shift((size_t)(layers + 1) * 256, 0.0f);
     for (int L = 0; L < layers; ++L) {
         std::string sfx = tc_block_name(L / 2) + ((L & 1) ? "_branch2b" : "_branch2a");
@@ -734,7 +992,8 @@ int az_nn_tc_prepare(az_nn* nn)
             scale[(size_t)L * 256 + c] = sc; shift[(size_t)L * 256 + c] = be[c] - mu[c] * sc;
         }
         pack_conv(w, 256, 32, reinterpret_cast<__nv_bfloat16*>(packed.data() + (size_t)L * TC_LAYER_BYTES));
-        pack_conv_pair(w, reinterpret_cast<__nv_bfloat16*>(packed2.data() + (size_t)L * TC_LAYER_BYTES));
+        pack_conv_pair(w, reinterpret_cast<__nv_bfloat16*>(packed2.data() + (size_t)L * TC_LAYER_BYTES), false);
+        pack_conv_pair(w, reinterpret_cast<__nv_bfloat16*>(packed3.data() + (size_t)L * TC_LAYER_BYTES), true);
     }
     {   // stem: conv/kernel [3][3][13][256], BatchNorm over the 7 board rows
         const float* w = az_nn_host_var(nn, "conv/kernel");
@@ -752,11 +1011,14 @@ int az_nn_tc_prepare(az_nn* nn)
     if (!tc->d_wpacked) {
         AZ_CUDA(cudaMalloc(&tc->d_wpacked, packed.size()));
         AZ_CUDA(cudaMalloc(&tc->d_wpacked2, packed2.size()));
+        AZ_CUDA(cudaMalloc(&tc->d_wpacked3, packed3.size()));
         AZ_CUDA(cudaMalloc(&tc->d_scale, scale.size() * sizeof(float)));
         AZ_CUDA(cudaMalloc(&tc->d_shift, shift.size() * sizeof(float)));
-        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<32>::SMEM_BYTES));
-        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::SMEM_BYTES));
+        AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<32, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<32>::smem_bytes(1))));
+        AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::smem_bytes(1))));
+        AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<2, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::smem_bytes(3))));
         AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
+        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
         int dev = 0, sms = 148;
         AZ_CUDA(cudaGetDevice(&dev));
         AZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -775,10 +1037,14 @@ int az_nn_tc_prepare(az_nn* nn)
             AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc2, &cfg));
             tc->max_pairs = nc < sms / 2 ? nc : sms / 2;
             if (tc->max_pairs < 1) tc->pair_mode = 0;
+            // board layout: 49 rows (masked operand copies, 12.5 % fewer MMAs; needs the CTA-pair kernel) unless AZ_TC_LAYOUT=56
+            const char* el = getenv("AZ_TC_LAYOUT");
+            tc->rpb = (tc->pair_mode && !(el && strcmp(el, "56") == 0)) ? 49 : 56;
         }
     }
     AZ_CUDA(cudaMemcpy(tc->d_wpacked, packed.data(), packed.size(), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_wpacked2, packed2.data(), packed2.size(), cudaMemcpyHostToDevice));
+    AZ_CUDA(cudaMemcpy(tc->d_wpacked3, packed3.data(), packed3.size(), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_scale, scale.data(), scale.size() * sizeof(float), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_shift, shift.data(), shift.size() * sizeof(float), cudaMemcpyHostToDevice));
     return AZ_OK;
@@ -789,7 +1055,7 @@ void az_nn_tc_release(az_nn* nn)
     if (!nn->tc) return;
     AzTcState* tc = nn->tc;
     for (int i = 0; i < 3; ++i) cudaFree(tc->d_act[i]);
-    cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_wpacked2); cudaFree(tc->d_scale); cudaFree(tc->d_shift); cudaFree(tc->d_x);
+    cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_wpacked2); cudaFree(tc->d_wpacked3); cudaFree(tc->d_scale); cudaFree(tc->d_shift); cudaFree(tc->d_x);
     delete tc;
     nn->tc = nullptr;
 }
@@ -799,15 +1065,18 @@ static int tc_reserve(AzTcState* tc, int n)
     if (n <= tc->cap_boards) return AZ_OK;
     for (int i = 0; i < 3; ++i) { cudaFree(tc->d_act[i]); tc->d_act[i] = nullptr; }
     cudaFree(tc->d_x); tc->d_x = nullptr; cudaFree(tc->d_in); tc->d_in = nullptr;
-    int tiles = (n * TC_ROWS_PER_BOARD + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    int tiles = (n * tc->rpb + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    tiles += tiles & 1;                                       // the pair kernels read whole tile pairs
     int r_alloc = tiles * TC_TILE_ROWS + 2 * TC_HALO;
     size_t bytes = (size_t)TC_CHUNKS * r_alloc * 16;
+    const int nv = tc->rpb == 49 ? 3 : 1;
     for (int i = 0; i < 3; ++i) {
         AZ_CUDA(cudaMalloc(&tc->d_act[i], bytes));
         AZ_CUDA(cudaMemset(tc->d_act[i], 0, bytes));          // padding rows and halos must read as zero
     }
-    AZ_CUDA(cudaMalloc(&tc->d_in, (size_t)2 * r_alloc * 16));
-    AZ_CUDA(cudaMemset(tc->d_in, 0, (size_t)2 * r_alloc * 16));
+    AZ_CUDA(cudaMalloc(&tc->d_in, (size_t)nv * 2 * r_alloc * 16));
+    AZ_CUDA(cudaMemset(tc->d_in, 0, (size_t)nv * 2 * r_alloc * 16));
+    tc->in_var_stride = (size_t)2 * r_alloc * 8;
     AZ_CUDA(cudaMalloc(&tc->d_x, sizeof(float) * (size_t)n * AZ_INPUT_FLOATS));
     tc->cap_boards = n; tc->n_tiles = tiles; tc->r_alloc = r_alloc;
     return AZ_OK;
@@ -823,32 +1092,39 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
         d_x = tc->d_x;
     }
     // buffers are sized for cap_boards; only the tiles that hold boards of this call are computed
-    const int tiles = (n * TC_ROWS_PER_BOARD + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    const int rpb = tc->rpb;
+    const int tiles = (n * rpb + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     const int grid = tiles < tc->n_sm ? tiles : tc->n_sm;
     const int layers = 2 * nn->blocks;
     int cur = 0, tmp = 1, nxt = 2;
-    k_nn_pack_input_tc<<<(n * 42 + 255) / 256, 256, 0, s>>>(d_x, n, tc->d_in, tc->r_alloc);
+    k_nn_pack_input_tc<<<(n * 42 + 255) / 256, 256, 0, s>>>(d_x, n, tc->d_in, tc->r_alloc, rpb, tc->in_var_stride);
     AZ_CUDA(cudaGetLastError());
-    AZ_CUDA((launch_conv<2, true>(grid, s, tc->d_in, tc->d_wpacked + (size_t)layers * TC_LAYER_BYTES, tc->d_scale + layers * 256,
-                                  tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n, tc->r_alloc, tiles)));
+    const uint8_t* w_stem = tc->d_wpacked + (size_t)layers * TC_LAYER_BYTES;
+    if (rpb == 49)
+        AZ_CUDA((launch_conv<2, true, 3>(grid, s, tc->d_in, w_stem, tc->d_scale + layers * 256, tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n,
+                                         tc->r_alloc, tiles, rpb, tc->in_var_stride * 2)));
+    else
+        AZ_CUDA((launch_conv<2, true, 1>(grid, s, tc->d_in, w_stem, tc->d_scale + layers * 256, tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n,
+                                         tc->r_alloc, tiles, rpb, 0)));
     const int pitems = (tiles + 1) / 2;
     const int pgrid = 2 * (pitems < tc->max_pairs ? pitems : tc->max_pairs);
     for (int i = 0; i < nn->blocks; ++i) {
-        const int L0 = 2 * i, L1 = 2 * i + 1;
-        if (tc->pair_mode) {
-            AZ_CUDA(launch_conv_pair(pgrid, s, tc->d_act[cur], tc->d_wpacked2 + (size_t)L0 * TC_LAYER_BYTES, tc->d_scale + L0 * 256,
-                                     tc->d_shift + L0 * 256, nullptr, tc->d_act[tmp], n, tc->r_alloc, tiles));
-            AZ_CUDA(launch_conv_pair(pgrid, s, tc->d_act[tmp], tc->d_wpacked2 + (size_t)L1 * TC_LAYER_BYTES, tc->d_scale + L1 * 256,
-                                     tc->d_shift + L1 * 256, tc->d_act[cur], tc->d_act[nxt], n, tc->r_alloc, tiles));
-        } else {
-            AZ_CUDA((launch_conv<32, false>(grid, s, tc->d_act[cur], tc->d_wpacked + (size_t)L0 * TC_LAYER_BYTES, tc->d_scale + L0 * 256,
-                                            tc->d_shift + L0 * 256, nullptr, tc->d_act[tmp], n, tc->r_alloc, tiles)));
-            AZ_CUDA((launch_conv<32, false>(grid, s, tc->d_act[tmp], tc->d_wpacked + (size_t)L1 * TC_LAYER_BYTES, tc->d_scale + L1 * 256,
-                                            tc->d_shift + L1 * 256, tc->d_act[cur], tc->d_act[nxt], n, tc->r_alloc, tiles)));
+        for (int h = 0; h < 2; ++h) {                        // branch2a: cur -> tmp; branch2b: tmp (+ cur as the residual) -> nxt
+            const int L = 2 * i + h;
+            const __nv_bfloat16* src = h ? tc->d_act[tmp] : tc->d_act[cur];
+            const __nv_bfloat16* res = h ? tc->d_act[cur] : nullptr;
+            __nv_bfloat16* dst = h ? tc->d_act[nxt] : tc->d_act[tmp];
+            const float* sc = tc->d_scale + L * 256; const float* sh = tc->d_shift + L * 256;
+            if (rpb == 49)
+                AZ_CUDA(launch_conv_pair3(pgrid, s, src, tc->d_wpacked3 + (size_t)L * TC_LAYER_BYTES, sc, sh, res, dst, n, tc->r_alloc, tiles));
+            else if (tc->pair_mode)
+                AZ_CUDA(launch_conv_pair(pgrid, s, src, tc->d_wpacked2 + (size_t)L * TC_LAYER_BYTES, sc, sh, res, dst, n, tc->r_alloc, tiles));
+            else
+                AZ_CUDA((launch_conv<32, false, 1>(grid, s, src, tc->d_wpacked + (size_t)L * TC_LAYER_BYTES, sc, sh, res, dst, n, tc->r_alloc, tiles, rpb, 0)));
         }
         int o = cur; cur = nxt; nxt = o;
     }
-    k_nn_heads_tc<<<(n + HB - 1) / HB, 256, 0, s>>>(tc->d_act[cur], n, tc->r_alloc, az_nn_head_params(nn), d_policy, d_value);
+    k_nn_heads_tc<<<(n + HB - 1) / HB, 256, 0, s>>>(tc->d_act[cur], n, tc->r_alloc, rpb, az_nn_head_params(nn), d_policy, d_value);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
