@@ -5,25 +5,26 @@
 // convolution is the only dense contraction on the self-play path: an implicit GEMM with
 // M = positions, N = 256 output channels, K = 9 taps x 256 input channels.
 //
-// Layout that makes the implicit GEMM a set of PLAIN shifted views (no im2col, no gather):
-//   * every board is stored as 8 x 7 = 56 "padded rows": cell (y, x) -> row y*7 + x, column x = 6
-//     and row-group y = 7 are zeros.  The one zero column is at the same time the right border of
-//     board row y and the left border of row y+1, the zero row-group is the bottom border of the
-//     board and the top border of the next one, so tap (ky, kx) of output row r reads input row
-//     r + (ky-1)*7 + (kx-1) with no masking at all (42 of 56 rows carry data).
-//   * activations are bf16, stored [channel chunk of 8][row][8 channels] (16-byte row cells), i.e.
-//     the canonical K-major SWIZZLE_NONE UMMA operand layout with an 8-row core-matrix stride of
-//     128 B: a row shift is just a different 16-byte-aligned start address in the smem descriptor.
-//   * weights are pre-packed per (layer, tap, 32-channel K block) as [chunk][256 out channels][8]
-//     = 16 KB contiguous, exactly one pipeline stage, fetched with one cp.async.bulk.
+// Layout that makes the implicit GEMM a set of shifted views (no im2col, no gather):
+//   * activations are bf16, stored [channel chunk of 8][row][8 channels] (16-byte row cells), i.e. the canonical K-major
+//     SWIZZLE_NONE UMMA operand layout with an 8-row core-matrix stride of 128 B: a row shift is just a different
+//     16-byte-aligned start address in the shared-memory descriptor, so tap (ky, kx) is the SAME operand tile, moved.
+//   * 49-row board layout (default): cell (y, x) -> row y*6 + x, then seven zero rows.  The zero rows are the bottom border of the
+//     board and the top border of the next one; the left / right border comes from two masked copies of the operand built in
+//     shared memory (kx = 0 taps read the copy with the x = 5 cells zeroed, kx = 2 taps the copy with the x = 0 cells zeroed).
+//     42 of 49 rows carry data.
+//   * 56-row board layout (one-CTA kernel, AZ_TC_LAYOUT=56 / AZ_TC_MODE=single): cell (y, x) -> row y*7 + x with a zero column
+//     x = 6 and a zero row-group y = 7, one operand copy, no masking; 42 of 56 rows carry data.
+//   * weights are pre-packed per layer into contiguous pipeline stages of K = 32 input channels of one tap:
+//     [chunk][256 out][8] = 16 KB for the one-CTA kernel, [half of the output channels][chunk][128 out][8] = 8 KB per CTA of a
+//     pair, each fetched with one cp.async.bulk.
 //
-// Persistent kernel, one CTA per SM, output tile = 128 padded rows x 256 channels.  Warp 0 streams
-// operands (one elected lane: the next tile's A operand is prefetched into the second A buffer while
-// the current tile is multiplied), warp 1 issues tcgen05.mma (one elected lane) into one of two
-// 256-column TMEM accumulators and owns the TMEM allocation, warps 2-5 run the epilogue of the
-// PREVIOUS tile concurrently: tcgen05.ld -> folded BatchNorm -> (+ skip) -> ReLU -> zero the padding
-// rows -> bf16 -> 16-byte coalesced stores.  The stem (13 -> 256 channels, BatchNorm indexed by board
-// row) is the same kernel instantiated with 2 input chunks (13 channels padded to 16).
+// Kernels: k_nn_conv_tc3 — the tower on CTA PAIRS (tcgen05 cta_group::2), 49-row layout, operand ring over K groups;
+// k_nn_conv_tc — one CTA per tile: the stem (13 -> 256 channels, 2 input chunks, BatchNorm indexed by board row; its three operand
+// copies come from global memory) and the 56-row tower (A/B reference).  Both are persistent, one CTA per SM: warp 0 streams
+// operands, warp 1 issues tcgen05.mma (one elected lane) into one of two 256-column TMEM accumulators and owns the TMEM
+// allocation, warps 2-5 run the epilogue of the PREVIOUS tile concurrently: tcgen05.ld -> folded BatchNorm -> (+ residual) ->
+// ReLU -> zero the padding rows -> bf16 -> 16-byte coalesced stores.
 #include <cstring>
 #include <vector>
 #include <cuda_bf16.h>
@@ -32,7 +33,6 @@
 #include "az_game.cuh"
 #include "az_nn.cuh"
 
-#define TC_ROWS_PER_BOARD 56
 #define TC_TILE_ROWS 128
 #define TC_HALO 8
 #define TC_A_ROWS (TC_TILE_ROWS + 2 * TC_HALO)              // 144
@@ -41,7 +41,6 @@
 #define TC_STAGES 4
 #endif
 #define TC_THREADS 192
-#define TC_SKIP_AHEAD 4                                      // residual-input prefetch distance in the epilogue (chunks); the loop is unrolled by the same 4
 #define TC_LAYER_BYTES (9 * 256 * 256 * 2)                   // 1179648 packed bf16 weights of one tower conv
 #define TC_STEM_BYTES (9 * 16 * 256 * 2)                     // 73728: stem weights, 13 input channels padded to 16
 
@@ -62,8 +61,7 @@ struct AzTcState {
     __nv_bfloat16* d_act[3] = { nullptr, nullptr, nullptr };   // [32][r_alloc][8]
     __nv_bfloat16* d_in = nullptr;                             // [2][r_alloc][8]: encoded input, 13 channels padded to 16
     uint8_t* d_wpacked = nullptr;                              // [2*blocks] x 1.18 MB tower weights, then the 72 KB stem weights
-    uint8_t* d_wpacked2 = nullptr;                             // tower weights in the CTA-pair layout (output channels split in two halves per stage)
-    int pair_mode = 1, max_pairs = 74;                         // tower on CTA pairs (k_nn_conv_tc2 / tc3) unless AZ_TC_MODE=single
+    int pair_mode = 1, max_pairs = 74;                         // tower on CTA pairs (k_nn_conv_tc3) unless AZ_TC_MODE=single (one-CTA kernel, 56-row layout)
     int rpb = 49;                                              // rows per board: 49 (masked-copy layout, k_nn_conv_tc3) or 56 (AZ_TC_LAYOUT=56)
     uint8_t* d_wpacked3 = nullptr;                             // tower weights for k_nn_conv_tc3: [K group][tap][half]
     size_t in_var_stride = 0;                                  // elements between the three copies of the encoded input (49-row layout)
@@ -163,10 +161,17 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8])
+// 32 consecutive accumulator columns of this thread's TMEM lane in one instruction (one wait per 4 channel chunks instead of per chunk)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -309,46 +314,51 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
             const int r = tile * TC_TILE_ROWS + q * 32 + lane;                 // padded row of this thread
             const bool valid = tc_row_valid(r, n_boards, rpb);
             const int yrow = tc_row_y(r, rpb);                                 // board row (stem BatchNorm index)
-            // the residual input is prefetched TC_SKIP_AHEAD chunks ahead (ncu, round 1: with a load-then-use skip read the
-            // branch2b layers ran 285 us against 220 us for the branch2a layers — the epilogue, not the MMA, set the tile time)
+            // (ncu, round 1: with a load-then-use residual read and one TMEM load + wait per 8 columns the branch2b layers ran 285 us
+            // against 220 us for the branch2a layers — the epilogue, not the MMA, set the tile time)
             const size_t cell0 = ((size_t)TC_HALO + r) * 8;
             const size_t cstride = (size_t)r_alloc * 8;
-            uint4 skq[TC_SKIP_AHEAD];
+            // four channel chunks (32 accumulator columns) per TMEM load; the residual cells of the NEXT four are in flight meanwhile
+            uint4 skq[4];
             if (skip) {
 #pragma unroll
-                for (int p = 0; p < TC_SKIP_AHEAD; ++p) skq[p] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)p * cstride));
+                for (int p = 0; p < 4; ++p) skq[p] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)p * cstride));
             }
-#pragma unroll 4
-            for (int c = 0; c < TC_CHUNKS; ++c) {
-                uint32_t v[8];
-                tc_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c * 8), v);
-                uint4 sk = make_uint4(0u, 0u, 0u, 0u);
-                if (skip) {
-                    sk = skq[c % TC_SKIP_AHEAD];
-                    if (c + TC_SKIP_AHEAD < TC_CHUNKS)
-                        skq[c % TC_SKIP_AHEAD] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)(c + TC_SKIP_AHEAD) * cstride));
+#pragma unroll 1
+            for (int c4 = 0; c4 < TC_CHUNKS / 4; ++c4) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c4 * 32), v);
+                uint4 sk[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) sk[p] = skq[p];
+                if (skip && c4 + 1 < TC_CHUNKS / 4) {
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) skq[p] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)((c4 + 1) * 4 + p) * cstride));
                 }
                 tc_ld_wait();
-                const size_t cell = cell0 + (size_t)c * cstride;               // element index of this 16-byte cell
-                float f[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int bi = ROW_BN ? (yrow < 7 ? yrow : 0) : c * 8 + e;
-                    f[e] = fmaf(__uint_as_float(v[e]), s_scale[bi], s_shift[bi]);
-                }
-                if (skip) {
-                    const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sk);
+                for (int p = 0; p < 4; ++p) {
+                    const int c = c4 * 4 + p;
+                    float f[8];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(s2[e]); f[2 * e] += x.x; f[2 * e + 1] += x.y; }
-                }
-                uint4 o;
-                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+                    for (int e = 0; e < 8; ++e) {
+                        const int bi = ROW_BN ? (yrow < 7 ? yrow : 0) : c * 8 + e;
+                        f[e] = fmaf(__uint_as_float(v[p * 8 + e]), s_scale[bi], s_shift[bi]);
+                    }
+                    if (skip) {
+                        const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sk[p]);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float x0 = valid ? fmaxf(f[2 * e], 0.0f) : 0.0f, x1 = valid ? fmaxf(f[2 * e + 1], 0.0f) : 0.0f;
-                    o2[e] = __floats2bfloat162_rn(x0, x1);
+                        for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(s2[e]); f[2 * e] += x.x; f[2 * e + 1] += x.y; }
+                    }
+                    uint4 o;
+                    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float x0 = valid ? fmaxf(f[2 * e], 0.0f) : 0.0f, x1 = valid ? fmaxf(f[2 * e + 1], 0.0f) : 0.0f;
+                        o2[e] = __floats2bfloat162_rn(x0, x1);
+                    }
+                    *reinterpret_cast<uint4*>(out + cell0 + (size_t)c * cstride) = o;
                 }
-                *reinterpret_cast<uint4*>(out + cell) = o;
             }
             }
             tc_fence_before();
@@ -364,207 +374,17 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
 }
 
 
-// ---------------------------------------------------------------- tower conv3x3 on a CTA PAIR (tcgen05 cta_group::2)
+// ---------------------------------------------------------------- CTA pairs (tcgen05 cta_group::2): shared constants
 // ncu on the one-CTA kernel: every M128 N256 K16 MMA reads 4 KB of A and 8 KB of B from shared memory; at 128 B/clk that is
 // 96 clk for an instruction the tensor pipe finishes in 64, and the kernel ran exactly at that bound (65 % pipe active).
-// Here two CTAs on the two SMs of a TPC compute one 256-row x 256-channel tile pair: each CTA keeps its own 128 rows of A and
-// only HALF of the weights (128 output channels, 8 KB per K=32 stage), the pair's tensor cores exchange the B halves, so
-// every SM reads 8 KB per MMA and streams half the weight bytes from L2.
-//   warp 0 (both CTAs): operand streamer — own A tile (double buffered) and own half of every weight stage (TC2_STAGES ring)
-//   warp 1, leader CTA: issues tcgen05.mma.cta_group::2 (M = 256); its commits arrive on the barriers of BOTH CTAs
-//   warp 1, peer CTA  : relay — forwards "my A tile / my weight half has landed" to the leader's barriers
-//   warps 2-5 (both)  : epilogue of the CTA's own 128 accumulator rows (TMEM double buffered), as in k_nn_conv_tc
+// On a CTA pair (two SMs of a TPC, M = 256) each CTA keeps its own 128 rows of A and only HALF of the weights (128 output
+// channels, 8 KB per K=32 stage); the pair's tensor cores exchange the B halves, so every SM reads 8 KB per MMA and streams half
+// the weight bytes from L2.
 #define TC2_STAGES 8
 #define TC2_STAGE_BYTES (4 * 128 * 16)                       // K = 32 (4 chunks) x 128 output channels
-#define TC2_ITERS (9 * 8)
-#define TC2_A_BYTES (TC_CHUNKS * TC_A_ROWS * 16)
-#define TC2_SMEM_BYTES (2 * TC2_A_BYTES + TC2_STAGES * TC2_STAGE_BYTES + 2 * 256 * 4 + 64 * 8 + 16)
-
-__global__ void __launch_bounds__(TC_THREADS, 1)
-k_nn_conv_tc2(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ wpacked2, const float* __restrict__ scale,
-              const float* __restrict__ shift, const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
-              int n_boards, int r_alloc, int n_tiles)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sA = smem;                                   // 2 x TC2_A_BYTES
-    uint8_t* sB = smem + 2 * TC2_A_BYTES;                 // TC2_STAGES x TC2_STAGE_BYTES
-    float* s_scale = reinterpret_cast<float*>(sB + TC2_STAGES * TC2_STAGE_BYTES);
-    float* s_shift = s_scale + 256;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
-    uint64_t* bar_a_full = bars;                          // [2] own A tile landed
-    uint64_t* bar_a_empty = bars + 2;                     // [2] MMAs reading that A buffer retired (leader commit, both CTAs)
-    uint64_t* bar_pa_full = bars + 4;                     // [2] leader only: the peer's A tile landed
-    uint64_t* bar_acc_full = bars + 6;                    // [2] accumulator complete (leader commit, both CTAs)
-    uint64_t* bar_acc_empty = bars + 8;                   // [2] leader only: drained by the 8 epilogue warps of the pair
-    uint64_t* bar_w_full = bars + 10;                     // [TC2_STAGES] own weight half landed
-    uint64_t* bar_w_empty = bars + 10 + TC2_STAGES;       // [TC2_STAGES] (leader commit, both CTAs)
-    uint64_t* bar_pw_full = bars + 10 + 2 * TC2_STAGES;   // [TC2_STAGES] leader only: the peer's weight half landed
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 64);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t crank;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-    const bool leader = crank == 0;
-    const int n_pairs = (int)(gridDim.x >> 1), pid = (int)(blockIdx.x >> 1);
-    const int n_items = (n_tiles + 1) >> 1;               // one item = two consecutive 128-row tiles
-
-    for (int i = threadIdx.x; i < 256; i += TC_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
-    if (threadIdx.x == 0) {
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_a_full + b, 1); mbar_init(bar_a_empty + b, 1); mbar_init(bar_pa_full + b, 1);
-            mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, 8);
-        }
-        for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(bar_w_full + s, 1); mbar_init(bar_w_empty + s, 1); mbar_init(bar_pw_full + s, 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *s_tmem;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ---- operand streamer (both CTAs)
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(in);
-            auto load_a = [&](int j, int item) {
-                int tile = 2 * item + (int)crank;
-                if (tile >= n_tiles) tile = n_tiles - 1;          // odd tile count: the peer's last tile is multiplied, never stored
-                const int b = j & 1;
-                if (j >= 2) mbar_wait_cluster(bar_a_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
-                mbar_expect_tx(bar_a_full + b, TC2_A_BYTES);
-                for (int c = 0; c < TC_CHUNKS; ++c)
-                    bulk_g2s(sA + (size_t)b * TC2_A_BYTES + (size_t)c * TC_A_ROWS * 16,
-                             src + ((size_t)c * r_alloc + (size_t)tile * TC_TILE_ROWS) * 16, TC_A_ROWS * 16, bar_a_full + b);
-            };
-            uint32_t wit = 0;
-            int j = 0;
-            if (pid < n_items) load_a(0, pid);
-            for (int item = pid; item < n_items; item += n_pairs, ++j) {
-                for (int it = 0; it < TC2_ITERS; ++it, ++wit) {
-                    const uint32_t s = wit % TC2_STAGES, k = wit / TC2_STAGES;
-                    if (k > 0) mbar_wait_cluster(bar_w_empty + s, (k - 1) & 1u);
-                    mbar_expect_tx(bar_w_full + s, TC2_STAGE_BYTES);
-                    bulk_g2s(sB + (size_t)s * TC2_STAGE_BYTES, wpacked2 + ((size_t)it * 2 + crank) * TC2_STAGE_BYTES, TC2_STAGE_BYTES, bar_w_full + s);
-                    if (it == 8 && item + n_pairs < n_items) load_a(j + 1, item + n_pairs);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && leader) {
-            // ---- MMA issuer (leader CTA)
-            const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-            uint32_t wit = 0;
-            int j = 0;
-            for (int item = pid; item < n_items; item += n_pairs, ++j) {
-                const int b = j & 1;
-                mbar_wait(bar_a_full + b, (uint32_t)((j >> 1) & 1));
-                mbar_wait_cluster(bar_pa_full + b, (uint32_t)((j >> 1) & 1));
-                if (j >= 2) mbar_wait_cluster(bar_acc_empty + b, (uint32_t)(((j >> 1) - 1) & 1));
-                tc_fence_after();
-                for (int it = 0; it < TC2_ITERS; ++it, ++wit) {
-                    const uint32_t s = wit % TC2_STAGES, k = wit / TC2_STAGES;
-                    mbar_wait(bar_w_full + s, k & 1u);
-                    mbar_wait_cluster(bar_pw_full + s, k & 1u);
-                    tc_fence_after();
-                    const int tap = it >> 3, kb = it & 7;
-                    const int sh = (tap / 3 - 1) * 7 + (tap % 3 - 1);
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const uint64_t bdesc = umma_desc(b_base + (uint32_t)(s * TC2_STAGE_BYTES + kk * 2 * 128 * 16), 128 * 16, 128);
-                        const int chunk0 = kb * 4 + kk * 2;
-                        const uint64_t adesc = umma_desc(a_base + (uint32_t)(b * TC2_A_BYTES + (chunk0 * TC_A_ROWS + TC_HALO + sh) * 16), TC_A_ROWS * 16, 128);
-                        tc2_mma_bf16(tmem_base + (uint32_t)(b * 256), adesc, bdesc, TC2_IDESC, (it > 0 || kk > 0) ? 1u : 0u);
-                    }
-                    tc2_commit(bar_w_empty + s);
-                }
-                tc2_commit(bar_a_empty + b);
-                tc2_commit(bar_acc_full + b);
-            }
-        } else if (lane == 0) {
-            // ---- relay (peer CTA): tell the leader when this CTA's operands have landed
-            uint32_t wit = 0;
-            int j = 0;
-            for (int item = pid; item < n_items; item += n_pairs, ++j) {
-                const int b = j & 1;
-                mbar_wait(bar_a_full + b, (uint32_t)((j >> 1) & 1));
-                mbar_arrive_remote(bar_pa_full + b, 0u);
-                for (int it = 0; it < TC2_ITERS; ++it, ++wit) {
-                    const uint32_t s = wit % TC2_STAGES, k = wit / TC2_STAGES;
-                    mbar_wait(bar_w_full + s, k & 1u);
-                    mbar_arrive_remote(bar_pw_full + s, 0u);
-                }
-            }
-        }
-    } else {
-        // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 of this CTA's half of the pair's accumulator
-        const int q = warp & 3;
-        int j = 0;
-        for (int item = pid; item < n_items; item += n_pairs, ++j) {
-            const int b = j & 1;
-            const int tile = 2 * item + (int)crank;
-            mbar_wait_cluster(bar_acc_full + b, (uint32_t)((j >> 1) & 1));
-            tc_fence_after();
-            if (tile < n_tiles) {
-                const int r = tile * TC_TILE_ROWS + q * 32 + lane;
-                const bool valid = tc_row_valid(r, n_boards, 56);
-                const size_t cell0 = ((size_t)TC_HALO + r) * 8;
-                const size_t cstride = (size_t)r_alloc * 8;
-                uint4 skq[TC_SKIP_AHEAD];
-                if (skip) {
-#pragma unroll
-                    for (int p = 0; p < TC_SKIP_AHEAD; ++p) skq[p] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)p * cstride));
-                }
-#pragma unroll 4
-                for (int c = 0; c < TC_CHUNKS; ++c) {
-                    uint32_t v[8];
-                    tc_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + c * 8), v);
-                    uint4 sk = make_uint4(0u, 0u, 0u, 0u);
-                    if (skip) {
-                        sk = skq[c % TC_SKIP_AHEAD];
-                        if (c + TC_SKIP_AHEAD < TC_CHUNKS)
-                            skq[c % TC_SKIP_AHEAD] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)(c + TC_SKIP_AHEAD) * cstride));
-                    }
-                    tc_ld_wait();
-                    const size_t cell = cell0 + (size_t)c * cstride;
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[e]), s_scale[c * 8 + e], s_shift[c * 8 + e]);
-                    if (skip) {
-                        const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sk);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(s2[e]); f[2 * e] += x.x; f[2 * e + 1] += x.y; }
-                    }
-                    uint4 o;
-                    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float x0 = valid ? fmaxf(f[2 * e], 0.0f) : 0.0f, x1 = valid ? fmaxf(f[2 * e + 1], 0.0f) : 0.0f;
-                        o2[e] = __floats2bfloat162_rn(x0, x1);
-                    }
-                    *reinterpret_cast<uint4*>(out + cell) = o;
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if (leader) mbar_arrive(bar_acc_empty + b); else mbar_arrive_remote(bar_acc_empty + b, 0u); }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();                     // nobody leaves while the other CTA may still signal its barriers or read its operands
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
 
 // ---------------------------------------------------------------- tower conv3x3 on a CTA pair, 49-row board layout
-// Same CTA-pair structure as k_nn_conv_tc2 (tcgen05 cta_group::2, half of the weights per CTA), on the 49-row layout: the A operand
+// tcgen05 cta_group::2, half of the weights per CTA (above), on the 49-row layout: the A operand
 // exists in three copies in shared memory (plain / x=5 cells zeroed / x=0 cells zeroed, see tc_tap_variant), so it no longer fits
 // twice.  The K loop is therefore turned inside out — K group (32 channels) outer, the nine taps inner — and the operand lives in a
 // RING of K groups: a group's slot is refilled for the next tile as soon as its nine taps have retired.
@@ -732,39 +552,44 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
                 const bool valid = tc_row_valid(r, n_boards, 49);
                 const size_t cell0 = ((size_t)TC_HALO + r) * 8;
                 const size_t cstride = (size_t)r_alloc * 8;
-                uint4 skq[TC_SKIP_AHEAD];
+                // four channel chunks (32 accumulator columns) per TMEM load; the residual cells of the NEXT four are in flight meanwhile
+                uint4 skq[4];
                 if (skip) {
 #pragma unroll
-                    for (int p = 0; p < TC_SKIP_AHEAD; ++p) skq[p] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)p * cstride));
+                    for (int p = 0; p < 4; ++p) skq[p] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)p * cstride));
                 }
-#pragma unroll 4
-                for (int c = 0; c < TC_CHUNKS; ++c) {
-                    uint32_t v[8];
-                    tc_ld8(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * 256 + c * 8), v);
-                    uint4 sk = make_uint4(0u, 0u, 0u, 0u);
-                    if (skip) {
-                        sk = skq[c % TC_SKIP_AHEAD];
-                        if (c + TC_SKIP_AHEAD < TC_CHUNKS)
-                            skq[c % TC_SKIP_AHEAD] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)(c + TC_SKIP_AHEAD) * cstride));
+#pragma unroll 1
+                for (int c4 = 0; c4 < TC_CHUNKS / 4; ++c4) {
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * 256 + c4 * 32), v);
+                    uint4 sk[4];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) sk[p] = skq[p];
+                    if (skip && c4 + 1 < TC_CHUNKS / 4) {
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) skq[p] = __ldg(reinterpret_cast<const uint4*>(skip + cell0 + (size_t)((c4 + 1) * 4 + p) * cstride));
                     }
                     tc_ld_wait();
-                    const size_t cell = cell0 + (size_t)c * cstride;
-                    float f[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[e]), s_scale[c * 8 + e], s_shift[c * 8 + e]);
-                    if (skip) {
-                        const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sk);
+                    for (int p = 0; p < 4; ++p) {
+                        const int c = c4 * 4 + p;
+                        float f[8];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(s2[e]); f[2 * e] += x.x; f[2 * e + 1] += x.y; }
+                        for (int e = 0; e < 8; ++e) f[e] = fmaf(__uint_as_float(v[p * 8 + e]), s_scale[c * 8 + e], s_shift[c * 8 + e]);
+                        if (skip) {
+                            const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(&sk[p]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { float2 x = __bfloat1622float2(s2[e]); f[2 * e] += x.x; f[2 * e + 1] += x.y; }
+                        }
+                        uint4 o;
+                        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float x0 = valid ? fmaxf(f[2 * e], 0.0f) : 0.0f, x1 = valid ? fmaxf(f[2 * e + 1], 0.0f) : 0.0f;
+                            o2[e] = __floats2bfloat162_rn(x0, x1);
+                        }
+                        *reinterpret_cast<uint4*>(out + cell0 + (size_t)c * cstride) = o;
                     }
-                    uint4 o;
-                    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float x0 = valid ? fmaxf(f[2 * e], 0.0f) : 0.0f, x1 = valid ? fmaxf(f[2 * e + 1], 0.0f) : 0.0f;
-                        o2[e] = __floats2bfloat162_rn(x0, x1);
-                    }
-                    *reinterpret_cast<uint4*>(out + cell) = o;
                 }
             }
             tc_fence_before();
@@ -923,7 +748,7 @@ static void pack_conv(const float* w, int cin, int kch, __nv_bfloat16* dst)
 
 // HWIO fp32 [3][3][256][256] -> bf16 [tap][K block of 32][half of the output channels][chunk 4][128 out][8]: one 8 KB stage per CTA of a pair
 // (kb_outer: stages ordered [K block][tap] for k_nn_conv_tc3 instead of [tap][K block])
-static void pack_conv_pair(const float* w, __nv_bfloat16* dst, bool kb_outer)
+static void pack_conv_pair(const float* w, __nv_bfloat16* dst, bool kb_outer = true)
 {
     for (int tap = 0; tap < 9; ++tap)
         for (int kb = 0; kb < 8; ++kb)
@@ -949,18 +774,6 @@ static cudaError_t launch_conv_pair3(int grid, cudaStream_t s, const __nv_bfloat
     return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles);
 }
 
-static cudaError_t launch_conv_pair(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w2, const float* scale, const float* shift,
-                                    const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC2_SMEM_BYTES; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc2, in, w2, scale, shift, skip, out, n_boards, r_alloc, n_tiles);
-}
-
 // persistent launch of one stem / one-CTA tower convolution
 template <int KCH, bool ROW_BN, int NV>
 static cudaError_t launch_conv(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w, const float* scale, const float* shift,
@@ -977,7 +790,7 @@ int az_nn_tc_prepare(az_nn* nn)
     AzTcState* tc = nn->tc;
     const int layers = 2 * nn->blocks;
     std::vector<uint8_t> packed((size_t)layers * TC_LAYER_BYTES + TC_STEM_BYTES);
-    std::vector<uint8_t> packed2((size_t)layers * TC_LAYER_BYTES), packed3((size_t)layers * TC_LAYER_BYTES);
+    std::vector<uint8_t> packed3((size_t)layers * TC_LAYER_BYTES);
     std::vector<float> scale((size_t)(layers + 1) * 256, 0.0f), shift((size_t)(layers + 1) * 256, 0.0f);
     for (int L = 0; L < layers; ++L) {
         std::string sfx = tc_block_name(L / 2) + ((L & 1) ? "_branch2b" : "_branch2a");
@@ -992,8 +805,7 @@ int az_nn_tc_prepare(az_nn* nn)
             scale[(size_t)L * 256 + c] = sc; shift[(size_t)L * 256 + c] = be[c] - mu[c] * sc;
         }
         pack_conv(w, 256, 32, reinterpret_cast<__nv_bfloat16*>(packed.data() + (size_t)L * TC_LAYER_BYTES));
-        pack_conv_pair(w, reinterpret_cast<__nv_bfloat16*>(packed2.data() + (size_t)L * TC_LAYER_BYTES), false);
-        pack_conv_pair(w, reinterpret_cast<__nv_bfloat16*>(packed3.data() + (size_t)L * TC_LAYER_BYTES), true);
+        pack_conv_pair(w, reinterpret_cast<__nv_bfloat16*>(packed3.data() + (size_t)L * TC_LAYER_BYTES));
     }
     {   // stem: conv/kernel [3][3][13][256], BatchNorm over the 7 board rows
         const float* w = az_nn_host_var(nn, "conv/kernel");
@@ -1010,14 +822,12 @@ int az_nn_tc_prepare(az_nn* nn)
     }
     if (!tc->d_wpacked) {
         AZ_CUDA(cudaMalloc(&tc->d_wpacked, packed.size()));
-        AZ_CUDA(cudaMalloc(&tc->d_wpacked2, packed2.size()));
         AZ_CUDA(cudaMalloc(&tc->d_wpacked3, packed3.size()));
         AZ_CUDA(cudaMalloc(&tc->d_scale, scale.size() * sizeof(float)));
         AZ_CUDA(cudaMalloc(&tc->d_shift, shift.size() * sizeof(float)));
         AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<32, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<32>::smem_bytes(1))));
         AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::smem_bytes(1))));
         AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<2, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::smem_bytes(3))));
-        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
         AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
         int dev = 0, sms = 148;
         AZ_CUDA(cudaGetDevice(&dev));
@@ -1028,13 +838,13 @@ int az_nn_tc_prepare(az_nn* nn)
             const char* em = getenv("AZ_TC_MODE");
             tc->pair_mode = !(em && strcmp(em, "single") == 0);
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(sms / 2 * 2)); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC2_SMEM_BYTES;
+            cfg.gridDim = dim3((unsigned)(sms / 2 * 2)); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             int nc = 0;
-            AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc2, &cfg));
+            AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc3, &cfg));
             tc->max_pairs = nc < sms / 2 ? nc : sms / 2;
             if (tc->max_pairs < 1) tc->pair_mode = 0;
             // board layout: 49 rows (masked operand copies, 12.5 % fewer MMAs; needs the CTA-pair kernel) unless AZ_TC_LAYOUT=56
@@ -1043,7 +853,6 @@ int az_nn_tc_prepare(az_nn* nn)
         }
     }
     AZ_CUDA(cudaMemcpy(tc->d_wpacked, packed.data(), packed.size(), cudaMemcpyHostToDevice));
-    AZ_CUDA(cudaMemcpy(tc->d_wpacked2, packed2.data(), packed2.size(), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_wpacked3, packed3.data(), packed3.size(), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_scale, scale.data(), scale.size() * sizeof(float), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_shift, shift.data(), shift.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1055,7 +864,7 @@ void az_nn_tc_release(az_nn* nn)
     if (!nn->tc) return;
     AzTcState* tc = nn->tc;
     for (int i = 0; i < 3; ++i) cudaFree(tc->d_act[i]);
-    cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_wpacked2); cudaFree(tc->d_wpacked3); cudaFree(tc->d_scale); cudaFree(tc->d_shift); cudaFree(tc->d_x);
+    cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_wpacked3); cudaFree(tc->d_scale); cudaFree(tc->d_shift); cudaFree(tc->d_x);
     delete tc;
     nn->tc = nullptr;
 }
@@ -1117,8 +926,6 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
             const float* sc = tc->d_scale + L * 256; const float* sh = tc->d_shift + L * 256;
             if (rpb == 49)
                 AZ_CUDA(launch_conv_pair3(pgrid, s, src, tc->d_wpacked3 + (size_t)L * TC_LAYER_BYTES, sc, sh, res, dst, n, tc->r_alloc, tiles));
-            else if (tc->pair_mode)
-                AZ_CUDA(launch_conv_pair(pgrid, s, src, tc->d_wpacked2 + (size_t)L * TC_LAYER_BYTES, sc, sh, res, dst, n, tc->r_alloc, tiles));
             else
                 AZ_CUDA((launch_conv<32, false, 1>(grid, s, src, tc->d_wpacked + (size_t)L * TC_LAYER_BYTES, sc, sh, res, dst, n, tc->r_alloc, tiles, rpb, 0)));
         }

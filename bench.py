@@ -274,7 +274,7 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
                                     "per batch), %d-block graph, random-init weights (seed 1234), bf16 tcgen05 forward, %d moves per step"
                                     % (n, sims, blocks, moves_per_step), "games_per_gpu": n, "sims_per_move": sims, "blocks": blocks},
                 roofline={"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
-                          "traffic": ncu_traffic("k_nn_conv_tc2"), "peak_source": src + " (sustained cuBLAS bf16)",
+                          "traffic": ncu_traffic("k_nn_conv_tc3"), "peak_source": src + " (sustained cuBLAS bf16)",
                           "executed_frac": achieved_tf * 56.0 / 42.0 / tf_peak,
                           "note": "conventional FLOPs/position (0.4981 G for 5 blocks) x positions pushed through the tower / whole-step device "
                                   "time (tree kernels, encode and heads included in the time); the padded board layout executes 56/42 of "

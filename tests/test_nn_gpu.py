@@ -124,15 +124,15 @@ def test_bf16_tcgen05_forward_close_to_fp32(api, blocks, n):
 
 
 def test_tower_variants_agree(api):
-    """the three tower implementations (one CTA / CTA pair on the 56-row layout, CTA pair on the 49-row masked-copy layout) compute
-    the same network: 56-row variants bit-identical, the 49-row one within accumulation-order noise (K group outer instead of tap outer)"""
+    """the two tower implementations (one CTA per tile on the 56-row layout, CTA pair on the 49-row masked-copy layout) compute the
+    same network: they differ by accumulation-order noise only (K group outer instead of tap outer)"""
     import os
     rng = np.random.default_rng(9)
     x = rng.random((300, 546), dtype=np.float32)
     outs = {}
     old = {k: os.environ.get(k) for k in ("AZ_TC_MODE", "AZ_TC_LAYOUT")}
     try:
-        for name, mode, layout in (("single56", "single", "56"), ("pair56", "pair", "56"), ("pair49", "pair", "49")):
+        for name, mode, layout in (("single56", "single", "56"), ("pair49", "pair", "49")):
             os.environ["AZ_TC_MODE"], os.environ["AZ_TC_LAYOUT"] = mode, layout
             net = api.Net(blocks=3, seed=77)
             outs[name] = net.forward(x, api.BF16)
@@ -145,7 +145,6 @@ def test_tower_variants_agree(api):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
-    assert (outs["single56"][0] == outs["pair56"][0]).all() and (outs["single56"][1] == outs["pair56"][1]).all()
-    assert np.abs(outs["pair49"][0] - outs["pair56"][0]).max() < 1e-3 and np.abs(outs["pair49"][1] - outs["pair56"][1]).max() < 5e-3
+    assert np.abs(outs["pair49"][0] - outs["single56"][0]).max() < 1e-3 and np.abs(outs["pair49"][1] - outs["single56"][1]).max() < 5e-3
     for name in outs:
         assert np.abs(outs[name][0] - p32).max() < 2e-3 and np.abs(outs[name][1] - v32).max() < 1e-2, name

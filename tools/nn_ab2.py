@@ -1,5 +1,5 @@
 """interleaved A/B of tower variants in ONE process (the forward is power-capped, so separate runs drift):
-one-CTA kernel / CTA pair on the 56-row layout / CTA pair on the 49-row layout"""
+one-CTA kernel on the 56-row layout / CTA pair on the 49-row layout"""
 import os, sys
 import numpy as np
 import torch
@@ -7,7 +7,7 @@ sys.path.insert(0, ".")
 from alphazero_risk_b200 import api
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 nets = {}
-for name, mode, layout in (("single56", "single", "56"), ("pair56", "pair", "56"), ("pair49", "pair", "49")):
+for name, mode, layout in (("single56", "single", "56"), ("pair49", "pair", "49")):
     os.environ["AZ_TC_MODE"] = mode; os.environ["AZ_TC_LAYOUT"] = layout
     nets[name] = api.Net(blocks=5, seed=1)
     nets[name].finalize()
