@@ -644,37 +644,41 @@ __device__ __forceinline__ float warp_sum_tc(float v)
 }
 
 // policy + value heads for HB boards per block (the head weights, 60 KB, are read once per block instead of once per board)
-#define HB 8
+#define HB 6     // 6 boards = 252 cells: one pass of the 256 threads over the 1x1 convolutions
 __global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __restrict__ act, int n, int r_alloc, int rpb, AzHeadParams hp,
                                                       float* __restrict__ policy, float* __restrict__ value)
 {
     __shared__ float s_pi[HB][84], s_v[HB][42], s_logit[HB][44], s_red[HB][8];
     const int b0 = blockIdx.x * HB, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nb = n - b0 < HB ? n - b0 : HB;
-    // 1x1 convolutions (pi: 2 channels, v: 1 channel) + BatchNorm + ReLU; one warp per board cell, lane = channel chunk
-    float wp0[8], wp1[8], wv[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { const int c = lane * 8 + e; wp0[e] = hp.pi_w[c * 2]; wp1[e] = hp.pi_w[c * 2 + 1]; wv[e] = hp.v_w[c]; }
+    // 1x1 convolutions (pi: 2 channels, v: 1 channel) + BatchNorm + ReLU.  One thread per board cell walks the 32 channel chunks:
+    // a warp reads 32 consecutive 16-byte cells of one chunk (512 contiguous bytes) per step and needs no reduction
+    // (lane = chunk with a warp reduction per cell read 16 bytes out of every 32-byte sector and ran 56 us for 4096 boards).
+    __shared__ float s_w[3][256];
+    for (int c = threadIdx.x; c < 256; c += 256) { s_w[0][c] = hp.pi_w[c * 2]; s_w[1][c] = hp.pi_w[c * 2 + 1]; s_w[2][c] = hp.v_w[c]; }
+    __syncthreads();
     const float sc0 = hp.bn_pi[0] * rsqrtf(hp.bn_pi[6] + AZ_NN_BN_EPS), sc1 = hp.bn_pi[1] * rsqrtf(hp.bn_pi[7] + AZ_NN_BN_EPS);
     const float scv = hp.bn_v[0] * rsqrtf(hp.bn_v[3] + AZ_NN_BN_EPS);
-    for (int i = warp; i < nb * 42; i += 8) {
+    for (int i = threadIdx.x; i < nb * 42; i += 256) {
         const int bl = i / 42, p = i - bl * 42;
         const int row = (b0 + bl) * rpb + tc_cell_row(p, rpb);
-        const uint4 cell = *reinterpret_cast<const uint4*>(act + ((size_t)lane * r_alloc + TC_HALO + row) * 8);
-        const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cell);
+        const __nv_bfloat16* cellp = act + ((size_t)TC_HALO + row) * 8;
         float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 4
+        for (int c = 0; c < TC_CHUNKS; ++c) {
+            const uint4 cell = __ldg(reinterpret_cast<const uint4*>(cellp + (size_t)c * r_alloc * 8));
+            const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cell);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 xv = __bfloat1622float2(c2[e]);
-            s0 = fmaf(xv.x, wp0[2 * e], s0); s1 = fmaf(xv.x, wp1[2 * e], s1); s2 = fmaf(xv.x, wv[2 * e], s2);
-            s0 = fmaf(xv.y, wp0[2 * e + 1], s0); s1 = fmaf(xv.y, wp1[2 * e + 1], s1); s2 = fmaf(xv.y, wv[2 * e + 1], s2);
+            for (int e = 0; e < 4; ++e) {
+                const float2 xv = __bfloat1622float2(c2[e]);
+                const int ch = c * 8 + 2 * e;
+                s0 = fmaf(xv.x, s_w[0][ch], s0); s1 = fmaf(xv.x, s_w[1][ch], s1); s2 = fmaf(xv.x, s_w[2][ch], s2);
+                s0 = fmaf(xv.y, s_w[0][ch + 1], s0); s1 = fmaf(xv.y, s_w[1][ch + 1], s1); s2 = fmaf(xv.y, s_w[2][ch + 1], s2);
+            }
         }
-        s0 = warp_sum_tc(s0); s1 = warp_sum_tc(s1); s2 = warp_sum_tc(s2);
-        if (lane == 0) {
-            s_pi[bl][p * 2 + 0] = fmaxf((s0 - hp.bn_pi[4]) * sc0 + hp.bn_pi[2], 0.0f);
-            s_pi[bl][p * 2 + 1] = fmaxf((s1 - hp.bn_pi[5]) * sc1 + hp.bn_pi[3], 0.0f);
-            s_v[bl][p] = fmaxf((s2 - hp.bn_v[2]) * scv + hp.bn_v[1], 0.0f);
-        }
+        s_pi[bl][p * 2 + 0] = fmaxf((s0 - hp.bn_pi[4]) * sc0 + hp.bn_pi[2], 0.0f);
+        s_pi[bl][p * 2 + 1] = fmaxf((s1 - hp.bn_pi[5]) * sc1 + hp.bn_pi[3], 0.0f);
+        s_v[bl][p] = fmaxf((s2 - hp.bn_v[2]) * scv + hp.bn_v[1], 0.0f);
     }
     __syncthreads();
     // dense 84 -> 43 (policy logits): thread = output, weights reused over the block's boards
