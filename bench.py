@@ -275,9 +275,9 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
                                     % (n, sims, blocks, moves_per_step), "games_per_gpu": n, "sims_per_move": sims, "blocks": blocks},
                 roofline={"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
                           "traffic": ncu_traffic("k_nn_conv_tc3"), "peak_source": src + " (sustained cuBLAS bf16)",
-                          "executed_frac": achieved_tf * 56.0 / 42.0 / tf_peak,
+                          "executed_frac": achieved_tf * 49.0 / 42.0 / tf_peak,
                           "note": "conventional FLOPs/position (0.4981 G for 5 blocks) x positions pushed through the tower / whole-step device "
-                                  "time (tree kernels, encode and heads included in the time); the padded board layout executes 56/42 of "
+                                  "time (tree kernels, encode and heads included in the time); the 49-row board layout executes 49/42 of "
                                   "that (executed_frac); the forward runs at the board's 1 kW power cap (clocks.reasons: sw_power_cap), "
                                   "like the cuBLAS run the peak comes from; traffic = DRAM bytes of one tower-layer launch (ncu)"},
                 clocks=sp_clocks,
