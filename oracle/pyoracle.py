@@ -97,8 +97,13 @@ def oracle_lib():
         L.ro_mcts_new.argtypes = [C.c_void_p, C.c_void_p]
         for fn in ("ro_mcts_free", "ro_mcts_clear", "ro_mcts_trim", "ro_mcts_table_size"):
             getattr(L, fn).argtypes = [C.c_void_p]
+        for fn in ("ro_mcts_vl_skips", "ro_mcts_vl_duplicates"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+            getattr(L, fn).restype = C.c_uint64
         L.ro_mcts_search.argtypes = [C.c_void_p, sp, rp, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p, f32p, f32p,
                                      C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        L.ro_mcts_search_lockstep.argtypes = [C.c_void_p, sp, rp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, u32p, f32p, f32p, f32p,
+                                              C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         L.ro_pick_move.argtypes = [f32p, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32]
         L.ro_bench_env.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(BenchOut)]
         _oracle = L
@@ -214,14 +219,23 @@ class OracleMcts:
     def table_size(self):
         return int(self.L.ro_mcts_table_size(self.h))
 
-    def search(self, game_obj, seed, game, ply):
+    def vl_counts(self):
+        """(moves passed over by the active_N rule, duplicate requests) so far"""
+        return int(self.L.ro_mcts_vl_skips(self.h)), int(self.L.ro_mcts_vl_duplicates(self.h))
+
+    def search(self, game_obj, seed, game, ply, lockstep=1):
+        """lockstep = K > 1: K descents select (virtual-loss rule) before any is evaluated, ro_mcts_search_lockstep"""
         N = np.zeros(MOVES, np.uint32)
         Q = np.zeros(MOVES, np.float32)
         P = np.zeros(MOVES, np.float32)
         pi = np.zeros(MOVES, np.float32)
         sumN, val = C.c_uint32(0), C.c_float(0)
-        rc = self.L.ro_mcts_search(self.h, C.byref(game_obj.s), C.byref(self.rules), seed, game, ply, N, Q, P, pi,
-                                   C.byref(sumN), C.byref(val))
+        if lockstep > 1:
+            rc = self.L.ro_mcts_search_lockstep(self.h, C.byref(game_obj.s), C.byref(self.rules), seed, game, ply, lockstep, N, Q, P,
+                                                pi, C.byref(sumN), C.byref(val))
+        else:
+            rc = self.L.ro_mcts_search(self.h, C.byref(game_obj.s), C.byref(self.rules), seed, game, ply, N, Q, P, pi,
+                                       C.byref(sumN), C.byref(val))
         assert rc == 0, rc
         return dict(N=N, Q=Q, P=P, pi=pi, sumN=int(sumN.value), value=float(val.value))
 
@@ -282,6 +296,8 @@ def ref_lib():
         L.ref_mcts_evals.restype = C.c_uint64
         L.ref_mcts_search.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p, f32p, f32p,
                                       C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        L.ref_mcts_search_lockstep.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, u32p, f32p, f32p, f32p,
+                                               C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
         L.ref_pick_move.argtypes = [vp, f32p, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32]
         L.ref_bench_env.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.POINTER(BenchOut)]
         L.ref_bench_selfplay.argtypes = [C.c_int, C.c_uint64, C.c_uint32, vp, vp, C.POINTER(BenchOut)]
@@ -387,13 +403,17 @@ class RefMcts:
     def table_size(self):
         return int(self.L.ref_mcts_table_size(self.h))
 
-    def search(self, game_obj, seed, game, ply):
+    def search(self, game_obj, seed, game, ply, lockstep=1):
+        """lockstep = K > 1: K real search threads of the reference taking turns (ref_mcts_search_lockstep)"""
         N = np.zeros(MOVES, np.uint32)
         Q = np.zeros(MOVES, np.float32)
         P = np.zeros(MOVES, np.float32)
         pi = np.zeros(MOVES, np.float32)
         sumN, val = C.c_uint32(0), C.c_float(0)
-        rc = self.L.ref_mcts_search(self.h, game_obj.s, seed, game, ply, N, Q, P, pi, C.byref(sumN), C.byref(val))
+        if lockstep > 1:
+            rc = self.L.ref_mcts_search_lockstep(self.h, game_obj.s, seed, game, ply, lockstep, N, Q, P, pi, C.byref(sumN), C.byref(val))
+        else:
+            rc = self.L.ref_mcts_search(self.h, game_obj.s, seed, game, ply, N, Q, P, pi, C.byref(sumN), C.byref(val))
         assert rc == 0, self.L.ref_last_error()
         return dict(N=N, Q=Q, P=P, pi=pi, sumN=int(sumN.value), value=float(val.value))
 

@@ -35,6 +35,11 @@ public:
 	RefEvalFn fn = nullptr;
 	void* user = nullptr;
 	uint64_t evals = 0;
+	/* lockstep schedule of THREADS_PER_MCTS search threads (ref_mcts_search_lockstep): called by a search
+	   thread when it reaches predictFuture — where the reference's thread blocks until the batch runs
+	   (alphazero_nn.cpp:282-320) — and returns when that thread may go on */
+	void (*park)(void*) = nullptr;
+	void* park_user = nullptr;
 
 	AlphaZeroNNId() {}
 	AlphaZeroNNId(RefEvalFn f, void* u) : fn(f), user(u) {}
@@ -57,6 +62,7 @@ public:
 
 	std::future<NNOutputData> predictFuture(const NNInputData& state)
 	{
+		if (park) park(park_user);
 		std::promise<NNOutputData> p;
 		p.set_value(predict(state));
 		return p.get_future();

@@ -25,6 +25,8 @@
 #include <atomic>
 #include <thread>
 #include <vector>
+#include <mutex>
+#include <condition_variable>
 
 #include "risk_game/player/alpha_zero/alphazero_mcts.h"
 #include "risk_game/player/alpha_zero/neural_network/alphazero_nn.h"
@@ -324,6 +326,25 @@ REF_API void ref_mcts_trim(void* m) { ((RefMcts*)m)->mcts.getStorage()->trimNode
 REF_API int ref_mcts_table_size(void* m) { return (int)((RefMcts*)m)->mcts.store.state_map.size(); }
 REF_API uint64_t ref_mcts_evals(void* m) { return ((RefMcts*)m)->nn->evals; }
 
+static void root_stats(RefMcts* h, State& root, uint32_t* N43, float* Q43, float* P43, float* pi43, uint32_t* sumN, float* root_value)
+{
+	std::shared_ptr<StateSimulations> ss = h->mcts.getStorage()->getStateSimulation(root);
+	std::vector<float> policy = ss->calculateMoveProbability(1.0f);
+	for (int i = 0; i < ALL_MOVES; i++)
+	{
+		LandIndex li = Utility::i2li((uint8_t)i);
+		if (ss->moveValues.contains(li))
+		{
+			const SimulationValue& sv = ss->moveValues.at(li);
+			N43[i] = sv.N; Q43[i] = sv.Q; P43[i] = sv.P;
+		}
+		else { N43[i] = 0; Q43[i] = 0.0f; P43[i] = 0.0f; }
+		pi43[i] = policy[i];
+	}
+	*sumN = ss->sumN;
+	*root_value = ss->value;
+}
+
 /*
  * One AlphaZeroMCTS::simulate (alphazero_mcts.cpp:255-287) with THREADS_PER_MCTS = 1
  * semantics, driven from the calling thread so that every simulation can be given
@@ -347,21 +368,95 @@ REF_API int ref_mcts_search(void* m, void* s, uint64_t seed, uint32_t game, uint
 			copyState.setLog(false);
 			h->mcts.search(copyState, h->nn);
 		}
-		std::shared_ptr<StateSimulations> ss = h->mcts.getStorage()->getStateSimulation(root);
-		std::vector<float> policy = ss->calculateMoveProbability(1.0f);
-		for (int i = 0; i < ALL_MOVES; i++)
+		root_stats(h, root, N43, Q43, P43, pi43, sumN, root_value);
+		return 0;
+	}
+	catch (const std::exception& e) { snprintf(g_err, sizeof g_err, "%s", e.what()); return -1; }
+}
+
+/*
+ * AlphaZeroMCTS::simulate with K REAL search threads (threadSimulateJob, alphazero_mcts.cpp:310-320) running the
+ * UNMODIFIED AlphaZeroMCTS::search, forced into ONE of the interleavings the reference's locks allow — the "lockstep"
+ * schedule the CUDA search implements:
+ *   round r = simulations r*K .. r*K+K-1; thread j runs simulation r*K+j (its dice stream is (game, ply, r*K+j));
+ *   selection: thread 0 descends first, thread j+1 starts its descent when thread j has either reached predictFuture
+ *     (an unseen state: it parks there, like the reference's thread blocks on the batch queue) or finished (terminal
+ *     state: search() has already backed the result up).  Every getNextBestMoveAndSetVisited therefore sees the
+ *     active_N marks of the descents before it in the round (the "virtual loss" rule, alphazero_mcts.cpp:91-107);
+ *   completion: when all K have selected, the parked threads are released one at a time in thread order: evaluator,
+ *     normalize, StateSimulationsStorage::add (drops a state a previous thread of the round has added), addValue up
+ *     the path.
+ * The threads only take turns; every tree operation is the reference's own code.
+ */
+struct Lockstep
+{
+	std::mutex mu; std::condition_variable cv;
+	int K = 1, round = 0, sel_turn = 0, fin_turn = -1;
+};
+static thread_local int tl_slot = -1;
+static thread_local bool tl_parked = false;
+
+static void lockstep_selected(Lockstep* L, std::unique_lock<std::mutex>& lk)
+{
+	L->sel_turn++;
+	if (L->sel_turn == L->K) L->fin_turn = 0;
+	L->cv.notify_all();
+	L->cv.wait(lk, [&] { return L->fin_turn == tl_slot; });
+}
+
+static void lockstep_park(void* user)
+{
+	Lockstep* L = (Lockstep*)user;
+	std::unique_lock<std::mutex> lk(L->mu);
+	tl_parked = true;
+	lockstep_selected(L, lk);
+}
+
+REF_API int ref_mcts_search_lockstep(void* m, void* s, uint64_t seed, uint32_t game, uint32_t ply, int K,
+                                     uint32_t* N43, float* Q43, float* P43, float* pi43, uint32_t* sumN, float* root_value)
+{
+	try
+	{
+		RefMcts* h = (RefMcts*)m;
+		State& root = *(State*)s;
+		rng_philox(seed, game, ply, 0);
+		h->mcts.setRootState(root, h->nn);
+		int count = SETTINGS.MCTS_SIMULATIONS - (SETTINGS.MCTS_SIMULATIONS % SETTINGS.THREADS_PER_MCTS);
+		if (K < 1 || count % K != 0) { snprintf(g_err, sizeof g_err, "simulation count %d is not a multiple of K = %d", count, K); return -1; }
+		const int rounds = count / K;
+		Lockstep L; L.K = K;
+		h->nn->park = lockstep_park; h->nn->park_user = &L;
+		std::atomic<int> failed{ 0 };
+		std::string what;                                   /* g_err is thread-local: carry a worker's message back */
+		std::vector<std::thread> threads;
+		for (int j = 0; j < K; j++)
 		{
-			LandIndex li = Utility::i2li((uint8_t)i);
-			if (ss->moveValues.contains(li))
-			{
-				const SimulationValue& sv = ss->moveValues.at(li);
-				N43[i] = sv.N; Q43[i] = sv.Q; P43[i] = sv.P;
-			}
-			else { N43[i] = 0; Q43[i] = 0.0f; P43[i] = 0.0f; }
-			pi43[i] = policy[i];
+			threads.push_back(std::thread([&, j] {
+				tl_slot = j;
+				for (int r = 0; r < rounds; r++)
+				{
+					{
+						std::unique_lock<std::mutex> lk(L.mu);
+						L.cv.wait(lk, [&] { return L.round == r && L.sel_turn == j; });
+					}
+					tl_parked = false;
+					rng_philox(seed, game, ply, (uint32_t)(r * K + j));
+					State copyState = root;
+					copyState.setLog(false);
+					try { h->mcts.search(copyState, h->nn); }
+					catch (const std::exception& e) { std::lock_guard<std::mutex> g(L.mu); what = e.what(); failed = 1; }
+					std::unique_lock<std::mutex> lk(L.mu);
+					if (!tl_parked) lockstep_selected(&L, lk);     /* terminal descent: backed up already, keeps its place in the order */
+					L.fin_turn++;
+					if (L.fin_turn == K) { L.round++; L.sel_turn = 0; L.fin_turn = -1; }
+					L.cv.notify_all();
+				}
+			}));
 		}
-		*sumN = ss->sumN;
-		*root_value = ss->value;
+		for (auto& t : threads) t.join();
+		h->nn->park = nullptr; h->nn->park_user = nullptr;
+		if (failed) { snprintf(g_err, sizeof g_err, "%s", what.c_str()); return -1; }
+		root_stats(h, root, N43, Q43, P43, pi43, sumN, root_value);
 		return 0;
 	}
 	catch (const std::exception& e) { snprintf(g_err, sizeof g_err, "%s", e.what()); return -1; }

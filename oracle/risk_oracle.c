@@ -896,6 +896,8 @@ ro_mcts* ro_mcts_new(ro_eval_fn eval, void* user)
 void ro_mcts_free(ro_mcts* m) { if (m) { free(m->nodes); free(m); } }
 void ro_mcts_clear(ro_mcts* m) { m->n_nodes = 0; }
 int ro_mcts_table_size(const ro_mcts* m) { return m->n_nodes; }
+uint64_t ro_mcts_vl_skips(const ro_mcts* m) { return m->vl_skips; }
+uint64_t ro_mcts_vl_duplicates(const ro_mcts* m) { return m->vl_duplicates; }
 
 /* StateSimulationsStorage::trimNodes, alphazero_mcts.cpp:229-245 */
 void ro_mcts_trim(ro_mcts* m)
@@ -934,12 +936,13 @@ static int expand(ro_mcts* m, const ro_state* s, uint64_t valid, float* value_ou
 }
 
 /* StateSimulations::getNextBestMoveAndSetVisited, alphazero_mcts.cpp:67-119 with the
-   ascending-index iteration order of the contract; active_N is always 0 at selection
-   time when THREADS_PER_MCTS = 1, so the duplicate-request branch never fires */
-static int select_move(ro_node* n, const ro_rules* r)
+   ascending-index iteration order of the contract.  A move nobody has backed up yet (N == 0)
+   that exactly one descent is exploring (active_N == 1) is passed over (:91-93) unless no
+   other move can be chosen (:108-111); with one descent at a time active_N is 0 here. */
+static int select_move(ro_mcts* m, ro_node* n, const ro_rules* r)
 {
     n->visited = 1;
-    int best = -1; float best_u = -INFINITY;
+    int best = -1, dup = -1; float best_u = -INFINITY, dup_u = -INFINITY;
     for (int i = 0; i < RO_MOVES; ++i) {
         if (!((n->valid >> i) & 1)) continue;
         float P = n->P[i];
@@ -947,9 +950,24 @@ static int select_move(ro_node* n, const ro_rules* r)
         float v = noiseP * r->cpuct * sqrtf(1.0f + (float)n->sumN);
         float nn = 1.0f + (float)n->N[i];
         float u = n->Q[i] + (v / nn);
-        if (u > best_u) { best_u = u; best = i; }
+        if (u > best_u) {
+            if (n->N[i] == 0 && n->active[i] == 1) { m->vl_skips++; if (u > dup_u) { dup_u = u; dup = i; } }
+            else { best_u = u; best = i; }
+        }
     }
+    if (best < 0) { best = dup; m->vl_duplicates++; }
+    n->active[best]++;
     return best;
+}
+
+/* SimulationValue::addValue + StateSimulations::addValue, alphazero_mcts.cpp:8-21, 56-61 */
+static void add_value(ro_node* n, int mv, float v)
+{
+    if (n->N[mv] == 0) n->Q[mv] = v;
+    else n->Q[mv] = ((float)n->N[mv] * n->Q[mv] + v) / (float)(n->N[mv] + 1);
+    n->N[mv]++;
+    n->active[mv]--;
+    n->sumN++;
 }
 
 /* AlphaZeroMCTS::search, alphazero_mcts.cpp:322-377 */
@@ -961,19 +979,96 @@ static float search(ro_mcts* m, ro_state* s, const ro_rules* r, ro_dice* dice, i
     int idx = find_node(m, s);
     if (idx < 0) { float v; expand(m, s, valid, &v); return v; }
     m->descents++;
-    int mv = select_move(&m->nodes[idx], r);
+    int mv = select_move(m, &m->nodes[idx], r);
     int cur = s->cur;
     if (ro_make_move(s, mv, r, dice) != RO_OK) { *err = 1; return 0.0f; }
     int next = s->cur;                 /* sampled BEFORE recursing: the recursion keeps mutating *s */
     float v = search(m, s, r, dice, err);
     if (next != cur) v = -v;
-    ro_node* n = &m->nodes[idx]; /* re-fetch: expand may have moved the array */
-    /* SimulationValue::addValue, alphazero_mcts.cpp:8-21 */
-    if (n->N[mv] == 0) n->Q[mv] = v;
-    else n->Q[mv] = ((float)n->N[mv] * n->Q[mv] + v) / (float)(n->N[mv] + 1);
-    n->N[mv]++;
-    n->sumN++;
+    add_value(&m->nodes[idx], mv, v);   /* re-fetched: expand may have moved the array */
     return v;
+}
+
+/* root statistics via calculateMoveProbability(1.0), alphazero_mcts.cpp:121-148 */
+static void root_stats(const ro_mcts* m, const ro_state* root, uint32_t N[RO_MOVES], float Q[RO_MOVES], float P[RO_MOVES],
+                       float pi[RO_MOVES], uint32_t* sumN, float* root_value)
+{
+    const ro_node* n = &m->nodes[find_node(m, root)];
+    float sum = 0.0f;
+    for (int i = 0; i < RO_MOVES; ++i) {
+        int ok = (int)((n->valid >> i) & 1);
+        N[i] = ok ? n->N[i] : 0; Q[i] = ok ? n->Q[i] : 0.0f; P[i] = ok ? n->P[i] : 0.0f;
+        pi[i] = ok ? (float)pow((double)n->N[i], 1.0 / 1.0f) : 0.0f;
+        if (ok) sum += pi[i];
+    }
+    for (int i = 0; i < RO_MOVES; ++i) pi[i] /= sum;
+    *sumN = n->sumN; *root_value = n->value;
+}
+
+
+/* one descent of the lockstep schedule: AlphaZeroMCTS::search (alphazero_mcts.cpp:322-377) unrolled up to the point where the
+   reference's thread would block in predictFuture (:350) */
+#define RO_PATH_MAX 1024
+typedef struct ro_descent {
+    int node[RO_PATH_MAX]; uint8_t mv[RO_PATH_MAX], flip[RO_PATH_MAX];
+    int len, pending;
+    ro_state leaf; uint64_t valid;
+} ro_descent;
+
+static void backup(ro_mcts* m, const ro_descent* d, float v)
+{
+    for (int k = d->len - 1; k >= 0; --k) {
+        if (d->flip[k]) v = -v;
+        add_value(&m->nodes[d->node[k]], d->mv[k], v);
+    }
+}
+
+int ro_mcts_search_lockstep(ro_mcts* m, const ro_state* root, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply, int K,
+                            uint32_t N[RO_MOVES], float Q[RO_MOVES], float P[RO_MOVES], float pi[RO_MOVES], uint32_t* sumN, float* root_value)
+{
+    ro_mcts_trim(m);
+    if (find_node(m, root) < 0) { float v; expand(m, root, ro_valid_moves(root, r), &v); }
+    int count = r->mcts_simulations - (r->mcts_simulations % r->threads_per_mcts);
+    if (K < 1 || count % K != 0) return RO_ERR_ILLEGAL_ACTION;
+    ro_descent* ds = (ro_descent*)malloc(sizeof(ro_descent) * (size_t)K);
+    int rc = RO_OK;
+    for (int round = 0; round < count / K && rc == RO_OK; ++round) {
+        for (int j = 0; j < K && rc == RO_OK; ++j) {                  /* selection, in thread order */
+            ro_descent* d = &ds[j];
+            d->len = 0; d->pending = 0;
+            ro_dice dice; ro_dice_philox(&dice, seed, game, ply, (uint32_t)(round * K + j));
+            ro_state s = *root;
+            for (;;) {
+                int gs = ro_game_status(&s, r);
+                if (gs != RO_NOT_ENDED) { backup(m, d, gs == RO_DRAW ? 0.0f : (gs == s.cur ? 1.0f : -1.0f)); break; }
+                uint64_t valid = ro_valid_moves(&s, r);
+                int idx = find_node(m, &s);
+                if (idx < 0) { d->leaf = s; d->valid = valid; d->pending = 1; break; }
+                if (d->len == RO_PATH_MAX) { rc = RO_ERR_ILLEGAL_ACTION; break; }
+                m->descents++;
+                int mv = select_move(m, &m->nodes[idx], r);
+                int cur = s.cur;
+                if (ro_make_move(&s, mv, r, &dice) != RO_OK) { rc = RO_ERR_ILLEGAL_ACTION; break; }
+                d->node[d->len] = idx; d->mv[d->len] = (uint8_t)mv; d->flip[d->len] = (uint8_t)(s.cur != cur); d->len++;
+            }
+        }
+        for (int j = 0; j < K && rc == RO_OK; ++j) {                  /* completion, in thread order */
+            ro_descent* d = &ds[j];
+            if (!d->pending) continue;
+            float v;
+            if (find_node(m, &d->leaf) < 0) expand(m, &d->leaf, d->valid, &v);       /* StateSimulationsStorage::add */
+            else {                                                                  /* ... which drops a duplicate (:210-213); the value still counts */
+                float policy[RO_MOVES];
+                m->eval(&d->leaf, policy, &v, m->user);
+                m->evals++;
+            }
+            backup(m, d, v);
+        }
+    }
+    free(ds);
+    if (rc != RO_OK) return rc;
+    root_stats(m, root, N, Q, P, pi, sumN, root_value);
+    return RO_OK;
 }
 
 /* AlphaZeroMCTS::simulate + setRootState, alphazero_mcts.cpp:255-307;
@@ -991,16 +1086,7 @@ int ro_mcts_search(ro_mcts* m, const ro_state* root, const ro_rules* r, uint64_t
         search(m, &copy, r, &dice, &err);
         if (err) return RO_ERR_ILLEGAL_ACTION;
     }
-    const ro_node* n = &m->nodes[find_node(m, root)];
-    float sum = 0.0f;
-    for (int i = 0; i < RO_MOVES; ++i) {
-        int ok = (int)((n->valid >> i) & 1);
-        N[i] = ok ? n->N[i] : 0; Q[i] = ok ? n->Q[i] : 0.0f; P[i] = ok ? n->P[i] : 0.0f;
-        pi[i] = ok ? (float)pow((double)n->N[i], 1.0 / 1.0f) : 0.0f;
-        if (ok) sum += pi[i];
-    }
-    for (int i = 0; i < RO_MOVES; ++i) pi[i] /= sum;
-    *sumN = n->sumN; *root_value = n->value;
+    root_stats(m, root, N, Q, P, pi, sumN, root_value);
     return RO_OK;
 }
 

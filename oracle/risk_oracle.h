@@ -125,6 +125,7 @@ typedef struct ro_node {
     uint8_t visited;
     float Q[RO_MOVES], P[RO_MOVES];
     uint32_t N[RO_MOVES];
+    uint8_t active[RO_MOVES];    /* SimulationValue::active_N, alphazero_mcts.h:16-28: descents that selected the move and have not backed up yet */
 } ro_node;
 
 typedef struct ro_mcts {
@@ -132,6 +133,7 @@ typedef struct ro_mcts {
     int n_nodes, cap;
     ro_eval_fn eval; void* user;
     uint64_t evals, max_nodes, descents;
+    uint64_t vl_skips, vl_duplicates;   /* times the active_N rule passed a move over / had to request a duplicate (alphazero_mcts.cpp:91-111) */
 } ro_mcts;
 
 ro_mcts* ro_mcts_new(ro_eval_fn eval, void* user);
@@ -139,9 +141,18 @@ void ro_mcts_free(ro_mcts* m);
 void ro_mcts_clear(ro_mcts* m);                                                  /* StateSimulationsStorage::clearNodes */
 void ro_mcts_trim(ro_mcts* m);                                                   /* StateSimulationsStorage::trimNodes */
 int ro_mcts_table_size(const ro_mcts* m);
+uint64_t ro_mcts_vl_skips(const ro_mcts* m);
+uint64_t ro_mcts_vl_duplicates(const ro_mcts* m);
 /* AlphaZeroMCTS::simulate with T = 1 semantics; outputs root statistics (zeros for illegal moves) */
 int ro_mcts_search(ro_mcts* m, const ro_state* root, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply,
                    uint32_t N[RO_MOVES], float Q[RO_MOVES], float P[RO_MOVES], float pi[RO_MOVES], uint32_t* sumN, float* root_value);
+/* AlphaZeroMCTS::simulate with K search threads in the LOCKSTEP schedule (one of the interleavings the reference's locks allow,
+   pinned against the reference's own threads taking turns in oracle/ref/ref_shim.cpp ref_mcts_search_lockstep): simulations run in
+   rounds of K; within a round descent j selects after descents 0..j-1 (seeing their active_N marks — the "virtual loss" rule,
+   alphazero_mcts.cpp:91-107), a descent that ends in a terminal state backs up at once, the others are evaluated together and then
+   expanded + backed up in order j = 0..K-1.  K = 1 is ro_mcts_search. */
+int ro_mcts_search_lockstep(ro_mcts* m, const ro_state* root, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply, int K,
+                            uint32_t N[RO_MOVES], float Q[RO_MOVES], float P[RO_MOVES], float pi[RO_MOVES], uint32_t* sumN, float* root_value);
 int ro_pick_move(const float pi[RO_MOVES], int sample, uint64_t seed, uint32_t game, uint32_t ply);
 
 /* ---- bounded CPU timing loops for bench.py's cpu_baseline "port" ---- */

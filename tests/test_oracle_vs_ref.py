@@ -88,6 +88,39 @@ def test_mcts_lockstep(sims, T, play_mode):
     assert ply > 100
 
 
+@pytest.mark.parametrize("sims,K,play_mode,evaluator", [(16, 2, True, "pseudo"), (48, 4, False, "pseudo"), (32, 8, False, "uniform"),
+                                                        (24, 3, True, "uniform")])
+def test_mcts_virtual_loss_lockstep(sims, K, play_mode, evaluator):
+    """THREADS_PER_MCTS = K search threads of the UNMODIFIED reference (AlphaZeroMCTS::search, active_N rule of
+    getNextBestMoveAndSetVisited, alphazero_mcts.cpp:67-119) made to take turns in the lockstep schedule ==
+    ro_mcts_search_lockstep, bit for bit, over whole games; the duplicate-request branch must have fired"""
+    seed = 0xFACADE
+    rules = po.default_rules(mcts_simulations=sims, threads_per_mcts=K)
+    po.ref_apply_rules(rules)
+    mask = po.data_byte_mask()
+    o, r, om, rm = po.OracleGame(rules), po.RefGame(), po.OracleMcts(rules, evaluator), po.RefMcts(evaluator)
+    o.new_game(seed, 5)
+    r.new_game(seed, 5)
+    ply, last = 0, None
+    while o.status() == -1:
+        if play_mode and o.s.cur != last:
+            om.trim(); rm.trim(); last = o.s.cur
+        a, b = om.search(o, seed, 5, ply, lockstep=K), rm.search(r, seed, 5, ply, lockstep=K)
+        for k in ("N", "Q", "P", "pi"):
+            assert (a[k].view(np.uint32) == b[k].view(np.uint32)).all(), (ply, k)
+        assert a["sumN"] == b["sumN"] and a["value"] == b["value"] and om.table_size() == rm.table_size()
+        sample = (not play_mode) and o.s.round <= rules.temperature_threshold
+        mv = om.pick(a["pi"], sample, seed, 5, ply)
+        assert mv == rm.pick(b["pi"], sample, seed, 5, ply)
+        assert o.move(mv, seed, 5, ply) == 0 and r.move(mv, seed, 5, ply) == 0
+        assert (o.data()[mask] == r.data()[mask]).all()
+        ply += 1
+    po.ref_apply_rules(po.default_rules())
+    skips, dups = om.vl_counts()
+    assert ply > 100 and skips > 0
+    print("active_N rule: %d moves passed over, %d duplicate requests" % (skips, dups))
+
+
 @pytest.mark.parametrize("mode", ["script_vs_script", "script_vs_random_mover", "mirror_pair"])
 def test_script_player_lockstep(mode):
     """ro_script_turn == the UNMODIFIED ScriptPlayer::takeTurn (player/script/script_player.cpp:162-227): every Data field
