@@ -27,7 +27,8 @@ class AzRules(C.Structure):
     _fields_ = [("allow_yield", C.c_int32), ("limit_reinforcement", C.c_int32), ("limit_attack", C.c_int32),
                 ("max_game_rounds", C.c_int32), ("min_unit_move", C.c_int32), ("mcts_simulations", C.c_int32),
                 ("threads_per_mcts", C.c_int32), ("cpuct", C.c_float), ("dir_noise_value", C.c_float),
-                ("dir_noise_epsi", C.c_float), ("temperature_threshold", C.c_int32)]
+                ("dir_noise_epsi", C.c_float), ("temperature_threshold", C.c_int32),
+                ("concurrent_descents", C.c_int32)]
 
 
 class AzCounters(C.Structure):

@@ -43,6 +43,7 @@ extern "C" void az_default_rules(az_rules* r)
     r->allow_yield = 1; r->limit_reinforcement = 1; r->limit_attack = 0; r->max_game_rounds = 58; r->min_unit_move = 3;
     r->mcts_simulations = 32; r->threads_per_mcts = 2; r->cpuct = 1.1f; r->dir_noise_value = 0.3f; r->dir_noise_epsi = 0.25f;
     r->temperature_threshold = 43;
+    r->concurrent_descents = 1;
 }
 
 // ---------------------------------------------------------------- tables in HBM (one copy per device)

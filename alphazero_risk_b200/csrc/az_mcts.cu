@@ -6,8 +6,11 @@
 // backup Q = (N*Q + v)/(N+1) (:8-21), trim of nodes not visited since the previous search
 // (:229-245), root policy from visit counts (:121-148) and move choice (:379-412).
 //
-// B200 design: one WARP per game, THREADS_PER_MCTS = 1 semantics (one leaf in flight per game, so a
-// leaf batch is "all games").  Every game owns two node pools + two hash indices in HBM that
+// B200 design: one WARP per game.  az_rules.concurrent_descents = K descents per tree are in flight per leaf batch
+// (batch = K x games): the lockstep schedule of K search threads — descent j of a round selects after descents
+// 0..j-1 and sees their active_N marks (the reference's virtual-loss rule, :91-107), a descent that ends in a
+// terminal state backs up at once, the others are evaluated in one batch and then expanded + backed up in order.
+// K = 1 is THREADS_PER_MCTS = 1.  Every game owns two node pools + two hash indices in HBM that
 // ping-pong per search: nodes created or visited during search k live in pool k&1 (a node found in
 // the previous pool is migrated on first touch), so "trimNodes" is an epoch bump + clearing one
 // small index, and a node is alive exactly when the reference would still hold it.  A node is one
@@ -41,19 +44,20 @@ enum { CNT_SIMS = 0, CNT_EVALS = 1, CNT_POOL_OVERFLOW = 2, CNT_DEPTH_OVERFLOW = 
 
 struct MctsDev {
     int n, cap, H, dmax;
+    int K;                  // descents per tree that select before any backs up (az_rules.concurrent_descents); slot = j * n + game
     uint32_t* nodes;        // [n][2][cap][NODE_WORDS]
     uint32_t* index;        // [n][2][H]     0 = empty, else tag16 << 16 | (node + 1)
     uint32_t* count;        // [n][2]
     uint32_t* epoch;        // [n]
     uint32_t* migrated;     // [n]
-    uint32_t* path;         // [n][dmax]     node | move << 16 | flip << 22
-    uint32_t* path_len;     // [n]
-    uint32_t* leaf_state;   // [16][n]
-    uint64_t* leaf_valid;   // [n]
-    int32_t* pending;       // [n]
-    float* term_value;      // [n]
-    float* nn_policy;       // [n][43]
-    float* nn_value;        // [n]
+    uint32_t* path;         // [K*n][dmax]   node | move << 16 | flip << 22
+    uint32_t* path_len;     // [K*n]
+    uint32_t* leaf_state;   // [16][K*n]
+    uint64_t* leaf_valid;   // [K*n]
+    int32_t* pending;       // [K*n]
+    float* term_value;      // [K*n]
+    float* nn_policy;       // [K*n][43]
+    float* nn_value;        // [K*n]
     uint32_t* root_state;   // env state [16][n]
     uint8_t* extra_trim;    // [n] trims to add before the next search (play-mode turn start / new game)
     uint32_t* out_visits; float* out_pi; float* out_q; float* out_p; uint8_t* out_move; float* out_value; uint32_t* out_sumn; int32_t* out_table; int8_t* out_status;
@@ -186,48 +190,81 @@ __device__ __forceinline__ int find_node(const MctsDev& m, int gi, uint32_t cur,
     return (int)cnt;
 }
 
-// StateSimulations::getNextBestMoveAndSetVisited, alphazero_mcts.cpp:67-119 (ascending-index
-// iteration = the contract; active_N never blocks at THREADS_PER_MCTS = 1)
-__device__ __forceinline__ int puct_select(const MctsDev& m, const uint32_t* nd, int lane)
+// StateSimulations::getNextBestMoveAndSetVisited, alphazero_mcts.cpp:67-119 (ascending-index iteration = the
+// contract).  The N word of a move holds SimulationValue::N in its low 24 bits and active_N in the top byte.  A move
+// with N == 0 && active_N == 1 (one descent in flight is about to open it) is passed over (:91-93); if nothing else
+// can be chosen the best such move is requested a second time (:108-111).  The chosen move's active_N is incremented.
+__device__ __forceinline__ int puct_select(const MctsDev& m, uint32_t* nd, int lane)
 {
     const uint64_t valid = (uint64_t)nd[NW_VALID] | ((uint64_t)nd[NW_VALID + 1] << 32);
     const float sq = __fsqrt_rn(__fadd_rn(1.0f, (float)nd[NW_SUMN]));
-    float bu = -INFINITY; int bi = 64;
+    float bu = -INFINITY, du = -INFINITY; int bi = 64, di = 64;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         int i = lane + 32 * k;
         if (i < AZ_MOVES && ((valid >> i) & 1ull)) {
             float P = __uint_as_float(nd[NW_P + i]), Q = __uint_as_float(nd[NW_Q + i]);
+            const uint32_t nw = nd[NW_N + i], N = nw & 0xffffffu;
             float noiseP = __fadd_rn(__fmul_rn(m.c1, P), m.c2);
             float v = __fmul_rn(__fmul_rn(noiseP, m.cpuct), sq);
-            float nn = __fadd_rn(1.0f, (float)nd[NW_N + i]);
+            float nn = __fadd_rn(1.0f, (float)N);
             float u = __fadd_rn(Q, __fdiv_rn(v, nn));
-            if (u > bu) { bu = u; bi = i; }
+            if (N == 0u && (nw >> 24) == 1u) { if (u > du) { du = u; di = i; } }
+            else if (u > bu) { bu = u; bi = i; }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         float ou = __shfl_xor_sync(FULL, bu, o); int oi = __shfl_xor_sync(FULL, bi, o);
         if (ou > bu || (ou == bu && oi < bi)) { bu = ou; bi = oi; }
+        ou = __shfl_xor_sync(FULL, du, o); oi = __shfl_xor_sync(FULL, di, o);
+        if (ou > du || (ou == du && oi < di)) { du = ou; di = oi; }
     }
+    if (bi == 64) bi = di;
+    if (bi < AZ_MOVES && lane == (bi & 31)) nd[NW_N + bi] += 1u << 24;
+    __syncwarp();
     return bi;
+}
+
+// StateSimulations::addValue up the recorded path of one descent (AlphaZeroMCTS::search :363-372, SimulationValue::addValue :8-21)
+__device__ __forceinline__ void backup_path(const MctsDev& m, int slot, int gi, uint32_t cur, float v, uint32_t len, int lane)
+{
+    __syncwarp();
+    if (len > 0 && lane == 0) {
+        for (int d = (int)len - 1; d >= 0; --d) {
+            uint32_t e = m.path[(size_t)slot * m.dmax + d];
+            uint32_t idx = e & 0xffffu, mv = (e >> 16) & 63u;
+            if ((e >> 22) & 1u) v = -v;
+            uint32_t* nd = node_ptr(m, gi, cur, idx);
+            const uint32_t nw = nd[NW_N + mv], N = nw & 0xffffffu, act = nw >> 24;
+            float Q = __uint_as_float(nd[NW_Q + mv]);
+            float q = N == 0 ? v : __fdiv_rn(__fadd_rn(__fmul_rn((float)N, Q), v), (float)(N + 1u));
+            nd[NW_Q + mv] = __float_as_uint(q);
+            nd[NW_N + mv] = (N + 1u) | (((act - 1u) & 0xffu) << 24);
+            nd[NW_SUMN] += 1u;
+        }
+        m.path_len[slot] = 0;
+        atomicAdd(&m.counters[CNT_SIMS], 1ull);
+    }
+    __syncwarp();
 }
 
 // part 1 of a simulation step: expand the pending leaf with the evaluator's output
 // (StateSimulations ctor :26-42 after NNOutputData::normalize, alphazero_nn_data.cpp:3-27)
 // and back the value up the recorded path (AlphaZeroMCTS::search :363-372, addValue :8-21)
-__device__ __forceinline__ void expand_and_backup(const MctsDev& m, int gi, uint32_t cur, WG& w, int lane)
+// for descent slot = j * n + gi; a state an earlier descent of the round has added is dropped (StateSimulationsStorage::add :203-215)
+__device__ __forceinline__ void expand_and_backup(const MctsDev& m, int slot, int gi, uint32_t cur, WG& w, int lane)
 {
-    const uint32_t len = m.path_len[gi];
-    float v = m.term_value[gi];
-    if (m.pending[gi]) {
-        wg_load(w, m.leaf_state, m.n, gi, lane);
-        const uint64_t valid = m.leaf_valid[gi];
+    const uint32_t len = m.path_len[slot];
+    float v = m.term_value[slot];
+    if (m.pending[slot]) {
+        wg_load(w, m.leaf_state, m.K * m.n, slot, lane);
+        const uint64_t valid = m.leaf_valid[slot];
         float p0 = 0.0f, p1 = 0.0f, value;
         if (m.eval_mode == EVAL_NN) {
-            p0 = m.nn_policy[(size_t)gi * AZ_MOVES + lane];
-            if (lane + 32 < AZ_MOVES) p1 = m.nn_policy[(size_t)gi * AZ_MOVES + 32 + lane];
-            value = m.nn_value[gi];
+            p0 = m.nn_policy[(size_t)slot * AZ_MOVES + lane];
+            if (lane + 32 < AZ_MOVES) p1 = m.nn_policy[(size_t)slot * AZ_MOVES + 32 + lane];
+            value = m.nn_value[slot];
         } else if (m.eval_mode == EVAL_PSEUDO) {
             uint64_t key = az_pn_key((const uint8_t*)w.row, (int)w.g.cur, (int)w.g.round, (int)w.g.phase);
             p0 = az_pn_policy(key, lane);
@@ -258,68 +295,57 @@ __device__ __forceinline__ void expand_and_backup(const MctsDev& m, int gi, uint
             nd[NW_P + lane] = __float_as_uint(p0); nd[NW_Q + lane] = 0u; nd[NW_N + lane] = 0u;
             if (lane < 12) { nd[NW_P + 32 + lane] = __float_as_uint(p1); nd[NW_Q + 32 + lane] = 0u; nd[NW_N + 32 + lane] = 0u; }
             __syncwarp();
-            if (lane == 0) { m.count[gi * 2 + cur] = cnt + 1; atomicAdd(&m.counters[CNT_EVALS], 1ull); }
+            if (lane == 0) m.count[gi * 2 + cur] = cnt + 1;
             index_insert(m, gi, cur, ins, h, cnt, lane);
         } else if (found < 0 && lane == 0) atomicAdd(&m.counters[CNT_POOL_OVERFLOW], 1ull);
         v = value;
-        if (lane == 0) m.pending[gi] = 0;
+        if (lane == 0) { m.pending[slot] = 0; atomicAdd(&m.counters[CNT_EVALS], 1ull); }
     }
-    if (len > 0 && lane == 0) {
-        for (int d = (int)len - 1; d >= 0; --d) {
-            uint32_t e = m.path[(size_t)gi * m.dmax + d];
-            uint32_t idx = e & 0xffffu, mv = (e >> 16) & 63u;
-            if ((e >> 22) & 1u) v = -v;
-            uint32_t* nd = node_ptr(m, gi, cur, idx);
-            uint32_t N = nd[NW_N + mv];
-            float Q = __uint_as_float(nd[NW_Q + mv]);
-            float q = N == 0 ? v : __fdiv_rn(__fadd_rn(__fmul_rn((float)N, Q), v), (float)(N + 1u));
-            nd[NW_Q + mv] = __float_as_uint(q);
-            nd[NW_N + mv] = N + 1u;
-            nd[NW_SUMN] += 1u;
-        }
-        m.path_len[gi] = 0;
-        atomicAdd(&m.counters[CNT_SIMS], 1ull);
-    }
-    __syncwarp();
+    backup_path(m, slot, gi, cur, v, len, lane);
 }
 
-// part 2: one descent from the root (AlphaZeroMCTS::search :322-377 unrolled into a loop).
-// sim < 0: only the root lookup of setRootState (:289-307).
-__device__ __forceinline__ void descend(const MctsDev& m, int gi, uint32_t cur, WG& w, const AzTables& T, int sim, int lane)
+// part 2: one descent from the root (AlphaZeroMCTS::search :322-377 unrolled into a loop) for descent slot = j * n + gi.
+// sim < 0: only the root lookup of setRootState (:289-307).  A descent that reaches a terminal state backs up here
+// (the reference's recursion unwinds at once); one that reaches an unseen state is queued for the evaluator.
+__device__ __forceinline__ void descend(const MctsDev& m, int slot, int gi, uint32_t cur, WG& w, const AzTables& T, int sim, int lane)
 {
+    const size_t ns = (size_t)m.K * m.n;
     wg_load(w, m.root_state, m.n, gi, lane);
     const uint32_t ply = w.row[AZ_W_PLY];
-    if (az_game_status(w.g, m.rules) != AZ_STATUS_RUNNING) { if (lane == 0) { m.pending[gi] = 0; m.path_len[gi] = 0; m.term_value[gi] = 0.0f; } return; }
+    if (az_game_status(w.g, m.rules) != AZ_STATUS_RUNNING) { if (lane == 0) { m.pending[slot] = 0; m.path_len[slot] = 0; m.term_value[slot] = 0.0f; } return; }
     AzDicePhilox dice; dice.init(m.seed, m.first_game + (uint32_t)gi, ply, (uint32_t)(sim < 0 ? 0 : sim));
     uint32_t depth = 0;
     for (;;) {
         __syncwarp();
         int st = az_game_status(w.g, m.rules);
         if (st != AZ_STATUS_RUNNING) {
-            if (lane == 0) { m.term_value[gi] = st == AZ_STATUS_DRAW ? 0.0f : ((uint32_t)st == w.g.cur ? 1.0f : -1.0f); m.pending[gi] = 0; }
+            const float tv = st == AZ_STATUS_DRAW ? 0.0f : ((uint32_t)st == w.g.cur ? 1.0f : -1.0f);
+            if (lane == 0) { m.term_value[slot] = tv; m.pending[slot] = 0; }
+            backup_path(m, slot, gi, cur, tv, depth, lane);
+            depth = 0;
             break;
         }
         uint64_t valid = az_valid_moves(w.g, T, m.rules);
         uint64_t h; int ins;
         int idx = find_node(m, gi, cur, w, lane, h, ins);
         if (idx < 0) {                                      // unseen state: queue it for evaluation
-            if (lane < 14) m.leaf_state[(size_t)lane * m.n + gi] = w.row[lane];
-            if (lane == 0) { m.leaf_valid[gi] = valid; m.pending[gi] = idx == -1 ? 1 : 0; m.term_value[gi] = 0.0f; }
+            if (lane < 14) m.leaf_state[(size_t)lane * ns + slot] = w.row[lane];
+            if (lane == 0) { m.leaf_valid[slot] = valid; m.pending[slot] = idx == -1 ? 1 : 0; m.term_value[slot] = 0.0f; }
             break;
         }
-        if (sim < 0) { if (lane == 0) m.pending[gi] = 0; break; }       // setRootState: root already known
-        if ((int)depth >= m.dmax) { if (lane == 0) { atomicAdd(&m.counters[CNT_DEPTH_OVERFLOW], 1ull); m.pending[gi] = 0; m.term_value[gi] = 0.0f; } break; }
-        const uint32_t* nd = node_ptr(m, gi, cur, (uint32_t)idx);
+        if (sim < 0) { if (lane == 0) m.pending[slot] = 0; break; }       // setRootState: root already known
+        if ((int)depth >= m.dmax) { if (lane == 0) { atomicAdd(&m.counters[CNT_DEPTH_OVERFLOW], 1ull); m.pending[slot] = 0; m.term_value[slot] = 0.0f; } break; }
+        uint32_t* nd = node_ptr(m, gi, cur, (uint32_t)idx);
         int mv = puct_select(m, nd, lane);
         uint32_t before = w.g.cur;
         __syncwarp();      // every lane runs the (identical) transition on the shared row: keep them converged
         az_make_move(w.g, w.land, w.scratch, T, m.rules, valid, mv, dice);
         wg_flush(w, lane);
         uint32_t flip = w.g.cur != before ? 1u : 0u;
-        if (lane == 0) m.path[(size_t)gi * m.dmax + depth] = (uint32_t)idx | ((uint32_t)mv << 16) | (flip << 22);
+        if (lane == 0) m.path[(size_t)slot * m.dmax + depth] = (uint32_t)idx | ((uint32_t)mv << 16) | (flip << 22);
         depth++;
     }
-    if (lane == 0) m.path_len[gi] = depth;
+    if (lane == 0) m.path_len[slot] = depth;
     __syncwarp();
 }
 
@@ -421,10 +447,13 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_begin(MctsDev m, int e
         for (int i = lane; i < m.H; i += 32) ix[i] = 0u;
         if (lane == 0) m.count[gi * 2 + pool] = 0u;
     }
-    if (lane == 0) { m.epoch[gi] = e; m.extra_trim[gi] = 0; m.migrated[gi] = 0; m.pending[gi] = 0; m.path_len[gi] = 0; }
+    if (lane == 0) { m.epoch[gi] = e; m.extra_trim[gi] = 0; m.migrated[gi] = 0; }
+    if (lane < m.K) { m.pending[lane * m.n + gi] = 0; m.path_len[lane * m.n + gi] = 0; }
 }
 
-__global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_sim(MctsDev m, const uint64_t* __restrict__ g_tab, int sim, int do_descent)
+// one round: complete the K descents of the previous round in order, then start the K descents of this one in order
+// (round < 0: setRootState)
+__global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_sim(MctsDev m, const uint64_t* __restrict__ g_tab, int round, int do_descent)
 {
     __shared__ uint64_t s_tab[AZ_TABLE_U64];
     __shared__ WarpSmem s_w;
@@ -436,8 +465,10 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_sim(MctsDev m, const u
     if (gi >= m.n) return;
     WG w; wg_bind(w, s_w, warp);
     const uint32_t cur = m.epoch[gi] & 1u;
-    expand_and_backup(m, gi, cur, w, lane);
-    if (do_descent) descend(m, gi, cur, w, T, sim, lane);
+    for (int j = 0; j < m.K; ++j) expand_and_backup(m, j * m.n + gi, gi, cur, w, lane);
+    if (!do_descent) return;
+    if (round < 0) descend(m, gi, gi, cur, w, T, -1, lane);
+    else for (int j = 0; j < m.K; ++j) descend(m, j * m.n + gi, gi, cur, w, T, round * m.K + j, lane);
 }
 
 // after the last simulation: root statistics (calculateMoveProbability :121-148), move choice
@@ -456,7 +487,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_finish(MctsDev m, cons
     if (gi >= m.n) return;
     WG w; wg_bind(w, s_w, warp);
     const uint32_t cur = m.epoch[gi] & 1u;
-    expand_and_backup(m, gi, cur, w, lane);
+    for (int j = 0; j < m.K; ++j) expand_and_backup(m, j * m.n + gi, gi, cur, w, lane);
     wg_load(w, m.root_state, m.n, gi, lane);
     uint32_t ply = w.row[AZ_W_PLY];
     const uint32_t game = m.first_game + (uint32_t)gi;
@@ -472,8 +503,8 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_finish(MctsDev m, cons
             const uint32_t* nd = node_ptr(m, gi, cur, (uint32_t)idx);
             valid = (uint64_t)nd[NW_VALID] | ((uint64_t)nd[NW_VALID + 1] << 32);
             sumn = nd[NW_SUMN]; value = __uint_as_float(nd[NW_VALUE]);
-            if ((valid >> lane) & 1ull) { n0 = nd[NW_N + lane]; q0 = __uint_as_float(nd[NW_Q + lane]); pr0 = __uint_as_float(nd[NW_P + lane]); }
-            if (lane + 32 < AZ_MOVES && ((valid >> (lane + 32)) & 1ull)) { n1 = nd[NW_N + 32 + lane]; q1 = __uint_as_float(nd[NW_Q + 32 + lane]); pr1 = __uint_as_float(nd[NW_P + 32 + lane]); }
+            if ((valid >> lane) & 1ull) { n0 = nd[NW_N + lane] & 0xffffffu; q0 = __uint_as_float(nd[NW_Q + lane]); pr0 = __uint_as_float(nd[NW_P + lane]); }
+            if (lane + 32 < AZ_MOVES && ((valid >> (lane + 32)) & 1ull)) { n1 = nd[NW_N + 32 + lane] & 0xffffffu; q1 = __uint_as_float(nd[NW_Q + 32 + lane]); pr1 = __uint_as_float(nd[NW_P + 32 + lane]); }
         }
         float f0 = (float)n0, f1 = (float)n1, sum = 0.0f;
         for (int i = 0; i < AZ_MOVES; ++i) {
@@ -586,6 +617,9 @@ extern "C" int az_mcts_create(az_env* env, az_nn* nn, int evaluator, int precisi
     int T = r->threads_per_mcts < 1 ? 1 : r->threads_per_mcts;
     int sims = r->mcts_simulations - (r->mcts_simulations % T);          // alphazero_mcts.cpp:265
     AZ_REQUIRE(sims >= 1, "mcts_simulations - mcts_simulations % threads_per_mcts must be >= 1");
+    const int K = r->concurrent_descents < 1 ? 1 : r->concurrent_descents;
+    AZ_REQUIRE(K <= 16, "concurrent_descents must be <= 16");
+    AZ_REQUIRE(sims % K == 0, "the simulation count (mcts_simulations - mcts_simulations % threads_per_mcts) must be a multiple of concurrent_descents");
     AzDeviceGuard guard(az_env_device(env));
     if (evaluator == EVAL_NN && !nn->finalized) { int frc = az_nn_finalize(nn); if (frc) return frc; }   // weights loaded but not yet folded / packed
     az_mcts* mc = new (std::nothrow) az_mcts();
@@ -593,24 +627,24 @@ extern "C" int az_mcts_create(az_env* env, az_nn* nn, int evaluator, int precisi
     mc->env = env; mc->nn = nn; mc->evaluator = evaluator; mc->precision = precision; mc->device = az_env_device(env);
     MctsDev& d = mc->d;
     memset(&d, 0, sizeof d);
-    d.n = az_env_n(env);
+    d.n = az_env_n(env); d.K = K;
     d.cap = 3 * (sims + 1) + 64; if (d.cap > 65000) d.cap = 65000;
     d.H = next_pow2(2 * d.cap);
     d.dmax = 192;
-    size_t n = (size_t)d.n;
+    size_t n = (size_t)d.n, ns = n * (size_t)K;          // ns = descent slots = leaf batch
     int rc = 0;
     rc |= dalloc(mc, &d.nodes, n * 2 * d.cap * NODE_WORDS, false);
     rc |= dalloc(mc, &d.index, n * 2 * d.H);
     rc |= dalloc(mc, &d.count, n * 2); rc |= dalloc(mc, &d.epoch, n); rc |= dalloc(mc, &d.migrated, n);
-    rc |= dalloc(mc, &d.path, n * d.dmax); rc |= dalloc(mc, &d.path_len, n);
-    rc |= dalloc(mc, &d.leaf_state, n * 16); rc |= dalloc(mc, &d.leaf_valid, n); rc |= dalloc(mc, &d.pending, n);
-    rc |= dalloc(mc, &d.term_value, n); rc |= dalloc(mc, &d.nn_policy, n * AZ_MOVES); rc |= dalloc(mc, &d.nn_value, n);
+    rc |= dalloc(mc, &d.path, ns * d.dmax); rc |= dalloc(mc, &d.path_len, ns);
+    rc |= dalloc(mc, &d.leaf_state, ns * 16); rc |= dalloc(mc, &d.leaf_valid, ns); rc |= dalloc(mc, &d.pending, ns);
+    rc |= dalloc(mc, &d.term_value, ns); rc |= dalloc(mc, &d.nn_policy, ns * AZ_MOVES); rc |= dalloc(mc, &d.nn_value, ns);
     rc |= dalloc(mc, &d.extra_trim, n);
     rc |= dalloc(mc, &d.out_visits, n * AZ_MOVES); rc |= dalloc(mc, &d.out_pi, n * AZ_MOVES); rc |= dalloc(mc, &d.out_q, n * AZ_MOVES);
     rc |= dalloc(mc, &d.out_p, n * AZ_MOVES); rc |= dalloc(mc, &d.out_move, n); rc |= dalloc(mc, &d.out_value, n);
     rc |= dalloc(mc, &d.out_sumn, n); rc |= dalloc(mc, &d.out_table, n); rc |= dalloc(mc, &d.out_status, n);
     rc |= dalloc(mc, &d.counters, (size_t)CNT_N);
-    if (evaluator == EVAL_NN) rc |= dalloc(mc, &mc->d_x, n * AZ_INPUT_FLOATS);
+    if (evaluator == EVAL_NN) rc |= dalloc(mc, &mc->d_x, ns * AZ_INPUT_FLOATS);
     if (rc) { for (void* p : mc->allocs) cudaFree(p); delete mc; return AZ_ERR_CUDA; }
     d.root_state = az_env_state_ptr(env);
     d.c1 = 1.0f - r->dir_noise_epsi;                 // (1 - SETTINGS.DIR_NOISE_EPSI), alphazero_mcts.cpp:81
@@ -653,12 +687,13 @@ static int evaluate_leaves(az_mcts* mc, cudaStream_t s)
 {
     if (mc->evaluator != EVAL_NN) return AZ_OK;
     MctsDev& d = mc->d;
+    const int ns = d.n * d.K;                            // every descent slot goes through the network (slot = j * n + game)
     if (mc->precision == AZ_NN_BF16) {
-        int rc = az_nn_reserve(mc->nn, d.n); if (rc) return rc;
-        return az_nn_tc_forward(mc->nn, nullptr, d.leaf_state, d.n, d.nn_policy, d.nn_value, s);
+        int rc = az_nn_reserve(mc->nn, ns); if (rc) return rc;
+        return az_nn_tc_forward(mc->nn, nullptr, d.leaf_state, ns, d.nn_policy, d.nn_value, s);
     }
-    int rc = az_launch_encode(d.leaf_state, d.n, mc->d_x, s); if (rc) return rc;
-    return az_nn_forward_dev(mc->nn, mc->d_x, d.n, d.nn_policy, d.nn_value, AZ_NN_FP32, s);
+    int rc = az_launch_encode(d.leaf_state, ns, mc->d_x, s); if (rc) return rc;
+    return az_nn_forward_dev(mc->nn, mc->d_x, ns, d.nn_policy, d.nn_value, AZ_NN_FP32, s);
 }
 
 // one AlphaZeroMCTS::simulate (alphazero_mcts.cpp:255-287) for every game, then the move choice
@@ -672,7 +707,7 @@ static int search_once(az_mcts* mc, int extra_all, int pick_mode, int apply_move
     k_mcts_sim<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, -1, 1);             // setRootState
     AZ_CUDA(cudaGetLastError());
     int rc = evaluate_leaves(mc, s); if (rc) return rc;
-    for (int i = 0; i < sims; ++i) {
+    for (int i = 0; i < sims / d.K; ++i) {               // rounds of K descents per tree
         k_mcts_sim<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, i, 1);
         AZ_CUDA(cudaGetLastError());
         rc = evaluate_leaves(mc, s); if (rc) return rc;

@@ -71,6 +71,9 @@ typedef struct az_rules {
     float dir_noise_value;           /* DIR_NOISE_VALUE           --dnv                   default 0.3 */
     float dir_noise_epsi;            /* DIR_NOISE_EPSI            --dne                   default 0.25 */
     int32_t temperature_threshold;   /* TEMPERATURE_TRESHOLD      --temp                  default 43 */
+    int32_t concurrent_descents;     /* K descents per tree in flight per leaf batch: the lockstep schedule of K of the reference's search
+                                        threads with its active_N ("virtual loss") rule, alphazero_mcts.cpp:91-111.  0 or 1 = one at a
+                                        time (THREADS_PER_MCTS = 1 semantics, default); must divide the simulation count; <= 16 */
 } az_rules;
 
 typedef struct az_env az_env;

@@ -25,9 +25,9 @@ def bits(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
 
-def run_lockstep(api, n, first, sims, T, play_mode, max_moves, evaluator="pseudo", net=None, oracle_eval=None):
+def run_lockstep(api, n, first, sims, T, play_mode, max_moves, evaluator="pseudo", net=None, oracle_eval=None, K=1):
     rules_o = po.default_rules(mcts_simulations=sims, threads_per_mcts=T)
-    rules_d = api.default_rules(mcts_simulations=sims, threads_per_mcts=T)
+    rules_d = api.default_rules(mcts_simulations=sims, threads_per_mcts=T, concurrent_descents=K)
     env = api.Env(n, rules=rules_d, first_game_id=first)
     env.reset(SEED)
     ev = {"pseudo": api.EVAL_PSEUDO, "uniform": api.EVAL_UNIFORM, "nn": api.EVAL_NN}[evaluator]
@@ -60,7 +60,7 @@ def run_lockstep(api, n, first, sims, T, play_mode, max_moves, evaluator="pseudo
                 continue
             if play_mode and extra[g]:
                 trees[g].trim(); last_cur[g] = o.s.cur
-            a = trees[g].search(o, SEED, first + g, int(ply[g]))
+            a = trees[g].search(o, SEED, first + g, int(ply[g]), lockstep=K)
             assert (res["N"][g] == a["N"]).all(), (step, g, res["N"][g], a["N"])
             assert (bits(rs["Q"][g]) == bits(a["Q"])).all(), (step, g)
             assert (bits(rs["P"][g]) == bits(a["P"])).all(), (step, g)
@@ -83,6 +83,8 @@ def run_lockstep(api, n, first, sims, T, play_mode, max_moves, evaluator="pseudo
     cnt = mc.counters()
     assert cnt["errors"] == 0 and cnt["illegal"] == 0
     assert cnt["sims"] == moves_done * (sims - sims % T)
+    if K > 1:      # the active_N rule must have fired: moves passed over and duplicate requests
+        assert sum(t.vl_counts()[0] for t in trees) > 0
     mc.close(); env.close()
     return moves_done
 
@@ -98,6 +100,22 @@ def test_selfplay_full_games_64_sims(api):
 def test_play_mode_turn_start_trim_and_thread_rounding(api):
     # MCTS_SIMULATIONS = 33 with THREADS_PER_MCTS = 2 -> 32 simulations (alphazero_mcts.cpp:265)
     assert run_lockstep(api, n=6, first=77, sims=33, T=2, play_mode=True, max_moves=150) > 500
+
+
+@pytest.mark.parametrize("sims,T,K,play_mode,evaluator", [(16, 2, 2, True, "pseudo"), (48, 1, 4, False, "pseudo"), (32, 1, 8, False, "uniform"),
+                                                          (64, 1, 16, False, "pseudo")])
+def test_virtual_loss_concurrent_descents(api, sims, T, K, play_mode, evaluator):
+    """az_rules.concurrent_descents = K: K descents per tree per leaf batch with the reference's active_N rule
+    (getNextBestMoveAndSetVisited, alphazero_mcts.cpp:91-111) == the oracle's lockstep schedule, which
+    tests/test_oracle_vs_ref.py pins to the reference's own search threads taking turns"""
+    assert run_lockstep(api, n=8, first=4100, sims=sims, T=T, play_mode=play_mode, max_moves=140, evaluator=evaluator, K=K) > 700
+
+
+def test_concurrent_descents_must_divide_the_simulation_count(api):
+    env = api.Env(2, rules=api.default_rules(mcts_simulations=16, threads_per_mcts=1, concurrent_descents=3))
+    with pytest.raises(api.AzError):
+        api.Mcts(env, evaluator=api.EVAL_PSEUDO)
+    env.close()
 
 
 def test_uniform_evaluator(api):
@@ -131,7 +149,8 @@ def test_reference_golden_search_traces(api, golden_dir, name):
     mc.close(); env.close()
 
 
-def test_search_with_network_matches_oracle_given_same_outputs(api):
+@pytest.mark.parametrize("K", [1, 3])
+def test_search_with_network_matches_oracle_given_same_outputs(api, K):
     """evaluator = the fp32 network.  The oracle search calls the SAME network (batch of one, the
     kernels are batch-invariant) for its leaf evaluations, so both sides see identical outputs."""
     net = api.Net(blocks=2, seed=1234)
@@ -147,7 +166,7 @@ def test_search_with_network_matches_oracle_given_same_outputs(api):
         value[0] = float(v[0])
 
     assert run_lockstep(api, n=5, first=4242, sims=12, T=1, play_mode=False, max_moves=70, evaluator="nn", net=net,
-                        oracle_eval=evaluator) > 300
+                        oracle_eval=evaluator, K=K) > 300
     net.close()
 
 
