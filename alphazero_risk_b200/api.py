@@ -83,6 +83,24 @@ def lib():
         L.az_nn_finalize.argtypes = [vp]
         L.az_nn_forward.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp]
         L.az_nn_forward_dev.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp]
+        L.az_nn_train_step.argtypes = [vp, vp, vp, vp, C.c_int, f32, f32, vp]
+        L.az_nn_train.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, vp, vp, vp]
+        L.az_nn_train_get_grad.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+        L.az_nn_optimizer_get.argtypes = [vp, C.c_char_p, C.c_int, vp, C.c_size_t]
+        L.az_nn_optimizer_powers.argtypes = [vp, f32, f32, u64]
+        L.az_nn_save_checkpoint.argtypes = [vp, C.c_char_p]
+        L.az_nn_load_checkpoint.argtypes = [vp, C.c_char_p]
+        L.az_ckpt_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.az_ckpt_close.argtypes = [vp]
+        L.az_ckpt_num_tensors.argtypes = [vp]
+        L.az_ckpt_tensor_info.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64 * 8),
+                                          C.POINTER(C.c_size_t)]
+        L.az_ckpt_find.argtypes = [vp, C.c_char_p]
+        L.az_ckpt_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+        L.az_ckpt_write.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_int64)),
+                                    C.POINTER(vp)]
+        L.az_crc32c.argtypes = [vp, C.c_size_t]
+        L.az_crc32c.restype = C.c_uint32
         L.az_mcts_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
         L.az_mcts_destroy.argtypes = [vp]
         L.az_mcts_simulations.argtypes = [vp]
@@ -279,6 +297,93 @@ class Net:
 
     def forward_dev(self, d_x, n, d_policy, d_value, precision=FP32, stream=None):
         check(self.L.az_nn_forward_dev(self.h, d_x, int(n), d_policy, d_value, precision, stream))
+
+    # ---- training step and checkpoints (AlphaZeroNN::train / saveCheckpoint / loadCheckpoint)
+    def train_step(self, x, target_policy, target_value, stream=None):
+        """one optimizer step on a batch; returns (policy loss, value loss)"""
+        a = np.ascontiguousarray(x, np.float32).reshape(-1, INPUT_FLOATS)
+        tp = np.ascontiguousarray(target_policy, np.float32).reshape(-1, MOVES)
+        tv = np.ascontiguousarray(target_value, np.float32).reshape(-1)
+        assert tp.shape[0] == a.shape[0] == tv.shape[0]
+        lp, lv = C.c_float(), C.c_float()
+        check(self.L.az_nn_train_step(self.h, _ptr(a), _ptr(tp), _ptr(tv), a.shape[0], C.byref(lp), C.byref(lv), stream))
+        return float(lp.value), float(lv.value)
+
+    def train(self, records, epochs, batch_size=512, seed=0, stream=None):
+        """AlphaZeroNN::train on packed 265-byte sample records; returns per-epoch (policy loss, value loss) means"""
+        r = np.ascontiguousarray(records, np.uint8).reshape(-1, SAMPLE_BYTES)
+        lp, lv = np.zeros(epochs, np.float32), np.zeros(epochs, np.float32)
+        check(self.L.az_nn_train(self.h, _ptr(r), r.shape[0], int(epochs), int(batch_size), int(seed), _ptr(lp), _ptr(lv), stream))
+        return lp, lv
+
+    def grad(self, name, shape):
+        a = np.empty(shape, np.float32)
+        check(self.L.az_nn_train_get_grad(self.h, name.encode(), _ptr(a), a.size))
+        return a
+
+    def optimizer_slot(self, name, which, shape):
+        a = np.empty(shape, np.float32)
+        check(self.L.az_nn_optimizer_get(self.h, name.encode(), int(which), _ptr(a), a.size))
+        return a
+
+    def optimizer_powers(self):
+        b1, b2, st = C.c_float(), C.c_float(), C.c_uint64()
+        check(self.L.az_nn_optimizer_powers(self.h, C.byref(b1), C.byref(b2), C.byref(st)))
+        return float(b1.value), float(b2.value), int(st.value)
+
+    def save_checkpoint(self, prefix):
+        check(self.L.az_nn_save_checkpoint(self.h, str(prefix).encode()))
+
+    def load_checkpoint(self, prefix):
+        check(self.L.az_nn_load_checkpoint(self.h, str(prefix).encode()))
+
+
+class Checkpoint:
+    """a TensorFlow V2 checkpoint bundle on the host (az_ckpt_*): <prefix>.index + <prefix>.data-00000-of-00001"""
+
+    def __init__(self, prefix):
+        self.L = lib()
+        h = C.c_void_p()
+        check(self.L.az_ckpt_open(str(prefix).encode(), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.az_ckpt_close(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def tensors(self):
+        """[(name, dtype, shape, bytes)] in table order"""
+        out = []
+        for i in range(self.L.az_ckpt_num_tensors(self.h)):
+            name, dt, rank, shp, nb = C.c_char_p(), C.c_int(), C.c_int(), (C.c_int64 * 8)(), C.c_size_t()
+            check(self.L.az_ckpt_tensor_info(self.h, i, C.byref(name), C.byref(dt), C.byref(rank), C.byref(shp), C.byref(nb)))
+            out.append((name.value.decode(), int(dt.value), tuple(int(shp[k]) for k in range(rank.value)), int(nb.value)))
+        return out
+
+    def read(self, name):
+        i = self.L.az_ckpt_find(self.h, name.encode())
+        if i < 0:
+            raise KeyError(name)
+        _, dt, shape, nb = self.tensors()[i]
+        a = np.empty(nb // 4, np.float32)
+        check(self.L.az_ckpt_read(self.h, name.encode(), _ptr(a), nb))
+        return a.reshape(shape)
+
+    @staticmethod
+    def write(prefix, tensors):
+        """tensors: {name: float32 array}"""
+        L = lib()
+        names = list(tensors)
+        arrs = [np.asarray(tensors[n], dtype=np.float32, order="C") for n in names]     # keeps scalars 0-d
+        shapes = [(C.c_int64 * max(1, a.ndim))(*a.shape) for a in arrs]
+        c_names = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        c_ranks = (C.c_int * len(names))(*[a.ndim for a in arrs])
+        c_shapes = (C.POINTER(C.c_int64) * len(names))(*[C.cast(s, C.POINTER(C.c_int64)) for s in shapes])
+        c_data = (C.c_void_p * len(names))(*[a.ctypes.data for a in arrs])
+        check(L.az_ckpt_write(str(prefix).encode(), len(names), c_names, c_ranks, c_shapes, c_data))
 
 
 EVAL_NN, EVAL_PSEUDO, EVAL_UNIFORM = 0, 1, 2

@@ -23,6 +23,8 @@ UNITS = {
     "az_mcts.cu": ["-fmad=false"],
     "az_nn.cu": [],
     "az_nn_tc.cu": [],
+    "az_nn_train.cu": ["-fmad=false"],   # training step: plain fp32, same roundings whatever the compiler would contract
+    "az_ckpt.cpp": [],       # host only: TensorFlow V2 checkpoint bundles
 }
 
 
@@ -43,7 +45,7 @@ def build(force=False, verbose=False):
         src = os.path.join(CSRC, unit)
         if not os.path.exists(src):
             continue
-        obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
+        obj = os.path.join(OBJ, os.path.splitext(unit)[0] + ".o")
         objs.append(obj)
         if force or _newer([src] + headers, obj):
             cmd = [nvcc] + ARCH + COMMON + extra + os.environ.get("AZ_B200_NVCC_FLAGS", "").split() + \

@@ -282,6 +282,7 @@ extern "C" int az_nn_destroy(az_nn* nn)
     cudaFree(nn->d_blob); cudaFree(nn->d_act[0]); cudaFree(nn->d_act[1]); cudaFree(nn->d_act[2]);
     cudaFree(nn->d_x); cudaFree(nn->d_policy); cudaFree(nn->d_value);
     az_nn_tc_release(nn);
+    az_nn_train_release(nn);
     delete nn;
     return AZ_OK;
 }
@@ -308,6 +309,7 @@ extern "C" int az_nn_load_weights(az_nn* nn, const char* name, const float* h_pt
     if (it == nn->index.end()) { az_set_error("unknown variable '%s'", name); return AZ_ERR_INVALID_ARG; }
     const AzVar& v = nn->vars[it->second];
     if (v.count != count) { az_set_error("variable '%s' has %zu elements, got %zu", name, v.count, count); return AZ_ERR_INVALID_ARG; }
+    { AzDeviceGuard guard(nn->device); int rc = az_nn_sync_host(nn); if (rc) return rc; }
     memcpy(nn->blob.data() + v.offset, h_ptr, sizeof(float) * count);
     nn->finalized = false;
     return AZ_OK;
@@ -316,6 +318,7 @@ extern "C" int az_nn_load_weights(az_nn* nn, const char* name, const float* h_pt
 extern "C" int az_nn_get_weights(const az_nn* nn, const char* name, float* h_ptr, size_t count)
 {
     AZ_REQUIRE(nn && name && h_ptr, "NULL argument");
+    { AzDeviceGuard guard(nn->device); int rc = az_nn_sync_host(const_cast<az_nn*>(nn)); if (rc) return rc; }
     auto it = nn->index.find(name);
     if (it == nn->index.end()) { az_set_error("unknown variable '%s'", name); return AZ_ERR_INVALID_ARG; }
     const AzVar& v = nn->vars[it->second];
@@ -327,6 +330,7 @@ extern "C" int az_nn_get_weights(const az_nn* nn, const char* name, float* h_ptr
 extern "C" int az_nn_export_blob(const az_nn* nn, float* h_out, size_t count)
 {
     AZ_REQUIRE(nn && h_out && count == nn->blob.size(), "blob size mismatch");
+    { AzDeviceGuard guard(nn->device); int rc = az_nn_sync_host(const_cast<az_nn*>(nn)); if (rc) return rc; }
     memcpy(h_out, nn->blob.data(), sizeof(float) * count);
     return AZ_OK;
 }
@@ -334,7 +338,7 @@ extern "C" int az_nn_import_blob(az_nn* nn, const float* h_in, size_t count)
 {
     AZ_REQUIRE(nn && h_in && count == nn->blob.size(), "blob size mismatch");
     memcpy(nn->blob.data(), h_in, sizeof(float) * count);
-    nn->finalized = false;
+    nn->finalized = false; nn->host_stale = false;
     return AZ_OK;
 }
 
@@ -343,6 +347,7 @@ extern "C" int az_nn_import_blob(az_nn* nn, const float* h_in, size_t count)
 extern "C" int az_nn_init_random(az_nn* nn, uint64_t seed)
 {
     AZ_REQUIRE(nn != nullptr, "nn is NULL");
+    nn->host_stale = false;
     uint64_t s = seed;
     for (const AzVar& v : nn->vars) {
         float* p = nn->blob.data() + v.offset;
@@ -359,8 +364,18 @@ extern "C" int az_nn_init_random(az_nn* nn, uint64_t seed)
     return AZ_OK;
 }
 
+// weights a training step has moved on the device -> nn->blob (the packed bf16 tiles are then rebuilt by the next finalize)
+int az_nn_sync_host(az_nn* nn)
+{
+    if (!nn->host_stale) return AZ_OK;
+    AZ_CUDA(cudaMemcpy(nn->blob.data(), nn->d_blob, sizeof(float) * nn->blob.size(), cudaMemcpyDeviceToHost));
+    nn->host_stale = false; nn->finalized = false;
+    return AZ_OK;
+}
+
 static int finalize(az_nn* nn)
 {
+    if (nn->host_stale) { int rc = az_nn_sync_host(nn); if (rc) return rc; }
     if (nn->finalized) return AZ_OK;
     int rc = upload(&nn->d_blob, nn->blob.data(), nn->blob.size());
     if (rc) return rc;

@@ -25,24 +25,29 @@ struct AzHeadParams {
 };
 
 struct AzTcState;   // az_nn_tc.cu
+struct AzTrainState; // az_nn_train.cu
 
 struct az_nn {
     int blocks = 5, device = 0;
     std::vector<AzVar> vars;
     std::map<std::string, int> index;
     std::vector<float> blob;          // every variable, fp32, TF layouts (HWIO kernels), inventory order
-    bool finalized = false;
+    bool finalized = false;           // d_blob == blob and the packed bf16 tiles are current
+    bool host_stale = false;          // training has moved d_blob ahead of blob (synced back by az_nn_sync_host)
     float* d_blob = nullptr;          // device copy of blob
     int cap = 0;                      // positions the work buffers are sized for
     float* d_act[3] = { nullptr, nullptr, nullptr };   // fp32 activations [cap][42][256]
     float* d_x = nullptr; float* d_policy = nullptr; float* d_value = nullptr;   // staging for host-buffer calls
     AzTcState* tc = nullptr;
+    AzTrainState* train = nullptr;    // optimizer state + training work buffers, created on first use
 };
 
 const float* az_nn_host_var(const az_nn* nn, const std::string& name);
 const float* az_nn_dev_var(const az_nn* nn, const std::string& name);
 AzHeadParams az_nn_head_params(const az_nn* nn);
 int az_nn_reserve(az_nn* nn, int n);
+int az_nn_sync_host(az_nn* nn);            // copies trained weights back into nn->blob when they are ahead
+void az_nn_train_release(az_nn* nn);        // az_nn_train.cu
 
 // bf16 tensor-core path (az_nn_tc.cu)
 int az_nn_tc_prepare(az_nn* nn);            // fold BN, pack bf16 weight tiles; called by finalize

@@ -215,7 +215,8 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
     n, sims, blocks = args.sp_games, args.sp_sims, args.blocks
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
-    rules = api.default_rules(mcts_simulations=sims, threads_per_mcts=1)
+    K = max(1, args.sp_descents)
+    rules = api.default_rules(mcts_simulations=sims, threads_per_mcts=1, concurrent_descents=K)
     env = api.Env(n, rules=rules, device=local, first_game_id=rank * n)
     env.reset(SEED, stream=sptr)
     net = api.Net(blocks=blocks, device=local)
@@ -266,13 +267,16 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
     if rank != 0:
         return None
     _, tf_peak, src = measured_peaks()
-    nn_launch_positions = n * (sims + 1) * moves_per_step * steps          # positions pushed through the tower per rank
+    nn_launch_positions = n * K * (sims // K + 1) * moves_per_step * steps    # positions pushed through the tower per rank (every descent slot)
     achieved_tf = nn_launch_positions * nn_flops_per_position(blocks) / (dev_ms * 1e-3) / 1e12
     return dict(metric="mcts_sims_per_sec", value=tot_sims / (dev_ms * 1e-3), unit="sims/s", ms_per_step=dev_ms / steps, steps=steps,
                 nn_evals_per_sec=tot_evals / (dev_ms * 1e-3), selfplay_env_steps_per_sec=tot_steps / (dev_ms * 1e-3),
-                config={"workload": "configs[2]: batched self-play, %d games x %d MCTS sims/move per GPU, T=1 semantics (one leaf per game "
-                                    "per batch), %d-block graph, random-init weights (seed 1234), bf16 tcgen05 forward, %d moves per step"
-                                    % (n, sims, blocks, moves_per_step), "games_per_gpu": n, "sims_per_move": sims, "blocks": blocks},
+                config={"workload": "configs[2]: batched self-play, %d games x %d MCTS sims/move per GPU, %s, "
+                                    "%d-block graph, random-init weights (seed 1234), bf16 tcgen05 forward, %d moves per step"
+                                    % (n, sims, "T=1 semantics (one leaf per game per batch)" if K == 1 else
+                                       "%d concurrent descents per tree with the active_N rule (leaf batch = %d)" % (K, n * K),
+                                       blocks, moves_per_step),
+                            "games_per_gpu": n, "sims_per_move": sims, "blocks": blocks, "concurrent_descents": K},
                 roofline={"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
                           "traffic": ncu_traffic("k_nn_conv_tc3"), "peak_source": src + " (sustained cuBLAS bf16)",
                           "executed_frac": achieved_tf * 49.0 / 42.0 / tf_peak,
@@ -283,18 +287,19 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
                 clocks=sp_clocks,
                 e2e={"value": n * sims * e2e_moves * world / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": n * 160,
                      "d2h_bytes_per_step": n * (43 * 8 + 2 + 160), "steps": e2e_moves},
-                gpu_launches=steps * moves_per_step * (2 + (sims + 1) * (2 + 1 + 2 * blocks + 1 + 1)),
+                gpu_launches=steps * moves_per_step * (2 + (sims // K + 1) * (2 + 1 + 2 * blocks + 1 + 1)),
                 dtype="bf16 tower / fp32 tree", results={"games_finished": tot_games, "table_errors": errors})
 
 
 def run_play(args, api, torch, rank, local):
     """BASELINE configs[0] on the device: `-m play --mcts=16 --cg=1000` — AlphaZero (random-init 5-block net, bf16 tcgen05 forward,
-    16 simulations per move = MCTS_SIMULATIONS 16 with the default 2 search threads) against the scripted opponent, mirror pairs.
+    16 simulations per move = MCTS_SIMULATIONS 16 with the default 2 search threads, run as 2 concurrent descents per tree with the
+    active_N rule) against the scripted opponent, mirror pairs.
     The reference runs 32 concurrent game threads; here every pair gets its own slot so the whole match is one lockstep batch."""
     games = args.play_games - args.play_games % 2
     slots = max(1, games // 2)
     stream = torch.cuda.current_stream(); sptr = stream.cuda_stream
-    rules = api.default_rules(mcts_simulations=16, threads_per_mcts=2)
+    rules = api.default_rules(mcts_simulations=16, threads_per_mcts=2, concurrent_descents=2)
     env = api.Env(slots, rules=rules, device=local, first_game_id=rank * slots)
     net = api.Net(blocks=args.blocks, device=local, seed=1234)
     mc = api.Mcts(env, net=net, evaluator=api.EVAL_NN, precision=api.BF16)
@@ -312,7 +317,8 @@ def run_play(args, api, torch, rank, local):
                 results={"count": r["count"], "draw": r["draw"], "win_az_script": r["win"], "win_and_started": r["win_and_started"],
                          "errors": r["errors"]},
                 config={"workload": "configs[0]: -m play --mcts=16 --cg=%d, AlphaZero (random-init %d-block net, bf16) vs ScriptPlayer, both "
-                                    "on the device, %d lockstep slots x 1 mirror pair" % (games, args.blocks, slots)})
+                                    "on the device, %d lockstep slots x 1 mirror pair, THREADS_PER_MCTS = 2 as 2 concurrent descents per tree"
+                                    % (games, args.blocks, slots)})
 
 
 def run_ours(args):
@@ -351,6 +357,13 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        # the timed region below lasts tens of milliseconds, nvidia-smi samples every 100 ms: run the same launches (untimed) until the
+        # sampler has seen the GPU under this load, so the clocks line describes the state the timed launches run in
+        t_lead = time.perf_counter()
+        while len(sampler.lines) < 3 and time.perf_counter() - t_lead < 3.0:
+            env.rollout(S, stream=sptr)
+            torch.cuda.synchronize()
+        env.counters(reset=True, stream=sptr)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall0 = time.perf_counter()
@@ -451,6 +464,7 @@ def main():
     ap.add_argument("--sp-sims", type=int, default=64)
     ap.add_argument("--sp-moves", type=int, default=2, help="self-play moves per timed step")
     ap.add_argument("--sp-steps", type=int, default=4, help="max timed self-play steps")
+    ap.add_argument("--sp-descents", type=int, default=1, help="az_rules.concurrent_descents for the self-play measurement")
     ap.add_argument("--blocks", type=int, default=5)
     ap.add_argument("--play-games", type=int, default=1000, help="configs[0] match size (--cg); 0 skips it")
     args = ap.parse_args()

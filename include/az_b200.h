@@ -173,6 +173,40 @@ AZ_API int az_nn_finalize(az_nn* nn);
 AZ_API int az_nn_forward(az_nn* nn, const float* h_x, int n, float* h_policy, float* h_value, int precision, void* stream);
 AZ_API int az_nn_forward_dev(az_nn* nn, const float* d_x, int n, float* d_policy, float* d_value, int precision, void* stream);
 
+/* ---------------------------------------------------------------- training step and TensorFlow checkpoints */
+/* One run of the graph's "optimize" op (AlphaZeroNN::train inner loop, neural_network/alphazero_nn.cpp:389-390;
+   python/src/build_graph.py:92-106): training-mode forward (batch statistics, moving averages updated with momentum 0.99), softmax
+   cross-entropy + mean squared error + 0.001 * L2 of the kernels, Adam(0.001, 0.9, 0.999, 1e-8).  x [n][7][6][13], target policy
+   [n][43], target value [n]; returns the batch's two losses (TF_OUTPUT_LOSS_POLICY / _VALUE).  fp32 on CUDA cores, deterministic. */
+AZ_API int az_nn_train_step(az_nn* nn, const float* h_x, const float* h_target_policy, const float* h_target_value, int n,
+                            float* loss_policy, float* loss_value, void* stream);
+/* AlphaZeroNN::train (alphazero_nn.cpp:351-410) on packed sample records (az_selfplay_samples / the reference's sample files):
+   `epochs` shuffled passes, whole batches of batch_size (SETTINGS.BATCH_SIZE = 512) only; per-epoch mean losses (may be NULL) */
+AZ_API int az_nn_train(az_nn* nn, const uint8_t* h_records, size_t n_records, int epochs, int batch_size, uint64_t seed,
+                       float* h_epoch_loss_policy, float* h_epoch_loss_value, void* stream);
+/* introspection for the parity tests: gradient of the total loss from the last step; Adam slots (which: 0 = m, 1 = v); beta powers */
+AZ_API int az_nn_train_get_grad(az_nn* nn, const char* name, float* h_out, size_t count);
+AZ_API int az_nn_optimizer_get(az_nn* nn, const char* name, int which, float* h_out, size_t count);
+AZ_API int az_nn_optimizer_powers(az_nn* nn, float* beta1_power, float* beta2_power, uint64_t* steps);
+/* AlphaZeroNN::saveCheckpoint / loadCheckpoint (alphazero_nn.cpp:189-214): TensorFlow V2 checkpoint bundle <prefix>.index +
+   <prefix>.data-00000-of-00001 holding the tensors of the graph's Saver (variables, moving statistics, "<var>/optimize",
+   "<var>/optimize_1", beta1_power, beta2_power) */
+AZ_API int az_nn_save_checkpoint(az_nn* nn, const char* prefix);
+AZ_API int az_nn_load_checkpoint(az_nn* nn, const char* prefix);
+
+/* the bundle format itself (host only, no device needed): tensorflow/core/util/tensor_bundle */
+typedef struct az_ckpt az_ckpt;
+AZ_API int az_ckpt_open(const char* prefix, az_ckpt** out);
+AZ_API int az_ckpt_close(az_ckpt* ckpt);
+AZ_API int az_ckpt_num_tensors(const az_ckpt* ckpt);
+/* i-th tensor in table (= ascending name) order; dtype is TensorFlow's DataType (DT_FLOAT = 1); shape8: up to 8 dims */
+AZ_API int az_ckpt_tensor_info(const az_ckpt* ckpt, int i, const char** name, int* dtype, int* rank, int64_t* shape8, size_t* bytes);
+AZ_API int az_ckpt_find(const az_ckpt* ckpt, const char* name);                 /* index or -1 */
+AZ_API int az_ckpt_read(az_ckpt* ckpt, const char* name, void* h_out, size_t bytes);   /* verifies the entry's CRC32C */
+AZ_API int az_ckpt_write(const char* prefix, int n, const char* const* names, const int* ranks, const int64_t* const* shapes,
+                         const float* const* data);                               /* float32 tensors, one shard */
+AZ_API uint32_t az_crc32c(const void* data, size_t n);
+
 /* ---------------------------------------------------------------- MCTS (AlphaZeroMCTS) and self-play */
 typedef struct az_mcts az_mcts;
 #define AZ_EVAL_NN 0        /* leaf evaluation by the network (az_nn) */

@@ -69,3 +69,99 @@ def forward(weights, x, blocks, dtype=torch.float32):
 def flops_per_position(blocks):
     """SURVEY.md §8d conventional count (padded taps included)"""
     return 2 * 42 * (9 * 13 * 256 + 2 * blocks * 9 * 256 * 256 + 256 * 2 + 256 * 1) + 2 * (84 * 43 + 42 * 256 + 256)
+
+
+# --------------------------------------------------------------------------- training step (SURVEY §8f N4)
+# What session->Run(TF_OP_OPTIMIZE) does for one batch (neural_network/alphazero_nn.cpp:389-390) according to
+# python/src/build_graph.py:92-106 and the constants recorded in the shipped GraphDef (python/model/model_txt_V2_5.pb):
+#   * every BatchNorm runs FusedBatchNormV3 with is_training = true: normalise with the BATCH mean and the biased batch
+#     variance, epsilon 0.001; the moving statistics move towards the batch mean and the UNBIASED batch variance
+#     (N / (N - 1)) with momentum 0.99 (conv_bn_cond_1_true: 0.9900000095, AssignMovingAvg: moving -= (moving - batch) * 0.01);
+#     the stem's BN is the NCHW variant over the board-row axis (conv_bn_cond_true: data_format "NCHW")
+#   * loss_pi = tf.losses.softmax_cross_entropy (mean over the batch), loss_v = tf.losses.mean_squared_error (mean),
+#     l2 = 0.001 * sum(w^2) over the 16 kernels that carry a kernel_regularizer (convs and dense kernels; no bias, no BN)
+#   * AdamOptimizer(0.001, beta1 0.9, beta2 0.999, epsilon 1e-8; optimize/{learning_rate,beta1,beta2,epsilon}):
+#     lr_t = lr * sqrt(1 - beta2_power) / (1 - beta1_power); m += (g - m)(1 - beta1); v += (g^2 - v)(1 - beta2);
+#     var -= lr_t * m / (sqrt(v) + eps); then beta1_power *= beta1, beta2_power *= beta2 (initially beta1, beta2)
+# PARITY UNPINNED at the TensorFlow boundary, like forward().
+BN_MOMENTUM = 0.99
+L2_C = 0.001
+ADAM = dict(lr=0.001, beta1=0.9, beta2=0.999, eps=1e-8)
+
+
+def trainable_names(blocks):
+    return [n for n in variable_names(blocks) if not n.endswith(("moving_mean", "moving_variance"))]
+
+
+def _bn_train(x, w, prefix, axis, batch_stats):
+    g, b = w[prefix + "/gamma"], w[prefix + "/beta"]
+    dims = [d for d in range(4) if d != axis]
+    mean = x.mean(dim=dims)
+    var = ((x - mean.reshape([-1 if d == axis else 1 for d in range(4)])) ** 2).mean(dim=dims)
+    n = x.numel() // x.shape[axis]
+    batch_stats[prefix] = (mean.detach(), (var * n / (n - 1)).detach())
+    shape = [1, 1, 1, 1]
+    shape[axis] = -1
+    return (x - mean.reshape(shape)) * torch.rsqrt(var.reshape(shape) + EPS) * g.reshape(shape) + b.reshape(shape)
+
+
+def train_losses(w, x, target_policy, target_value, blocks, batch_stats):
+    """training-mode forward; w: dict of torch tensors (leaf tensors requiring grad for the trainable ones)"""
+    t = x.reshape(-1, 7, 6, 13).permute(0, 3, 1, 2)
+    t = torch.relu(_bn_train(_conv(t, w["conv/kernel"]), w, "conv_bn", 2, batch_stats))
+    for i in range(blocks):
+        sfx = "%d%s" % (i, chr(ord("a") + i))
+        r = torch.relu(_bn_train(_conv(t, w["res%s_branch2a/kernel" % sfx]), w, "bn%s_branch2a" % sfx, 1, batch_stats))
+        r = _bn_train(_conv(r, w["res%s_branch2b/kernel" % sfx]), w, "bn%s_branch2b" % sfx, 1, batch_stats)
+        t = torch.relu(r + t)
+    p = torch.relu(_bn_train(_conv(t, w["pi/kernel"]), w, "bn_pi", 1, batch_stats))
+    logits = p.permute(0, 2, 3, 1).reshape(-1, 84) @ w["dense/kernel"] + w["dense/bias"]
+    loss_pi = -(target_policy * torch.log_softmax(logits, dim=1)).sum(dim=1).mean()
+    v = torch.relu(_bn_train(_conv(t, w["v/kernel"]), w, "bn_v", 1, batch_stats))
+    v = torch.relu(v.permute(0, 2, 3, 1).reshape(-1, 42) @ w["dense_1/kernel"] + w["dense_1/bias"])
+    v = torch.tanh(v @ w["dense_2/kernel"] + w["dense_2/bias"]).reshape(-1)
+    loss_v = ((v - target_value) ** 2).mean()
+    l2 = sum((w[n] ** 2).sum() for n in w if n.endswith("/kernel")) * L2_C
+    return loss_pi, loss_v, l2
+
+
+class Trainer:
+    """the graph's variables + Adam slots; step() = one TF_OP_OPTIMIZE run"""
+
+    def __init__(self, weights, blocks, dtype=torch.float64):
+        self.blocks, self.dtype = blocks, dtype
+        self.w = {k: torch.as_tensor(np.asarray(v), dtype=dtype).clone() for k, v in weights.items()}
+        self.m = {k: torch.zeros_like(self.w[k]) for k in trainable_names(blocks)}
+        self.v = {k: torch.zeros_like(self.w[k]) for k in trainable_names(blocks)}
+        self.beta1_power, self.beta2_power = ADAM["beta1"], ADAM["beta2"]
+        self.grads = {}
+
+    def step(self, x, target_policy, target_value):
+        names = trainable_names(self.blocks)
+        for k in names:
+            self.w[k].requires_grad_(True)
+            self.w[k].grad = None
+        stats = {}
+        x = torch.as_tensor(np.asarray(x), dtype=self.dtype)
+        tp = torch.as_tensor(np.asarray(target_policy), dtype=self.dtype).reshape(-1, 43)
+        tv = torch.as_tensor(np.asarray(target_value), dtype=self.dtype).reshape(-1)
+        loss_pi, loss_v, l2 = train_losses(self.w, x, tp, tv, self.blocks, stats)
+        (loss_pi + loss_v + l2).backward()
+        lr_t = ADAM["lr"] * np.sqrt(1.0 - self.beta2_power) / (1.0 - self.beta1_power)
+        with torch.no_grad():
+            for k in names:
+                g = self.w[k].grad
+                self.grads[k] = g.detach().clone()
+                self.m[k] += (g - self.m[k]) * (1.0 - ADAM["beta1"])
+                self.v[k] += (g * g - self.v[k]) * (1.0 - ADAM["beta2"])
+                self.w[k] -= lr_t * self.m[k] / (torch.sqrt(self.v[k]) + ADAM["eps"])
+                self.w[k].requires_grad_(False)
+            for prefix, (mean, var_unbiased) in stats.items():
+                self.w[prefix + "/moving_mean"] -= (self.w[prefix + "/moving_mean"] - mean) * (1.0 - BN_MOMENTUM)
+                self.w[prefix + "/moving_variance"] -= (self.w[prefix + "/moving_variance"] - var_unbiased) * (1.0 - BN_MOMENTUM)
+        self.beta1_power *= ADAM["beta1"]
+        self.beta2_power *= ADAM["beta2"]
+        return float(loss_pi.detach()), float(loss_v.detach())
+
+    def weights(self):
+        return {k: v.detach().numpy().astype(np.float32) for k, v in self.w.items()}

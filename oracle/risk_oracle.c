@@ -1129,3 +1129,16 @@ void ro_bench_env(uint64_t n_steps, uint64_t seed, ro_bench_out* out)
     out->steps = steps; out->games = games;
     out->seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------ CRC32C for oracle/ckpt_oracle.py (checkpoint bundles)
+   bit-serial restatement (reflected Castagnoli polynomial 0x82f63b78), 8 bits per byte, no table: independent of the product's
+   table-driven az_crc32c */
+uint32_t ro_crc32c(const uint8_t* p, uint64_t n, uint32_t crc)
+{
+    uint32_t c = crc ^ 0xffffffffu;
+    for (uint64_t i = 0; i < n; ++i) {
+        c ^= p[i];
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0x82f63b78u & (0u - (c & 1u)));
+    }
+    return c ^ 0xffffffffu;
+}

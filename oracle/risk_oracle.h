@@ -159,6 +159,8 @@ int ro_pick_move(const float pi[RO_MOVES], int sample, uint64_t seed, uint32_t g
 typedef struct ro_bench_out { uint64_t steps, games, sims, evals, moves; double seconds; } ro_bench_out;
 void ro_bench_env(uint64_t n_steps, uint64_t seed, ro_bench_out* out);
 
+uint32_t ro_crc32c(const uint8_t* p, uint64_t n, uint32_t crc);                  /* CRC32C, for oracle/ckpt_oracle.py */
+
 #ifdef __cplusplus
 }
 #endif
