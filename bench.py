@@ -321,6 +321,34 @@ def run_play(args, api, torch, rank, local):
                                     % (games, args.blocks, slots)})
 
 
+def run_train(args, api, torch, local):
+    """SURVEY §8f N4: one optimizer step (AlphaZeroNN::train inner loop) on a batch of SETTINGS.BATCH_SIZE = 512 synthetic samples"""
+    import numpy as np
+    n = args.train_batch
+    rng = np.random.default_rng(5)
+    net = api.Net(blocks=args.blocks, device=local, seed=1234)
+    x = rng.random((n, 7, 6, 13), dtype=np.float32)
+    tp = rng.random((n, 43)).astype(np.float32); tp /= tp.sum(1, keepdims=True)
+    tv = rng.choice([-1.0, 0.0, 1.0], n).astype(np.float32)
+    stream = torch.cuda.current_stream(); sptr = stream.cuda_stream
+    for _ in range(2):
+        net.train_step(x, tp, tv, stream=sptr)
+    torch.cuda.synchronize()
+    steps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        loss = net.train_step(x, tp, tv, stream=sptr)          # host batch in, two losses out, every step
+    e1.record(stream); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    net.close()
+    flops = 3.0 * nn_flops_per_position(args.blocks) * n       # forward + data gradient + weight gradient
+    return dict(metric="train_samples_per_sec", value=n / (ms * 1e-3), unit="samples/s", ms_per_step=ms, batch=n, blocks=args.blocks,
+                achieved_tflops_fp32=flops / (ms * 1e-3) / 1e12, last_losses=list(loss),
+                config={"workload": "one az_nn_train_step per step: batch %d, %d-block graph, fp32 CUDA-core kernels (not on the self-play "
+                                    "hot path), host batch copied in and losses copied out inside the timed region" % (n, args.blocks)})
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -413,6 +441,10 @@ def run_ours(args):
     if args.play_games >= 2 and rank == 0 and world == 1:
         play_line = run_play(args, api, torch, rank, local)
 
+    train_line = None
+    if args.train_batch >= 2 and rank == 0 and world == 1:
+        train_line = run_train(args, api, torch, local)
+
     if rank == 0:
         hbm_peak, _, src = measured_peaks()
         total_steps = n * S * args.steps * world
@@ -439,6 +471,8 @@ def run_ours(args):
             line["gpu_launches"] += mcts_line["gpu_launches"]
         if play_line is not None:
             line["play"] = play_line
+        if train_line is not None:
+            line["train"] = train_line
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_env_baseline(12.0)
             line["cpu_baseline"] = cb
@@ -466,6 +500,7 @@ def main():
     ap.add_argument("--sp-steps", type=int, default=4, help="max timed self-play steps")
     ap.add_argument("--sp-descents", type=int, default=1, help="az_rules.concurrent_descents for the self-play measurement")
     ap.add_argument("--blocks", type=int, default=5)
+    ap.add_argument("--train-batch", type=int, default=512, help="training-step measurement batch (SETTINGS.BATCH_SIZE); 0 skips it")
     ap.add_argument("--play-games", type=int, default=1000, help="configs[0] match size (--cg); 0 skips it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
