@@ -11,10 +11,12 @@
 //                        alphazero_gpu_cluster.cpp:13-71; queue capacity max(1, registeredThreads / 2),
 //                        alphazero_nn.cpp:291-309; the call blocks while the queue is full
 //   registerThread / unregisterThread   batch-size hint, as above
-//   loadCheckpoint(path) missing file => random init (the graph's "init" op) + save, alphazero_nn.cpp:189-204.
-//                        File format here: the flat fp32 weight blob of az_nn_export_blob (TF checkpoint import
-//                        is SURVEY §8f N4, not built)
-//   train(...)           throws std::logic_error (training is out of scope)
+//   loadCheckpoint(path) `path` is a TensorFlow checkpoint prefix: restores <path>.index + <path>.data-00000-of-00001 when the
+//                        index exists, else random init (the graph's "init" op) + saveCheckpoint, alphazero_nn.cpp:189-204
+//   saveCheckpoint(path) creates the directory and writes the bundle the graph's Saver writes (variables, moving statistics,
+//                        Adam slots, beta powers), alphazero_nn.cpp:207-214
+//   train(data, epochs)  AlphaZeroNN::train, alphazero_nn.cpp:351-410: `epochs` shuffled passes in whole batches of
+//                        SETTINGS.BATCH_SIZE (512; setBatchSize) through az_nn_train
 // Errors: the reference aborts through TF_CHECK_OK; here every ABI failure throws std::runtime_error with
 // az_last_error().
 //
@@ -26,6 +28,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <future>
 #include <memory>
@@ -83,6 +86,8 @@ class NNService {
     std::condition_variable cv_full_, cv_empty_;
     std::vector<Pending> accepting_, processing_;
     int registered_ = 0, queue_size_ = 1;
+    int batch_size_ = 512;              // SETTINGS.BATCH_SIZE, settings.h:74
+    uint64_t train_seed_ = 1;           // shuffle stream of the next train() call
     bool running_ = true;
     std::thread consumer_;
     std::vector<float> x_, pol_, val_;
@@ -140,23 +145,43 @@ public:
 
     void saveCheckpoint(const std::string& path)
     {
-        std::vector<float> blob(az_nn_num_params(nn_));
-        check(az_nn_export_blob(nn_, blob.data(), blob.size()), "az_nn_export_blob");
-        std::ofstream out(path, std::ios::binary);
-        out.write(reinterpret_cast<const char*>(blob.data()), (std::streamsize)(blob.size() * sizeof(float)));
+        const size_t cut = path.find_last_of("/\\");
+        if (cut != std::string::npos) std::filesystem::create_directories(path.substr(0, cut + 1));
+        std::lock_guard<std::mutex> g(gpu_lock_);
+        check(az_nn_save_checkpoint(nn_, path.c_str()), "az_nn_save_checkpoint");
     }
     void loadCheckpoint(const std::string& path)
     {
-        std::vector<float> blob(az_nn_num_params(nn_));
-        std::ifstream in(path, std::ios::binary);
-        if (in && in.read(reinterpret_cast<char*>(blob.data()), (std::streamsize)(blob.size() * sizeof(float)))) {
+        if (std::filesystem::exists(path + ".index")) {
             std::lock_guard<std::mutex> g(gpu_lock_);
-            check(az_nn_import_blob(nn_, blob.data(), blob.size()), "az_nn_import_blob");
+            check(az_nn_load_checkpoint(nn_, path.c_str()), "az_nn_load_checkpoint");
         } else {
             printf("Checkpoint '%s' not found initialized random weights\n", path.c_str());
             initRandom(1234);
             saveCheckpoint(path);
         }
+    }
+
+    // AlphaZeroNN::train (alphazero_nn.cpp:351-410).  TrainData = the reference's NNTrainData {int8 playerIndex; NNInputData in;
+    // NNOutputData out}: packed into the 265-byte records of the sample file layout (alphazero_nn_data.cpp:115-138)
+    void setBatchSize(int b) { batch_size_ = b; }
+    template <class TrainData> void train(const std::vector<TrainData>& data, int epochs)
+    {
+        if ((int)data.size() < batch_size_) return;             // batchCount == 0: the reference's loops do nothing
+        std::vector<uint8_t> rec(data.size() * (size_t)AZ_SAMPLE_BYTES);
+        for (size_t i = 0; i < data.size(); ++i) {
+            uint8_t* r = rec.data() + i * (size_t)AZ_SAMPLE_BYTES;
+            r[0] = (uint8_t)data[i].playerIndex;
+            static_assert(sizeof(In) == 88, "NNInputData must be the reference's 88-byte INPUT_VECTOR_TYPE_2 layout");
+            std::memcpy(r + 1, &data[i].in, 88);
+            std::memcpy(r + 89, &data[i].out.value, 4);
+            std::memcpy(r + 93, data[i].out.policy.data(), 43 * sizeof(float));
+        }
+        std::vector<float> lp((size_t)epochs), lv((size_t)epochs);
+        printf("Started training\n");
+        std::lock_guard<std::mutex> g(gpu_lock_);
+        check(az_nn_train(nn_, rec.data(), data.size(), epochs, batch_size_, train_seed_++, lp.data(), lv.data(), nullptr), "az_nn_train");
+        for (int e = 0; e < epochs; ++e) printf("EPOCH %d\nLoss Policy / Value: %f / %f\n", e, lp[(size_t)e], lv[(size_t)e]);
     }
 
     void registerThread()
@@ -207,7 +232,7 @@ public:
     }
     void loadCheckpoint(std::string filePath) { svc_->loadCheckpoint(filePath); }
     void saveCheckpoint(std::string filePath) { svc_->saveCheckpoint(filePath); }
-    void train(const std::vector<TrainData>&, int) { throw std::logic_error("AlphaZeroNNId::train: the training step is out of scope of the B200 hot path"); }
+    void train(const std::vector<TrainData>& data, int epochs) { svc_->train(data, epochs); }
     void registerThread() { svc_->registerThread(); }
     void unregisterThread() { svc_->unregisterThread(); }
     std::future<Out> predictFuture(const In& state) { return svc_->predictFuture(state); }

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <filesystem>
 #include <thread>
 #include "az_nn_service.hpp"
 
@@ -37,7 +38,10 @@ int main()
     try { cluster.initPlayerGroup("az1", "model_bin_V2_2.pb"); } catch (const std::invalid_argument&) { dup = true; }   // upstream behaviour
     if (!dup) { printf("duplicate group accepted\n"); return 1; }
     auto nn = group->getNN(0);
-    nn->loadCheckpoint("/tmp/az_b200_test_ckpt.bin");          // missing -> random init + save
+    std::filesystem::remove_all("/tmp/az_b200_test_ckpt");
+    nn->loadCheckpoint("/tmp/az_b200_test_ckpt/az1");          // missing -> random init + save (a TensorFlow checkpoint bundle)
+    if (!std::filesystem::exists("/tmp/az_b200_test_ckpt/az1.index") || !std::filesystem::exists("/tmp/az_b200_test_ckpt/az1.data-00000-of-00001")) {
+        printf("checkpoint bundle was not written\n"); return 1; }
     const int T = 16, R = 40;
     std::atomic<int> bad{ 0 };
     std::vector<std::thread> th;
@@ -56,9 +60,28 @@ int main()
             nn->unregisterThread();
         });
     for (auto& x : th) x.join();
-    bool threw = false;
-    try { nn->train({}, 1); } catch (const std::logic_error&) { threw = true; }
-    if (bad || !threw) { printf("SERVICE_FAIL bad=%d threw=%d\n", bad.load(), (int)threw); return 1; }
+    // AlphaZeroNNGroup::train (alphazero_nn.cpp:351-410): 2 epochs over 96 samples in batches of 32 must change the predictions,
+    // and a checkpoint written afterwards must restore them in a second group
+    std::vector<NNTrainData> data;
+    for (unsigned k = 0; k < 96; ++k) {
+        NNTrainData td; td.playerIndex = (int8_t)(k & 1); td.in = make_input(5000 + k);
+        td.out.policy.assign(43, 0.0f); td.out.policy[k % 43] = 0.75f; td.out.policy[(k * 5 + 1) % 43] += 0.25f;
+        td.out.value = (k % 3 == 0) ? 1.0f : -1.0f;
+        data.push_back(td);
+    }
+    NNInputData probe = make_input(777);
+    NNOutputData before = nn->predict(probe);
+    nn->service().setBatchSize(32);
+    group->train(data, 2);
+    NNOutputData after = nn->predict(probe);
+    bool moved = before.value != after.value;
+    group->saveCheckpoint("/tmp/az_b200_test_ckpt/trained");
+    auto group2 = cluster.initPlayerGroup("az2", "model_bin_V2_2.pb");
+    group2->loadCheckpoint("/tmp/az_b200_test_ckpt/trained");
+    NNOutputData again = group2->getNN(0)->predict(probe);
+    bool restored = again.value == after.value;
+    for (int i = 0; i < 43; ++i) restored = restored && again.policy[i] == after.policy[i];
+    if (bad || !moved || !restored) { printf("SERVICE_FAIL bad=%d moved=%d restored=%d\n", bad.load(), (int)moved, (int)restored); return 1; }
     printf("SERVICE_OK\n");
     return 0;
 }
