@@ -33,11 +33,12 @@ class AzRules(C.Structure):
 
 class AzCounters(C.Structure):
     _fields_ = [("steps", C.c_uint64), ("games", C.c_uint64), ("wins", C.c_uint64 * 2), ("draws", C.c_uint64),
-                ("illegal", C.c_uint64), ("sims", C.c_uint64), ("evals", C.c_uint64)]
+                ("illegal", C.c_uint64), ("sims", C.c_uint64), ("evals", C.c_uint64), ("path_nodes", C.c_uint64)]
 
     def as_dict(self):
         return dict(steps=int(self.steps), games=int(self.games), wins=[int(self.wins[0]), int(self.wins[1])],
-                    draws=int(self.draws), illegal=int(self.illegal), sims=int(self.sims), evals=int(self.evals))
+                    draws=int(self.draws), illegal=int(self.illegal), sims=int(self.sims), evals=int(self.evals),
+                    path_nodes=int(self.path_nodes))
 
 
 _lib = None

@@ -817,7 +817,7 @@ extern "C" int az_env_counters(az_env* e, az_counters* h_out, int reset, void* s
     if (reset) AZ_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof h, s));
     AZ_CUDA(cudaStreamSynchronize(s));
     h_out->steps = h[0]; h_out->games = h[1]; h_out->wins[0] = h[2]; h_out->wins[1] = h[3]; h_out->draws = h[4];
-    h_out->illegal = h[5]; h_out->sims = h[6]; h_out->evals = h[7];
+    h_out->illegal = h[5]; h_out->sims = h[6]; h_out->evals = h[7]; h_out->path_nodes = 0;
     return AZ_OK;
 }
 

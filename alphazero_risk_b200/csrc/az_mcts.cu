@@ -40,7 +40,7 @@
 
 enum { EVAL_NN = 0, EVAL_PSEUDO = 1, EVAL_UNIFORM = 2 };
 #define REC_BYTES AZ_SAMPLE_BYTES
-enum { CNT_SIMS = 0, CNT_EVALS = 1, CNT_POOL_OVERFLOW = 2, CNT_DEPTH_OVERFLOW = 3, CNT_STEPS = 4, CNT_GAMES = 5, CNT_W0 = 6, CNT_W1 = 7, CNT_DRAW = 8, CNT_ILLEGAL = 9, CNT_N = 12 };
+enum { CNT_SIMS = 0, CNT_EVALS = 1, CNT_POOL_OVERFLOW = 2, CNT_DEPTH_OVERFLOW = 3, CNT_STEPS = 4, CNT_GAMES = 5, CNT_W0 = 6, CNT_W1 = 7, CNT_DRAW = 8, CNT_ILLEGAL = 9, CNT_PATH = 10, CNT_N = 12 };
 
 struct MctsDev {
     int n, cap, H, dmax;
@@ -245,6 +245,7 @@ __device__ __forceinline__ void backup_path(const MctsDev& m, int slot, int gi, 
         }
         m.path_len[slot] = 0;
         atomicAdd(&m.counters[CNT_SIMS], 1ull);
+        atomicAdd(&m.counters[CNT_PATH], (unsigned long long)len);
     }
     __syncwarp();
 }
@@ -837,7 +838,7 @@ extern "C" int az_mcts_counters(az_mcts* mc, az_counters* h_out, uint64_t* h_err
     if (reset) AZ_CUDA(cudaMemsetAsync(mc->d.counters, 0, sizeof h, s));
     AZ_CUDA(cudaStreamSynchronize(s));
     h_out->sims = h[CNT_SIMS]; h_out->evals = h[CNT_EVALS]; h_out->steps = h[CNT_STEPS]; h_out->games = h[CNT_GAMES];
-    h_out->wins[0] = h[CNT_W0]; h_out->wins[1] = h[CNT_W1]; h_out->draws = h[CNT_DRAW]; h_out->illegal = h[CNT_ILLEGAL];
+    h_out->wins[0] = h[CNT_W0]; h_out->wins[1] = h[CNT_W1]; h_out->draws = h[CNT_DRAW]; h_out->illegal = h[CNT_ILLEGAL]; h_out->path_nodes = h[CNT_PATH];
     if (h_errors) *h_errors = h[CNT_POOL_OVERFLOW] + h[CNT_DEPTH_OVERFLOW];
     return AZ_OK;
 }

@@ -11,7 +11,7 @@ stream is keyed by its GLOBAL id, so results do not depend on the number of rank
 """
 import numpy as np
 
-COUNTER_KEYS = ("steps", "games", "wins0", "wins1", "draws", "illegal", "sims", "evals", "errors")
+COUNTER_KEYS = ("steps", "games", "wins0", "wins1", "draws", "illegal", "sims", "evals", "errors", "path_nodes")
 
 
 def shard(n_total, rank, world):

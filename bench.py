@@ -264,6 +264,36 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
         cnt = azdist.reduce_counters(cnt, dist)           # stats gather (replaces GameResults::add, game.cpp:298-309)
     tot_sims, tot_evals, tot_steps, tot_games, errors = [float(cnt[k]) for k in ("sims", "evals", "steps", "games", "errors")]
     mc.close(); net.close(); env.close()
+    # ---- the tree kernels alone: the same search with the null evaluator (uniform prior, value 0: no network launches), so the
+    # timed region is k_mcts_begin / k_mcts_sim / k_mcts_finish only.  HBM roofline with SURVEY §8d's per-simulation bytes.
+    tree = None
+    if rank == 0:
+        env2 = api.Env(n, rules=rules, device=local, first_game_id=rank * n)
+        env2.reset(SEED, stream=sptr)
+        mt = api.Mcts(env2, evaluator=api.EVAL_UNIFORM)
+        mt.selfplay(4, stream=sptr)
+        torch.cuda.synchronize()
+        mt.counters(reset=True, stream=sptr)
+        t_moves = 8
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        mt.selfplay(t_moves, stream=sptr)
+        b.record(stream); torch.cuda.synchronize()
+        t_ms = a.elapsed_time(b)
+        tc = mt.counters(stream=sptr)
+        depth = tc["path_nodes"] / max(1, tc["sims"]) + 1.0           # nodes visited per simulation incl. the leaf
+        bytes_per_sim = 2900.0 + 328.0 * depth
+        hbm_peak, _, psrc = measured_peaks()
+        tree_gbs = tc["sims"] * bytes_per_sim / (t_ms * 1e-3) / 1e9
+        tree = {"sims_per_sec": tc["sims"] / (t_ms * 1e-3), "ms_per_round": t_ms / (t_moves * (sims // K + 2)), "mean_depth": depth,
+                "bytes_per_sim": bytes_per_sim,
+                "roofline": {"bound": "hbm", "achieved": tree_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": tree_gbs / hbm_peak,
+                             "traffic": ncu_traffic("k_mcts_sim"), "peak_source": psrc,
+                             "note": "null evaluator (no network): device time of the tree kernels only; algorithmic bytes per simulation = "
+                                     "2.9 KB + 328 B x depth (SURVEY 8d), depth measured (path_nodes counter); one warp per game, so "
+                                     "%d games give %d warps: latency-bound, not bandwidth-bound" % (n, n)},
+                "errors": tc["errors"]}
+        mt.close(); env2.close()
     if rank != 0:
         return None
     _, tf_peak, src = measured_peaks()
@@ -288,7 +318,7 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
                 e2e={"value": n * sims * e2e_moves * world / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": n * 160,
                      "d2h_bytes_per_step": n * (43 * 8 + 2 + 160), "steps": e2e_moves},
                 gpu_launches=steps * moves_per_step * (2 + (sims // K + 1) * (2 + 1 + 2 * blocks + 1 + 1)),
-                dtype="bf16 tower / fp32 tree", results={"games_finished": tot_games, "table_errors": errors})
+                dtype="bf16 tower / fp32 tree", results={"games_finished": tot_games, "table_errors": errors}, tree=tree)
 
 
 def run_play(args, api, torch, rank, local):

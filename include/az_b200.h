@@ -87,6 +87,7 @@ typedef struct az_counters {
     uint64_t illegal;      /* rejected actions (always 0 for rollouts)  */
     uint64_t sims;         /* MCTS simulations                          */
     uint64_t evals;        /* network evaluations                       */
+    uint64_t path_nodes;   /* sum over the simulations of the tree nodes walked through on the way down (depth of the descent) */
 } az_counters;
 
 AZ_API const char* az_last_error(void);

@@ -70,6 +70,6 @@ def test_two_rank_broadcast_and_reduce():
     want = FakeNet(5949 + 13, seed=100).blob.tobytes()
     assert res[0][1] == want and res[1][1] == want and res[1][2] == want      # rank 1 now holds rank 0's weights
     for r in res:
-        assert r[3] == dict(steps=4096 * 10, games=3, draws=0, illegal=0, sims=4096 * 64, evals=4096 * 65, errors=0, wins=[1, 2])
+        assert r[3] == dict(steps=4096 * 10, games=3, draws=0, illegal=0, sims=4096 * 64, evals=4096 * 65, errors=0, path_nodes=0, wins=[1, 2])
         assert r[4] == [11.0, 5.0]
     assert (res[0][5], res[0][6], res[1][5], res[1][6]) == (0, 2048, 2048, 2048)
