@@ -23,6 +23,7 @@ UNITS = {
     "az_mcts.cu": ["-fmad=false"],
     "az_nn.cu": [],
     "az_nn_tc.cu": [],
+    "az_tc_gemm.cu": [],
     "az_nn_train.cu": ["-fmad=false"],   # training step: plain fp32, same roundings whatever the compiler would contract
     "az_ckpt.cpp": [],       # host only: TensorFlow V2 checkpoint bundles
 }

@@ -207,6 +207,9 @@ AZ_API int az_ckpt_read(az_ckpt* ckpt, const char* name, void* h_out, size_t byt
 AZ_API int az_ckpt_write(const char* prefix, int n, const char* const* names, const int* ranks, const int64_t* const* shapes,
                          const float* const* data);                               /* float32 tensors, one shard */
 AZ_API uint32_t az_crc32c(const void* data, size_t n);
+/* test / measurement entry of the training step's bf16 tcgen05 GEMM: C[M][256] = A[M][K] * B[256][K]^T for row-major fp32 host
+   matrices (rounded to bf16), `splits` K splits; *ms = median device time of the GEMM launch over `reps` runs */
+AZ_API int az_tc_gemm_test(const float* h_a, const float* h_b, int M, int K, int splits, int reps, float* h_c, float* ms);
 
 /* ---------------------------------------------------------------- MCTS (AlphaZeroMCTS) and self-play */
 typedef struct az_mcts az_mcts;
