@@ -87,6 +87,8 @@ def lib():
         L.az_nn_train_step.argtypes = [vp, vp, vp, vp, C.c_int, f32, f32, vp]
         L.az_nn_train.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, vp, vp, vp]
         L.az_nn_train_get_grad.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
+        L.az_nn_train_precision.argtypes = [vp, C.c_int]
+        L.az_nn_train_get_layer.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t]
         L.az_nn_optimizer_get.argtypes = [vp, C.c_char_p, C.c_int, vp, C.c_size_t]
         L.az_nn_optimizer_powers.argtypes = [vp, f32, f32, u64]
         L.az_nn_save_checkpoint.argtypes = [vp, C.c_char_p]
@@ -316,6 +318,16 @@ class Net:
         lp, lv = np.zeros(epochs, np.float32), np.zeros(epochs, np.float32)
         check(self.L.az_nn_train(self.h, _ptr(r), r.shape[0], int(epochs), int(batch_size), int(seed), _ptr(lp), _ptr(lv), stream))
         return lp, lv
+
+    def train_precision(self, precision):
+        """FP32 (default, parity path) or BF16 (contractions as tcgen05 GEMMs)"""
+        check(self.L.az_nn_train_precision(self.h, int(precision)))
+
+    def layer(self, layer, which, n):
+        """convolution output (which = 0) / activation (1) of tower layer `layer` from the last training step, [n, 7, 6, 256]"""
+        a = np.empty((n, 7, 6, 256), np.float32)
+        check(self.L.az_nn_train_get_layer(self.h, int(layer), int(which), _ptr(a), a.size))
+        return a
 
     def grad(self, name, shape):
         a = np.empty(shape, np.float32)

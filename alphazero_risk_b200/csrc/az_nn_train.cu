@@ -27,6 +27,7 @@
 
 #include "az_common.cuh"
 #include "az_nn.cuh"
+#include "az_tc_gemm.cuh"
 
 #define TR_CH AZ_NN_CH
 #define TR_BN_MOMENTUM 0.99f
@@ -37,6 +38,9 @@
 #define TR_ADAM_EPS 1e-8f
 #define TR_STAT_CHUNKS 64          // row chunks of the column reductions
 #define TR_WG_SPLITS 16            // board splits of the weight-gradient reduction
+
+static inline size_t tr_mp(int rows) { return ((size_t)rows + 127) / 128 * 128; }     // rows of a GEMM output, 128-row tiles
+static inline size_t tr_kp(int k) { return ((size_t)k + 63) / 64 * 64; }            // K of a GEMM, 64-element blocks
 
 struct az_ckpt;
 extern "C" int az_ckpt_open(const char* prefix, az_ckpt** out);
@@ -50,6 +54,8 @@ int az_nn_sync_host(az_nn* nn);      // az_nn.cu
 
 struct AzTrainState {
     int cap = 0;                                       // boards the work buffers are sized for
+    int precision = AZ_NN_FP32;                        // AZ_NN_BF16: the three contractions run on the tensor cores (az_tc_gemm.cu)
+    __nv_bfloat16 *d_colA = nullptr, *d_colB = nullptr;   // GEMM operands: im2col / transposed im2col, weights / transposed gradient
     float *d_grad = nullptr, *d_m = nullptr, *d_v = nullptr;      // blob-sized: gradient of the total loss, Adam slots
     std::vector<float> h_m, h_v;                       // host mirrors (checkpoints)
     bool slots_on_device = false, host_slots_stale = false;
@@ -605,7 +611,7 @@ void az_nn_train_release(az_nn* nn)
     for (float* p : t->a) cudaFree(p);
     cudaFree(t->d_stats); cudaFree(t->d_part); for (int i = 0; i < 3; ++i) cudaFree(t->d_g[i]);
     cudaFree(t->d_wT); cudaFree(t->d_wpart); cudaFree(t->d_hz); cudaFree(t->d_hg); cudaFree(t->d_hfeat); cudaFree(t->d_hpart);
-    cudaFree(t->d_tp); cudaFree(t->d_tv); cudaFree(t->d_loss);
+    cudaFree(t->d_tp); cudaFree(t->d_tv); cudaFree(t->d_loss); cudaFree(t->d_colA); cudaFree(t->d_colB);
     delete t;
     nn->train = nullptr;
 }
@@ -640,11 +646,12 @@ static int train_reserve(az_nn* nn, AzTrainState* t, int n)
 {
     if (n <= t->cap) return AZ_OK;
     const int layers = 2 * nn->blocks + 1;
-    const size_t act = (size_t)n * 42 * TR_CH;
+    const size_t act = tr_mp(n * 42) * TR_CH;                   // rows padded to the GEMM's 128-row tiles (the tensor-core path writes whole tiles)
     for (float* p : t->z) cudaFree(p);
     for (float* p : t->a) cudaFree(p);
     t->z.assign((size_t)layers, nullptr); t->a.assign((size_t)layers, nullptr);
     cudaFree(t->d_x); cudaFree(t->d_hz); cudaFree(t->d_hg); cudaFree(t->d_hfeat); cudaFree(t->d_tp); cudaFree(t->d_tv);
+    cudaFree(t->d_colA); cudaFree(t->d_colB); t->d_colA = t->d_colB = nullptr;
     for (int i = 0; i < 3; ++i) { cudaFree(t->d_g[i]); t->d_g[i] = nullptr; }
     t->d_x = t->d_hz = t->d_hg = t->d_hfeat = t->d_tp = t->d_tv = nullptr; t->cap = 0;
     for (int L = 0; L < layers; ++L) { AZ_CUDA(cudaMalloc(&t->z[(size_t)L], sizeof(float) * act)); AZ_CUDA(cudaMalloc(&t->a[(size_t)L], sizeof(float) * act)); }
@@ -653,6 +660,11 @@ static int train_reserve(az_nn* nn, AzTrainState* t, int n)
     AZ_CUDA(cudaMalloc(&t->d_hz, sizeof(float) * (size_t)n * 42 * 4)); AZ_CUDA(cudaMalloc(&t->d_hg, sizeof(float) * (size_t)n * 42 * 4));
     AZ_CUDA(cudaMalloc(&t->d_hfeat, sizeof(float) * (size_t)n * HF_STRIDE));
     AZ_CUDA(cudaMalloc(&t->d_tp, sizeof(float) * (size_t)n * 43)); AZ_CUDA(cudaMalloc(&t->d_tv, sizeof(float) * (size_t)n));
+    {   // GEMM operands of the tensor-core path: A = max(im2col [Mp][9*256], transposed im2col [9*256][Kp]), B = max(weights, dz^T)
+        const size_t mp = tr_mp(n * 42), kpw = tr_kp(n * 42);
+        const size_t a_elems = (size_t)9 * TR_CH * (mp > kpw ? mp : kpw), b_elems = (size_t)TR_CH * (kpw > (size_t)9 * TR_CH ? kpw : (size_t)9 * TR_CH);
+        AZ_CUDA(cudaMalloc(&t->d_colA, a_elems * sizeof(__nv_bfloat16))); AZ_CUDA(cudaMalloc(&t->d_colB, b_elems * sizeof(__nv_bfloat16)));
+    }
     if (!t->d_stats) {
         AZ_CUDA(cudaMalloc(&t->d_stats, sizeof(float) * (size_t)(layers + 1) * 4 * TR_CH));
         AZ_CUDA(cudaMalloc(&t->d_part, sizeof(double) * TR_STAT_CHUNKS * TR_CH * 2));
@@ -670,6 +682,26 @@ static int train_reserve(az_nn* nn, AzTrainState* t, int n)
         AZ_CUDA(cudaMemcpyToSymbol(c_tnb, nb, sizeof nb));
     }
     t->cap = n;
+    return AZ_OK;
+}
+
+// one raw 3x3 convolution out[r][256] = conv(in[r][cin], w[9][cin][256]) (flip: the data-gradient kernel w[8-t] transposed)
+static int conv_any(az_nn* nn, AzTrainState* t, const float* in, int n, int cin, const float* w, int flip, float* out, cudaStream_t s)
+{
+    if (t->precision == AZ_NN_BF16) {
+        const int rows = n * 42, mp = (int)tr_mp(rows), cpad = (cin + 7) / 8 * 8, kp = (int)tr_kp(9 * cpad);
+        int rc = az_tg_im2col(in, rows, cin, cpad, mp, kp, t->d_colA, s); if (rc) return rc;
+        rc = az_tg_weights(w, cin, cpad, kp, flip, t->d_colB, s); if (rc) return rc;
+        return az_tg_gemm(t->d_colA, t->d_colB, out, mp, kp, 1, s);
+    }
+    const float* wk = w;
+    if (flip) {
+        k_tr_flip_transpose<<<(9 * TR_CH * TR_CH + 255) / 256, 256, 0, s>>>(w, t->d_wT);
+        wk = t->d_wT;
+    }
+    const dim3 cgrid((unsigned)((n + TC_BOARDS - 1) / TC_BOARDS), TR_CH / TC_CO);
+    k_tr_conv<<<cgrid, 128, TC_SMEM_FLOATS * sizeof(float), s>>>(in, n, cin, wk, out);
+    AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
 
@@ -713,6 +745,14 @@ static int bn_backward(az_nn* nn, AzTrainState* t, int L, int n, const float* do
 
 static int conv_wgrad(az_nn* nn, AzTrainState* t, int L, int n, const float* in, int cin, const float* dz, cudaStream_t s)
 {
+    if (t->precision == AZ_NN_BF16) {                          // dW[t*cin + ci][co] = im2col(in)^T . dz, K = board cells, split over K
+        const int rows = n * 42, mp = (int)tr_mp(9 * cin), kp = (int)tr_kp(rows);
+        const int splits = az_tg_splits(kp, 148 / (mp / 128) > TR_WG_SPLITS ? TR_WG_SPLITS : 148 / (mp / 128));
+        int rc = az_tg_im2col_t(in, rows, cin, mp, kp, t->d_colA, s); if (rc) return rc;
+        rc = az_tg_rows_t(dz, rows, kp, t->d_colB, s); if (rc) return rc;
+        rc = az_tg_gemm(t->d_colA, t->d_colB, t->d_wpart, mp, kp, splits, s); if (rc) return rc;
+        return az_tg_reduce(t->d_wpart, splits, mp, 9 * cin, gvar(nn, t, tr_conv_name(L) + "/kernel"), s);
+    }
     dim3 grid((unsigned)((cin + TC_CI - 1) / TC_CI), TR_CH / TC_CO, TR_WG_SPLITS);
     k_tr_wgrad<<<grid, 256, 0, s>>>(in, cin, dz, n, t->d_wpart);
     const size_t count = (size_t)9 * cin * TR_CH;
@@ -729,15 +769,15 @@ static int train_step_dev(az_nn* nn, const float* d_x, const float* d_tp, const 
     if (!nn->host_stale) { rc = az_nn_finalize(nn); if (rc) return rc; }      // device copy of the weights is current (or already ahead)
     rc = slots_to_device(nn, t); if (rc) return rc;
     rc = train_reserve(nn, t, n); if (rc) return rc;
+    if (t->precision == AZ_NN_BF16) { rc = az_tg_init(); if (rc) return rc; }
     const int layers = 2 * nn->blocks + 1, rows = n * 42;
-    const size_t total = (size_t)rows * TR_CH, smem = TC_SMEM_FLOATS * sizeof(float);
-    const dim3 cgrid((unsigned)((n + TC_BOARDS - 1) / TC_BOARDS), TR_CH / TC_CO);
+    const size_t total = (size_t)rows * TR_CH;
     const unsigned egrid = (unsigned)((total + 255) / 256);
     // ---- forward
-    k_tr_conv<<<cgrid, 128, smem, s>>>(d_x, n, AZ_NN_IN_CH, dvar(nn, "conv/kernel"), t->z[0]);
+    rc = conv_any(nn, t, d_x, n, AZ_NN_IN_CH, dvar(nn, "conv/kernel"), 0, t->z[0], s); if (rc) return rc;
     rc = bn_forward(nn, t, 0, n, nullptr, s); if (rc) return rc;
     for (int L = 1; L < layers; ++L) {
-        k_tr_conv<<<cgrid, 128, smem, s>>>(t->a[(size_t)L - 1], n, TR_CH, dvar(nn, tr_conv_name(L) + "/kernel"), t->z[(size_t)L]);
+        rc = conv_any(nn, t, t->a[(size_t)L - 1], n, TR_CH, dvar(nn, tr_conv_name(L) + "/kernel"), 0, t->z[(size_t)L], s); if (rc) return rc;
         rc = bn_forward(nn, t, L, n, (L & 1) ? nullptr : t->a[(size_t)L - 2], s); if (rc) return rc;      // 2b adds the block input
     }
     const float* act = t->a[(size_t)layers - 1];
@@ -759,17 +799,14 @@ static int train_step_dev(az_nn* nn, const float* d_x, const float* d_tp, const 
     k_tr_head_wgrad_final<<<1, 256, 0, s>>>(t->d_hpart, gvar(nn, t, "pi/kernel"), gvar(nn, t, "v/kernel"));
     AZ_CUDA(cudaGetLastError());
     // ---- backward: tower.  G0 = gradient w.r.t. the output of block i
-    const unsigned fgrid = (9 * TR_CH * TR_CH + 255) / 256;
     for (int i = nn->blocks - 1; i >= 0; --i) {
         const int La = 1 + 2 * i, Lb = 2 + 2 * i;
         rc = bn_backward(nn, t, Lb, n, G0, G1, s); if (rc) return rc;                                   // dz of 2b
         rc = conv_wgrad(nn, t, Lb, n, t->a[(size_t)La], TR_CH, G1, s); if (rc) return rc;
-        k_tr_flip_transpose<<<fgrid, 256, 0, s>>>(dvar(nn, tr_conv_name(Lb) + "/kernel"), t->d_wT);
-        k_tr_conv<<<cgrid, 128, smem, s>>>(G1, n, TR_CH, t->d_wT, G2);                                  // gradient w.r.t. the 2a activation
+        rc = conv_any(nn, t, G1, n, TR_CH, dvar(nn, tr_conv_name(Lb) + "/kernel"), 1, G2, s); if (rc) return rc;   // gradient w.r.t. the 2a activation
         rc = bn_backward(nn, t, La, n, G2, G1, s); if (rc) return rc;                                   // dz of 2a
         rc = conv_wgrad(nn, t, La, n, t->a[(size_t)La - 1], TR_CH, G1, s); if (rc) return rc;
-        k_tr_flip_transpose<<<fgrid, 256, 0, s>>>(dvar(nn, tr_conv_name(La) + "/kernel"), t->d_wT);
-        k_tr_conv<<<cgrid, 128, smem, s>>>(G1, n, TR_CH, t->d_wT, G2);                                  // gradient w.r.t. the block input ...
+        rc = conv_any(nn, t, G1, n, TR_CH, dvar(nn, tr_conv_name(La) + "/kernel"), 1, G2, s); if (rc) return rc;   // gradient w.r.t. the block input ...
         k_tr_add_masked<<<egrid, 256, 0, s>>>(G2, G0, t->a[(size_t)Lb], total);                         // ... plus the skip connection's share
         float* tmp = G0; G0 = G2; G2 = tmp;
     }
@@ -859,6 +896,18 @@ extern "C" int az_nn_train(az_nn* nn, const uint8_t* h_records, size_t n_records
     return rc;
 }
 
+// AZ_NN_FP32 (default): every contraction on the fp32 pipes — the parity path.  AZ_NN_BF16: forward convolutions, data gradients and
+// weight gradients as bf16 tcgen05 GEMMs with fp32 accumulation (az_tc_gemm.cu); statistics, BatchNorm, heads, losses, Adam stay fp32.
+extern "C" int az_nn_train_precision(az_nn* nn, int precision)
+{
+    AZ_REQUIRE(nn != nullptr, "nn is NULL");
+    AZ_REQUIRE(precision == AZ_NN_FP32 || precision == AZ_NN_BF16, "precision must be AZ_NN_FP32 or AZ_NN_BF16");
+    AzTrainState* t = train_state(nn);
+    AZ_REQUIRE(t != nullptr, "out of host memory");
+    t->precision = precision;
+    return AZ_OK;
+}
+
 // gradient of the total loss (L2 term included) w.r.t. a trainable variable, as of the last step (test introspection)
 extern "C" int az_nn_train_get_grad(az_nn* nn, const char* name, float* h_out, size_t count)
 {
@@ -870,6 +919,20 @@ extern "C" int az_nn_train_get_grad(az_nn* nn, const char* name, float* h_out, s
     AZ_REQUIRE(v.count == count, "element count mismatch");
     AzDeviceGuard guard(nn->device);
     AZ_CUDA(cudaMemcpy(h_out, nn->train->d_grad + v.offset, sizeof(float) * count, cudaMemcpyDeviceToHost));
+    return AZ_OK;
+}
+
+// raw convolution output z (which = 0) or activation a (which = 1) of tower layer `layer` (0 = stem, 2i+1 / 2i+2 = branch 2a / 2b of
+// block i) as of the last step, [boards][42][256] (test introspection: per-layer forward parity of the two precisions)
+extern "C" int az_nn_train_get_layer(az_nn* nn, int layer, int which, float* h_out, size_t count)
+{
+    AZ_REQUIRE(nn && h_out && (which == 0 || which == 1), "bad argument");
+    AZ_REQUIRE(nn->train && nn->train->cap > 0, "no training step has run on this network");
+    AzTrainState* t = nn->train;
+    AZ_REQUIRE(layer >= 0 && layer < (int)t->z.size(), "layer out of range");
+    AZ_REQUIRE(count <= (size_t)t->cap * 42 * TR_CH, "more elements than the last batch holds");
+    AzDeviceGuard guard(nn->device);
+    AZ_CUDA(cudaMemcpy(h_out, (which ? t->a : t->z)[(size_t)layer], sizeof(float) * count, cudaMemcpyDeviceToHost));
     return AZ_OK;
 }
 

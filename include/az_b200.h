@@ -185,8 +185,12 @@ AZ_API int az_nn_train_step(az_nn* nn, const float* h_x, const float* h_target_p
    `epochs` shuffled passes, whole batches of batch_size (SETTINGS.BATCH_SIZE = 512) only; per-epoch mean losses (may be NULL) */
 AZ_API int az_nn_train(az_nn* nn, const uint8_t* h_records, size_t n_records, int epochs, int batch_size, uint64_t seed,
                        float* h_epoch_loss_policy, float* h_epoch_loss_value, void* stream);
+/* AZ_NN_FP32 (default, the parity path) or AZ_NN_BF16: the three convolution-shaped contractions of the step (forward, data gradient,
+   weight gradient) as bf16 tcgen05 GEMMs with fp32 accumulation; everything else stays fp32 */
+AZ_API int az_nn_train_precision(az_nn* nn, int precision);
 /* introspection for the parity tests: gradient of the total loss from the last step; Adam slots (which: 0 = m, 1 = v); beta powers */
 AZ_API int az_nn_train_get_grad(az_nn* nn, const char* name, float* h_out, size_t count);
+AZ_API int az_nn_train_get_layer(az_nn* nn, int layer, int which /* 0 = convolution output, 1 = activation */, float* h_out, size_t count);
 AZ_API int az_nn_optimizer_get(az_nn* nn, const char* name, int which, float* h_out, size_t count);
 AZ_API int az_nn_optimizer_powers(az_nn* nn, float* beta1_power, float* beta2_power, uint64_t* steps);
 /* AlphaZeroNN::saveCheckpoint / loadCheckpoint (alphazero_nn.cpp:189-214): TensorFlow V2 checkpoint bundle <prefix>.index +

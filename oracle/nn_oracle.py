@@ -39,10 +39,40 @@ def _bn(x, w, prefix, axis):
     return (x - m.reshape(shape)) * scale.reshape(shape) + b.reshape(shape)
 
 
+def _rb(t):
+    """round to bf16 (round-to-nearest-even from fp32, what the device does to a GEMM operand) and back"""
+    return t.to(torch.float32).to(torch.bfloat16).to(t.dtype)
+
+
+class _ConvBf16(torch.autograd.Function):
+    """the 3x3 convolution of the tensor-core training mode (az_nn_train_precision(AZ_NN_BF16)): each of its three contractions
+    (forward, data gradient, weight gradient) takes both operands rounded to bf16 and accumulates exactly (fp32 on the device)"""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        ctx.save_for_backward(x, k)
+        return F.conv2d(_rb(x), _rb(k), padding=k.shape[2] // 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, k = ctx.saved_tensors
+        pad = k.shape[2] // 2
+        gx = torch.nn.grad.conv2d_input(x.shape, _rb(k), _rb(g), padding=pad)
+        gk = torch.nn.grad.conv2d_weight(_rb(x), k.shape, _rb(g), padding=pad)
+        return gx, gk
+
+
+TRACE = None                   # a dict here collects every BatchNorm's input during train_losses (per-layer forward checks)
+BF16_CONTRACTIONS = False      # set by Trainer(bf16=True) around its step: 3x3 convolutions through _ConvBf16
+
+
 def _conv(x, k):
     """k: HWIO -> conv2d with SAME padding, stride 1, no bias; x NCHW"""
     kh = k.shape[0]
-    return F.conv2d(x, k.permute(3, 2, 0, 1).contiguous(), padding=kh // 2)
+    kk = k.permute(3, 2, 0, 1).contiguous()
+    if BF16_CONTRACTIONS and kh == 3:
+        return _ConvBf16.apply(x, kk)
+    return F.conv2d(x, kk, padding=kh // 2)
 
 
 def forward(weights, x, blocks, dtype=torch.float32):
@@ -100,6 +130,8 @@ def _bn_train(x, w, prefix, axis, batch_stats):
     var = ((x - mean.reshape([-1 if d == axis else 1 for d in range(4)])) ** 2).mean(dim=dims)
     n = x.numel() // x.shape[axis]
     batch_stats[prefix] = (mean.detach(), (var * n / (n - 1)).detach())
+    if TRACE is not None:
+        TRACE[prefix] = x.detach().permute(0, 2, 3, 1).numpy().copy()       # the convolution output entering this BatchNorm, NHWC
     shape = [1, 1, 1, 1]
     shape[axis] = -1
     return (x - mean.reshape(shape)) * torch.rsqrt(var.reshape(shape) + EPS) * g.reshape(shape) + b.reshape(shape)
@@ -128,8 +160,8 @@ def train_losses(w, x, target_policy, target_value, blocks, batch_stats):
 class Trainer:
     """the graph's variables + Adam slots; step() = one TF_OP_OPTIMIZE run"""
 
-    def __init__(self, weights, blocks, dtype=torch.float64):
-        self.blocks, self.dtype = blocks, dtype
+    def __init__(self, weights, blocks, dtype=torch.float64, bf16=False):
+        self.blocks, self.dtype, self.bf16 = blocks, dtype, bf16
         self.w = {k: torch.as_tensor(np.asarray(v), dtype=dtype).clone() for k, v in weights.items()}
         self.m = {k: torch.zeros_like(self.w[k]) for k in trainable_names(blocks)}
         self.v = {k: torch.zeros_like(self.w[k]) for k in trainable_names(blocks)}
@@ -145,8 +177,13 @@ class Trainer:
         x = torch.as_tensor(np.asarray(x), dtype=self.dtype)
         tp = torch.as_tensor(np.asarray(target_policy), dtype=self.dtype).reshape(-1, 43)
         tv = torch.as_tensor(np.asarray(target_value), dtype=self.dtype).reshape(-1)
-        loss_pi, loss_v, l2 = train_losses(self.w, x, tp, tv, self.blocks, stats)
-        (loss_pi + loss_v + l2).backward()
+        global BF16_CONTRACTIONS
+        BF16_CONTRACTIONS = self.bf16
+        try:
+            loss_pi, loss_v, l2 = train_losses(self.w, x, tp, tv, self.blocks, stats)
+            (loss_pi + loss_v + l2).backward()
+        finally:
+            BF16_CONTRACTIONS = False
         lr_t = ADAM["lr"] * np.sqrt(1.0 - self.beta2_power) / (1.0 - self.beta1_power)
         with torch.no_grad():
             for k in names:
