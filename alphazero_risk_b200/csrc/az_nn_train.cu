@@ -19,6 +19,7 @@
 //             reduced in a fixed order) and k_tr_conv (data gradient)
 //   update    k_tr_adam per trainable variable (L2 term added to the kernels' gradients)
 // Results are deterministic: no floating-point atomics anywhere.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -36,7 +37,7 @@
 #define TR_BETA1 0.9f
 #define TR_BETA2 0.999f
 #define TR_ADAM_EPS 1e-8f
-#define TR_STAT_CHUNKS 64          // row chunks of the column reductions
+#define TR_STAT_CHUNKS 296         // row chunks of the column reductions (2 per SM)
 #define TR_WG_SPLITS 16            // board splits of the weight-gradient reduction
 
 static inline size_t tr_mp(int rows) { return ((size_t)rows + 127) / 128 * 128; }     // rows of a GEMM output, 128-row tiles
@@ -56,6 +57,8 @@ struct AzTrainState {
     int cap = 0;                                       // boards the work buffers are sized for
     int precision = AZ_NN_FP32;                        // AZ_NN_BF16: the three contractions run on the tensor cores (az_tc_gemm.cu)
     __nv_bfloat16 *d_colA = nullptr, *d_colB = nullptr;   // GEMM operands: im2col / transposed im2col, weights / transposed gradient
+    uint8_t* d_kind = nullptr;                         // per blob element: 0 not trainable, 1 plain, 2 kernel (L2 term)
+    __nv_bfloat16* d_src16 = nullptr;                  // bf16 chunked copy of the tensor being unrolled
     float *d_grad = nullptr, *d_m = nullptr, *d_v = nullptr;      // blob-sized: gradient of the total loss, Adam slots
     std::vector<float> h_m, h_v;                       // host mirrors (checkpoints)
     bool slots_on_device = false, host_slots_stale = false;
@@ -158,23 +161,55 @@ __global__ void k_tr_flip_transpose(const float* __restrict__ w, float* __restri
 // mode 0: sum z, sum z^2           (forward statistics)
 // mode 1: sum g, sum g * xhat      (backward), g = dout * [a > 0], xhat = (z - mean) * invstd
 // stem = 1: the statistic group of element (r, c) is the board row y = (r % 42) / 6 instead of the channel c.
-// grid = TR_STAT_CHUNKS blocks of 256 threads (thread = channel); partials in double, reduced in chunk order by k_tr_stats_final.
+// grid = TR_STAT_CHUNKS blocks of 256 threads = 64 channel quads (16-byte loads) x 4 row lanes; partials in double, the row lanes are
+// combined in lane order here and the chunks in chunk order by k_tr_stats_final.  (The stem variant keeps thread = channel.)
 __global__ void __launch_bounds__(256) k_tr_stats(const float* __restrict__ z, const float* __restrict__ dout, const float* __restrict__ a,
                                                    const float* __restrict__ stats, int rows, int mode, int stem, double* __restrict__ part)
 {
     __shared__ double s_red[8][7][2];
+    __shared__ double s_lane[3][TR_CH][2];
     const int c = threadIdx.x, chunk = blockIdx.x;
     const int per = ((rows / 42 + TR_STAT_CHUNKS - 1) / TR_STAT_CHUNKS) * 42;           // whole boards per chunk
-    const int r0 = chunk * per, r1 = min(rows, r0 + per);
+    const int r0 = min(rows, chunk * per), r1 = min(rows, r0 + per);
     if (!stem) {
-        double s0 = 0.0, s1 = 0.0;
-        const float mean = mode ? stats[c] : 0.0f, inv = mode ? stats[TR_CH + c] : 0.0f;
-        for (int r = r0; r < r1; ++r) {
-            const size_t o = (size_t)r * TR_CH + c;
-            if (mode == 0) { const float v = z[o]; s0 += (double)v; s1 += (double)v * (double)v; }
-            else { const float g = a[o] > 0.0f ? dout[o] : 0.0f; s0 += (double)g; s1 += (double)g * (double)((z[o] - mean) * inv); }
+        const int cq = threadIdx.x & 63, rl = threadIdx.x >> 6;
+        double s0[4] = { 0.0, 0.0, 0.0, 0.0 }, s1[4] = { 0.0, 0.0, 0.0, 0.0 };
+        float mean[4] = { 0, 0, 0, 0 }, inv[4] = { 0, 0, 0, 0 };
+        if (mode) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { mean[e] = stats[cq * 4 + e]; inv[e] = stats[TR_CH + cq * 4 + e]; }
         }
-        part[((size_t)chunk * TR_CH + c) * 2 + 0] = s0; part[((size_t)chunk * TR_CH + c) * 2 + 1] = s1;
+#pragma unroll 2
+        for (int r = r0 + rl; r < r1; r += 4) {
+            const size_t o = (size_t)r * TR_CH + cq * 4;
+            const float4 zv = *reinterpret_cast<const float4*>(z + o);
+            const float zz[4] = { zv.x, zv.y, zv.z, zv.w };
+            if (mode == 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { s0[e] += (double)zz[e]; s1[e] += (double)zz[e] * (double)zz[e]; }
+            } else {
+                const float4 av = *reinterpret_cast<const float4*>(a + o), dv = *reinterpret_cast<const float4*>(dout + o);
+                const float aa[4] = { av.x, av.y, av.z, av.w }, dd[4] = { dv.x, dv.y, dv.z, dv.w };
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float g = aa[e] > 0.0f ? dd[e] : 0.0f;
+                    s0[e] += (double)g; s1[e] += (double)g * (double)((zz[e] - mean[e]) * inv[e]);
+                }
+            }
+        }
+        if (rl > 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { s_lane[rl - 1][cq * 4 + e][0] = s0[e]; s_lane[rl - 1][cq * 4 + e][1] = s1[e]; }
+        }
+        __syncthreads();
+        if (rl == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                double v0 = s0[e], v1 = s1[e];
+                for (int l = 0; l < 3; ++l) { v0 += s_lane[l][cq * 4 + e][0]; v1 += s_lane[l][cq * 4 + e][1]; }
+                part[((size_t)chunk * TR_CH + cq * 4 + e) * 2 + 0] = v0; part[((size_t)chunk * TR_CH + cq * 4 + e) * 2 + 1] = v1;
+            }
+        }
     } else {
         double s0[7], s1[7];
 #pragma unroll
@@ -215,10 +250,20 @@ __global__ void __launch_bounds__(256) k_tr_stats_final(const double* __restrict
                                                          float* __restrict__ moving_mean, float* __restrict__ moving_var,
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta)
 {
-    const int c = threadIdx.x;
-    if (c >= groups) return;
+    // grid = 8 blocks of 32 groups; 256 threads = 8 chunk lanes x 32 groups; each lane sums its chunks in order, then the lanes in order
+    __shared__ double s_q[7][32][2];
+    const int cl = threadIdx.x & 31, q = threadIdx.x >> 5, c = blockIdx.x * 32 + cl;
     double s0 = 0.0, s1 = 0.0;
-    for (int k = 0; k < TR_STAT_CHUNKS; ++k) { s0 += part[((size_t)k * TR_CH + c) * 2 + 0]; s1 += part[((size_t)k * TR_CH + c) * 2 + 1]; }
+    constexpr int QN = TR_STAT_CHUNKS / 8;
+    static_assert(TR_STAT_CHUNKS % 8 == 0, "chunk count must split into eight lanes");
+    if (c < groups) {
+#pragma unroll 8
+        for (int k = q * QN; k < (q + 1) * QN; ++k) { s0 += part[((size_t)k * TR_CH + c) * 2 + 0]; s1 += part[((size_t)k * TR_CH + c) * 2 + 1]; }
+    }
+    if (q > 0) { s_q[q - 1][cl][0] = s0; s_q[q - 1][cl][1] = s1; }
+    __syncthreads();
+    if (q > 0 || c >= groups) return;
+    for (int l = 0; l < 7; ++l) { s0 += s_q[l][cl][0]; s1 += s_q[l][cl][1]; }
     if (mode == 0) {
         const double mean = s0 / count;
         double var = s1 / count - mean * mean; if (var < 0.0) var = 0.0;
@@ -545,12 +590,15 @@ __global__ void __launch_bounds__(256) k_tr_head_wgrad_final(const float* __rest
 }
 
 // ---------------------------------------------------------------- Adam (TensorFlow's ResourceApplyAdam), L2 term for kernels
+// one launch over the whole variable blob; kind[i]: 0 = not trainable (moving statistics), 1 = plain, 2 = kernel (carries the L2 term)
 __global__ void __launch_bounds__(256) k_tr_adam(float* __restrict__ w, float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, size_t count,
-                                                  float l2_scale, float lr_t)
+                                                  const uint8_t* __restrict__ kind, float l2_scale, float lr_t)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    const float g = grad[i] + l2_scale * w[i];                  // d(0.001 * sum w^2)/dw = 0.002 * w
+    const uint8_t kd = kind[i];
+    if (kd == 0) return;
+    const float g = grad[i] + (kd == 2 ? l2_scale : 0.0f) * w[i];   // d(0.001 * sum w^2)/dw = 0.002 * w
     grad[i] = g;
     const float mi = m[i] + (g - m[i]) * (1.0f - TR_BETA1);
     const float vi = v[i] + (g * g - v[i]) * (1.0f - TR_BETA2);
@@ -611,7 +659,7 @@ void az_nn_train_release(az_nn* nn)
     for (float* p : t->a) cudaFree(p);
     cudaFree(t->d_stats); cudaFree(t->d_part); for (int i = 0; i < 3; ++i) cudaFree(t->d_g[i]);
     cudaFree(t->d_wT); cudaFree(t->d_wpart); cudaFree(t->d_hz); cudaFree(t->d_hg); cudaFree(t->d_hfeat); cudaFree(t->d_hpart);
-    cudaFree(t->d_tp); cudaFree(t->d_tv); cudaFree(t->d_loss); cudaFree(t->d_colA); cudaFree(t->d_colB);
+    cudaFree(t->d_tp); cudaFree(t->d_tv); cudaFree(t->d_loss); cudaFree(t->d_colA); cudaFree(t->d_colB); cudaFree(t->d_src16); cudaFree(t->d_kind);
     delete t;
     nn->train = nullptr;
 }
@@ -622,6 +670,11 @@ static int slots_to_device(az_nn* nn, AzTrainState* t)
     if (!t->d_grad) {
         AZ_CUDA(cudaMalloc(&t->d_grad, sizeof(float) * np)); AZ_CUDA(cudaMalloc(&t->d_m, sizeof(float) * np)); AZ_CUDA(cudaMalloc(&t->d_v, sizeof(float) * np));
         AZ_CUDA(cudaMemset(t->d_grad, 0, sizeof(float) * np));
+        std::vector<uint8_t> kind(np, 0);
+        for (const AzVar& v : nn->vars)
+            if (!is_moving(v.name)) std::fill(kind.begin() + (ptrdiff_t)v.offset, kind.begin() + (ptrdiff_t)(v.offset + v.count), (uint8_t)(is_kernel(v.name) ? 2 : 1));
+        AZ_CUDA(cudaMalloc(&t->d_kind, np));
+        AZ_CUDA(cudaMemcpy(t->d_kind, kind.data(), np, cudaMemcpyHostToDevice));
     }
     if (!t->slots_on_device) {
         AZ_CUDA(cudaMemcpy(t->d_m, t->h_m.data(), sizeof(float) * np, cudaMemcpyHostToDevice));
@@ -651,7 +704,7 @@ static int train_reserve(az_nn* nn, AzTrainState* t, int n)
     for (float* p : t->a) cudaFree(p);
     t->z.assign((size_t)layers, nullptr); t->a.assign((size_t)layers, nullptr);
     cudaFree(t->d_x); cudaFree(t->d_hz); cudaFree(t->d_hg); cudaFree(t->d_hfeat); cudaFree(t->d_tp); cudaFree(t->d_tv);
-    cudaFree(t->d_colA); cudaFree(t->d_colB); t->d_colA = t->d_colB = nullptr;
+    cudaFree(t->d_colA); cudaFree(t->d_colB); cudaFree(t->d_src16); t->d_colA = t->d_colB = t->d_src16 = nullptr;
     for (int i = 0; i < 3; ++i) { cudaFree(t->d_g[i]); t->d_g[i] = nullptr; }
     t->d_x = t->d_hz = t->d_hg = t->d_hfeat = t->d_tp = t->d_tv = nullptr; t->cap = 0;
     for (int L = 0; L < layers; ++L) { AZ_CUDA(cudaMalloc(&t->z[(size_t)L], sizeof(float) * act)); AZ_CUDA(cudaMalloc(&t->a[(size_t)L], sizeof(float) * act)); }
@@ -664,6 +717,7 @@ static int train_reserve(az_nn* nn, AzTrainState* t, int n)
         const size_t mp = tr_mp(n * 42), kpw = tr_kp(n * 42);
         const size_t a_elems = (size_t)9 * TR_CH * (mp > kpw ? mp : kpw), b_elems = (size_t)TR_CH * (kpw > (size_t)9 * TR_CH ? kpw : (size_t)9 * TR_CH);
         AZ_CUDA(cudaMalloc(&t->d_colA, a_elems * sizeof(__nv_bfloat16))); AZ_CUDA(cudaMalloc(&t->d_colB, b_elems * sizeof(__nv_bfloat16)));
+        AZ_CUDA(cudaMalloc(&t->d_src16, (size_t)n * 42 * TR_CH * sizeof(__nv_bfloat16)));
     }
     if (!t->d_stats) {
         AZ_CUDA(cudaMalloc(&t->d_stats, sizeof(float) * (size_t)(layers + 1) * 4 * TR_CH));
@@ -690,7 +744,7 @@ static int conv_any(az_nn* nn, AzTrainState* t, const float* in, int n, int cin,
 {
     if (t->precision == AZ_NN_BF16) {
         const int rows = n * 42, mp = (int)tr_mp(rows), cpad = (cin + 7) / 8 * 8, kp = (int)tr_kp(9 * cpad);
-        int rc = az_tg_im2col(in, rows, cin, cpad, mp, kp, t->d_colA, s); if (rc) return rc;
+        int rc = az_tg_im2col(in, rows, cin, cpad, mp, kp, t->d_src16, t->d_colA, s); if (rc) return rc;
         rc = az_tg_weights(w, cin, cpad, kp, flip, t->d_colB, s); if (rc) return rc;
         return az_tg_gemm(t->d_colA, t->d_colB, out, mp, kp, 1, s);
     }
@@ -721,7 +775,7 @@ static int bn_forward(az_nn* nn, AzTrainState* t, int L, int n, const float* ski
     float* st = t->d_stats + (size_t)L * 4 * TR_CH;
     const std::string bn = tr_bn_name(L);
     k_tr_stats<<<TR_STAT_CHUNKS, 256, 0, s>>>(t->z[(size_t)L], nullptr, nullptr, st, rows, 0, stem, t->d_part);
-    k_tr_stats_final<<<1, 256, 0, s>>>(t->d_part, stem ? 7 : TR_CH, stem ? (double)n * 6 * TR_CH : (double)rows, 0, st,
+    k_tr_stats_final<<<8, 256, 0, s>>>(t->d_part, stem ? 7 : TR_CH, stem ? (double)n * 6 * TR_CH : (double)rows, 0, st,
                                        dvar(nn, bn + "/moving_mean"), dvar(nn, bn + "/moving_variance"), nullptr, nullptr);
     k_tr_bn_apply<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(t->z[(size_t)L], st, dvar(nn, bn + "/gamma"), dvar(nn, bn + "/beta"), skip, t->a[(size_t)L], total, stem);
     AZ_CUDA(cudaGetLastError());
@@ -736,7 +790,7 @@ static int bn_backward(az_nn* nn, AzTrainState* t, int L, int n, const float* do
     float* st = t->d_stats + (size_t)L * 4 * TR_CH;
     const std::string bn = tr_bn_name(L);
     k_tr_stats<<<TR_STAT_CHUNKS, 256, 0, s>>>(t->z[(size_t)L], dout, t->a[(size_t)L], st, rows, 1, stem, t->d_part);
-    k_tr_stats_final<<<1, 256, 0, s>>>(t->d_part, stem ? 7 : TR_CH, stem ? (double)n * 6 * TR_CH : (double)rows, 1, st, nullptr, nullptr,
+    k_tr_stats_final<<<8, 256, 0, s>>>(t->d_part, stem ? 7 : TR_CH, stem ? (double)n * 6 * TR_CH : (double)rows, 1, st, nullptr, nullptr,
                                        gvar(nn, t, bn + "/gamma"), gvar(nn, t, bn + "/beta"));
     k_tr_bn_bwd<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(t->z[(size_t)L], dout, t->a[(size_t)L], st, dvar(nn, bn + "/gamma"), dz, total, stem);
     AZ_CUDA(cudaGetLastError());
@@ -748,7 +802,7 @@ static int conv_wgrad(az_nn* nn, AzTrainState* t, int L, int n, const float* in,
     if (t->precision == AZ_NN_BF16) {                          // dW[t*cin + ci][co] = im2col(in)^T . dz, K = board cells, split over K
         const int rows = n * 42, mp = (int)tr_mp(9 * cin), kp = (int)tr_kp(rows);
         const int splits = az_tg_splits(kp, 148 / (mp / 128) > TR_WG_SPLITS ? TR_WG_SPLITS : 148 / (mp / 128));
-        int rc = az_tg_im2col_t(in, rows, cin, mp, kp, t->d_colA, s); if (rc) return rc;
+        int rc = az_tg_im2col_t(in, rows, cin, mp, kp, t->d_src16, t->d_colA, s); if (rc) return rc;
         rc = az_tg_rows_t(dz, rows, kp, t->d_colB, s); if (rc) return rc;
         rc = az_tg_gemm(t->d_colA, t->d_colB, t->d_wpart, mp, kp, splits, s); if (rc) return rc;
         return az_tg_reduce(t->d_wpart, splits, mp, 9 * cin, gvar(nn, t, tr_conv_name(L) + "/kernel"), s);
@@ -814,11 +868,8 @@ static int train_step_dev(az_nn* nn, const float* d_x, const float* d_tp, const 
     rc = conv_wgrad(nn, t, 0, n, d_x, AZ_NN_IN_CH, G1, s); if (rc) return rc;
     // ---- Adam
     const float lr_t = (float)((double)TR_LR * sqrt(1.0 - (double)t->beta2_power) / (1.0 - (double)t->beta1_power));
-    for (const AzVar& v : nn->vars) {
-        if (is_moving(v.name)) continue;
-        k_tr_adam<<<(unsigned)((v.count + 255) / 256), 256, 0, s>>>(nn->d_blob + v.offset, t->d_grad + v.offset, t->d_m + v.offset, t->d_v + v.offset, v.count,
-                                                                     is_kernel(v.name) ? 2.0f * TR_L2 : 0.0f, lr_t);
-    }
+    const size_t np = nn->blob.size();
+    k_tr_adam<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(nn->d_blob, t->d_grad, t->d_m, t->d_v, np, t->d_kind, 2.0f * TR_L2, lr_t);
     AZ_CUDA(cudaGetLastError());
     t->beta1_power *= TR_BETA1; t->beta2_power *= TR_BETA2; t->steps++;
     t->host_slots_stale = true;

@@ -136,48 +136,126 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8])
     return o;
 }
 
-// im2col, chunked K-major: out[kc][r][8], k = t * cpad + ci (cpad = channels padded to a multiple of 8), value = src[nb(r,t)][ci] or 0.
-// src: fp32 [rows][cin].  Rows >= rows (up to Mp) and k >= 9 * cpad (up to Kp) are zero.  Thread = (kc, r).
-__global__ void __launch_bounds__(256) k_tg_im2col(const float* __restrict__ src, int rows, int cin, int cpad, int Mp, int Kp, __nv_bfloat16* __restrict__ out)
+// fp32 row-major [rows][cin] -> bf16 chunked [cpad/8][rows][8] (channels >= cin are zero).  One block = 32 rows x up to 32 chunks
+// through shared memory, so both the global reads (a row's channels) and the global writes (a chunk's rows) are contiguous.
+__global__ void __launch_bounds__(256) k_tg_chunk(const float* __restrict__ src, int rows, int cin, int cpad, __nv_bfloat16* __restrict__ out)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)(Kp / 8) * Mp;
-    if (i >= total) return;
-    const int kc = (int)(i / Mp), r = (int)(i - (size_t)kc * Mp);
-    const int k0 = kc * 8, t = k0 / cpad, ci0 = k0 - t * cpad;
-    float f[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-    if (r < rows && t < 9) {
-        const int b = r / 42, p = r - b * 42, q = c_gnb[p * 9 + t];
-        if (q >= 0) {
-            const float* s = src + ((size_t)b * 42 + q) * cin + ci0;
+    __shared__ uint4 tile[32][33];
+    const int chunks = cpad / 8, r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.x; j < 1024; j += 256) {
+        const int rl = j >> 5, cc = c0 + (j & 31), r = r0 + rl;
+        if (r < rows && cc < chunks) {
+            float f[8];
+            const float* s = src + (size_t)r * cin + cc * 8;
+            if ((cin & 7) == 0) {
+                const float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+            } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = ci0 + e < cin ? s[e] : 0.0f;
+                for (int e = 0; e < 8; ++e) f[e] = cc * 8 + e < cin ? s[e] : 0.0f;
+            }
+            tile[rl][j & 31] = pack8(f);
         }
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+    __syncthreads();
+    uint4* o = reinterpret_cast<uint4*>(out);
+    for (int j = threadIdx.x; j < 1024; j += 256) {
+        const int cl = j >> 5, rl = j & 31, cc = c0 + cl, r = r0 + rl;
+        if (r < rows && cc < chunks) o[(size_t)cc * rows + r] = tile[rl][cl];
+    }
+}
+
+// im2col, chunked K-major: out[kc][r][8], k = t * cpad + ci (cpad = channels padded to a multiple of 8), value = src[nb(r,t)][ci] or 0,
+// from the bf16 chunked copy of the source (k_tg_chunk): one 16-byte load and one 16-byte store per thread, both contiguous along r.
+// Rows >= rows (up to Mp) and k >= 9 * cpad (up to Kp) are zero.  grid = (Mp / 256, Kp / 8): block = 256 rows of one K chunk.
+__global__ void __launch_bounds__(256) k_tg_im2col(const __nv_bfloat16* __restrict__ src16, int rows, int cpad, int Mp, int Kp, __nv_bfloat16* __restrict__ out)
+{
+    const int r = blockIdx.x * 256 + threadIdx.x, kc = blockIdx.y;
+    if (r >= Mp) return;
+    const int chunks = cpad / 8, t = kc / chunks, cc = kc - t * chunks;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows && t < 9) {
+        const int b = r / 42, p = r - b * 42, y = p / 6, x = p - y * 6;
+        const int dy = t / 3 - 1, dx = t - (t / 3) * 3 - 1;
+        if ((unsigned)(y + dy) < 7u && (unsigned)(x + dx) < 6u)
+            v = reinterpret_cast<const uint4*>(src16)[(size_t)cc * rows + (size_t)(r + dy * 6 + dx)];
+    }
+    reinterpret_cast<uint4*>(out)[(size_t)kc * Mp + r] = v;
 }
 
 // transposed im2col for the weight gradient: out[rc][m][8], k = board cell row r = rc * 8 + e, m = t * cin + ci (no channel padding:
-// m indexes the gradient's rows directly), value = src[nb(r,t)][ci] or 0.  Thread = (rc, m); rows >= rows and m >= 9 * cin are zero.
-__global__ void __launch_bounds__(256) k_tg_im2col_t(const float* __restrict__ src, int rows, int cin, int Mp, int Kp, __nv_bfloat16* __restrict__ out)
+// m indexes the gradient's rows directly), value = src[nb(r,t)][ci] or 0, from the bf16 chunked copy of the source (k_tg_chunk).
+// Thread = (rc, t, channel chunk): eight 16-byte loads (rows r .. r+7 of the chunk, shifted by the tap), an 8 x 8 transpose in
+// registers, eight 16-byte stores to consecutive m.  Rows >= rows are zero; m >= 9 * cin (up to Mp) is left alone (those output rows
+// are dropped by the reduction).  grid = (ceil(9 * chunks / 96), Kp / 8), block = 96.
+__global__ void __launch_bounds__(96) k_tg_im2col_t(const __nv_bfloat16* __restrict__ src16, int rows, int cin, int cpad, int Mp, int Kp, __nv_bfloat16* __restrict__ out)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)(Kp / 8) * Mp;
-    if (i >= total) return;
-    const int rc = (int)(i / Mp), m = (int)(i - (size_t)rc * Mp);
-    float f[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
-    if (m < 9 * cin) {
-        const int t = m / cin, ci = m - t * cin;
+    const int chunks = cpad / 8, tc = blockIdx.x * 96 + threadIdx.x, rc = blockIdx.y;
+    if (tc >= 9 * chunks) return;
+    const int t = tc / chunks, cc = tc - t * chunks;
+    const int dy = t / 3 - 1, dx = t - (t / 3) * 3 - 1;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src16) + (size_t)cc * rows;
+    uint32_t w[8][4];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int r = rc * 8 + e;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows) {
+            const int b = r / 42, p = r - b * 42, y = p / 6, x = p - y * 6;
+            if ((unsigned)(y + dy) < 7u && (unsigned)(x + dx) < 6u) v = s4[r + dy * 6 + dx];
+        }
+        w[e][0] = v.x; w[e][1] = v.y; w[e][2] = v.z; w[e][3] = v.w;
+    }
+    uint4* o = reinterpret_cast<uint4*>(out) + (size_t)rc * Mp + (size_t)t * cin + cc * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (cc * 8 + j >= cin) break;
+        const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+        uint4 v;
+        v.x = __byte_perm(w[0][j >> 1], w[1][j >> 1], sel); v.y = __byte_perm(w[2][j >> 1], w[3][j >> 1], sel);
+        v.z = __byte_perm(w[4][j >> 1], w[5][j >> 1], sel); v.w = __byte_perm(w[6][j >> 1], w[7][j >> 1], sel);
+        o[j] = v;
+    }
+}
+
+// the same for cin a multiple of 8 (m = tc * 8 + j: a block's 96 x 8 output chunks are one contiguous 12 KB run): the transposed chunks
+// go through shared memory (XOR-swizzled against bank conflicts) so that every store instruction writes 512 contiguous bytes per warp
+__global__ void __launch_bounds__(96) k_tg_im2col_t8(const __nv_bfloat16* __restrict__ src16, int rows, int chunks, int Mp, int Kp, __nv_bfloat16* __restrict__ out)
+{
+    __shared__ uint4 stage[96 * 8];
+    const int tc = blockIdx.x * 96 + threadIdx.x, rc = blockIdx.y, total = 9 * chunks;
+    if (tc < total) {
+        const int t = tc / chunks, cc = tc - t * chunks;
+        const int dy = t / 3 - 1, dx = t - (t / 3) * 3 - 1;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src16) + (size_t)cc * rows;
+        uint32_t w[8][4];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int r = rc * 8 + e;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (r < rows) {
-                const int b = r / 42, p = r - b * 42, q = c_gnb[p * 9 + t];
-                if (q >= 0) f[e] = src[((size_t)b * 42 + q) * cin + ci];
+                const int b = r / 42, p = r - b * 42, y = p / 6, x = p - y * 6;
+                if ((unsigned)(y + dy) < 7u && (unsigned)(x + dx) < 6u) v = s4[r + dy * 6 + dx];
             }
+            w[e][0] = v.x; w[e][1] = v.y; w[e][2] = v.z; w[e][3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+            uint4 v;
+            v.x = __byte_perm(w[0][j >> 1], w[1][j >> 1], sel); v.y = __byte_perm(w[2][j >> 1], w[3][j >> 1], sel);
+            v.z = __byte_perm(w[4][j >> 1], w[5][j >> 1], sel); v.w = __byte_perm(w[6][j >> 1], w[7][j >> 1], sel);
+            stage[threadIdx.x * 8 + (j ^ (threadIdx.x & 7))] = v;
         }
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+    __syncthreads();
+    uint4* o = reinterpret_cast<uint4*>(out) + (size_t)rc * Mp + (size_t)blockIdx.x * 96 * 8;
+    const int valid = min(96, total - blockIdx.x * 96) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int q = k * 96 + threadIdx.x;
+        if (q < valid) o[q] = stage[(q & ~7) | ((q & 7) ^ ((q >> 3) & 7))];
+    }
 }
 
 // dz^T for the weight gradient: out[rc][co][8] = dz[rc * 8 + e][co]; thread = (rc, co)
@@ -271,15 +349,20 @@ int az_tg_splits(int Kp, int want)
 
 static unsigned blocks_for(size_t total) { return (unsigned)((total + 255) / 256); }
 
-int az_tg_im2col(const float* src, int rows, int cin, int cpad, int Mp, int Kp, __nv_bfloat16* out, cudaStream_t s)
+int az_tg_im2col(const float* src, int rows, int cin, int cpad, int Mp, int Kp, __nv_bfloat16* scratch16, __nv_bfloat16* out, cudaStream_t s)
 {
-    k_tg_im2col<<<blocks_for((size_t)(Kp / 8) * Mp), 256, 0, s>>>(src, rows, cin, cpad, Mp, Kp, out);
+    k_tg_chunk<<<dim3((unsigned)((rows + 31) / 32), (unsigned)((cpad / 8 + 31) / 32)), 256, 0, s>>>(src, rows, cin, cpad, scratch16);
+    k_tg_im2col<<<dim3((unsigned)((Mp + 255) / 256), (unsigned)(Kp / 8)), 256, 0, s>>>(scratch16, rows, cpad, Mp, Kp, out);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
-int az_tg_im2col_t(const float* src, int rows, int cin, int Mp, int Kp, __nv_bfloat16* out, cudaStream_t s)
+int az_tg_im2col_t(const float* src, int rows, int cin, int Mp, int Kp, __nv_bfloat16* scratch16, __nv_bfloat16* out, cudaStream_t s)
 {
-    k_tg_im2col_t<<<blocks_for((size_t)(Kp / 8) * Mp), 256, 0, s>>>(src, rows, cin, Mp, Kp, out);
+    const int cpad = (cin + 7) / 8 * 8;
+    k_tg_chunk<<<dim3((unsigned)((rows + 31) / 32), (unsigned)((cpad / 8 + 31) / 32)), 256, 0, s>>>(src, rows, cin, cpad, scratch16);
+    const dim3 grid((unsigned)((9 * (cpad / 8) + 95) / 96), (unsigned)(Kp / 8));
+    if (cin % 8 == 0) k_tg_im2col_t8<<<grid, 96, 0, s>>>(scratch16, rows, cpad / 8, Mp, Kp, out);
+    else k_tg_im2col_t<<<grid, 96, 0, s>>>(scratch16, rows, cin, cpad, Mp, Kp, out);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }

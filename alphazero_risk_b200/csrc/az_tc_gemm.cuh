@@ -9,7 +9,8 @@ int az_tg_splits(int Kp, int want);                           // largest K-split
 // C[split][Mp][256] = A[Mp][Kp] * B[256][Kp]^T over the split's K blocks; chunked K-major bf16 operands ([K/8][rows][8])
 int az_tg_gemm(const __nv_bfloat16* A, const __nv_bfloat16* B, float* C, int Mp, int Kp, int splits, cudaStream_t s);
 int az_tg_reduce(const float* part, int splits, int Mp, int rows_out, float* out, cudaStream_t s);
-int az_tg_im2col(const float* src, int rows, int cin, int cpad, int Mp, int Kp, __nv_bfloat16* out, cudaStream_t s);
-int az_tg_im2col_t(const float* src, int rows, int cin, int Mp, int Kp, __nv_bfloat16* out, cudaStream_t s);
+// scratch16: [cpad/8][rows][8] bf16 (the chunked copy of src the gather reads)
+int az_tg_im2col(const float* src, int rows, int cin, int cpad, int Mp, int Kp, __nv_bfloat16* scratch16, __nv_bfloat16* out, cudaStream_t s);
+int az_tg_im2col_t(const float* src, int rows, int cin, int Mp, int Kp, __nv_bfloat16* scratch16, __nv_bfloat16* out, cudaStream_t s);
 int az_tg_rows_t(const float* dz, int rows, int Kp, __nv_bfloat16* out, cudaStream_t s);
 int az_tg_weights(const float* w, int cin, int cpad, int Kp, int flip, __nv_bfloat16* out, cudaStream_t s);
