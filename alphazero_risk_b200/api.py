@@ -88,6 +88,7 @@ def lib():
         L.az_nn_train.argtypes = [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, vp, vp, vp]
         L.az_nn_train_get_grad.argtypes = [vp, C.c_char_p, vp, C.c_size_t]
         L.az_nn_train_precision.argtypes = [vp, C.c_int]
+        L.az_nn_copy_state.argtypes = [vp, vp, vp]
         L.az_nn_train_get_layer.argtypes = [vp, C.c_int, C.c_int, vp, C.c_size_t]
         L.az_nn_optimizer_get.argtypes = [vp, C.c_char_p, C.c_int, vp, C.c_size_t]
         L.az_nn_optimizer_powers.argtypes = [vp, f32, f32, u64]
@@ -318,6 +319,10 @@ class Net:
         lp, lv = np.zeros(epochs, np.float32), np.zeros(epochs, np.float32)
         check(self.L.az_nn_train(self.h, _ptr(r), r.shape[0], int(epochs), int(batch_size), int(seed), _ptr(lp), _ptr(lv), stream))
         return lp, lv
+
+    def copy_state_from(self, other, stream=None):
+        """variables + Adam slots + beta powers of `other` (same architecture, any device) into this network"""
+        check(self.L.az_nn_copy_state(self.h, other.h, stream))
 
     def train_precision(self, precision):
         """FP32 (default, parity path) or BF16 (contractions as tcgen05 GEMMs)"""

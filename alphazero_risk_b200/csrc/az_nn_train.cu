@@ -1014,6 +1014,50 @@ extern "C" int az_nn_optimizer_powers(az_nn* nn, float* beta1_power, float* beta
     return AZ_OK;
 }
 
+// ---------------------------------------------------------------- replica hand-off
+// AlphaZeroNNGroup::train (alphazero_gpu_cluster.cpp:221-231) trains the first network of a group, saves a temporary checkpoint and
+// loads it into the group's copies on the other GPUs.  Here the same state (every variable, both Adam slots of every trainable
+// variable, the beta powers — what the graph's Saver writes) goes from `src` to `dst` by peer copies over NVLink when it lives on
+// the device, by a host copy when it does not; no file in between.  dst must have the same number of residual blocks.
+extern "C" int az_nn_copy_state(az_nn* dst, az_nn* src, void* stream)
+{
+    AZ_REQUIRE(dst && src, "NULL argument");
+    AZ_REQUIRE(dst->blocks == src->blocks && dst->blob.size() == src->blob.size(), "networks differ in architecture");
+    if (dst == src) return AZ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t np = src->blob.size(), bytes = sizeof(float) * np;
+    AzTrainState* ts = src->train;
+    AzTrainState* td = ts ? train_state(dst) : dst->train;
+    AZ_REQUIRE(!ts || td, "out of host memory");
+    {
+        AzDeviceGuard guard(dst->device);
+        if (src->host_stale) {                                   // the device copy is the current one: peer copy, dst is then "ahead" too
+            if (!dst->d_blob) AZ_CUDA(cudaMalloc(&dst->d_blob, bytes));
+            AZ_CUDA(cudaMemcpyPeerAsync(dst->d_blob, dst->device, src->d_blob, src->device, bytes, s));
+            dst->host_stale = true; dst->finalized = false;
+        } else {
+            dst->blob = src->blob; dst->host_stale = false; dst->finalized = false;
+        }
+        if (ts) {
+            if (ts->slots_on_device) {
+                int rc = slots_to_device(dst, td); if (rc) return rc;          // allocates dst's slot buffers
+                AZ_CUDA(cudaMemcpyPeerAsync(td->d_m, dst->device, ts->d_m, src->device, bytes, s));
+                AZ_CUDA(cudaMemcpyPeerAsync(td->d_v, dst->device, ts->d_v, src->device, bytes, s));
+                td->host_slots_stale = true;
+            } else {
+                td->h_m = ts->h_m; td->h_v = ts->h_v; td->slots_on_device = false; td->host_slots_stale = false;
+            }
+            td->beta1_power = ts->beta1_power; td->beta2_power = ts->beta2_power; td->steps = ts->steps;
+        } else if (td) {                                         // src never trained: dst goes back to a fresh optimizer
+            std::fill(td->h_m.begin(), td->h_m.end(), 0.0f); std::fill(td->h_v.begin(), td->h_v.end(), 0.0f);
+            td->slots_on_device = false; td->host_slots_stale = false;
+            td->beta1_power = TR_BETA1; td->beta2_power = TR_BETA2; td->steps = 0;
+        }
+        AZ_CUDA(cudaStreamSynchronize(s));
+    }
+    return AZ_OK;
+}
+
 // ---------------------------------------------------------------- checkpoints
 // TF_OP_SAVE (alphazero_nn.cpp:207-214): every tensor of the graph's Saver
 extern "C" int az_nn_save_checkpoint(az_nn* nn, const char* prefix)

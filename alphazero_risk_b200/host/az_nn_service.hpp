@@ -184,6 +184,17 @@ public:
         for (int e = 0; e < epochs; ++e) printf("EPOCH %d\nLoss Policy / Value: %f / %f\n", e, lp[(size_t)e], lv[(size_t)e]);
     }
 
+    // contractions of the training step: AZ_NN_FP32 (default, parity path) or AZ_NN_BF16 (tcgen05 GEMMs, ~7x faster at batch 512)
+    void setTrainPrecision(int precision) { std::lock_guard<std::mutex> g(gpu_lock_); check(az_nn_train_precision(nn_, precision), "az_nn_train_precision"); }
+
+    // variables + optimizer state of `other` into this network (the group hand-off after train, alphazero_gpu_cluster.cpp:221-231)
+    void copyStateFrom(NNService& other)
+    {
+        if (&other == this) return;
+        std::scoped_lock g(gpu_lock_, other.gpu_lock_);
+        check(az_nn_copy_state(nn_, other.nn_, nullptr), "az_nn_copy_state");
+    }
+
     void registerThread()
     {
         { std::lock_guard<std::mutex> g(lock_); registered_++; queue_size_ = registered_ / 2 > 1 ? registered_ / 2 : 1; }
@@ -249,7 +260,13 @@ public:
     void add(std::shared_ptr<AlphaZeroNNIdT<In, Out, TrainData>> id) { ids_.push_back(std::move(id)); }
     void loadCheckpoint(std::string filePath) { for (auto& id : ids_) id->loadCheckpoint(filePath); }
     void saveCheckpoint(std::string filePath) { ids_[0]->saveCheckpoint(filePath); }
-    void train(const std::vector<TrainData>& d, int e) { ids_[0]->train(d, e); }
+    // alphazero_gpu_cluster.cpp:221-231: train the first copy, hand the result to the others (the reference goes through a
+    // temporary checkpoint file; here az_nn_copy_state moves variables + optimizer state device to device)
+    void train(const std::vector<TrainData>& d, int e)
+    {
+        ids_[0]->train(d, e);
+        for (size_t i = 1; i < ids_.size(); ++i) ids_[i]->service().copyStateFrom(ids_[0]->service());
+    }
     int size() { return (int)ids_.size(); }
     std::shared_ptr<AlphaZeroNNIdT<In, Out, TrainData>> getNN(int i) { return ids_[i]; }
 };

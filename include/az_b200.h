@@ -188,6 +188,10 @@ AZ_API int az_nn_train(az_nn* nn, const uint8_t* h_records, size_t n_records, in
 /* AZ_NN_FP32 (default, the parity path) or AZ_NN_BF16: the three convolution-shaped contractions of the step (forward, data gradient,
    weight gradient) as bf16 tcgen05 GEMMs with fp32 accumulation; everything else stays fp32 */
 AZ_API int az_nn_train_precision(az_nn* nn, int precision);
+/* AlphaZeroNNGroup::train's hand-off to the group's copies on the other GPUs (alphazero_gpu_cluster.cpp:221-231 saves a temporary
+   checkpoint and reloads it): every variable, the Adam slots and the beta powers from src to dst, device to device (peer copy over
+   NVLink) when the state lives on the device.  Same architecture required; synchronises `stream` */
+AZ_API int az_nn_copy_state(az_nn* dst, az_nn* src, void* stream);
 /* introspection for the parity tests: gradient of the total loss from the last step; Adam slots (which: 0 = m, 1 = v); beta powers */
 AZ_API int az_nn_train_get_grad(az_nn* nn, const char* name, float* h_out, size_t count);
 AZ_API int az_nn_train_get_layer(az_nn* nn, int layer, int which /* 0 = convolution output, 1 = activation */, float* h_out, size_t count);

@@ -81,6 +81,26 @@ int main()
     NNOutputData again = group2->getNN(0)->predict(probe);
     bool restored = again.value == after.value;
     for (int i = 0; i < 43; ++i) restored = restored && again.policy[i] == after.policy[i];
+    // the group hand-off after train (alphazero_gpu_cluster.cpp:221-231) without the temporary checkpoint file: a third network takes
+    // the trained state device to device; with >= 2 GPUs the group itself spans two devices and train() must leave both copies equal
+    auto group3 = cluster.initPlayerGroup("az3", "model_bin_V2_2.pb");
+    group3->getNN(0)->service().initRandom(99);
+    group3->getNN(0)->service().copyStateFrom(nn->service());
+    NNOutputData copied = group3->getNN(0)->predict(probe);
+    for (int i = 0; i < 43; ++i) restored = restored && copied.policy[i] == after.policy[i];
+    restored = restored && copied.value == after.value;
+    if (az_device_count() >= 2) {
+        Cluster two(AZ_NN_FP32, 2);
+        two.initGpus(2);
+        auto g2 = two.initPlayerGroup("pair", "model_bin_V2_2.pb");
+        g2->loadCheckpoint("/tmp/az_b200_test_ckpt/az1");
+        g2->getNN(0)->service().setBatchSize(32);
+        g2->train(data, 1);
+        NNOutputData p0 = g2->getNN(0)->predict(probe), p1 = g2->getNN(1)->predict(probe);
+        for (int i = 0; i < 43; ++i) restored = restored && p0.policy[i] == p1.policy[i];
+        restored = restored && p0.value == p1.value && p0.value != before.value;
+        printf("two-GPU group hand-off checked\n");
+    }
     if (bad || !moved || !restored) { printf("SERVICE_FAIL bad=%d moved=%d restored=%d\n", bad.load(), (int)moved, (int)restored); return 1; }
     printf("SERVICE_OK\n");
     return 0;

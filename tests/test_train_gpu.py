@@ -268,6 +268,46 @@ def test_train_on_sample_records_equals_manual_batches(api):
     a.close(); b.close()
 
 
+def test_replica_hand_off_copies_variables_and_optimizer_state(api):
+    """az_nn_copy_state = AlphaZeroNNGroup::train's save-temp-checkpoint + reload into the other copies (alphazero_gpu_cluster.cpp:221-231)
+    without the file: after the copy both networks predict the same, and one more identical step leaves weights and Adam slots equal bit
+    for bit (so the slots and beta powers travelled too).  With two GPUs the copy crosses devices."""
+    blocks, n = 2, 24
+    x, tp, tv = positions(n)
+    a = perturbed_net(api, blocks, 3)
+    for _ in range(2):
+        a.train_step(x, tp, tv)
+    devices = [0] + ([1] if api.lib().az_device_count() >= 2 else [])
+    for dev in devices:
+        b = api.Net(blocks=blocks, seed=99, device=dev)
+        b.train_step(x[:8], tp[:8], tv[:8])                      # b has its own (different) optimizer history to be overwritten
+        b.copy_state_from(a)
+        pa, va = a.forward(x, api.FP32)
+        pb, vb = b.forward(x, api.FP32)
+        assert (pa == pb).all() and (va == vb).all()
+        a2 = api.Net(blocks=blocks, seed=5)
+        a2.copy_state_from(a)                                    # a stays untouched for the next device: step a copy of it
+        la, lb = a2.train_step(x, tp, tv), b.train_step(x, tp, tv)
+        assert la == lb
+        wa, wb = a2.weights(), b.weights()
+        shapes = dict(a2.variables())
+        for name in shapes:
+            assert (wa[name] == wb[name]).all(), name
+        for name in no.trainable_names(blocks):
+            for which in (0, 1):
+                assert (a2.optimizer_slot(name, which, shapes[name]) == b.optimizer_slot(name, which, shapes[name])).all(), (name, which)
+        assert a2.optimizer_powers() == b.optimizer_powers()
+        a2.close(); b.close()
+    fresh, target = api.Net(blocks=blocks, seed=8), api.Net(blocks=blocks, seed=9)
+    target.train_step(x[:8], tp[:8], tv[:8])
+    target.copy_state_from(fresh)                                # a source that never trained resets the target's optimizer
+    assert target.optimizer_powers()[2] == 0 and (target.weights()["conv/kernel"] == fresh.weights()["conv/kernel"]).all()
+    other = api.Net(blocks=3, seed=1)
+    with pytest.raises(api.AzError):
+        other.copy_state_from(a)
+    a.close(); fresh.close(); target.close(); other.close()
+
+
 def test_bad_arguments(api):
     net = api.Net(blocks=1, seed=3)
     x, tp, tv = positions(4)
