@@ -117,6 +117,7 @@ def lib():
         L.az_env_script_turn.argtypes = [vp, vp, vp, vp]
         L.az_env_random_turn.argtypes = [vp, vp, vp]
         L.az_arena_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+        L.az_arena_create_versus.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
         L.az_arena_destroy.argtypes = [vp]
         L.az_arena_play.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(AzArenaResults), vp]
         L.az_selfplay_samples.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), vp]
@@ -405,7 +406,7 @@ class Checkpoint:
 
 
 EVAL_NN, EVAL_PSEUDO, EVAL_UNIFORM = 0, 1, 2
-OPPONENT_SCRIPT, OPPONENT_RANDOM = 1, 2
+OPPONENT_SCRIPT, OPPONENT_RANDOM, OPPONENT_ALPHAZERO = 1, 2, 3
 SCRIPT_INIT = 0x00ffffff
 
 
@@ -424,10 +425,14 @@ class AzArenaResults(C.Structure):
 class Arena:
     """`-m play` on the device: the Mcts handle's games as AlphaZero (player 0) vs a device-side opponent (player 1)"""
 
-    def __init__(self, mcts, opponent=OPPONENT_SCRIPT, mirror_games=True):
-        self.L, self.mcts = lib(), mcts
+    def __init__(self, mcts, opponent=OPPONENT_SCRIPT, mirror_games=True, opponent_mcts=None):
+        """opponent_mcts: a second Mcts over the same Env = AlphaZero vs AlphaZero (the trainer's comparison match, az_arena_create_versus)"""
+        self.L, self.mcts, self.opponent_mcts = lib(), mcts, opponent_mcts
         h = C.c_void_p()
-        check(self.L.az_arena_create(mcts.h, opponent, int(mirror_games), C.byref(h)))
+        if opponent_mcts is not None:
+            check(self.L.az_arena_create_versus(mcts.h, opponent_mcts.h, int(mirror_games), C.byref(h)))
+        else:
+            check(self.L.az_arena_create(mcts.h, opponent, int(mirror_games), C.byref(h)))
         self.h = h
 
     def close(self):

@@ -7,7 +7,7 @@
 #include "az_b200.h"
 
 enum { ARENA_COUNT = 0, ARENA_DRAW = 1, ARENA_WIN0 = 2, ARENA_WIN1 = 3, ARENA_WAS0 = 4, ARENA_WAS1 = 5, ARENA_OPP_TURNS = 6,
-       ARENA_CLAIMED = 7, ARENA_ACTIVE = 8, ARENA_N = 12 };
+       ARENA_CLAIMED = 7, ARENA_ACTIVE = 8, ARENA_TOMOVE0 = 9, ARENA_TOMOVE1 = 10, ARENA_N = 12 };
 
 struct ArenaDev {
     int n;
@@ -21,6 +21,9 @@ struct ArenaDev {
     uint8_t* active;            // [n]      slot still plays
     uint8_t* last_mover;        // [n]      side that moved last in the running game (0xff = nobody yet)
     uint8_t* extra_trim;        // [n]      the MCTS handle's pending trimNodes counter
+    uint8_t* extra_trim_opp;    // [n]      the same for the second searcher (AZ_OPPONENT_ALPHAZERO), else NULL
+    uint8_t* ended;             // [n]      game that ended in this advance call: 0 none, 1 / 2 = winner 0 / 1, 3 = draw (sample flush)
+    uint8_t* to_move;           // [n]      side whose searcher moves next in this slot (AZ_OPPONENT_ALPHAZERO; 0xff = slot is done)
     unsigned long long* res;    // [ARENA_N]
     unsigned long long total_games;
     int opponent, mirror;

@@ -350,12 +350,13 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_arena_advance(ArenaDev a, const u
     uint32_t player_start = a.player_start[gi];
     bool fresh = a.fresh[gi] != 0, active = true;
     uint32_t last = a.last_mover[gi];
-    unsigned trim = 0;
+    unsigned trim = 0, trim_opp = 0;
     for (int it = 0; it < 64; ++it) {
         const int st = az_game_status(c.g, rules);
         if (fresh || st != AZ_STATUS_RUNNING) {
             if (!fresh) {                                             // GameResults::addGame, game.cpp:193-213
                 atomicAdd(&a.res[ARENA_COUNT], 1ull);
+                a.ended[gi] = (uint8_t)(st == AZ_STATUS_DRAW ? 3 : 1 + st);       // Player::gameFinished -> trainStorage->updateValues
                 if (st == AZ_STATUS_DRAW) atomicAdd(&a.res[ARENA_DRAW], 1ull);
                 else {
                     atomicAdd(&a.res[ARENA_WIN0 + st], 1ull);
@@ -392,8 +393,14 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_arena_advance(ArenaDev a, const u
                 env_store(c, sm, a.start_state, a.n, gi);             // previousStartState
             }
             fresh = false;
-            trim = 2; last = 0xffu;                                   // Player::newGame: AlphaZeroPlayer clears its table
+            trim = 2; trim_opp = 2; last = 0xffu;                     // Player::newGame: AlphaZeroPlayer clears its table
             continue;
+        }
+        if (a.opponent == AZ_OPPONENT_ALPHAZERO) {                    // both sides search: hand the slot to the side to move
+            if (c.g.cur == 0u) { if (last != 0u && trim < 2) trim = 1; }          // AlphaZeroPlayer::takeTurn trims when its turn starts
+            else if (last != 1u && trim_opp < 2) trim_opp = 1;
+            last = c.g.cur;
+            break;
         }
         if (c.g.cur == 1u) {                                          // the opponent's whole turn
             uint32_t spw = a.script[(size_t)gi * 2 + 1];
@@ -414,6 +421,10 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_arena_advance(ArenaDev a, const u
     a.player_start[gi] = (uint8_t)player_start; a.fresh[gi] = 0; a.last_mover[gi] = (uint8_t)last;
     a.active[gi] = active ? 1 : 0;
     if (active) { a.extra_trim[gi] = (uint8_t)(a.extra_trim[gi] + trim); atomicAdd(&a.res[ARENA_ACTIVE], 1ull); }
+    if (a.opponent == AZ_OPPONENT_ALPHAZERO) {
+        a.to_move[gi] = active ? (uint8_t)c.g.cur : (uint8_t)0xff;
+        if (active) { a.extra_trim_opp[gi] = (uint8_t)(a.extra_trim_opp[gi] + trim_opp); atomicAdd(&a.res[ARENA_TOMOVE0 + c.g.cur], 1ull); }
+    }
 }
 
 // AoS Data image (state/state.h:86-105, g++ x86-64 layout) <-> device SoA

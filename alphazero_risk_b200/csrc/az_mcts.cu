@@ -60,6 +60,7 @@ struct MctsDev {
     float* nn_value;        // [K*n]
     uint32_t* root_state;   // env state [16][n]
     uint8_t* extra_trim;    // [n] trims to add before the next search (play-mode turn start / new game)
+    const uint8_t* side_sel; int side;   // arena with two searchers: only games with side_sel[game] == side take part in this search (NULL = all)
     uint32_t* out_visits; float* out_pi; float* out_q; float* out_p; uint8_t* out_move; float* out_value; uint32_t* out_sumn; int32_t* out_table; int8_t* out_status;
     unsigned long long* counters;
     // self-play sample recording (NNTrainData, alphazero_nn_data.h:112-121): per-game staging until the game ends
@@ -440,6 +441,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_begin(MctsDev m, int e
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int gi = blockIdx.x * MCTS_WARPS + warp;
     if (gi >= m.n) return;
+    if (m.side_sel && m.side_sel[gi] != (uint8_t)m.side) return;          // the other searcher's game: its table must not age
     uint32_t trims = 1u + (uint32_t)extra_all + (uint32_t)m.extra_trim[gi];
     uint32_t e = m.epoch[gi] + trims;
     for (uint32_t t = 0; t < (trims > 2 ? 2u : trims); ++t) {
@@ -464,6 +466,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_sim(MctsDev m, const u
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int gi = blockIdx.x * MCTS_WARPS + warp;
     if (gi >= m.n) return;
+    if (m.side_sel && m.side_sel[gi] != (uint8_t)m.side) return;
     WG w; wg_bind(w, s_w, warp);
     const uint32_t cur = m.epoch[gi] & 1u;
     for (int j = 0; j < m.K; ++j) expand_and_backup(m, j * m.n + gi, gi, cur, w, lane);
@@ -486,6 +489,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_finish(MctsDev m, cons
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int gi = blockIdx.x * MCTS_WARPS + warp;
     if (gi >= m.n) return;
+    if (m.side_sel && m.side_sel[gi] != (uint8_t)m.side) return;
     WG w; wg_bind(w, s_w, warp);
     const uint32_t cur = m.epoch[gi] & 1u;
     for (int j = 0; j < m.K; ++j) expand_and_backup(m, j * m.n + gi, gi, cur, w, lane);
@@ -583,6 +587,19 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_finish(MctsDev m, cons
         if (lane == 0) { m.out_move[gi] = AZ_NONE; m.out_value[gi] = 0.0f; m.out_sumn[gi] = 0; m.out_table[gi] = 0; }
     }
     if (m.out_status && lane == 0) m.out_status[gi] = (int8_t)status;
+}
+
+// arena: a game ended outside this searcher's own move (the opponent's turn, or the other searcher's move): Player::gameFinished ->
+// NNTrainDataStorage::updateValues for the samples this searcher staged during the game (alphazero_player.cpp:24-30)
+__global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_rec_end(MctsDev m, const uint8_t* __restrict__ ended)
+{
+    __shared__ uint8_t s_rec[MCTS_WARPS][272];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int gi = blockIdx.x * MCTS_WARPS + warp;
+    if (gi >= m.n) return;
+    const uint32_t e = ended[gi];
+    if (e == 0) return;
+    rec_flush(m, gi, e == 3 ? AZ_STATUS_DRAW : (int)e - 1, s_rec[warp], lane);
 }
 
 // ---------------------------------------------------------------- host side
@@ -852,6 +869,7 @@ int az_env_reset(az_env* e, uint64_t seed, void* stream);
 
 struct az_arena {
     az_mcts* mc = nullptr;
+    az_mcts* opp = nullptr;          // AZ_OPPONENT_ALPHAZERO: the searcher of player index 1
     ArenaDev a;
     std::vector<void*> allocs;
 };
@@ -879,9 +897,37 @@ extern "C" int az_arena_create(az_mcts* mc, int opponent, int mirror_games, az_a
     int rc = 0;
     rc |= aalloc(ar, &a.start_state, n * 16); rc |= aalloc(ar, &a.script, n * 2);
     rc |= aalloc(ar, &a.player_start, n); rc |= aalloc(ar, &a.fresh, n); rc |= aalloc(ar, &a.active, n); rc |= aalloc(ar, &a.last_mover, n);
+    rc |= aalloc(ar, &a.ended, n);
     rc |= aalloc(ar, &a.res, (size_t)ARENA_N);
     if (rc) { for (void* p : ar->allocs) cudaFree(p); delete ar; return AZ_ERR_CUDA; }
     a.state = mc->d.root_state; a.extra_trim = mc->d.extra_trim;
+    *out = ar;
+    return AZ_OK;
+}
+
+// AlphaZero vs AlphaZero (AlphaZeroTrainer::updateIfImprovement's comparison match): two searchers over one set of game states.
+// k_arena_advance hands every running slot to the side to move (to_move); each tick runs one search per side restricted to its
+// slots (MctsDev::side_sel), so a searcher's table ages exactly when its AlphaZeroPlayer would search.
+extern "C" int az_arena_create_versus(az_mcts* mc, az_mcts* opp, int mirror_games, az_arena** out)
+{
+    AZ_REQUIRE(mc && opp && out, "NULL argument");
+    AZ_REQUIRE(mc != opp, "the two searchers must be different handles (each AlphaZeroPlayer owns its table)");
+    AZ_REQUIRE(mc->env == opp->env, "both searchers must be built over the same env");
+    AzDeviceGuard guard(mc->device);
+    az_arena* ar = new (std::nothrow) az_arena();
+    AZ_REQUIRE(ar != nullptr, "out of host memory");
+    ar->mc = mc; ar->opp = opp;
+    ArenaDev& a = ar->a;
+    memset(&a, 0, sizeof a);
+    a.n = mc->d.n; a.opponent = AZ_OPPONENT_ALPHAZERO; a.mirror = mirror_games ? 1 : 0;
+    size_t n = (size_t)a.n;
+    int rc = 0;
+    rc |= aalloc(ar, &a.start_state, n * 16); rc |= aalloc(ar, &a.script, n * 2);
+    rc |= aalloc(ar, &a.player_start, n); rc |= aalloc(ar, &a.fresh, n); rc |= aalloc(ar, &a.active, n); rc |= aalloc(ar, &a.last_mover, n);
+    rc |= aalloc(ar, &a.to_move, n); rc |= aalloc(ar, &a.ended, n);
+    rc |= aalloc(ar, &a.res, (size_t)ARENA_N);
+    if (rc) { for (void* p : ar->allocs) cudaFree(p); delete ar; return AZ_ERR_CUDA; }
+    a.state = mc->d.root_state; a.extra_trim = mc->d.extra_trim; a.extra_trim_opp = opp->d.extra_trim;
     *out = ar;
     return AZ_OK;
 }
@@ -913,26 +959,53 @@ extern "C" int az_arena_play(az_arena* ar, uint64_t n_games, uint64_t seed, az_a
     AZ_CUDA(cudaMemsetAsync(a.active, 1, n, s)); AZ_CUDA(cudaMemsetAsync(a.last_mover, 0xff, n, s));
     AZ_CUDA(cudaMemsetAsync(a.res, 0, sizeof(unsigned long long) * ARENA_N, s));
     AZ_CUDA(cudaMemsetAsync(mc->d.counters, 0, sizeof(unsigned long long) * CNT_N, s));
+    az_mcts* opp = ar->opp;
+    if (mc->d.rec_out) AZ_CUDA(cudaMemsetAsync(mc->d.rec_len, 0, sizeof(uint32_t) * n, s));          // a match starts with nothing staged
+    if (opp && opp->d.rec_out) AZ_CUDA(cudaMemsetAsync(opp->d.rec_len, 0, sizeof(uint32_t) * n, s));
+    if (opp) {
+        AZ_CUDA(cudaMemsetAsync(opp->d.counters, 0, sizeof(unsigned long long) * CNT_N, s));
+        AZ_CUDA(cudaMemsetAsync(a.to_move, 0xff, n, s));
+    }
     AZ_CUDA(cudaStreamSynchronize(s));                                        // `init` goes out of scope below
-    unsigned long long active = 0;
+    unsigned long long act[3] = { 0, 0, 0 };                                  // ARENA_ACTIVE, ARENA_TOMOVE0, ARENA_TOMOVE1
     uint64_t ticks = 0;
     for (;;) {
-        AZ_CUDA(cudaMemsetAsync(a.res + ARENA_ACTIVE, 0, sizeof(unsigned long long), s));
+        AZ_CUDA(cudaMemsetAsync(a.res + ARENA_ACTIVE, 0, 3 * sizeof(unsigned long long), s));
+        const bool recording = mc->d.rec_out || (opp && opp->d.rec_out);
+        if (recording) AZ_CUDA(cudaMemsetAsync(a.ended, 0, n, s));
         rc = az_launch_arena_advance(a, az_env_rules(mc->env), s); if (rc) return rc;
-        AZ_CUDA(cudaMemcpyAsync(&active, a.res + ARENA_ACTIVE, sizeof active, cudaMemcpyDeviceToHost, s));
+        if (recording) {                                                      // games that ended: value targets for the staged samples
+            const int rgrid = (a.n + MCTS_WARPS - 1) / MCTS_WARPS;
+            if (mc->d.rec_out) k_mcts_rec_end<<<rgrid, MCTS_WARPS * 32, 0, s>>>(mc->d, a.ended);
+            if (opp && opp->d.rec_out) k_mcts_rec_end<<<rgrid, MCTS_WARPS * 32, 0, s>>>(opp->d, a.ended);
+            AZ_CUDA(cudaGetLastError());
+        }
+        AZ_CUDA(cudaMemcpyAsync(act, a.res + ARENA_ACTIVE, sizeof act, cudaMemcpyDeviceToHost, s));
         AZ_CUDA(cudaStreamSynchronize(s));
-        if (active == 0) break;
-        rc = search_once(mc, 0, 0, 1, 0, s); if (rc) return rc;               // one AlphaZero move on every slot that is waiting for one
+        if (act[0] == 0) break;
+        if (!opp) { rc = search_once(mc, 0, 0, 1, 0, s); if (rc) return rc; }   // one AlphaZero move on every slot that is waiting for one
+        else {
+            // one move of player 0's searcher on its slots, then one of player 1's on the others; a slot whose move passed the turn
+            // over waits for the next tick (k_arena_advance sets the turn-start trim first)
+            mc->d.side_sel = a.to_move; mc->d.side = 0; opp->d.side_sel = a.to_move; opp->d.side = 1;
+            if (act[1]) rc = search_once(mc, 0, 0, 1, 0, s);
+            if (!rc && act[2]) rc = search_once(opp, 0, 0, 1, 0, s);
+            mc->d.side_sel = nullptr; opp->d.side_sel = nullptr;
+            if (rc) return rc;
+        }
         ++ticks;
     }
-    unsigned long long r[ARENA_N], c[CNT_N];
+    unsigned long long r[ARENA_N], c[CNT_N], co[CNT_N];
+    memset(co, 0, sizeof co);
     AZ_CUDA(cudaMemcpyAsync(r, a.res, sizeof r, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaMemcpyAsync(c, mc->d.counters, sizeof c, cudaMemcpyDeviceToHost, s));
+    if (opp) AZ_CUDA(cudaMemcpyAsync(co, opp->d.counters, sizeof co, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaStreamSynchronize(s));
+    if (opp) r[ARENA_OPP_TURNS] = co[CNT_STEPS];
     h_out->count = r[ARENA_COUNT]; h_out->draw = r[ARENA_DRAW];
     h_out->win[0] = r[ARENA_WIN0]; h_out->win[1] = r[ARENA_WIN1];
     h_out->win_and_started[0] = r[ARENA_WAS0]; h_out->win_and_started[1] = r[ARENA_WAS1];
     h_out->opponent_turns = r[ARENA_OPP_TURNS]; h_out->az_moves = c[CNT_STEPS]; h_out->az_sims = c[CNT_SIMS]; h_out->az_evals = c[CNT_EVALS];
-    h_out->ticks = ticks; h_out->errors = c[CNT_POOL_OVERFLOW] + c[CNT_DEPTH_OVERFLOW] + c[CNT_ILLEGAL];
+    h_out->ticks = ticks; h_out->errors = c[CNT_POOL_OVERFLOW] + c[CNT_DEPTH_OVERFLOW] + c[CNT_ILLEGAL] + co[CNT_POOL_OVERFLOW] + co[CNT_DEPTH_OVERFLOW] + co[CNT_ILLEGAL];
     return AZ_OK;
 }

@@ -1,12 +1,15 @@
 // az_play.hpp — host-side C++ adapter for SURVEY.md §8b seam 2 / §8f N1: the reference's
 //     GameResults GameGroup::playGames(std::shared_ptr<PlayerGroup> pg1, std::shared_ptr<PlayerGroup> pg2, int games)
-// (/root/reference/src/risk_game/game/game.cpp:277-312) for the pairing executePlay sets up by default
-// (src/alphazero_risk.cpp:4-47: an AlphaZeroPlayerGroup against a ScriptPlayerGroup), played entirely on the device through the
-// az_arena_* entry points of libaz_b200.so instead of one std::thread per game.
+// (/root/reference/src/risk_game/game/game.cpp:277-312) for the pairings the reference sets up — executePlay's AlphaZeroPlayerGroup
+// against a ScriptPlayerGroup (src/alphazero_risk.cpp:4-47), the trainer's benchmark against a RandomPlayerGroup and its comparison
+// match of the new against the old model (alphazero_trainer.cpp:121-166) — played entirely on the device through the az_arena_*
+// entry points of libaz_b200.so instead of one std::thread per game.
 //
 //   azb200::DevicePlay play(settings);                       // settings: the SETTINGS fields the path reads, see PlaySettings
 //   play.loadCheckpoint(path);                               // AlphaZeroNNGroup::loadCheckpoint semantics (missing file => random init + save)
-//   GameResults gr = play.playGames<GameResults>(SETTINGS.COMPARE_GAMES);
+//   GameResults gr = play.playGames<GameResults>(SETTINGS.COMPARE_GAMES);            // vs ScriptPlayer (setOpponent: RandomPlayer)
+//   play.setOpponentNetwork(old.network());                  // player index 1 = a second AlphaZeroPlayer on `old`'s network
+//   GameResults cmp = play.playGames<GameResults>(SETTINGS.COMPARE_GAMES);           // isModelImproved(cmp) as in the trainer
 //
 // GameResultsT is the reference's own class (game/game.h:17-29: count, draw, players[i].win, players[i].winAndStartedGame); the
 // template keeps this header compilable without the reference tree (tests/host/test_play.cpp uses a mirror type).
@@ -51,20 +54,28 @@ public:
     DevicePlay(const DevicePlay&) = delete;
     DevicePlay& operator=(const DevicePlay&) = delete;
 
-    // AlphaZeroNN::loadCheckpoint, alphazero_nn.cpp:189-204: restore, or (missing file) keep the random init and save it.
-    // File format: the flat fp32 blob of az_nn_export_blob (TF checkpoint import is SURVEY §8f N4, not built).
+    // AlphaZeroNN::loadCheckpoint, alphazero_nn.cpp:189-204: restore the TensorFlow checkpoint bundle <path>.index +
+    // <path>.data-00000-of-00001, or (missing) keep the random init and save it (TF_OP_SAVE, :207-214)
     void loadCheckpoint(const std::string& path)
     {
-        const size_t count = az_nn_num_params(nn);
-        std::vector<float> blob(count);
-        std::ifstream in(path, std::ios::binary);
-        if (in && in.read(reinterpret_cast<char*>(blob.data()), (std::streamsize)(count * sizeof(float)))) {
-            ck(az_nn_import_blob(nn, blob.data(), count), "az_nn_import_blob");
-        } else {
-            ck(az_nn_export_blob(nn, blob.data(), count), "az_nn_export_blob");
-            std::ofstream out(path, std::ios::binary);
-            out.write(reinterpret_cast<const char*>(blob.data()), (std::streamsize)(count * sizeof(float)));
-        }
+        if (std::ifstream(path + ".index", std::ios::binary).good()) ck(az_nn_load_checkpoint(nn, path.c_str()), "az_nn_load_checkpoint");
+        else ck(az_nn_save_checkpoint(nn, path.c_str()), "az_nn_save_checkpoint");
+        release();                                            // the searcher re-packs the weights when it is rebuilt
+    }
+    az_nn* network() { return nn; }
+
+    // player index 1: AZ_OPPONENT_SCRIPT (default, ScriptPlayerGroup) or AZ_OPPONENT_RANDOM (RandomPlayerGroup, the trainer's benchmark)
+    void setOpponent(int kind)
+    {
+        if (kind != AZ_OPPONENT_SCRIPT && kind != AZ_OPPONENT_RANDOM) throw std::invalid_argument("azb200::DevicePlay: unknown opponent kind");
+        opponent = kind; opponent_nn = nullptr; release();
+    }
+    // player index 1 = a second AlphaZeroPlayer searching with `other` (not owned; same number of blocks not required): the
+    // trainer's comparison match GameGroup::playGames(trainAZPG, generateAZPG, COMPARE_GAMES), alphazero_trainer.cpp:147-166
+    void setOpponentNetwork(az_nn* other)
+    {
+        if (!other || other == nn) throw std::invalid_argument("azb200::DevicePlay: the opponent needs its own network");
+        opponent = AZ_OPPONENT_ALPHAZERO; opponent_nn = other; release();
     }
 
     // GameGroup::playGames(alphaZeroGroup, scriptGroup, games): 2 * floor(games / 2) games in mirror pairs
@@ -86,12 +97,17 @@ public:
         az_arena_results r;
         ck(az_arena_play(arena, (uint64_t)games, st.seed, &r, nullptr), "az_arena_play");
         if (r.errors) throw std::runtime_error("azb200::DevicePlay: MCTS node pool overflow");
+        last = r;
         return r;
     }
+
+    az_arena_results last{};          // counters of the last match (moves, simulations, ticks)
 
 private:
     PlaySettings st;
     az_nn* nn = nullptr; az_env* env = nullptr; az_mcts* mcts = nullptr; az_arena* arena = nullptr;
+    az_nn* opponent_nn = nullptr; az_mcts* opponent_mcts = nullptr;
+    int opponent = AZ_OPPONENT_SCRIPT;
     int n_slots = 0;
 
     static void ck(int rc, const char* what) { if (rc != AZ_OK) throw std::runtime_error(std::string(what) + ": " + az_last_error()); }
@@ -105,15 +121,19 @@ private:
         r.max_game_rounds = st.MAX_GAME_ROUNDS; r.min_unit_move = st.MIN_UNIT_MOVE;
         ck(az_env_create(slots, &r, st.device, 0, &env), "az_env_create");
         ck(az_mcts_create(env, nn, AZ_EVAL_NN, st.precision, &mcts), "az_mcts_create");
-        ck(az_arena_create(mcts, AZ_OPPONENT_SCRIPT, st.MIRROR_GAMES ? 1 : 0, &arena), "az_arena_create");
+        if (opponent == AZ_OPPONENT_ALPHAZERO) {
+            ck(az_mcts_create(env, opponent_nn, AZ_EVAL_NN, st.precision, &opponent_mcts), "az_mcts_create");
+            ck(az_arena_create_versus(mcts, opponent_mcts, st.MIRROR_GAMES ? 1 : 0, &arena), "az_arena_create_versus");
+        } else ck(az_arena_create(mcts, opponent, st.MIRROR_GAMES ? 1 : 0, &arena), "az_arena_create");
         n_slots = slots;
     }
     void release()
     {
         if (arena) az_arena_destroy(arena);
+        if (opponent_mcts) az_mcts_destroy(opponent_mcts);
         if (mcts) az_mcts_destroy(mcts);
         if (env) az_env_destroy(env);
-        arena = nullptr; mcts = nullptr; env = nullptr; n_slots = 0;
+        arena = nullptr; mcts = nullptr; opponent_mcts = nullptr; env = nullptr; n_slots = 0;
     }
 };
 

@@ -272,6 +272,7 @@ AZ_API int az_mcts_counters(az_mcts* mcts, az_counters* h_out, uint64_t* h_error
    (Game::newGame, game.cpp:170-191); results are GameResults (game/game.h:17-29). */
 #define AZ_OPPONENT_SCRIPT 1   /* ScriptPlayer, player/script/script_player.cpp:162-227, on the device */
 #define AZ_OPPONENT_RANDOM 2   /* RandomPlayer, player/random/random_player.cpp:22-111, on the device */
+#define AZ_OPPONENT_ALPHAZERO 3   /* a second AlphaZeroPlayer with its own network and search tables (az_arena_create_versus) */
 typedef struct az_arena az_arena;
 typedef struct az_arena_results {
     uint64_t count;               /* GameResults::count */
@@ -281,6 +282,11 @@ typedef struct az_arena_results {
     uint64_t az_moves, az_sims, az_evals, opponent_turns, ticks, errors;
 } az_arena_results;
 AZ_API int az_arena_create(az_mcts* mcts, int opponent, int mirror_games, az_arena** out);
+/* AlphaZero vs AlphaZero: the trainer's comparison match between the new and the old model (AlphaZeroTrainer::updateIfImprovement,
+   alphazero_trainer.cpp:147-166: GameGroup::playGames(trainAZPG, generateAZPG, COMPARE_GAMES)).  Player index 0 is searched by
+   `mcts`, player index 1 by `opponent_mcts`; both handles must be built over the SAME env (they share the game states) and keep
+   separate tables, networks and evaluators.  In the results az_* count player 0's moves, opponent_turns counts player 1's MOVES. */
+AZ_API int az_arena_create_versus(az_mcts* mcts, az_mcts* opponent_mcts, int mirror_games, az_arena** out);
 AZ_API int az_arena_destroy(az_arena* arena);
 /* plays 2 * floor(n_games / 2) games (pairs, like the reference) over the env's slots; seed fixes the Philox contract */
 AZ_API int az_arena_play(az_arena* arena, uint64_t n_games, uint64_t seed, az_arena_results* h_out, void* stream);

@@ -18,13 +18,25 @@ int main()
         return 1;
     }
     azb200::DevicePlay p(s);
-    p.loadCheckpoint("/tmp/az_b200_play_ckpt.bin");
+    remove("/tmp/az_b200_play_ckpt.index"); remove("/tmp/az_b200_play_ckpt.data-00000-of-00001");
+    p.loadCheckpoint("/tmp/az_b200_play_ckpt");            // missing: random init kept and saved as a TensorFlow checkpoint bundle
     GameResults a = p.playGames<GameResults>(41);          // odd request: 40 games, like Counter::hasNext(2)
     GameResults b = p.playGames<GameResults>(41);          // same seed, same weights: the match is reproducible
     bool ok = a.count == 40 && a.draw + a.players[0].win + a.players[1].win == 40 &&
               a.players[0].winAndStartedGame <= a.players[0].win && a.players[1].winAndStartedGame <= a.players[1].win &&
               b.count == a.count && b.draw == a.draw && b.players[0].win == a.players[0].win && b.players[1].win == a.players[1].win;
-    printf("%s count=%d draw=%d az=%d/%d script=%d/%d\n", ok ? "PLAY_OK" : "PLAY_FAIL", a.count, a.draw, a.players[0].win,
-           a.players[0].winAndStartedGame, a.players[1].win, a.players[1].winAndStartedGame);
+    // the trainer's comparison match: a second DevicePlay holds the "old" model (here the same checkpoint), player index 1 searches
+    // with its network and its own tables
+    azb200::DevicePlay old(s);
+    old.loadCheckpoint("/tmp/az_b200_play_ckpt");
+    p.setOpponentNetwork(old.network());
+    GameResults c = p.playGames<GameResults>(12);
+    ok = ok && c.count == 12 && c.draw + c.players[0].win + c.players[1].win == 12 && p.last.opponent_turns > 0 && p.last.az_moves > 0;
+    p.setOpponent(AZ_OPPONENT_RANDOM);                     // the trainer's benchmark opponent
+    GameResults d = p.playGames<GameResults>(6);
+    ok = ok && d.count == 6;
+    printf("%s count=%d draw=%d az=%d/%d script=%d/%d | new vs old %d/%d %d/%d draw %d | vs random az %d of %d\n", ok ? "PLAY_OK" : "PLAY_FAIL",
+           a.count, a.draw, a.players[0].win, a.players[0].winAndStartedGame, a.players[1].win, a.players[1].winAndStartedGame,
+           c.players[0].win, c.players[0].winAndStartedGame, c.players[1].win, c.players[1].winAndStartedGame, c.draw, d.players[0].win, d.count);
     return ok ? 0 : 1;
 }

@@ -70,13 +70,34 @@ def test_random_vs_random_lockstep(api):
     env.close()
 
 
+def records_of(staged, status, rules):
+    """the 265-byte records of one game's staged (state, pi) pairs once the game ended with `status` (NNTrainDataStorage::updateValues)"""
+    out = []
+    for st, pi in staged:
+        o2 = po.OracleGame(rules)
+        o2.s = st
+        out.append(o2.sample_record(pi, status))
+    return np.stack(out).tobytes()
+
+
+def match_record_stream(recs, expected):
+    """every game's records are contiguous in the device queue; games arrive in a data-dependent order"""
+    assert sum(len(e) for e in expected) == recs.size
+    blob, left, pos = recs.tobytes(), sorted(expected, key=len, reverse=True), 0
+    while pos < len(blob):
+        hit = [e for e in left if blob.startswith(e, pos)]
+        assert hit, "record stream at byte %d matches no expected game" % pos
+        left.remove(hit[0]); pos += len(hit[0])
+    assert not left
+
+
 def oracle_pair(slot_game, sims, ply0=0, opponent="script"):
     """one claimed pair on one slot, replayed on the oracle: AlphaZero (player 0, play mode, pseudo evaluator) vs Script (player 1),
     fresh deal then the mirror game (Game::newGame, game/game.cpp:170-191); returns GameResults-style tallies, the final Data
     image and the ply counter"""
     rules = po.default_rules(mcts_simulations=sims, threads_per_mcts=1)
     o, tree, sp = po.OracleGame(rules), po.OracleMcts(rules, "pseudo"), po.new_script()
-    res = dict(count=0, draw=0, win=[0, 0], was=[0, 0], az_moves=0, opp_turns=0)
+    res = dict(count=0, draw=0, win=[0, 0], was=[0, 0], az_moves=0, opp_turns=0, samples=[])
     ply = ply0
     start = None
     for player_start in (0, 1):
@@ -88,7 +109,7 @@ def oracle_pair(slot_game, sims, ply0=0, opponent="script"):
             o.invert_players()
             o.s.cur = 1
         tree.clear()
-        last = None
+        last, staged = None, []
         while o.status() == -1:
             if o.s.cur == 1:
                 assert (o.script_turn(sp, SEED, slot_game, ply) if opponent == "script" else o.random_turn(SEED, slot_game, ply)) == 0
@@ -98,12 +119,15 @@ def oracle_pair(slot_game, sims, ply0=0, opponent="script"):
                 if last != 0:
                     tree.trim()            # AlphaZeroPlayer::takeTurn: trimNodes when its turn starts
                 a = tree.search(o, SEED, slot_game, ply)
+                staged.append((po.RoState.from_buffer_copy(o.s), a["pi"].copy()))      # AlphaZeroPlayer::takeTurn pushes before the move
                 mv = tree.pick(a["pi"], False, SEED, slot_game, ply)
                 assert o.move(mv, SEED, slot_game, ply) == 0
                 res["az_moves"] += 1
                 last = 0
             ply += 1
         st = o.status()
+        if staged:
+            res["samples"].append(records_of(staged, st, rules))
         res["count"] += 1
         if st == -2:
             res["draw"] += 1
@@ -120,12 +144,17 @@ def test_arena_one_pair_per_slot_matches_oracle(api, opponent):
     env = api.Env(n, rules=api.default_rules(mcts_simulations=sims, threads_per_mcts=1), first_game_id=first)
     mc = api.Mcts(env, evaluator=api.EVAL_PSEUDO)
     arena = api.Arena(mc, api.OPPONENT_SCRIPT if opponent == "script" else api.OPPONENT_RANDOM, mirror_games=True)
+    mc.record(capacity_samples=n * 2 * 700, max_moves_per_game=1024)      # playGames(pg1, pg2, games, trainStorage): AlphaZero's samples
     r = arena.play(2 * n, SEED)
     assert r["errors"] == 0 and r["count"] == 2 * n
     dev = env.export_aos()
+    recs, dropped = mc.samples()
+    assert dropped == 0
     tot = dict(count=0, draw=0, win=[0, 0], was=[0, 0], az_moves=0, opp_turns=0)
+    expected = []
     for g in range(n):
         res, data, _ = oracle_pair(first + g, sims, opponent=opponent)
+        expected += res["samples"]
         assert (dev[g] == data).all(), "slot %d: final position differs from the oracle replay" % g
         for k in ("count", "draw", "az_moves", "opp_turns"):
             tot[k] += res[k]
@@ -133,7 +162,95 @@ def test_arena_one_pair_per_slot_matches_oracle(api, opponent):
             tot["win"][i] += res["win"][i]; tot["was"][i] += res["was"][i]
     assert (r["count"], r["draw"], r["win"], r["win_and_started"]) == (tot["count"], tot["draw"], tot["win"], tot["was"])
     assert r["az_moves"] == tot["az_moves"] and r["opponent_turns"] == tot["opp_turns"] and r["az_sims"] == tot["az_moves"] * sims
+    # games that end on the opponent's turn are flushed by the arena (Player::gameFinished), the others by the searcher itself
+    match_record_stream(recs, expected)
     arena.close(); mc.close(); env.close()
+
+
+def oracle_versus_pair(slot_game, sims, evaluators, K=1):
+    """one claimed pair on one slot with an AlphaZeroPlayer on each side (GameGroup::playGames(trainAZPG, generateAZPG, ...),
+    alphazero_trainer.cpp:147-166), replayed on the oracle: each side owns a search table (cleared at a new game, trimmed when its
+    turn starts), play mode (argmax) on both sides"""
+    rules = po.default_rules(mcts_simulations=sims, threads_per_mcts=1)
+    o = po.OracleGame(rules)
+    trees = [po.OracleMcts(rules, evaluators[0]), po.OracleMcts(rules, evaluators[1])]
+    res = dict(count=0, draw=0, win=[0, 0], was=[0, 0], moves=[0, 0], samples=[[], []])
+    ply, start = 0, None
+    for player_start in (0, 1):
+        if player_start == 0:
+            o.new_game(SEED, slot_game, ply)
+            start = po.RoState.from_buffer_copy(o.s)
+        else:
+            o.s = po.RoState.from_buffer_copy(start)
+            o.invert_players()
+            o.s.cur = 1
+        for t in trees:
+            t.clear()
+        last, staged = None, [[], []]
+        while o.status() == -1:
+            side = int(o.s.cur)
+            if last != side:
+                trees[side].trim()
+            a = trees[side].search(o, SEED, slot_game, ply, lockstep=K)
+            staged[side].append((po.RoState.from_buffer_copy(o.s), a["pi"].copy()))
+            mv = trees[side].pick(a["pi"], False, SEED, slot_game, ply)
+            assert o.move(mv, SEED, slot_game, ply) == 0
+            res["moves"][side] += 1
+            last = side
+            ply += 1
+        st = o.status()
+        for side in (0, 1):
+            if staged[side]:
+                res["samples"][side].append(records_of(staged[side], st, rules))
+        res["count"] += 1
+        if st == -2:
+            res["draw"] += 1
+        else:
+            res["win"][st] += 1
+            res["was"][st] += int(st == player_start)
+    return res, o.data()
+
+
+@pytest.mark.parametrize("n,first,sims,K,evaluators", [(6, 300, 8, 1, ("pseudo", "uniform")), (5, 17, 6, 2, ("uniform", "pseudo")),
+                                                         (4, 950, 8, 1, ("pseudo", "pseudo"))])
+def test_arena_alphazero_vs_alphazero_matches_oracle(api, n, first, sims, K, evaluators):
+    """the trainer's comparison match on the device: two searchers (own tables, own evaluators) over one set of game states; every slot
+    plays one mirror pair, so final positions, tallies and per-side move counts must equal the oracle replay bit for bit"""
+    kinds = dict(pseudo=api.EVAL_PSEUDO, uniform=api.EVAL_UNIFORM)
+    env = api.Env(n, rules=api.default_rules(mcts_simulations=sims, threads_per_mcts=1, concurrent_descents=K), first_game_id=first)
+    mc0, mc1 = api.Mcts(env, evaluator=kinds[evaluators[0]]), api.Mcts(env, evaluator=kinds[evaluators[1]])
+    arena = api.Arena(mc0, mirror_games=True, opponent_mcts=mc1)
+    for mc in (mc0, mc1):                              # INCLUDE_COMPARE_GAMES_TRAIN_SAMPLES: both players collect their samples
+        mc.record(capacity_samples=n * 2 * 700, max_moves_per_game=1024)
+    r = arena.play(2 * n, SEED)
+    assert r["errors"] == 0 and r["count"] == 2 * n
+    dev = env.export_aos()
+    got = [mc0.samples(), mc1.samples()]
+    tot = dict(count=0, draw=0, win=[0, 0], was=[0, 0], moves=[0, 0])
+    expected = [[], []]
+    for g in range(n):
+        res, data = oracle_versus_pair(first + g, sims, evaluators, K)
+        for side in (0, 1):
+            expected[side] += res["samples"][side]
+        assert (dev[g] == data).all(), "slot %d: final position differs from the oracle replay" % g
+        tot["count"] += res["count"]; tot["draw"] += res["draw"]
+        for i in range(2):
+            tot["win"][i] += res["win"][i]; tot["was"][i] += res["was"][i]; tot["moves"][i] += res["moves"][i]
+    assert (r["count"], r["draw"], r["win"], r["win_and_started"]) == (tot["count"], tot["draw"], tot["win"], tot["was"])
+    assert r["az_moves"] == tot["moves"][0] and r["opponent_turns"] == tot["moves"][1] and r["az_sims"] == tot["moves"][0] * sims
+    for side in (0, 1):
+        assert got[side][1] == 0
+        match_record_stream(got[side][0], expected[side])
+    # the searchers are usable on their own again afterwards (the side selection is lifted)
+    env.reset(SEED)
+    assert mc0.search(pick_mode=api.PICK_ARGMAX, apply_move=False)["N"].sum() > 0
+    other = api.Env(n, rules=api.default_rules(mcts_simulations=sims, threads_per_mcts=1), first_game_id=first)
+    mc2 = api.Mcts(other, evaluator=api.EVAL_UNIFORM)
+    with pytest.raises(api.AzError):
+        api.Arena(mc0, opponent_mcts=mc2)              # different env
+    with pytest.raises(api.AzError):
+        api.Arena(mc0, opponent_mcts=mc0)              # the same handle twice
+    arena.close(); mc0.close(); mc1.close(); mc2.close(); other.close(); env.close()
 
 
 def test_arena_claims_pairs_like_the_counter(api):
