@@ -718,6 +718,8 @@ static int evaluate_leaves(az_mcts* mc, cudaStream_t s)
 static int search_once(az_mcts* mc, int extra_all, int pick_mode, int apply_move, int auto_reset, cudaStream_t s)
 {
     MctsDev& d = mc->d;
+    // the network may have been trained, restored or overwritten since the last search: fold + pack the current weights first
+    if (mc->evaluator == EVAL_NN && !mc->nn->finalized) { int frc = az_nn_finalize(mc->nn); if (frc) return frc; }
     d.seed = az_env_seed(mc->env); d.first_game = az_env_first_game(mc->env);
     const uint64_t* tab = az_device_tables();
     int grid = (d.n + MCTS_WARPS - 1) / MCTS_WARPS, sims = az_mcts_simulations(mc);
