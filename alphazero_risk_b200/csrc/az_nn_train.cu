@@ -606,6 +606,12 @@ __global__ void __launch_bounds__(256) k_tr_adam(float* __restrict__ w, float* _
     w[i] = w[i] - (mi * lr_t) / (sqrtf(vi) + TR_ADAM_EPS);
 }
 
+// epoch means without a host round trip per batch: the two batch losses are added, in batch order, to double accumulators
+__global__ void k_tr_loss_accum(const float* __restrict__ loss2, double* __restrict__ acc2)
+{
+    if (threadIdx.x < 2) acc2[threadIdx.x] += (double)loss2[threadIdx.x];
+}
+
 // NNInputData images (88 bytes, alphazero_nn_data.h:73-101) -> input planes [n][7][6][13] (setInStateTensor, alphazero_nn.cpp:31-67);
 // sample record = 1 + 88 + 4 + 43 * 4 bytes (alphazero_nn_data.cpp:115-138): also unpacks the value and policy targets
 __global__ void __launch_bounds__(64) k_tr_unpack_samples(const uint8_t* __restrict__ rec, const uint32_t* __restrict__ order, int n, float* __restrict__ x,
@@ -915,9 +921,11 @@ extern "C" int az_nn_train(az_nn* nn, const uint8_t* h_records, size_t n_records
     AzTrainState* t = train_state(nn);
     AZ_REQUIRE(t != nullptr, "out of host memory");
     int rc = train_reserve(nn, t, batch_size); if (rc) return rc;
-    uint8_t* d_rec = nullptr; uint32_t* d_order = nullptr;
+    uint8_t* d_rec = nullptr; uint32_t* d_order = nullptr; double* d_acc = nullptr;
     AZ_CUDA(cudaMalloc(&d_rec, n_records * (size_t)AZ_SAMPLE_BYTES));
-    if (cudaMalloc(&d_order, sizeof(uint32_t) * n_records) != cudaSuccess) { cudaFree(d_rec); az_set_error("out of device memory"); return AZ_ERR_CUDA; }
+    if (cudaMalloc(&d_order, sizeof(uint32_t) * n_records) != cudaSuccess || cudaMalloc(&d_acc, 2 * sizeof(double)) != cudaSuccess) {
+        cudaFree(d_rec); cudaFree(d_order); az_set_error("out of device memory"); return AZ_ERR_CUDA;
+    }
     cudaError_t ce = cudaMemcpyAsync(d_rec, h_records, n_records * (size_t)AZ_SAMPLE_BYTES, cudaMemcpyHostToDevice, s);
     std::vector<uint32_t> order(n_records);
     for (size_t i = 0; i < n_records; ++i) order[i] = (uint32_t)i;
@@ -932,17 +940,21 @@ extern "C" int az_nn_train(az_nn* nn, const uint8_t* h_records, size_t n_records
         }
         ce = cudaMemcpyAsync(d_order, order.data(), sizeof(uint32_t) * n_records, cudaMemcpyHostToDevice, s);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-        double lp = 0.0, lv = 0.0;
+        // the batches of an epoch are enqueued back to back; the losses are accumulated on the device and read once per epoch
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(d_acc, 0, 2 * sizeof(double), s);
         for (size_t b = 0; b < batches && ce == cudaSuccess && rc == AZ_OK; ++b) {
             k_tr_unpack_samples<<<(unsigned)batch_size, 64, 0, s>>>(d_rec, d_order + b * (size_t)batch_size, batch_size, t->d_x, t->d_tp, t->d_tv);
-            float loss[2];
-            rc = train_step_dev(nn, t->d_x, t->d_tp, t->d_tv, batch_size, loss, s);
-            lp += loss[0]; lv += loss[1];
+            rc = train_step_dev(nn, t->d_x, t->d_tp, t->d_tv, batch_size, nullptr, s);
+            if (rc == AZ_OK) k_tr_loss_accum<<<1, 32, 0, s>>>(t->d_loss, d_acc);
         }
-        if (h_epoch_loss_policy) h_epoch_loss_policy[e] = (float)(lp / (double)batches);
-        if (h_epoch_loss_value) h_epoch_loss_value[e] = (float)(lv / (double)batches);
+        double acc[2] = { 0.0, 0.0 };
+        if (ce == cudaSuccess && rc == AZ_OK) ce = cudaMemcpyAsync(acc, d_acc, sizeof acc, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (h_epoch_loss_policy) h_epoch_loss_policy[e] = (float)(acc[0] / (double)batches);
+        if (h_epoch_loss_value) h_epoch_loss_value[e] = (float)(acc[1] / (double)batches);
     }
-    cudaFree(d_rec); cudaFree(d_order);
+    cudaStreamSynchronize(s);
+    cudaFree(d_rec); cudaFree(d_order); cudaFree(d_acc);
     if (ce != cudaSuccess) { az_set_error("az_nn_train: %s", cudaGetErrorString(ce)); return AZ_ERR_CUDA; }
     return rc;
 }

@@ -376,10 +376,33 @@ def run_train(args, api, torch, local):
         e1.record(stream); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         out[mode] = dict(samples_per_sec=n / (ms * 1e-3), ms_per_step=ms, achieved_tflops=flops / (ms * 1e-3) / 1e12, last_losses=list(loss))
+    # AlphaZeroNN::train itself (az_nn_train: shuffled epochs over packed sample records, batches enqueued back to back): records from
+    # a short device self-play with the uniform evaluator (real positions, visit-count policies, game outcomes)
+    epoch = None
+    try:
+        env = api.Env(512, rules=api.default_rules(mcts_simulations=2, threads_per_mcts=1), device=local)
+        env.reset(0x5EED0001)
+        mc = api.Mcts(env, evaluator=api.EVAL_UNIFORM)
+        mc.record(capacity_samples=600000, max_moves_per_game=1024)
+        mc.selfplay(700)
+        recs, _ = mc.samples()
+        mc.close(); env.close()
+        recs = recs[:(min(len(recs), 32 * n) // n) * n]
+        if len(recs) >= 4 * n:
+            net.train(recs, 1, n, 1)                           # warm-up epoch
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lp, lv = net.train(recs, 2, n, 2)
+            dt = time.perf_counter() - t0
+            epoch = dict(samples_per_sec=2 * len(recs) / dt, ms_per_batch=dt * 1e3 / (2 * len(recs) // n), records=int(len(recs)), epochs=2,
+                         losses_policy=[float(v) for v in lp], losses_value=[float(v) for v in lv],
+                         note="az_nn_train wall time: record upload, per-epoch shuffle upload, every batch of every epoch, one loss read per epoch")
+    except Exception as e:                                      # the step numbers above stand on their own
+        epoch = dict(error=str(e))
     net.close()
     best = out["bf16_tcgen05"]
     return dict(metric="train_samples_per_sec", value=best["samples_per_sec"], unit="samples/s", ms_per_step=best["ms_per_step"], batch=n,
-                blocks=args.blocks, modes=out,
+                blocks=args.blocks, modes=out, epoch=epoch,
                 config={"workload": "one az_nn_train_step per step: batch %d, %d-block graph; value = the bf16 tcgen05 mode (the three "
                                     "contractions as tensor-core GEMMs), modes.fp32 = the fp32 parity path; host batch copied in and losses "
                                     "copied out inside the timed region" % (n, args.blocks)})
