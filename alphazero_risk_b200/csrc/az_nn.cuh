@@ -5,6 +5,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "az_b200.h"
@@ -54,3 +55,14 @@ int az_nn_tc_prepare(az_nn* nn);            // fold BN, pack bf16 weight tiles; 
 void az_nn_tc_release(az_nn* nn);
 // x: fp32 [n][7][6][13] (or NULL when env_state is given: encode fused into the stem)
 int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, int n, float* d_policy, float* d_value, cudaStream_t s);
+
+// raw 3x3 convolution of the training step on the tower kernel (az_nn_tc.cu): fp32 [n * 42][256] in, fp32 HWIO device weights
+// [9][256][256] (flip = 1: the data gradient's kernel), fp32 [n * 42][256] out; bf16 operands, fp32 accumulation
+struct AzTcConvScratch {
+    int cap_boards = 0, r_alloc = 0, max_pairs = 0;
+    __nv_bfloat16* d_in = nullptr;      // [32][r_alloc][8], 49 rows per board
+    uint8_t* d_w = nullptr;             // one layer's packed stages
+};
+int az_tc_conv_raw_reserve(AzTcConvScratch* sc, int n);
+int az_tc_conv_raw(AzTcConvScratch* sc, const float* d_src, int n, const float* d_w, int flip, float* d_out, cudaStream_t s);
+void az_tc_conv_raw_release(AzTcConvScratch* sc);

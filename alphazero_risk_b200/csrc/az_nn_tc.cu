@@ -282,10 +282,13 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
 #define T3_SLOT_BYTES (3 * T3_VAR_BYTES)
 #define T3_SMEM_BYTES (T3_G * T3_SLOT_BYTES + TC2_STAGES * TC2_STAGE_BYTES + 2 * 256 * 4 + 64 * 8 + 16)
 
+// RAW = true (training step, az_tc_conv_raw): the epilogue stores the fp32 accumulators of the real board cells to out32
+// [board * 42 + cell][256] row-major — no BatchNorm fold, residual, ReLU or bf16 rounding; scale / shift / skip / out are unused.
+template <bool RAW>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ wpacked3, const float* __restrict__ scale,
               const float* __restrict__ shift, const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
-              int n_boards, int r_alloc, int n_tiles)
+              int n_boards, int r_alloc, int n_tiles, float* __restrict__ out32)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;                                   // T3_G x T3_SLOT_BYTES
@@ -317,7 +320,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
         return tile < n_tiles ? tile : n_tiles - 1;       // odd tile count: the peer's last tile is multiplied, never stored
     };
 
-    for (int i = threadIdx.x; i < 256; i += T3_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+    if (!RAW) for (int i = threadIdx.x; i < 256; i += T3_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
     if (threadIdx.x == 0) {
         for (int g = 0; g < T3_G; ++g) { mbar_init(bar_a_full + g, 1); mbar_init(bar_a_ready + g, 1); mbar_init(bar_pa_ready + g, 1); mbar_init(bar_a_empty + g, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, 8); }
@@ -429,7 +432,26 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
             const int tile = 2 * (pid + j * n_pairs) + (int)crank;
             mbar_wait_cluster(bar_acc_full + b, (uint32_t)((j >> 1) & 1));
             tc_fence_after();
-            if (tile < n_tiles) {
+            if (RAW) {
+                if (tile < n_tiles) {
+                    const int r = tile * TC_TILE_ROWS + q4 * 32 + lane;
+                    const bool valid = tc_row_valid(r, n_boards, 49);
+                    const int bb = r / 49;
+                    float* orow = out32 + ((size_t)bb * 42 + (size_t)(r - bb * 49)) * 256;
+#pragma unroll 1
+                    for (int c4 = 0; c4 < TC_CHUNKS / 4; ++c4) {
+                        uint32_t v[32];
+                        tc_ld32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(b * 256 + c4 * 32), v);
+                        tc_ld_wait();
+                        if (valid) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                *reinterpret_cast<float4*>(orow + c4 * 32 + e * 4) = make_float4(__uint_as_float(v[e * 4]), __uint_as_float(v[e * 4 + 1]),
+                                                                                               __uint_as_float(v[e * 4 + 2]), __uint_as_float(v[e * 4 + 3]));
+                        }
+                    }
+                }
+            } else if (tile < n_tiles) {
                 const int r = tile * TC_TILE_ROWS + q4 * 32 + lane;
                 const bool valid = tc_row_valid(r, n_boards, 49);
                 const size_t cell0 = ((size_t)TC_HALO + r) * 8;
@@ -657,7 +679,7 @@ static cudaError_t launch_conv_pair3(int grid, cudaStream_t s, const __nv_bfloat
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles);
+    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<false>, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles, (float*)nullptr);
 }
 
 // persistent launch of one stem / one-CTA tower convolution
@@ -714,7 +736,7 @@ int az_nn_tc_prepare(az_nn* nn)
         AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<32, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<32>::smem_bytes(1))));
         AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::smem_bytes(1))));
         AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<2, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::smem_bytes(3))));
-        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
+        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
         int dev = 0, sms = 148;
         AZ_CUDA(cudaGetDevice(&dev));
         AZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -730,7 +752,7 @@ int az_nn_tc_prepare(az_nn* nn)
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             int nc = 0;
-            AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc3, &cfg));
+            AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc3<false>, &cfg));
             tc->max_pairs = nc < sms / 2 ? nc : sms / 2;
             if (tc->max_pairs < 1) tc->pair_mode = 0;
             // board layout: 49 rows (masked operand copies, 12.5 % fewer MMAs; needs the CTA-pair kernel) unless AZ_TC_LAYOUT=56
@@ -743,6 +765,116 @@ int az_nn_tc_prepare(az_nn* nn)
     AZ_CUDA(cudaMemcpy(tc->d_scale, scale.data(), scale.size() * sizeof(float), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_shift, shift.data(), shift.size() * sizeof(float), cudaMemcpyHostToDevice));
     return AZ_OK;
+}
+
+// ---------------------------------------------------------------- raw 3x3 convolution for the training step (az_nn_train.cu)
+// out[r][co] = sum_{t,ci} in[nb(r,t)][ci] * w[t][ci][co]           (flip = 0: forward)
+// out[r][ci] = sum_{t,co} in[nb(r,t)][co] * w[8-t][ci][co]         (flip = 1: data gradient)
+// on the tower kernel: bf16 operands, fp32 accumulation, fp32 result [n * 42][256].  The fp32 source goes into the 49-row chunked
+// bf16 layout, the fp32 HWIO weights (which change every step) are packed into the kernel's stage order on the device.
+
+// fp32 [n * 42][256] -> bf16 [32 chunks][r_alloc][8] at rows TC_HALO + board * 49 + cell; padding rows are never written (zero from the
+// allocation).  Block = 32 source rows x 32 chunks through shared memory: contiguous reads along a row, contiguous writes along a chunk.
+__global__ void __launch_bounds__(256) k_tc_chunk49(const float* __restrict__ src, int rows, int r_alloc, __nv_bfloat16* __restrict__ out)
+{
+    __shared__ uint4 tile[32][33];
+    const int r0 = blockIdx.x * 32;
+    for (int j = threadIdx.x; j < 1024; j += 256) {
+        const int rl = j >> 5, cc = j & 31, r = r0 + rl;
+        if (r < rows) {
+            const float* sp = src + (size_t)r * 256 + cc * 8;
+            const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+            uint4 o;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+            o2[0] = __floats2bfloat162_rn(a.x, a.y); o2[1] = __floats2bfloat162_rn(a.z, a.w);
+            o2[2] = __floats2bfloat162_rn(b.x, b.y); o2[3] = __floats2bfloat162_rn(b.z, b.w);
+            tile[rl][cc] = o;
+        }
+    }
+    __syncthreads();
+    uint4* o = reinterpret_cast<uint4*>(out);
+    for (int j = threadIdx.x; j < 1024; j += 256) {
+        const int cl = j >> 5, rl = j & 31, r = r0 + rl;
+        if (r < rows) { const int bb = r / 42; o[(size_t)cl * r_alloc + TC_HALO + (size_t)bb * 49 + (r - bb * 42)] = tile[rl][cl]; }
+    }
+}
+
+// fp32 HWIO [9][256][256] (device) -> the stage order of pack_conv_pair(kb_outer): [K group][tap][half][chunk 4][128 out][8].
+// flip: the data gradient's kernel, tap 8 - t with input and output channels exchanged.  Thread = one 16-byte group (8 k values).
+__global__ void __launch_bounds__(256) k_tc_pack_pair(const float* __restrict__ w, int flip, __nv_bfloat16* __restrict__ dst)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;                      // ((((kb * 9 + tap) * 2 + h) * 4 + ch) * 128 + n)
+    if (i >= 8 * 9 * 2 * 4 * 128) return;
+    const int n = i & 127, ch = (i >> 7) & 3, h = (i >> 9) & 1, st = i >> 10, tap = st % 9, kb = st / 9;
+    const int co = h * 128 + n, ci0 = (kb * 4 + ch) * 8;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        f[e] = flip ? w[((size_t)(8 - tap) * 256 + co) * 256 + ci0 + e] : w[((size_t)tap * 256 + ci0 + e) * 256 + co];
+    uint4 o;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+}
+
+int az_tc_conv_raw_reserve(AzTcConvScratch* sc, int n)
+{
+    if (sc->max_pairs == 0) {
+        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
+        int dev = 0, sms = 148;
+        AZ_CUDA(cudaGetDevice(&dev));
+        AZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(sms / 2 * 2)); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc3<true>, &cfg));
+        sc->max_pairs = nc < sms / 2 ? nc : sms / 2;
+        if (sc->max_pairs < 1) { az_set_error("the device cannot hold one CTA pair of the tower kernel"); return AZ_ERR_CUDA; }
+        AZ_CUDA(cudaMalloc(&sc->d_w, TC_LAYER_BYTES));
+    }
+    if (n <= sc->cap_boards) return AZ_OK;
+    cudaFree(sc->d_in); sc->d_in = nullptr; sc->cap_boards = 0;
+    int tiles = (n * 49 + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    tiles += tiles & 1;
+    const int r_alloc = tiles * TC_TILE_ROWS + 2 * TC_HALO;
+    const size_t bytes = (size_t)TC_CHUNKS * r_alloc * 16;
+    AZ_CUDA(cudaMalloc(&sc->d_in, bytes));
+    AZ_CUDA(cudaMemset(sc->d_in, 0, bytes));                  // padding rows and halos must read as zero
+    sc->cap_boards = n; sc->r_alloc = r_alloc;
+    return AZ_OK;
+}
+
+int az_tc_conv_raw(AzTcConvScratch* sc, const float* d_src, int n, const float* d_w, int flip, float* d_out, cudaStream_t s)
+{
+    int rc = az_tc_conv_raw_reserve(sc, n); if (rc) return rc;
+    const int rows = n * 42;
+    // (boards a larger earlier batch left behind are harmless: every board's own seven zero rows separate it from its neighbours,
+    // and rows of boards >= n are computed but never stored)
+    k_tc_chunk49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_src, rows, sc->r_alloc, sc->d_in);
+    k_tc_pack_pair<<<(8 * 9 * 2 * 4 * 128) / 256, 256, 0, s>>>(d_w, flip, reinterpret_cast<__nv_bfloat16*>(sc->d_w));
+    AZ_CUDA(cudaGetLastError());
+    const int tiles = (n * 49 + TC_TILE_ROWS - 1) / TC_TILE_ROWS, pitems = (tiles + 1) / 2;
+    const int pgrid = 2 * (pitems < sc->max_pairs ? pitems : sc->max_pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)pgrid); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    AZ_CUDA(cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<true>, (const __nv_bfloat16*)sc->d_in, (const uint8_t*)sc->d_w, (const float*)nullptr, (const float*)nullptr,
+                               (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, n, sc->r_alloc, tiles, d_out));
+    return AZ_OK;
+}
+
+void az_tc_conv_raw_release(AzTcConvScratch* sc)
+{
+    cudaFree(sc->d_in); cudaFree(sc->d_w);
+    *sc = AzTcConvScratch();
 }
 
 void az_nn_tc_release(az_nn* nn)

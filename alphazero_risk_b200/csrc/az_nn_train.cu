@@ -21,6 +21,7 @@
 // Results are deterministic: no floating-point atomics anywhere.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -55,8 +56,10 @@ int az_nn_sync_host(az_nn* nn);      // az_nn.cu
 
 struct AzTrainState {
     int cap = 0;                                       // boards the work buffers are sized for
+    bool conv_by_gemm = false;                         // AZ_TRAIN_CONV=gemm: A/B switch back to im2col + k_tc_gemm for the 256-channel convolutions
     int precision = AZ_NN_FP32;                        // AZ_NN_BF16: the three contractions run on the tensor cores (az_tc_gemm.cu)
     __nv_bfloat16 *d_colA = nullptr, *d_colB = nullptr;   // GEMM operands: im2col / transposed im2col, weights / transposed gradient
+    AzTcConvScratch conv;                              // 256-channel convolutions of the tensor-core mode run on the tower kernel
     uint8_t* d_kind = nullptr;                         // per blob element: 0 not trainable, 1 plain, 2 kernel (L2 term)
     __nv_bfloat16* d_src16 = nullptr;                  // bf16 chunked copy of the tensor being unrolled
     float *d_grad = nullptr, *d_m = nullptr, *d_v = nullptr;      // blob-sized: gradient of the total loss, Adam slots
@@ -666,6 +669,7 @@ void az_nn_train_release(az_nn* nn)
     cudaFree(t->d_stats); cudaFree(t->d_part); for (int i = 0; i < 3; ++i) cudaFree(t->d_g[i]);
     cudaFree(t->d_wT); cudaFree(t->d_wpart); cudaFree(t->d_hz); cudaFree(t->d_hg); cudaFree(t->d_hfeat); cudaFree(t->d_hpart);
     cudaFree(t->d_tp); cudaFree(t->d_tv); cudaFree(t->d_loss); cudaFree(t->d_colA); cudaFree(t->d_colB); cudaFree(t->d_src16); cudaFree(t->d_kind);
+    az_tc_conv_raw_release(&t->conv);
     delete t;
     nn->train = nullptr;
 }
@@ -748,6 +752,8 @@ static int train_reserve(az_nn* nn, AzTrainState* t, int n)
 // one raw 3x3 convolution out[r][256] = conv(in[r][cin], w[9][cin][256]) (flip: the data-gradient kernel w[8-t] transposed)
 static int conv_any(az_nn* nn, AzTrainState* t, const float* in, int n, int cin, const float* w, int flip, float* out, cudaStream_t s)
 {
+    if (t->precision == AZ_NN_BF16 && cin == TR_CH && !t->conv_by_gemm)         // implicit GEMM on the tower kernel (no unrolled operand in HBM)
+        return az_tc_conv_raw(&t->conv, in, n, w, flip, out, s);
     if (t->precision == AZ_NN_BF16) {
         const int rows = n * 42, mp = (int)tr_mp(rows), cpad = (cin + 7) / 8 * 8, kp = (int)tr_kp(9 * cpad);
         int rc = az_tg_im2col(in, rows, cin, cpad, mp, kp, t->d_src16, t->d_colA, s); if (rc) return rc;
@@ -968,6 +974,8 @@ extern "C" int az_nn_train_precision(az_nn* nn, int precision)
     AzTrainState* t = train_state(nn);
     AZ_REQUIRE(t != nullptr, "out of host memory");
     t->precision = precision;
+    const char* ec = getenv("AZ_TRAIN_CONV");
+    t->conv_by_gemm = ec && strcmp(ec, "gemm") == 0;
     return AZ_OK;
 }
 
