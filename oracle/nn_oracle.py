@@ -4,10 +4,13 @@ shipped GraphDef python/model/model_txt_V2_5.pb (variable names and shapes, SAME
 epsilon 0.001, the stem's BatchNorm running over the board-ROW axis: build_graph.py:68 passes
 axis=1 on an NHWC tensor, so conv_bn/* have 7 elements).
 
-PARITY UNPINNED: the arithmetic the reference executes lives in TensorFlow (un-vendored, un-pinned,
-not installable here) and the reference ships neither a checkpoint nor an example output, so there
-is no reference number to pin this restatement to.  It is the checker for the <= 1e-5 fp32
-agreement north_star asks for; only tests/ and __graft_entry__.smoke() may import it.
+PARITY: the arithmetic the reference executes lives in TensorFlow (un-vendored, un-pinned, not installable here) and the reference
+ships neither a checkpoint nor an example output.  What CAN be pinned is pinned: oracle/graphdef_oracle.py executes the inference
+slice of the reference's own shipped GraphDef (tests/golden/graph_V2_5_inference.json, extracted from python/model/model_txt_V2_5.pb)
+op by op, and tests/test_graphdef_cpu.py holds this restatement to it (< 1e-9 in float64; golden vectors in
+tests/golden/graph_forward_V2_5.npz).  PARITY UNPINNED remains true for the TensorFlow kernels themselves (Conv2D, FusedBatchNormV3, ...:
+restated from their published definitions) and for the training step (gradient ops, Adam), which is checked against autograd only.
+This module is the checker for the <= 1e-5 fp32 agreement north_star asks for; only tests/ and __graft_entry__.smoke() may import it.
 """
 import numpy as np
 import torch

@@ -50,6 +50,25 @@ def test_variable_inventory_matches_graph(api):
     net.close()
 
 
+def test_forward_matches_the_golden_vectors_of_the_shipped_graphdef(api, golden_dir):
+    """tests/golden/graph_forward_V2_5.npz: the reference's own GraphDef (python/model/model_txt_V2_5.pb, inference slice) executed by
+    oracle/graphdef_oracle.py in float64 on 12 real positions.  fp32 path within 1e-5, bf16 tensor-core path within its stated tolerance;
+    the variable inventory and shapes of the library equal the GraphDef's VarHandleOps."""
+    import os
+    from oracle import graphdef_oracle as go
+    g = np.load(os.path.join(golden_dir, "graph_forward_V2_5.npz"))
+    sl = go.load_slice()
+    net = api.Net(blocks=5)
+    assert dict(net.variables()) == dict(go.variables(sl))
+    for name, value in go.golden_weights(sl, int(g["seed"])).items():
+        net.load(name, value)
+    p32, v32 = net.forward(g["x"], api.FP32)
+    assert np.abs(p32 - g["policy"]).max() <= FP32_TOL and np.abs(v32 - g["value"]).max() <= FP32_TOL
+    p16, v16 = net.forward(g["x"], api.BF16)
+    assert np.abs(p16 - g["policy"]).max() <= 2e-3 and np.abs(v16 - g["value"]).max() <= 1e-2
+    net.close()
+
+
 @pytest.mark.parametrize("blocks,n", [(5, 37), (2, 1), (5, 130)])
 def test_fp32_forward_matches_torch(api, blocks, n):
     net = api.Net(blocks=blocks, seed=1234)
