@@ -7,7 +7,11 @@ inference call takes (input_training = false -> every If runs its else_branch) a
 What remains restated are the kernels of the TensorFlow ops themselves (un-vendored, un-pinned dependency; GraphDef producer 175):
 Conv2D (NHWC, HWIO filter, SAME: pad_total = k - 1, pad_before = pad_total // 2), FusedBatchNormV3 with is_training = false
 (y = (x - mean) * rsqrt(variance + epsilon) * scale + offset along the channel axis of data_format), Relu, Add, Reshape, MatMul,
-BiasAdd, Softmax (last axis), Tanh, Squeeze, Identity — their published definitions, evaluated in float64.
+BiasAdd, Softmax (last axis), Tanh, Squeeze, Identity — their published definitions, evaluated in float64.  The training slice
+(graph_V2_5_training.json: input_training = true, the then_branch of every If) adds FusedBatchNormV3 with is_training = true (batch
+statistics; the variance output carries N / (N - 1)), SoftmaxCrossEntropyWithLogits, SquaredDifference, DivNoNan, Select, Sum, ... —
+enough to evaluate the two losses, the minimised total (add_6) and the amount every moving statistic is decreased by.  The gradient
+sub-graph is NOT interpreted: it is TensorFlow's derivative of exactly this forward, which is what nn_oracle.Trainer's autograd takes.
 Only tests/ may import this module.
 """
 import json
@@ -24,6 +28,9 @@ DTYPES = {"DT_FLOAT": np.float32, "DT_INT32": np.int32, "DT_INT64": np.int64, "D
 class _Resource:
     def __init__(self, name):
         self.name = name
+
+
+TRAINING_SLICE = os.path.join(os.path.dirname(HERE), "tests", "golden", "graph_V2_5_training.json")
 
 
 def load_slice(path=DEFAULT_SLICE):
@@ -45,9 +52,11 @@ def _const(t):
         a = np.frombuffer(bytes(t["content"]), dtype=dt)
     else:
         key = {"DT_FLOAT": "float_val", "DT_INT32": "int_val", "DT_INT64": "int64_val", "DT_BOOL": "bool_val"}[t["dtype"]]
-        vals = [(v == "true") if dt is np.bool_ else float(v) if dt is np.float32 else int(v) for v in t[key]]
+        vals = [(v == "true") if dt is np.bool_ else float(v) if dt is np.float32 else int(v) for v in t.get(key, [])]   # absent: all zero / empty
         a = np.array(vals, dtype=dt)
         count = int(np.prod(t["shape"])) if t["shape"] else 1
+        if a.size == 0 and count > 0:
+            a = np.zeros(count, dtype=dt)
         if a.size == 1 and count > 1:
             a = np.repeat(a, count)
     return a.reshape(t["shape"])
@@ -68,27 +77,42 @@ def _conv2d(x, w, attr):
 
 
 def _fused_batch_norm(x, scale, offset, mean, var, attr):
-    assert attr["is_training"]["b"] is False
+    """outputs (y, batch_mean, batch_variance).  is_training = false: the given statistics; true: the batch mean and the biased batch
+    variance normalise, and the variance OUTPUT (what AssignMovingAvg consumes) carries Bessel's correction N / (N - 1)"""
     axis = {"NHWC": 3, "NCHW": 1}[attr["data_format"]["s"]]
     shape = [1, 1, 1, 1]
     shape[axis] = -1
-    inv = 1.0 / np.sqrt(var + np.float64(np.float32(attr["epsilon"]["f"])))
-    return (x - mean.reshape(shape)) * (inv * scale).reshape(shape) + offset.reshape(shape)
+    eps = np.float64(np.float32(attr["epsilon"]["f"]))
+    if attr["is_training"]["b"]:
+        assert np.float32(attr.get("exponential_avg_factor", {"f": 1.0})["f"]) == 1.0
+        red = tuple(d for d in range(4) if d != axis)
+        n = x.size // x.shape[axis]
+        mean = x.mean(axis=red)
+        var = ((x - mean.reshape(shape)) ** 2).mean(axis=red)
+        y = (x - mean.reshape(shape)) * (scale / np.sqrt(var + eps)).reshape(shape) + offset.reshape(shape)
+        return y, mean, var * n / (n - 1)
+    inv = 1.0 / np.sqrt(var + eps)
+    return (x - mean.reshape(shape)) * (inv * scale).reshape(shape) + offset.reshape(shape), mean, var
 
 
-def run(sl, weights, x, training=False):
-    """feeds input_state = x [n,7,6,13] and input_training = training; returns (output_policy [n,43], output_value [n]) in float64.
+def run(sl, weights, x, training=False, targets=None, fetch=None):
+    """feeds input_state = x [n,7,6,13], input_training = training and (training slice) target_policy [n,43] / target_value [n,1] =
+    `targets`; returns (output_policy [n,43], output_value [n]) in float64, or the list of tensors named in `fetch`.
     `weights`: dict variable name -> array (any float dtype; used as float64)."""
-    assert training is False, "the slice holds the else branches only"
+    assert training == (sl.get("branch", "else_branch") == "then_branch"), "the slice holds one branch of every If only"
     nodes = {n["name"]: n for n in sl["nodes"]}
     memo = {}
+    feeds = {"input_state": np.asarray(x, np.float64).reshape(-1, 7, 6, 13), "input_training": np.array(training)}
+    if targets is not None:
+        feeds["target_policy"] = np.asarray(targets[0], np.float64).reshape(-1, 43)
+        feeds["target_value"] = np.asarray(targets[1], np.float64).reshape(-1, 1)
 
     def tensor(t):
-        name = t.split("#")[0]
+        name, _, out_arg = t.partition("#")         # inlined function bodies name tensors node:output_arg:index; the slice keeps "#output_arg"
         idx = 0
         if ":" in name:
             name, i = name.rsplit(":", 1)
-            idx = int(i)
+            idx = int(i) + {"batch_mean": 1, "batch_variance": 2}.get(out_arg, 0)     # FusedBatchNormV3: y, batch_mean, batch_variance, ...
         v = node(name)
         return v[idx] if isinstance(v, tuple) else v
 
@@ -99,7 +123,7 @@ def run(sl, weights, x, training=False):
         op, a = n["op"], n["attr"]
         ins = n["input"]
         if op == "Placeholder":
-            v = {"input_state": np.asarray(x, np.float64).reshape(-1, 7, 6, 13), "input_training": np.array(training)}[name]
+            v = feeds[name]
         elif op == "Const":
             v = _const(a["value"]["tensor"])
         elif op == "VarHandleOp":
@@ -117,8 +141,47 @@ def run(sl, weights, x, training=False):
             v = tensor(ins[0])
         elif op == "Conv2D":
             v = _conv2d(tensor(ins[0]), tensor(ins[1]), a)
+        elif op == "IfThenOutput":
+            assert bool(tensor(ins[-1])), "predicate is false: the else branch (inference) is not in the slice"
+            v = tuple(tensor(t) for t in ins[:-1])
         elif op == "FusedBatchNormV3":
-            v = (_fused_batch_norm(*[tensor(t) for t in ins[:5]], a),)
+            v = _fused_batch_norm(*[tensor(t) for t in ins[:5]], a)
+        elif op == "Shape":
+            v = np.array(np.shape(tensor(ins[0])), np.int32)
+        elif op == "Sub":
+            v = tensor(ins[0]) - tensor(ins[1])
+        elif op == "Mul":
+            v = tensor(ins[0]) * tensor(ins[1])
+        elif op == "Square":
+            v = tensor(ins[0]) ** 2
+        elif op == "SquaredDifference":
+            v = (tensor(ins[0]) - tensor(ins[1])) ** 2
+        elif op == "AddN":
+            v = sum(tensor(t) for t in ins)
+        elif op == "Pack":
+            v = np.stack([tensor(t) for t in ins], axis=a.get("axis", {"i": 0})["i"])
+        elif op == "Slice":
+            t, b, sz = tensor(ins[0]), tensor(ins[1]), tensor(ins[2])
+            v = t[tuple(slice(int(b[d]), None if int(sz[d]) < 0 else int(b[d]) + int(sz[d])) for d in range(t.ndim))]
+        elif op == "ConcatV2":
+            v = np.concatenate([np.atleast_1d(tensor(t)) for t in ins[:-1]], axis=int(tensor(ins[-1])))
+        elif op == "Sum":
+            axes = tuple(int(d) for d in np.atleast_1d(tensor(ins[1])))
+            v = np.sum(tensor(ins[0]), axis=axes, keepdims=bool(a.get("keep_dims", {"b": False})["b"]))
+        elif op == "Equal":
+            v = np.equal(tensor(ins[0]), tensor(ins[1]))
+        elif op == "Fill":
+            v = np.full([int(d) for d in np.atleast_1d(tensor(ins[0]))], tensor(ins[1]), dtype=np.float64)
+        elif op == "Select":
+            v = np.where(tensor(ins[0]), tensor(ins[1]), tensor(ins[2]))
+        elif op == "DivNoNan":
+            p, q = np.asarray(tensor(ins[0]), np.float64), np.asarray(tensor(ins[1]), np.float64)
+            v = np.where(q == 0.0, 0.0, p / np.where(q == 0.0, 1.0, q))
+        elif op == "SoftmaxCrossEntropyWithLogits":
+            z, lab = tensor(ins[0]), tensor(ins[1])
+            ls = z - z.max(axis=1, keepdims=True)
+            ls = ls - np.log(np.exp(ls).sum(axis=1, keepdims=True))
+            v = (-(lab * ls).sum(axis=1), np.exp(ls) - lab)
         elif op == "Relu":
             v = np.maximum(tensor(ins[0]), 0.0)
         elif op in ("Add", "AddV2"):
@@ -144,6 +207,8 @@ def run(sl, weights, x, training=False):
         memo[name] = v
         return v
 
+    if fetch is not None:
+        return [np.asarray(tensor(t)) for t in fetch]
     policy, value = node("output_policy"), node("output_value")
     return np.asarray(policy), np.asarray(value).reshape(-1)
 

@@ -9,14 +9,17 @@ ships neither a checkpoint nor an example output.  What CAN be pinned is pinned:
 slice of the reference's own shipped GraphDef (tests/golden/graph_V2_5_inference.json, extracted from python/model/model_txt_V2_5.pb)
 op by op, and tests/test_graphdef_cpu.py holds this restatement to it (< 1e-9 in float64; golden vectors in
 tests/golden/graph_forward_V2_5.npz).  PARITY UNPINNED remains true for the TensorFlow kernels themselves (Conv2D, FusedBatchNormV3, ...:
-restated from their published definitions) and for the training step (gradient ops, Adam), which is checked against autograd only.
+restated from their published definitions).  Training step: the graph's TRAINING forward (input_training = true: both losses, the
+minimised total add_6, every moving-average update) is evaluated from the reference's own nodes (tests/golden/graph_V2_5_training.json)
+and equals train_losses / Trainer's update to < 1e-11, and the 45 ResourceApplyAdam ops' wiring and constants are read from the file;
+the gradient sub-graph itself is not interpreted (it is TensorFlow's derivative of that same forward; Trainer uses autograd).
 This module is the checker for the <= 1e-5 fp32 agreement north_star asks for; only tests/ and __graft_entry__.smoke() may import it.
 """
 import numpy as np
 import torch
 import torch.nn.functional as F
 
-EPS = 0.001
+EPS = float(np.float32(0.001))           # the GraphDef's attr is a float32: 0.0010000000474974513
 
 
 def variable_names(blocks):
@@ -116,10 +119,12 @@ def flops_per_position(blocks):
 #   * AdamOptimizer(0.001, beta1 0.9, beta2 0.999, epsilon 1e-8; optimize/{learning_rate,beta1,beta2,epsilon}):
 #     lr_t = lr * sqrt(1 - beta2_power) / (1 - beta1_power); m += (g - m)(1 - beta1); v += (g^2 - v)(1 - beta2);
 #     var -= lr_t * m / (sqrt(v) + eps); then beta1_power *= beta1, beta2_power *= beta2 (initially beta1, beta2)
-# PARITY UNPINNED at the TensorFlow boundary, like forward().
-BN_MOMENTUM = 0.99
-L2_C = 0.001
-ADAM = dict(lr=0.001, beta1=0.9, beta2=0.999, eps=1e-8)
+# Pinned to the GraphDef's own training-forward nodes and optimizer wiring by tests/test_graphdef_cpu.py; the TensorFlow kernels
+# (FusedBatchNormV3 training mode, ResourceApplyAdam) are restated from their published definitions.
+# float32 constants of the GraphDef, as float32 values (tests/test_graphdef_cpu.py evaluates the graph's own nodes against these)
+BN_MOMENTUM = float(np.float32(0.99))
+L2_C = float(np.float32(0.001))
+ADAM = dict(lr=float(np.float32(0.001)), beta1=float(np.float32(0.9)), beta2=float(np.float32(0.999)), eps=float(np.float32(1e-8)))
 
 
 def trainable_names(blocks):

@@ -3,7 +3,10 @@ neural_network/alphazero_nn.cpp loads) into tests/golden/graph_V2_5_inference.js
 depend on with input_training = false, the If ops replaced by the body of their else_branch function (inlined, names prefixed).
 The JSON is what oracle/graphdef_oracle.py executes; this script is the only thing that reads /root/reference.
 
-    python tests/golden/gen_graph_slice.py [/root/reference/python/model/model_txt_V2_5.pb] [out.json]
+A second file, graph_V2_5_training.json, is the same for a training call (input_training = true, then_branch of every If): the nodes
+the two losses, the minimised total and the moving-average updates depend on, plus the optimizer's wiring and constants.
+
+    python tests/golden/gen_graph_slice.py [/root/reference/python/model/model_txt_V2_5.pb] [inference.json] [training.json]
 """
 import json
 import os
@@ -81,10 +84,10 @@ def attr_value(av):
     if "b" in av: return {"b": text_of(av["b"][0]) == "true"}
     if "type" in av: return {"type": text_of(av["type"][0])}
     if "func" in av: return {"func": text_of(av["func"][0]["name"][0])}
-    if "shape" in av: return {"shape": [int(text_of(d["size"][0])) for d in av["shape"][0].get("dim", [])]}
+    if "shape" in av: return {"shape": [int(text_of(d["size"][0])) if "size" in d else 0 for d in av["shape"][0].get("dim", [])]}
     if "tensor" in av:
         t = av["tensor"][0]
-        out = {"dtype": text_of(t["dtype"][0]), "shape": [int(text_of(d["size"][0])) for d in t.get("tensor_shape", [{}])[0].get("dim", [])]}
+        out = {"dtype": text_of(t["dtype"][0]), "shape": [int(text_of(d["size"][0])) if "size" in d else 0 for d in t.get("tensor_shape", [{}])[0].get("dim", [])]}
         if "tensor_content" in t: out["content"] = t["tensor_content"][0][1]
         for k in ("float_val", "int_val", "bool_val", "int64_val"):
             if k in t: out[k] = [text_of(x) for x in t[k]]
@@ -102,7 +105,9 @@ def node_json(nd, prefix=""):
             "attr": {text_of(a["key"][0]): attr_value(a["value"][0]) for a in nd.get("attr", [])}}
 
 
-def main(src, dst):
+def main(src, dst, outputs=("output_policy", "output_value"), branch="else_branch", n_if_outputs=1):
+    """branch: which function of every If / StatelessIf runs (else_branch: input_training = false, then_branch: true);
+    n_if_outputs: how many leading outputs of an If are kept (1: the normalised tensor; 3: + batch mean and variance)"""
     g = parse(open(src).read())
     nodes = {text_of(n["name"][0]): n for n in g["node"]}
     funcs = {text_of(f["signature"][0]["name"][0]): f for f in g["library"][0]["function"]}
@@ -122,10 +127,10 @@ def main(src, dst):
         if op in ("If", "StatelessIf"):
             # input_training is fed false: only the else branch runs.  Inline it: function argument k = If input k + 1;
             # the If node itself becomes an "IfOutputs" node whose inputs are the function's return tensors (in output_arg order)
-            fn = funcs[j["attr"]["else_branch"]["func"]]
+            fn = funcs[j["attr"][branch]["func"]]
             sig = fn["signature"][0]
             args = [text_of(a["name"][0]) for a in sig.get("input_arg", [])]
-            prefix = name + "/else/"
+            prefix = name + "/" + branch.split("_")[0] + "/"
             argmap = {a: j["input"][k + 1] for k, a in enumerate(args)}
             body = {text_of(n["name"][0]): n for n in fn.get("node_def", [])}
             ret = {text_of(r["key"][0]): text_of(r["value"][0]) for r in fn.get("ret", [])}
@@ -151,11 +156,13 @@ def main(src, dst):
                     if not t.startswith(prefix):
                         visit(tensor_node(t))
                 out.append(jn)
-            # only output 0 (the normalised tensor) is consumed on the inference path
-            first_out = text_of(sig["output_arg"][0]["name"][0])
-            visit_inner(ret[first_out].split(":")[0])
+            # only the leading outputs are consumed on the paths of interest (0: the tensor; 1, 2: batch mean / variance)
+            outs = [text_of(o["name"][0]) for o in sig["output_arg"]][:n_if_outputs]
+            for o in outs:
+                visit_inner(ret[o].split(":")[0])
             visit(tensor_node(j["input"][0]))            # the predicate, kept so that the slice shows what selects the branch
-            out.append({"name": name, "op": "IfElseOutput", "input": [remap(ret[first_out]), j["input"][0]],
+            out.append({"name": name, "op": "IfElseOutput" if branch == "else_branch" else "IfThenOutput",
+                        "input": [remap(ret[o]) if ret[o].split(":")[0] not in argmap else argmap[ret[o].split(":")[0]] for o in outs] + [j["input"][0]],
                         "attr": {"else_branch": j["attr"]["else_branch"], "then_branch": j["attr"]["then_branch"]}})
             return
         for t in j["input"]:
@@ -164,16 +171,54 @@ def main(src, dst):
         j["input"] = [t for t in j["input"] if not t.startswith("^")]
         out.append(j)
 
-    for o in ("output_policy", "output_value"):
+    for o in outputs:
         visit(o)
-    json.dump({"source": "python/model/" + os.path.basename(src), "outputs": ["output_policy", "output_value"], "nodes": out}, open(dst, "w"), indent=0)
+    json.dump({"source": "python/model/" + os.path.basename(src), "outputs": list(outputs), "branch": branch, "nodes": out}, open(dst, "w"), indent=0)
     ops = {}
     for n in out:
         ops[n["op"]] = ops.get(n["op"], 0) + 1
     print("wrote %s: %d nodes" % (dst, len(out)), ops)
 
 
+def training_slice(src, dst):
+    """input_training = true: the two losses, the total loss the optimizer minimises, the value every moving statistic is decreased by
+    (AssignMovingAvg: AssignSubVariableOp(variable, <node>)), and what the 45 ResourceApplyAdam ops are wired to"""
+    g = parse(open(src).read())
+    nodes = {text_of(n["name"][0]): n for n in g["node"]}
+    updates, adam_vars, adam_inputs, nesterov = [], [], set(), set()
+    for name, nd in nodes.items():
+        op = text_of(nd["op"][0])
+        ins = [text_of(x) for x in nd.get("input", [])]
+        if op == "AssignSubVariableOp" and "AssignMovingAvg" in name:
+            updates.append([ins[0], ins[1]])
+        if op == "ResourceApplyAdam":
+            adam_vars.append(ins[0])
+            adam_inputs.add(tuple(ins[5:9]))          # lr, beta1, beta2, epsilon (inputs 3 and 4 read the beta1_power / beta2_power variables)
+            assert [text_of(nodes[ins[k]]["input"][0]) for k in (3, 4)] == ["beta1_power", "beta2_power"] and ins[1:3] == [ins[0] + "/optimize", ins[0] + "/optimize_1"]
+            attrs = {text_of(a["key"][0]): attr_value(a["value"][0]) for a in nd.get("attr", [])}
+            nesterov.add(bool(attrs.get("use_nesterov", {"b": False})["b"]))
+            # the gradient fed to the update is d(total loss)/d(variable): its producer lives under gradients/ of the total loss
+    assert len(adam_inputs) == 1 and nesterov == {False}
+    hyper = list(adam_inputs)[0]
+    outputs = ["softmax_cross_entropy_loss/value", "mean_squared_error/value", "add_6"] + [u[1] for u in sorted(updates)]
+    main(src, dst, outputs=outputs, branch="then_branch", n_if_outputs=3)
+    d = json.load(open(dst))
+
+    def const_value(name):
+        t = attr_value([a for a in nodes[name]["attr"] if text_of(a["key"][0]) == "value"][0]["value"][0])["tensor"]
+        return float(t["float_val"][0])
+    grad_of_total = [n for n in nodes if n.startswith("gradients/add_6_grad/")]           # tf.gradients(add_6, ...): add_6 is what is minimised
+    d["adam"] = {"variables": sorted(adam_vars), "learning_rate": const_value(hyper[0]), "beta1": const_value(hyper[1]), "beta2": const_value(hyper[2]),
+                 "epsilon": const_value(hyper[3]), "use_nesterov": False, "hyper_nodes": list(hyper), "slots": ["<variable>/optimize", "<variable>/optimize_1"],
+                 "minimised": "add_6" if grad_of_total else None}
+    d["moving_average_updates"] = sorted(updates)
+    json.dump(d, open(dst, "w"), indent=0)
+    print("training slice: %d moving-average updates, %d Adam variables, lr %g beta1 %g beta2 %g eps %g"
+          % (len(updates), len(adam_vars), d["adam"]["learning_rate"], d["adam"]["beta1"], d["adam"]["beta2"], d["adam"]["epsilon"]))
+
+
 if __name__ == "__main__":
     here = os.path.dirname(os.path.abspath(__file__))
-    main(sys.argv[1] if len(sys.argv) > 1 else "/root/reference/python/model/model_txt_V2_5.pb",
-         sys.argv[2] if len(sys.argv) > 2 else os.path.join(here, "graph_V2_5_inference.json"))
+    src = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/python/model/model_txt_V2_5.pb"
+    main(src, sys.argv[2] if len(sys.argv) > 2 else os.path.join(here, "graph_V2_5_inference.json"))
+    training_slice(src, sys.argv[3] if len(sys.argv) > 3 else os.path.join(here, "graph_V2_5_training.json"))

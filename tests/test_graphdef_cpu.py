@@ -56,7 +56,7 @@ def test_restatement_equals_the_graphdef(sl):
         x = np.random.default_rng(100 + seed).random((n, 7, 6, 13)).astype(np.float32)
         p, v = go.run(sl, w, x)
         pr, vr = no.forward(w, x, 5, dtype=torch.float64)
-        assert np.abs(p - pr).max() < 1e-9 and np.abs(v - vr).max() < 1e-9          # (epsilon: float32(0.001) in the graph, 0.001 in the restatement)
+        assert np.abs(p - pr).max() < 1e-12 and np.abs(v - vr).max() < 1e-12
         p32, v32 = no.forward(w, x, 5, dtype=torch.float32)
         assert np.abs(p - p32).max() < 1e-5 and np.abs(v - v32).max() < 1e-5
 
@@ -71,8 +71,50 @@ def test_golden_forward_vectors(sl, golden_dir):
     assert np.allclose(g["policy"].sum(1), 1.0, atol=1e-12) and g["policy"].std(0).max() > 1e-3
 
 
+def test_training_forward_of_the_graphdef_equals_the_restatement(sl):
+    """input_training = true: the two losses, the minimised total (add_6 = loss_pi + loss_v + total_regularization_loss) and the amount
+    every moving statistic is decreased by, evaluated from the reference's own nodes, against nn_oracle.train_losses.  The optimizer
+    differentiates exactly this forward (tf.gradients of add_6), so pinning it pins what nn_oracle.Trainer's autograd differentiates."""
+    ts = go.load_slice(go.TRAINING_SLICE)
+    upd = ts["moving_average_updates"]
+    assert len(upd) == 26 and ts["adam"]["minimised"] == "add_6"
+    for seed, n in ((5, 6), (6, 17)):
+        w = go.golden_weights(sl, seed)
+        rng = np.random.default_rng(seed)
+        x = rng.random((n, 7, 6, 13)).astype(np.float32)
+        tp = rng.random((n, 43))
+        tp /= tp.sum(1, keepdims=True)
+        tv = rng.choice([-1.0, 0.0, 1.0], n)
+        out = go.run(ts, w, x, training=True, targets=(tp, tv),
+                     fetch=["softmax_cross_entropy_loss/value", "mean_squared_error/value", "add_6"] + [u[1] for u in upd])
+        wt = {k: torch.as_tensor(v, dtype=torch.float64) for k, v in w.items()}
+        stats = {}
+        lp, lv, l2 = no.train_losses(wt, torch.as_tensor(x, dtype=torch.float64), torch.as_tensor(tp), torch.as_tensor(tv), 5, stats)
+        assert abs(float(out[0]) - float(lp)) < 1e-11 and abs(float(out[1]) - float(lv)) < 1e-11
+        assert abs(float(out[2]) - float(lp + lv + l2)) < 1e-11
+        for (var, _), val in zip(upd, out[3:]):
+            prefix, which = var.rsplit("/", 1)
+            mean, var_unbiased = stats[prefix]
+            target = (mean if which == "moving_mean" else var_unbiased).numpy()
+            ref = (w[var].astype(np.float64) - target) * (1.0 - no.BN_MOMENTUM)          # Trainer.step: moving -= (moving - batch) * (1 - momentum)
+            assert np.abs(val - ref).max() < 1e-12, var
+
+
+def test_optimizer_wiring_and_constants(sl):
+    """the 45 ResourceApplyAdam ops of the graph: which variables they update, their slots, hyper-parameters and beta-power inputs"""
+    ts = go.load_slice(go.TRAINING_SLICE)
+    ad = ts["adam"]
+    assert ad["variables"] == sorted(no.trainable_names(5)) and len(ad["variables"]) == 45
+    assert np.float32(ad["learning_rate"]) == np.float32(no.ADAM["lr"]) and np.float32(ad["beta1"]) == np.float32(no.ADAM["beta1"])
+    assert np.float32(ad["beta2"]) == np.float32(no.ADAM["beta2"]) and np.float32(ad["epsilon"]) == np.float32(no.ADAM["eps"])
+    assert ad["use_nesterov"] is False and ad["slots"] == ["<variable>/optimize", "<variable>/optimize_1"]
+    regularised = sorted(n["name"].split("/Regularizer/")[0] for n in ts["nodes"] if n["name"].endswith("/Regularizer/Square"))
+    assert regularised == sorted(n for n in no.variable_names(5) if n.endswith("/kernel")) and len(regularised) == 16
+
+
 @pytest.mark.skipif(not os.path.exists(REF_PB), reason="the reference tree is not present (GPU box)")
-def test_committed_slice_is_what_the_extractor_produces(tmp_path, golden_dir):
-    out = str(tmp_path / "slice.json")
-    subprocess.check_call([sys.executable, os.path.join(golden_dir, "gen_graph_slice.py"), REF_PB, out], stdout=subprocess.DEVNULL)
-    assert json.load(open(out)) == json.load(open(os.path.join(golden_dir, "graph_V2_5_inference.json")))
+def test_committed_slices_are_what_the_extractor_produces(tmp_path, golden_dir):
+    a, b = str(tmp_path / "inference.json"), str(tmp_path / "training.json")
+    subprocess.check_call([sys.executable, os.path.join(golden_dir, "gen_graph_slice.py"), REF_PB, a, b], stdout=subprocess.DEVNULL)
+    assert json.load(open(a)) == json.load(open(os.path.join(golden_dir, "graph_V2_5_inference.json")))
+    assert json.load(open(b)) == json.load(open(os.path.join(golden_dir, "graph_V2_5_training.json")))
