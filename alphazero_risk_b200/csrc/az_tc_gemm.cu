@@ -305,13 +305,13 @@ __global__ void __launch_bounds__(256) k_tg_reduce(const float* __restrict__ par
 }
 
 // ---------------------------------------------------------------- host side
-static int g_tables_dev = -1;
+static unsigned long long g_tables_devs = 0;       // bit d: device d holds the tap table and the kernel attribute
 
 int az_tg_init()
 {
     int dev = 0;
     AZ_CUDA(cudaGetDevice(&dev));
-    if (g_tables_dev == dev) return AZ_OK;
+    if (dev < 64 && ((g_tables_devs >> dev) & 1ull)) return AZ_OK;
     int8_t nb[42 * 9];
     for (int p = 0; p < 42; ++p)
         for (int k = 0; k < 9; ++k) {
@@ -320,7 +320,7 @@ int az_tg_init()
         }
     AZ_CUDA(cudaMemcpyToSymbol(c_gnb, nb, sizeof nb));
     AZ_CUDA(cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
-    g_tables_dev = dev;
+    if (dev < 64) g_tables_devs |= 1ull << dev;
     return AZ_OK;
 }
 
