@@ -19,6 +19,7 @@
 // reductions; the float operations use explicit _rn intrinsics (and the TU is built with
 // -fmad=false) so every rounding matches the reference's x86 build bit for bit.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -602,6 +603,49 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_rec_end(MctsDev m, con
     rec_flush(m, gi, e == 3 ? AZ_STATUS_DRAW : (int)e - 1, s_rec[warp], lane);
 }
 
+// arena leaf batches: compacted position i = j * count + k holds descent slot j * n + games[k]
+__global__ void __launch_bounds__(256) k_mcts_gather_leaves(const uint32_t* __restrict__ leaf, int ns, int n, const int32_t* __restrict__ games,
+                                                             int count, int K, uint32_t* __restrict__ out)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x, m = count * K;
+    if (i >= m * 16) return;
+    const int w = i / m, c = i - w * m, j = c / count, k = c - j * count;
+    out[(size_t)w * m + c] = leaf[(size_t)w * ns + (size_t)j * n + games[k]];
+}
+__global__ void __launch_bounds__(256) k_mcts_scatter_evals(const float* __restrict__ pol_c, const float* __restrict__ val_c, int n,
+                                                             const int32_t* __restrict__ games, int count, int K, float* __restrict__ pol,
+                                                             float* __restrict__ val)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x, m = count * K;
+    if (i >= m * 44) return;
+    const int c = i / 44, e = i - c * 44, j = c / count, k = c - j * count;
+    const size_t slot = (size_t)j * n + games[k];
+    if (e < 43) pol[slot * 43 + e] = pol_c[(size_t)c * 43 + e];
+    else val[slot] = val_c[c];
+}
+// ascending list of the games with flags[g] == want (one block; a running count over 1024-game strips keeps the order)
+__global__ void __launch_bounds__(1024) k_arena_list(const uint8_t* __restrict__ flags, int n, int want, int32_t* __restrict__ out)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g0 = 0; g0 < n; g0 += 1024) {
+        const int g = g0 + threadIdx.x;
+        const bool on = g < n && flags[g] == (uint8_t)want;
+        const unsigned bal = __ballot_sync(FULL, on);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (on) out[before + __popc(bal & ((1u << lane) - 1u))] = g;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 32; ++w) t += s_warp[w]; s_base += t; }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- host side
 int az_launch_encode(const uint32_t* d_state, int n, float* d_x, cudaStream_t s);   // az_env.cu
 uint32_t* az_env_state_ptr(az_env* e); int az_env_n(const az_env* e); int az_env_device(const az_env* e);
@@ -612,6 +656,10 @@ struct az_mcts {
     int evaluator = EVAL_NN, precision = AZ_NN_FP32, device = 0;
     MctsDev d;
     float* d_x = nullptr;
+    // arena: only the slots that take part in a search go through the network (az_arena_play sets these around search_once)
+    const int32_t* eval_games = nullptr;   // device list of the participating games, ascending
+    int eval_count = 0;                    // its length; 0 = every slot is evaluated
+    uint32_t* d_leaf_c = nullptr; float* d_pol_c = nullptr; float* d_val_c = nullptr;   // compacted leaf batch [16][m], [m][43], [m]
     std::vector<void*> allocs;
 };
 
@@ -662,7 +710,10 @@ extern "C" int az_mcts_create(az_env* env, az_nn* nn, int evaluator, int precisi
     rc |= dalloc(mc, &d.out_p, n * AZ_MOVES); rc |= dalloc(mc, &d.out_move, n); rc |= dalloc(mc, &d.out_value, n);
     rc |= dalloc(mc, &d.out_sumn, n); rc |= dalloc(mc, &d.out_table, n); rc |= dalloc(mc, &d.out_status, n);
     rc |= dalloc(mc, &d.counters, (size_t)CNT_N);
-    if (evaluator == EVAL_NN) rc |= dalloc(mc, &mc->d_x, ns * AZ_INPUT_FLOATS);
+    if (evaluator == EVAL_NN) {
+        rc |= dalloc(mc, &mc->d_x, ns * AZ_INPUT_FLOATS);
+        rc |= dalloc(mc, &mc->d_leaf_c, ns * 16); rc |= dalloc(mc, &mc->d_pol_c, ns * AZ_MOVES); rc |= dalloc(mc, &mc->d_val_c, ns);
+    }
     if (rc) { for (void* p : mc->allocs) cudaFree(p); delete mc; return AZ_ERR_CUDA; }
     d.root_state = az_env_state_ptr(env);
     d.c1 = 1.0f - r->dir_noise_epsi;                 // (1 - SETTINGS.DIR_NOISE_EPSI), alphazero_mcts.cpp:81
@@ -706,6 +757,22 @@ static int evaluate_leaves(az_mcts* mc, cudaStream_t s)
     if (mc->evaluator != EVAL_NN) return AZ_OK;
     MctsDev& d = mc->d;
     const int ns = d.n * d.K;                            // every descent slot goes through the network (slot = j * n + game)
+    if (mc->eval_count > 0 && mc->eval_count < d.n) {
+        // arena: gather the participating games' leaves, evaluate that batch, scatter the outputs back to their slots
+        const int m = mc->eval_count * d.K;
+        k_mcts_gather_leaves<<<(m * 16 + 255) / 256, 256, 0, s>>>(d.leaf_state, ns, d.n, mc->eval_games, mc->eval_count, d.K, mc->d_leaf_c);
+        int rc;
+        if (mc->precision == AZ_NN_BF16) {
+            rc = az_nn_reserve(mc->nn, ns); if (rc) return rc;
+            rc = az_nn_tc_forward(mc->nn, nullptr, mc->d_leaf_c, m, mc->d_pol_c, mc->d_val_c, s); if (rc) return rc;
+        } else {
+            rc = az_launch_encode(mc->d_leaf_c, m, mc->d_x, s); if (rc) return rc;
+            rc = az_nn_forward_dev(mc->nn, mc->d_x, m, mc->d_pol_c, mc->d_val_c, AZ_NN_FP32, s); if (rc) return rc;
+        }
+        k_mcts_scatter_evals<<<(m * 44 + 255) / 256, 256, 0, s>>>(mc->d_pol_c, mc->d_val_c, d.n, mc->eval_games, mc->eval_count, d.K, d.nn_policy, d.nn_value);
+        AZ_CUDA(cudaGetLastError());
+        return AZ_OK;
+    }
     if (mc->precision == AZ_NN_BF16) {
         int rc = az_nn_reserve(mc->nn, ns); if (rc) return rc;
         return az_nn_tc_forward(mc->nn, nullptr, d.leaf_state, ns, d.nn_policy, d.nn_value, s);
@@ -872,6 +939,8 @@ int az_env_reset(az_env* e, uint64_t seed, void* stream);
 struct az_arena {
     az_mcts* mc = nullptr;
     az_mcts* opp = nullptr;          // AZ_OPPONENT_ALPHAZERO: the searcher of player index 1
+    int32_t* d_list[2] = { nullptr, nullptr };   // games waiting for searcher 0 / 1 this tick (leaf-batch compaction)
+    bool compact = true;             // AZ_ARENA_COMPACT=0: evaluate every slot (A/B and parity switch)
     ArenaDev a;
     std::vector<void*> allocs;
 };
@@ -901,7 +970,9 @@ extern "C" int az_arena_create(az_mcts* mc, int opponent, int mirror_games, az_a
     rc |= aalloc(ar, &a.player_start, n); rc |= aalloc(ar, &a.fresh, n); rc |= aalloc(ar, &a.active, n); rc |= aalloc(ar, &a.last_mover, n);
     rc |= aalloc(ar, &a.ended, n);
     rc |= aalloc(ar, &a.res, (size_t)ARENA_N);
+    rc |= aalloc(ar, &ar->d_list[0], n);
     if (rc) { for (void* p : ar->allocs) cudaFree(p); delete ar; return AZ_ERR_CUDA; }
+    { const char* ec = getenv("AZ_ARENA_COMPACT"); ar->compact = !(ec && ec[0] == '0'); }
     a.state = mc->d.root_state; a.extra_trim = mc->d.extra_trim;
     *out = ar;
     return AZ_OK;
@@ -928,7 +999,9 @@ extern "C" int az_arena_create_versus(az_mcts* mc, az_mcts* opp, int mirror_game
     rc |= aalloc(ar, &a.player_start, n); rc |= aalloc(ar, &a.fresh, n); rc |= aalloc(ar, &a.active, n); rc |= aalloc(ar, &a.last_mover, n);
     rc |= aalloc(ar, &a.to_move, n); rc |= aalloc(ar, &a.ended, n);
     rc |= aalloc(ar, &a.res, (size_t)ARENA_N);
+    rc |= aalloc(ar, &ar->d_list[0], n); rc |= aalloc(ar, &ar->d_list[1], n);
     if (rc) { for (void* p : ar->allocs) cudaFree(p); delete ar; return AZ_ERR_CUDA; }
+    { const char* ec = getenv("AZ_ARENA_COMPACT"); ar->compact = !(ec && ec[0] == '0'); }
     a.state = mc->d.root_state; a.extra_trim = mc->d.extra_trim; a.extra_trim_opp = opp->d.extra_trim;
     *out = ar;
     return AZ_OK;
@@ -985,13 +1058,31 @@ extern "C" int az_arena_play(az_arena* ar, uint64_t n_games, uint64_t seed, az_a
         AZ_CUDA(cudaMemcpyAsync(act, a.res + ARENA_ACTIVE, sizeof act, cudaMemcpyDeviceToHost, s));
         AZ_CUDA(cudaStreamSynchronize(s));
         if (act[0] == 0) break;
-        if (!opp) { rc = search_once(mc, 0, 0, 1, 0, s); if (rc) return rc; }   // one AlphaZero move on every slot that is waiting for one
-        else {
+        // leaf batches hold only the slots that search this tick (their number is known on the host: act[])
+        const bool compact = ar->compact && mc->evaluator == EVAL_NN;
+        if (!opp) {
+            if (compact && act[0] < (unsigned long long)a.n) {
+                k_arena_list<<<1, 1024, 0, s>>>(a.active, a.n, 1, ar->d_list[0]);
+                mc->eval_games = ar->d_list[0]; mc->eval_count = (int)act[0];
+            }
+            rc = search_once(mc, 0, 0, 1, 0, s);                                // one AlphaZero move on every slot that is waiting for one
+            mc->eval_games = nullptr; mc->eval_count = 0;
+            if (rc) return rc;
+        } else {
             // one move of player 0's searcher on its slots, then one of player 1's on the others; a slot whose move passed the turn
             // over waits for the next tick (k_arena_advance sets the turn-start trim first)
             mc->d.side_sel = a.to_move; mc->d.side = 0; opp->d.side_sel = a.to_move; opp->d.side = 1;
-            if (act[1]) rc = search_once(mc, 0, 0, 1, 0, s);
-            if (!rc && act[2]) rc = search_once(opp, 0, 0, 1, 0, s);
+            az_mcts* side_mc[2] = { mc, opp };
+            for (int side = 0; side < 2 && !rc; ++side) {
+                if (!act[1 + side]) continue;
+                az_mcts* m2 = side_mc[side];
+                if (ar->compact && m2->evaluator == EVAL_NN && act[1 + side] < (unsigned long long)a.n) {
+                    k_arena_list<<<1, 1024, 0, s>>>(a.to_move, a.n, side, ar->d_list[side]);
+                    m2->eval_games = ar->d_list[side]; m2->eval_count = (int)act[1 + side];
+                }
+                rc = search_once(m2, 0, 0, 1, 0, s);
+                m2->eval_games = nullptr; m2->eval_count = 0;
+            }
             mc->d.side_sel = nullptr; opp->d.side_sel = nullptr;
             if (rc) return rc;
         }

@@ -253,6 +253,41 @@ def test_arena_alphazero_vs_alphazero_matches_oracle(api, n, first, sims, K, eva
     arena.close(); mc0.close(); mc1.close(); mc2.close(); other.close(); env.close()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_arena_leaf_compaction_changes_nothing(api, precision):
+    """with a network evaluator the arena sends only the slots that search this tick through the network (gather -> forward ->
+    scatter); AZ_ARENA_COMPACT=0 evaluates every slot.  Both must play the same match, move for move: vs Script with slots finishing
+    at different times, and AlphaZero vs AlphaZero where each searcher owns about half of the slots per tick."""
+    import os
+    prec = api.FP32 if precision == "fp32" else api.BF16
+    rules = api.default_rules(mcts_simulations=6, threads_per_mcts=1, concurrent_descents=2)
+    nets = [api.Net(blocks=1, seed=5), api.Net(blocks=1, seed=6)]
+    outcome = {}
+    for compact in ("1", "0"):
+        os.environ["AZ_ARENA_COMPACT"] = compact
+        try:
+            env = api.Env(9, rules=rules, first_game_id=70)
+            mc0 = api.Mcts(env, net=nets[0], evaluator=api.EVAL_NN, precision=prec)
+            mc1 = api.Mcts(env, net=nets[1], evaluator=api.EVAL_NN, precision=prec)
+            a_script = api.Arena(mc0, api.OPPONENT_SCRIPT, mirror_games=True)
+            r1 = a_script.play(26, SEED)
+            s1 = env.export_aos().copy()
+            a_versus = api.Arena(mc0, mirror_games=True, opponent_mcts=mc1)
+            r2 = a_versus.play(18, SEED + 3)
+            s2 = env.export_aos().copy()
+            for r in (r1, r2):
+                assert r["errors"] == 0
+            outcome[compact] = (r1, s1, r2, s2)
+            a_versus.close(); a_script.close(); mc1.close(); mc0.close(); env.close()
+        finally:
+            os.environ.pop("AZ_ARENA_COMPACT", None)
+    (r1, s1, r2, s2), (q1, t1, q2, t2) = outcome["1"], outcome["0"]
+    assert r1 == q1 and r2 == q2 and (s1 == t1).all() and (s2 == t2).all()
+    assert r1["count"] == 26 and r2["count"] == 18
+    for n in nets:
+        n.close()
+
+
 def test_arena_claims_pairs_like_the_counter(api):
     """more games than slots, odd request: 2 * floor(n / 2) games are played (Counter::hasNext(2)), tallies are consistent"""
     n, sims = 6, 4
