@@ -466,25 +466,50 @@ def run_ours(args):
     cnt = env.counters(stream=sptr)
     assert cnt["steps"] == n * S * args.steps, cnt
 
-    # ---- e2e: host State images in pinned memory -> device -> rollout -> host, every step
+    # ---- e2e: host State images in pinned memory -> device -> rollout -> host, every step.  The public calls are synchronous
+    # (az_env_import_aos / az_env_rollout / az_env_export_aos return when the data is there), so a host that wants the copies of one
+    # shard to overlap the rollout of another drives shards from separate threads, each with its own env handle and stream: here two
+    # shards (--e2e-shards) of games/2.  Every step of a shard continues from the images its previous step exported.
     e2e_steps = max(3, min(args.steps, 10))
-    h_in = torch.empty((n, 160), dtype=torch.uint8).pin_memory()
-    h_out = torch.empty((n, 160), dtype=torch.uint8).pin_memory()
-    env.reset(SEED, stream=sptr)
-    env.export_aos(out=h_in.numpy(), stream=sptr)
-    for _ in range(2):        # every step continues from the images the previous step exported (host buffers swap roles)
-        env.import_aos(h_in.numpy(), stream=sptr); env.rollout(S, stream=sptr); env.export_aos(out=h_out.numpy(), stream=sptr)
-        h_in, h_out = h_out, h_in
+    n_sh = max(1, args.e2e_shards)
+    per = n // n_sh
+    shards = []
+    for k in range(n_sh):
+        st = torch.cuda.Stream()
+        e = api.Env(per, device=local, first_game_id=rank * n + k * per)
+        h_a = torch.empty((per, 160), dtype=torch.uint8).pin_memory()
+        h_b = torch.empty((per, 160), dtype=torch.uint8).pin_memory()
+        e.reset(SEED, stream=st.cuda_stream)
+        e.export_aos(out=h_a.numpy(), stream=st.cuda_stream)
+        shards.append([e, st, h_a, h_b])
+
+    def e2e_shard(sh, steps):
+        e, st, h_in, h_out = sh
+        torch.cuda.set_device(local)
+        for _ in range(steps):
+            e.import_aos(h_in.numpy(), stream=st.cuda_stream)
+            e.rollout(S, stream=st.cuda_stream)
+            e.export_aos(out=h_out.numpy(), stream=st.cuda_stream)
+            e.counters(stream=st.cuda_stream)
+            h_in, h_out = h_out, h_in
+        sh[2], sh[3] = h_in, h_out
+
+    def e2e_run(steps):
+        th = [threading.Thread(target=e2e_shard, args=(sh, steps)) for sh in shards]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        env.import_aos(h_in.numpy(), stream=sptr)
-        env.rollout(S, stream=sptr)
-        env.export_aos(out=h_out.numpy(), stream=sptr)
-        env.counters(stream=sptr)
-        h_in, h_out = h_out, h_in
+    e2e_run(e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_games = per * n_sh
+    for sh in shards:
+        sh[0].close()
 
     dev_ms, e2e_ms, wall_ms = dev_ms, e2e_s * 1e3, t_wall * 1e3
     if dist is not None:
@@ -521,8 +546,10 @@ def run_ours(args):
                               "note": "algorithmic 330 B/step x games x moves per launch / CUDA-event time of k_env_rollout; the state "
                                       "stays on chip between the moves of one launch (traffic = the ncu DRAM bytes of one launch: the "
                                       "64 B/game SoA state read once), so this is an issue-bound kernel, not a DRAM-bound one"},
-                    e2e={"value": n * S * e2e_steps * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": n * 160,
-                         "d2h_bytes_per_step": n * 160 + 64, "steps": e2e_steps},
+                    e2e={"value": e2e_games * S * e2e_steps * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": e2e_games * 160,
+                         "d2h_bytes_per_step": e2e_games * 160 + 64 * n_sh, "steps": e2e_steps,
+                         "note": "%d host threads x %d games, each: import State images (pinned host) -> 512-move rollout -> export images + "
+                                 "counters, every step; one shard's copies overlap the other's rollout" % (n_sh, per)},
                     gpu_launches=args.steps, wall_ms_timed_region=wall_ms, clocks=clocks,
                     results={"games_finished": cnt["games"], "wins": cnt["wins"], "draws": cnt["draws"]})
         if mcts_line is not None:
@@ -552,6 +579,7 @@ def main():
     ap.add_argument("--games", type=int, default=65536)
     ap.add_argument("--lockstep", type=int, default=512, help="lockstep moves per launch (one bench step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-shards", type=int, default=2, help="host threads (each with its own env shard and stream) of the e2e measurement")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the configs[2] self-play measurement")
     ap.add_argument("--sp-games", type=int, default=4096)
     ap.add_argument("--sp-sims", type=int, default=64)
