@@ -775,7 +775,10 @@ int az_nn_tc_prepare(az_nn* nn)
 
 // fp32 [n * 42][256] -> bf16 [32 chunks][r_alloc][8] at rows TC_HALO + board * 49 + cell; padding rows are never written (zero from the
 // allocation).  Block = 32 source rows x 32 chunks through shared memory: contiguous reads along a row, contiguous writes along a chunk.
-__global__ void __launch_bounds__(256) k_tc_chunk49(const float* __restrict__ src, int rows, int r_alloc, __nv_bfloat16* __restrict__ out)
+// variants = 3: two more copies var_stride_u4 apart — cells with x = 0 zeroed, cells with x = 5 zeroed (the weight gradient masks the
+// OUTPUT cell of a tap that would reach over the left / right board border).
+__global__ void __launch_bounds__(256) k_tc_chunk49(const float* __restrict__ src, int rows, int r_alloc, __nv_bfloat16* __restrict__ out,
+                                                     int variants, size_t var_stride_u4)
 {
     __shared__ uint4 tile[32][33];
     const int r0 = blockIdx.x * 32;
@@ -795,7 +798,138 @@ __global__ void __launch_bounds__(256) k_tc_chunk49(const float* __restrict__ sr
     uint4* o = reinterpret_cast<uint4*>(out);
     for (int j = threadIdx.x; j < 1024; j += 256) {
         const int cl = j >> 5, rl = j & 31, r = r0 + rl;
-        if (r < rows) { const int bb = r / 42; o[(size_t)cl * r_alloc + TC_HALO + (size_t)bb * 49 + (r - bb * 42)] = tile[rl][cl]; }
+        if (r < rows) {
+            const int bb = r / 42, p = r - bb * 42, x = p % 6;
+            const size_t at = (size_t)cl * r_alloc + TC_HALO + (size_t)bb * 49 + p;
+            const uint4 v = tile[rl][cl], zero = make_uint4(0u, 0u, 0u, 0u);
+            o[at] = v;
+            if (variants == 3) { o[var_stride_u4 + at] = x == 0 ? zero : v; o[2 * var_stride_u4 + at] = x == 5 ? zero : v; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- weight gradient of a 256 -> 256 convolution, no unrolled operand
+//   dW[t][ci][co] = sum over board cells r of a[nb(r, t)][ci] * dz[r][co]
+// as nine GEMMs D_t[ci][co] = A_t^T . dZ with K = rows of the 49-row layout.  Both operands are read straight from the chunked bf16
+// buffers [chunk][row][8]: seen with the row index as K they are MN-MAJOR UMMA operands (8 K-rows x 16 bytes of MN per core matrix,
+// K groups 128 B apart = LBO, chunks = SBO apart), so the transposition costs nothing, and tap t is the A operand read `shift(t)` rows
+// further on — a 16-byte-aligned address offset.  Top / bottom borders come from the zero rows between boards, left / right borders
+// from the x-masked copies of dz (k_tc_chunk49 variants).
+// One CTA = one tap x one K split: M = 2 x 128 input channels (two accumulators, all 512 TMEM columns), N = 256, 64 K-rows per stage.
+// The kernel is bound by L2 -> SM delivery (116 FLOP per operand byte; measured 255 MB into the SMs in 64 us = 4 TB/s, tensor pipe
+// active 21 %), so the three taps of one kernel COLUMN (same dx: same dz copy, activation rows 6 apart) run as a CLUSTER of three
+// CTAs that share every operand slab by multicast: each CTA requests a third of the slabs for all three (a: 64 + 12 rows, every CTA
+// reads its own 6-row offset; dz: 64 rows), a stage is refilled once the MMAs of all three have retired (tcgen05.commit multicast to
+// the three "empty" barriers).  Measured gain of the multicast: 4 us per launch (the SMs still ingest the same bytes); one contiguous
+// copy per operand per stage instead of 64 slabs would give another 7 us (timing experiment) — the lever that is left is more
+// FLOPs per delivered byte (two taps per CTA pair sharing dz and overlapping activation rows).
+#define WG_STAGES 3
+#define WG_KROWS 64
+#define WG_A_ROWS (WG_KROWS + 12)
+#define WG_A_STAGE (32 * WG_A_ROWS * 16)                      // 38912
+#define WG_B_STAGE (32 * WG_KROWS * 16)                       // 32768
+#define WG_SMEM (WG_STAGES * (WG_A_STAGE + WG_B_STAGE) + 16 * 8 + 16)
+#define WG_IDESC (TC_IDESC | (1u << 15) | (1u << 16))         // A and B MN-major
+
+__global__ void __launch_bounds__(192, 1)
+k_tc_wgrad(const __nv_bfloat16* __restrict__ a49, const __nv_bfloat16* __restrict__ dz49, size_t var_stride_bytes, int r_alloc, int kb_total,
+           int kb_per_split, float* __restrict__ part)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + WG_STAGES * WG_A_STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + WG_STAGES * WG_B_STAGE);
+    uint64_t* bar_full = bars;
+    uint64_t* bar_empty = bars + WG_STAGES;
+    uint64_t* bar_acc = bars + 2 * WG_STAGES;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int kx = (int)(blockIdx.x / 3), ky = (int)crank, tap = ky * 3 + kx;          // cluster = the three ky of one kx
+    const int split = blockIdx.y;
+    const int kb0 = split * kb_per_split;
+    const int nkb = min(kb_per_split, kb_total - kb0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 3); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ---- loaders: lane l owns chunk l of both operands; the CTA with rank l % 3 requests it for the whole cluster
+        const int var = kx == 0 ? 1 : (kx == 2 ? 2 : 0);
+        const bool mine = (uint32_t)(lane % 3) == crank;
+        const uint8_t* a8 = reinterpret_cast<const uint8_t*>(a49) + ((size_t)lane * r_alloc + TC_HALO - 6 + (kx - 1)) * 16;
+        const uint8_t* b8 = reinterpret_cast<const uint8_t*>(dz49) + (size_t)var * var_stride_bytes + ((size_t)lane * r_alloc + TC_HALO) * 16;
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % WG_STAGES, k = i / WG_STAGES;
+            if (k > 0) mbar_wait_cluster(bar_empty + s, (uint32_t)((k - 1) & 1));
+            if (lane == 0) mbar_expect_tx(bar_full + s, WG_A_STAGE + WG_B_STAGE);
+            __syncwarp();
+            if (mine) {
+                const size_t r0 = (size_t)(kb0 + i) * WG_KROWS * 16;
+                bulk_g2s_multicast(sA + (size_t)s * WG_A_STAGE + (size_t)lane * (WG_A_ROWS * 16), a8 + r0, WG_A_ROWS * 16, bar_full + s, (uint16_t)7);
+                bulk_g2s_multicast(sB + (size_t)s * WG_B_STAGE + (size_t)lane * (WG_KROWS * 16), b8 + r0, WG_KROWS * 16, bar_full + s, (uint16_t)7);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t a_base = smem_u32(sA) + (uint32_t)(ky * 6 * 16), b_base = smem_u32(sB);      // this CTA's row offset inside the shared slab
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % WG_STAGES, k = i / WG_STAGES;
+                mbar_wait(bar_full + s, (uint32_t)(k & 1));
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < WG_KROWS / 16; ++kk) {
+                    const uint64_t bdesc = umma_desc(b_base + (uint32_t)(s * WG_B_STAGE + kk * 256), 128, WG_KROWS * 16);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint64_t adesc = umma_desc(a_base + (uint32_t)(s * WG_A_STAGE + h * 16 * WG_A_ROWS * 16 + kk * 256), 128, WG_A_ROWS * 16);
+                        tc_mma_bf16(tmem_base + (uint32_t)(h * 256), adesc, bdesc, WG_IDESC, (i > 0 || kk > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit_multicast(bar_empty + s, (uint16_t)7);
+            }
+            tc_commit(bar_acc);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(bar_acc, 0u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            float* crow = part + ((size_t)split * (9 * 256) + (size_t)(tap * 256 + h * 128 + q * 32 + lane)) * 256;
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256 + c * 32), v);
+                tc_ld_wait();
+                if (nkb > 0) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        *reinterpret_cast<float4*>(crow + c * 32 + e * 4) = make_float4(__uint_as_float(v[e * 4]), __uint_as_float(v[e * 4 + 1]),
+                                                                                       __uint_as_float(v[e * 4 + 2]), __uint_as_float(v[e * 4 + 3]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                       // nobody leaves while a peer may still write into its shared memory or barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -822,6 +956,7 @@ int az_tc_conv_raw_reserve(AzTcConvScratch* sc, int n)
 {
     if (sc->max_pairs == 0) {
         AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
+        AZ_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
         int dev = 0, sms = 148;
         AZ_CUDA(cudaGetDevice(&dev));
         AZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -834,28 +969,26 @@ int az_tc_conv_raw_reserve(AzTcConvScratch* sc, int n)
         int nc = 0;
         AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc3<true>, &cfg));
         sc->max_pairs = nc < sms / 2 ? nc : sms / 2;
+        sc->n_sm = sms;
         if (sc->max_pairs < 1) { az_set_error("the device cannot hold one CTA pair of the tower kernel"); return AZ_ERR_CUDA; }
         AZ_CUDA(cudaMalloc(&sc->d_w, TC_LAYER_BYTES));
     }
     if (n <= sc->cap_boards) return AZ_OK;
-    cudaFree(sc->d_in); sc->d_in = nullptr; sc->cap_boards = 0;
+    cudaFree(sc->d_in); cudaFree(sc->d_in3); sc->d_in = nullptr; sc->d_in3 = nullptr; sc->cap_boards = 0;
     int tiles = (n * 49 + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     tiles += tiles & 1;
     const int r_alloc = tiles * TC_TILE_ROWS + 2 * TC_HALO;
     const size_t bytes = (size_t)TC_CHUNKS * r_alloc * 16;
     AZ_CUDA(cudaMalloc(&sc->d_in, bytes));
     AZ_CUDA(cudaMemset(sc->d_in, 0, bytes));                  // padding rows and halos must read as zero
-    sc->cap_boards = n; sc->r_alloc = r_alloc;
+    AZ_CUDA(cudaMalloc(&sc->d_in3, 3 * bytes));
+    AZ_CUDA(cudaMemset(sc->d_in3, 0, 3 * bytes));
+    sc->cap_boards = n; sc->r_alloc = r_alloc; sc->dz_boards = 0;
     return AZ_OK;
 }
 
-int az_tc_conv_raw(AzTcConvScratch* sc, const float* d_src, int n, const float* d_w, int flip, float* d_out, cudaStream_t s)
+static int conv_raw_launch(AzTcConvScratch* sc, const __nv_bfloat16* in49, int n, const float* d_w, int flip, float* d_out, cudaStream_t s)
 {
-    int rc = az_tc_conv_raw_reserve(sc, n); if (rc) return rc;
-    const int rows = n * 42;
-    // (boards a larger earlier batch left behind are harmless: every board's own seven zero rows separate it from its neighbours,
-    // and rows of boards >= n are computed but never stored)
-    k_tc_chunk49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_src, rows, sc->r_alloc, sc->d_in);
     k_tc_pack_pair<<<(8 * 9 * 2 * 4 * 128) / 256, 256, 0, s>>>(d_w, flip, reinterpret_cast<__nv_bfloat16*>(sc->d_w));
     AZ_CUDA(cudaGetLastError());
     const int tiles = (n * 49 + TC_TILE_ROWS - 1) / TC_TILE_ROWS, pitems = (tiles + 1) / 2;
@@ -866,14 +999,66 @@ int az_tc_conv_raw(AzTcConvScratch* sc, const float* d_src, int n, const float* 
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    AZ_CUDA(cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<true>, (const __nv_bfloat16*)sc->d_in, (const uint8_t*)sc->d_w, (const float*)nullptr, (const float*)nullptr,
+    AZ_CUDA(cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<true>, in49, (const uint8_t*)sc->d_w, (const float*)nullptr, (const float*)nullptr,
                                (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, n, sc->r_alloc, tiles, d_out));
+    return AZ_OK;
+}
+
+int az_tc_conv_raw(AzTcConvScratch* sc, const float* d_src, int n, const float* d_w, int flip, float* d_out, cudaStream_t s)
+{
+    int rc = az_tc_conv_raw_reserve(sc, n); if (rc) return rc;
+    const int rows = n * 42;
+    // (boards a larger earlier batch left behind are harmless here: every board's own seven zero rows separate it from its
+    // neighbours, and rows of boards >= n are computed but never stored)
+    k_tc_chunk49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_src, rows, sc->r_alloc, sc->d_in, 1, 0);
+    return conv_raw_launch(sc, sc->d_in, n, d_w, flip, d_out, s);
+}
+
+// the gradient dz of a layer, converted once (plain + the two x-masked copies) for both of its consumers
+int az_tc_dz_prepare(AzTcConvScratch* sc, const float* d_dz, int n, cudaStream_t s)
+{
+    int rc = az_tc_conv_raw_reserve(sc, n); if (rc) return rc;
+    const size_t bytes = (size_t)TC_CHUNKS * sc->r_alloc * 16;
+    // the weight gradient SUMS over rows: what a larger earlier batch left behind its last board must read as zero again
+    if (n < sc->dz_boards) AZ_CUDA(cudaMemsetAsync(sc->d_in3, 0, 3 * bytes, s));
+    sc->dz_boards = n;
+    const int rows = n * 42;
+    k_tc_chunk49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_dz, rows, sc->r_alloc, sc->d_in3, 3, bytes / 16);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+// data gradient from the prepared dz: out[r][ci] = sum_{t,co} dz[nb(r,t)][co] * w[8-t][ci][co]
+int az_tc_dgrad_prepared(AzTcConvScratch* sc, int n, const float* d_w, float* d_out, cudaStream_t s)
+{
+    return conv_raw_launch(sc, sc->d_in3, n, d_w, 1, d_out, s);
+}
+
+// weight gradient partials [splits][9 * 256][256] from the prepared dz and the layer's fp32 input activation; returns the split count
+int az_tc_wgrad_prepared(AzTcConvScratch* sc, const float* d_a, int n, float* d_part, int max_splits, int* splits_out, cudaStream_t s)
+{
+    const int rows = n * 42;
+    k_tc_chunk49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_a, rows, sc->r_alloc, sc->d_in, 1, 0);
+    const int kb_total = (n * 49 + WG_KROWS - 1) / WG_KROWS;                   // 64-row K blocks that hold board rows
+    int want = sc->n_sm / 9; if (want > max_splits) want = max_splits; if (want > kb_total) want = kb_total; if (want < 1) want = 1;
+    const int per = (kb_total + want - 1) / want, splits = (kb_total + per - 1) / per;      // no empty split
+    const size_t bytes = (size_t)TC_CHUNKS * sc->r_alloc * 16;
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(9, (unsigned)splits); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = WG_SMEM; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 3; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        AZ_CUDA(cudaLaunchKernelEx(&cfg, k_tc_wgrad, (const __nv_bfloat16*)sc->d_in, (const __nv_bfloat16*)sc->d_in3, bytes, sc->r_alloc, kb_total, per, d_part));
+    }
+    *splits_out = splits;
     return AZ_OK;
 }
 
 void az_tc_conv_raw_release(AzTcConvScratch* sc)
 {
-    cudaFree(sc->d_in); cudaFree(sc->d_w);
+    cudaFree(sc->d_in); cudaFree(sc->d_in3); cudaFree(sc->d_w);
     *sc = AzTcConvScratch();
 }
 

@@ -56,6 +56,8 @@ int az_nn_sync_host(az_nn* nn);      // az_nn.cu
 
 struct AzTrainState {
     int cap = 0;                                       // boards the work buffers are sized for
+    bool dz_prepared = false;                          // the current layer's dz sits converted in conv.d_in3 (weight gradient done, data gradient next)
+    bool wgrad_by_gemm = false;                        // AZ_TRAIN_WGRAD=gemm: A/B switch back to the transposed-im2col GEMM
     bool conv_by_gemm = false;                         // AZ_TRAIN_CONV=gemm: A/B switch back to im2col + k_tc_gemm for the 256-channel convolutions
     int precision = AZ_NN_FP32;                        // AZ_NN_BF16: the three contractions run on the tensor cores (az_tc_gemm.cu)
     __nv_bfloat16 *d_colA = nullptr, *d_colB = nullptr;   // GEMM operands: im2col / transposed im2col, weights / transposed gradient
@@ -752,8 +754,10 @@ static int train_reserve(az_nn* nn, AzTrainState* t, int n)
 // one raw 3x3 convolution out[r][256] = conv(in[r][cin], w[9][cin][256]) (flip: the data-gradient kernel w[8-t] transposed)
 static int conv_any(az_nn* nn, AzTrainState* t, const float* in, int n, int cin, const float* w, int flip, float* out, cudaStream_t s)
 {
-    if (t->precision == AZ_NN_BF16 && cin == TR_CH && !t->conv_by_gemm)         // implicit GEMM on the tower kernel (no unrolled operand in HBM)
+    if (t->precision == AZ_NN_BF16 && cin == TR_CH && !t->conv_by_gemm) {       // implicit GEMM on the tower kernel (no unrolled operand in HBM)
+        if (flip && t->dz_prepared) { t->dz_prepared = false; return az_tc_dgrad_prepared(&t->conv, n, w, out, s); }
         return az_tc_conv_raw(&t->conv, in, n, w, flip, out, s);
+    }
     if (t->precision == AZ_NN_BF16) {
         const int rows = n * 42, mp = (int)tr_mp(rows), cpad = (cin + 7) / 8 * 8, kp = (int)tr_kp(9 * cpad);
         int rc = az_tg_im2col(in, rows, cin, cpad, mp, kp, t->d_src16, t->d_colA, s); if (rc) return rc;
@@ -811,6 +815,15 @@ static int bn_backward(az_nn* nn, AzTrainState* t, int L, int n, const float* do
 
 static int conv_wgrad(az_nn* nn, AzTrainState* t, int L, int n, const float* in, int cin, const float* dz, cudaStream_t s)
 {
+    t->dz_prepared = false;
+    if (t->precision == AZ_NN_BF16 && cin == TR_CH && !t->conv_by_gemm && !t->wgrad_by_gemm) {
+        // nine GEMMs over the board rows with both operands read in place from the chunked bf16 buffers (k_tc_wgrad)
+        int rc = az_tc_dz_prepare(&t->conv, dz, n, s); if (rc) return rc;
+        int splits = 1;
+        rc = az_tc_wgrad_prepared(&t->conv, in, n, t->d_wpart, TR_WG_SPLITS, &splits, s); if (rc) return rc;
+        t->dz_prepared = true;
+        return az_tg_reduce(t->d_wpart, splits, 9 * TR_CH, 9 * TR_CH, gvar(nn, t, tr_conv_name(L) + "/kernel"), s);
+    }
     if (t->precision == AZ_NN_BF16) {                          // dW[t*cin + ci][co] = im2col(in)^T . dz, K = board cells, split over K
         const int rows = n * 42, mp = (int)tr_mp(9 * cin), kp = (int)tr_kp(rows);
         const int splits = az_tg_splits(kp, 148 / (mp / 128) > TR_WG_SPLITS ? TR_WG_SPLITS : 148 / (mp / 128));
@@ -976,6 +989,8 @@ extern "C" int az_nn_train_precision(az_nn* nn, int precision)
     t->precision = precision;
     const char* ec = getenv("AZ_TRAIN_CONV");
     t->conv_by_gemm = ec && strcmp(ec, "gemm") == 0;
+    const char* ew = getenv("AZ_TRAIN_WGRAD");
+    t->wgrad_by_gemm = ew && strcmp(ew, "gemm") == 0;
     return AZ_OK;
 }
 
