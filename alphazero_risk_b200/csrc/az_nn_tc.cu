@@ -34,7 +34,7 @@
 #include "az_nn.cuh"
 
 #define TC_TILE_ROWS 128
-#define TC_HALO 8
+#define TC_HALO AZ_TC_HALO
 #define TC_A_ROWS (TC_TILE_ROWS + 2 * TC_HALO)              // 144
 #define TC_CHUNKS 32                                         // 256 channels / 8
 #ifndef TC_STAGES
@@ -975,6 +975,8 @@ int az_tc_conv_raw_reserve(AzTcConvScratch* sc, int n)
     }
     if (n <= sc->cap_boards) return AZ_OK;
     cudaFree(sc->d_in); cudaFree(sc->d_in3); sc->d_in = nullptr; sc->d_in3 = nullptr; sc->cap_boards = 0;
+    for (__nv_bfloat16* p : sc->a49) cudaFree(p);
+    sc->a49.clear();
     int tiles = (n * 49 + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     tiles += tiles & 1;
     const int r_alloc = tiles * TC_TILE_ROWS + 2 * TC_HALO;
@@ -1034,11 +1036,44 @@ int az_tc_dgrad_prepared(AzTcConvScratch* sc, int n, const float* d_w, float* d_
     return conv_raw_launch(sc, sc->d_in3, n, d_w, 1, d_out, s);
 }
 
+int az_tc_layers_reserve(AzTcConvScratch* sc, int n, int layers)
+{
+    int rc = az_tc_conv_raw_reserve(sc, n); if (rc) return rc;
+    const size_t bytes = (size_t)TC_CHUNKS * sc->r_alloc * 16;
+    while ((int)sc->a49.size() < layers) {
+        __nv_bfloat16* p = nullptr;
+        AZ_CUDA(cudaMalloc(&p, bytes));
+        AZ_CUDA(cudaMemset(p, 0, bytes));
+        sc->a49.push_back(p);
+    }
+    return AZ_OK;
+}
+
+int az_tc_dz_target(AzTcConvScratch* sc, int n, cudaStream_t s, __nv_bfloat16** d_dz3, size_t* var_stride_u4)
+{
+    int rc = az_tc_conv_raw_reserve(sc, n); if (rc) return rc;
+    const size_t bytes = (size_t)TC_CHUNKS * sc->r_alloc * 16;
+    if (n < sc->dz_boards) AZ_CUDA(cudaMemsetAsync(sc->d_in3, 0, 3 * bytes, s));      // see az_tc_dz_prepare
+    sc->dz_boards = n;
+    *d_dz3 = sc->d_in3; *var_stride_u4 = bytes / 16;
+    return AZ_OK;
+}
+
+int az_tc_conv_raw49(AzTcConvScratch* sc, const __nv_bfloat16* in49, int n, const float* d_w, int flip, float* d_out, cudaStream_t s)
+{
+    return conv_raw_launch(sc, in49, n, d_w, flip, d_out, s);
+}
+
 // weight gradient partials [splits][9 * 256][256] from the prepared dz and the layer's fp32 input activation; returns the split count
 int az_tc_wgrad_prepared(AzTcConvScratch* sc, const float* d_a, int n, float* d_part, int max_splits, int* splits_out, cudaStream_t s)
 {
     const int rows = n * 42;
     k_tc_chunk49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_a, rows, sc->r_alloc, sc->d_in, 1, 0);
+    return az_tc_wgrad49(sc, sc->d_in, n, d_part, max_splits, splits_out, s);
+}
+
+int az_tc_wgrad49(AzTcConvScratch* sc, const __nv_bfloat16* a49, int n, float* d_part, int max_splits, int* splits_out, cudaStream_t s)
+{
     const int kb_total = (n * 49 + WG_KROWS - 1) / WG_KROWS;                   // 64-row K blocks that hold board rows
     int want = sc->n_sm / 9; if (want > max_splits) want = max_splits; if (want > kb_total) want = kb_total; if (want < 1) want = 1;
     const int per = (kb_total + want - 1) / want, splits = (kb_total + per - 1) / per;      // no empty split
@@ -1050,7 +1085,7 @@ int az_tc_wgrad_prepared(AzTcConvScratch* sc, const float* d_a, int n, float* d_
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 3; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        AZ_CUDA(cudaLaunchKernelEx(&cfg, k_tc_wgrad, (const __nv_bfloat16*)sc->d_in, (const __nv_bfloat16*)sc->d_in3, bytes, sc->r_alloc, kb_total, per, d_part));
+        AZ_CUDA(cudaLaunchKernelEx(&cfg, k_tc_wgrad, a49, (const __nv_bfloat16*)sc->d_in3, bytes, sc->r_alloc, kb_total, per, d_part));
     }
     *splits_out = splits;
     return AZ_OK;
@@ -1059,6 +1094,7 @@ int az_tc_wgrad_prepared(AzTcConvScratch* sc, const float* d_a, int n, float* d_
 void az_tc_conv_raw_release(AzTcConvScratch* sc)
 {
     cudaFree(sc->d_in); cudaFree(sc->d_in3); cudaFree(sc->d_w);
+    for (__nv_bfloat16* p : sc->a49) cudaFree(p);
     *sc = AzTcConvScratch();
 }
 

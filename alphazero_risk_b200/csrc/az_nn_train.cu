@@ -318,6 +318,111 @@ __global__ void __launch_bounds__(256) k_tr_add_masked(float* __restrict__ dst, 
     if (i < total && a[i] > 0.0f) dst[i] += dout[i];
 }
 
+// ---------------------------------------------------------------- tensor-core mode: BatchNorm passes that also emit the bf16 operands
+// Block = 32 rows x 256 channels, thread = (row, 8-channel chunk) four times over; the chunk values go through shared memory so that the
+// 49-row chunked bf16 layout of the tower kernel ([chunk][AZ_TC_HALO + board * 49 + cell][8]) is written in contiguous runs.
+__device__ __forceinline__ void ld8(const float* __restrict__ p, float (&v)[8])
+{
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+// k_tr_bn_apply49: a = relu(gamma * (z - mean) * invstd + beta [+ skip]) as fp32 AND as the next convolution's operand.
+__global__ void __launch_bounds__(256) k_tr_bn_apply49(const float* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ skip, float* __restrict__ a,
+                                                        int rows, int stem, __nv_bfloat16* __restrict__ a49, int r_alloc)
+{
+    __shared__ uint4 tile[32][33];
+    const int r0 = blockIdx.x * 32;
+    for (int j = threadIdx.x; j < 1024; j += 256) {
+        const int rl = j >> 5, cc = j & 31, r = r0 + rl;
+        if (r < rows) {
+            const size_t o = (size_t)r * TR_CH + cc * 8;
+            const float4 z0 = *reinterpret_cast<const float4*>(z + o), z1 = *reinterpret_cast<const float4*>(z + o + 4);
+            float v[8] = { z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w };
+            if (stem) {
+                const int grp = (r % 42) / 6;
+                const float mu = stats[grp], inv = stats[TR_CH + grp], ga = gamma[grp], be = beta[grp];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = (v[e] - mu) * inv * ga + be;
+            } else {
+                float mu[8], inv[8], ga[8], be[8];
+                ld8(stats + cc * 8, mu); ld8(stats + TR_CH + cc * 8, inv); ld8(gamma + cc * 8, ga); ld8(beta + cc * 8, be);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = (v[e] - mu[e]) * inv[e] * ga[e] + be[e];
+            }
+            if (skip) {
+                const float4 s0 = *reinterpret_cast<const float4*>(skip + o), s1 = *reinterpret_cast<const float4*>(skip + o + 4);
+                v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = v[e] > 0.0f ? v[e] : 0.0f;
+            *reinterpret_cast<float4*>(a + o) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(a + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            uint4 pk;
+            __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            tile[rl][cc] = pk;
+        }
+    }
+    __syncthreads();
+    uint4* o4 = reinterpret_cast<uint4*>(a49);
+    for (int j = threadIdx.x; j < 1024; j += 256) {
+        const int cl = j >> 5, rl = j & 31, r = r0 + rl;
+        if (r < rows) { const int bb = r / 42; o4[(size_t)cl * r_alloc + AZ_TC_HALO + (size_t)bb * 49 + (r - bb * 42)] = tile[rl][cl]; }
+    }
+}
+
+// k_tr_bn_bwd49: dz = gamma * invstd * (g - c1 - xhat * c2), g = dout * [a > 0], written as the data gradient's / weight gradient's
+// bf16 operand: plain, cells with x = 0 zeroed, cells with x = 5 zeroed (var_stride_u4 apart); the fp32 copy only if dz32 != NULL.
+__global__ void __launch_bounds__(256) k_tr_bn_bwd49(const float* __restrict__ z, const float* __restrict__ dout, const float* __restrict__ a,
+                                                      const float* __restrict__ stats, const float* __restrict__ gamma, float* __restrict__ dz32,
+                                                      int rows, __nv_bfloat16* __restrict__ dz49, int r_alloc, size_t var_stride_u4)
+{
+    __shared__ uint4 tile[32][33];
+    const int r0 = blockIdx.x * 32;
+    for (int j = threadIdx.x; j < 1024; j += 256) {
+        const int rl = j >> 5, cc = j & 31, r = r0 + rl;
+        if (r < rows) {
+            const size_t o = (size_t)r * TR_CH + cc * 8;
+            const float4 z0 = *reinterpret_cast<const float4*>(z + o), z1 = *reinterpret_cast<const float4*>(z + o + 4);
+            const float4 d0 = *reinterpret_cast<const float4*>(dout + o), d1 = *reinterpret_cast<const float4*>(dout + o + 4);
+            const float4 a0 = *reinterpret_cast<const float4*>(a + o), a1 = *reinterpret_cast<const float4*>(a + o + 4);
+            const float zz[8] = { z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w }, dd[8] = { d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w };
+            const float aa[8] = { a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w };
+            float v[8], mu[8], inv[8], c1[8], c2[8], ga[8];
+            ld8(stats + cc * 8, mu); ld8(stats + TR_CH + cc * 8, inv); ld8(stats + 2 * TR_CH + cc * 8, c1); ld8(stats + 3 * TR_CH + cc * 8, c2);
+            ld8(gamma + cc * 8, ga);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float g = aa[e] > 0.0f ? dd[e] : 0.0f;
+                const float xh = (zz[e] - mu[e]) * inv[e];
+                v[e] = ga[e] * inv[e] * (g - c1[e] - xh * c2[e]);
+            }
+            if (dz32) {
+                *reinterpret_cast<float4*>(dz32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dz32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            uint4 pk;
+            __nv_bfloat162* p2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            tile[rl][cc] = pk;
+        }
+    }
+    __syncthreads();
+    uint4* o4 = reinterpret_cast<uint4*>(dz49);
+    for (int j = threadIdx.x; j < 1024; j += 256) {
+        const int cl = j >> 5, rl = j & 31, r = r0 + rl;
+        if (r < rows) {
+            const int bb = r / 42, p = r - bb * 42, x = p % 6;
+            const size_t at = (size_t)cl * r_alloc + AZ_TC_HALO + (size_t)bb * 49 + p;
+            const uint4 v = tile[rl][cl], zero = make_uint4(0u, 0u, 0u, 0u);
+            o4[at] = v; o4[var_stride_u4 + at] = x == 0 ? zero : v; o4[2 * var_stride_u4 + at] = x == 5 ? zero : v;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- weight gradient of a 3x3 convolution
 // dW[t][ci][co] = sum_r in[nb(r, t)][ci] * dz[r][co].  Block = (32 input channels) x (64 output channels) x all 9 taps for one split of
 // the boards; 256 threads, thread = 2 ci x 4 co x 9 taps = 72 accumulators; one board (42 rows) staged in shared memory per iteration.
@@ -752,10 +857,12 @@ static int train_reserve(az_nn* nn, AzTrainState* t, int n)
 }
 
 // one raw 3x3 convolution out[r][256] = conv(in[r][cin], w[9][cin][256]) (flip: the data-gradient kernel w[8-t] transposed)
-static int conv_any(az_nn* nn, AzTrainState* t, const float* in, int n, int cin, const float* w, int flip, float* out, cudaStream_t s)
+static int conv_any(az_nn* nn, AzTrainState* t, const float* in, int n, int cin, const float* w, int flip, float* out, cudaStream_t s,
+                    const __nv_bfloat16* in49 = nullptr)
 {
     if (t->precision == AZ_NN_BF16 && cin == TR_CH && !t->conv_by_gemm) {       // implicit GEMM on the tower kernel (no unrolled operand in HBM)
         if (flip && t->dz_prepared) { t->dz_prepared = false; return az_tc_dgrad_prepared(&t->conv, n, w, out, s); }
+        if (!flip && in49) return az_tc_conv_raw49(&t->conv, in49, n, w, 0, out, s);
         return az_tc_conv_raw(&t->conv, in, n, w, flip, out, s);
     }
     if (t->precision == AZ_NN_BF16) {
@@ -775,6 +882,9 @@ static int conv_any(az_nn* nn, AzTrainState* t, const float* in, int n, int cin,
     return AZ_OK;
 }
 
+// the fused tensor-core route: tower kernel + k_tc_wgrad with the bf16 operands written by the BatchNorm passes themselves
+static bool tr_tower(const AzTrainState* t) { return t->precision == AZ_NN_BF16 && !t->conv_by_gemm && !t->wgrad_by_gemm; }
+
 static std::string tr_block_sfx(int i) { return std::to_string(i) + std::string(1, (char)('a' + i)); }
 // layer L >= 1 of the tower: block (L - 1) / 2, branch 2a for odd L, 2b for even L
 static std::string tr_conv_name(int L) { return L == 0 ? "conv" : "res" + tr_block_sfx((L - 1) / 2) + ((L & 1) ? "_branch2a" : "_branch2b"); }
@@ -793,7 +903,11 @@ static int bn_forward(az_nn* nn, AzTrainState* t, int L, int n, const float* ski
     k_tr_stats<<<TR_STAT_CHUNKS, 256, 0, s>>>(t->z[(size_t)L], nullptr, nullptr, st, rows, 0, stem, t->d_part);
     k_tr_stats_final<<<8, 256, 0, s>>>(t->d_part, stem ? 7 : TR_CH, stem ? (double)n * 6 * TR_CH : (double)rows, 0, st,
                                        dvar(nn, bn + "/moving_mean"), dvar(nn, bn + "/moving_variance"), nullptr, nullptr);
-    k_tr_bn_apply<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(t->z[(size_t)L], st, dvar(nn, bn + "/gamma"), dvar(nn, bn + "/beta"), skip, t->a[(size_t)L], total, stem);
+    if (tr_tower(t) && L + 1 < 2 * nn->blocks + 1)          // the next 256-channel convolution (and its weight gradient) read the chunked bf16 copy
+        k_tr_bn_apply49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(t->z[(size_t)L], st, dvar(nn, bn + "/gamma"), dvar(nn, bn + "/beta"), skip,
+                                                                  t->a[(size_t)L], rows, stem, t->conv.a49[(size_t)L], t->conv.r_alloc);
+    else
+        k_tr_bn_apply<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(t->z[(size_t)L], st, dvar(nn, bn + "/gamma"), dvar(nn, bn + "/beta"), skip, t->a[(size_t)L], total, stem);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
@@ -808,20 +922,27 @@ static int bn_backward(az_nn* nn, AzTrainState* t, int L, int n, const float* do
     k_tr_stats<<<TR_STAT_CHUNKS, 256, 0, s>>>(t->z[(size_t)L], dout, t->a[(size_t)L], st, rows, 1, stem, t->d_part);
     k_tr_stats_final<<<8, 256, 0, s>>>(t->d_part, stem ? 7 : TR_CH, stem ? (double)n * 6 * TR_CH : (double)rows, 1, st, nullptr, nullptr,
                                        gvar(nn, t, bn + "/gamma"), gvar(nn, t, bn + "/beta"));
-    k_tr_bn_bwd<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(t->z[(size_t)L], dout, t->a[(size_t)L], st, dvar(nn, bn + "/gamma"), dz, total, stem);
+    t->dz_prepared = false;
+    if (tr_tower(t) && L >= 1) {                            // dz goes straight into the operand buffers of k_tc_wgrad and the data gradient; no fp32 copy
+        __nv_bfloat16* dz3 = nullptr; size_t vs = 0;
+        int rc = az_tc_dz_target(&t->conv, n, s, &dz3, &vs); if (rc) return rc;
+        k_tr_bn_bwd49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(t->z[(size_t)L], dout, t->a[(size_t)L], st, dvar(nn, bn + "/gamma"), nullptr, rows,
+                                                                dz3, t->conv.r_alloc, vs);
+        t->dz_prepared = true;
+    } else
+        k_tr_bn_bwd<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(t->z[(size_t)L], dout, t->a[(size_t)L], st, dvar(nn, bn + "/gamma"), dz, total, stem);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
 
 static int conv_wgrad(az_nn* nn, AzTrainState* t, int L, int n, const float* in, int cin, const float* dz, cudaStream_t s)
 {
-    t->dz_prepared = false;
-    if (t->precision == AZ_NN_BF16 && cin == TR_CH && !t->conv_by_gemm && !t->wgrad_by_gemm) {
-        // nine GEMMs over the board rows with both operands read in place from the chunked bf16 buffers (k_tc_wgrad)
-        int rc = az_tc_dz_prepare(&t->conv, dz, n, s); if (rc) return rc;
+    if (tr_tower(t) && cin == TR_CH) {
+        // nine GEMMs over the board rows with both operands read in place from the chunked bf16 buffers (k_tc_wgrad): dz was written
+        // by k_tr_bn_bwd49, the layer's input activation by k_tr_bn_apply49 during the forward pass
+        AZ_REQUIRE(t->dz_prepared && L >= 1, "weight gradient before its dz");
         int splits = 1;
-        rc = az_tc_wgrad_prepared(&t->conv, in, n, t->d_wpart, TR_WG_SPLITS, &splits, s); if (rc) return rc;
-        t->dz_prepared = true;
+        int rc = az_tc_wgrad49(&t->conv, t->conv.a49[(size_t)L - 1], n, t->d_wpart, TR_WG_SPLITS, &splits, s); if (rc) return rc;
         return az_tg_reduce(t->d_wpart, splits, 9 * TR_CH, 9 * TR_CH, gvar(nn, t, tr_conv_name(L) + "/kernel"), s);
     }
     if (t->precision == AZ_NN_BF16) {                          // dW[t*cin + ci][co] = im2col(in)^T . dz, K = board cells, split over K
@@ -849,6 +970,7 @@ static int train_step_dev(az_nn* nn, const float* d_x, const float* d_tp, const 
     rc = slots_to_device(nn, t); if (rc) return rc;
     rc = train_reserve(nn, t, n); if (rc) return rc;
     if (t->precision == AZ_NN_BF16) { rc = az_tg_init(); if (rc) return rc; }
+    if (tr_tower(t)) { rc = az_tc_layers_reserve(&t->conv, n, 2 * nn->blocks); if (rc) return rc; }
     const int layers = 2 * nn->blocks + 1, rows = n * 42;
     const size_t total = (size_t)rows * TR_CH;
     const unsigned egrid = (unsigned)((total + 255) / 256);
@@ -856,7 +978,8 @@ static int train_step_dev(az_nn* nn, const float* d_x, const float* d_tp, const 
     rc = conv_any(nn, t, d_x, n, AZ_NN_IN_CH, dvar(nn, "conv/kernel"), 0, t->z[0], s); if (rc) return rc;
     rc = bn_forward(nn, t, 0, n, nullptr, s); if (rc) return rc;
     for (int L = 1; L < layers; ++L) {
-        rc = conv_any(nn, t, t->a[(size_t)L - 1], n, TR_CH, dvar(nn, tr_conv_name(L) + "/kernel"), 0, t->z[(size_t)L], s); if (rc) return rc;
+        rc = conv_any(nn, t, t->a[(size_t)L - 1], n, TR_CH, dvar(nn, tr_conv_name(L) + "/kernel"), 0, t->z[(size_t)L], s,
+                      tr_tower(t) ? t->conv.a49[(size_t)L - 1] : nullptr); if (rc) return rc;
         rc = bn_forward(nn, t, L, n, (L & 1) ? nullptr : t->a[(size_t)L - 2], s); if (rc) return rc;      // 2b adds the block input
     }
     const float* act = t->a[(size_t)layers - 1];
