@@ -194,3 +194,48 @@ def test_selfplay_run_device_loop(api):
             t.clear()
     assert (env.export_aos()[0] == o.data()).all()
     mc.close(); env.close()
+
+
+def test_full_size_search_properties_and_shard_invariance(api):
+    """BASELINE configs[2] at full size (4096 games x 64 simulations, 5-block network, bf16 tcgen05 forward): properties that need no
+    oracle replay — visit counts live on legal moves only and add up to the root's sumN >= simulations, pi is the normalised count
+    vector, the move played is legal (no illegal / overflow counters), every simulation is counted, the search is reproducible bit for
+    bit, and the second half of the games searched as its own shard (first_game_id = 2048, the multi-GPU partitioning) reproduces the
+    second half of the full run exactly."""
+    n, sims, moves = 4096, 64, 3
+    rules = api.default_rules(mcts_simulations=sims, threads_per_mcts=1)
+    net = api.Net(blocks=5, seed=1234)
+
+    def run(count, first):
+        env = api.Env(count, rules=rules, first_game_id=first)
+        env.reset(SEED)
+        mc = api.Mcts(env, net=net, evaluator=api.EVAL_NN, precision=api.BF16)
+        out = []
+        for _ in range(moves):
+            valid = env.valid_moves()
+            res = mc.search(pick_mode=api.PICK_SELFPLAY, apply_move=True)
+            out.append((valid, res["N"].copy(), res["pi"].copy(), res["move"].copy()))
+        cnt = mc.counters()
+        stats = mc.root_stats()
+        final = env.export_aos().copy()
+        mc.close(); env.close()
+        return out, cnt, final, stats
+
+    full, cnt, final, _ = run(n, 0)
+    assert cnt["errors"] == 0 and cnt["illegal"] == 0 and cnt["sims"] == n * sims * moves and cnt["steps"] == n * moves
+    for valid, N, pi, move in full:
+        legal = ((valid[:, None] >> np.arange(43, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool)
+        assert (N[~legal] == 0).all()
+        tot = N.sum(1)
+        assert (tot >= sims - 1).all()                       # the root's own expansion is not a visit of a child
+        assert np.allclose(pi, N / tot[:, None], atol=1e-6)
+        assert legal[np.arange(n), move].all()
+    again, cnt2, final2, _ = run(n, 0)
+    assert cnt2 == cnt and (final2 == final).all()
+    for (v1, n1, p1, m1), (v2, n2, p2, m2) in zip(full, again):
+        assert (n1 == n2).all() and (m1 == m2).all() and (p1.view(np.uint32) == p2.view(np.uint32)).all()
+    half, _, final_h, _ = run(n // 2, n // 2)
+    assert (final_h == final[n // 2:]).all()
+    for (v1, n1, p1, m1), (v2, n2, p2, m2) in zip(full, half):
+        assert (n1[n // 2:] == n2).all() and (m1[n // 2:] == m2).all()
+    net.close()
