@@ -57,10 +57,19 @@ int az_upload_tables()
     std::lock_guard<std::mutex> lk(g_tables_mu);
     if (dev < 0 || dev >= 64) { az_set_error("device index %d out of range", dev); return AZ_ERR_INVALID_ARG; }
     if (g_tables_dev[dev]) return AZ_OK;
-    uint64_t h[AZ_TABLE_U64];
+    static uint64_t h[AZ_TABLE_U64 + AZ_LUT11_U64];               // guarded by g_tables_mu
     memcpy(h, AZ_NBR_UNION_LUT_H, sizeof AZ_NBR_UNION_LUT_H);
     memcpy(h + 7 * 64, AZ_NBR_MASK_H, sizeof AZ_NBR_MASK_H);
     memcpy(h + 7 * 64 + 42, AZ_NBR_LIST6_H, sizeof AZ_NBR_LIST6_H);
+    // the rollout kernel's wide tables (az_nbr_union(AzTablesWide)): entry v of table k = union of the neighbour masks of
+    // the lands 11k + b, b = the set bits of v
+    for (int k = 0; k < 4; ++k)
+        for (int v = 0; v < 2048; ++v) {
+            uint64_t u = 0;
+            for (int b = 0; b < 11; ++b)
+                if (((v >> b) & 1) && 11 * k + b < AZ_LANDS) u |= AZ_NBR_MASK_H[11 * k + b];
+            h[AZ_TABLE_U64 + k * 2048 + v] = u;
+        }
     uint64_t* d = nullptr;
     AZ_CUDA(cudaMalloc(&d, sizeof h));
     AZ_CUDA(cudaMemcpy(d, h, sizeof h, cudaMemcpyHostToDevice));
@@ -90,6 +99,25 @@ __device__ __forceinline__ AzTables env_stage_tables(EnvSmem& sm, const uint64_t
     for (int i = threadIdx.x; i < AZ_TABLE_U64; i += blockDim.x) sm.tab[i] = g_tab[i];
     __syncthreads();
     return az_tables_from_smem(sm.tab);
+}
+
+// k_env_rollout's (dynamic) shared memory: the same two members first, so the per-thread helpers below work on it unchanged
+struct EnvSmemWide {
+    uint64_t tab[AZ_TABLE_U64];
+    uint32_t col[ENV_COL_WORDS * ENV_BLOCK];
+    uint64_t lut11[AZ_LUT11_U64];
+};
+
+__device__ __forceinline__ AzTablesWide env_stage_tables_wide(EnvSmemWide& sm, const uint64_t* __restrict__ g_tab)
+{
+    for (int i = threadIdx.x; i < AZ_TABLE_U64; i += blockDim.x) sm.tab[i] = g_tab[i];
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(g_tab + AZ_TABLE_U64);     // AZ_TABLE_U64 is even: 16-byte aligned
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(sm.lut11);
+    for (int i = threadIdx.x; i < AZ_LUT11_U64 / 2; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    AzTablesWide t;
+    t.lut = sm.tab; t.nbr = sm.tab + 7 * 64; t.list6 = sm.tab + 7 * 64 + 42; t.lut11 = sm.lut11;
+    return t;
 }
 
 struct EnvCtx {
@@ -251,8 +279,10 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout(uint32_t* __restrict_
                                                             int n_steps, uint64_t seed, uint32_t first_game, AzRulesDev rules,
                                                             unsigned long long* __restrict__ counters, int park_f, int park_r)
 {
-    __shared__ EnvSmem sm;
-    AzTables T = env_stage_tables(sm, g_tab);
+    extern __shared__ __align__(16) unsigned char env_dyn_smem[];
+    EnvSmemWide& smw = *reinterpret_cast<EnvSmemWide*>(env_dyn_smem);
+    EnvSmem& sm = *reinterpret_cast<EnvSmem*>(env_dyn_smem);
+    const AzTablesWide T = env_stage_tables_wide(smw, g_tab);
     const int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
     const bool live = gi < n;
     unsigned games = 0, w0 = 0, w1 = 0, dr = 0;
@@ -809,9 +839,15 @@ extern "C" int az_env_rollout(az_env* e, int n_steps, void* stream)
     if (v1)
         k_env_rollout_v1<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
                                                                dev_rules(e->rules), e->d_counters);
-    else
-        k_env_rollout<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
+    else {
+        static bool smem_set[64] = { false };                      // 64 KB of wide tables + columns: above the 48 KB default
+        if (!smem_set[e->device & 63]) {
+            AZ_CUDA(cudaFuncSetAttribute(k_env_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmemWide)));
+            smem_set[e->device & 63] = true;
+        }
+        k_env_rollout<<<env_grid(e->n), ENV_BLOCK, sizeof(EnvSmemWide), s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
                                                             dev_rules(e->rules), e->d_counters, park_f, park_r);
+    }
     AZ_CUDA(cudaGetLastError());
     AZ_CUDA(cudaEventRecord(e->ev1, s));
     e->timed = true;

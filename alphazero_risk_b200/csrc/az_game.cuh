@@ -83,6 +83,20 @@ __device__ __forceinline__ uint64_t az_nbr_union(const AzTables& T, uint64_t S)
     return u;
 }
 
+// The 512-move rollout kernel trades shared memory for instructions: four 2048-entry tables indexed by 11-bit slices of S
+// (64 KB, built at upload time) instead of seven 64-entry ones.  Everything that takes the tables as a template parameter
+// picks the matching az_nbr_union overload.
+#define AZ_LUT11_U64 (4 * 2048)
+struct AzTablesWide : AzTables {
+    const uint64_t* lut11;
+};
+__device__ __forceinline__ uint64_t az_nbr_union(const AzTablesWide& T, uint64_t S)
+{
+    const uint32_t lo = (uint32_t)S, hi = (uint32_t)(S >> 32);
+    const uint32_t i0 = lo & 2047u, i1 = (lo >> 11) & 2047u, i2 = __funnelshift_r(lo, hi, 22) & 2047u, i3 = (hi >> 1) & 2047u;
+    return (T.lut11[i0] | T.lut11[2048 + i1]) | (T.lut11[4096 + i2] | T.lut11[6144 + i3]);
+}
+
 struct AzRulesDev {
     int allow_yield, limit_reinforcement, limit_attack, max_game_rounds, min_unit_move;
 };
@@ -153,6 +167,16 @@ __device__ __forceinline__ void az_set_land(AzGame& g, LandT& land, int i, uint3
     g.full = army == AZ_ARMY_MAX ? (g.full | m) : (g.full & ~m);
 }
 
+// the same write when the land keeps its owner (`owner` is only repeated into the byte): the ownership masks do not change
+template <class LandT>
+__device__ __forceinline__ void az_set_army(AzGame& g, LandT& land, int i, uint32_t army, uint32_t owner)
+{
+    land.set(i, (army & 63u) | (owner << 6));
+    uint64_t m = 1ull << i;
+    g.gt1 = army > 1 ? (g.gt1 | m) : (g.gt1 & ~m);
+    g.full = army == AZ_ARMY_MAX ? (g.full | m) : (g.full & ~m);
+}
+
 // ---------------------------------------------------------------- rules
 // State::calculateReinforcementValue, state/state.cpp:457-491
 __device__ __forceinline__ int az_reinforcement_value(uint64_t owned)
@@ -179,7 +203,8 @@ __device__ __forceinline__ int az_game_status(const AzGame& g, const AzRulesDev&
 }
 
 // PlayerStatus::attackLandsWithArmy of player p: N(owned ∧ army>1) \ owned
-__device__ __forceinline__ uint64_t az_attack_army(const AzGame& g, const AzTables& T, uint32_t p)
+template <class TabT>
+__device__ __forceinline__ uint64_t az_attack_army(const AzGame& g, const TabT& T, uint32_t p)
 {
     uint64_t o = g.own(p);
     return az_nbr_union(T, o & g.gt1) & ~o;
@@ -269,15 +294,25 @@ struct AzDiceTape {                   // explicit dice (golden vectors)
 // tied lands.  (The walk replaces the reference's recursion by parent pointers: after returning to a
 // node, rescanning its list from the start finds the same next child because everything before it is
 // already seen.)
-template <class LandT, class ScratchT>
-__device__ __forceinline__ void az_fortify_source(const AzGame& g, const LandT& land, ScratchT& parent, const AzTables& T,
+template <class LandT, class ScratchT, class TabT>
+__device__ __forceinline__ void az_fortify_source(const AzGame& g, const LandT& land, ScratchT& parent, const TabT& T,
                                                   int li, int& from_out, int& amount_out)
 {
     const uint64_t owned = g.own(g.cur);
     uint64_t comp = 1ull << li;
-    for (;;) { uint64_t n = (comp | az_nbr_union(T, comp)) & owned; if (n == comp) break; comp = n; }   // (a per-land BFS has fewer instructions but a longer dependent chain: measured 4 % slower)
+    // Only lands with army >= 2 can be the source, so the closure may stop as soon as it has absorbed every such land the
+    // mover owns (`rest` empty); the full component is only needed by the tie walk below, which then finishes it.
+    const uint64_t movable = owned & g.gt1 & ~(1ull << li);
     from_out = -1; amount_out = 0;
-    uint64_t cand = comp & ~(1ull << li) & g.gt1;                       // army - 1 > 0
+    if (movable == 0) return;
+    bool closed = false;
+    for (;;) {     // (a per-land BFS has fewer instructions but a longer dependent chain: measured 4 % slower)
+        uint64_t n = (comp | az_nbr_union(T, comp)) & owned;
+        if (n == comp) { closed = true; break; }
+        comp = n;
+        if ((movable & ~comp) == 0) break;
+    }
+    uint64_t cand = comp & movable;                                     // army - 1 > 0
     if (cand == 0) return;
     const uint64_t inter = cand & ~az_nbr_union(T, AZ_ALL_LANDS & ~owned);   // not adjacent to any land the mover does not own
     if (inter) cand = inter;
@@ -292,6 +327,7 @@ __device__ __forceinline__ void az_fortify_source(const AzGame& g, const LandT& 
     amount_out = best - 1;
     if ((tie & (tie - 1)) == 0) { from_out = __ffsll((long long)tie) - 1; return; }
     // several lands hold the maximum: the first one in DFS pre-order wins
+    if (!closed) for (;;) { uint64_t n = (comp | az_nbr_union(T, comp)) & owned; if (n == comp) break; comp = n; }
     uint64_t seen = 0;
     int v = __ffsll((long long)comp) - 1;
     for (;;) {
@@ -450,7 +486,8 @@ __device__ __forceinline__ int az_make_move(AzGame& g, LandT& land, ScratchT& sc
 // check) hoisted into code every lane runs once; only short phase-specific arithmetic stays under branches.
 
 // == az_valid_moves (UtilityNN::getValidMoves, alphazero_moves.cpp:3-70) with a single neighbour union
-__device__ __forceinline__ uint64_t az_valid_moves_flat(const AzGame& g, const AzTables& T, const AzRulesDev& r)
+template <class TabT>
+__device__ __forceinline__ uint64_t az_valid_moves_flat(const AzGame& g, const TabT& T, const AzRulesDev& r)
 {
     const uint64_t oc = g.own(g.cur), oe = g.own(g.cur ^ 1u);
     const uint32_t ph = g.phase;
@@ -476,8 +513,8 @@ __device__ __forceinline__ uint64_t az_valid_moves_flat(const AzGame& g, const A
 // `dice_word` (word 0 of the real-move Philox block: at most 5 dice per move, include/az_philox.h).
 // Returns 1 WITHOUT touching the state when the move is a FORTIFY onto a non-full land: that one needs the owned
 // component search (az_fortify_source), which the rollout kernel batches over several lanes; returns 0 otherwise.
-template <class LandT>
-__device__ __forceinline__ int az_move_flat(AzGame& g, LandT& land, const AzTables& T, const AzRulesDev& r, int action, uint32_t dice_word)
+template <class LandT, class TabT>
+__device__ __forceinline__ int az_move_flat(AzGame& g, LandT& land, const TabT& T, const AzRulesDev& r, int action, uint32_t dice_word)
 {
     const uint32_t cur = g.cur, ph = g.phase;
     const bool skip = action == AZ_SKIP;
@@ -488,8 +525,8 @@ __device__ __forceinline__ int az_move_flat(AzGame& g, LandT& land, const AzTabl
 
     bool ga = false, et = false;                 // State::gotoAttack / nextPlayerGameTurn after the land writes
     int ia = li, ib = li;
-    uint32_t va = 0, vb = 0, oa = cur, ob = cur;
-    bool wa = false, wb = false;
+    uint32_t va = 0, vb = 0, ob = cur;
+    bool wa = false, wb = false, captured = false;
     if (skip) {                                                    // alphazero_moves.cpp:79-92
         ga = ph == AZ_PH_REINFORCEMENT;
         et = ph == AZ_PH_FORTIFY;
@@ -531,7 +568,7 @@ __device__ __forceinline__ int az_move_flat(AzGame& g, LandT& land, const AzTabl
             a -= units;
             if (a > 1) { g.phase = AZ_PH_MOBILIZATION; g.mob_from = (uint32_t)from; g.mob_to = (uint32_t)li; }
             g.allow_draw = 1;
-            va = (uint32_t)a; vb = (uint32_t)units;
+            va = (uint32_t)a; vb = (uint32_t)units; captured = true;
         } else { va = (uint32_t)a; vb = (uint32_t)d; ob = defender; }
     } else if (ph == AZ_PH_MOBILIZATION) {                         // alphazero_moves.cpp:146-171, State::attackReinforcementMove
         if ((uint32_t)li == g.mob_from) ga = true;
@@ -573,8 +610,14 @@ __device__ __forceinline__ int az_move_flat(AzGame& g, LandT& land, const AzTabl
         }
         vb = (uint32_t)(at + gain); wb = true;
     }
-    if (wa) az_set_land(g, land, ia, va, oa);
-    if (wb) az_set_land(g, land, ib, vb, ob);
+    // land A (attack / mobilisation source) and land B keep their owners in every case but a capture, so only the army
+    // masks are updated here; a capture moves land B's bit between the ownership masks
+    if (wa) az_set_army(g, land, ia, va, cur);
+    if (wb) az_set_army(g, land, ib, vb, ob);
+    if (captured) {
+        const uint64_t m = 1ull << ib;
+        if (cur == 0) { g.own0 |= m; g.own1 &= ~m; } else { g.own1 |= m; g.own0 &= ~m; }
+    }
     if (ga) { g.phase = AZ_PH_ATTACK; g.mob_from = AZ_NONE; g.mob_to = AZ_NONE; g.reinf = 0; }
     // gotoAttack (state.cpp:20-40) and the end of attackMove (:909-912) share one test, run once for every lane:
     // the ATTACK phase is only entered / kept while the mover still has a land that can attack
@@ -585,8 +628,8 @@ __device__ __forceinline__ int az_move_flat(AzGame& g, LandT& land, const AzTabl
 }
 
 // the deferred half of a FORTIFY move (alphazero_moves.cpp:172-231 + State::fortifyMove state.cpp:949-974 + nextPlayerGameTurn)
-template <class LandT, class ScratchT>
-__device__ __forceinline__ void az_fortify_finish(AzGame& g, LandT& land, ScratchT& scratch, const AzTables& T, int li)
+template <class LandT, class ScratchT, class TabT>
+__device__ __forceinline__ void az_fortify_finish(AzGame& g, LandT& land, ScratchT& scratch, const TabT& T, int li)
 {
     const uint32_t cur = g.cur;
     const int at = (int)(land.get(li) & 63u);
@@ -596,8 +639,8 @@ __device__ __forceinline__ void az_fortify_finish(AzGame& g, LandT& land, Scratc
         const int space = AZ_ARMY_MAX - at;
         const int mv = space < amount ? space : amount;
         const int af = (int)(land.get(from) & 63u);
-        az_set_land(g, land, from, (uint32_t)(af - mv), cur);
-        az_set_land(g, land, li, (uint32_t)(at + mv), cur);
+        az_set_army(g, land, from, (uint32_t)(af - mv), cur);
+        az_set_army(g, land, li, (uint32_t)(at + mv), cur);
     }
     az_end_turn(g);
 }

@@ -468,8 +468,8 @@ def run_ours(args):
 
     # ---- e2e: host State images in pinned memory -> device -> rollout -> host, every step.  The public calls are synchronous
     # (az_env_import_aos / az_env_rollout / az_env_export_aos return when the data is there), so a host that wants the copies of one
-    # shard to overlap the rollout of another drives shards from separate threads, each with its own env handle and stream: here two
-    # shards (--e2e-shards) of games/2.  Every step of a shard continues from the images its previous step exported.
+    # shard to overlap the rollout of another drives shards from separate threads, each with its own env handle and stream: here
+    # --e2e-shards shards (default 4; swept 2 / 3 / 4 / 8 on B200: 12.1 / 12.3 / 12.4 / 8.3 G steps/s) of games/shards.  Every step of a shard continues from the images its previous step exported.
     e2e_steps = max(3, min(args.steps, 10))
     n_sh = max(1, args.e2e_shards)
     per = n // n_sh
@@ -549,7 +549,7 @@ def run_ours(args):
                     e2e={"value": e2e_games * S * e2e_steps * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": e2e_games * 160,
                          "d2h_bytes_per_step": e2e_games * 160 + 64 * n_sh, "steps": e2e_steps,
                          "note": "%d host threads x %d games, each: import State images (pinned host) -> 512-move rollout -> export images + "
-                                 "counters, every step; one shard's copies overlap the other's rollout" % (n_sh, per)},
+                                 "counters, every step; one shard's copies overlap the others' rollouts" % (n_sh, per)},
                     gpu_launches=args.steps, wall_ms_timed_region=wall_ms, clocks=clocks,
                     results={"games_finished": cnt["games"], "wins": cnt["wins"], "draws": cnt["draws"]})
         if mcts_line is not None:
@@ -579,7 +579,7 @@ def main():
     ap.add_argument("--games", type=int, default=65536)
     ap.add_argument("--lockstep", type=int, default=512, help="lockstep moves per launch (one bench step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-shards", type=int, default=2, help="host threads (each with its own env shard and stream) of the e2e measurement")
+    ap.add_argument("--e2e-shards", type=int, default=4, help="host threads (each with its own env shard and stream) of the e2e measurement")
     ap.add_argument("--no-selfplay", action="store_true", help="skip the configs[2] self-play measurement")
     ap.add_argument("--sp-games", type=int, default=4096)
     ap.add_argument("--sp-sims", type=int, default=64)
