@@ -57,6 +57,35 @@ class RoDice(C.Structure):
                 ("tape_pos", C.c_int)]
 
 
+class RoTurnSink(C.Structure):
+    _fields_ = [("states", C.c_void_p), ("moves", C.c_void_p), ("cap", C.c_int), ("n", C.c_int)]
+
+
+class TurnSink:
+    """what Player::addTrainingSample received during scripted / random turns: (state before the move, move) pairs"""
+
+    def __init__(self, cap=8192):
+        self.states = (RoState * cap)()
+        self.moves = np.zeros(cap, np.uint8)
+        self.c = RoTurnSink(C.cast(self.states, C.c_void_p), self.moves.ctypes.data, cap, 0)
+
+    def __len__(self):
+        assert self.c.n <= self.c.cap, "TurnSink overflow"
+        return int(self.c.n)
+
+    def records(self, status, oracle_game):
+        """the 265-byte records NNTrainDataStorage::saveTrainingSamples writes for these samples once the game ended with `status`"""
+        out = np.zeros((len(self), 265), np.uint8)
+        keep = RoState.from_buffer_copy(oracle_game.s)
+        for i in range(len(self)):
+            C.memmove(C.byref(oracle_game.s), C.byref(self.states[i]), C.sizeof(RoState))
+            pi = np.zeros(MOVES, np.float32)
+            pi[self.moves[i]] = 1.0
+            out[i] = oracle_game.sample_record(pi, status)
+        C.memmove(C.byref(oracle_game.s), C.byref(keep), C.sizeof(RoState))
+        return out
+
+
 class BenchOut(C.Structure):
     _fields_ = [("steps", C.c_uint64), ("games", C.c_uint64), ("sims", C.c_uint64), ("evals", C.c_uint64),
                 ("moves", C.c_uint64), ("seconds", C.c_double)]
@@ -91,6 +120,8 @@ def oracle_lib():
         L.ro_script_init.argtypes = [C.POINTER(RoScript)]
         L.ro_script_turn.argtypes = [sp, C.POINTER(RoScript), rp, C.c_uint64, C.c_uint32, C.c_uint32]
         L.ro_invert_players.argtypes = [sp]
+        L.ro_script_turn_rec.argtypes = [sp, C.POINTER(RoScript), rp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(RoTurnSink)]
+        L.ro_random_turn_rec.argtypes = [sp, rp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(RoTurnSink)]
         L.ro_random_turn.argtypes = [sp, rp, C.c_uint64, C.c_uint32, C.c_uint32]
         L.ro_sample_record.argtypes = [sp, f32p, C.c_int, u8p]
         L.ro_mcts_new.restype = C.c_void_p
@@ -181,6 +212,13 @@ class OracleGame:
     def random_turn(self, seed, game, ply):
         """RandomPlayer::takeTurn on this game"""
         return int(self.L.ro_random_turn(C.byref(self.s), C.byref(self.rules), seed, game, ply))
+
+    def script_turn_rec(self, script, seed, game, ply, sink):
+        """ScriptPlayer::takeTurn with its Player::addTrainingSample calls collected by `sink` (TurnSink)"""
+        return int(self.L.ro_script_turn_rec(C.byref(self.s), C.byref(script), C.byref(self.rules), seed, game, ply, C.byref(sink.c)))
+
+    def random_turn_rec(self, seed, game, ply, sink):
+        return int(self.L.ro_random_turn_rec(C.byref(self.s), C.byref(self.rules), seed, game, ply, C.byref(sink.c)))
 
     def invert_players(self):
         self.L.ro_invert_players(C.byref(self.s))
@@ -276,6 +314,15 @@ def ref_lib():
         L.ref_script_free.argtypes = [vp]
         L.ref_script_turn.argtypes = [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32]
         L.ref_state_invert_players.argtypes = [vp]
+        L.ref_storage_new.restype = vp
+        L.ref_storage_free.argtypes = [vp]
+        L.ref_script_set_storage.argtypes = [vp, vp]
+        L.ref_random_set_storage.argtypes = [vp, vp]
+        L.ref_script_game_finished.argtypes = [vp, C.c_int, C.c_int]
+        L.ref_random_game_finished.argtypes = [vp, C.c_int, C.c_int]
+        L.ref_storage_count.argtypes = [vp]
+        L.ref_storage_count.restype = C.c_long
+        L.ref_storage_save.argtypes = [vp, C.c_char_p]
         L.ref_random_new.restype = vp
         L.ref_random_new.argtypes = [C.c_int]
         L.ref_random_free.argtypes = [vp]

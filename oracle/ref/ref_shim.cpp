@@ -222,6 +222,21 @@ REF_API int ref_random_turn(void* p, void* s, uint64_t seed, uint32_t game, uint
 	c.mode = REF_RNG_ENGINE; c.sim = AZ_STREAM_REAL;
 	return 0;
 }
+/* ---- Player::addTrainingSample / gameFinished (player/base/player.cpp:9-17, script_player.cpp:229-235, random_player.cpp:113-119):
+   a real NNTrainDataStorage attached to real players, as AlphaZeroTrainer::trainOnGeneratedData does (alphazero_trainer.cpp:227-275) */
+REF_API void* ref_storage_new() { return new NNTrainDataStorage(); }
+REF_API void ref_storage_free(void* st) { delete (NNTrainDataStorage*)st; }
+REF_API void ref_script_set_storage(void* p, void* st) { ((ScriptPlayer*)p)->setTrainStorage((NNTrainDataStorage*)st); }
+REF_API void ref_random_set_storage(void* p, void* st) { ((RandomPlayer*)p)->setTrainStorage((NNTrainDataStorage*)st); }
+REF_API void ref_script_game_finished(void* p, int status, int rounds) { ((ScriptPlayer*)p)->gameFinished(status, rounds); }
+REF_API void ref_random_game_finished(void* p, int status, int rounds) { ((RandomPlayer*)p)->gameFinished(status, rounds); }
+REF_API long ref_storage_count(void* st) { return (long)((NNTrainDataStorage*)st)->data.size(); }
+REF_API int ref_storage_save(void* st, const char* path)
+{
+	try { ((NNTrainDataStorage*)st)->saveTrainingSamples(path); return 0; }
+	catch (std::exception& e) { snprintf(g_err, sizeof g_err, "%s", e.what()); return -1; }
+}
+
 /* Game::newGame's mirror game (game/game.cpp:170-179): previous start state with the sides swapped */
 REF_API void ref_state_invert_players(void* s) { ((State*)s)->invertPlayers(); }
 REF_API void ref_state_set_current_player(void* s, int p) { ((State*)s)->setCurrentPlayerTurn(p); }

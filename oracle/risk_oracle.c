@@ -529,7 +529,17 @@ typedef struct script_ctx {
     ro_state* s; ro_script* sp; const ro_rules* r;
     uint64_t seed; uint32_t game, ply, die_j, int_j;
     uint64_t owned_attack_mask, attack_mask;     /* ScriptPlayer::ownedAttackLandBitMask / attackLandBitMask */
+    ro_turn_sink* sink;
 } script_ctx;
+
+/* Player::addTrainingSample(state, move), player/base/player.cpp:9-17 */
+static void emit(script_ctx* c, int move)
+{
+    ro_turn_sink* k = c->sink;
+    if (!k) return;
+    if (k->n < k->cap) { k->states[k->n] = *c->s; k->moves[k->n] = (uint8_t)move; }
+    k->n++;
+}
 
 static int script_die(script_ctx* c) { return az_rng_die(c->seed, c->game, c->ply, AZ_STREAM_OPP, c->die_j++); }
 
@@ -626,6 +636,7 @@ static void script_attack_land(script_ctx* c)
         if (s->reinf < amount) amount = s->reinf;
         while (amount > 0) {                       /* State::reinforcementMove, state.cpp:976-998 */
             int step = amount < c->r->min_unit_move ? amount : c->r->min_unit_move;
+            emit(c, to);                                                              /* script_player.cpp:105 */
             s->reinf = (uint8_t)(s->reinf - step);
             set_land(s, to, army_of(s, to) + step, me);
             if (s->reinf == 0) goto_attack(s);
@@ -634,12 +645,14 @@ static void script_attack_land(script_ctx* c)
     }
     sp->from_army = (uint8_t)army_of(s, sp->from);
     while (sp->from_army > 1) {
+        emit(c, sp->to);                                                              /* :115 */
         int captured = script_attack(c, sp->from, sp->to);
         sp->from_army = (uint8_t)army_of(s, sp->from);
         if (captured && sp->from_army > 1) {       /* move everything but one army into the new land, MIN_UNIT_MOVE at a time */
             int left = sp->from_army - 1;
             while (left > 0) {                     /* State::attackReinforcementMove, state.cpp:920-947 */
                 int step = left < c->r->min_unit_move ? left : c->r->min_unit_move;
+                emit(c, sp->to);                                                      /* :125 */
                 left -= step;
                 set_land(s, s->mob_from, army_of(s, s->mob_from) - step, me);
                 set_land(s, s->mob_to, army_of(s, s->mob_to) + step, me);
@@ -676,23 +689,30 @@ static void script_fortify(script_ctx* c)
         if (from_amount > best_amount) { best_amount = from_amount; best_from = from; best_to = to; }
     }
     if (best_amount > 0 && best_to >= 0) {          /* State::fortifyMove, state.cpp:949-974 */
+        emit(c, best_to);                                                             /* :151 */
         int amount = army_of(s, best_from) - 1, space = RO_ARMY_MAX - army_of(s, best_to);
         if (space < amount) amount = space;
         set_land(s, best_from, army_of(s, best_from) - amount, me);
         set_land(s, best_to, army_of(s, best_to) + amount, me);
-    }
+    } else emit(c, RO_SKIP);                                                          /* :157 */
 }
 
 int ro_script_turn(ro_state* s, ro_script* sp, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply)
 {
+    return ro_script_turn_rec(s, sp, r, seed, game, ply, NULL);
+}
+
+int ro_script_turn_rec(ro_state* s, ro_script* sp, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply, ro_turn_sink* sink)
+{
     if (ro_game_status(s, r) != RO_NOT_ENDED) return RO_ERR_GAME_OVER;
     script_ctx c; memset(&c, 0, sizeof c);
-    c.s = s; c.sp = sp; c.r = r; c.seed = seed; c.game = game; c.ply = ply;
+    c.s = s; c.sp = sp; c.r = r; c.seed = seed; c.game = game; c.ply = ply; c.sink = sink;
     int me = s->cur;
     derived d; derive(s, &d);
     c.owned_attack_mask = d.owned[me]; c.attack_mask = d.attack[me];
     if (s->phase == RO_SETUP) {
         script_pick_target(&c);
+        emit(&c, sp->from);                                       /* script_player.cpp:176 */
         s->reinf = (uint8_t)(s->reinf - 2);                       /* setupReinforcementMove, state.cpp:1009-1030 */
         set_land(s, sp->from, army_of(s, sp->from) + 2, me);
         s->phase = RO_SETUP_NEUTRAL;
@@ -703,6 +723,7 @@ int ro_script_turn(ro_state* s, ro_script* sp, const ro_rules* r, uint64_t seed,
         int k = (int)(az_rng_opp_int(seed, game, ply, c.int_j++) % (uint32_t)popc(pool));   /* Utility::randomMask */
         while (k--) pool &= pool - 1;
         int land = ctz(pool);
+        emit(&c, land);                                           /* :198 */
         set_land(s, land, army_of(s, land) + 1, RO_NEUTRAL);      /* setupReinforcementNeutralMove + nextPlayerSetupTurn */
         s->phase = RO_SETUP; s->round++; s->cur ^= 1;
         if (s->reinf == 0) {
@@ -742,15 +763,21 @@ static int random_pick(script_ctx* c, uint64_t mask)
 
 int ro_random_turn(ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply)
 {
+    return ro_random_turn_rec(s, r, seed, game, ply, NULL);
+}
+
+int ro_random_turn_rec(ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply, ro_turn_sink* sink)
+{
     if (ro_game_status(s, r) != RO_NOT_ENDED) return RO_ERR_GAME_OVER;
     script_ctx c; memset(&c, 0, sizeof c);
-    c.s = s; c.r = r; c.seed = seed; c.game = game; c.ply = ply;
+    c.s = s; c.r = r; c.seed = seed; c.game = game; c.ply = ply; c.sink = sink;
     const int me = s->cur;
     while (ro_game_status(s, r) == RO_NOT_ENDED && s->cur == me) {
         derived d; derive(s, &d);
         switch (s->phase) {
         case RO_SETUP: {
             int li = random_pick(&c, d.owned[me]);
+            emit(&c, li);                                            /* random_player.cpp:29 */
             s->reinf = (uint8_t)(s->reinf - 2);
             set_land(s, li, army_of(s, li) + 2, me);
             s->phase = RO_SETUP_NEUTRAL;
@@ -758,6 +785,7 @@ int ro_random_turn(ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game,
         }
         case RO_SETUP_NEUTRAL: {
             int li = random_pick(&c, ALL_LANDS & ~d.owned[0] & ~d.owned[1]);
+            emit(&c, li);                                            /* :35 */
             set_land(s, li, army_of(s, li) + 1, RO_NEUTRAL);
             s->phase = RO_SETUP; s->round++; s->cur ^= 1;
             if (s->reinf == 0) {
@@ -774,6 +802,7 @@ int ro_random_turn(ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game,
                 s->reinf = (uint8_t)(s->reinf + (cs <= 5 ? 2 + 2 * cs : 15 + (cs - 6) * 5));
             }
             int li = random_pick(&c, d.owned[me] & ~d.full[me]);
+            emit(&c, li);                                            /* :43, after playCards */
             s->reinf = (uint8_t)(s->reinf - 1);                      /* reinforcementMove(1, li) */
             set_land(s, li, army_of(s, li) + 1, me);
             if (s->reinf == 0) goto_attack(s);
@@ -781,6 +810,7 @@ int ro_random_turn(ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game,
         }
         case RO_ATTACK: {
             int li = random_pick(&c, d.attack_army[me] | SKIP_MASK);
+            emit(&c, li);                                            /* :49 */
             if (li == RO_SKIP) s->phase = RO_FORTIFY;                 /* gotoFortify */
             else {
                 int from = random_pick(&c, RO_NBR_MASK[li] & d.owned_army[me]);
@@ -793,14 +823,16 @@ int ro_random_turn(ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game,
             if (f > 0.5f) {
                 int amount = army_of(s, s->mob_from) - 1;
                 if (r->min_unit_move < amount) amount = r->min_unit_move;
+                emit(&c, s->mob_to);                                 /* :68 */
                 set_land(s, s->mob_from, army_of(s, s->mob_from) - amount, me);
                 set_land(s, s->mob_to, army_of(s, s->mob_to) + amount, me);
                 if (army_of(s, s->mob_from) == 1) goto_attack(s);
-            } else goto_attack(s);
+            } else { emit(&c, s->mob_from); goto_attack(s); }        /* :73 */
             break;
         }
         default: { /* FORTIFY */
             int to = random_pick(&c, (d.owned[me] & ~d.full[me]) | SKIP_MASK);
+            emit(&c, to);                                            /* :82 */
             if (to != RO_SKIP) {
                 uint64_t seen = 0; int order[RO_LANDS], n = 0;
                 dfs(to, d.owned[me], &seen, order, &n);               /* the owned component that holds `to` */

@@ -106,6 +106,11 @@ typedef struct ro_script { int8_t set, to, from; uint8_t from_army; } ro_script;
 void ro_script_init(ro_script* sp);
 int ro_script_turn(ro_state* s, ro_script* sp, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply);  /* ScriptPlayer::takeTurn */
 int ro_random_turn(ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply);                 /* RandomPlayer::takeTurn */
+/* Player::addTrainingSample (player/base/player.cpp:9-17) inside those turns: every call site of script_player.cpp / random_player.cpp
+   hands over (state before the move, move); the sink keeps at most `cap` of them and counts all in `n`. */
+typedef struct ro_turn_sink { ro_state* states; uint8_t* moves; int cap; int n; } ro_turn_sink;
+int ro_script_turn_rec(ro_state* s, ro_script* sp, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply, ro_turn_sink* sink);
+int ro_random_turn_rec(ro_state* s, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply, ro_turn_sink* sink);
 void ro_invert_players(ro_state* s);                                             /* State::invertPlayers */
 #define RO_NN_INPUT_BYTES 88   /* sizeof(NNInputData), alphazero_nn_data.h:73-101 */
 #define RO_SAMPLE_BYTES 265    /* 1 + 88 + 4 + 43 * 4, alphazero_nn_data.cpp:115-138 */

@@ -109,3 +109,57 @@ def test_device_recording_matches_oracle_replay():
     again, _ = mc.samples()
     assert len(again) == 0
     mc.close(); env.close()
+
+
+@NEED_REF
+@pytest.mark.parametrize("pairing", ["script_vs_script", "script_vs_random"])
+def test_scripted_turn_samples_match_reference(pairing, tmp_path):
+    """Player::addTrainingSample inside ScriptPlayer / RandomPlayer turns (script_player.cpp:105-198, random_player.cpp:29-82) and
+    the values gameFinished -> updateValues gives them: real reference players with ONE shared NNTrainDataStorage, as
+    AlphaZeroTrainer::trainOnGeneratedData sets them up (alphazero_trainer.cpp:242-268), against ro_*_turn_rec; compared on the bytes
+    saveTrainingSamples writes (NNInputData padding bytes excluded)"""
+    L = po.ref_lib()
+    po.ref_apply_rules(po.default_rules())
+    keep = np.ones(265, bool); keep[[1 + 43, 1 + 46, 1 + 47]] = False
+    total, skips = 0, 0
+    for g in range(6):
+        ref, orc = po.RefGame(), po.OracleGame()
+        ref.new_game(SEED, 500 + g, 0); orc.new_game(SEED, 500 + g, 0)
+        st = L.ref_storage_new()
+        rs, os_ = [L.ref_script_new(), L.ref_script_new()], [po.new_script(), po.new_script()]
+        rr = L.ref_random_new(1)
+        for h in rs:
+            L.ref_script_set_storage(h, st)
+        L.ref_random_set_storage(rr, st)
+        sink = po.TurnSink(1 << 15)
+        ply = 0
+        while ref.status() == -1:
+            cur = orc.s.cur
+            if pairing == "script_vs_script" or cur == 0:
+                assert ref.script_turn(rs[cur], SEED, 500 + g, ply) == 0, L.ref_last_error()
+                assert orc.script_turn_rec(os_[cur], SEED, 500 + g, ply, sink) == 0
+            else:
+                assert ref.random_turn(rr, SEED, 500 + g, ply) == 0, L.ref_last_error()
+                assert orc.random_turn_rec(SEED, 500 + g, ply, sink) == 0
+            ply += 1
+            assert L.ref_storage_count(st) == len(sink), "game %d ply %d" % (g, ply)
+        status = ref.status()
+        assert status == orc.status()
+        L.ref_script_game_finished(rs[0], status, int(orc.s.round))      # Game::playGame end: every player's gameFinished
+        if pairing == "script_vs_script":
+            L.ref_script_game_finished(rs[1], status, int(orc.s.round))
+        else:
+            L.ref_random_game_finished(rr, status, int(orc.s.round))
+        path = str(tmp_path / ("g%d.bin" % g))
+        assert L.ref_storage_save(st, path.encode()) == 0
+        raw = np.fromfile(path, np.uint8)
+        n = int(raw[:8].view(np.uint64)[0])
+        assert n == len(sink) and raw.size == 8 + 265 * n
+        theirs, ours = raw[8:].reshape(n, 265), sink.records(status, orc)
+        assert (theirs[:, keep] == ours[:, keep]).all()
+        total += n
+        skips += int((sink.moves[:n] == po.SKIP).sum())
+        for h in rs:
+            L.ref_script_free(h)
+        L.ref_random_free(rr); L.ref_storage_free(st)
+    assert total > 1500 and (skips > 0 or pairing == "script_vs_script")     # the script's fortify rarely has nothing to move
