@@ -116,6 +116,9 @@ def lib():
         L.az_selfplay_record.argtypes = [vp, C.c_size_t, C.c_int]
         L.az_env_script_turn.argtypes = [vp, vp, vp, vp]
         L.az_env_random_turn.argtypes = [vp, vp, vp]
+        L.az_env_play_turn.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+        L.az_env_record_turns.argtypes = [vp, C.c_size_t, C.c_int]
+        L.az_env_turn_samples.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), vp]
         L.az_arena_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
         L.az_arena_create_versus.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
         L.az_arena_destroy.argtypes = [vp]
@@ -211,6 +214,24 @@ class Env:
         st = np.empty(self.n, np.int8)
         check(self.L.az_env_random_turn(self.h, _ptr(st), stream))
         return st
+
+    def play_turn(self, kind_side0, kind_side1, script=None, stream=None):
+        """one turn of every running game, side 0 / side 1 played by OPPONENT_SCRIPT or OPPONENT_RANDOM (az_env_play_turn)"""
+        st = np.empty(self.n, np.int8)
+        check(self.L.az_env_play_turn(self.h, int(kind_side0), int(kind_side1), _ptr(script) if script is not None else None, _ptr(st), stream))
+        return st
+
+    def record_turns(self, capacity_samples, max_samples_per_game=4096):
+        """record what Player::addTrainingSample receives inside scripted / random turns (az_env_record_turns)"""
+        check(self.L.az_env_record_turns(self.h, C.c_size_t(int(capacity_samples)), int(max_samples_per_game)))
+
+    def turn_samples(self, stream=None):
+        """finished games' samples as a [k, 265] uint8 array (reference file layout per record) and the dropped count"""
+        n, dropped = C.c_size_t(0), C.c_uint64(0)
+        check(self.L.az_env_turn_samples(self.h, None, C.c_size_t(0), C.byref(n), C.byref(dropped), stream))
+        out = np.empty((n.value, SAMPLE_BYTES), np.uint8)
+        check(self.L.az_env_turn_samples(self.h, _ptr(out) if n.value else None, C.c_size_t(n.value), C.byref(n), C.byref(dropped), stream))
+        return out[:n.value], int(dropped.value)
 
     def encode(self, stream=None):
         a = np.empty((self.n, 7, 6, 13), np.float32)

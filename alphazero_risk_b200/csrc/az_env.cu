@@ -21,6 +21,7 @@
 #include "az_tables_gen.h"
 #include "az_script.cuh"
 #include "az_arena.cuh"
+#include "az_samples.cuh"
 
 // ---------------------------------------------------------------- error string
 static thread_local char g_az_err[512] = "";
@@ -336,10 +337,20 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout(uint32_t* __restrict_
 
 
 
-// ScriptPlayer::takeTurn for the side to move of every running game (one whole turn per call, one ply)
+// staging of the samples scripted / random turns emit (Player::addTrainingSample), per game; st == NULL: not recording
+struct TurnRecDev {
+    uint32_t* st;      // [n][max][14]  state before the move
+    uint8_t* mv;       // [n][max]      the move
+    uint32_t* len;     // [n]           staged samples of the running game (> max = overflowed)
+    int max;
+};
+
+// ScriptPlayer::takeTurn / RandomPlayer::takeTurn for the side to move of every running game (one whole turn per call, one ply);
+// kind0 / kind1 = who plays side 0 / side 1
 __global__ void __launch_bounds__(ENV_BLOCK) k_env_script_turn(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
                                                                 uint32_t* __restrict__ script, int8_t* __restrict__ status,
-                                                                uint64_t seed, uint32_t first_game, AzRulesDev rules, int kind)
+                                                                uint64_t seed, uint32_t first_game, AzRulesDev rules, int kind0, int kind1,
+                                                                TurnRecDev rec)
 {
     __shared__ EnvSmem sm;
     AzTables T = env_stage_tables(sm, g_tab);
@@ -350,16 +361,68 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_script_turn(uint32_t* __restr
     if (out != AZ_STATUS_RUNNING) out = AZ_STATUS_OVER;
     else {
         const uint32_t side = c.g.cur;
+        const int kind = side ? kind1 : kind0;
+        AzTurnSink sink; AzTurnSink* sk = nullptr;
+        if (rec.st) {
+            sink.st = rec.st + (size_t)gi * rec.max * AZ_PRIMARY_WORDS; sink.mv = rec.mv + (size_t)gi * rec.max;
+            sink.cap = (uint32_t)rec.max; sink.n = rec.len[gi];
+            sk = &sink;
+        }
         uint32_t spw = kind == AZ_OPPONENT_SCRIPT ? script[(size_t)gi * 2 + side] : 0u;
-        const int rc = kind == AZ_OPPONENT_SCRIPT ? az_script_turn(c.g, c.land, c.scratch, T, rules, spw, seed, first_game + (uint32_t)gi, c.ply)
-                                                  : az_random_turn(c.g, c.land, c.scratch, T, rules, seed, first_game + (uint32_t)gi, c.ply);
+        const int rc = kind == AZ_OPPONENT_SCRIPT ? az_script_turn(c.g, c.land, c.scratch, T, rules, spw, seed, first_game + (uint32_t)gi, c.ply, sk)
+                                                  : az_random_turn(c.g, c.land, c.scratch, T, rules, seed, first_game + (uint32_t)gi, c.ply, sk);
         if (rc == 0) {
             if (kind == AZ_OPPONENT_SCRIPT) script[(size_t)gi * 2 + side] = spw;
+            if (sk) rec.len[gi] = sink.n;
             c.ply++; env_store(c, sm, st, n, gi); out = az_game_status(c.g, rules);
         }
         else out = rc;
     }
     status[gi] = (int8_t)out;
+}
+
+// gameFinished -> NNTrainDataStorage::updateValues (script_player.cpp:229-235, random_player.cpp:113-119, alphazero_nn_data.cpp:51-65)
+// for the games the turn kernel just ended: one warp per game turns the staged (state, move) pairs into packed 265-byte records
+// (one-hot policy, Player::addTrainingSample) in the output queue.
+#define REC_END_WARPS 4
+__global__ void __launch_bounds__(REC_END_WARPS * 32) k_env_rec_end(TurnRecDev rec, const int8_t* __restrict__ status, int n,
+                                                                    uint8_t* __restrict__ out, unsigned long long* __restrict__ count,
+                                                                    unsigned long long cap)
+{
+    __shared__ uint8_t s_rec_all[REC_END_WARPS][272];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gi = blockIdx.x * REC_END_WARPS + warp;
+    if (gi >= n) return;
+    const int stt = status[gi];
+    if (stt != 0 && stt != 1 && stt != AZ_STATUS_DRAW) return;
+    const uint32_t len = rec.len[gi];
+    if (len == 0) return;
+    uint8_t* s_rec = s_rec_all[warp];
+    unsigned long long base = 0;
+    bool ok = len <= (uint32_t)rec.max;
+    if (lane == 0) {
+        if (ok) { base = atomicAdd(&count[0], (unsigned long long)len); if (base + len > cap) ok = false; }
+        if (!ok) atomicAdd(&count[1], (unsigned long long)len);
+    }
+    ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+    base = ((unsigned long long)__shfl_sync(0xffffffffu, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (uint32_t)base, 0);
+    if (ok) {
+        for (uint32_t i = 0; i < len; ++i) {
+            const uint32_t* stp = rec.st + ((size_t)gi * rec.max + i) * AZ_PRIMARY_WORDS;
+            const int mv = rec.mv[(size_t)gi * rec.max + i];
+            __syncwarp();
+            az_sample_head(stp, stt, s_rec, lane);
+            for (int k = lane; k < AZ_MOVES; k += 32) {
+                const uint32_t u = k == mv ? 0x3f800000u : 0u;               // policy[li2i(move)] = 1.0f
+                for (int b = 0; b < 4; ++b) s_rec[93 + 4 * k + b] = (uint8_t)(u >> (8 * b));
+            }
+            __syncwarp();
+            uint8_t* dst = out + (base + i) * AZ_SAMPLE_BYTES;
+            for (int k = lane; k < AZ_SAMPLE_BYTES; k += 32) dst[k] = s_rec[k];
+        }
+    }
+    __syncwarp();
+    if (lane == 0) rec.len[gi] = 0;
 }
 
 // ---------------------------------------------------------------- arena (-m play): everything between two AlphaZero moves
@@ -584,6 +647,9 @@ struct az_env {
     uint8_t* d_aos = nullptr; float* d_x = nullptr; int* d_bad = nullptr; uint32_t* d_script = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    // samples of scripted / random turns (az_env_record_turns)
+    TurnRecDev rec = { nullptr, nullptr, nullptr, 0 };
+    uint8_t* d_rec_out = nullptr; unsigned long long* d_rec_count = nullptr; size_t rec_cap = 0;
 };
 
 static AzRulesDev dev_rules(const az_rules& r)
@@ -642,6 +708,7 @@ extern "C" int az_env_destroy(az_env* e)
     AzDeviceGuard guard(e->device);
     cudaFree(e->d_state); cudaFree(e->d_counters); cudaFree(e->d_action); cudaFree(e->d_dice); cudaFree(e->d_status);
     cudaFree(e->d_valid); cudaFree(e->d_aos); cudaFree(e->d_x); cudaFree(e->d_bad); cudaFree(e->d_script);
+    cudaFree(e->rec.st); cudaFree(e->rec.mv); cudaFree(e->rec.len); cudaFree(e->d_rec_out); cudaFree(e->d_rec_count);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     delete e;
@@ -663,6 +730,7 @@ extern "C" int az_env_reset(az_env* e, uint64_t seed, void* stream)
     AzDeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     e->seed = seed;
+    if (e->rec.len) AZ_CUDA(cudaMemsetAsync(e->rec.len, 0, sizeof(uint32_t) * (size_t)e->n, s));     // nothing staged for a fresh deal
     k_env_reset<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, seed, e->first_game);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
@@ -758,33 +826,97 @@ extern "C" int az_env_step(az_env* e, const uint8_t* h_action, const uint8_t* h_
     return AZ_OK;
 }
 
+// one turn of every running game; kind0 / kind1 = AZ_OPPONENT_SCRIPT or AZ_OPPONENT_RANDOM for side 0 / side 1
+static int env_play_turn(az_env* e, int kind0, int kind1, uint32_t* h_script, int8_t* h_status, cudaStream_t s)
+{
+    const bool scripted = kind0 == AZ_OPPONENT_SCRIPT || kind1 == AZ_OPPONENT_SCRIPT;
+    int rc = ensure(&e->d_status, (size_t)e->n); if (rc) return rc;
+    if (scripted) {
+        rc = ensure(&e->d_script, (size_t)e->n * 2); if (rc) return rc;
+        AZ_CUDA(cudaMemcpyAsync(e->d_script, h_script, sizeof(uint32_t) * 2 * (size_t)e->n, cudaMemcpyHostToDevice, s));
+    }
+    k_env_script_turn<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), scripted ? e->d_script : nullptr, e->d_status,
+                                                            e->seed, e->first_game, dev_rules(e->rules), kind0, kind1, e->rec);
+    AZ_CUDA(cudaGetLastError());
+    if (e->rec.st) {
+        k_env_rec_end<<<(e->n + REC_END_WARPS - 1) / REC_END_WARPS, REC_END_WARPS * 32, 0, s>>>(e->rec, e->d_status, e->n, e->d_rec_out,
+                                                                                                  e->d_rec_count, (unsigned long long)e->rec_cap);
+        AZ_CUDA(cudaGetLastError());
+    }
+    if (scripted) AZ_CUDA(cudaMemcpyAsync(h_script, e->d_script, sizeof(uint32_t) * 2 * (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(h_status, e->d_status, (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
 extern "C" int az_env_script_turn(az_env* e, uint32_t* h_script, int8_t* h_status, void* stream)
 {
     AZ_REQUIRE(e && h_script && h_status, "NULL argument");
     AzDeviceGuard guard(e->device);
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc = ensure(&e->d_script, (size_t)e->n * 2); if (rc) return rc;
-    rc = ensure(&e->d_status, (size_t)e->n); if (rc) return rc;
-    AZ_CUDA(cudaMemcpyAsync(e->d_script, h_script, sizeof(uint32_t) * 2 * (size_t)e->n, cudaMemcpyHostToDevice, s));
-    k_env_script_turn<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), e->d_script, e->d_status, e->seed,
-                                                            e->first_game, dev_rules(e->rules), AZ_OPPONENT_SCRIPT);
-    AZ_CUDA(cudaGetLastError());
-    AZ_CUDA(cudaMemcpyAsync(h_script, e->d_script, sizeof(uint32_t) * 2 * (size_t)e->n, cudaMemcpyDeviceToHost, s));
-    AZ_CUDA(cudaMemcpyAsync(h_status, e->d_status, (size_t)e->n, cudaMemcpyDeviceToHost, s));
-    AZ_CUDA(cudaStreamSynchronize(s));
-    return AZ_OK;
+    return env_play_turn(e, AZ_OPPONENT_SCRIPT, AZ_OPPONENT_SCRIPT, h_script, h_status, (cudaStream_t)stream);
 }
 
 extern "C" int az_env_random_turn(az_env* e, int8_t* h_status, void* stream)
 {
     AZ_REQUIRE(e && h_status, "NULL argument");
     AzDeviceGuard guard(e->device);
+    return env_play_turn(e, AZ_OPPONENT_RANDOM, AZ_OPPONENT_RANDOM, nullptr, h_status, (cudaStream_t)stream);
+}
+
+extern "C" int az_env_play_turn(az_env* e, int kind_side0, int kind_side1, uint32_t* h_script, int8_t* h_status, void* stream)
+{
+    AZ_REQUIRE(e && h_status, "NULL argument");
+    AZ_REQUIRE((kind_side0 == AZ_OPPONENT_SCRIPT || kind_side0 == AZ_OPPONENT_RANDOM) &&
+               (kind_side1 == AZ_OPPONENT_SCRIPT || kind_side1 == AZ_OPPONENT_RANDOM), "kind: AZ_OPPONENT_SCRIPT or AZ_OPPONENT_RANDOM");
+    AZ_REQUIRE(h_script || (kind_side0 == AZ_OPPONENT_RANDOM && kind_side1 == AZ_OPPONENT_RANDOM), "h_script is NULL but a side is scripted");
+    AzDeviceGuard guard(e->device);
+    return env_play_turn(e, kind_side0, kind_side1, h_script, h_status, (cudaStream_t)stream);
+}
+
+// ---- samples of scripted / random turns (Player::addTrainingSample; the data of AlphaZeroTrainer::trainOnGeneratedData)
+extern "C" int az_env_record_turns(az_env* e, size_t capacity_samples, int max_samples_per_game)
+{
+    AZ_REQUIRE(e != nullptr, "env is NULL");
+    AZ_REQUIRE(capacity_samples > 0 && max_samples_per_game > 0, "capacity_samples and max_samples_per_game must be positive");
+    AZ_REQUIRE(e->rec.st == nullptr, "recording is already enabled on this handle");
+    AzDeviceGuard guard(e->device);
+    const size_t n = (size_t)e->n, m = (size_t)max_samples_per_game;
+    uint32_t* st = nullptr;
+    cudaError_t ce = cudaMalloc(&st, sizeof(uint32_t) * n * m * AZ_PRIMARY_WORDS);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->rec.mv, n * m);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->rec.len, sizeof(uint32_t) * n);
+    if (ce == cudaSuccess) ce = cudaMemset(e->rec.len, 0, sizeof(uint32_t) * n);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_rec_out, capacity_samples * (size_t)AZ_SAMPLE_BYTES);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_rec_count, 2 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMemset(e->d_rec_count, 0, 2 * sizeof(unsigned long long));
+    if (ce != cudaSuccess) {
+        az_set_error("CUDA error %s while allocating the sample staging", cudaGetErrorString(ce));
+        cudaGetLastError();
+        cudaFree(st); cudaFree(e->rec.mv); cudaFree(e->rec.len); cudaFree(e->d_rec_out); cudaFree(e->d_rec_count);
+        e->rec.mv = nullptr; e->rec.len = nullptr; e->d_rec_out = nullptr; e->d_rec_count = nullptr;
+        return AZ_ERR_CUDA;
+    }
+    e->rec.max = max_samples_per_game; e->rec_cap = capacity_samples;
+    e->rec.st = st;                                      // set last: the kernels record iff rec.st != NULL
+    return AZ_OK;
+}
+
+extern "C" int az_env_turn_samples(az_env* e, uint8_t* h_records, size_t max_records, size_t* n_out, uint64_t* h_dropped, void* stream)
+{
+    AZ_REQUIRE(e && n_out, "NULL argument");
+    AZ_REQUIRE(e->rec.st != nullptr, "az_env_record_turns has not been called");
+    AzDeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = ensure(&e->d_status, (size_t)e->n); if (rc) return rc;
-    k_env_script_turn<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), nullptr, e->d_status, e->seed,
-                                                            e->first_game, dev_rules(e->rules), AZ_OPPONENT_RANDOM);
-    AZ_CUDA(cudaGetLastError());
-    AZ_CUDA(cudaMemcpyAsync(h_status, e->d_status, (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    unsigned long long h[2];
+    AZ_CUDA(cudaMemcpyAsync(h, e->d_rec_count, sizeof h, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    const size_t have = (size_t)(h[0] < e->rec_cap ? h[0] : e->rec_cap);     // reservations past the capacity were dropped (and counted)
+    if (h_dropped) *h_dropped = h[1];
+    *n_out = have;
+    if (!h_records) return AZ_OK;                        // size query
+    AZ_REQUIRE(max_records >= have, "h_records is too small: query the size with h_records = NULL first");
+    if (have) AZ_CUDA(cudaMemcpyAsync(h_records, e->d_rec_out, have * (size_t)AZ_SAMPLE_BYTES, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemsetAsync(e->d_rec_count, 0, sizeof h, s));
     AZ_CUDA(cudaStreamSynchronize(s));
     return AZ_OK;
 }

@@ -31,12 +31,34 @@ struct AzScript {
 };
 #define AZ_SCRIPT_INIT 0x00ffffffu
 
+// Player::addTrainingSample (player/base/player.cpp:9-17) inside a scripted / random turn: every call site of script_player.cpp and
+// random_player.cpp hands over (state before the move, move).  The sink is this game's staging slice in HBM: packed primary states
+// (14 words each, the layout of AZ_PRIMARY_WORDS) and one move byte per sample; `n` counts every call, also those past `cap`.
+struct AzTurnSink {
+    uint32_t* st; uint8_t* mv; uint32_t cap, n;
+};
+template <class LandT>
+__device__ __noinline__ void az_turn_emit(AzTurnSink* k, const AzGame& g, const LandT& land, int move)
+{
+    if (k == nullptr) return;
+    if (k->n < k->cap) {
+        uint32_t* dst = k->st + (size_t)k->n * AZ_PRIMARY_WORDS;
+        for (int w = 0; w < 10; ++w)
+            dst[w] = land.get(4 * w) | (land.get(4 * w + 1) << 8) | (land.get(4 * w + 2) << 16) | (land.get(4 * w + 3) << 24);
+        dst[10] = land.get(40) | (land.get(41) << 8) | (g.cards0 << 16) | (g.cards1 << 24);
+        dst[11] = az_pack_w11(g); dst[12] = az_pack_w12(g); dst[13] = az_pack_w13(g);
+        k->mv[k->n] = (uint8_t)move;
+    }
+    k->n++;
+}
+
 template <class LandT>
 struct AzScriptCtx {
     AzGame& g; LandT& land; const AzTables& T; const AzRulesDev& r;
     AzScript sp;
     AzDicePhilox dice;
     uint64_t owned_attack_mask, attack_mask;      // ScriptPlayer::ownedAttackLandBitMask / attackLandBitMask
+    AzTurnSink* sink = nullptr;
     __device__ AzScriptCtx(AzGame& g_, LandT& l_, const AzTables& T_, const AzRulesDev& r_) : g(g_), land(l_), T(T_), r(r_) {}
 };
 
@@ -141,14 +163,27 @@ __device__ __forceinline__ void az_script_attack_land(AzScriptCtx<LandT>& c)
         int army = (int)(c.land.get(to) & 63u);
         int amount = AZ_ARMY_MAX - army;
         if ((int)g.reinf < amount) amount = (int)g.reinf;
-        // State::reinforcementMove in MIN_UNIT_MOVE steps (state.cpp:976-998): only the sum and the last step's gotoAttack are observable
-        g.reinf = (g.reinf - (uint32_t)amount) & 0xff;
-        az_set_land(g, c.land, to, (uint32_t)(army + amount), me);
-        if (amount > 0 && g.reinf == 0) az_goto_attack(g, c.T);
+        // State::reinforcementMove in MIN_UNIT_MOVE steps (state.cpp:976-998): only the sum and the last step's gotoAttack are
+        // observable — unless the samples are recorded: then every step's state is one (script_player.cpp:99-109)
+        if (c.sink) {
+            for (int rem = amount; rem > 0; ) {
+                const int step = rem < c.r.min_unit_move ? rem : c.r.min_unit_move;
+                az_turn_emit(c.sink, g, c.land, to);
+                g.reinf = (g.reinf - (uint32_t)step) & 0xff;
+                army += step; rem -= step;
+                az_set_land(g, c.land, to, (uint32_t)army, me);
+                if (g.reinf == 0) az_goto_attack(g, c.T);
+            }
+        } else {
+            g.reinf = (g.reinf - (uint32_t)amount) & 0xff;
+            az_set_land(g, c.land, to, (uint32_t)(army + amount), me);
+            if (amount > 0 && g.reinf == 0) az_goto_attack(g, c.T);
+        }
         if (amount == 0) break;                    // every owned land is full: the reference would spin here
     }
     c.sp.from_army = c.land.get(c.sp.from) & 63u;
     while (c.sp.from_army > 1) {
+        az_turn_emit(c.sink, g, c.land, (int)c.sp.to);                            // script_player.cpp:115
         const bool captured = az_script_attack(c, (int)c.sp.from, (int)c.sp.to);
         c.sp.from_army = c.land.get(c.sp.from) & 63u;
         if (captured && c.sp.from_army > 1) {
@@ -156,8 +191,19 @@ __device__ __forceinline__ void az_script_attack_land(AzScriptCtx<LandT>& c)
             const int left = (int)c.sp.from_army - 1;
             const int at = (int)(c.land.get(g.mob_to) & 63u);
             const uint32_t mf = g.mob_from, mt = g.mob_to;
-            az_set_land(g, c.land, (int)mf, 1u, me);
-            az_set_land(g, c.land, (int)mt, (uint32_t)(at + left), me);
+            if (c.sink) {                                                         // one sample per step, script_player.cpp:122-131
+                int af = (int)c.sp.from_army, t = at;
+                for (int rem = left; rem > 0; ) {
+                    const int step = rem < c.r.min_unit_move ? rem : c.r.min_unit_move;
+                    az_turn_emit(c.sink, g, c.land, (int)c.sp.to);
+                    af -= step; t += step; rem -= step;
+                    az_set_land(g, c.land, (int)mf, (uint32_t)af, me);
+                    az_set_land(g, c.land, (int)mt, (uint32_t)t, me);
+                }
+            } else {
+                az_set_land(g, c.land, (int)mf, 1u, me);
+                az_set_land(g, c.land, (int)mt, (uint32_t)(at + left), me);
+            }
             az_goto_attack(g, c.T);
             break;
         }
@@ -169,7 +215,7 @@ __device__ __forceinline__ void az_script_attack_land(AzScriptCtx<LandT>& c)
 // maximum) is the source, the border land with the most foreign neighbours (first strict maximum) the target; the component with
 // the largest source army is used (std::sort on <= 16 elements = libstdc++'s stable insertion sort: the first maximum).
 template <class LandT, class ScratchT>
-__device__ __forceinline__ void az_script_fortify(AzGame& g, LandT& land, ScratchT& parent, const AzTables& T)
+__device__ __forceinline__ void az_script_fortify(AzGame& g, LandT& land, ScratchT& parent, const AzTables& T, AzTurnSink* sink = nullptr)
 {
     const uint32_t me = g.cur;
     const uint64_t owned = g.own(me);
@@ -209,18 +255,20 @@ __device__ __forceinline__ void az_script_fortify(AzGame& g, LandT& land, Scratc
         int amount = af - 1;
         const int space = AZ_ARMY_MAX - at;
         if (space < amount) amount = space;
+        az_turn_emit(sink, g, land, best_to);                                     // script_player.cpp:151
         az_set_land(g, land, best_from, (uint32_t)(af - amount), me);
         az_set_land(g, land, best_to, (uint32_t)(at + amount), me);
-    }
+    } else az_turn_emit(sink, g, land, AZ_SKIP);                                  // :157
 }
 
 // ScriptPlayer::takeTurn.  `sp_word` = the packed AzScript of this (game slot, side); returns 0, or AZ_STATUS_ILLEGAL when the
 // game is not at the start of a turn (the script never resumes one).
 template <class LandT, class ScratchT>
 __device__ __forceinline__ int az_script_turn(AzGame& g, LandT& land, ScratchT& scratch, const AzTables& T, const AzRulesDev& r,
-                                              uint32_t& sp_word, uint64_t seed, uint32_t game, uint32_t ply)
+                                              uint32_t& sp_word, uint64_t seed, uint32_t game, uint32_t ply, AzTurnSink* sink = nullptr)
 {
     AzScriptCtx<LandT> c(g, land, T, r);
+    c.sink = sink;
     c.sp.unpack(sp_word);
     c.dice.init(seed, game, ply, AZ_STREAM_OPP);
     const uint32_t me = g.cur;
@@ -229,6 +277,7 @@ __device__ __forceinline__ int az_script_turn(AzGame& g, LandT& land, ScratchT& 
     c.attack_mask = az_nbr_union(T, owned) & ~owned;
     if (g.phase == AZ_PH_SETUP) {
         az_script_pick_target(c);
+        az_turn_emit(sink, g, land, (int)c.sp.from);                  // script_player.cpp:176
         g.reinf = (g.reinf - 2) & 0xff;                               // setupReinforcementMove, state.cpp:1009-1030
         az_set_land(g, land, (int)c.sp.from, (land.get(c.sp.from) & 63u) + 2, me);
         const uint64_t neutral = AZ_ALL_LANDS & ~owned & ~enemy;
@@ -238,6 +287,8 @@ __device__ __forceinline__ int az_script_turn(AzGame& g, LandT& land, ScratchT& 
         const uint64_t pool = near_enemy ? near_enemy : neutral;
         const uint32_t k = az_rng_opp_int(seed, game, ply, 0) % (uint32_t)__popcll(pool);      // Utility::randomMask, land.cpp:100-112
         const int l = az_nth_set_bit(pool, k);
+        g.phase = AZ_PH_SETUP_NEUTRAL;                                // (the state the sample sees)
+        az_turn_emit(sink, g, land, l);                               // :198
         az_set_land(g, land, l, (land.get(l) & 63u) + 1, AZ_NEUTRAL);   // setupReinforcementNeutralMove + nextPlayerSetupTurn
         g.phase = AZ_PH_SETUP; g.round = (g.round + 1) & 0xffff; g.cur ^= 1u;
         if (g.reinf == 0) { g.phase = AZ_PH_REINFORCEMENT; g.reinf = (uint32_t)az_reinforcement_value(g.own(g.cur)); }
@@ -261,7 +312,7 @@ __device__ __forceinline__ int az_script_turn(AzGame& g, LandT& land, ScratchT& 
         c.owned_attack_mask = o & g.gt1;
         c.attack_mask = az_attack_army(g, T, me);
     }
-    az_script_fortify(g, land, scratch, T);
+    az_script_fortify(g, land, scratch, T, sink);
     az_end_turn(g);
     sp_word = c.sp.pack();
     return 0;
@@ -284,7 +335,7 @@ struct AzRandomCtx {
 
 template <class LandT, class ScratchT>
 __device__ __forceinline__ int az_random_turn(AzGame& g, LandT& land, ScratchT& scratch, const AzTables& T, const AzRulesDev& r,
-                                              uint64_t seed, uint32_t game, uint32_t ply)
+                                              uint64_t seed, uint32_t game, uint32_t ply, AzTurnSink* sink = nullptr)
 {
     AzScriptCtx<LandT> c(g, land, T, r);                 // only for az_script_attack (State::attackMove with sequential dice)
     c.dice.init(seed, game, ply, AZ_STREAM_OPP);
@@ -296,6 +347,7 @@ __device__ __forceinline__ int az_random_turn(AzGame& g, LandT& land, ScratchT& 
         switch (g.phase) {
         case AZ_PH_SETUP: {
             const int li = rc.pick(owned);
+            az_turn_emit(sink, g, land, li);                                      // random_player.cpp:29
             g.reinf = (g.reinf - 2) & 0xff;
             az_set_land(g, land, li, (land.get(li) & 63u) + 2, me);
             g.phase = AZ_PH_SETUP_NEUTRAL;
@@ -303,6 +355,7 @@ __device__ __forceinline__ int az_random_turn(AzGame& g, LandT& land, ScratchT& 
         }
         case AZ_PH_SETUP_NEUTRAL: {
             const int li = rc.pick(AZ_ALL_LANDS & ~g.own0 & ~g.own1);
+            az_turn_emit(sink, g, land, li);                                      // :35
             az_set_land(g, land, li, (land.get(li) & 63u) + 1, AZ_NEUTRAL);
             g.phase = AZ_PH_SETUP; g.round = (g.round + 1) & 0xffff; g.cur ^= 1u;
             if (g.reinf == 0) { g.phase = AZ_PH_REINFORCEMENT; g.reinf = (uint32_t)az_reinforcement_value(g.own(g.cur)); }
@@ -318,6 +371,7 @@ __device__ __forceinline__ int az_random_turn(AzGame& g, LandT& land, ScratchT& 
                 g.reinf = (g.reinf + (uint32_t)(cs <= 5 ? 2 + 2 * cs : 15 + (cs - 6) * 5)) & 0xff;
             }
             const int li = rc.pick(owned & ~g.full);
+            az_turn_emit(sink, g, land, li);                                      // :43 (after playCards)
             g.reinf = (g.reinf - 1) & 0xff;
             az_set_land(g, land, li, (land.get(li) & 63u) + 1, me);
             if (g.reinf == 0) az_goto_attack(g, T);
@@ -325,6 +379,7 @@ __device__ __forceinline__ int az_random_turn(AzGame& g, LandT& land, ScratchT& 
         }
         case AZ_PH_ATTACK: {
             const int li = rc.pick(az_attack_army(g, T, me) | AZ_SKIP_MASK);
+            az_turn_emit(sink, g, land, li);                                      // :49
             if (li == AZ_SKIP) g.phase = AZ_PH_FORTIFY;
             else {
                 const int from = rc.pick(T.nbr[li] & owned & g.gt1);
@@ -339,14 +394,16 @@ __device__ __forceinline__ int az_random_turn(AzGame& g, LandT& land, ScratchT& 
                 int amount = af - 1;
                 if (r.min_unit_move < amount) amount = r.min_unit_move;
                 const uint32_t mf = g.mob_from, mt = g.mob_to;
+                az_turn_emit(sink, g, land, (int)mt);                             // :68
                 az_set_land(g, land, (int)mf, (uint32_t)(af - amount), me);
                 az_set_land(g, land, (int)mt, (uint32_t)(at + amount), me);
                 if (af - amount == 1) az_goto_attack(g, T);
-            } else az_goto_attack(g, T);
+            } else { az_turn_emit(sink, g, land, (int)g.mob_from); az_goto_attack(g, T); }     // :73
             break;
         }
         default: {
             const int to = rc.pick((owned & ~g.full) | AZ_SKIP_MASK);
+            az_turn_emit(sink, g, land, to);                                      // :82
             if (to != AZ_SKIP) {
                 uint64_t comp = 1ull << to;
                 for (;;) { const uint64_t n = (comp | az_nbr_union(T, comp)) & owned; if (n == comp) break; comp = n; }

@@ -131,6 +131,18 @@ AZ_API int az_env_step_dev(az_env* env, const uint8_t* d_action, const uint8_t* 
 AZ_API int az_env_script_turn(az_env* env, uint32_t* h_script, int8_t* h_status, void* stream);
 /* RandomPlayer::takeTurn (player/random/random_player.cpp:22-111), same calling convention (the random player keeps no members) */
 AZ_API int az_env_random_turn(az_env* env, int8_t* h_status, void* stream);
+/* The same with a player kind per side (AZ_OPPONENT_SCRIPT / AZ_OPPONENT_RANDOM, defined below): the games of
+   AlphaZeroTrainer::trainOnGeneratedData (alphazero_trainer.cpp:242-268: Script vs Script, Script vs Random).  h_script may be NULL
+   when neither side is scripted. */
+AZ_API int az_env_play_turn(az_env* env, int kind_side0, int kind_side1, uint32_t* h_script, int8_t* h_status, void* stream);
+/* Player::addTrainingSample (player/base/player.cpp:9-17) for those turns: every call site of script_player.cpp:105-198 and
+   random_player.cpp:29-82 stages (state before the move, move) per game; when a turn ends the game, gameFinished ->
+   NNTrainDataStorage::updateValues (alphazero_nn_data.cpp:51-65) turns the game's samples into packed AZ_SAMPLE_BYTES records
+   (one-hot policy) in an output queue of `capacity_samples`.  A game with more than max_samples_per_game samples, or one that
+   does not fit the queue any more, is dropped whole and counted.  az_env_reset discards what is staged.  az_env_turn_samples
+   drains the queue (h_records = NULL: size query) — same record format and calling convention as az_selfplay_samples. */
+AZ_API int az_env_record_turns(az_env* env, size_t capacity_samples, int max_samples_per_game);
+AZ_API int az_env_turn_samples(az_env* env, uint8_t* h_records, size_t max_records, size_t* n_out, uint64_t* h_dropped, void* stream);
 
 /* NNInputData(State) + setInStateTensor (neural_network/alphazero_nn_data.cpp:165-196,
    alphazero_nn.cpp:31-67): fp32 [n][7][6][13] */

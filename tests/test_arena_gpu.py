@@ -302,3 +302,60 @@ def test_arena_claims_pairs_like_the_counter(api):
     r2 = arena.play(4, SEED + 1)          # the handle can be reused for another match
     assert r2["count"] == 4 and r2["errors"] == 0
     arena.close(); mc.close(); env.close()
+
+
+@pytest.mark.parametrize("pairing", ["script_vs_script", "script_vs_random", "random_vs_random"])
+def test_scripted_turn_samples(api, pairing):
+    """Player::addTrainingSample inside scripted / random turns, recorded on the device (az_env_record_turns): every finished game's
+    records — state image, one-hot policy, value from updateValues — equal the oracle's (which is pinned byte for byte to the
+    reference's own players and NNTrainDataStorage, tests/test_samples.py), and the board states stay in lockstep while recording
+    (the recording path applies reinforcement / mobilisation in MIN_UNIT_MOVE steps, the plain path in one)"""
+    n, first = 48, 4100
+    kinds = {"script_vs_script": (api.OPPONENT_SCRIPT, api.OPPONENT_SCRIPT), "script_vs_random": (api.OPPONENT_SCRIPT, api.OPPONENT_RANDOM),
+             "random_vs_random": (api.OPPONENT_RANDOM, api.OPPONENT_RANDOM)}[pairing]
+    env = api.Env(n, first_game_id=first)
+    env.reset(SEED)
+    env.record_turns(capacity_samples=n * 3000, max_samples_per_game=4096)
+    script = np.full((n, 2), api.SCRIPT_INIT, np.uint32)
+    games = [po.OracleGame() for _ in range(n)]
+    sps = [[po.new_script(), po.new_script()] for _ in range(n)]
+    sinks = [po.TurnSink(4096) for _ in range(n)]
+    for g, o in enumerate(games):
+        o.new_game(SEED, first + g, 0)
+    expect = {}
+    for ply in range(130):
+        st = env.play_turn(kinds[0], kinds[1], script)
+        dev = env.export_aos()
+        for g, o in enumerate(games):
+            if o.status() != -1:
+                assert st[g] == -4
+                continue
+            cur = o.s.cur
+            if kinds[cur] == api.OPPONENT_SCRIPT:
+                assert o.script_turn_rec(sps[g][cur], SEED, first + g, ply, sinks[g]) == 0
+            else:
+                assert o.random_turn_rec(SEED, first + g, ply, sinks[g]) == 0
+            assert st[g] == o.status()
+            assert (dev[g] == o.data()).all(), "game %d differs after turn %d" % (g, ply)
+            if o.status() != -1:
+                expect[g] = sinks[g].records(o.status(), o)
+    assert len(expect) > n // 2
+    recs, dropped = env.turn_samples()
+    assert dropped == 0 and len(recs) == sum(len(v) for v in expect.values()) and len(recs) > 5000
+    # the queue holds whole games in the order their warps reserved space: match each game's block by content
+    want = sorted(v.tobytes() for v in expect.values())
+    got, i = [], 0
+    blob = recs.tobytes()
+    remaining = dict((k, v.tobytes()) for k, v in expect.items())
+    while i < len(recs):
+        hit = None
+        for g, b in remaining.items():
+            if blob.startswith(b, i * 265):
+                hit = g
+                break
+        assert hit is not None, "record %d starts no expected game block" % i
+        got.append(remaining.pop(hit))
+        i += len(got[-1]) // 265
+    assert sorted(got) == want and not remaining
+    assert env.turn_samples()[0].shape[0] == 0              # drained
+    env.close()
