@@ -102,9 +102,15 @@ __device__ __forceinline__ void wg_load(WG& w, const uint32_t* __restrict__ st, 
     __syncwarp();
     if (lane < 16) w.row[lane] = st[(size_t)lane * n + gi];
     __syncwarp();
-    w.g.own0 = w.g.own1 = w.g.gt1 = w.g.full = 0;
-#pragma unroll
-    for (int k = 0; k < 11; ++k) az_masks_add_word(w.g, w.row[k], k);
+    // the four land masks by warp votes: lane l looks at lands l and l + 32 (ncu: the per-lane loop over all 42 lands that
+    // az_masks_add_word runs was 17 % of k_mcts_sim's instructions)
+    const uint8_t* lb = (const uint8_t*)w.row;
+    const uint32_t b0 = lb[lane], b1 = lane < AZ_LANDS - 32 ? lb[32 + lane] : 0x80u;      // 0x80: neutral, no army
+    const uint32_t a0 = b0 & 63u, a1 = b1 & 63u;
+    w.g.own0 = (uint64_t)__ballot_sync(FULL, (b0 >> 6) == 0u) | ((uint64_t)__ballot_sync(FULL, (b1 >> 6) == 0u) << 32);
+    w.g.own1 = (uint64_t)__ballot_sync(FULL, (b0 >> 6) == 1u) | ((uint64_t)__ballot_sync(FULL, (b1 >> 6) == 1u) << 32);
+    w.g.gt1 = (uint64_t)__ballot_sync(FULL, a0 > 1u) | ((uint64_t)__ballot_sync(FULL, a1 > 1u) << 32);
+    w.g.full = (uint64_t)__ballot_sync(FULL, a0 == AZ_ARMY_MAX) | ((uint64_t)__ballot_sync(FULL, a1 == AZ_ARMY_MAX) << 32);
     az_unpack_scalars(w.g, w.row[10], w.row[11], w.row[12], w.row[13]);
 }
 
@@ -277,11 +283,13 @@ __device__ __forceinline__ void expand_and_backup(const MctsDev& m, int slot, in
         } else { p0 = 1.0f / 43.0f; p1 = lane + 32 < AZ_MOVES ? 1.0f / 43.0f : 0.0f; value = 0.0f; }
         if (!((valid >> lane) & 1ull)) p0 = 0.0f;
         if (lane + 32 >= AZ_MOVES || !((valid >> (lane + 32)) & 1ull)) p1 = 0.0f;
-        float sum = 0.0f;                                   // ascending-order fp32 sum, like the reference loop
-        for (int i = 0; i < AZ_MOVES; ++i) {
-            float pi = __shfl_sync(FULL, i < 32 ? p0 : p1, i & 31);
-            if ((valid >> i) & 1ull) sum = __fadd_rn(sum, pi);
-        }
+        // ascending-order fp32 sum over the valid entries, like the reference loop (alphazero_nn_data.cpp:3-27); the invalid ones
+        // were set to +0 above and x + 0 == x exactly, so no entry needs a test
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sum = __fadd_rn(sum, __shfl_sync(FULL, p0, i));
+#pragma unroll
+        for (int i = 0; i < AZ_MOVES - 32; ++i) sum = __fadd_rn(sum, __shfl_sync(FULL, p1, i));
         if (p0 > 0.0f) p0 = __fdiv_rn(p0, sum);
         if (p1 > 0.0f) p1 = __fdiv_rn(p1, sum);
         uint64_t h; int ins;
