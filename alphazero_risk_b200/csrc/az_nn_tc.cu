@@ -307,6 +307,9 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
     uint64_t* bar_pw_full = bars + 36 + 2 * TC2_STAGES;   // leader only
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 64);
 
+    // let the next tower layer (launched with the programmatic-serialization attribute) be scheduled onto SMs as this grid's
+    // CTAs exit: its barrier / TMEM set-up then overlaps this layer's last wave; it reads nothing of ours before its pdl_wait()
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t crank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
@@ -336,6 +339,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    pdl_wait();                                           // the previous kernel's activations are complete and visible from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -558,8 +562,8 @@ __global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __rest
     // 1x1 convolutions (pi: 2 channels, v: 1 channel) + BatchNorm + ReLU.  One thread per board cell walks the 32 channel chunks:
     // a warp reads 32 consecutive 16-byte cells of one chunk (512 contiguous bytes) per step and needs no reduction
     // (lane = chunk with a warp reduction per cell read 16 bytes out of every 32-byte sector and ran 56 us for 4096 boards).
-    __shared__ float s_w[3][256];
-    for (int c = threadIdx.x; c < 256; c += 256) { s_w[0][c] = hp.pi_w[c * 2]; s_w[1][c] = hp.pi_w[c * 2 + 1]; s_w[2][c] = hp.v_w[c]; }
+    __shared__ float4 s_w[256];                    // (pi0, pi1, v, -) per input channel: one 16-byte broadcast load per channel
+    for (int c = threadIdx.x; c < 256; c += 256) s_w[c] = make_float4(hp.pi_w[c * 2], hp.pi_w[c * 2 + 1], hp.v_w[c], 0.0f);
     __syncthreads();
     const float sc0 = hp.bn_pi[0] * rsqrtf(hp.bn_pi[6] + AZ_NN_BN_EPS), sc1 = hp.bn_pi[1] * rsqrtf(hp.bn_pi[7] + AZ_NN_BN_EPS);
     const float scv = hp.bn_v[0] * rsqrtf(hp.bn_v[3] + AZ_NN_BN_EPS);
@@ -576,8 +580,9 @@ __global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __rest
             for (int e = 0; e < 4; ++e) {
                 const float2 xv = __bfloat1622float2(c2[e]);
                 const int ch = c * 8 + 2 * e;
-                s0 = fmaf(xv.x, s_w[0][ch], s0); s1 = fmaf(xv.x, s_w[1][ch], s1); s2 = fmaf(xv.x, s_w[2][ch], s2);
-                s0 = fmaf(xv.y, s_w[0][ch + 1], s0); s1 = fmaf(xv.y, s_w[1][ch + 1], s1); s2 = fmaf(xv.y, s_w[2][ch + 1], s2);
+                const float4 wa = s_w[ch], wb = s_w[ch + 1];
+                s0 = fmaf(xv.x, wa.x, s0); s1 = fmaf(xv.x, wa.y, s1); s2 = fmaf(xv.x, wa.z, s2);
+                s0 = fmaf(xv.y, wb.x, s0); s1 = fmaf(xv.y, wb.y, s1); s2 = fmaf(xv.y, wb.z, s2);
             }
         }
         s_pi[bl][p * 2 + 0] = fmaxf((s0 - hp.bn_pi[4]) * sc0 + hp.bn_pi[2], 0.0f);
@@ -675,10 +680,14 @@ static cudaError_t launch_conv_pair3(int grid, cudaStream_t s, const __nv_bfloat
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES; cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    // programmatic dependent launch between consecutive layers (AZ_TC_PDL=0 turns it off for A/B runs)
+    static const bool pdl = !(getenv("AZ_TC_PDL") && atoi(getenv("AZ_TC_PDL")) == 0);
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<false>, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles, (float*)nullptr);
 }
 
