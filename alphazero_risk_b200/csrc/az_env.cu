@@ -967,7 +967,7 @@ extern "C" int az_env_rollout(az_env* e, int n_steps, void* stream)
     // parked lanes a warp collects before it runs the component search / the re-deal for them
     static const bool v1 = getenv("AZ_ENV_ROLLOUT") != nullptr && strcmp(getenv("AZ_ENV_ROLLOUT"), "v1") == 0;
     static const int park_f = getenv("AZ_ENV_PARK_F") ? atoi(getenv("AZ_ENV_PARK_F")) : 8;
-    static const int park_r = getenv("AZ_ENV_PARK_R") ? atoi(getenv("AZ_ENV_PARK_R")) : 2;
+    static const int park_r = getenv("AZ_ENV_PARK_R") ? atoi(getenv("AZ_ENV_PARK_R")) : 3;      // swept 1..8 x park_f 4..12 on B200: 8 / 3 = 15.1 G steps/s
     if (v1)
         k_env_rollout_v1<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
                                                                dev_rules(e->rules), e->d_counters);
