@@ -67,6 +67,7 @@ struct AzTcState {
     size_t in_var_stride = 0;                                  // elements between the three copies of the encoded input (49-row layout)
     float* d_scale = nullptr; float* d_shift = nullptr;        // [2*blocks][256] folded BN, then [256] (7 used) for the stem's row BN
     float* d_x = nullptr;                                      // fp32 encode of the leaf states
+    unsigned* d_tile_done = nullptr;                           // [tile pairs] layer-to-layer pipelining counters (k_nn_conv_tc3)
 };
 
 #include "az_tc_ptx.cuh"
@@ -288,8 +289,14 @@ template <bool RAW>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ wpacked3, const float* __restrict__ scale,
               const float* __restrict__ shift, const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
-              int n_boards, int r_alloc, int n_tiles, float* __restrict__ out32)
+              int n_boards, int r_alloc, int n_tiles, float* __restrict__ out32, unsigned* __restrict__ tile_done, unsigned poll_target)
 {
+    // Layer-to-layer pipelining (inference tower): tile_done[item] counts the epilogue warps (8 per tile pair) that have stored
+    // their rows of `item`, summed over the layers of this forward (zeroed per forward).  A layer with poll_target = 8 x (its index)
+    // does not wait for the whole previous layer (no griddepcontrol.wait): its streamer waits, per item, for the three items of the
+    // previous layer its operand rows come from (the item and the 8-row halos of its neighbours).  The same condition covers the
+    // write-after-read hazards of the three rotating activation buffers (whoever still reads rows near item i is one of those three
+    // items of the previous layer), and at most two consecutive layers are ever resident (a CTA pair needs a whole SM pair).
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;                                   // T3_G x T3_SLOT_BYTES
     uint8_t* sB = smem + T3_G * T3_SLOT_BYTES;            // TC2_STAGES x TC2_STAGE_BYTES
@@ -339,7 +346,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
-    pdl_wait();                                           // the previous kernel's activations are complete and visible from here on
+    if (poll_target == 0u) pdl_wait();                    // the previous kernel's activations are complete and visible from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -349,6 +356,16 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
             const uint8_t* src = reinterpret_cast<const uint8_t*>(in);
             auto load_group = [&](int q) {
                 const int slot = q % T3_G, rnd = q / T3_G, kb = q & 7, tile = tile_of_group(q);
+                if (poll_target != 0u && kb == 0) {       // first K group of an item: the previous layer's rows must be there
+                    const int item = pid + (q >> 3) * n_pairs;
+                    for (int jj = item - 1; jj <= item + 1; ++jj) {
+                        if (jj < 0 || jj >= n_items) continue;
+                        unsigned v;
+                        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tile_done + jj) : "memory"); }
+                        while ((int)(v - poll_target) < 0);
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");      // those generic-proxy stores -> this thread's bulk copies
+                }
                 if (rnd > 0) mbar_wait_cluster(bar_a_empty + slot, (uint32_t)((rnd - 1) & 1));
                 mbar_expect_tx(bar_a_full + slot, T3_VAR_BYTES);
                 for (int c = 0; c < 4; ++c)
@@ -502,7 +519,11 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (leader) mbar_arrive(bar_acc_empty + b); else mbar_arrive_remote(bar_acc_empty + b, 0u); }
+            if (lane == 0) {
+                if (tile_done)                            // this warp's rows of the item are stored (also counted when the tile is padding)
+                    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(tile_done + pid + j * n_pairs), "r"(1u) : "memory");
+                if (leader) mbar_arrive(bar_acc_empty + b); else mbar_arrive_remote(bar_acc_empty + b, 0u);
+            }
         }
     }
     tc_fence_before();
@@ -676,7 +697,8 @@ static void pack_conv_pair(const float* w, __nv_bfloat16* dst, bool kb_outer = t
 }
 
 static cudaError_t launch_conv_pair3(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w3, const float* scale, const float* shift,
-                                     const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles)
+                                     const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles,
+                                     unsigned* tile_done, unsigned poll_target)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES; cfg.stream = s;
@@ -688,7 +710,8 @@ static cudaError_t launch_conv_pair3(int grid, cudaStream_t s, const __nv_bfloat
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<false>, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles, (float*)nullptr);
+    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<false>, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles, (float*)nullptr,
+                              tile_done, poll_target);
 }
 
 // persistent launch of one stem / one-CTA tower convolution
@@ -1011,7 +1034,7 @@ static int conv_raw_launch(AzTcConvScratch* sc, const __nv_bfloat16* in49, int n
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     AZ_CUDA(cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<true>, in49, (const uint8_t*)sc->d_w, (const float*)nullptr, (const float*)nullptr,
-                               (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, n, sc->r_alloc, tiles, d_out));
+                               (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, n, sc->r_alloc, tiles, d_out, (unsigned*)nullptr, 0u));
     return AZ_OK;
 }
 
@@ -1113,6 +1136,7 @@ void az_nn_tc_release(az_nn* nn)
     AzTcState* tc = nn->tc;
     for (int i = 0; i < 3; ++i) cudaFree(tc->d_act[i]);
     cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_wpacked3); cudaFree(tc->d_scale); cudaFree(tc->d_shift); cudaFree(tc->d_x);
+    cudaFree(tc->d_tile_done);
     delete tc;
     nn->tc = nullptr;
 }
@@ -1135,6 +1159,8 @@ static int tc_reserve(AzTcState* tc, int n)
     AZ_CUDA(cudaMemset(tc->d_in, 0, (size_t)nv * 2 * r_alloc * 16));
     tc->in_var_stride = (size_t)2 * r_alloc * 8;
     AZ_CUDA(cudaMalloc(&tc->d_x, sizeof(float) * (size_t)n * AZ_INPUT_FLOATS));
+    cudaFree(tc->d_tile_done); tc->d_tile_done = nullptr;
+    AZ_CUDA(cudaMalloc(&tc->d_tile_done, sizeof(unsigned) * (size_t)(tiles / 2 + 1)));
     tc->cap_boards = n; tc->n_tiles = tiles; tc->r_alloc = r_alloc;
     return AZ_OK;
 }
@@ -1165,6 +1191,12 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
                                          tc->r_alloc, tiles, rpb, 0)));
     const int pitems = (tiles + 1) / 2;
     const int pgrid = 2 * (pitems < tc->max_pairs ? pitems : tc->max_pairs);
+    // layer-to-layer pipelining of the tower: an experiment kept behind AZ_TC_PIPE=1 (needs the programmatic launches).  Same results,
+    // but 1.6 % SLOWER at configs[2] (1.952 vs 1.985 M simulations/s, two interleaved A/B pairs): the forward sits at the board's power
+    // cap, so filling the idle SM pairs of a layer's last wave only lowers the clock of everything else (profiles/README.md)
+    static const bool pipe = getenv("AZ_TC_PIPE") && atoi(getenv("AZ_TC_PIPE")) == 1 && !(getenv("AZ_TC_PDL") && atoi(getenv("AZ_TC_PDL")) == 0);
+    unsigned* tile_done = (pipe && rpb == 49) ? tc->d_tile_done : nullptr;
+    if (tile_done) AZ_CUDA(cudaMemsetAsync(tile_done, 0, sizeof(unsigned) * (size_t)pitems, s));
     for (int i = 0; i < nn->blocks; ++i) {
         for (int h = 0; h < 2; ++h) {                        // branch2a: cur -> tmp; branch2b: tmp (+ cur as the residual) -> nxt
             const int L = 2 * i + h;
@@ -1173,7 +1205,8 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
             __nv_bfloat16* dst = h ? tc->d_act[nxt] : tc->d_act[tmp];
             const float* sc = tc->d_scale + L * 256; const float* sh = tc->d_shift + L * 256;
             if (rpb == 49)
-                AZ_CUDA(launch_conv_pair3(pgrid, s, src, tc->d_wpacked3 + (size_t)L * TC_LAYER_BYTES, sc, sh, res, dst, n, tc->r_alloc, tiles));
+                AZ_CUDA(launch_conv_pair3(pgrid, s, src, tc->d_wpacked3 + (size_t)L * TC_LAYER_BYTES, sc, sh, res, dst, n, tc->r_alloc, tiles,
+                                          tile_done, tile_done ? 8u * (unsigned)L : 0u));
             else
                 AZ_CUDA((launch_conv<32, false, 1>(grid, s, src, tc->d_wpacked + (size_t)L * TC_LAYER_BYTES, sc, sh, res, dst, n, tc->r_alloc, tiles, rpb, 0)));
         }
