@@ -86,7 +86,11 @@ const uint64_t* az_device_tables()
 
 // ---------------------------------------------------------------- per-thread game context
 #ifndef ENV_BLOCK
-#define ENV_BLOCK 256      // swept 32..256 on B200 (tools/env_block.sh): 13.7 / 13.8 / 13.8 / 14.2 G steps/s — the kernel is latency bound per warp
+// The rollout kernel is bound by the latency of each warp's dependent instructions, so what matters is how many warps share an SM's
+// schedulers.  65536 games are 13.8 warps per SM: 448-thread blocks make 147 blocks = one per SM = 14 warps on every SM, where
+// 256-thread blocks put two blocks (16 warps) on 108 SMs and one on 40.  Swept on B200 (tools/env_block.sh, G steps/s):
+// 32..128: 13.7-13.8 (before the wide tables), 224: 15.3, 256: 15.1, 320: 13.0, 448: 15.85.  Static shared memory stays under 48 KB.
+#define ENV_BLOCK 448
 #endif
 #define ENV_COL_WORDS 22     // 11 land words + 11 fortify-DFS parent words per thread
 
