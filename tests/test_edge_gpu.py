@@ -58,6 +58,25 @@ def test_bad_arguments_are_rejected_with_a_message(api):
         mc.samples()                                                      # recording was never enabled
     with pytest.raises(api.AzError):
         api.Arena(mc, opponent=7)
+    # recorder of scripted / random turns: drained before it was enabled, enabled twice, bad player kinds, a scripted side without
+    # its member array; a game with more samples than its staging area is dropped whole and counted
+    with pytest.raises(api.AzError):
+        env.turn_samples()
+    with pytest.raises(api.AzError):
+        env.record_turns(0)
+    env.record_turns(capacity_samples=1000, max_samples_per_game=8)
+    with pytest.raises(api.AzError):
+        env.record_turns(1000)
+    with pytest.raises(api.AzError):
+        env.play_turn(api.OPPONENT_SCRIPT, api.OPPONENT_ALPHAZERO, np.full((4, 2), api.SCRIPT_INIT, np.uint32))
+    with pytest.raises(api.AzError):
+        env.play_turn(api.OPPONENT_SCRIPT, api.OPPONENT_RANDOM, None)
+    env.reset(SEED)
+    for _ in range(200):
+        if (env.play_turn(api.OPPONENT_RANDOM, api.OPPONENT_RANDOM) != -1).all():
+            break
+    recs, dropped = env.turn_samples()
+    assert len(recs) == 0 and dropped > 4 * 8                          # every game overflowed its 8-sample staging area
     mc.close(); env.close()
 
 
