@@ -565,6 +565,73 @@ __global__ void __launch_bounds__(256) k_nn_pack_input_tc(const float* __restric
     }
 }
 
+// The same packed input straight from the game states (the leaf batch of a search): NNInputData + setInStateTensor
+// (alphazero_nn_data.cpp:165-196, alphazero_nn.cpp:31-67) as k_env_encode computes them (az_env.cu — same expressions, same
+// roundings), rounded to bf16 and written in the layout above without the fp32 [n][42][13] round trip through HBM.
+// One warp per position; lane l packs board cells l and l + 32.
+__global__ void __launch_bounds__(128) k_nn_pack_state_tc(const uint32_t* __restrict__ st, int n, __nv_bfloat16* __restrict__ out, int r_alloc,
+                                                           int rpb, size_t var_stride)
+{
+    __shared__ uint32_t s_words[4][16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gi = blockIdx.x * 4 + warp;
+    if (gi >= n) return;
+    if (lane < 14) s_words[warp][lane] = st[(size_t)lane * n + gi];
+    __syncwarp();
+    const uint8_t* land = (const uint8_t*)s_words[warp];
+    AzGame g;
+    az_unpack_scalars(g, s_words[warp][10], s_words[warp][11], s_words[warp][12], s_words[warp][13]);
+    const uint32_t b0 = land[lane], b1 = lane < 10 ? land[32 + lane] : (3u << 6);
+    const uint32_t m0a = __ballot_sync(0xffffffffu, (b0 >> 6) == 0), m0b = __ballot_sync(0xffffffffu, (b1 >> 6) == 0);
+    const uint32_t m1a = __ballot_sync(0xffffffffu, (b0 >> 6) == 1), m1b = __ballot_sync(0xffffffffu, (b1 >> 6) == 1);
+    g.own0 = (uint64_t)m0a | ((uint64_t)m0b << 32); g.own1 = (uint64_t)m1a | ((uint64_t)m1b << 32);
+    int t0 = ((b0 >> 6) == 0 ? (int)(b0 & 63u) : 0) + ((b1 >> 6) == 0 ? (int)(b1 & 63u) : 0);
+    int t1 = ((b0 >> 6) == 1 ? (int)(b0 & 63u) : 0) + ((b1 >> 6) == 1 ? (int)(b1 & 63u) : 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
+    const uint32_t cur = g.cur, enemy = cur ^ 1u;
+    const float ref = (float)az_reinforcement_value(g.own(cur)), eref = (float)az_reinforcement_value(g.own(enemy));
+    const float reinf_share = __fdiv_rn(ref, __fadd_rn(ref, eref));
+    float att = __fdiv_rn((float)g.attacks, 8.0f); att = att < 1.0f ? att : 1.0f;
+    const float ta = (float)(cur ? t1 : t0), eta = (float)(cur ? t0 : t1);
+    const float army_share = __fdiv_rn(ta, __fadd_rn(ta, eta));
+    // channels 3..12 are the same for every cell of the board: chunk 0 = {own, enemy, neutral, 3, 4, 5, 6, 7}, chunk 1 = {8..12, 0, 0, 0}
+    float sc[10];
+    sc[0] = army_share; sc[1] = reinf_share; sc[2] = att; sc[3] = g.allow_draw ? 1.0f : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sc[4 + k] = g.phase == (uint32_t)k ? 1.0f : 0.0f;
+    uint4 c1;
+    {
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&c1);
+        o2[0] = __floats2bfloat162_rn(sc[5], sc[6]); o2[1] = __floats2bfloat162_rn(sc[7], sc[8]);
+        o2[2] = __floats2bfloat162_rn(sc[9], 0.0f); o2[3] = __floats2bfloat162_rn(0.0f, 0.0f);
+    }
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int p = lane + 32 * h;
+        if (p >= 42) break;
+        const uint32_t v = h ? b1 : b0, o = v >> 6;
+        const float fa = __fdiv_rn((float)(v & 63u), 32.0f);
+        uint4 c0;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&c0);
+        o2[0] = __floats2bfloat162_rn(o == cur ? fa : 0.0f, o == enemy ? fa : 0.0f);
+        o2[1] = __floats2bfloat162_rn(o == AZ_NEUTRAL ? fa : 0.0f, sc[0]);
+        o2[2] = __floats2bfloat162_rn(sc[1], sc[2]); o2[3] = __floats2bfloat162_rn(sc[3], sc[4]);
+        const int row = gi * rpb + tc_cell_row(p, rpb);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const uint4 val = c ? c1 : c0;
+            const size_t at = ((size_t)c * r_alloc + TC_HALO + row) * 8;
+            *reinterpret_cast<uint4*>(out + at) = val;
+            if (rpb == 49) {
+                *reinterpret_cast<uint4*>(out + var_stride + at) = (p % 6) == 5 ? zero : val;
+                *reinterpret_cast<uint4*>(out + 2 * var_stride + at) = (p % 6) == 0 ? zero : val;
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ float warp_sum_tc(float v)
 {
 #pragma unroll
@@ -1170,7 +1237,11 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
     AzTcState* tc = nn->tc;
     if (!tc || !tc->d_wpacked) { az_set_error("network not finalized"); return AZ_ERR_NOT_READY; }
     int rc = tc_reserve(tc, n); if (rc) return rc;
-    if (!d_x) {
+    // from game states: one kernel packs the stem's bf16 input (AZ_TC_FUSED_PACK=0: k_env_encode to fp32, then k_nn_pack_input_tc)
+    const char* fp_env = getenv("AZ_TC_FUSED_PACK");            // read per call: the A/B test flips it inside one process
+    const bool fused_pack = !(fp_env && atoi(fp_env) == 0);
+    const bool from_state = !d_x && fused_pack;
+    if (!d_x && !fused_pack) {
         rc = az_launch_encode(d_env_state, n, tc->d_x, s); if (rc) return rc;
         d_x = tc->d_x;
     }
@@ -1180,7 +1251,8 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
     const int grid = tiles < tc->n_sm ? tiles : tc->n_sm;
     const int layers = 2 * nn->blocks;
     int cur = 0, tmp = 1, nxt = 2;
-    k_nn_pack_input_tc<<<(n * 42 + 255) / 256, 256, 0, s>>>(d_x, n, tc->d_in, tc->r_alloc, rpb, tc->in_var_stride);
+    if (from_state) k_nn_pack_state_tc<<<(n + 3) / 4, 128, 0, s>>>(d_env_state, n, tc->d_in, tc->r_alloc, rpb, tc->in_var_stride);
+    else k_nn_pack_input_tc<<<(n * 42 + 255) / 256, 256, 0, s>>>(d_x, n, tc->d_in, tc->r_alloc, rpb, tc->in_var_stride);
     AZ_CUDA(cudaGetLastError());
     const uint8_t* w_stem = tc->d_wpacked + (size_t)layers * TC_LAYER_BYTES;
     if (rpb == 49)

@@ -317,7 +317,7 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
                 clocks=sp_clocks,
                 e2e={"value": n * sims * e2e_moves * world / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": n * 160,
                      "d2h_bytes_per_step": n * (43 * 8 + 2 + 160), "steps": e2e_moves},
-                gpu_launches=steps * moves_per_step * (2 + (sims // K + 1) * (2 + 1 + 2 * blocks + 1 + 1)),
+                gpu_launches=steps * moves_per_step * (2 + (sims // K + 1) * (1 + 1 + 1 + 2 * blocks + 1)),   # begin, finish; per round: tree, pack, stem, tower, heads
                 dtype="bf16 tower / fp32 tree", results={"games_finished": tot_games, "table_errors": errors}, tree=tree)
 
 

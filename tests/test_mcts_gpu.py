@@ -239,3 +239,33 @@ def test_full_size_search_properties_and_shard_invariance(api):
     for (v1, n1, p1, m1), (v2, n2, p2, m2) in zip(full, half):
         assert (n1[n // 2:] == n2).all() and (m1[n // 2:] == m2).all()
     net.close()
+
+
+def test_fused_state_packing_changes_nothing(api):
+    """the leaf batch of a bf16 search reaches the stem through ONE kernel that packs bf16 operands straight from the game states
+    (k_nn_pack_state_tc); AZ_TC_FUSED_PACK=0 takes the two-step route (k_env_encode to fp32, k_nn_pack_input_tc).  Same
+    expressions, same roundings: the two routes must give the same search — visit counts, moves and states, bit for bit."""
+    import os
+    rules = api.default_rules(mcts_simulations=12, threads_per_mcts=1)
+    net = api.Net(blocks=2, seed=77)
+    out = {}
+    for fused in ("1", "0"):
+        os.environ["AZ_TC_FUSED_PACK"] = fused
+        try:
+            env = api.Env(70, rules=rules, first_game_id=900)          # 70 positions: more than one 128-row tile, ragged
+            env.reset(SEED)
+            env.rollout(90)                                            # out of the set-up phase: every channel of the encoding is live
+            mc = api.Mcts(env, net=net, evaluator=api.EVAL_NN, precision=api.BF16)
+            visits = []
+            for _ in range(5):
+                r = mc.search(pick_mode=api.PICK_SELFPLAY, apply_move=True)
+                visits.append((r["N"].copy(), r["move"].copy()))
+            assert mc.counters()["errors"] == 0
+            out[fused] = (visits, env.export_aos().copy())
+            mc.close(); env.close()
+        finally:
+            os.environ.pop("AZ_TC_FUSED_PACK", None)
+    for (n1, m1), (n0, m0) in zip(out["1"][0], out["0"][0]):
+        assert (n1 == n0).all() and (m1 == m0).all()
+    assert (out["1"][1] == out["0"][1]).all()
+    net.close()
