@@ -7,6 +7,8 @@ import pytest
 
 from oracle import pyoracle as po
 
+SEED = 0x5EED0001
+
 
 @pytest.fixture(scope="module")
 def env_trace(golden_dir):
@@ -138,3 +140,28 @@ def test_mcts_trace_bit_exact(golden_dir, name):
         assert o.move(mv, seed, g, ply) == 0
     assert (o.data() == t[name + "_final"]).all()
     assert o.status() == int(t[name + "_status"])
+
+
+@pytest.mark.parametrize("pairing", ["script_vs_script", "script_vs_random"])
+def test_turn_samples_golden(golden_dir, pairing):
+    """Player::addTrainingSample inside scripted / random turns: the oracle's recorder (ro_script_turn_rec / ro_random_turn_rec)
+    against the bytes the REFERENCE's own players and NNTrainDataStorage::saveTrainingSamples wrote for the same games
+    (tests/golden/turn_samples.npz, generator tests/golden/gen_turn_samples.py; runs without /root/reference)."""
+    z = np.load(os.path.join(golden_dir, "turn_samples.npz"))
+    games = sorted(int(k.split("_")[-2]) for k in z.files if k.startswith(pairing) and k.endswith("_records"))
+    assert len(games) == 2
+    for game in games:
+        want = z["%s_%d_records" % (pairing, game)]
+        status, plies, n = (int(v) for v in z["%s_%d_meta" % (pairing, game)])
+        orc = po.OracleGame()
+        orc.new_game(SEED, game, 0)
+        sps, sink, ply = [po.new_script(), po.new_script()], po.TurnSink(4096), 0
+        while orc.status() == -1:
+            cur = orc.s.cur
+            if pairing == "script_vs_script" or cur == 0:
+                assert orc.script_turn_rec(sps[cur], SEED, game, ply, sink) == 0
+            else:
+                assert orc.random_turn_rec(SEED, game, ply, sink) == 0
+            ply += 1
+        assert (orc.status(), ply, len(sink)) == (status, plies, n)
+        assert (sink.records(status, orc) == want).all()
