@@ -16,6 +16,7 @@
 // Errors: std::runtime_error with az_last_error(), like az_nn_service.hpp.  No CPU fallback.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <fstream>
 #include <stdexcept>
@@ -135,6 +136,71 @@ private:
         if (env) az_env_destroy(env);
         arena = nullptr; mcts = nullptr; opponent_mcts = nullptr; env = nullptr; n_slots = 0;
     }
+};
+
+// The data generation of AlphaZeroTrainer::trainOnGeneratedData (alphazero_trainer.cpp:242-268): DATA_GAMES_SS Script-vs-Script and
+// DATA_GAMES_SR Script-vs-Random games whose players carry a shared NNTrainDataStorage (Player::addTrainingSample, one-hot policies;
+// values from gameFinished -> updateValues) — played in lockstep on the device.  play() returns packed AZ_SAMPLE_BYTES records, the
+// layout NNTrainDataStorage::saveTrainingSamples writes, ready for az_nn_train / az_samples_write_file:
+//
+//   azb200::DeviceDataGames gen(settings, 4096);
+//   auto recs = gen.play(SETTINGS.DATA_GAMES_SS, /*second_is_random*/ false);
+//   auto more = gen.play(SETTINGS.DATA_GAMES_SR, true);          recs.insert(recs.end(), more.begin(), more.end());
+//   az_nn_train(nn, recs.data(), recs.size() / AZ_SAMPLE_BYTES, 3, SETTINGS.BATCH_SIZE, seed, nullptr, nullptr, nullptr);
+class DeviceDataGames {
+public:
+    DeviceDataGames(const PlaySettings& s, int slots, int max_samples_per_game = 4096) : st(s), n(slots)
+    {
+        if (az_device_count() == 0) throw std::runtime_error("azb200::DeviceDataGames: no CUDA device (libaz_b200 has no CPU fallback)");
+        if (slots <= 0) throw std::invalid_argument("azb200::DeviceDataGames: slots must be positive");
+        az_rules r; az_default_rules(&r);
+        r.allow_yield = st.ALLOW_YIELD; r.limit_reinforcement = st.LIMIT_REINFORCEMENT_MOVES; r.limit_attack = st.LIMIT_ATTACK_MOVES;
+        r.max_game_rounds = st.MAX_GAME_ROUNDS; r.min_unit_move = st.MIN_UNIT_MOVE;
+        ck(az_env_create(n, &r, st.device, 0, &env), "az_env_create");
+        ck(az_env_record_turns(env, (size_t)n * (size_t)max_samples_per_game, max_samples_per_game), "az_env_record_turns");
+    }
+    ~DeviceDataGames() { if (env) az_env_destroy(env); }
+    DeviceDataGames(const DeviceDataGames&) = delete;
+    DeviceDataGames& operator=(const DeviceDataGames&) = delete;
+
+    // at least `games` games (whole batches of `slots`), player index 0 = ScriptPlayer, player index 1 = ScriptPlayer or RandomPlayer
+    std::vector<uint8_t> play(int games, bool second_is_random)
+    {
+        std::vector<uint8_t> out;
+        std::vector<uint32_t> script((size_t)n * 2);
+        std::vector<int8_t> status((size_t)n);
+        games_played = 0; dropped = 0;
+        while (games_played < games) {
+            ck(az_env_reset(env, st.seed + 0x9E3779B97F4A7C15ull * (uint64_t)(++batches), nullptr), "az_env_reset");
+            std::fill(script.begin(), script.end(), (uint32_t)AZ_SCRIPT_INIT);      // new ScriptPlayer objects per Game, alphazero_trainer.cpp:246-249
+            bool running = true;
+            for (int turn = 0; running && turn < 4096; ++turn) {
+                ck(az_env_play_turn(env, AZ_OPPONENT_SCRIPT, second_is_random ? AZ_OPPONENT_RANDOM : AZ_OPPONENT_SCRIPT, script.data(),
+                                    status.data(), nullptr), "az_env_play_turn");
+                running = false;
+                for (int8_t v : status) if (v == AZ_STATUS_RUNNING) { running = true; break; }
+            }
+            size_t have = 0; uint64_t d = 0;
+            ck(az_env_turn_samples(env, nullptr, 0, &have, &d, nullptr), "az_env_turn_samples");
+            const size_t at = out.size();
+            out.resize(at + have * (size_t)AZ_SAMPLE_BYTES);
+            ck(az_env_turn_samples(env, have ? out.data() + at : nullptr, have, &have, &d, nullptr), "az_env_turn_samples");
+            out.resize(at + have * (size_t)AZ_SAMPLE_BYTES);
+            dropped += d;
+            games_played += n;
+        }
+        return out;
+    }
+
+    int games_played = 0;             // of the last play()
+    uint64_t dropped = 0;             // samples of games that overflowed their staging area (0 with the default 4096 per game)
+
+private:
+    PlaySettings st;
+    int n;
+    az_env* env = nullptr;
+    uint64_t batches = 0;
+    static void ck(int rc, const char* what) { if (rc != AZ_OK) throw std::runtime_error(std::string(what) + ": " + az_last_error()); }
 };
 
 }  // namespace azb200

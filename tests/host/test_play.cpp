@@ -1,6 +1,7 @@
 // Standalone test of alphazero_risk_b200/host/az_play.hpp with a mirror of the reference's GameResults (game/game.h:10-29).
 // Without a GPU: construction must fail loudly -> NO_DEVICE_OK.  With a GPU: a 40-game match (--mcts=16, -t 2) -> PLAY_OK.
 #include <cstdio>
+#include <cstring>
 #include <vector>
 #include "az_play.hpp"
 
@@ -35,6 +36,24 @@ int main()
     p.setOpponent(AZ_OPPONENT_RANDOM);                     // the trainer's benchmark opponent
     GameResults d = p.playGames<GameResults>(6);
     ok = ok && d.count == 6;
+    // trainOnGeneratedData's bootstrap games: Script vs Random with every Player::addTrainingSample recorded, then three epochs on them
+    {
+        azb200::DeviceDataGames gen(s, 24);
+        std::vector<uint8_t> recs = gen.play(30, true);        // 30 games asked: two batches of 24
+        const size_t nrec = recs.size() / AZ_SAMPLE_BYTES;
+        bool data_ok = gen.games_played == 48 && gen.dropped == 0 && nrec > 48 * 100 && recs.size() % AZ_SAMPLE_BYTES == 0;
+        for (size_t i = 0; data_ok && i < nrec; i += 97) {     // one-hot policy, value in {-1, 0, 1}, player byte = NNInputData::playerIndex
+            const uint8_t* r = recs.data() + i * AZ_SAMPLE_BYTES;
+            float v, pol[43]; memcpy(&v, r + 89, 4); memcpy(pol, r + 93, sizeof pol);
+            int ones = 0, zeros = 0;
+            for (float x : pol) { ones += x == 1.0f; zeros += x == 0.0f; }
+            data_ok = ones == 1 && zeros == 42 && (v == 1.0f || v == -1.0f || v == 0.0f) && r[0] < 2 && r[0] == r[1 + 42];
+        }
+        float lp[3] = { 0, 0, 0 }, lv[3] = { 0, 0, 0 };
+        data_ok = data_ok && az_nn_train(p.network(), recs.data(), nrec, 3, 512, 7, lp, lv, nullptr) == AZ_OK && lp[2] < lp[0];
+        printf("%s bootstrap games %d samples %zu policy loss %.3f -> %.3f\n", data_ok ? "DATA_OK" : "DATA_FAIL", gen.games_played, nrec, lp[0], lp[2]);
+        ok = ok && data_ok;
+    }
     printf("%s count=%d draw=%d az=%d/%d script=%d/%d | new vs old %d/%d %d/%d draw %d | vs random az %d of %d\n", ok ? "PLAY_OK" : "PLAY_FAIL",
            a.count, a.draw, a.players[0].win, a.players[0].winAndStartedGame, a.players[1].win, a.players[1].winAndStartedGame,
            c.players[0].win, c.players[0].winAndStartedGame, c.players[1].win, c.players[1].winAndStartedGame, c.draw, d.players[0].win, d.count);
