@@ -180,6 +180,13 @@ def cpu_selfplay_baseline(sims, seconds_target):
     return res
 
 
+def env_config(n, S):
+    """the workload both arms are measured on (BASELINE.json configs[1])"""
+    return {"workload": "configs[1]: raw env throughput, %d lockstep 2-player games per GPU, uniform-random legal moves, %d moves "
+                        "per launch, finished games re-dealt in place" % (n, S),
+            "games_per_gpu": n, "lockstep_moves_per_step": S}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -195,8 +202,9 @@ def run_reference(args):
     line = dict(impl="reference", metric="env_steps_per_sec", value=value, unit="steps/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * secs / max(1, args.steps), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="u8", data="synthetic",
-                config={"workload": "configs[1]: raw env throughput, uniform-random legal moves, 2-player games re-dealt in place; "
-                                    "reference CPU path, bounded sample per step"},
+                config=dict(env_config(args.games, args.lockstep),
+                            reference_sample="the reference's State / UtilityNN code on all host threads, one game per thread re-dealt in "
+                                             "place, a bounded 1.5 s sample of the same uniform-random-move workload per step"),
                 cpu_baseline=cb, e2e={"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 wall_s=time.time() - t0)
     print(json.dumps(line))
@@ -542,10 +550,8 @@ def run_ours(args):
         achieved = ENV_BYTES_PER_STEP * n * S / (kernel_ms * 1e-3) / 1e9
         line = dict(metric="env_steps_per_sec", value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=kernel_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
-                    config={"workload": "configs[1]: raw env throughput, %d lockstep 2-player games per GPU, uniform-random legal "
-                                        "moves, %d moves per launch, finished games re-dealt in place" % (n, S),
-                            "games_per_gpu": n, "lockstep_moves_per_step": S, "l2": "256 MiB flush between timed iterations",
-                            "sharding": "games by contiguous global id, no data-path collective"},
+                    config=dict(env_config(n, S), l2="256 MiB flush between timed iterations",
+                                sharding="games by contiguous global id, no data-path collective"),
                     roofline={"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                               "traffic": ncu_traffic("k_env_rollout"), "peak_source": src,
                               "note": "algorithmic 330 B/step x games x moves per launch / CUDA-event time of k_env_rollout; the state "
