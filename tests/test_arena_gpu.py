@@ -304,7 +304,7 @@ def test_arena_claims_pairs_like_the_counter(api):
     arena.close(); mc.close(); env.close()
 
 
-@pytest.mark.parametrize("pairing", ["script_vs_script", "script_vs_random", "random_vs_random"])
+@pytest.mark.parametrize("pairing", ["script_vs_script", "script_vs_random", "random_vs_random", "script_vs_random_unit_move_1"])
 def test_scripted_turn_samples(api, pairing):
     """Player::addTrainingSample inside scripted / random turns, recorded on the device (az_env_record_turns): every finished game's
     records — state image, one-hot policy, value from updateValues — equal the oracle's (which is pinned byte for byte to the
@@ -312,14 +312,18 @@ def test_scripted_turn_samples(api, pairing):
     (the recording path applies reinforcement / mobilisation in MIN_UNIT_MOVE steps, the plain path in one)"""
     n, first = 48, 4100
     kinds = {"script_vs_script": (api.OPPONENT_SCRIPT, api.OPPONENT_SCRIPT), "script_vs_random": (api.OPPONENT_SCRIPT, api.OPPONENT_RANDOM),
-             "random_vs_random": (api.OPPONENT_RANDOM, api.OPPONENT_RANDOM)}[pairing]
-    env = api.Env(n, first_game_id=first)
+             "random_vs_random": (api.OPPONENT_RANDOM, api.OPPONENT_RANDOM),
+             "script_vs_random_unit_move_1": (api.OPPONENT_SCRIPT, api.OPPONENT_RANDOM)}[pairing]
+    # MIN_UNIT_MOVE sets the step of the recorded reinforcement / mobilisation moves: also with a non-default value
+    rule_kw = {"min_unit_move": 1, "allow_yield": 0} if pairing.endswith("unit_move_1") else {}
+    o_rules = po.default_rules(**rule_kw)
+    env = api.Env(n, rules=api.default_rules(**rule_kw), first_game_id=first)
     env.reset(SEED)
-    env.record_turns(capacity_samples=n * 3000, max_samples_per_game=4096)
+    env.record_turns(capacity_samples=n * 6000, max_samples_per_game=8192)
     script = np.full((n, 2), api.SCRIPT_INIT, np.uint32)
-    games = [po.OracleGame() for _ in range(n)]
+    games = [po.OracleGame(o_rules) for _ in range(n)]
     sps = [[po.new_script(), po.new_script()] for _ in range(n)]
-    sinks = [po.TurnSink(4096) for _ in range(n)]
+    sinks = [po.TurnSink(8192) for _ in range(n)]
     for g, o in enumerate(games):
         o.new_game(SEED, first + g, 0)
     expect = {}

@@ -112,18 +112,20 @@ def test_device_recording_matches_oracle_replay():
 
 
 @NEED_REF
+@pytest.mark.parametrize("rule_kw", [{}, {"min_unit_move": 1, "allow_yield": 0, "max_game_rounds": 40}], ids=["default_rules", "unit_move_1_no_yield"])
 @pytest.mark.parametrize("pairing", ["script_vs_script", "script_vs_random"])
-def test_scripted_turn_samples_match_reference(pairing, tmp_path):
+def test_scripted_turn_samples_match_reference(pairing, rule_kw, tmp_path):
     """Player::addTrainingSample inside ScriptPlayer / RandomPlayer turns (script_player.cpp:105-198, random_player.cpp:29-82) and
     the values gameFinished -> updateValues gives them: real reference players with ONE shared NNTrainDataStorage, as
     AlphaZeroTrainer::trainOnGeneratedData sets them up (alphazero_trainer.cpp:242-268), against ro_*_turn_rec; compared on the bytes
     saveTrainingSamples writes (NNInputData padding bytes excluded)"""
     L = po.ref_lib()
-    po.ref_apply_rules(po.default_rules())
+    rules = po.default_rules(**rule_kw)
+    po.ref_apply_rules(rules)
     keep = np.ones(265, bool); keep[[1 + 43, 1 + 46, 1 + 47]] = False
     total, skips = 0, 0
     for g in range(6):
-        ref, orc = po.RefGame(), po.OracleGame()
+        ref, orc = po.RefGame(), po.OracleGame(rules)
         ref.new_game(SEED, 500 + g, 0); orc.new_game(SEED, 500 + g, 0)
         st = L.ref_storage_new()
         rs, os_ = [L.ref_script_new(), L.ref_script_new()], [po.new_script(), po.new_script()]
@@ -162,4 +164,5 @@ def test_scripted_turn_samples_match_reference(pairing, tmp_path):
         for h in rs:
             L.ref_script_free(h)
         L.ref_random_free(rr); L.ref_storage_free(st)
+    po.ref_apply_rules(po.default_rules())                  # the reference's SETTINGS are process-wide
     assert total > 1500 and (skips > 0 or pairing == "script_vs_script")     # the script's fortify rarely has nothing to move
