@@ -230,7 +230,8 @@ class Env:
         n, dropped = C.c_size_t(0), C.c_uint64(0)
         check(self.L.az_env_turn_samples(self.h, None, C.c_size_t(0), C.byref(n), C.byref(dropped), stream))
         out = np.empty((n.value, SAMPLE_BYTES), np.uint8)
-        check(self.L.az_env_turn_samples(self.h, _ptr(out) if n.value else None, C.c_size_t(n.value), C.byref(n), C.byref(dropped), stream))
+        if n.value:          # an empty queue was drained (and its dropped count reset) by the query itself
+            check(self.L.az_env_turn_samples(self.h, _ptr(out), C.c_size_t(n.value), C.byref(n), C.byref(dropped), stream))
         return out[:n.value], int(dropped.value)
 
     def encode(self, stream=None):
@@ -530,7 +531,8 @@ class Mcts:
         n, dropped = C.c_size_t(0), C.c_uint64(0)
         check(self.L.az_selfplay_samples(self.h, None, C.c_size_t(0), C.byref(n), C.byref(dropped), stream))
         out = np.empty((n.value, SAMPLE_BYTES), np.uint8)
-        check(self.L.az_selfplay_samples(self.h, _ptr(out) if n.value else None, C.c_size_t(n.value), C.byref(n), C.byref(dropped), stream))
+        if n.value:          # an empty queue was drained (and its dropped count reset) by the query itself
+            check(self.L.az_selfplay_samples(self.h, _ptr(out), C.c_size_t(n.value), C.byref(n), C.byref(dropped), stream))
         return out[:n.value], int(dropped.value)
 
     def counters(self, reset=False, stream=None):

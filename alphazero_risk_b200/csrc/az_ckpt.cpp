@@ -236,7 +236,8 @@ bool write_file(const std::string& path, const std::string& data)
 // one block of `file` at handle (offset, size): checks the trailer, walks the entries
 bool read_block(const std::string& file, uint64_t off, uint64_t size, std::vector<std::pair<std::string, std::string>>& out, std::string& why)
 {
-    if (off + size + 5 > file.size() || size < 4) { why = "block handle outside the file"; return false; }
+    // no additions on file-supplied values (a hostile handle such as off = 2^64 - 10 must not wrap past the test)
+    if (size < 4 || file.size() < 5 || size > file.size() - 5 || off > file.size() - 5 - size) { why = "block handle outside the file"; return false; }
     const uint8_t* b = (const uint8_t*)file.data() + off;
     if (b[size] != 0) { why = "compressed table block (snappy) is not supported"; return false; }
     if (crc_unmask(get_fixed32(b + size + 1)) != crc32c_extend(0, b, size + 1)) { why = "table block checksum mismatch"; return false; }
@@ -346,7 +347,8 @@ extern "C" int az_ckpt_read(az_ckpt* c, const char* name, void* h_out, size_t by
     std::string& shard = c->shard_cache[(size_t)e.shard];
     if (shard.empty() && !read_file(shard_path(c->prefix, e.shard, c->num_shards), shard)) {
         az_set_error("cannot read %s", shard_path(c->prefix, e.shard, c->num_shards).c_str()); return AZ_ERR_INVALID_ARG; }
-    if ((uint64_t)e.offset + (uint64_t)e.size > shard.size()) { az_set_error("tensor '%s' lies outside its data shard", name); return AZ_ERR_INVALID_ARG; }
+    if (e.offset < 0 || e.size < 0 || (uint64_t)e.size > shard.size() || (uint64_t)e.offset > shard.size() - (uint64_t)e.size) {
+        az_set_error("tensor '%s' lies outside its data shard", name); return AZ_ERR_INVALID_ARG; }
     if (crc_unmask(e.crc) != crc32c_extend(0, shard.data() + e.offset, (size_t)e.size)) {
         az_set_error("tensor '%s': data checksum mismatch", name); return AZ_ERR_BAD_STATE; }
     memcpy(h_out, shard.data() + e.offset, bytes);

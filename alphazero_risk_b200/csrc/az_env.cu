@@ -404,10 +404,7 @@ __global__ void __launch_bounds__(REC_END_WARPS * 32) k_env_rec_end(TurnRecDev r
     uint8_t* s_rec = s_rec_all[warp];
     unsigned long long base = 0;
     bool ok = len <= (uint32_t)rec.max;
-    if (lane == 0) {
-        if (ok) { base = atomicAdd(&count[0], (unsigned long long)len); if (base + len > cap) ok = false; }
-        if (!ok) atomicAdd(&count[1], (unsigned long long)len);
-    }
+    if (lane == 0) ok = az_rec_reserve(count, cap, len, ok, &base);
     ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
     base = ((unsigned long long)__shfl_sync(0xffffffffu, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (uint32_t)base, 0);
     if (ok) {
@@ -914,10 +911,11 @@ extern "C" int az_env_turn_samples(az_env* e, uint8_t* h_records, size_t max_rec
     unsigned long long h[2];
     AZ_CUDA(cudaMemcpyAsync(h, e->d_rec_count, sizeof h, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaStreamSynchronize(s));
-    const size_t have = (size_t)(h[0] < e->rec_cap ? h[0] : e->rec_cap);     // reservations past the capacity were dropped (and counted)
+    AZ_REQUIRE(h[0] <= e->rec_cap, "sample queue corrupted: committed count exceeds the capacity");
+    const size_t have = (size_t)h[0];                    // committed records: az_rec_reserve never reserves past the capacity
     if (h_dropped) *h_dropped = h[1];
     *n_out = have;
-    if (!h_records) return AZ_OK;                        // size query
+    if (!h_records && have) return AZ_OK;                // size query; with an empty queue the call drains (resets the dropped count)
     AZ_REQUIRE(max_records >= have, "h_records is too small: query the size with h_records = NULL first");
     if (have) AZ_CUDA(cudaMemcpyAsync(h_records, e->d_rec_out, have * (size_t)AZ_SAMPLE_BYTES, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaMemsetAsync(e->d_rec_count, 0, sizeof h, s));

@@ -374,10 +374,7 @@ __device__ __noinline__ void rec_flush(const MctsDev& m, int gi, int status, uin
     if (len == 0) return;
     unsigned long long base = 0;
     bool ok = len <= (uint32_t)m.rec_moves;
-    if (lane == 0) {
-        if (ok) { base = atomicAdd(&m.rec_count[0], (unsigned long long)len); if (base + len > m.rec_cap) ok = false; }
-        if (!ok) atomicAdd(&m.rec_count[1], (unsigned long long)len);
-    }
+    if (lane == 0) ok = az_rec_reserve(m.rec_count, m.rec_cap, len, ok, &base);
     ok = __shfl_sync(FULL, (int)ok, 0) != 0;
     base = ((unsigned long long)__shfl_sync(FULL, (uint32_t)(base >> 32), 0) << 32) | __shfl_sync(FULL, (uint32_t)base, 0);
     if (ok) {
@@ -854,10 +851,11 @@ extern "C" int az_selfplay_samples(az_mcts* mc, uint8_t* h_records, size_t max_r
     unsigned long long h[2];
     AZ_CUDA(cudaMemcpyAsync(h, mc->d.rec_count, sizeof h, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaStreamSynchronize(s));
-    size_t have = (size_t)(h[0] < mc->d.rec_cap ? h[0] : mc->d.rec_cap);   // reservations past the capacity were dropped (and counted)
+    AZ_REQUIRE(h[0] <= mc->d.rec_cap, "sample queue corrupted: committed count exceeds the capacity");
+    const size_t have = (size_t)h[0];                  // committed records: az_rec_reserve never reserves past the capacity
     if (h_dropped) *h_dropped = h[1];
     *n_out = have;
-    if (!h_records) return AZ_OK;                      // size query
+    if (!h_records && have) return AZ_OK;              // size query; with an empty queue the call drains (resets the dropped count)
     AZ_REQUIRE(max_records >= have, "h_records is too small: query the size with h_records = NULL first");
     if (have) AZ_CUDA(cudaMemcpyAsync(h_records, mc->d.rec_out, have * (size_t)REC_BYTES, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaMemsetAsync(mc->d.rec_count, 0, sizeof h, s));

@@ -10,6 +10,24 @@
 
 #include "az_game.cuh"
 
+// Reserves `len` consecutive records of an output queue of `cap` records.  count[0] = records committed (never moves past cap, so
+// [0, count[0]) is exactly what was written), count[1] = samples dropped.  A game that does not fit is dropped whole and counted;
+// it leaves no hole (the reservation is a compare-and-swap that only succeeds when the whole game fits).  One lane calls this.
+__device__ __forceinline__ bool az_rec_reserve(unsigned long long* count, unsigned long long cap, uint32_t len, bool fits_staging,
+                                               unsigned long long* base)
+{
+    if (fits_staging) {
+        unsigned long long old = *(volatile unsigned long long*)&count[0];
+        while (old + len <= cap) {
+            const unsigned long long prev = atomicCAS(&count[0], old, old + len);
+            if (prev == old) { *base = old; return true; }
+            old = prev;
+        }
+    }
+    atomicAdd(&count[1], (unsigned long long)len);
+    return false;
+}
+
 // Fills s_rec[0..92] (player, NNInputData image, value target for a game that ended with `status`: NNTrainDataStorage::updateValues,
 // alphazero_nn_data.cpp:51-65) from the packed primary state st[14].  Called by all 32 lanes of a warp; the caller adds the policy
 // (bytes 93..264) and a __syncwarp() before reading s_rec.

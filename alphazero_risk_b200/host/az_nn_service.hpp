@@ -101,9 +101,16 @@ class NNService {
         const int n = (int)batch.size();
         x_.resize((size_t)n * AZ_INPUT_FLOATS); pol_.resize((size_t)n * AZ_MOVES); val_.resize(n);
         for (int i = 0; i < n; ++i) encode_input(&batch[i].in, x_.data() + (size_t)i * AZ_INPUT_FLOATS);
-        {
+        try {
             std::lock_guard<std::mutex> g(gpu_lock_);         // one Run per GPU at a time, alphazero_gpu_cluster.cpp:33
             check(az_nn_forward(nn_, x_.data(), n, pol_.data(), val_.data(), precision_, nullptr), "az_nn_forward");
+        } catch (...) {
+            // a failed batch (e.g. out of memory in az_nn_reserve) must reach every MCTS thread blocked in future.get() instead of
+            // unwinding out of the consumer thread (std::terminate, the waiters hang): the reference aborts with a message at the
+            // call site (TF_CHECK_OK, alphazero_nn.cpp:268); here predictFuture().get() rethrows az_last_error's text
+            for (int i = 0; i < n; ++i) batch[i].promise.set_exception(std::current_exception());
+            batch.clear();
+            return;
         }
         for (int i = 0; i < n; ++i) batch[i].promise.set_value(make_out(pol_.data() + (size_t)i * AZ_MOVES, val_[i]));
         batch.clear();

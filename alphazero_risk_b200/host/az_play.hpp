@@ -184,8 +184,10 @@ public:
             ck(az_env_turn_samples(env, nullptr, 0, &have, &d, nullptr), "az_env_turn_samples");
             const size_t at = out.size();
             out.resize(at + have * (size_t)AZ_SAMPLE_BYTES);
-            ck(az_env_turn_samples(env, have ? out.data() + at : nullptr, have, &have, &d, nullptr), "az_env_turn_samples");
-            out.resize(at + have * (size_t)AZ_SAMPLE_BYTES);
+            if (have) {                                   // an empty queue was drained (dropped count reset) by the query itself
+                ck(az_env_turn_samples(env, out.data() + at, have, &have, &d, nullptr), "az_env_turn_samples");
+                out.resize(at + have * (size_t)AZ_SAMPLE_BYTES);
+            }
             dropped += d;
             games_played += n;
         }

@@ -269,7 +269,10 @@ AZ_API int az_selfplay_run(az_mcts* mcts, int n_moves, void* stream);
 /* enable recording in az_selfplay_run / az_mcts_search(apply_move): device staging of max_moves_per_game samples per running game
    and an output queue of capacity_samples records of FINISHED games (samples that do not fit are counted as dropped) */
 AZ_API int az_selfplay_record(az_mcts* mcts, size_t capacity_samples, int max_moves_per_game);
-/* copies the queued records to h_records (NULL = only report the count in *n_out) and empties the queue */
+/* copies the queued records to h_records and empties the queue.  h_records = NULL while records are queued = size query
+   (*n_out, *h_dropped reported, nothing reset).  Any other call DRAINS: it reports *h_dropped = samples dropped since the last
+   draining call and resets that count — also when the queue is empty (h_records may then be NULL).  Every returned record was
+   written: a game that does not fit the queue is dropped whole and leaves no hole (the reservation never moves past the capacity) */
 AZ_API int az_selfplay_samples(az_mcts* mcts, uint8_t* h_records, size_t max_records, size_t* n_out, uint64_t* h_dropped, void* stream);
 /* NNTrainDataStorage::saveTrainingSamples file: size_t count, then the records (readable by the reference's trainer) */
 AZ_API int az_samples_write_file(const char* path, const uint8_t* h_records, size_t n);

@@ -158,8 +158,9 @@ def read_bundle(prefix):
     return out
 
 
-def write_bundle(prefix, tensors, block_size=262144, restart_interval=16):
-    """{name: array} -> the two files, entries and data in ascending name order"""
+def write_bundle(prefix, tensors, block_size=262144, restart_interval=16, hostile_entries=None):
+    """{name: array} -> the two files, entries and data in ascending name order.  hostile_entries = {name: (offset, size)} writes
+    those (out-of-range) values into the entry instead of the true ones: for the reader's bounds-check tests"""
     blob = bytearray()
     entries = [(b"", b"\x08\x01" + b"\x1a\x02\x08\x01")]          # num_shards = 1, version { producer = 1 }
     for name in sorted(tensors):
@@ -167,9 +168,10 @@ def write_bundle(prefix, tensors, block_size=262144, restart_interval=16):
         raw = a.tobytes()
         shape = b"".join(b"\x12" + _varint(len(d)) + d for d in (b"\x08" + _varint(s) for s in a.shape))
         e = b"\x08\x01" + b"\x12" + _varint(len(shape)) + shape
-        if len(blob):
-            e += b"\x20" + _varint(len(blob))
-        e += b"\x28" + _varint(len(raw)) + b"\x35" + struct.pack("<I", mask(crc32c(raw)))
+        off, size = (hostile_entries or {}).get(name, (len(blob), len(raw)))
+        if off:
+            e += b"\x20" + _varint(off)
+        e += b"\x28" + _varint(size) + b"\x35" + struct.pack("<I", mask(crc32c(raw)))
         entries.append((name.encode(), e))
         blob += raw
 

@@ -12,6 +12,8 @@ Fixtures (all numpy .npz, a few hundred KB in total):
   encode.npz      Data image -> the reference's [7,6,13] input tensor for sampled states
   mcts_trace.npz  self-play / play-mode games searched with the pseudo network: root state,
                   N/Q/P/pi (bit patterns), sumN, root value, chosen move, table size per move
+  mcts_trace_deep.npz  (`--deep`) the same for one full self-play game at 200 and one at 800
+                  simulations per move
 """
 import os
 import sys
@@ -96,9 +98,12 @@ def gen_env(n_games=6):
     print("env_trace: %d steps, encode: %d states" % (len(rec["action"]), len(enc_x)))
 
 
-def gen_mcts():
+def gen_mcts(deep=False):
+    """deep = the 200 / 800 simulation traces (SURVEY 8c iv), kept in their own file: minutes of reference time"""
     mask = po.data_byte_mask()
     cases = [("selfplay16", 16, 1, False, 0), ("selfplay64", 64, 1, False, 1), ("play32t2", 33, 2, True, 2)]
+    if deep:
+        cases = [("selfplay200", 200, 1, False, 3), ("selfplay800", 800, 1, False, 4)]
     out = {}
     for name, sims, T, play_mode, g in cases:
         rules = po.default_rules(mcts_simulations=sims, threads_per_mcts=T)
@@ -130,11 +135,14 @@ def gen_mcts():
         out[name + "_status"] = np.int64(r.status())
         print(name, "moves", ply, "status", r.status())
     out["seed"] = np.uint64(SEED)
-    np.savez_compressed(os.path.join(HERE, "mcts_trace.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "mcts_trace_deep.npz" if deep else "mcts_trace.npz"), **out)
 
 
 if __name__ == "__main__":
     if not po.ref_available():
         po.build_ref()
-    gen_env()
-    gen_mcts()
+    if "--deep" in sys.argv:
+        gen_mcts(deep=True)
+    else:
+        gen_env()
+        gen_mcts()

@@ -103,3 +103,26 @@ def test_corruption_is_detected(api, tmp_path):
         one = np.zeros(1, np.float32)
         shp = (C.POINTER(C.c_int64) * 2)(); dat = (C.c_void_p * 2)(one.ctypes.data, one.ctypes.data)
         api.check(L.az_ckpt_write(str(tmp_path / "d").encode(), 2, names, ranks, shp, dat))
+
+
+def test_hostile_offsets_do_not_wrap_the_bounds_checks(api, tmp_path):
+    """values read from the file are never added before they are checked: an entry offset / block handle near 2^64 (or a negative
+    varint offset) must be rejected, not wrapped past the test into an out-of-bounds read"""
+    import struct
+    from oracle import ckpt_oracle as co
+    t = {"w": np.arange(6, dtype=np.float32)}
+    for i, (off, size) in enumerate([(2 ** 64 - 10, 24), (2 ** 63 + 5, 24), (2 ** 64 - 24, 24), (1 << 40, 24)]):
+        prefix = str(tmp_path / ("h%d" % i))
+        co.write_bundle(prefix, t, hostile_entries={"w": (off, size)})
+        ck = api.Checkpoint(prefix)
+        with pytest.raises(api.AzError, match="outside"):
+            ck.read("w")
+        ck.close()
+    prefix = str(tmp_path / "f")
+    co.write_bundle(prefix, t)
+    idx = bytearray(open(prefix + ".index", "rb").read())
+    foot = co._varint(0) + co._varint(8) + co._varint(2 ** 64 - 10) + co._varint(20)       # index handle wraps off + size + 5
+    idx[-48:] = foot + b"\x00" * (40 - len(foot)) + bytes(idx[-8:])
+    open(prefix + ".index", "wb").write(bytes(idx))
+    with pytest.raises(api.AzError, match="outside|corrupt|bad|checksum"):
+        api.Checkpoint(prefix)

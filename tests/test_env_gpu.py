@@ -10,6 +10,12 @@ from oracle import pyoracle as po
 pytestmark = pytest.mark.gpu
 
 SEED = 0x5EED0001
+# the rule sets tests/test_oracle_vs_ref.py pins oracle-vs-reference, here CUDA-vs-oracle: LIMIT_ATTACK_MOVES,
+# LIMIT_REINFORCEMENT_MOVES off, ALLOW_YIELD off, MAX_GAME_ROUNDS, MIN_UNIT_MOVE (alphazero_moves.cpp:18,36,59,
+# state.cpp:518-565, settings.h:40-62)
+RULE_SETS = [dict(), dict(limit_attack=1), dict(limit_reinforcement=0), dict(allow_yield=0, max_game_rounds=40),
+             dict(min_unit_move=1), dict(limit_attack=1, limit_reinforcement=0, allow_yield=0, max_game_rounds=45, min_unit_move=5)]
+RULE_IDS = ["default", "limit_attack", "no_limit_reinf", "no_yield_40_rounds", "min_unit_move_1", "all_non_default"]
 
 
 @pytest.fixture(scope="module")
@@ -62,12 +68,14 @@ def test_encode_matches_reference_tensor(api, golden_dir):
     env.close()
 
 
-def test_lockstep_random_play_vs_oracle_philox(api):
-    """host-chosen legal actions, dice from the Philox contract on the device; states compared as we go"""
+@pytest.mark.parametrize("kw", RULE_SETS, ids=RULE_IDS)
+def test_lockstep_random_play_vs_oracle_philox(api, kw):
+    """host-chosen legal actions, dice from the Philox contract on the device; legal masks (az_valid_moves), status and
+    states compared as we go, under the default and every non-default rule set"""
     n, steps = 192, 420
-    env = api.Env(n, first_game_id=1000)
+    env = api.Env(n, rules=api.default_rules(**kw), first_game_id=1000)
     env.reset(SEED)
-    games = [po.OracleGame() for _ in range(n)]
+    games = [po.OracleGame(po.default_rules(**kw)) for _ in range(n)]
     for g, o in enumerate(games):
         o.new_game(SEED, 1000 + g, 0)
     ply = np.zeros(n, int)
@@ -127,16 +135,18 @@ def test_import_rejects_inconsistent_image(api, golden_dir):
     env.close()
 
 
-def test_rollout_matches_oracle_including_redeals(api):
+@pytest.mark.parametrize("kw", RULE_SETS, ids=RULE_IDS)
+def test_rollout_matches_oracle_including_redeals(api, kw):
+    """k_env_rollout (az_valid_moves_flat + az_move_flat, the headline kernel) against the oracle, all rule sets"""
     n, steps, first = 160, 700, 77
-    env = api.Env(n, first_game_id=first)
+    env = api.Env(n, rules=api.default_rules(**kw), first_game_id=first)
     env.reset(SEED)
     env.rollout(steps // 2)
     env.rollout(steps - steps // 2)          # two launches == one: state and ply persist in HBM
     dev = env.export_aos()
     cnt = env.counters()
     games = wins0 = wins1 = draws = 0
-    o = po.OracleGame()
+    o = po.OracleGame(po.default_rules(**kw))
     for g in range(n):
         o.new_game(SEED, first + g, 0)
         ply = 0
@@ -168,6 +178,16 @@ def test_full_size_rollout_properties(api):
     assert 2.3 * n < cnt["games"] < 3.9 * n
     assert abs(cnt["wins"][0] - cnt["wins"][1]) < 0.05 * cnt["games"]
     img = env.export_aos()
+    # 64 sampled global game ids replayed on the oracle (re-deals included): bit-exact at full size
+    o = po.OracleGame()
+    for g in np.random.default_rng(7).choice(n, 64, replace=False):
+        g = int(g)
+        o.new_game(SEED, g, 0)
+        for ply in range(steps):
+            if o.status() != -1:
+                o.new_game(SEED, g, ply)
+            assert o.move(o.random_action(SEED, g, ply), SEED, g, ply) == 0
+        assert (img[g] == o.data()).all(), g
     # every exported image is self-consistent: re-import runs the reference's consistencyCheck invariant
     env2 = api.Env(n)
     env2.import_aos(img)

@@ -25,9 +25,10 @@ def bits(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
 
-def run_lockstep(api, n, first, sims, T, play_mode, max_moves, evaluator="pseudo", net=None, oracle_eval=None, K=1):
-    rules_o = po.default_rules(mcts_simulations=sims, threads_per_mcts=T)
-    rules_d = api.default_rules(mcts_simulations=sims, threads_per_mcts=T, concurrent_descents=K)
+def run_lockstep(api, n, first, sims, T, play_mode, max_moves, evaluator="pseudo", net=None, oracle_eval=None, K=1, rules_kw=None):
+    rules_kw = rules_kw or {}
+    rules_o = po.default_rules(mcts_simulations=sims, threads_per_mcts=T, **rules_kw)
+    rules_d = api.default_rules(mcts_simulations=sims, threads_per_mcts=T, concurrent_descents=K, **rules_kw)
     env = api.Env(n, rules=rules_d, first_game_id=first)
     env.reset(SEED)
     ev = {"pseudo": api.EVAL_PSEUDO, "uniform": api.EVAL_UNIFORM, "nn": api.EVAL_NN}[evaluator]
@@ -111,6 +112,21 @@ def test_virtual_loss_concurrent_descents(api, sims, T, K, play_mode, evaluator)
     assert run_lockstep(api, n=8, first=4100, sims=sims, T=T, play_mode=play_mode, max_moves=140, evaluator=evaluator, K=K) > 700
 
 
+# the sets tests/test_oracle_vs_ref.py::test_mcts_lockstep pins oracle-vs-reference (CPUCT, DIR_NOISE_VALUE, DIR_NOISE_EPSI,
+# TEMPERATURE_THRESHOLD of settings.h:40-62 -> alphazero_mcts.cpp:67-119, alphazero_trainer.cpp:98-106; game rules inside the
+# search -> alphazero_moves.cpp:18,36,59), here CUDA-vs-oracle
+MCTS_RULE_SETS = [dict(cpuct=2.5, dir_noise_value=0.05, dir_noise_epsi=0.5, temperature_threshold=6),
+                  dict(cpuct=0.4, dir_noise_epsi=0.0, temperature_threshold=0, limit_attack=1, limit_reinforcement=0),
+                  dict(dir_noise_value=1.0, dir_noise_epsi=1.0, allow_yield=0, max_game_rounds=40, min_unit_move=1)]
+
+
+@pytest.mark.parametrize("sims,K,play_mode,kw", [(24, 1, False, 0), (20, 1, False, 1), (16, 1, True, 2), (32, 1, False, 2),
+                                                 (32, 4, False, 0), (16, 2, True, 1)])
+def test_non_default_hyper_parameters_and_rules(api, sims, K, play_mode, kw):
+    assert run_lockstep(api, n=6, first=2600 + 10 * kw, sims=sims, T=1, play_mode=play_mode, max_moves=130, K=K,
+                        rules_kw=MCTS_RULE_SETS[kw]) > 500
+
+
 def test_concurrent_descents_must_divide_the_simulation_count(api):
     env = api.Env(2, rules=api.default_rules(mcts_simulations=16, threads_per_mcts=1, concurrent_descents=3))
     with pytest.raises(api.AzError):
@@ -122,10 +138,11 @@ def test_uniform_evaluator(api):
     assert run_lockstep(api, n=4, first=31, sims=24, T=1, play_mode=False, max_moves=60, evaluator="uniform") > 200
 
 
-@pytest.mark.parametrize("name", ["selfplay16", "selfplay64", "play32t2"])
+@pytest.mark.parametrize("name", ["selfplay16", "selfplay64", "play32t2", "selfplay200", "selfplay800"])
 def test_reference_golden_search_traces(api, golden_dir, name):
-    """the compiled reference's own search traces (tests/golden/mcts_trace.npz), one game each"""
-    t = np.load(os.path.join(golden_dir, "mcts_trace.npz"))
+    """the compiled reference's own search traces (tests/golden/mcts_trace*.npz), one full game each; 200 and 800 simulations
+    per move are the depths of BASELINE configs[3] / [4] (pool migration, long paths)"""
+    t = np.load(os.path.join(golden_dir, "mcts_trace_deep.npz" if name in ("selfplay200", "selfplay800") else "mcts_trace.npz"))
     sims, T, play_mode, g = [int(v) for v in t[name + "_cfg"]]
     seed = int(t["seed"])
     env = api.Env(1, rules=api.default_rules(mcts_simulations=sims, threads_per_mcts=T), first_game_id=g)
@@ -230,6 +247,33 @@ def test_full_size_search_properties_and_shard_invariance(api):
         assert (tot >= sims - 1).all()                       # the root's own expansion is not a visit of a child
         assert np.allclose(pi, N / tot[:, None], atol=1e-6)
         assert legal[np.arange(n), move].all()
+    # 64 sampled global game ids replayed on the oracle search; its evaluator calls the SAME bf16 tcgen05 forward on a batch of
+    # one (the tower is batch-invariant), so both sides see identical network outputs: N, pi and moves bit for bit at full size
+    L = po.oracle_lib()
+
+    @C.CFUNCTYPE(None, C.POINTER(po.RoState), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p)
+    def evaluator(sp, policy, value, user):
+        x = np.zeros(po.INPUT_FLOATS, np.float32)
+        L.ro_encode(sp, x)
+        p, v = net.forward(x.reshape(1, -1), api.BF16)
+        C.memmove(policy, p.ctypes.data, 43 * 4)
+        value[0] = float(v[0])
+
+    rules_o = po.default_rules(mcts_simulations=sims, threads_per_mcts=1)
+    for g in np.random.default_rng(11).choice(n, 64, replace=False):
+        g = int(g)
+        o, t = po.OracleGame(rules_o), po.OracleMcts(rules_o, "pseudo")
+        t.L.ro_mcts_free(t.h)
+        t.h = t.L.ro_mcts_new(C.cast(evaluator, C.c_void_p), None)
+        o.new_game(SEED, g, 0)
+        for ply, (valid, N, pi, move) in enumerate(full):
+            assert int(valid[g]) == o.valid()
+            a = t.search(o, SEED, g, ply)
+            assert (N[g] == a["N"]).all(), (g, ply, N[g], a["N"])
+            assert (bits(pi[g]) == bits(a["pi"])).all(), (g, ply)
+            mv = t.pick(a["pi"], o.s.round <= rules_o.temperature_threshold, SEED, g, ply)
+            assert move[g] == mv and o.move(mv, SEED, g, ply) == 0
+        assert (final[g] == o.data()).all(), g
     again, cnt2, final2, _ = run(n, 0)
     assert cnt2 == cnt and (final2 == final).all()
     for (v1, n1, p1, m1), (v2, n2, p2, m2) in zip(full, again):

@@ -114,9 +114,9 @@ def test_normalize_policy():
             assert q[i] == exp
 
 
-@pytest.mark.parametrize("name", ["selfplay16", "selfplay64", "play32t2"])
+@pytest.mark.parametrize("name", ["selfplay16", "selfplay64", "play32t2", "selfplay200", "selfplay800"])
 def test_mcts_trace_bit_exact(golden_dir, name):
-    t = np.load(os.path.join(golden_dir, "mcts_trace.npz"))
+    t = np.load(os.path.join(golden_dir, "mcts_trace_deep.npz" if name in ("selfplay200", "selfplay800") else "mcts_trace.npz"))
     sims, T, play_mode, g = [int(v) for v in t[name + "_cfg"]]
     seed = int(t["seed"])
     rules = po.default_rules(mcts_simulations=sims, threads_per_mcts=T)

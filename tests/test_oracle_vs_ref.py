@@ -32,7 +32,12 @@ def test_map_tables_match_reference():
     assert list((C.c_int * 6).in_dll(L, "RO_CONTINENT_BONUS")) == list(cb)
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(allow_yield=0), dict(limit_reinforcement=0), dict(limit_attack=1)])
+RULE_SETS = [dict(), dict(allow_yield=0), dict(limit_reinforcement=0), dict(limit_attack=1),
+             dict(allow_yield=0, max_game_rounds=40), dict(min_unit_move=1),
+             dict(limit_attack=1, limit_reinforcement=0, allow_yield=0, max_game_rounds=45, min_unit_move=5)]
+
+
+@pytest.mark.parametrize("kw", RULE_SETS)
 def test_random_games_lockstep(kw):
     seed = 0xC0FFEE
     rules = po.default_rules(**kw)
@@ -61,10 +66,18 @@ def test_random_games_lockstep(kw):
     assert steps > 5000
 
 
-@pytest.mark.parametrize("sims,T,play_mode", [(16, 1, False), (48, 1, False), (33, 2, True)])
-def test_mcts_lockstep(sims, T, play_mode):
+# non-default search hyper-parameters (settings.h:40-62: CPUCT, DIR_NOISE_VALUE, DIR_NOISE_EPSI, TEMPERATURE_THRESHOLD) and
+# game rules inside the search; tests/test_mcts_gpu.py runs the SAME sets CUDA-vs-oracle
+MCTS_RULE_SETS = [dict(), dict(cpuct=2.5, dir_noise_value=0.05, dir_noise_epsi=0.5, temperature_threshold=6),
+                  dict(cpuct=0.4, dir_noise_epsi=0.0, temperature_threshold=0, limit_attack=1, limit_reinforcement=0),
+                  dict(dir_noise_value=1.0, dir_noise_epsi=1.0, allow_yield=0, max_game_rounds=40, min_unit_move=1)]
+
+
+@pytest.mark.parametrize("sims,T,play_mode,kw", [(16, 1, False, 0), (48, 1, False, 0), (33, 2, True, 0),
+                                                 (24, 1, False, 1), (20, 1, False, 2), (16, 1, True, 3), (32, 1, False, 3)])
+def test_mcts_lockstep(sims, T, play_mode, kw):
     seed = 0xFACADE
-    rules = po.default_rules(mcts_simulations=sims, threads_per_mcts=T)
+    rules = po.default_rules(mcts_simulations=sims, threads_per_mcts=T, **MCTS_RULE_SETS[kw])
     po.ref_apply_rules(rules)
     mask = po.data_byte_mask()
     o, r, om, rm = po.OracleGame(rules), po.RefGame(), po.OracleMcts(rules), po.RefMcts()

@@ -166,3 +166,66 @@ def test_scripted_turn_samples_match_reference(pairing, rule_kw, tmp_path):
         L.ref_random_free(rr); L.ref_storage_free(st)
     po.ref_apply_rules(po.default_rules())                  # the reference's SETTINGS are process-wide
     assert total > 1500 and (skips > 0 or pairing == "script_vs_script")     # the script's fortify rarely has nothing to move
+
+
+def _well_formed(recs):
+    """every record is a written one: player 0/1, the mirrored playerIndex inside NNInputData, 42 land bytes with army 1..32 and
+    owner 0..2, value target in {-1, 0, +1}, a policy that sums to one"""
+    assert recs.shape[1] == 265
+    assert (recs[:, 0] <= 1).all() and (recs[:, 1 + 42] == recs[:, 0]).all()
+    land = recs[:, 1:43]
+    assert ((land & 63) >= 1).all() and ((land & 63) <= 32).all() and ((land >> 6) <= 2).all()
+    value = recs[:, 89:93].copy().view(np.float32).reshape(-1)
+    assert np.isin(value, [-1.0, 0.0, 1.0]).all()
+    pol = recs[:, 93:265].copy().view(np.float32).reshape(-1, 43)
+    assert (pol >= 0).all() and np.abs(pol.sum(1) - 1).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_output_queue_overflow_returns_only_written_records():
+    """a sample queue smaller than what finishes: games that do not fit are dropped WHOLE and counted, the reservation never moves
+    past the capacity, so every record a drain returns was written (no hole of stale bytes), and returned + dropped = everything
+    the finished games produced.  Both recorders: the self-play one (az_selfplay_samples) and the scripted / random turn one
+    (az_env_turn_samples)."""
+    from alphazero_risk_b200 import api
+    if api.lib().az_device_count() == 0:
+        pytest.fail("no CUDA device visible: the gpu suite must run on a B200")
+    n, moves, sims = 48, 700, 2
+    rules = api.default_rules(mcts_simulations=sims, threads_per_mcts=1)
+
+    def run(capacity):
+        env = api.Env(n, rules=rules, first_game_id=40)
+        env.reset(SEED)
+        mc = api.Mcts(env, evaluator=api.EVAL_PSEUDO)
+        mc.record(capacity_samples=capacity, max_moves_per_game=1024)
+        mc.selfplay(moves)
+        recs, dropped = mc.samples()
+        again, dropped2 = mc.samples()
+        assert len(again) == 0 and dropped2 == 0          # an empty drain reports nothing twice
+        mc.close(); env.close()
+        return recs.copy(), dropped
+
+    full, d0 = run(n * moves)
+    assert d0 == 0 and len(full) > 3000
+    cap = 1000
+    part, d1 = run(cap)
+    assert 0 < len(part) <= cap and d1 > 0
+    assert len(part) + d1 == len(full)
+    _well_formed(part)
+    # each returned game is one of the games of the unconstrained run, byte for byte
+    fb = full.tobytes()
+    assert all(fb.find(part[i].tobytes()) >= 0 for i in range(0, len(part), 37))
+    # scripted / random turn recorder
+    env = api.Env(64, first_game_id=9)
+    env.record_turns(capacity_samples=1500, max_samples_per_game=4096)
+    env.reset(SEED)
+    script = np.full((64, 2), api.SCRIPT_INIT, np.uint32)
+    for _ in range(400):
+        if (env.play_turn(api.OPPONENT_SCRIPT, api.OPPONENT_RANDOM, script) != -1).all():
+            break
+    recs, dropped = env.turn_samples()
+    assert 0 < len(recs) <= 1500 and dropped > 0
+    _well_formed(recs)
+    recs2, dropped2 = env.turn_samples()
+    assert len(recs2) == 0 and dropped2 == 0
+    env.close()
