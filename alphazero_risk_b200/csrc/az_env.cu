@@ -225,55 +225,10 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_query(const uint32_t* __restr
     if (status) status[gi] = (int8_t)az_game_status(c.g, rules);
 }
 
-// BASELINE config 2, first version (kept as the A/B reference, AZ_ENV_ROLLOUT=v1): every lane runs az_valid_moves /
-// az_make_move as written for the single-step kernel; the six phase paths, the fortify component search and the re-deal
-// serialise inside a warp (ncu round 1: 4.5 of 32 lanes active, 3200 warp instructions per move).
-__global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout_v1(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
-                                                            int n_steps, uint64_t seed, uint32_t first_game, AzRulesDev rules,
-                                                            unsigned long long* __restrict__ counters)
-{
-    __shared__ EnvSmem sm;
-    AzTables T = env_stage_tables(sm, g_tab);
-    int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
-    unsigned steps = 0, games = 0, w0 = 0, w1 = 0, dr = 0;
-    if (gi < n) {
-        EnvCtx c; env_load(c, sm, st, n, gi);
-        const uint32_t game = first_game + (uint32_t)gi;
-        for (int s = 0; s < n_steps; ++s) {
-            int stt = az_game_status(c.g, rules);
-            if (stt != AZ_STATUS_RUNNING) {
-                games++; w0 += stt == 0; w1 += stt == 1; dr += stt == AZ_STATUS_DRAW;
-                az_new_game(c.g, c.land, seed, game, c.ply);
-            }
-            uint64_t valid = az_valid_moves(c.g, T, rules);
-            az_u32x4 blk = az_rng_block(seed, game, c.ply, AZ_STREAM_REAL, 0);
-            int action = az_nth_set_bit(valid, az_mulhi32(blk.y, (uint32_t)__popcll(valid)));
-            AzDicePhilox d; d.init_with_block0(seed, game, c.ply, AZ_STREAM_REAL, blk);
-            az_make_move(c.g, c.land, c.scratch, T, rules, valid, action, d);
-            c.ply++; steps++;
-        }
-        env_store(c, sm, st, n, gi);
-    }
-    // warp-reduce, one atomic per warp and counter
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        steps += __shfl_xor_sync(0xffffffffu, steps, o); games += __shfl_xor_sync(0xffffffffu, games, o);
-        w0 += __shfl_xor_sync(0xffffffffu, w0, o); w1 += __shfl_xor_sync(0xffffffffu, w1, o); dr += __shfl_xor_sync(0xffffffffu, dr, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&counters[0], (unsigned long long)steps);
-        if (games) atomicAdd(&counters[1], (unsigned long long)games);
-        if (w0) atomicAdd(&counters[2], (unsigned long long)w0);
-        if (w1) atomicAdd(&counters[3], (unsigned long long)w1);
-        if (dr) atomicAdd(&counters[4], (unsigned long long)dr);
-    }
-}
-
-
 // BASELINE config 2: n_steps uniform-random legal moves per game inside one launch; the state stays in registers /
-// shared memory between moves, finished games are re-dealt in place.  Same results as k_env_rollout_v1, restructured
-// around what ncu showed (profiles/README.md): ~60 % of the v1 instructions were the fortify component search and the
-// re-deal executing with 1-2 active lanes.  Here
+// shared memory between moves, finished games are re-dealt in place.  Structured around what ncu showed of the first version
+// (every lane running az_valid_moves / az_make_move as written for the single-step kernel; profiles/README.md): ~60 % of its
+// instructions were the fortify component search and the re-deal executing with 1-2 active lanes.  Here
 //   * the common work of a move (status, legal mask with ONE neighbour union, Philox block, action pick, land writes,
 //     attack-army check) is one instruction stream for all lanes (az_valid_moves_flat / az_move_flat);
 //   * a lane whose move needs the component search, or whose game ended, PARKS; parked lanes are served together once
@@ -965,23 +920,16 @@ extern "C" int az_env_rollout(az_env* e, int n_steps, void* stream)
     AzDeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     AZ_CUDA(cudaEventRecord(e->ev0, s));
-    // AZ_ENV_ROLLOUT=v1 selects the first version of the kernel (A/B reference); AZ_ENV_PARK_F / AZ_ENV_PARK_R tune how many
-    // parked lanes a warp collects before it runs the component search / the re-deal for them
-    static const bool v1 = getenv("AZ_ENV_ROLLOUT") != nullptr && strcmp(getenv("AZ_ENV_ROLLOUT"), "v1") == 0;
-    static const int park_f = getenv("AZ_ENV_PARK_F") ? atoi(getenv("AZ_ENV_PARK_F")) : 8;
-    static const int park_r = getenv("AZ_ENV_PARK_R") ? atoi(getenv("AZ_ENV_PARK_R")) : 3;      // swept 1..8 x park_f 4..12 on B200: 8 / 3 = 15.1 G steps/s
-    if (v1)
-        k_env_rollout_v1<<<env_grid(e->n), ENV_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
-                                                               dev_rules(e->rules), e->d_counters);
-    else {
-        static bool smem_set[64] = { false };                      // 64 KB of wide tables + columns: above the 48 KB default
-        if (!smem_set[e->device & 63]) {
-            AZ_CUDA(cudaFuncSetAttribute(k_env_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmemWide)));
-            smem_set[e->device & 63] = true;
-        }
-        k_env_rollout<<<env_grid(e->n), ENV_BLOCK, sizeof(EnvSmemWide), s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
-                                                            dev_rules(e->rules), e->d_counters, park_f, park_r);
+    // how many parked lanes a warp collects before it runs the component search / the re-deal for them: swept on B200
+    // (park_f 4..12 x park_r 1..8, profiles/README.md) -> 8 / 3
+    constexpr int park_f = 8, park_r = 3;
+    static bool smem_set[64] = { false };                      // 64 KB of wide tables + columns: above the 48 KB default
+    if (!smem_set[e->device & 63]) {
+        AZ_CUDA(cudaFuncSetAttribute(k_env_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmemWide)));
+        smem_set[e->device & 63] = true;
     }
+    k_env_rollout<<<env_grid(e->n), ENV_BLOCK, sizeof(EnvSmemWide), s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
+                                                                        dev_rules(e->rules), e->d_counters, park_f, park_r);
     AZ_CUDA(cudaGetLastError());
     AZ_CUDA(cudaEventRecord(e->ev1, s));
     e->timed = true;

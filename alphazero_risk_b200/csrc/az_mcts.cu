@@ -902,7 +902,6 @@ struct az_arena {
     az_mcts* mc = nullptr;
     az_mcts* opp = nullptr;          // AZ_OPPONENT_ALPHAZERO: the searcher of player index 1
     int32_t* d_list[2] = { nullptr, nullptr };   // games waiting for searcher 0 / 1 this tick (leaf-batch compaction)
-    bool compact = true;             // AZ_ARENA_COMPACT=0: evaluate every slot (A/B and parity switch)
     ArenaDev a;
     std::vector<void*> allocs;
 };
@@ -934,7 +933,6 @@ extern "C" int az_arena_create(az_mcts* mc, int opponent, int mirror_games, az_a
     rc |= aalloc(ar, &a.res, (size_t)ARENA_N);
     rc |= aalloc(ar, &ar->d_list[0], n);
     if (rc) { for (void* p : ar->allocs) cudaFree(p); delete ar; return AZ_ERR_CUDA; }
-    { const char* ec = getenv("AZ_ARENA_COMPACT"); ar->compact = !(ec && ec[0] == '0'); }
     a.state = mc->d.root_state; a.extra_trim = mc->d.extra_trim;
     *out = ar;
     return AZ_OK;
@@ -963,7 +961,6 @@ extern "C" int az_arena_create_versus(az_mcts* mc, az_mcts* opp, int mirror_game
     rc |= aalloc(ar, &a.res, (size_t)ARENA_N);
     rc |= aalloc(ar, &ar->d_list[0], n); rc |= aalloc(ar, &ar->d_list[1], n);
     if (rc) { for (void* p : ar->allocs) cudaFree(p); delete ar; return AZ_ERR_CUDA; }
-    { const char* ec = getenv("AZ_ARENA_COMPACT"); ar->compact = !(ec && ec[0] == '0'); }
     a.state = mc->d.root_state; a.extra_trim = mc->d.extra_trim; a.extra_trim_opp = opp->d.extra_trim;
     *out = ar;
     return AZ_OK;
@@ -1021,7 +1018,7 @@ extern "C" int az_arena_play(az_arena* ar, uint64_t n_games, uint64_t seed, az_a
         AZ_CUDA(cudaStreamSynchronize(s));
         if (act[0] == 0) break;
         // leaf batches hold only the slots that search this tick (their number is known on the host: act[])
-        const bool compact = ar->compact && mc->evaluator == EVAL_NN;
+        const bool compact = mc->evaluator == EVAL_NN;
         if (!opp) {
             if (compact && act[0] < (unsigned long long)a.n) {
                 k_arena_list<<<1, 1024, 0, s>>>(a.active, a.n, 1, ar->d_list[0]);
@@ -1038,7 +1035,7 @@ extern "C" int az_arena_play(az_arena* ar, uint64_t n_games, uint64_t seed, az_a
             for (int side = 0; side < 2 && !rc; ++side) {
                 if (!act[1 + side]) continue;
                 az_mcts* m2 = side_mc[side];
-                if (ar->compact && m2->evaluator == EVAL_NN && act[1 + side] < (unsigned long long)a.n) {
+                if (m2->evaluator == EVAL_NN && act[1 + side] < (unsigned long long)a.n) {
                     k_arena_list<<<1, 1024, 0, s>>>(a.to_move, a.n, side, ar->d_list[side]);
                     m2->eval_games = ar->d_list[side]; m2->eval_count = (int)act[1 + side];
                 }

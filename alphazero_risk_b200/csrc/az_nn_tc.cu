@@ -13,15 +13,15 @@
 //     board and the top border of the next one; the left / right border comes from two masked copies of the operand built in
 //     shared memory (kx = 0 taps read the copy with the x = 5 cells zeroed, kx = 2 taps the copy with the x = 0 cells zeroed).
 //     42 of 49 rows carry data.
-//   * 56-row board layout (one-CTA kernel, AZ_TC_LAYOUT=56 / AZ_TC_MODE=single): cell (y, x) -> row y*7 + x with a zero column
-//     x = 6 and a zero row-group y = 7, one operand copy, no masking; 42 of 56 rows carry data.
 //   * weights are pre-packed per layer into contiguous pipeline stages of K = 32 input channels of one tap:
-//     [chunk][256 out][8] = 16 KB for the one-CTA kernel, [half of the output channels][chunk][128 out][8] = 8 KB per CTA of a
-//     pair, each fetched with one cp.async.bulk.
+//     [half of the output channels][chunk][128 out][8] = 8 KB per CTA of a pair (tower), [chunk][256 out][8] (stem), each fetched
+//     with one cp.async.bulk.
+//   (The first tower kernel — one CTA per tile on a 56-row layout with a zero column instead of masked copies — and the
+//   layer-to-layer pipelining experiment are history: numbers in profiles/README.md, code in the round-1 tree.)
 //
-// Kernels: k_nn_conv_tc3 — the tower on CTA PAIRS (tcgen05 cta_group::2), 49-row layout, operand ring over K groups;
+// Kernels: k_nn_conv_tc3 — the tower on CTA PAIRS (tcgen05 cta_group::2), operand ring over K groups;
 // k_nn_conv_tc — one CTA per tile: the stem (13 -> 256 channels, 2 input chunks, BatchNorm indexed by board row; its three operand
-// copies come from global memory) and the 56-row tower (A/B reference).  Both are persistent, one CTA per SM: warp 0 streams
+// copies come from global memory).  Both are persistent, one CTA per SM: warp 0 streams
 // operands, warp 1 issues tcgen05.mma (one elected lane) into one of two 256-column TMEM accumulators and owns the TMEM
 // allocation, warps 2-5 run the epilogue of the PREVIOUS tile concurrently: tcgen05.ld -> folded BatchNorm -> (+ residual) ->
 // ReLU -> zero the padding rows -> bf16 -> 16-byte coalesced stores.
@@ -61,41 +61,32 @@ struct AzTcState {
     __nv_bfloat16* d_act[3] = { nullptr, nullptr, nullptr };   // [32][r_alloc][8]
     __nv_bfloat16* d_in = nullptr;                             // [2][r_alloc][8]: encoded input, 13 channels padded to 16
     uint8_t* d_wpacked = nullptr;                              // [2*blocks] x 1.18 MB tower weights, then the 72 KB stem weights
-    int pair_mode = 1, max_pairs = 74;                         // tower on CTA pairs (k_nn_conv_tc3) unless AZ_TC_MODE=single (one-CTA kernel, 56-row layout)
-    int rpb = 49;                                              // rows per board: 49 (masked-copy layout, k_nn_conv_tc3) or 56 (AZ_TC_LAYOUT=56)
+    int max_pairs = 74;                                        // CTA pairs of k_nn_conv_tc3 the device holds at once
     uint8_t* d_wpacked3 = nullptr;                             // tower weights for k_nn_conv_tc3: [K group][tap][half]
     size_t in_var_stride = 0;                                  // elements between the three copies of the encoded input (49-row layout)
     float* d_scale = nullptr; float* d_shift = nullptr;        // [2*blocks][256] folded BN, then [256] (7 used) for the stem's row BN
-    float* d_x = nullptr;                                      // fp32 encode of the leaf states
-    unsigned* d_tile_done = nullptr;                           // [tile pairs] layer-to-layer pipelining counters (k_nn_conv_tc3)
 };
 
 #include "az_tc_ptx.cuh"
 
-// Two board layouts (rows per board = rpb):
-//   56: cell (y, x) -> row y*7 + x, zero column x = 6 and zero row-group y = 7 (taps are plain shifts of ONE operand)
-//   49: cell (y, x) -> row y*6 + x, seven zero rows behind the 42 cells.  The zero rows still serve as top / bottom border; the
-//       left / right border comes from two masked copies of the operand: taps with kx = 0 read the copy whose x = 5 cells are
-//       zero, taps with kx = 2 the copy whose x = 0 cells are zero (what they would wrongly pick up from the neighbouring board
-//       row is exactly such a cell).  12.5 % fewer rows = 12.5 % fewer MMAs for a forward that runs at the board's power cap.
-__device__ __forceinline__ int tc_cell_row(int p, int rpb) { return rpb == 56 ? (p / 6) * 7 + (p % 6) : p; }
-__device__ __forceinline__ bool tc_row_valid(int r, int n_boards, int rpb)
-{
-    int b = r / rpb, p = r - b * rpb;
-    return b < n_boards && (rpb == 56 ? (p < 49 && (p % 7) != 6) : p < 42);
-}
-__device__ __forceinline__ int tc_row_y(int r, int rpb) { int p = r % rpb; return rpb == 56 ? p / 7 : p / 6; }
-__device__ __forceinline__ int tc_tap_shift(int tap, int rpb) { return (tap / 3 - 1) * (rpb == 56 ? 7 : 6) + (tap % 3 - 1); }
-__device__ __forceinline__ int tc_tap_variant(int tap, int rpb) { return rpb == 56 ? 0 : (tap % 3 == 0 ? 1 : (tap % 3 == 2 ? 2 : 0)); }
+// Board layout: cell (y, x) -> row y*6 + x, seven zero rows behind the 42 cells (49 rows per board).  The zero rows serve as top /
+// bottom border; the left / right border comes from two masked copies of the operand: taps with kx = 0 read the copy whose x = 5
+// cells are zero, taps with kx = 2 the copy whose x = 0 cells are zero (what they would wrongly pick up from the neighbouring
+// board row is exactly such a cell).
+#define TC_RPB 49
+__device__ __forceinline__ bool tc_row_valid(int r, int n_boards) { int b = r / TC_RPB, p = r - b * TC_RPB; return b < n_boards && p < 42; }
+__device__ __forceinline__ int tc_row_y(int r) { return (r % TC_RPB) / 6; }
+__device__ __forceinline__ int tc_tap_shift(int tap) { return (tap / 3 - 1) * 6 + (tap % 3 - 1); }
+__device__ __forceinline__ int tc_tap_variant(int tap) { return tap % 3 == 0 ? 1 : (tap % 3 == 2 ? 2 : 0); }
 
 // ---------------------------------------------------------------- conv3x3 on tensor cores (tower and stem)
-// NV = operand copies per A buffer: 1 (56-row layout) or 3 (49-row layout: plain, x=5 zeroed, x=0 zeroed — read from three global
-// arrays var_stride_bytes apart; only used for the 2-chunk stem, the tower builds its copies in shared memory, k_nn_conv_tc3)
+// (the stem: KCH = 2).  NV = 3 operand copies per A buffer (plain, x=5 zeroed, x=0 zeroed) read from three global arrays
+// var_stride_bytes apart, written by the pack kernels; the tower builds its copies in shared memory, k_nn_conv_tc3
 template <int KCH, bool ROW_BN, int NV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ wpacked, const float* __restrict__ scale,
              const float* __restrict__ shift, const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
-             int n_boards, int r_alloc, int n_tiles, int rpb, size_t var_stride_bytes)
+             int n_boards, int r_alloc, int n_tiles, size_t var_stride_bytes)
 {
     using S = TcShape<KCH>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -171,7 +162,7 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
                     mbar_wait(bar_w_full + s, k & 1u);
                     tc_fence_after();
                     const int tap = it / S::KBLOCKS, kb = it - tap * S::KBLOCKS;
-                    const int sh = tc_tap_shift(tap, rpb), var = NV > 1 ? tc_tap_variant(tap, rpb) : 0;
+                    const int sh = tc_tap_shift(tap), var = NV > 1 ? tc_tap_variant(tap) : 0;
 #pragma unroll
                     for (int kk = 0; kk < S::KSTEPS; ++kk) {
                         const uint64_t bdesc = umma_desc(b_base + (uint32_t)(s * S::STAGE_BYTES + kk * 2 * 256 * 16), 256 * 16, 128);
@@ -195,8 +186,8 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
             tc_fence_after();
             {
             const int r = tile * TC_TILE_ROWS + q * 32 + lane;                 // padded row of this thread
-            const bool valid = tc_row_valid(r, n_boards, rpb);
-            const int yrow = tc_row_y(r, rpb);                                 // board row (stem BatchNorm index)
+            const bool valid = tc_row_valid(r, n_boards);
+            const int yrow = tc_row_y(r);                                      // board row (stem BatchNorm index)
             // (ncu, round 1: with a load-then-use residual read and one TMEM load + wait per 8 columns the branch2b layers ran 285 us
             // against 220 us for the branch2a layers — the epilogue, not the MMA, set the tile time)
             const size_t cell0 = ((size_t)TC_HALO + r) * 8;
@@ -289,14 +280,8 @@ template <bool RAW>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ wpacked3, const float* __restrict__ scale,
               const float* __restrict__ shift, const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
-              int n_boards, int r_alloc, int n_tiles, float* __restrict__ out32, unsigned* __restrict__ tile_done, unsigned poll_target)
+              int n_boards, int r_alloc, int n_tiles, float* __restrict__ out32)
 {
-    // Layer-to-layer pipelining (inference tower): tile_done[item] counts the epilogue warps (8 per tile pair) that have stored
-    // their rows of `item`, summed over the layers of this forward (zeroed per forward).  A layer with poll_target = 8 x (its index)
-    // does not wait for the whole previous layer (no griddepcontrol.wait): its streamer waits, per item, for the three items of the
-    // previous layer its operand rows come from (the item and the 8-row halos of its neighbours).  The same condition covers the
-    // write-after-read hazards of the three rotating activation buffers (whoever still reads rows near item i is one of those three
-    // items of the previous layer), and at most two consecutive layers are ever resident (a CTA pair needs a whole SM pair).
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;                                   // T3_G x T3_SLOT_BYTES
     uint8_t* sB = smem + T3_G * T3_SLOT_BYTES;            // TC2_STAGES x TC2_STAGE_BYTES
@@ -346,7 +331,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
-    if (poll_target == 0u) pdl_wait();                    // the previous kernel's activations are complete and visible from here on
+    pdl_wait();                                           // the previous kernel's activations are complete and visible from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -356,16 +341,6 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
             const uint8_t* src = reinterpret_cast<const uint8_t*>(in);
             auto load_group = [&](int q) {
                 const int slot = q % T3_G, rnd = q / T3_G, kb = q & 7, tile = tile_of_group(q);
-                if (poll_target != 0u && kb == 0) {       // first K group of an item: the previous layer's rows must be there
-                    const int item = pid + (q >> 3) * n_pairs;
-                    for (int jj = item - 1; jj <= item + 1; ++jj) {
-                        if (jj < 0 || jj >= n_items) continue;
-                        unsigned v;
-                        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(tile_done + jj) : "memory"); }
-                        while ((int)(v - poll_target) < 0);
-                    }
-                    asm volatile("fence.proxy.async;" ::: "memory");      // those generic-proxy stores -> this thread's bulk copies
-                }
                 if (rnd > 0) mbar_wait_cluster(bar_a_empty + slot, (uint32_t)((rnd - 1) & 1));
                 mbar_expect_tx(bar_a_full + slot, T3_VAR_BYTES);
                 for (int c = 0; c < 4; ++c)
@@ -423,7 +398,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
                         mbar_wait(bar_w_full + s, k & 1u);
                         mbar_wait_cluster(bar_pw_full + s, k & 1u);
                         tc_fence_after();
-                        const int sh = tc_tap_shift(tap, 49), var = tc_tap_variant(tap, 49);
+                        const int sh = tc_tap_shift(tap), var = tc_tap_variant(tap);
 #pragma unroll
                         for (int kk = 0; kk < 2; ++kk) {
                             const uint64_t bdesc = umma_desc(b_base + (uint32_t)(s * TC2_STAGE_BYTES + kk * 2 * 128 * 16), 128 * 16, 128);
@@ -456,7 +431,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
             if (RAW) {
                 if (tile < n_tiles) {
                     const int r = tile * TC_TILE_ROWS + q4 * 32 + lane;
-                    const bool valid = tc_row_valid(r, n_boards, 49);
+                    const bool valid = tc_row_valid(r, n_boards);
                     const int bb = r / 49;
                     float* orow = out32 + ((size_t)bb * 42 + (size_t)(r - bb * 49)) * 256;
 #pragma unroll 1
@@ -474,7 +449,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
                 }
             } else if (tile < n_tiles) {
                 const int r = tile * TC_TILE_ROWS + q4 * 32 + lane;
-                const bool valid = tc_row_valid(r, n_boards, 49);
+                const bool valid = tc_row_valid(r, n_boards);
                 const size_t cell0 = ((size_t)TC_HALO + r) * 8;
                 const size_t cstride = (size_t)r_alloc * 8;
                 // four channel chunks (32 accumulator columns) per TMEM load; the residual cells of the NEXT four are in flight meanwhile
@@ -520,8 +495,6 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (tile_done)                            // this warp's rows of the item are stored (also counted when the tile is padding)
-                    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(tile_done + pid + j * n_pairs), "r"(1u) : "memory");
                 if (leader) mbar_arrive(bar_acc_empty + b); else mbar_arrive_remote(bar_acc_empty + b, 0u);
             }
         }
@@ -538,13 +511,13 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
 // fp32 [n][42][13] -> bf16 [2 chunks][r_alloc][8] (channels 13..15 = 0); thread = board cell
 // (49-row layout: three copies var_stride elements apart — plain, x = 5 cells zeroed, x = 0 cells zeroed — for the stem's taps)
 __global__ void __launch_bounds__(256) k_nn_pack_input_tc(const float* __restrict__ x, int n, __nv_bfloat16* __restrict__ out, int r_alloc,
-                                                           int rpb, size_t var_stride)
+                                                           size_t var_stride)
 {
     int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n * 42) return;
     int b = i / 42, p = i - b * 42;
     const float* src = x + (size_t)i * AZ_NN_IN_CH;
-    int row = b * rpb + tc_cell_row(p, rpb);
+    int row = b * TC_RPB + p;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         uint4 o;
@@ -557,11 +530,9 @@ __global__ void __launch_bounds__(256) k_nn_pack_input_tc(const float* __restric
         }
         const size_t at = ((size_t)c * r_alloc + TC_HALO + row) * 8;
         *reinterpret_cast<uint4*>(out + at) = o;
-        if (rpb == 49) {
-            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(out + var_stride + at) = (p % 6) == 5 ? zero : o;
-            *reinterpret_cast<uint4*>(out + 2 * var_stride + at) = (p % 6) == 0 ? zero : o;
-        }
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(out + var_stride + at) = (p % 6) == 5 ? zero : o;
+        *reinterpret_cast<uint4*>(out + 2 * var_stride + at) = (p % 6) == 0 ? zero : o;
     }
 }
 
@@ -570,7 +541,7 @@ __global__ void __launch_bounds__(256) k_nn_pack_input_tc(const float* __restric
 // roundings), rounded to bf16 and written in the layout above without the fp32 [n][42][13] round trip through HBM.
 // One warp per position; lane l packs board cells l and l + 32.
 __global__ void __launch_bounds__(128) k_nn_pack_state_tc(const uint32_t* __restrict__ st, int n, __nv_bfloat16* __restrict__ out, int r_alloc,
-                                                           int rpb, size_t var_stride)
+                                                           size_t var_stride)
 {
     __shared__ uint32_t s_words[4][16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -618,16 +589,14 @@ __global__ void __launch_bounds__(128) k_nn_pack_state_tc(const uint32_t* __rest
         o2[0] = __floats2bfloat162_rn(o == cur ? fa : 0.0f, o == enemy ? fa : 0.0f);
         o2[1] = __floats2bfloat162_rn(o == AZ_NEUTRAL ? fa : 0.0f, sc[0]);
         o2[2] = __floats2bfloat162_rn(sc[1], sc[2]); o2[3] = __floats2bfloat162_rn(sc[3], sc[4]);
-        const int row = gi * rpb + tc_cell_row(p, rpb);
+        const int row = gi * TC_RPB + p;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const uint4 val = c ? c1 : c0;
             const size_t at = ((size_t)c * r_alloc + TC_HALO + row) * 8;
             *reinterpret_cast<uint4*>(out + at) = val;
-            if (rpb == 49) {
-                *reinterpret_cast<uint4*>(out + var_stride + at) = (p % 6) == 5 ? zero : val;
-                *reinterpret_cast<uint4*>(out + 2 * var_stride + at) = (p % 6) == 0 ? zero : val;
-            }
+            *reinterpret_cast<uint4*>(out + var_stride + at) = (p % 6) == 5 ? zero : val;
+            *reinterpret_cast<uint4*>(out + 2 * var_stride + at) = (p % 6) == 0 ? zero : val;
         }
     }
 }
@@ -641,7 +610,7 @@ __device__ __forceinline__ float warp_sum_tc(float v)
 
 // policy + value heads for HB boards per block (the head weights, 60 KB, are read once per block instead of once per board)
 #define HB 6     // 6 boards = 252 cells: one pass of the 256 threads over the 1x1 convolutions
-__global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __restrict__ act, int n, int r_alloc, int rpb, AzHeadParams hp,
+__global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __restrict__ act, int n, int r_alloc, AzHeadParams hp,
                                                       float* __restrict__ policy, float* __restrict__ value)
 {
     __shared__ float s_pi[HB][84], s_v[HB][42], s_logit[HB][44], s_red[HB][8];
@@ -657,7 +626,7 @@ __global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __rest
     const float scv = hp.bn_v[0] * rsqrtf(hp.bn_v[3] + AZ_NN_BN_EPS);
     for (int i = threadIdx.x; i < nb * 42; i += 256) {
         const int bl = i / 42, p = i - bl * 42;
-        const int row = (b0 + bl) * rpb + tc_cell_row(p, rpb);
+        const int row = (b0 + bl) * TC_RPB + p;
         const __nv_bfloat16* cellp = act + ((size_t)TC_HALO + row) * 8;
         float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
 #pragma unroll 4
@@ -728,7 +697,6 @@ __global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __rest
 }
 
 // ---------------------------------------------------------------- host side
-int az_launch_encode(const uint32_t* d_state, int n, float* d_x, cudaStream_t s);   // az_env.cu
 
 static std::string tc_block_name(int i) { return std::to_string(i) + std::string(1, (char)('a' + i)); }
 
@@ -764,30 +732,27 @@ static void pack_conv_pair(const float* w, __nv_bfloat16* dst, bool kb_outer = t
 }
 
 static cudaError_t launch_conv_pair3(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w3, const float* scale, const float* shift,
-                                     const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles,
-                                     unsigned* tile_done, unsigned poll_target)
+                                     const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES; cfg.stream = s;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    // programmatic dependent launch between consecutive layers (AZ_TC_PDL=0 turns it off for A/B runs)
-    static const bool pdl = !(getenv("AZ_TC_PDL") && atoi(getenv("AZ_TC_PDL")) == 0);
+    // programmatic dependent launch between consecutive layers: the next layer's barrier / TMEM set-up overlaps this layer's last wave
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<false>, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles, (float*)nullptr,
-                              tile_done, poll_target);
+    cfg.attrs = at; cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<false>, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles, (float*)nullptr);
 }
 
-// persistent launch of one stem / one-CTA tower convolution
+// persistent launch of the stem convolution
 template <int KCH, bool ROW_BN, int NV>
 static cudaError_t launch_conv(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w, const float* scale, const float* shift,
-                               const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles, int rpb, size_t var_stride_bytes)
+                               const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles, size_t var_stride_bytes)
 {
     k_nn_conv_tc<KCH, ROW_BN, NV><<<grid, TC_THREADS, TcShape<KCH>::smem_bytes(NV), s>>>(in, w, scale, shift, skip, out, n_boards, r_alloc, n_tiles,
-                                                                                        rpb, var_stride_bytes);
+                                                                                        var_stride_bytes);
     return cudaGetLastError();
 }
 
@@ -796,8 +761,8 @@ int az_nn_tc_prepare(az_nn* nn)
     if (!nn->tc) nn->tc = new AzTcState();
     AzTcState* tc = nn->tc;
     const int layers = 2 * nn->blocks;
-    std::vector<uint8_t> packed((size_t)layers * TC_LAYER_BYTES + TC_STEM_BYTES);
-    std::vector<uint8_t> packed3((size_t)layers * TC_LAYER_BYTES);
+    std::vector<uint8_t> packed((size_t)TC_STEM_BYTES);                   // stem stages
+    std::vector<uint8_t> packed3((size_t)layers * TC_LAYER_BYTES);         // tower stages, one half per CTA of a pair
     std::vector<float> scale((size_t)(layers + 1) * 256, 0.0f), shift((size_t)(layers + 1) * 256, 0.0f);
     for (int L = 0; L < layers; ++L) {
         std::string sfx = tc_block_name(L / 2) + ((L & 1) ? "_branch2b" : "_branch2a");
@@ -811,7 +776,6 @@ int az_nn_tc_prepare(az_nn* nn)
             float sc = g[c] / sqrtf(var[c] + AZ_NN_BN_EPS);
             scale[(size_t)L * 256 + c] = sc; shift[(size_t)L * 256 + c] = be[c] - mu[c] * sc;
         }
-        pack_conv(w, 256, 32, reinterpret_cast<__nv_bfloat16*>(packed.data() + (size_t)L * TC_LAYER_BYTES));
         pack_conv_pair(w, reinterpret_cast<__nv_bfloat16*>(packed3.data() + (size_t)L * TC_LAYER_BYTES));
     }
     {   // stem: conv/kernel [3][3][13][256], BatchNorm over the 7 board rows
@@ -825,25 +789,20 @@ int az_nn_tc_prepare(az_nn* nn)
             float sc = g[y] / sqrtf(var[y] + AZ_NN_BN_EPS);
             scale[(size_t)layers * 256 + y] = sc; shift[(size_t)layers * 256 + y] = be[y] - mu[y] * sc;
         }
-        pack_conv(w, AZ_NN_IN_CH, 2, reinterpret_cast<__nv_bfloat16*>(packed.data() + (size_t)layers * TC_LAYER_BYTES));
+        pack_conv(w, AZ_NN_IN_CH, 2, reinterpret_cast<__nv_bfloat16*>(packed.data()));
     }
     if (!tc->d_wpacked) {
         AZ_CUDA(cudaMalloc(&tc->d_wpacked, packed.size()));
         AZ_CUDA(cudaMalloc(&tc->d_wpacked3, packed3.size()));
         AZ_CUDA(cudaMalloc(&tc->d_scale, scale.size() * sizeof(float)));
         AZ_CUDA(cudaMalloc(&tc->d_shift, shift.size() * sizeof(float)));
-        AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<32, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<32>::smem_bytes(1))));
-        AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::smem_bytes(1))));
         AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<2, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::smem_bytes(3))));
         AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
         int dev = 0, sms = 148;
         AZ_CUDA(cudaGetDevice(&dev));
         AZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         tc->n_sm = sms;
-        if (const char* eg = getenv("AZ_TC_GRID")) { int g = atoi(eg); if (g >= 1 && g < sms) tc->n_sm = sms = g; }   // experiment knob: fewer persistent CTAs
         {   // CTA pairs the device can hold at once
-            const char* em = getenv("AZ_TC_MODE");
-            tc->pair_mode = !(em && strcmp(em, "single") == 0);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(sms / 2 * 2)); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES;
             cudaLaunchAttribute at[1];
@@ -853,10 +812,7 @@ int az_nn_tc_prepare(az_nn* nn)
             int nc = 0;
             AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc3<false>, &cfg));
             tc->max_pairs = nc < sms / 2 ? nc : sms / 2;
-            if (tc->max_pairs < 1) tc->pair_mode = 0;
-            // board layout: 49 rows (masked operand copies, 12.5 % fewer MMAs; needs the CTA-pair kernel) unless AZ_TC_LAYOUT=56
-            const char* el = getenv("AZ_TC_LAYOUT");
-            tc->rpb = (tc->pair_mode && !(el && strcmp(el, "56") == 0)) ? 49 : 56;
+            if (tc->max_pairs < 1) { az_set_error("the device cannot hold one CTA pair of the tower kernel (sm_100a thread-block clusters needed)"); return AZ_ERR_CUDA; }
         }
     }
     AZ_CUDA(cudaMemcpy(tc->d_wpacked, packed.data(), packed.size(), cudaMemcpyHostToDevice));
@@ -1101,7 +1057,7 @@ static int conv_raw_launch(AzTcConvScratch* sc, const __nv_bfloat16* in49, int n
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     AZ_CUDA(cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<true>, in49, (const uint8_t*)sc->d_w, (const float*)nullptr, (const float*)nullptr,
-                               (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, n, sc->r_alloc, tiles, d_out, (unsigned*)nullptr, 0u));
+                               (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, n, sc->r_alloc, tiles, d_out));
     return AZ_OK;
 }
 
@@ -1202,8 +1158,7 @@ void az_nn_tc_release(az_nn* nn)
     if (!nn->tc) return;
     AzTcState* tc = nn->tc;
     for (int i = 0; i < 3; ++i) cudaFree(tc->d_act[i]);
-    cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_wpacked3); cudaFree(tc->d_scale); cudaFree(tc->d_shift); cudaFree(tc->d_x);
-    cudaFree(tc->d_tile_done);
+    cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_wpacked3); cudaFree(tc->d_scale); cudaFree(tc->d_shift);
     delete tc;
     nn->tc = nullptr;
 }
@@ -1212,12 +1167,12 @@ static int tc_reserve(AzTcState* tc, int n)
 {
     if (n <= tc->cap_boards) return AZ_OK;
     for (int i = 0; i < 3; ++i) { cudaFree(tc->d_act[i]); tc->d_act[i] = nullptr; }
-    cudaFree(tc->d_x); tc->d_x = nullptr; cudaFree(tc->d_in); tc->d_in = nullptr;
-    int tiles = (n * tc->rpb + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
-    tiles += tiles & 1;                                       // the pair kernels read whole tile pairs
+    cudaFree(tc->d_in); tc->d_in = nullptr;
+    int tiles = (n * TC_RPB + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    tiles += tiles & 1;                                       // the pair kernel reads whole tile pairs
     int r_alloc = tiles * TC_TILE_ROWS + 2 * TC_HALO;
     size_t bytes = (size_t)TC_CHUNKS * r_alloc * 16;
-    const int nv = tc->rpb == 49 ? 3 : 1;
+    const int nv = 3;                                         // the stem's three operand copies
     for (int i = 0; i < 3; ++i) {
         AZ_CUDA(cudaMalloc(&tc->d_act[i], bytes));
         AZ_CUDA(cudaMemset(tc->d_act[i], 0, bytes));          // padding rows and halos must read as zero
@@ -1225,9 +1180,6 @@ static int tc_reserve(AzTcState* tc, int n)
     AZ_CUDA(cudaMalloc(&tc->d_in, (size_t)nv * 2 * r_alloc * 16));
     AZ_CUDA(cudaMemset(tc->d_in, 0, (size_t)nv * 2 * r_alloc * 16));
     tc->in_var_stride = (size_t)2 * r_alloc * 8;
-    AZ_CUDA(cudaMalloc(&tc->d_x, sizeof(float) * (size_t)n * AZ_INPUT_FLOATS));
-    cudaFree(tc->d_tile_done); tc->d_tile_done = nullptr;
-    AZ_CUDA(cudaMalloc(&tc->d_tile_done, sizeof(unsigned) * (size_t)(tiles / 2 + 1)));
     tc->cap_boards = n; tc->n_tiles = tiles; tc->r_alloc = r_alloc;
     return AZ_OK;
 }
@@ -1237,54 +1189,34 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
     AzTcState* tc = nn->tc;
     if (!tc || !tc->d_wpacked) { az_set_error("network not finalized"); return AZ_ERR_NOT_READY; }
     int rc = tc_reserve(tc, n); if (rc) return rc;
-    // from game states: one kernel packs the stem's bf16 input (AZ_TC_FUSED_PACK=0: k_env_encode to fp32, then k_nn_pack_input_tc)
-    const char* fp_env = getenv("AZ_TC_FUSED_PACK");            // read per call: the A/B test flips it inside one process
-    const bool fused_pack = !(fp_env && atoi(fp_env) == 0);
-    const bool from_state = !d_x && fused_pack;
-    if (!d_x && !fused_pack) {
-        rc = az_launch_encode(d_env_state, n, tc->d_x, s); if (rc) return rc;
-        d_x = tc->d_x;
-    }
+    // from game states (d_x == NULL): one kernel packs the stem's bf16 input straight from the states; from an fp32 tensor:
+    // k_nn_pack_input_tc.  Same expressions and roundings on both routes (tests/test_mcts_gpu.py compares a search fed by the
+    // first with an oracle search fed by the second)
+    const bool from_state = d_x == nullptr;
     // buffers are sized for cap_boards; only the tiles that hold boards of this call are computed
-    const int rpb = tc->rpb;
-    const int tiles = (n * rpb + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    const int tiles = (n * TC_RPB + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     const int grid = tiles < tc->n_sm ? tiles : tc->n_sm;
     const int layers = 2 * nn->blocks;
     int cur = 0, tmp = 1, nxt = 2;
-    if (from_state) k_nn_pack_state_tc<<<(n + 3) / 4, 128, 0, s>>>(d_env_state, n, tc->d_in, tc->r_alloc, rpb, tc->in_var_stride);
-    else k_nn_pack_input_tc<<<(n * 42 + 255) / 256, 256, 0, s>>>(d_x, n, tc->d_in, tc->r_alloc, rpb, tc->in_var_stride);
+    if (from_state) k_nn_pack_state_tc<<<(n + 3) / 4, 128, 0, s>>>(d_env_state, n, tc->d_in, tc->r_alloc, tc->in_var_stride);
+    else k_nn_pack_input_tc<<<(n * 42 + 255) / 256, 256, 0, s>>>(d_x, n, tc->d_in, tc->r_alloc, tc->in_var_stride);
     AZ_CUDA(cudaGetLastError());
-    const uint8_t* w_stem = tc->d_wpacked + (size_t)layers * TC_LAYER_BYTES;
-    if (rpb == 49)
-        AZ_CUDA((launch_conv<2, true, 3>(grid, s, tc->d_in, w_stem, tc->d_scale + layers * 256, tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n,
-                                         tc->r_alloc, tiles, rpb, tc->in_var_stride * 2)));
-    else
-        AZ_CUDA((launch_conv<2, true, 1>(grid, s, tc->d_in, w_stem, tc->d_scale + layers * 256, tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n,
-                                         tc->r_alloc, tiles, rpb, 0)));
+    AZ_CUDA((launch_conv<2, true, 3>(grid, s, tc->d_in, tc->d_wpacked, tc->d_scale + layers * 256, tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n,
+                                     tc->r_alloc, tiles, tc->in_var_stride * 2)));
     const int pitems = (tiles + 1) / 2;
     const int pgrid = 2 * (pitems < tc->max_pairs ? pitems : tc->max_pairs);
-    // layer-to-layer pipelining of the tower: an experiment kept behind AZ_TC_PIPE=1 (needs the programmatic launches).  Same results,
-    // but 1.6 % SLOWER at configs[2] (1.952 vs 1.985 M simulations/s, two interleaved A/B pairs): the forward sits at the board's power
-    // cap, so filling the idle SM pairs of a layer's last wave only lowers the clock of everything else (profiles/README.md)
-    static const bool pipe = getenv("AZ_TC_PIPE") && atoi(getenv("AZ_TC_PIPE")) == 1 && !(getenv("AZ_TC_PDL") && atoi(getenv("AZ_TC_PDL")) == 0);
-    unsigned* tile_done = (pipe && rpb == 49) ? tc->d_tile_done : nullptr;
-    if (tile_done) AZ_CUDA(cudaMemsetAsync(tile_done, 0, sizeof(unsigned) * (size_t)pitems, s));
     for (int i = 0; i < nn->blocks; ++i) {
         for (int h = 0; h < 2; ++h) {                        // branch2a: cur -> tmp; branch2b: tmp (+ cur as the residual) -> nxt
             const int L = 2 * i + h;
             const __nv_bfloat16* src = h ? tc->d_act[tmp] : tc->d_act[cur];
             const __nv_bfloat16* res = h ? tc->d_act[cur] : nullptr;
             __nv_bfloat16* dst = h ? tc->d_act[nxt] : tc->d_act[tmp];
-            const float* sc = tc->d_scale + L * 256; const float* sh = tc->d_shift + L * 256;
-            if (rpb == 49)
-                AZ_CUDA(launch_conv_pair3(pgrid, s, src, tc->d_wpacked3 + (size_t)L * TC_LAYER_BYTES, sc, sh, res, dst, n, tc->r_alloc, tiles,
-                                          tile_done, tile_done ? 8u * (unsigned)L : 0u));
-            else
-                AZ_CUDA((launch_conv<32, false, 1>(grid, s, src, tc->d_wpacked + (size_t)L * TC_LAYER_BYTES, sc, sh, res, dst, n, tc->r_alloc, tiles, rpb, 0)));
+            AZ_CUDA(launch_conv_pair3(pgrid, s, src, tc->d_wpacked3 + (size_t)L * TC_LAYER_BYTES, tc->d_scale + L * 256, tc->d_shift + L * 256, res, dst, n,
+                                      tc->r_alloc, tiles));
         }
         int o = cur; cur = nxt; nxt = o;
     }
-    k_nn_heads_tc<<<(n + HB - 1) / HB, 256, 0, s>>>(tc->d_act[cur], n, tc->r_alloc, rpb, az_nn_head_params(nn), d_policy, d_value);
+    k_nn_heads_tc<<<(n + HB - 1) / HB, 256, 0, s>>>(tc->d_act[cur], n, tc->r_alloc, az_nn_head_params(nn), d_policy, d_value);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }

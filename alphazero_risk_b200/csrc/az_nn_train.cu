@@ -57,8 +57,6 @@ int az_nn_sync_host(az_nn* nn);      // az_nn.cu
 struct AzTrainState {
     int cap = 0;                                       // boards the work buffers are sized for
     bool dz_prepared = false;                          // the current layer's dz sits converted in conv.d_in3 (weight gradient done, data gradient next)
-    bool wgrad_by_gemm = false;                        // AZ_TRAIN_WGRAD=gemm: A/B switch back to the transposed-im2col GEMM
-    bool conv_by_gemm = false;                         // AZ_TRAIN_CONV=gemm: A/B switch back to im2col + k_tc_gemm for the 256-channel convolutions
     int precision = AZ_NN_FP32;                        // AZ_NN_BF16: the three contractions run on the tensor cores (az_tc_gemm.cu)
     __nv_bfloat16 *d_colA = nullptr, *d_colB = nullptr;   // GEMM operands: im2col / transposed im2col, weights / transposed gradient
     AzTcConvScratch conv;                              // 256-channel convolutions of the tensor-core mode run on the tower kernel
@@ -860,12 +858,12 @@ static int train_reserve(az_nn* nn, AzTrainState* t, int n)
 static int conv_any(az_nn* nn, AzTrainState* t, const float* in, int n, int cin, const float* w, int flip, float* out, cudaStream_t s,
                     const __nv_bfloat16* in49 = nullptr)
 {
-    if (t->precision == AZ_NN_BF16 && cin == TR_CH && !t->conv_by_gemm) {       // implicit GEMM on the tower kernel (no unrolled operand in HBM)
+    if (t->precision == AZ_NN_BF16 && cin == TR_CH) {       // implicit GEMM on the tower kernel (no unrolled operand in HBM)
         if (flip && t->dz_prepared) { t->dz_prepared = false; return az_tc_dgrad_prepared(&t->conv, n, w, out, s); }
         if (!flip && in49) return az_tc_conv_raw49(&t->conv, in49, n, w, 0, out, s);
         return az_tc_conv_raw(&t->conv, in, n, w, flip, out, s);
     }
-    if (t->precision == AZ_NN_BF16) {
+    if (t->precision == AZ_NN_BF16) {                       // the 13-channel stem: chunked im2col + k_tc_gemm
         const int rows = n * 42, mp = (int)tr_mp(rows), cpad = (cin + 7) / 8 * 8, kp = (int)tr_kp(9 * cpad);
         int rc = az_tg_im2col(in, rows, cin, cpad, mp, kp, t->d_src16, t->d_colA, s); if (rc) return rc;
         rc = az_tg_weights(w, cin, cpad, kp, flip, t->d_colB, s); if (rc) return rc;
@@ -883,7 +881,7 @@ static int conv_any(az_nn* nn, AzTrainState* t, const float* in, int n, int cin,
 }
 
 // the fused tensor-core route: tower kernel + k_tc_wgrad with the bf16 operands written by the BatchNorm passes themselves
-static bool tr_tower(const AzTrainState* t) { return t->precision == AZ_NN_BF16 && !t->conv_by_gemm && !t->wgrad_by_gemm; }
+static bool tr_tower(const AzTrainState* t) { return t->precision == AZ_NN_BF16; }
 
 static std::string tr_block_sfx(int i) { return std::to_string(i) + std::string(1, (char)('a' + i)); }
 // layer L >= 1 of the tower: block (L - 1) / 2, branch 2a for odd L, 2b for even L
@@ -945,7 +943,7 @@ static int conv_wgrad(az_nn* nn, AzTrainState* t, int L, int n, const float* in,
         int rc = az_tc_wgrad49(&t->conv, t->conv.a49[(size_t)L - 1], n, t->d_wpart, TR_WG_SPLITS, &splits, s); if (rc) return rc;
         return az_tg_reduce(t->d_wpart, splits, 9 * TR_CH, 9 * TR_CH, gvar(nn, t, tr_conv_name(L) + "/kernel"), s);
     }
-    if (t->precision == AZ_NN_BF16) {                          // dW[t*cin + ci][co] = im2col(in)^T . dz, K = board cells, split over K
+    if (t->precision == AZ_NN_BF16) {                          // the stem: dW[t*cin + ci][co] = im2col(in)^T . dz, K = board cells, split over K
         const int rows = n * 42, mp = (int)tr_mp(9 * cin), kp = (int)tr_kp(rows);
         const int splits = az_tg_splits(kp, 148 / (mp / 128) > TR_WG_SPLITS ? TR_WG_SPLITS : 148 / (mp / 128));
         int rc = az_tg_im2col_t(in, rows, cin, mp, kp, t->d_src16, t->d_colA, s); if (rc) return rc;
@@ -1110,10 +1108,6 @@ extern "C" int az_nn_train_precision(az_nn* nn, int precision)
     AzTrainState* t = train_state(nn);
     AZ_REQUIRE(t != nullptr, "out of host memory");
     t->precision = precision;
-    const char* ec = getenv("AZ_TRAIN_CONV");
-    t->conv_by_gemm = ec && strcmp(ec, "gemm") == 0;
-    const char* ew = getenv("AZ_TRAIN_WGRAD");
-    t->wgrad_by_gemm = ew && strcmp(ew, "gemm") == 0;
     return AZ_OK;
 }
 

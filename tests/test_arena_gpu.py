@@ -91,12 +91,15 @@ def match_record_stream(recs, expected):
     assert not left
 
 
-def oracle_pair(slot_game, sims, ply0=0, opponent="script"):
+def oracle_pair(slot_game, sims, ply0=0, opponent="script", oracle_eval=None, K=1):
     """one claimed pair on one slot, replayed on the oracle: AlphaZero (player 0, play mode, pseudo evaluator) vs Script (player 1),
     fresh deal then the mirror game (Game::newGame, game/game.cpp:170-191); returns GameResults-style tallies, the final Data
     image and the ply counter"""
     rules = po.default_rules(mcts_simulations=sims, threads_per_mcts=1)
     o, tree, sp = po.OracleGame(rules), po.OracleMcts(rules, "pseudo"), po.new_script()
+    if oracle_eval is not None:            # the search's evaluator = a caller-supplied function (e.g. the CUDA network, batch of one)
+        tree.L.ro_mcts_free(tree.h)
+        tree.h = tree.L.ro_mcts_new(C.cast(oracle_eval, C.c_void_p), None)
     res = dict(count=0, draw=0, win=[0, 0], was=[0, 0], az_moves=0, opp_turns=0, samples=[])
     ply = ply0
     start = None
@@ -118,7 +121,7 @@ def oracle_pair(slot_game, sims, ply0=0, opponent="script"):
             else:
                 if last != 0:
                     tree.trim()            # AlphaZeroPlayer::takeTurn: trimNodes when its turn starts
-                a = tree.search(o, SEED, slot_game, ply)
+                a = tree.search(o, SEED, slot_game, ply, lockstep=K)
                 staged.append((po.RoState.from_buffer_copy(o.s), a["pi"].copy()))      # AlphaZeroPlayer::takeTurn pushes before the move
                 mv = tree.pick(a["pi"], False, SEED, slot_game, ply)
                 assert o.move(mv, SEED, slot_game, ply) == 0
@@ -254,38 +257,45 @@ def test_arena_alphazero_vs_alphazero_matches_oracle(api, n, first, sims, K, eva
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_arena_leaf_compaction_changes_nothing(api, precision):
+def test_arena_with_network_matches_oracle_replay(api, precision):
     """with a network evaluator the arena sends only the slots that search this tick through the network (gather -> forward ->
-    scatter); AZ_ARENA_COMPACT=0 evaluates every slot.  Both must play the same match, move for move: vs Script with slots finishing
-    at different times, and AlphaZero vs AlphaZero where each searcher owns about half of the slots per tick."""
-    import os
+    scatter: the leaf batch shrinks and changes composition as slots finish at different times).  The oracle replays every slot's
+    pair with an evaluator that calls the SAME network on a batch of one (the kernels are batch-invariant), so the match must be
+    identical move for move: final positions, GameResults tallies, move and simulation counts.  K = 2 descents per tree."""
     prec = api.FP32 if precision == "fp32" else api.BF16
-    rules = api.default_rules(mcts_simulations=6, threads_per_mcts=1, concurrent_descents=2)
-    nets = [api.Net(blocks=1, seed=5), api.Net(blocks=1, seed=6)]
-    outcome = {}
-    for compact in ("1", "0"):
-        os.environ["AZ_ARENA_COMPACT"] = compact
-        try:
-            env = api.Env(9, rules=rules, first_game_id=70)
-            mc0 = api.Mcts(env, net=nets[0], evaluator=api.EVAL_NN, precision=prec)
-            mc1 = api.Mcts(env, net=nets[1], evaluator=api.EVAL_NN, precision=prec)
-            a_script = api.Arena(mc0, api.OPPONENT_SCRIPT, mirror_games=True)
-            r1 = a_script.play(26, SEED)
-            s1 = env.export_aos().copy()
-            a_versus = api.Arena(mc0, mirror_games=True, opponent_mcts=mc1)
-            r2 = a_versus.play(18, SEED + 3)
-            s2 = env.export_aos().copy()
-            for r in (r1, r2):
-                assert r["errors"] == 0
-            outcome[compact] = (r1, s1, r2, s2)
-            a_versus.close(); a_script.close(); mc1.close(); mc0.close(); env.close()
-        finally:
-            os.environ.pop("AZ_ARENA_COMPACT", None)
-    (r1, s1, r2, s2), (q1, t1, q2, t2) = outcome["1"], outcome["0"]
-    assert r1 == q1 and r2 == q2 and (s1 == t1).all() and (s2 == t2).all()
-    assert r1["count"] == 26 and r2["count"] == 18
-    for n in nets:
-        n.close()
+    n, first, sims, K = 9, 70, 6, 2
+    rules = api.default_rules(mcts_simulations=sims, threads_per_mcts=1, concurrent_descents=K)
+    net = api.Net(blocks=1, seed=5)
+    L = po.oracle_lib()
+
+    @C.CFUNCTYPE(None, C.POINTER(po.RoState), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p)
+    def evaluator(sp, policy, value, user):
+        x = np.zeros(po.INPUT_FLOATS, np.float32)
+        L.ro_encode(sp, x)
+        p, v = net.forward(x.reshape(1, -1), prec)
+        C.memmove(policy, p.ctypes.data, 43 * 4)
+        value[0] = float(v[0])
+
+    env = api.Env(n, rules=rules, first_game_id=first)
+    mc = api.Mcts(env, net=net, evaluator=api.EVAL_NN, precision=prec)
+    arena = api.Arena(mc, api.OPPONENT_SCRIPT, mirror_games=True)
+    r = arena.play(2 * n, SEED)
+    assert r["errors"] == 0 and r["count"] == 2 * n
+    dev = env.export_aos()
+    tot = dict(count=0, draw=0, win=[0, 0], was=[0, 0], az_moves=0, opp_turns=0)
+    lengths = []
+    for g in range(n):
+        res, data, ply = oracle_pair(first + g, sims, oracle_eval=evaluator, K=K)
+        lengths.append(ply)
+        assert (dev[g] == data).all(), "slot %d: final position differs from the oracle replay" % g
+        for k in ("count", "draw", "az_moves", "opp_turns"):
+            tot[k] += res[k]
+        for i in range(2):
+            tot["win"][i] += res["win"][i]; tot["was"][i] += res["was"][i]
+    assert (r["count"], r["draw"], r["win"], r["win_and_started"]) == (tot["count"], tot["draw"], tot["win"], tot["was"])
+    assert r["az_moves"] == tot["az_moves"] and r["opponent_turns"] == tot["opp_turns"] and r["az_sims"] == tot["az_moves"] * sims
+    assert len(set(lengths)) > 1            # slots finished at different times: the compacted batch really shrank
+    arena.close(); mc.close(); env.close(); net.close()
 
 
 def test_arena_claims_pairs_like_the_counter(api):

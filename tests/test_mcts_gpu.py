@@ -285,31 +285,50 @@ def test_full_size_search_properties_and_shard_invariance(api):
     net.close()
 
 
-def test_fused_state_packing_changes_nothing(api):
+def test_fused_state_packing_matches_the_tensor_route(api):
     """the leaf batch of a bf16 search reaches the stem through ONE kernel that packs bf16 operands straight from the game states
-    (k_nn_pack_state_tc); AZ_TC_FUSED_PACK=0 takes the two-step route (k_env_encode to fp32, k_nn_pack_input_tc).  Same
-    expressions, same roundings: the two routes must give the same search — visit counts, moves and states, bit for bit."""
-    import os
-    rules = api.default_rules(mcts_simulations=12, threads_per_mcts=1)
+    (k_nn_pack_state_tc); az_nn_forward on an fp32 input tensor takes the other route (k_nn_pack_input_tc on what the reference's
+    encoder produces).  Same expressions, same roundings: a device search (first route) and an oracle search whose evaluator calls
+    the network on the oracle's own encoding (second route, batch of one) must agree on visit counts, pi and moves, bit for bit.
+    Mid-game positions (every channel of the encoding is live), 70 positions = more than one 128-row tile, ragged."""
+    n, first, sims, start = 70, 900, 12, 90
+    rules = api.default_rules(mcts_simulations=sims, threads_per_mcts=1)
+    rules_o = po.default_rules(mcts_simulations=sims, threads_per_mcts=1)
     net = api.Net(blocks=2, seed=77)
-    out = {}
-    for fused in ("1", "0"):
-        os.environ["AZ_TC_FUSED_PACK"] = fused
-        try:
-            env = api.Env(70, rules=rules, first_game_id=900)          # 70 positions: more than one 128-row tile, ragged
-            env.reset(SEED)
-            env.rollout(90)                                            # out of the set-up phase: every channel of the encoding is live
-            mc = api.Mcts(env, net=net, evaluator=api.EVAL_NN, precision=api.BF16)
-            visits = []
-            for _ in range(5):
-                r = mc.search(pick_mode=api.PICK_SELFPLAY, apply_move=True)
-                visits.append((r["N"].copy(), r["move"].copy()))
-            assert mc.counters()["errors"] == 0
-            out[fused] = (visits, env.export_aos().copy())
-            mc.close(); env.close()
-        finally:
-            os.environ.pop("AZ_TC_FUSED_PACK", None)
-    for (n1, m1), (n0, m0) in zip(out["1"][0], out["0"][0]):
-        assert (n1 == n0).all() and (m1 == m0).all()
-    assert (out["1"][1] == out["0"][1]).all()
-    net.close()
+    L = po.oracle_lib()
+
+    @C.CFUNCTYPE(None, C.POINTER(po.RoState), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p)
+    def evaluator(sp, policy, value, user):
+        x = np.zeros(po.INPUT_FLOATS, np.float32)
+        L.ro_encode(sp, x)
+        p, v = net.forward(x.reshape(1, -1), api.BF16)
+        C.memmove(policy, p.ctypes.data, 43 * 4)
+        value[0] = float(v[0])
+
+    env = api.Env(n, rules=rules, first_game_id=first)
+    env.reset(SEED)
+    env.rollout(start)                                            # out of the set-up phase
+    img = env.export_aos()
+    mc = api.Mcts(env, net=net, evaluator=api.EVAL_NN, precision=api.BF16)
+    dev = []
+    for _ in range(4):
+        r = mc.search(pick_mode=api.PICK_SELFPLAY, apply_move=True)
+        dev.append((r["N"].copy(), r["pi"].copy(), r["move"].copy()))
+    assert mc.counters()["errors"] == 0
+    final = env.export_aos()
+    for g in range(0, n, 3):
+        o, t = po.OracleGame(rules_o), po.OracleMcts(rules_o, "pseudo")
+        t.L.ro_mcts_free(t.h)
+        t.h = t.L.ro_mcts_new(C.cast(evaluator, C.c_void_p), None)
+        assert o.set_data(img[g]) == 0
+        for k, (N, pi, move) in enumerate(dev):
+            if o.status() != -1:
+                assert move[g] == 43
+                continue
+            a = t.search(o, SEED, first + g, start + k)
+            assert (N[g] == a["N"]).all(), (g, k)
+            assert (bits(pi[g]) == bits(a["pi"])).all(), (g, k)
+            mv = t.pick(a["pi"], o.s.round <= rules_o.temperature_threshold, SEED, first + g, start + k)
+            assert move[g] == mv and o.move(mv, SEED, first + g, start + k) == 0
+        assert (final[g] == o.data()).all(), g
+    mc.close(); env.close(); net.close()
