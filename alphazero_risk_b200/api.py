@@ -125,6 +125,19 @@ def lib():
         L.az_arena_play.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(AzArenaResults), vp]
         L.az_selfplay_samples.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), vp]
         L.az_samples_write_file.argtypes = [C.c_char_p, vp, C.c_size_t]
+        L.az_dist_nccl_version.argtypes = [C.POINTER(C.c_int)]
+        L.az_dist_init.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
+        L.az_dist_unique_id.argtypes = [vp]
+        L.az_dist_init_rank.argtypes = [C.c_int, C.c_int, vp, C.c_int, C.POINTER(vp)]
+        L.az_dist_destroy.argtypes = [vp]
+        L.az_dist_world_size.argtypes = [vp]
+        L.az_dist_local_count.argtypes = [vp]
+        L.az_dist_rank.argtypes = [vp, C.c_int]
+        L.az_dist_broadcast_weights.argtypes = [vp, C.POINTER(vp), C.c_int, C.c_int]
+        L.az_dist_gather_stats.argtypes = [vp, vp, C.c_int, vp, vp]
+        L.az_dist_gather_counters.argtypes = [vp, C.POINTER(AzCounters), C.POINTER(AzCounters)]
+        L.az_dist_gather_results.argtypes = [vp, C.POINTER(AzArenaResults), C.POINTER(AzArenaResults)]
+        L.az_dist_barrier.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -541,3 +554,97 @@ class Mcts:
         d = c.as_dict()
         d["errors"] = int(err.value)
         return d
+
+
+DIST_ID_BYTES = 128
+
+
+class Dist:
+    """the two cross-GPU exchanges over NCCL (az_dist_*): weight broadcast and statistics gather.
+
+    Dist(devices=[0, 1, ...])                      one process drives several GPUs (the reference's model)
+    Dist(world_size=N, rank=r, unique_id=b, device=d)   one process per GPU; rank 0 makes the id with Dist.unique_id()
+    """
+
+    def __init__(self, devices=None, world_size=None, rank=None, unique_id=None, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        if world_size is None:
+            devs = list(devices) if devices is not None else [0]
+            arr = (C.c_int * len(devs))(*devs)
+            check(self.L.az_dist_init(len(devs), arr, C.byref(h)))
+        else:
+            idb = np.frombuffer(bytes(unique_id), np.uint8).copy()
+            assert idb.size == DIST_ID_BYTES
+            check(self.L.az_dist_init_rank(int(world_size), int(rank), _ptr(idb), int(device), C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def unique_id():
+        out = np.zeros(DIST_ID_BYTES, np.uint8)
+        check(lib().az_dist_unique_id(_ptr(out)))
+        return out.tobytes()
+
+    @staticmethod
+    def nccl_version():
+        v = C.c_int(0)
+        check(lib().az_dist_nccl_version(C.byref(v)))
+        return int(v.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.az_dist_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def world_size(self):
+        return int(self.L.az_dist_world_size(self.h))
+
+    def local_count(self):
+        return int(self.L.az_dist_local_count(self.h))
+
+    def rank(self, local_index=0):
+        return int(self.L.az_dist_rank(self.h, int(local_index)))
+
+    def broadcast_weights(self, nets, root_rank=0):
+        """nets: one Net per local member, in member order"""
+        nets = list(nets)
+        arr = (C.c_void_p * len(nets))(*[n.h for n in nets])
+        check(self.L.az_dist_broadcast_weights(self.h, arr, len(nets), int(root_rank)))
+
+    def gather_stats(self, local, per_rank=False):
+        """local: uint64 [local_count, n] -> (sum [n], per-rank [world, n] or None)"""
+        a = np.ascontiguousarray(local, np.uint64).reshape(self.local_count(), -1)
+        n = a.shape[1]
+        total = np.zeros(n, np.uint64)
+        ranks = np.zeros((self.world_size(), n), np.uint64) if per_rank else None
+        check(self.L.az_dist_gather_stats(self.h, _ptr(a), n, _ptr(total), _ptr(ranks) if per_rank else None))
+        return total, ranks
+
+    def gather_counters(self, counters):
+        """counters: list of dicts as returned by Env.counters() / Mcts.counters(), one per local member -> summed dict"""
+        loc = (AzCounters * len(counters))()
+        for i, c in enumerate(counters):
+            loc[i].steps, loc[i].games, loc[i].draws = c["steps"], c["games"], c["draws"]
+            loc[i].wins[0], loc[i].wins[1] = c["wins"]
+            loc[i].illegal, loc[i].sims, loc[i].evals, loc[i].path_nodes = c["illegal"], c["sims"], c["evals"], c.get("path_nodes", 0)
+        tot = AzCounters()
+        check(self.L.az_dist_gather_counters(self.h, loc, C.byref(tot)))
+        return tot.as_dict()
+
+    def gather_results(self, results):
+        """results: list of Arena.play() dicts, one per local member -> GameResults::add over every rank"""
+        loc = (AzArenaResults * len(results))()
+        for i, r in enumerate(results):
+            loc[i].count, loc[i].draw = r["count"], r["draw"]
+            loc[i].win[0], loc[i].win[1] = r["win"]
+            loc[i].win_and_started[0], loc[i].win_and_started[1] = r["win_and_started"]
+            loc[i].az_moves, loc[i].az_sims, loc[i].az_evals = r["az_moves"], r["az_sims"], r["az_evals"]
+            loc[i].opponent_turns, loc[i].ticks, loc[i].errors = r["opponent_turns"], r["ticks"], r["errors"]
+        tot = AzArenaResults()
+        check(self.L.az_dist_gather_results(self.h, loc, C.byref(tot)))
+        return tot.as_dict()
+
+    def barrier(self):
+        check(self.L.az_dist_barrier(self.h))

@@ -26,6 +26,7 @@ UNITS = {
     "az_tc_gemm.cu": [],
     "az_nn_train.cu": ["-fmad=false"],   # training step: plain fp32, same roundings whatever the compiler would contract
     "az_ckpt.cpp": [],       # host only: TensorFlow V2 checkpoint bundles
+    "az_dist.cu": [],        # NCCL weight broadcast + statistics gather (NCCL itself is dlopen'ed at run time)
 }
 
 
@@ -61,7 +62,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or not os.path.exists(LIB):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda"]
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda", "-ldl"]
         subprocess.check_call(cmd)
     return LIB
 

@@ -39,6 +39,7 @@ struct PlaySettings {
     int BLOCKS = 5;                       // CMake BLOCKS / the GraphDef in use (model_bin_V2_5.pb = 5)
     int device = 0;                       // the reference's gpu index
     int slots = 0;                        // concurrent games; 0 = one slot per claimed pair (the reference: gpus x gpu-games threads)
+    uint32_t first_game_id = 0;           // global id of slot 0: shards of one match on several GPUs use disjoint id ranges (az_cluster.hpp)
     int precision = AZ_NN_BF16;
     uint64_t seed = 0x5EED0001ull;        // Philox contract seed (the reference seeds from random_device)
 };
@@ -64,6 +65,8 @@ public:
         release();                                            // the searcher re-packs the weights when it is rebuilt
     }
     az_nn* network() { return nn; }
+    // global id of slot 0 (az_cluster.hpp gives every GPU's shard of a match its own id range)
+    void setFirstGameId(uint32_t id) { if (id != st.first_game_id) { st.first_game_id = id; release(); } }
 
     // player index 1: AZ_OPPONENT_SCRIPT (default, ScriptPlayerGroup) or AZ_OPPONENT_RANDOM (RandomPlayerGroup, the trainer's benchmark)
     void setOpponent(int kind)
@@ -120,7 +123,7 @@ private:
         r.dir_noise_value = st.DIR_NOISE_VALUE; r.dir_noise_epsi = st.DIR_NOISE_EPSI; r.allow_yield = st.ALLOW_YIELD;
         r.limit_reinforcement = st.LIMIT_REINFORCEMENT_MOVES; r.limit_attack = st.LIMIT_ATTACK_MOVES;
         r.max_game_rounds = st.MAX_GAME_ROUNDS; r.min_unit_move = st.MIN_UNIT_MOVE;
-        ck(az_env_create(slots, &r, st.device, 0, &env), "az_env_create");
+        ck(az_env_create(slots, &r, st.device, st.first_game_id, &env), "az_env_create");
         ck(az_mcts_create(env, nn, AZ_EVAL_NN, st.precision, &mcts), "az_mcts_create");
         if (opponent == AZ_OPPONENT_ALPHAZERO) {
             ck(az_mcts_create(env, opponent_nn, AZ_EVAL_NN, st.precision, &opponent_mcts), "az_mcts_create");

@@ -39,14 +39,35 @@ def measured_peaks():
     return 6650.0, 1400.0, "fallback"
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), or None"""
+def ncu_capture(kernel):
+    """the committed ncu --set full numbers of `kernel` (profiles/traffic.json, tools/traffic_from_ncu.py) — only if they were
+    measured on the sources this library was built from; otherwise None and a reason (a capture of another binary is not evidence)"""
+    import hashlib
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         d = json.load(open(p)).get(kernel)
-        return None if d is None else float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
-    except (OSError, ValueError, KeyError):
-        return None
+    except (OSError, ValueError):
+        return None, "profiles/traffic.json missing or unreadable"
+    if d is None:
+        return None, "no capture of %s in profiles/traffic.json" % kernel
+    for f, want in (d.get("sources") or {"<none>": ""}).items():
+        path = os.path.join(ROOT, "include" if f.endswith(".h") and not f.startswith("az_tables") else "alphazero_risk_b200/csrc", f)
+        try:
+            have = hashlib.sha256(open(path, "rb").read()).hexdigest()[:16]
+        except OSError:
+            have = None
+        if have != want:
+            return None, "capture %s was taken on a different %s (re-run tools/round_profile.sh)" % (d.get("capture"), f)
+    return d, None
+
+
+def ncu_traffic(kernel):
+    """roofline.traffic (DRAM bytes per launch, ncu) plus where it comes from; null + the reason when the capture is stale"""
+    d, why = ncu_capture(kernel)
+    if d is None:
+        sys.stderr.write("bench.py: roofline.traffic of %s not reported: %s\n" % (kernel, why))
+        return {"traffic": None, "traffic_stale": why}
+    return {"traffic": float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), "traffic_capture": d.get("capture")}
 
 
 class ClockSampler:
@@ -215,12 +236,15 @@ def nn_flops_per_position(blocks):
     return 2 * 42 * (9 * 13 * 256 + 2 * blocks * 9 * 256 * 256 + 256 * 2 + 256 * 1) + 2 * (84 * 43 + 42 * 256 + 256)
 
 
-def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
-    from alphazero_risk_b200 import dist as azdist
+def run_selfplay(args, api, torch, dist, azd, rank, world, local, barrier, shape=None, label="configs[2]", with_tree=True):
     """BASELINE configs[2]: batched self-play, 4096 games x 64 MCTS sims/move per GPU, leaf-batched bf16
-    tcgen05 network forward (5-block graph = the only GraphDef the reference ships, random-init weights)."""
-    import numpy as np
+    tcgen05 network forward (5-block graph = the only GraphDef the reference ships, random-init weights).
+    shape = (games, sims, blocks, moves_per_step, steps, warmup_moves) overrides the command-line shape: the cfg5 / blocks20 sub-lines."""
+    from alphazero_risk_b200 import dist as azdist
     n, sims, blocks = args.sp_games, args.sp_sims, args.blocks
+    moves_per_step, steps, warm_moves = args.sp_moves, max(2, min(args.steps, args.sp_steps)), None
+    if shape is not None:
+        n, sims, blocks, moves_per_step, steps, warm_moves = shape
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
     K = max(1, args.sp_descents)
@@ -230,16 +254,17 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
     net = api.Net(blocks=blocks, device=local)
     if rank == 0:
         net.init_random(1234)
-    if dist is not None:      # weight broadcast (replaces the checkpoint-file hand-off of alphazero_gpu_cluster.cpp:221-231)
-        azdist.broadcast_weights(net, dist, src=0)
+    if azd is not None:       # az_dist_broadcast_weights: ncclBroadcast of rank 0's blob (replaces the checkpoint-file hand-off of
+        azd.broadcast_weights([net], 0)           # alphazero_gpu_cluster.cpp:221-231)
     net.finalize()
     mc = api.Mcts(env, net=net, evaluator=api.EVAL_NN, precision=api.BF16)
-    moves_per_step = args.sp_moves
-    for _ in range(max(1, args.warmup // 2)):
-        mc.selfplay(moves_per_step, stream=sptr)
+    if warm_moves is None:
+        for _ in range(max(1, args.warmup // 2)):
+            mc.selfplay(moves_per_step, stream=sptr)
+    elif warm_moves > 0:
+        mc.selfplay(warm_moves, stream=sptr)
     torch.cuda.synchronize()
     mc.counters(reset=True, stream=sptr)
-    steps = max(2, min(args.steps, args.sp_steps))
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     sampler = ClockSampler(local)
     if rank == 0:
@@ -254,8 +279,9 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     cnt = mc.counters(stream=sptr)
     # e2e: the call a host-side game loop makes per move — State images in from pinned host memory (az_env_import_aos), one
-    # az_mcts_search through the host-buffer ABI (visit counts, pi, moves, status copied back), images out again
-    e2e_moves = max(2, moves_per_step)
+    # az_mcts_search through the host-buffer ABI (visit counts, pi, moves, status copied back), images out again; as many moves as
+    # the device-timed region above
+    e2e_moves = max(2, moves_per_step * steps) if shape is None else max(1, moves_per_step)
     h_img = torch.empty((n, 160), dtype=torch.uint8).pin_memory()
     env.export_aos(out=h_img.numpy(), stream=sptr)
     barrier()
@@ -269,13 +295,15 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
     dev_ms, e2e_ms = dev_ms, e2e_s * 1e3
     if dist is not None:
         dev_ms, e2e_ms = azdist.max_over_ranks([dev_ms, e2e_ms], dist)
-        cnt = azdist.reduce_counters(cnt, dist)           # stats gather (replaces GameResults::add, game.cpp:298-309)
+        errs = cnt["errors"]                              # az_dist_gather_counters / _stats: ncclAllReduce of the tallies
+        cnt = azd.gather_counters([cnt])                  # (replaces GameResults::add, game.cpp:298-309)
+        cnt["errors"] = int(azd.gather_stats([[errs]])[0][0])
     tot_sims, tot_evals, tot_steps, tot_games, errors = [float(cnt[k]) for k in ("sims", "evals", "steps", "games", "errors")]
     mc.close(); net.close(); env.close()
     # ---- the tree kernels alone: the same search with the null evaluator (uniform prior, value 0: no network launches), so the
     # timed region is k_mcts_begin / k_mcts_sim / k_mcts_finish only.  HBM roofline with SURVEY §8d's per-simulation bytes.
     tree = None
-    if rank == 0:
+    if rank == 0 and with_tree:
         env2 = api.Env(n, rules=rules, device=local, first_game_id=rank * n)
         env2.reset(SEED, stream=sptr)
         mt = api.Mcts(env2, evaluator=api.EVAL_UNIFORM)
@@ -296,7 +324,7 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
         tree = {"sims_per_sec": tc["sims"] / (t_ms * 1e-3), "ms_per_round": t_ms / (t_moves * (sims // K + 2)), "mean_depth": depth,
                 "bytes_per_sim": bytes_per_sim,
                 "roofline": {"bound": "hbm", "achieved": tree_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": tree_gbs / hbm_peak,
-                             "traffic": ncu_traffic("k_mcts_sim"), "peak_source": psrc,
+                             **ncu_traffic("k_mcts_sim"), "peak_source": psrc,
                              "note": "null evaluator (no network): device time of the tree kernels only; algorithmic bytes per simulation = "
                                      "2.9 KB + 328 B x depth (SURVEY 8d), depth measured (path_nodes counter); one warp per game, so "
                                      "%d games give %d warps: latency-bound, not bandwidth-bound" % (n, n)},
@@ -309,14 +337,14 @@ def run_selfplay(args, api, torch, dist, rank, world, local, barrier):
     achieved_tf = nn_launch_positions * nn_flops_per_position(blocks) / (dev_ms * 1e-3) / 1e12
     return dict(metric="mcts_sims_per_sec", value=tot_sims / (dev_ms * 1e-3), unit="sims/s", ms_per_step=dev_ms / steps, steps=steps,
                 nn_evals_per_sec=tot_evals / (dev_ms * 1e-3), selfplay_env_steps_per_sec=tot_steps / (dev_ms * 1e-3),
-                config={"workload": "configs[2]: batched self-play, %d games x %d MCTS sims/move per GPU, %s, "
+                config={"workload": "%s: batched self-play, %d games x %d MCTS sims/move per GPU, %s, "
                                     "%d-block graph, random-init weights (seed 1234), bf16 tcgen05 forward, %d moves per step"
-                                    % (n, sims, "T=1 semantics (one leaf per game per batch)" if K == 1 else
+                                    % (label, n, sims, "T=1 semantics (one leaf per game per batch)" if K == 1 else
                                        "%d concurrent descents per tree with the active_N rule (leaf batch = %d)" % (K, n * K),
                                        blocks, moves_per_step),
                             "games_per_gpu": n, "sims_per_move": sims, "blocks": blocks, "concurrent_descents": K},
                 roofline={"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
-                          "traffic": ncu_traffic("k_nn_conv_tc3"), "peak_source": src + " (sustained cuBLAS bf16)",
+                          **ncu_traffic("k_nn_conv_tc3"), "peak_source": src + " (sustained cuBLAS bf16)",
                           "executed_frac": achieved_tf * 49.0 / 42.0 / tf_peak,
                           "note": "conventional FLOPs/position (0.4981 G for 5 blocks) x positions pushed through the tower / whole-step device "
                                   "time (tree kernels, encode and heads included in the time); the 49-row board layout executes 49/42 of "
@@ -344,16 +372,15 @@ def run_play(args, api, torch, rank, local):
     arena = api.Arena(mc, api.OPPONENT_SCRIPT, mirror_games=True)
     arena.play(min(games, 2 * min(slots, 64)), SEED + 7, stream=sptr)          # warm-up match
     torch.cuda.synchronize()
-    # the match is a chain of small launches with one host read-back per tick, so its time follows the host's wake-up latency and
-    # the GPU's clock ramp (measured 215..586 games/s for the same match on the same code): the same match twice, the faster one
+    # the match is a chain of small launches with one host read-back per tick: the same match three times, the MEDIAN is reported
     ms_all = []
-    for _ in range(2):
+    for _ in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         r = arena.play(games, SEED, stream=sptr)
         e1.record(stream); torch.cuda.synchronize()
         ms_all.append(e0.elapsed_time(e1))
-    ms = min(ms_all)
+    ms = sorted(ms_all)[len(ms_all) // 2]
     arena.close(); mc.close(); net.close(); env.close()
     return dict(metric="play_games_per_sec", value=r["count"] / (ms * 1e-3), unit="games/s", ms=ms, ms_runs=ms_all,
                 az_sims_per_sec=r["az_sims"] / (ms * 1e-3), az_moves=r["az_moves"], opponent_turns=r["opponent_turns"],
@@ -432,10 +459,16 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
-    dist = None
+    dist, azd = None, None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the product's own multi-GPU entry points (az_dist_*, NCCL): rank 0's communicator id travels over the launcher's channel
+        idt = torch.zeros(api.DIST_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(api.Dist.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, src=0)
+        azd = api.Dist(world_size=world, rank=rank, unique_id=bytes(idt.cpu().numpy().tobytes()), device=local)
 
     def barrier():
         if dist is not None:
@@ -528,11 +561,20 @@ def run_ours(args):
     if dist is not None:
         from alphazero_risk_b200 import dist as azdist
         dev_ms, e2e_ms, wall_ms = azdist.max_over_ranks([dev_ms, e2e_ms, wall_ms], dist)
-        cnt = azdist.reduce_counters(dict(cnt, errors=0), dist)
+        cnt = azd.gather_counters([cnt])                  # az_dist_gather_counters (GameResults::add over the ranks)
 
     mcts_line = None
     if not args.no_selfplay:
-        mcts_line = run_selfplay(args, api, torch, dist, rank, world, local, barrier)
+        mcts_line = run_selfplay(args, api, torch, dist, azd, rank, world, local, barrier)
+    # BASELINE configs[4]'s per-GPU shape (16384 games x 800 simulations, one move after one warm-up move) and the CMake-default
+    # 20-block graph at configs[2]'s shape: sub-lines of the same JSON line, at every N
+    cfg5_line = blocks20_line = None
+    if not args.no_selfplay and args.cfg5_games > 0:
+        cfg5_line = run_selfplay(args, api, torch, dist, azd, rank, world, local, barrier, label="configs[4] per-GPU shape", with_tree=False,
+                                 shape=(args.cfg5_games, args.cfg5_sims, args.blocks, 1, 1, 1))
+    if not args.no_selfplay and args.blocks20:
+        blocks20_line = run_selfplay(args, api, torch, dist, azd, rank, world, local, barrier, label="configs[2] shape, CMake-default graph",
+                                     with_tree=False, shape=(args.sp_games, args.sp_sims, 20, 1, 2, 1))
 
     play_line = None
     if args.play_games >= 2 and rank == 0 and world == 1:
@@ -544,6 +586,19 @@ def run_ours(args):
 
     if rank == 0:
         hbm_peak, _, src = measured_peaks()
+        env_traffic = ncu_traffic("k_env_rollout")
+        if env_traffic["traffic"] is not None:
+            env_traffic["dram_achieved"] = env_traffic["traffic"] / (dev_ms / args.steps * 1e-3) / 1e9        # GB/s really moved
+        cap, why = ncu_capture("k_env_rollout")
+        if cap is not None and "issue_active_pct" in cap:
+            # the roofline that can still move: thread-instructions issued per cycle against 4 schedulers x 32 lanes per SM
+            ia, lanes = cap["issue_active_pct"] / 100.0, cap["lanes_per_inst"]
+            env_issue = {"bound": "issue", "issue_slots_busy": ia, "active_lanes_per_instruction": lanes, "lanes": 32,
+                         "frac": ia * lanes / 32.0, "warps_active_pct": cap.get("warps_active_pct"), "capture": cap.get("capture"),
+                         "note": "ncu --set full of this binary's k_env_rollout (sources hash-checked): fraction of the SM's lane-issue "
+                                 "capacity doing game work = issue slots busy x active lanes / 32; 65536 games are only 13.8 warps per SM"}
+        else:
+            env_issue = {"bound": "issue", "frac": None, "stale": why}
         total_steps = n * S * args.steps * world
         value = total_steps / (dev_ms * 1e-3)
         kernel_ms = dev_ms / args.steps
@@ -552,11 +607,14 @@ def run_ours(args):
                     ms_per_step=kernel_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
                     config=dict(env_config(n, S), l2="256 MiB flush between timed iterations",
                                 sharding="games by contiguous global id, no data-path collective"),
-                    roofline={"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                              "traffic": ncu_traffic("k_env_rollout"), "peak_source": src,
-                              "note": "algorithmic 330 B/step x games x moves per launch / CUDA-event time of k_env_rollout; the state "
-                                      "stays on chip between the moves of one launch (traffic = the ncu DRAM bytes of one launch: the "
-                                      "64 B/game SoA state read once), so this is an issue-bound kernel, not a DRAM-bound one"},
+                    roofline=dict({"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                                   "algorithmic_bytes_per_launch": ENV_BYTES_PER_STEP * n * S, "peak_source": src,
+                                   "note": "achieved = ALGORITHMIC bytes (330 B/step x games x moves per launch, SURVEY 8d) / CUDA-event time of "
+                                           "k_env_rollout, as the metric contract asks; it is NOT the kernel's DRAM rate: the state stays on chip "
+                                           "for the moves of a launch (traffic = ncu DRAM bytes of one launch, dram_achieved = traffic / time), "
+                                           "so the kernel is bound by instruction issue / latency — see issue_roofline"},
+                                  **env_traffic),
+                    issue_roofline=env_issue,
                     e2e={"value": e2e_games * S * e2e_steps * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": e2e_games * 160,
                          "d2h_bytes_per_step": e2e_games * 160 + 64 * n_sh, "steps": e2e_steps,
                          "note": "%d host threads x %d games, each: import State images (pinned host) -> 512-move rollout -> export images + "
@@ -566,6 +624,10 @@ def run_ours(args):
         if mcts_line is not None:
             line["mcts"] = mcts_line
             line["gpu_launches"] += mcts_line["gpu_launches"]
+        for key, sub in (("cfg5", cfg5_line), ("blocks20", blocks20_line)):
+            if sub is not None:
+                line[key] = sub
+                line["gpu_launches"] += sub["gpu_launches"]
         if play_line is not None:
             line["play"] = play_line
         if train_line is not None:
@@ -577,6 +639,8 @@ def run_ours(args):
                 mcts_line["cpu_baseline"] = cpu_selfplay_baseline(args.sp_sims, 10.0)
         print(json.dumps(line))
     env.close()
+    if azd is not None:
+        azd.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -598,6 +662,9 @@ def main():
     ap.add_argument("--sp-steps", type=int, default=4, help="max timed self-play steps")
     ap.add_argument("--sp-descents", type=int, default=1, help="az_rules.concurrent_descents for the self-play measurement")
     ap.add_argument("--blocks", type=int, default=5)
+    ap.add_argument("--cfg5-games", type=int, default=16384, help="games per GPU of the configs[4] sub-line (0 skips it)")
+    ap.add_argument("--cfg5-sims", type=int, default=800)
+    ap.add_argument("--no-blocks20", dest="blocks20", action="store_false", help="skip the 20-block (CMake default graph) sub-line")
     ap.add_argument("--train-batch", type=int, default=512, help="training-step measurement batch (SETTINGS.BATCH_SIZE); 0 skips it")
     ap.add_argument("--play-games", type=int, default=1000, help="configs[0] match size (--cg); 0 skips it")
     args = ap.parse_args()

@@ -306,6 +306,39 @@ AZ_API int az_arena_destroy(az_arena* arena);
 /* plays 2 * floor(n_games / 2) games (pairs, like the reference) over the env's slots; seed fixes the Philox contract */
 AZ_API int az_arena_play(az_arena* arena, uint64_t n_games, uint64_t seed, az_arena_results* h_out, void* stream);
 
+/* ---------------------------------------------------------------- multi-GPU: NCCL over NVLink / NVSwitch, never inside a search
+   Games shard over GPUs by contiguous global id (first_game_id of az_env_create) and never migrate; every GPU holds a full copy of
+   the network.  The only exchanges are the two below.  NCCL is loaded at run time (libnccl.so.2); without it az_dist_init* fail
+   with AZ_ERR_NOT_READY and the rest of the library works unchanged.
+   Process models: az_dist_init = ONE process drives n GPUs, the reference's model (AlphaZeroCluster::initGpus, neural_network/
+   alphazero_gpu_cluster.cpp:147-158; rank i = devices[i], n local members); az_dist_init_rank = one process per GPU (one local
+   member; rank 0 creates the id with az_dist_unique_id and ships its AZ_DIST_ID_BYTES bytes to the other ranks by any side
+   channel).  Arrays indexed "per local member" have az_dist_local_count() entries, in member order. */
+typedef struct az_dist az_dist;
+#define AZ_DIST_ID_BYTES 128
+AZ_API int az_dist_nccl_version(int* version);
+AZ_API int az_dist_init(int n_devices, const int* devices /* NULL = 0 .. n-1 */, az_dist** out);
+AZ_API int az_dist_unique_id(uint8_t* id128);
+AZ_API int az_dist_init_rank(int world_size, int rank, const uint8_t* id128, int device, az_dist** out);
+AZ_API int az_dist_destroy(az_dist* dist);
+AZ_API int az_dist_world_size(const az_dist* dist);
+AZ_API int az_dist_local_count(const az_dist* dist);
+AZ_API int az_dist_rank(const az_dist* dist, int local_index);
+/* AlphaZeroNNGroup::train's hand-off of the trained model to the group's copies on the other GPUs (alphazero_gpu_cluster.cpp:221-231
+   writes a temporary checkpoint file and reloads it on every other GPU): ncclBroadcast of root_rank's variables (weights and
+   BatchNorm moving statistics, fp32, device to device) into nn[i] of every member.  The optimizer slots stay with the trainer
+   (az_nn_copy_state moves them too, inside one process).  Collective: every rank must call it. */
+AZ_API int az_dist_broadcast_weights(az_dist* dist, az_nn* const* nn, int n_local, int root_rank);
+/* GameResults::add over the per-thread results after thread::join (game/game.cpp:298-309): n 64-bit counters per member,
+   h_local = [n_local][n]; h_sum = [n] totals over every rank (ncclAllReduce), h_per_rank = [world][n] (ncclAllGather); either
+   output may be NULL.  Collective.  The typed forms sum az_counters (az_env_counters / az_mcts_counters) and az_arena_results
+   (az_arena_play) field by field. */
+AZ_API int az_dist_gather_stats(az_dist* dist, const uint64_t* h_local, int n, uint64_t* h_sum, uint64_t* h_per_rank);
+AZ_API int az_dist_gather_counters(az_dist* dist, const az_counters* h_local, az_counters* h_total);
+AZ_API int az_dist_gather_results(az_dist* dist, const az_arena_results* h_local, az_arena_results* h_total);
+/* every rank has arrived and the earlier device work of its members is complete */
+AZ_API int az_dist_barrier(az_dist* dist);
+
 #ifdef __cplusplus
 }
 #endif
