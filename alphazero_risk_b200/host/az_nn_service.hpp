@@ -289,6 +289,9 @@ class AlphaZeroClusterT {
 public:
     explicit AlphaZeroClusterT(int precision = AZ_NN_BF16, int defaultBlocks = 5) : precision_(precision), defaultBlocks_(defaultBlocks) { printf("Creating AZ Cluster\n"); }
     void initGpus(int numberOfGpus) { gpus_ = numberOfGpus; nnPerGpu_.assign(numberOfGpus, 0); printf("Initializing gpus: %d\n", numberOfGpus); }
+    // the reference's signature (alphazero_gpu_cluster.h:104, called as nnCluster->initGpus(nnCluster, SETTINGS.NUMBER_OF_GPUS),
+    // src/alphazero_risk.cpp:7): the self pointer its AlphaZeroGPU objects keep is not needed here
+    template <class Self> void initGpus(const std::shared_ptr<Self>&, int numberOfGpus) { initGpus(numberOfGpus); }
     static int blocksFromGraphPath(const std::string& path, int dflt)
     {
         size_t dot = path.rfind(".pb"), us = path.rfind('_');

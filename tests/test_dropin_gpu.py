@@ -73,3 +73,29 @@ def test_config1_play_az_vs_script_through_reference_game_loop(ref):
     assert count == 8 and az + script + draw == 8
     print("config-1 shape: 8 games AZ(16 sims, T=2, random-init 5-block net on B200) vs ScriptPlayer: az %d script %d draw %d in %.1f s"
           % (az, script, draw, secs.value))
+
+
+MAIN = os.path.join(ROOT, "oracle", "_ref", "AlphaZero_risk")
+
+
+def test_reference_main_runs_config0_verbatim(tmp_path):
+    """BASELINE configs[0] verbatim: the reference's OWN program — main(), settings.h command line, executePlay, GameGroup::playGames
+    with one host thread per game, AlphaZeroPlayer / AlphaZeroMCTS with 2 search threads per tree, ScriptPlayer, its own rng.h —
+    compiled unmodified (oracle/ref/build_ref_main.sh) against the B200 network through the NN facade adapter, run as
+    `AlphaZero_risk -m play --mcts=16 --cg=<n>` and read from the result lines it prints (src/alphazero_risk.cpp:46)."""
+    import re
+    import subprocess
+    if not os.path.exists(MAIN):
+        pytest.skip("oracle/_ref/AlphaZero_risk not built (needs /root/reference at build time)")
+    (tmp_path / "log").mkdir()                     # LOG.init / Settings::init write log/*.txt relative to the working directory
+    games = 64
+    out = subprocess.run([MAIN, "-m", "play", "--mcts=16", "--cg=%d" % games], cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    m = re.search(r"Games: (\d+)\s+Draws:(\d+)\s+Player 1:(\d+)\s+Player 2:(\d+)", out.stdout)
+    assert m, out.stdout[-2000:]
+    count, draws, p1, p2 = [int(v) for v in m.groups()]
+    assert count == games and draws + p1 + p2 == games
+    assert "Starting program with GPUs: 1" in out.stdout and "MCTS simulations 16" in out.stdout
+    assert (tmp_path / "checkpoints" / "latest-checkpoint.bin.index").exists()      # AlphaZeroNN::loadCheckpoint: missing -> init + save
+    assert (tmp_path / "log" / "settings.txt").exists()
+    print("AlphaZero_risk -m play --mcts=16 --cg=%d on B200: AlphaZero %d, ScriptPlayer %d, draws %d" % (games, p1, p2, draws))
