@@ -58,11 +58,16 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
 
 // raw 3x3 convolution of the training step on the tower kernel (az_nn_tc.cu): fp32 [n * 42][256] in, fp32 HWIO device weights
 // [9][256][256] (flip = 1: the data gradient's kernel), fp32 [n * 42][256] out; bf16 operands, fp32 accumulation
-#define AZ_TC_HALO 8                   // zero rows in front of the first board of the 49-row chunked layout (az_nn_tc.cu: TC_HALO)
+// The chunked bf16 board layout of the tensor-core kernels: [channel chunk of 8][row][8 channels], AZ_TC_RPB rows per board —
+// cell (y, x) at row y*6 + x, then six zero rows.  Six is the minimum: a vertical tap reaches 6 rows up or down, and the seventh row a
+// diagonal tap would reach (the previous board's cell (6,5), the next board's cell (0,0)) is exactly a cell the x-masked operand
+// copy of that tap zeroes (az_nn_tc.cu).  42 of 48 rows carry data (the first version had 49 rows; 56 before the masked copies).
+#define AZ_TC_RPB 48
+#define AZ_TC_HALO 8                   // zero rows in front of the first board (az_nn_tc.cu: TC_HALO)
 struct AzTcConvScratch {
     int cap_boards = 0, r_alloc = 0, max_pairs = 0, n_sm = 148, dz_boards = 0;
-    std::vector<__nv_bfloat16*> a49;    // per tower layer: the layer's activation in the 49-row chunked layout (written by the fused BN kernel)
-    __nv_bfloat16* d_in = nullptr;      // [32][r_alloc][8], 49 rows per board: the tensor being convolved / the weight gradient's activation
+    std::vector<__nv_bfloat16*> a_rpb;    // per tower layer: the layer's activation in the chunked layout (written by the fused BN kernel)
+    __nv_bfloat16* d_in = nullptr;      // [32][r_alloc][8], AZ_TC_RPB rows per board: the tensor being convolved / the weight gradient's activation
     __nv_bfloat16* d_in3 = nullptr;     // [3][32][r_alloc][8]: a layer's dz — plain, x = 0 cells zeroed, x = 5 cells zeroed
     uint8_t* d_w = nullptr;             // one layer's packed stages
 };
@@ -76,6 +81,6 @@ int az_tc_dgrad_prepared(AzTcConvScratch* sc, int n, const float* d_w, float* d_
 // the fused BatchNorm kernels of az_nn_train.cu write the chunked copies themselves: per-layer activation buffers, the dz target
 int az_tc_layers_reserve(AzTcConvScratch* sc, int n, int layers);
 int az_tc_dz_target(AzTcConvScratch* sc, int n, cudaStream_t s, __nv_bfloat16** d_dz3, size_t* var_stride_u4);
-int az_tc_conv_raw49(AzTcConvScratch* sc, const __nv_bfloat16* in49, int n, const float* d_w, int flip, float* d_out, cudaStream_t s);
-int az_tc_wgrad49(AzTcConvScratch* sc, const __nv_bfloat16* a49, int n, float* d_part, int max_splits, int* splits_out, cudaStream_t s);
+int az_tc_conv_raw_rpb(AzTcConvScratch* sc, const __nv_bfloat16* in_rpb, int n, const float* d_w, int flip, float* d_out, cudaStream_t s);
+int az_tc_wgrad_rpb(AzTcConvScratch* sc, const __nv_bfloat16* a_rpb, int n, float* d_part, int max_splits, int* splits_out, cudaStream_t s);
 void az_tc_conv_raw_release(AzTcConvScratch* sc);

@@ -9,10 +9,10 @@
 //   * activations are bf16, stored [channel chunk of 8][row][8 channels] (16-byte row cells), i.e. the canonical K-major
 //     SWIZZLE_NONE UMMA operand layout with an 8-row core-matrix stride of 128 B: a row shift is just a different
 //     16-byte-aligned start address in the shared-memory descriptor, so tap (ky, kx) is the SAME operand tile, moved.
-//   * 49-row board layout (default): cell (y, x) -> row y*6 + x, then seven zero rows.  The zero rows are the bottom border of the
+//   * 48-row board layout (AZ_TC_RPB, az_nn.cuh): cell (y, x) -> row y*6 + x, then six zero rows.  The zero rows are the bottom border of the
 //     board and the top border of the next one; the left / right border comes from two masked copies of the operand built in
 //     shared memory (kx = 0 taps read the copy with the x = 5 cells zeroed, kx = 2 taps the copy with the x = 0 cells zeroed).
-//     42 of 49 rows carry data.
+//     42 of 48 rows carry data.
 //   * weights are pre-packed per layer into contiguous pipeline stages of K = 32 input channels of one tap:
 //     [half of the output channels][chunk][128 out][8] = 8 KB per CTA of a pair (tower), [chunk][256 out][8] (stem), each fetched
 //     with one cp.async.bulk.
@@ -63,17 +63,19 @@ struct AzTcState {
     uint8_t* d_wpacked = nullptr;                              // [2*blocks] x 1.18 MB tower weights, then the 72 KB stem weights
     int max_pairs = 74;                                        // CTA pairs of k_nn_conv_tc3 the device holds at once
     uint8_t* d_wpacked3 = nullptr;                             // tower weights for k_nn_conv_tc3: [K group][tap][half]
-    size_t in_var_stride = 0;                                  // elements between the three copies of the encoded input (49-row layout)
+    size_t in_var_stride = 0;                                  // elements between the three copies of the encoded input (three-copy layout)
     float* d_scale = nullptr; float* d_shift = nullptr;        // [2*blocks][256] folded BN, then [256] (7 used) for the stem's row BN
+    float4* d_head_w = nullptr;                                // [256] (pi0, pi1, v, 0): the heads' 1x1 convolutions, per input channel
+    float4* d_head_z = nullptr;                                // [cap_boards * 42] (pi0, pi1, v, -) per board cell, written by the last tower layer
 };
 
 #include "az_tc_ptx.cuh"
 
-// Board layout: cell (y, x) -> row y*6 + x, seven zero rows behind the 42 cells (49 rows per board).  The zero rows serve as top /
+// Board layout: cell (y, x) -> row y*6 + x, six zero rows behind the 42 cells (48 rows per board).  The zero rows serve as top /
 // bottom border; the left / right border comes from two masked copies of the operand: taps with kx = 0 read the copy whose x = 5
 // cells are zero, taps with kx = 2 the copy whose x = 0 cells are zero (what they would wrongly pick up from the neighbouring
-// board row is exactly such a cell).
-#define TC_RPB 49
+// board row — or, for the diagonal taps at a board's first / last cell, from the neighbouring BOARD — is exactly such a cell).
+#define TC_RPB AZ_TC_RPB
 __device__ __forceinline__ bool tc_row_valid(int r, int n_boards) { int b = r / TC_RPB, p = r - b * TC_RPB; return b < n_boards && p < 42; }
 __device__ __forceinline__ int tc_row_y(int r) { return (r % TC_RPB) / 6; }
 __device__ __forceinline__ int tc_tap_shift(int tap) { return (tap / 3 - 1) * 6 + (tap % 3 - 1); }
@@ -257,8 +259,8 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
 #define TC2_STAGES 8
 #define TC2_STAGE_BYTES (4 * 128 * 16)                       // K = 32 (4 chunks) x 128 output channels
 
-// ---------------------------------------------------------------- tower conv3x3 on a CTA pair, 49-row board layout
-// tcgen05 cta_group::2, half of the weights per CTA (above), on the 49-row layout: the A operand
+// ---------------------------------------------------------------- tower conv3x3 on a CTA pair, 48-row board layout
+// tcgen05 cta_group::2, half of the weights per CTA (above), on the 48-row layout: the A operand
 // exists in three copies in shared memory (plain / x=5 cells zeroed / x=0 cells zeroed, see tc_tap_variant), so it no longer fits
 // twice.  The K loop is therefore turned inside out — K group (32 channels) outer, the nine taps inner — and the operand lives in a
 // RING of K groups: a group's slot is refilled for the next tile as soon as its nine taps have retired.
@@ -273,15 +275,25 @@ k_nn_conv_tc(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ w
 #define T3_VAR_BYTES (4 * TC_A_ROWS * 16)                    // one copy of one K group: 4 chunks x 144 rows x 16 B = 9216
 #define T3_SLOT_BYTES (3 * T3_VAR_BYTES)
 #define T3_SMEM_BYTES (T3_G * T3_SLOT_BYTES + TC2_STAGES * TC2_STAGE_BYTES + 2 * 256 * 4 + 64 * 8 + 16)
+#define T3_HEAD_BYTES (256 * 16)                             // T3_HEADS: (pi0, pi1, v, -) head weights per input channel
 
-// RAW = true (training step, az_tc_conv_raw): the epilogue stores the fp32 accumulators of the real board cells to out32
+// MODE = T3_RAW (training step, az_tc_conv_raw): the epilogue stores the fp32 accumulators of the real board cells to out32
 // [board * 42 + cell][256] row-major — no BatchNorm fold, residual, ReLU or bf16 rounding; scale / shift / skip / out are unused.
-template <bool RAW>
+// MODE = T3_HEADS (the LAST tower layer of a forward): the activation is not stored at all.  Each epilogue thread holds one board
+// cell's 256 output channels anyway, so it applies the two heads' 1x1 convolutions (pi: 2 channels, v: 1 channel,
+// build_graph.py:76-90) on the spot — on the bf16-rounded activation, in the channel order the separate head kernel used, so the
+// sums are bit-identical to reading the stored activation back — and writes (pi0, pi1, v) per cell to out32 (as float4
+// [board * 42 + cell]).  Saves the layer's 57 MB store and the head kernel's 103 MB read per 4096 boards.
+#define T3_ACT 0
+#define T3_RAW 1
+#define T3_HEADS 2
+template <int MODE>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ wpacked3, const float* __restrict__ scale,
               const float* __restrict__ shift, const __nv_bfloat16* __restrict__ skip, __nv_bfloat16* __restrict__ out,
-              int n_boards, int r_alloc, int n_tiles, float* __restrict__ out32)
+              int n_boards, int r_alloc, int n_tiles, float* __restrict__ out32, const float4* __restrict__ head_w)
 {
+    constexpr bool RAW = MODE == T3_RAW;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sA = smem;                                   // T3_G x T3_SLOT_BYTES
     uint8_t* sB = smem + T3_G * T3_SLOT_BYTES;            // TC2_STAGES x TC2_STAGE_BYTES
@@ -298,6 +310,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
     uint64_t* bar_w_empty = bars + 36 + TC2_STAGES;
     uint64_t* bar_pw_full = bars + 36 + 2 * TC2_STAGES;   // leader only
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 64);
+    float4* s_hw = reinterpret_cast<float4*>(smem + T3_SMEM_BYTES);      // T3_HEADS only (the launch adds T3_HEAD_BYTES)
 
     // let the next tower layer (launched with the programmatic-serialization attribute) be scheduled onto SMs as this grid's
     // CTAs exit: its barrier / TMEM set-up then overlaps this layer's last wave; it reads nothing of ours before its pdl_wait()
@@ -316,6 +329,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
     };
 
     if (!RAW) for (int i = threadIdx.x; i < 256; i += T3_THREADS) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+    if (MODE == T3_HEADS) for (int i = threadIdx.x; i < 256; i += T3_THREADS) s_hw[i] = head_w[i];
     if (threadIdx.x == 0) {
         for (int g = 0; g < T3_G; ++g) { mbar_init(bar_a_full + g, 1); mbar_init(bar_a_ready + g, 1); mbar_init(bar_pa_ready + g, 1); mbar_init(bar_a_empty + g, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full + b, 1); mbar_init(bar_acc_empty + b, 8); }
@@ -369,7 +383,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
             uint8_t* base = sA + (size_t)slot * T3_SLOT_BYTES;
             for (int idx = lane; idx < 4 * TC_A_ROWS; idx += 32) {
                 const int row = idx % TC_A_ROWS;
-                const int p = (row0 + row + 49) % 49;                             // row0 + row >= -8
+                const int p = (row0 + row + TC_RPB) % TC_RPB;                     // row0 + row >= -8
                 const int x = p < 42 ? p % 6 : -1;
                 const uint4 cell = *reinterpret_cast<const uint4*>(base + (size_t)idx * 16);
                 const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -432,8 +446,8 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
                 if (tile < n_tiles) {
                     const int r = tile * TC_TILE_ROWS + q4 * 32 + lane;
                     const bool valid = tc_row_valid(r, n_boards);
-                    const int bb = r / 49;
-                    float* orow = out32 + ((size_t)bb * 42 + (size_t)(r - bb * 49)) * 256;
+                    const int bb = r / TC_RPB;
+                    float* orow = out32 + ((size_t)bb * 42 + (size_t)(r - bb * TC_RPB)) * 256;
 #pragma unroll 1
                     for (int c4 = 0; c4 < TC_CHUNKS / 4; ++c4) {
                         uint32_t v[32];
@@ -452,6 +466,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
                 const bool valid = tc_row_valid(r, n_boards);
                 const size_t cell0 = ((size_t)TC_HALO + r) * 8;
                 const size_t cstride = (size_t)r_alloc * 8;
+                float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f;             // T3_HEADS: the cell's three head sums
                 // four channel chunks (32 accumulator columns) per TMEM load; the residual cells of the NEXT four are in flight meanwhile
                 uint4 skq[4];
                 if (skip) {
@@ -487,9 +502,19 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
                         for (int e = 0; e < 4; ++e) {
                             float x0 = valid ? fmaxf(f[2 * e], 0.0f) : 0.0f, x1 = valid ? fmaxf(f[2 * e + 1], 0.0f) : 0.0f;
                             o2[e] = __floats2bfloat162_rn(x0, x1);
+                            if (MODE == T3_HEADS) {                // same values, same order as a head kernel reading the stored bf16 cell
+                                const float2 xv = __bfloat1622float2(o2[e]);
+                                const float4 wa = s_hw[c * 8 + 2 * e], wb = s_hw[c * 8 + 2 * e + 1];
+                                h0 = fmaf(xv.x, wa.x, h0); h1 = fmaf(xv.x, wa.y, h1); h2 = fmaf(xv.x, wa.z, h2);
+                                h0 = fmaf(xv.y, wb.x, h0); h1 = fmaf(xv.y, wb.y, h1); h2 = fmaf(xv.y, wb.z, h2);
+                            }
                         }
-                        *reinterpret_cast<uint4*>(out + cell0 + (size_t)c * cstride) = o;
+                        if (MODE != T3_HEADS) *reinterpret_cast<uint4*>(out + cell0 + (size_t)c * cstride) = o;
                     }
+                }
+                if (MODE == T3_HEADS && valid) {
+                    const int bb = r / TC_RPB;
+                    reinterpret_cast<float4*>(out32)[(size_t)bb * 42 + (size_t)(r - bb * TC_RPB)] = make_float4(h0, h1, h2, 0.0f);
                 }
             }
             tc_fence_before();
@@ -509,7 +534,7 @@ k_nn_conv_tc3(const __nv_bfloat16* __restrict__ in, const uint8_t* __restrict__ 
 
 // ---------------------------------------------------------------- input packing + heads on the padded bf16 layout
 // fp32 [n][42][13] -> bf16 [2 chunks][r_alloc][8] (channels 13..15 = 0); thread = board cell
-// (49-row layout: three copies var_stride elements apart — plain, x = 5 cells zeroed, x = 0 cells zeroed — for the stem's taps)
+// (three copies var_stride elements apart — plain, x = 5 cells zeroed, x = 0 cells zeroed — for the stem's taps)
 __global__ void __launch_bounds__(256) k_nn_pack_input_tc(const float* __restrict__ x, int n, __nv_bfloat16* __restrict__ out, int r_alloc,
                                                            size_t var_stride)
 {
@@ -608,43 +633,23 @@ __device__ __forceinline__ float warp_sum_tc(float v)
     return v;
 }
 
-// policy + value heads for HB boards per block (the head weights, 60 KB, are read once per block instead of once per board)
-#define HB 6     // 6 boards = 252 cells: one pass of the 256 threads over the 1x1 convolutions
-__global__ void __launch_bounds__(256) k_nn_heads_tc(const __nv_bfloat16* __restrict__ act, int n, int r_alloc, AzHeadParams hp,
-                                                      float* __restrict__ policy, float* __restrict__ value)
+// policy + value heads for HB boards per block, from the per-cell 1x1-convolution sums the last tower layer's epilogue wrote
+// (k_nn_conv_tc3<T3_HEADS>): BatchNorm + ReLU per cell, the dense layers, softmax / tanh (build_graph.py:76-90)
+#define HB 6     // 6 boards = 252 cells: one pass of the 256 threads
+__global__ void __launch_bounds__(256) k_nn_heads_tail(const float4* __restrict__ head_z, int n, AzHeadParams hp,
+                                                        float* __restrict__ policy, float* __restrict__ value)
 {
     __shared__ float s_pi[HB][84], s_v[HB][42], s_logit[HB][44], s_red[HB][8];
     const int b0 = blockIdx.x * HB, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nb = n - b0 < HB ? n - b0 : HB;
-    // 1x1 convolutions (pi: 2 channels, v: 1 channel) + BatchNorm + ReLU.  One thread per board cell walks the 32 channel chunks:
-    // a warp reads 32 consecutive 16-byte cells of one chunk (512 contiguous bytes) per step and needs no reduction
-    // (lane = chunk with a warp reduction per cell read 16 bytes out of every 32-byte sector and ran 56 us for 4096 boards).
-    __shared__ float4 s_w[256];                    // (pi0, pi1, v, -) per input channel: one 16-byte broadcast load per channel
-    for (int c = threadIdx.x; c < 256; c += 256) s_w[c] = make_float4(hp.pi_w[c * 2], hp.pi_w[c * 2 + 1], hp.v_w[c], 0.0f);
-    __syncthreads();
     const float sc0 = hp.bn_pi[0] * rsqrtf(hp.bn_pi[6] + AZ_NN_BN_EPS), sc1 = hp.bn_pi[1] * rsqrtf(hp.bn_pi[7] + AZ_NN_BN_EPS);
     const float scv = hp.bn_v[0] * rsqrtf(hp.bn_v[3] + AZ_NN_BN_EPS);
     for (int i = threadIdx.x; i < nb * 42; i += 256) {
         const int bl = i / 42, p = i - bl * 42;
-        const int row = (b0 + bl) * TC_RPB + p;
-        const __nv_bfloat16* cellp = act + ((size_t)TC_HALO + row) * 8;
-        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
-#pragma unroll 4
-        for (int c = 0; c < TC_CHUNKS; ++c) {
-            const uint4 cell = __ldg(reinterpret_cast<const uint4*>(cellp + (size_t)c * r_alloc * 8));
-            const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&cell);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 xv = __bfloat1622float2(c2[e]);
-                const int ch = c * 8 + 2 * e;
-                const float4 wa = s_w[ch], wb = s_w[ch + 1];
-                s0 = fmaf(xv.x, wa.x, s0); s1 = fmaf(xv.x, wa.y, s1); s2 = fmaf(xv.x, wa.z, s2);
-                s0 = fmaf(xv.y, wb.x, s0); s1 = fmaf(xv.y, wb.y, s1); s2 = fmaf(xv.y, wb.z, s2);
-            }
-        }
-        s_pi[bl][p * 2 + 0] = fmaxf((s0 - hp.bn_pi[4]) * sc0 + hp.bn_pi[2], 0.0f);
-        s_pi[bl][p * 2 + 1] = fmaxf((s1 - hp.bn_pi[5]) * sc1 + hp.bn_pi[3], 0.0f);
-        s_v[bl][p] = fmaxf((s2 - hp.bn_v[2]) * scv + hp.bn_v[1], 0.0f);
+        const float4 z = __ldg(head_z + (size_t)(b0 + bl) * 42 + p);
+        s_pi[bl][p * 2 + 0] = fmaxf((z.x - hp.bn_pi[4]) * sc0 + hp.bn_pi[2], 0.0f);
+        s_pi[bl][p * 2 + 1] = fmaxf((z.y - hp.bn_pi[5]) * sc1 + hp.bn_pi[3], 0.0f);
+        s_v[bl][p] = fmaxf((z.z - hp.bn_v[2]) * scv + hp.bn_v[1], 0.0f);
     }
     __syncthreads();
     // dense 84 -> 43 (policy logits): thread = output, weights reused over the block's boards
@@ -731,11 +736,14 @@ static void pack_conv_pair(const float* w, __nv_bfloat16* dst, bool kb_outer = t
                         }
 }
 
+// heads != NULL: the last layer — no activation out, per-cell head sums to head_z instead (T3_HEADS)
 static cudaError_t launch_conv_pair3(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w3, const float* scale, const float* shift,
-                                     const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles)
+                                     const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles,
+                                     const float4* head_w = nullptr, float4* head_z = nullptr)
 {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES; cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(T3_THREADS); cfg.stream = s;
+    cfg.dynamicSmemBytes = T3_SMEM_BYTES + (head_w ? T3_HEAD_BYTES : 0);
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -743,7 +751,11 @@ static cudaError_t launch_conv_pair3(int grid, cudaStream_t s, const __nv_bfloat
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 2;
-    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<false>, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles, (float*)nullptr);
+    if (head_w)
+        return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<T3_HEADS>, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles,
+                                  reinterpret_cast<float*>(head_z), head_w);
+    return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<T3_ACT>, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles, (float*)nullptr,
+                              (const float4*)nullptr);
 }
 
 // persistent launch of the stem convolution
@@ -797,20 +809,22 @@ int az_nn_tc_prepare(az_nn* nn)
         AZ_CUDA(cudaMalloc(&tc->d_scale, scale.size() * sizeof(float)));
         AZ_CUDA(cudaMalloc(&tc->d_shift, shift.size() * sizeof(float)));
         AZ_CUDA((cudaFuncSetAttribute(k_nn_conv_tc<2, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcShape<2>::smem_bytes(3))));
-        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
+        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3<T3_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
+        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3<T3_HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES + T3_HEAD_BYTES));
+        AZ_CUDA(cudaMalloc(&tc->d_head_w, 256 * sizeof(float4)));
         int dev = 0, sms = 148;
         AZ_CUDA(cudaGetDevice(&dev));
         AZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         tc->n_sm = sms;
         {   // CTA pairs the device can hold at once
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(sms / 2 * 2)); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES;
+            cfg.gridDim = dim3((unsigned)(sms / 2 * 2)); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES + T3_HEAD_BYTES;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             int nc = 0;
-            AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc3<false>, &cfg));
+            AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc3<T3_HEADS>, &cfg));
             tc->max_pairs = nc < sms / 2 ? nc : sms / 2;
             if (tc->max_pairs < 1) { az_set_error("the device cannot hold one CTA pair of the tower kernel (sm_100a thread-block clusters needed)"); return AZ_ERR_CUDA; }
         }
@@ -819,20 +833,28 @@ int az_nn_tc_prepare(az_nn* nn)
     AZ_CUDA(cudaMemcpy(tc->d_wpacked3, packed3.data(), packed3.size(), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_scale, scale.data(), scale.size() * sizeof(float), cudaMemcpyHostToDevice));
     AZ_CUDA(cudaMemcpy(tc->d_shift, shift.data(), shift.size() * sizeof(float), cudaMemcpyHostToDevice));
+    {   // the heads' 1x1 convolutions: pi/kernel [1][1][256][2], v/kernel [1][1][256][1] -> (pi0, pi1, v, 0) per input channel
+        const float* pw = az_nn_host_var(nn, "pi/kernel");
+        const float* vw = az_nn_host_var(nn, "v/kernel");
+        if (!pw || !vw) { az_set_error("missing head variable"); return AZ_ERR_INVALID_ARG; }
+        std::vector<float4> hw(256);
+        for (int c = 0; c < 256; ++c) hw[(size_t)c] = make_float4(pw[c * 2], pw[c * 2 + 1], vw[c], 0.0f);
+        AZ_CUDA(cudaMemcpy(tc->d_head_w, hw.data(), hw.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
     return AZ_OK;
 }
 
 // ---------------------------------------------------------------- raw 3x3 convolution for the training step (az_nn_train.cu)
 // out[r][co] = sum_{t,ci} in[nb(r,t)][ci] * w[t][ci][co]           (flip = 0: forward)
 // out[r][ci] = sum_{t,co} in[nb(r,t)][co] * w[8-t][ci][co]         (flip = 1: data gradient)
-// on the tower kernel: bf16 operands, fp32 accumulation, fp32 result [n * 42][256].  The fp32 source goes into the 49-row chunked
+// on the tower kernel: bf16 operands, fp32 accumulation, fp32 result [n * 42][256].  The fp32 source goes into the 48-row chunked
 // bf16 layout, the fp32 HWIO weights (which change every step) are packed into the kernel's stage order on the device.
 
-// fp32 [n * 42][256] -> bf16 [32 chunks][r_alloc][8] at rows TC_HALO + board * 49 + cell; padding rows are never written (zero from the
+// fp32 [n * 42][256] -> bf16 [32 chunks][r_alloc][8] at rows TC_HALO + board * TC_RPB + cell; padding rows are never written (zero from the
 // allocation).  Block = 32 source rows x 32 chunks through shared memory: contiguous reads along a row, contiguous writes along a chunk.
 // variants = 3: two more copies var_stride_u4 apart — cells with x = 0 zeroed, cells with x = 5 zeroed (the weight gradient masks the
 // OUTPUT cell of a tap that would reach over the left / right board border).
-__global__ void __launch_bounds__(256) k_tc_chunk49(const float* __restrict__ src, int rows, int r_alloc, __nv_bfloat16* __restrict__ out,
+__global__ void __launch_bounds__(256) k_tc_chunk_rpb(const float* __restrict__ src, int rows, int r_alloc, __nv_bfloat16* __restrict__ out,
                                                      int variants, size_t var_stride_u4)
 {
     __shared__ uint4 tile[32][33];
@@ -855,7 +877,7 @@ __global__ void __launch_bounds__(256) k_tc_chunk49(const float* __restrict__ sr
         const int cl = j >> 5, rl = j & 31, r = r0 + rl;
         if (r < rows) {
             const int bb = r / 42, p = r - bb * 42, x = p % 6;
-            const size_t at = (size_t)cl * r_alloc + TC_HALO + (size_t)bb * 49 + p;
+            const size_t at = (size_t)cl * r_alloc + TC_HALO + (size_t)bb * TC_RPB + p;
             const uint4 v = tile[rl][cl], zero = make_uint4(0u, 0u, 0u, 0u);
             o[at] = v;
             if (variants == 3) { o[var_stride_u4 + at] = x == 0 ? zero : v; o[2 * var_stride_u4 + at] = x == 5 ? zero : v; }
@@ -865,11 +887,11 @@ __global__ void __launch_bounds__(256) k_tc_chunk49(const float* __restrict__ sr
 
 // ---------------------------------------------------------------- weight gradient of a 256 -> 256 convolution, no unrolled operand
 //   dW[t][ci][co] = sum over board cells r of a[nb(r, t)][ci] * dz[r][co]
-// as nine GEMMs D_t[ci][co] = A_t^T . dZ with K = rows of the 49-row layout.  Both operands are read straight from the chunked bf16
+// as nine GEMMs D_t[ci][co] = A_t^T . dZ with K = rows of the 48-row layout.  Both operands are read straight from the chunked bf16
 // buffers [chunk][row][8]: seen with the row index as K they are MN-MAJOR UMMA operands (8 K-rows x 16 bytes of MN per core matrix,
 // K groups 128 B apart = LBO, chunks = SBO apart), so the transposition costs nothing, and tap t is the A operand read `shift(t)` rows
 // further on — a 16-byte-aligned address offset.  Top / bottom borders come from the zero rows between boards, left / right borders
-// from the x-masked copies of dz (k_tc_chunk49 variants).
+// from the x-masked copies of dz (k_tc_chunk_rpb variants).
 // One CTA = one tap x one K split: M = 2 x 128 input channels (two accumulators, all 512 TMEM columns), N = 256, 64 K-rows per stage.
 // The kernel is bound by L2 -> SM delivery (116 FLOP per operand byte; measured 255 MB into the SMs in 64 us = 4 TB/s, tensor pipe
 // active 21 %), so the three taps of one kernel COLUMN (same dx: same dz copy, activation rows 6 apart) run as a CLUSTER of three
@@ -887,7 +909,7 @@ __global__ void __launch_bounds__(256) k_tc_chunk49(const float* __restrict__ sr
 #define WG_IDESC (TC_IDESC | (1u << 15) | (1u << 16))         // A and B MN-major
 
 __global__ void __launch_bounds__(192, 1)
-k_tc_wgrad(const __nv_bfloat16* __restrict__ a49, const __nv_bfloat16* __restrict__ dz49, size_t var_stride_bytes, int r_alloc, int kb_total,
+k_tc_wgrad(const __nv_bfloat16* __restrict__ a_rpb, const __nv_bfloat16* __restrict__ dz_rpb, size_t var_stride_bytes, int r_alloc, int kb_total,
            int kb_per_split, float* __restrict__ part)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -926,8 +948,8 @@ k_tc_wgrad(const __nv_bfloat16* __restrict__ a49, const __nv_bfloat16* __restric
         // ---- loaders: lane l owns chunk l of both operands; the CTA with rank l % 3 requests it for the whole cluster
         const int var = kx == 0 ? 1 : (kx == 2 ? 2 : 0);
         const bool mine = (uint32_t)(lane % 3) == crank;
-        const uint8_t* a8 = reinterpret_cast<const uint8_t*>(a49) + ((size_t)lane * r_alloc + TC_HALO - 6 + (kx - 1)) * 16;
-        const uint8_t* b8 = reinterpret_cast<const uint8_t*>(dz49) + (size_t)var * var_stride_bytes + ((size_t)lane * r_alloc + TC_HALO) * 16;
+        const uint8_t* a8 = reinterpret_cast<const uint8_t*>(a_rpb) + ((size_t)lane * r_alloc + TC_HALO - 6 + (kx - 1)) * 16;
+        const uint8_t* b8 = reinterpret_cast<const uint8_t*>(dz_rpb) + (size_t)var * var_stride_bytes + ((size_t)lane * r_alloc + TC_HALO) * 16;
         for (int i = 0; i < nkb; ++i) {
             const int s = i % WG_STAGES, k = i / WG_STAGES;
             if (k > 0) mbar_wait_cluster(bar_empty + s, (uint32_t)((k - 1) & 1));
@@ -1010,7 +1032,7 @@ __global__ void __launch_bounds__(256) k_tc_pack_pair(const float* __restrict__ 
 int az_tc_conv_raw_reserve(AzTcConvScratch* sc, int n)
 {
     if (sc->max_pairs == 0) {
-        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
+        AZ_CUDA(cudaFuncSetAttribute(k_nn_conv_tc3<T3_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
         AZ_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
         int dev = 0, sms = 148;
         AZ_CUDA(cudaGetDevice(&dev));
@@ -1022,7 +1044,7 @@ int az_tc_conv_raw_reserve(AzTcConvScratch* sc, int n)
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int nc = 0;
-        AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc3<true>, &cfg));
+        AZ_CUDA(cudaOccupancyMaxActiveClusters(&nc, k_nn_conv_tc3<T3_RAW>, &cfg));
         sc->max_pairs = nc < sms / 2 ? nc : sms / 2;
         sc->n_sm = sms;
         if (sc->max_pairs < 1) { az_set_error("the device cannot hold one CTA pair of the tower kernel"); return AZ_ERR_CUDA; }
@@ -1030,9 +1052,9 @@ int az_tc_conv_raw_reserve(AzTcConvScratch* sc, int n)
     }
     if (n <= sc->cap_boards) return AZ_OK;
     cudaFree(sc->d_in); cudaFree(sc->d_in3); sc->d_in = nullptr; sc->d_in3 = nullptr; sc->cap_boards = 0;
-    for (__nv_bfloat16* p : sc->a49) cudaFree(p);
-    sc->a49.clear();
-    int tiles = (n * 49 + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
+    for (__nv_bfloat16* p : sc->a_rpb) cudaFree(p);
+    sc->a_rpb.clear();
+    int tiles = (n * TC_RPB + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     tiles += tiles & 1;
     const int r_alloc = tiles * TC_TILE_ROWS + 2 * TC_HALO;
     const size_t bytes = (size_t)TC_CHUNKS * r_alloc * 16;
@@ -1044,11 +1066,11 @@ int az_tc_conv_raw_reserve(AzTcConvScratch* sc, int n)
     return AZ_OK;
 }
 
-static int conv_raw_launch(AzTcConvScratch* sc, const __nv_bfloat16* in49, int n, const float* d_w, int flip, float* d_out, cudaStream_t s)
+static int conv_raw_launch(AzTcConvScratch* sc, const __nv_bfloat16* in_rpb, int n, const float* d_w, int flip, float* d_out, cudaStream_t s)
 {
     k_tc_pack_pair<<<(8 * 9 * 2 * 4 * 128) / 256, 256, 0, s>>>(d_w, flip, reinterpret_cast<__nv_bfloat16*>(sc->d_w));
     AZ_CUDA(cudaGetLastError());
-    const int tiles = (n * 49 + TC_TILE_ROWS - 1) / TC_TILE_ROWS, pitems = (tiles + 1) / 2;
+    const int tiles = (n * TC_RPB + TC_TILE_ROWS - 1) / TC_TILE_ROWS, pitems = (tiles + 1) / 2;
     const int pgrid = 2 * (pitems < sc->max_pairs ? pitems : sc->max_pairs);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)pgrid); cfg.blockDim = dim3(T3_THREADS); cfg.dynamicSmemBytes = T3_SMEM_BYTES; cfg.stream = s;
@@ -1056,8 +1078,8 @@ static int conv_raw_launch(AzTcConvScratch* sc, const __nv_bfloat16* in49, int n
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    AZ_CUDA(cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<true>, in49, (const uint8_t*)sc->d_w, (const float*)nullptr, (const float*)nullptr,
-                               (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, n, sc->r_alloc, tiles, d_out));
+    AZ_CUDA(cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<T3_RAW>, in_rpb, (const uint8_t*)sc->d_w, (const float*)nullptr, (const float*)nullptr,
+                               (const __nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, n, sc->r_alloc, tiles, d_out, (const float4*)nullptr));
     return AZ_OK;
 }
 
@@ -1065,9 +1087,9 @@ int az_tc_conv_raw(AzTcConvScratch* sc, const float* d_src, int n, const float* 
 {
     int rc = az_tc_conv_raw_reserve(sc, n); if (rc) return rc;
     const int rows = n * 42;
-    // (boards a larger earlier batch left behind are harmless here: every board's own seven zero rows separate it from its
-    // neighbours, and rows of boards >= n are computed but never stored)
-    k_tc_chunk49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_src, rows, sc->r_alloc, sc->d_in, 1, 0);
+    // (boards a larger earlier batch left behind are harmless here: every board's own six zero rows plus the x-masked operand
+    // copies separate it from its neighbours, and rows of boards >= n are computed but never stored)
+    k_tc_chunk_rpb<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_src, rows, sc->r_alloc, sc->d_in, 1, 0);
     return conv_raw_launch(sc, sc->d_in, n, d_w, flip, d_out, s);
 }
 
@@ -1080,7 +1102,7 @@ int az_tc_dz_prepare(AzTcConvScratch* sc, const float* d_dz, int n, cudaStream_t
     if (n < sc->dz_boards) AZ_CUDA(cudaMemsetAsync(sc->d_in3, 0, 3 * bytes, s));
     sc->dz_boards = n;
     const int rows = n * 42;
-    k_tc_chunk49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_dz, rows, sc->r_alloc, sc->d_in3, 3, bytes / 16);
+    k_tc_chunk_rpb<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_dz, rows, sc->r_alloc, sc->d_in3, 3, bytes / 16);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }
@@ -1095,11 +1117,11 @@ int az_tc_layers_reserve(AzTcConvScratch* sc, int n, int layers)
 {
     int rc = az_tc_conv_raw_reserve(sc, n); if (rc) return rc;
     const size_t bytes = (size_t)TC_CHUNKS * sc->r_alloc * 16;
-    while ((int)sc->a49.size() < layers) {
+    while ((int)sc->a_rpb.size() < layers) {
         __nv_bfloat16* p = nullptr;
         AZ_CUDA(cudaMalloc(&p, bytes));
         AZ_CUDA(cudaMemset(p, 0, bytes));
-        sc->a49.push_back(p);
+        sc->a_rpb.push_back(p);
     }
     return AZ_OK;
 }
@@ -1114,22 +1136,22 @@ int az_tc_dz_target(AzTcConvScratch* sc, int n, cudaStream_t s, __nv_bfloat16** 
     return AZ_OK;
 }
 
-int az_tc_conv_raw49(AzTcConvScratch* sc, const __nv_bfloat16* in49, int n, const float* d_w, int flip, float* d_out, cudaStream_t s)
+int az_tc_conv_raw_rpb(AzTcConvScratch* sc, const __nv_bfloat16* in_rpb, int n, const float* d_w, int flip, float* d_out, cudaStream_t s)
 {
-    return conv_raw_launch(sc, in49, n, d_w, flip, d_out, s);
+    return conv_raw_launch(sc, in_rpb, n, d_w, flip, d_out, s);
 }
 
 // weight gradient partials [splits][9 * 256][256] from the prepared dz and the layer's fp32 input activation; returns the split count
 int az_tc_wgrad_prepared(AzTcConvScratch* sc, const float* d_a, int n, float* d_part, int max_splits, int* splits_out, cudaStream_t s)
 {
     const int rows = n * 42;
-    k_tc_chunk49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_a, rows, sc->r_alloc, sc->d_in, 1, 0);
-    return az_tc_wgrad49(sc, sc->d_in, n, d_part, max_splits, splits_out, s);
+    k_tc_chunk_rpb<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(d_a, rows, sc->r_alloc, sc->d_in, 1, 0);
+    return az_tc_wgrad_rpb(sc, sc->d_in, n, d_part, max_splits, splits_out, s);
 }
 
-int az_tc_wgrad49(AzTcConvScratch* sc, const __nv_bfloat16* a49, int n, float* d_part, int max_splits, int* splits_out, cudaStream_t s)
+int az_tc_wgrad_rpb(AzTcConvScratch* sc, const __nv_bfloat16* a_rpb, int n, float* d_part, int max_splits, int* splits_out, cudaStream_t s)
 {
-    const int kb_total = (n * 49 + WG_KROWS - 1) / WG_KROWS;                   // 64-row K blocks that hold board rows
+    const int kb_total = (n * TC_RPB + WG_KROWS - 1) / WG_KROWS;                   // 64-row K blocks that hold board rows
     int want = sc->n_sm / 9; if (want > max_splits) want = max_splits; if (want > kb_total) want = kb_total; if (want < 1) want = 1;
     const int per = (kb_total + want - 1) / want, splits = (kb_total + per - 1) / per;      // no empty split
     const size_t bytes = (size_t)TC_CHUNKS * sc->r_alloc * 16;
@@ -1140,7 +1162,7 @@ int az_tc_wgrad49(AzTcConvScratch* sc, const __nv_bfloat16* a49, int n, float* d
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 3; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        AZ_CUDA(cudaLaunchKernelEx(&cfg, k_tc_wgrad, a49, (const __nv_bfloat16*)sc->d_in3, bytes, sc->r_alloc, kb_total, per, d_part));
+        AZ_CUDA(cudaLaunchKernelEx(&cfg, k_tc_wgrad, a_rpb, (const __nv_bfloat16*)sc->d_in3, bytes, sc->r_alloc, kb_total, per, d_part));
     }
     *splits_out = splits;
     return AZ_OK;
@@ -1149,7 +1171,7 @@ int az_tc_wgrad49(AzTcConvScratch* sc, const __nv_bfloat16* a49, int n, float* d
 void az_tc_conv_raw_release(AzTcConvScratch* sc)
 {
     cudaFree(sc->d_in); cudaFree(sc->d_in3); cudaFree(sc->d_w);
-    for (__nv_bfloat16* p : sc->a49) cudaFree(p);
+    for (__nv_bfloat16* p : sc->a_rpb) cudaFree(p);
     *sc = AzTcConvScratch();
 }
 
@@ -1159,6 +1181,7 @@ void az_nn_tc_release(az_nn* nn)
     AzTcState* tc = nn->tc;
     for (int i = 0; i < 3; ++i) cudaFree(tc->d_act[i]);
     cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_wpacked3); cudaFree(tc->d_scale); cudaFree(tc->d_shift);
+    cudaFree(tc->d_head_w); cudaFree(tc->d_head_z);
     delete tc;
     nn->tc = nullptr;
 }
@@ -1168,6 +1191,8 @@ static int tc_reserve(AzTcState* tc, int n)
     if (n <= tc->cap_boards) return AZ_OK;
     for (int i = 0; i < 3; ++i) { cudaFree(tc->d_act[i]); tc->d_act[i] = nullptr; }
     cudaFree(tc->d_in); tc->d_in = nullptr;
+    cudaFree(tc->d_head_z); tc->d_head_z = nullptr;
+    AZ_CUDA(cudaMalloc(&tc->d_head_z, sizeof(float4) * (size_t)n * 42));
     int tiles = (n * TC_RPB + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
     tiles += tiles & 1;                                       // the pair kernel reads whole tile pairs
     int r_alloc = tiles * TC_TILE_ROWS + 2 * TC_HALO;
@@ -1211,12 +1236,13 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
             const __nv_bfloat16* src = h ? tc->d_act[tmp] : tc->d_act[cur];
             const __nv_bfloat16* res = h ? tc->d_act[cur] : nullptr;
             __nv_bfloat16* dst = h ? tc->d_act[nxt] : tc->d_act[tmp];
+            const bool last = L == layers - 1;              // the last layer feeds the heads directly: no activation store
             AZ_CUDA(launch_conv_pair3(pgrid, s, src, tc->d_wpacked3 + (size_t)L * TC_LAYER_BYTES, tc->d_scale + L * 256, tc->d_shift + L * 256, res, dst, n,
-                                      tc->r_alloc, tiles));
+                                      tc->r_alloc, tiles, last ? tc->d_head_w : nullptr, last ? tc->d_head_z : nullptr));
         }
         int o = cur; cur = nxt; nxt = o;
     }
-    k_nn_heads_tc<<<(n + HB - 1) / HB, 256, 0, s>>>(tc->d_act[cur], n, tc->r_alloc, az_nn_head_params(nn), d_policy, d_value);
+    k_nn_heads_tail<<<(n + HB - 1) / HB, 256, 0, s>>>(tc->d_head_z, n, az_nn_head_params(nn), d_policy, d_value);
     AZ_CUDA(cudaGetLastError());
     return AZ_OK;
 }

@@ -318,16 +318,16 @@ __global__ void __launch_bounds__(256) k_tr_add_masked(float* __restrict__ dst, 
 
 // ---------------------------------------------------------------- tensor-core mode: BatchNorm passes that also emit the bf16 operands
 // Block = 32 rows x 256 channels, thread = (row, 8-channel chunk) four times over; the chunk values go through shared memory so that the
-// 49-row chunked bf16 layout of the tower kernel ([chunk][AZ_TC_HALO + board * 49 + cell][8]) is written in contiguous runs.
+// chunked bf16 board layout of the tower kernel ([chunk][AZ_TC_HALO + board * AZ_TC_RPB + cell][8]) is written in contiguous runs.
 __device__ __forceinline__ void ld8(const float* __restrict__ p, float (&v)[8])
 {
     const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-// k_tr_bn_apply49: a = relu(gamma * (z - mean) * invstd + beta [+ skip]) as fp32 AND as the next convolution's operand.
-__global__ void __launch_bounds__(256) k_tr_bn_apply49(const float* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ gamma,
+// k_tr_bn_apply_rpb: a = relu(gamma * (z - mean) * invstd + beta [+ skip]) as fp32 AND as the next convolution's operand.
+__global__ void __launch_bounds__(256) k_tr_bn_apply_rpb(const float* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, const float* __restrict__ skip, float* __restrict__ a,
-                                                        int rows, int stem, __nv_bfloat16* __restrict__ a49, int r_alloc)
+                                                        int rows, int stem, __nv_bfloat16* __restrict__ a_rpb, int r_alloc)
 {
     __shared__ uint4 tile[32][33];
     const int r0 = blockIdx.x * 32;
@@ -364,18 +364,18 @@ __global__ void __launch_bounds__(256) k_tr_bn_apply49(const float* __restrict__
         }
     }
     __syncthreads();
-    uint4* o4 = reinterpret_cast<uint4*>(a49);
+    uint4* o4 = reinterpret_cast<uint4*>(a_rpb);
     for (int j = threadIdx.x; j < 1024; j += 256) {
         const int cl = j >> 5, rl = j & 31, r = r0 + rl;
-        if (r < rows) { const int bb = r / 42; o4[(size_t)cl * r_alloc + AZ_TC_HALO + (size_t)bb * 49 + (r - bb * 42)] = tile[rl][cl]; }
+        if (r < rows) { const int bb = r / 42; o4[(size_t)cl * r_alloc + AZ_TC_HALO + (size_t)bb * AZ_TC_RPB + (r - bb * 42)] = tile[rl][cl]; }
     }
 }
 
-// k_tr_bn_bwd49: dz = gamma * invstd * (g - c1 - xhat * c2), g = dout * [a > 0], written as the data gradient's / weight gradient's
+// k_tr_bn_bwd_rpb: dz = gamma * invstd * (g - c1 - xhat * c2), g = dout * [a > 0], written as the data gradient's / weight gradient's
 // bf16 operand: plain, cells with x = 0 zeroed, cells with x = 5 zeroed (var_stride_u4 apart); the fp32 copy only if dz32 != NULL.
-__global__ void __launch_bounds__(256) k_tr_bn_bwd49(const float* __restrict__ z, const float* __restrict__ dout, const float* __restrict__ a,
+__global__ void __launch_bounds__(256) k_tr_bn_bwd_rpb(const float* __restrict__ z, const float* __restrict__ dout, const float* __restrict__ a,
                                                       const float* __restrict__ stats, const float* __restrict__ gamma, float* __restrict__ dz32,
-                                                      int rows, __nv_bfloat16* __restrict__ dz49, int r_alloc, size_t var_stride_u4)
+                                                      int rows, __nv_bfloat16* __restrict__ dz_rpb, int r_alloc, size_t var_stride_u4)
 {
     __shared__ uint4 tile[32][33];
     const int r0 = blockIdx.x * 32;
@@ -409,12 +409,12 @@ __global__ void __launch_bounds__(256) k_tr_bn_bwd49(const float* __restrict__ z
         }
     }
     __syncthreads();
-    uint4* o4 = reinterpret_cast<uint4*>(dz49);
+    uint4* o4 = reinterpret_cast<uint4*>(dz_rpb);
     for (int j = threadIdx.x; j < 1024; j += 256) {
         const int cl = j >> 5, rl = j & 31, r = r0 + rl;
         if (r < rows) {
             const int bb = r / 42, p = r - bb * 42, x = p % 6;
-            const size_t at = (size_t)cl * r_alloc + AZ_TC_HALO + (size_t)bb * 49 + p;
+            const size_t at = (size_t)cl * r_alloc + AZ_TC_HALO + (size_t)bb * AZ_TC_RPB + p;
             const uint4 v = tile[rl][cl], zero = make_uint4(0u, 0u, 0u, 0u);
             o4[at] = v; o4[var_stride_u4 + at] = x == 0 ? zero : v; o4[2 * var_stride_u4 + at] = x == 5 ? zero : v;
         }
@@ -856,11 +856,11 @@ static int train_reserve(az_nn* nn, AzTrainState* t, int n)
 
 // one raw 3x3 convolution out[r][256] = conv(in[r][cin], w[9][cin][256]) (flip: the data-gradient kernel w[8-t] transposed)
 static int conv_any(az_nn* nn, AzTrainState* t, const float* in, int n, int cin, const float* w, int flip, float* out, cudaStream_t s,
-                    const __nv_bfloat16* in49 = nullptr)
+                    const __nv_bfloat16* in_rpb = nullptr)
 {
     if (t->precision == AZ_NN_BF16 && cin == TR_CH) {       // implicit GEMM on the tower kernel (no unrolled operand in HBM)
         if (flip && t->dz_prepared) { t->dz_prepared = false; return az_tc_dgrad_prepared(&t->conv, n, w, out, s); }
-        if (!flip && in49) return az_tc_conv_raw49(&t->conv, in49, n, w, 0, out, s);
+        if (!flip && in_rpb) return az_tc_conv_raw_rpb(&t->conv, in_rpb, n, w, 0, out, s);
         return az_tc_conv_raw(&t->conv, in, n, w, flip, out, s);
     }
     if (t->precision == AZ_NN_BF16) {                       // the 13-channel stem: chunked im2col + k_tc_gemm
@@ -902,8 +902,8 @@ static int bn_forward(az_nn* nn, AzTrainState* t, int L, int n, const float* ski
     k_tr_stats_final<<<8, 256, 0, s>>>(t->d_part, stem ? 7 : TR_CH, stem ? (double)n * 6 * TR_CH : (double)rows, 0, st,
                                        dvar(nn, bn + "/moving_mean"), dvar(nn, bn + "/moving_variance"), nullptr, nullptr);
     if (tr_tower(t) && L + 1 < 2 * nn->blocks + 1)          // the next 256-channel convolution (and its weight gradient) read the chunked bf16 copy
-        k_tr_bn_apply49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(t->z[(size_t)L], st, dvar(nn, bn + "/gamma"), dvar(nn, bn + "/beta"), skip,
-                                                                  t->a[(size_t)L], rows, stem, t->conv.a49[(size_t)L], t->conv.r_alloc);
+        k_tr_bn_apply_rpb<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(t->z[(size_t)L], st, dvar(nn, bn + "/gamma"), dvar(nn, bn + "/beta"), skip,
+                                                                  t->a[(size_t)L], rows, stem, t->conv.a_rpb[(size_t)L], t->conv.r_alloc);
     else
         k_tr_bn_apply<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(t->z[(size_t)L], st, dvar(nn, bn + "/gamma"), dvar(nn, bn + "/beta"), skip, t->a[(size_t)L], total, stem);
     AZ_CUDA(cudaGetLastError());
@@ -924,7 +924,7 @@ static int bn_backward(az_nn* nn, AzTrainState* t, int L, int n, const float* do
     if (tr_tower(t) && L >= 1) {                            // dz goes straight into the operand buffers of k_tc_wgrad and the data gradient; no fp32 copy
         __nv_bfloat16* dz3 = nullptr; size_t vs = 0;
         int rc = az_tc_dz_target(&t->conv, n, s, &dz3, &vs); if (rc) return rc;
-        k_tr_bn_bwd49<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(t->z[(size_t)L], dout, t->a[(size_t)L], st, dvar(nn, bn + "/gamma"), nullptr, rows,
+        k_tr_bn_bwd_rpb<<<(unsigned)((rows + 31) / 32), 256, 0, s>>>(t->z[(size_t)L], dout, t->a[(size_t)L], st, dvar(nn, bn + "/gamma"), nullptr, rows,
                                                                 dz3, t->conv.r_alloc, vs);
         t->dz_prepared = true;
     } else
@@ -937,10 +937,10 @@ static int conv_wgrad(az_nn* nn, AzTrainState* t, int L, int n, const float* in,
 {
     if (tr_tower(t) && cin == TR_CH) {
         // nine GEMMs over the board rows with both operands read in place from the chunked bf16 buffers (k_tc_wgrad): dz was written
-        // by k_tr_bn_bwd49, the layer's input activation by k_tr_bn_apply49 during the forward pass
+        // by k_tr_bn_bwd_rpb, the layer's input activation by k_tr_bn_apply_rpb during the forward pass
         AZ_REQUIRE(t->dz_prepared && L >= 1, "weight gradient before its dz");
         int splits = 1;
-        int rc = az_tc_wgrad49(&t->conv, t->conv.a49[(size_t)L - 1], n, t->d_wpart, TR_WG_SPLITS, &splits, s); if (rc) return rc;
+        int rc = az_tc_wgrad_rpb(&t->conv, t->conv.a_rpb[(size_t)L - 1], n, t->d_wpart, TR_WG_SPLITS, &splits, s); if (rc) return rc;
         return az_tg_reduce(t->d_wpart, splits, 9 * TR_CH, 9 * TR_CH, gvar(nn, t, tr_conv_name(L) + "/kernel"), s);
     }
     if (t->precision == AZ_NN_BF16) {                          // the stem: dW[t*cin + ci][co] = im2col(in)^T . dz, K = board cells, split over K
@@ -977,7 +977,7 @@ static int train_step_dev(az_nn* nn, const float* d_x, const float* d_tp, const 
     rc = bn_forward(nn, t, 0, n, nullptr, s); if (rc) return rc;
     for (int L = 1; L < layers; ++L) {
         rc = conv_any(nn, t, t->a[(size_t)L - 1], n, TR_CH, dvar(nn, tr_conv_name(L) + "/kernel"), 0, t->z[(size_t)L], s,
-                      tr_tower(t) ? t->conv.a49[(size_t)L - 1] : nullptr); if (rc) return rc;
+                      tr_tower(t) ? t->conv.a_rpb[(size_t)L - 1] : nullptr); if (rc) return rc;
         rc = bn_forward(nn, t, L, n, (L & 1) ? nullptr : t->a[(size_t)L - 2], s); if (rc) return rc;      // 2b adds the block input
     }
     const float* act = t->a[(size_t)layers - 1];

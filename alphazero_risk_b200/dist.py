@@ -1,5 +1,9 @@
-"""Multi-GPU plumbing of the self-play path: one process per GPU, games sharded by contiguous global id,
-torch.distributed (NCCL on the GPU box, gloo in the CPU tests) for exactly two exchanges, both OUTSIDE the search loop:
+"""Multi-GPU plumbing of the self-play path: one process per GPU, games sharded by contiguous global id.
+
+The product's own entry points for the two exchanges are az_dist_* in libaz_b200.so (csrc/az_dist.cu, NCCL; api.Dist) — that is
+what bench.py uses on the GPU box.  This module holds the sharding rule, the max-over-ranks reduction of timings, and the same two
+exchanges over torch.distributed, which also runs on gloo so that the N > 1 host logic is testable without a GPU
+(tests/test_dist_cpu.py).  Both exchanges are OUTSIDE the search loop:
 
   * broadcast_weights — rank 0's fp32 weight blob to every rank; replaces the reference's checkpoint-file hand-off
     (nn[0] saves temp.bin, the other GPUs restore it: neural_network/alphazero_gpu_cluster.cpp:221-231);

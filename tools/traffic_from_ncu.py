@@ -43,7 +43,7 @@ def main():
     for pair in a.pairs:
         kernel, path = pair.split("=", 1)
         rows = list(csv.reader(open(path)))
-        hdr, data = rows[0], [r for r in rows[1:] if r and r[0].split("<")[0] == kernel]
+        hdr, data = rows[0], [r for r in rows[1:] if r and r[0].replace("void ", "").split("<")[0].strip() == kernel]
         if not data:
             raise SystemExit("no launch of %s in %s" % (kernel, path))
         ent = {"capture": path, "launches": len(data), "launch": launch.get(kernel, "")}
