@@ -713,15 +713,18 @@ extern "C" int az_mcts_clear(az_mcts* mc, void* stream)
     return AZ_OK;
 }
 
-static int evaluate_leaves(az_mcts* mc, cudaStream_t s)
+// k_used = descents per tree whose leaves this batch holds: K for a simulation round, 1 for the root round (setRootState uses
+// descent slot 0 only, so the other K - 1 slots of every game would be evaluated for nothing)
+static int evaluate_leaves(az_mcts* mc, cudaStream_t s, int k_used)
 {
     if (mc->evaluator != EVAL_NN) return AZ_OK;
     MctsDev& d = mc->d;
-    const int ns = d.n * d.K;                            // every descent slot goes through the network (slot = j * n + game)
+    const int ns = d.n * d.K;                            // descent slots (slot = j * n + game): the stride of the SoA leaf arrays
+    const int nb = d.n * k_used;                         // the first k_used * n of them go through the network
     if (mc->eval_count > 0 && mc->eval_count < d.n) {
         // arena: gather the participating games' leaves, evaluate that batch, scatter the outputs back to their slots
-        const int m = mc->eval_count * d.K;
-        k_mcts_gather_leaves<<<(m * 16 + 255) / 256, 256, 0, s>>>(d.leaf_state, ns, d.n, mc->eval_games, mc->eval_count, d.K, mc->d_leaf_c);
+        const int m = mc->eval_count * k_used;
+        k_mcts_gather_leaves<<<(m * 16 + 255) / 256, 256, 0, s>>>(d.leaf_state, ns, d.n, mc->eval_games, mc->eval_count, k_used, mc->d_leaf_c);
         int rc;
         if (mc->precision == AZ_NN_BF16) {
             rc = az_nn_reserve(mc->nn, ns); if (rc) return rc;
@@ -730,16 +733,16 @@ static int evaluate_leaves(az_mcts* mc, cudaStream_t s)
             rc = az_launch_encode(mc->d_leaf_c, m, mc->d_x, s); if (rc) return rc;
             rc = az_nn_forward_dev(mc->nn, mc->d_x, m, mc->d_pol_c, mc->d_val_c, AZ_NN_FP32, s); if (rc) return rc;
         }
-        k_mcts_scatter_evals<<<(m * 44 + 255) / 256, 256, 0, s>>>(mc->d_pol_c, mc->d_val_c, d.n, mc->eval_games, mc->eval_count, d.K, d.nn_policy, d.nn_value);
+        k_mcts_scatter_evals<<<(m * 44 + 255) / 256, 256, 0, s>>>(mc->d_pol_c, mc->d_val_c, d.n, mc->eval_games, mc->eval_count, k_used, d.nn_policy, d.nn_value);
         AZ_CUDA(cudaGetLastError());
         return AZ_OK;
     }
     if (mc->precision == AZ_NN_BF16) {
         int rc = az_nn_reserve(mc->nn, ns); if (rc) return rc;
-        return az_nn_tc_forward(mc->nn, nullptr, d.leaf_state, ns, d.nn_policy, d.nn_value, s);
+        return az_nn_tc_forward(mc->nn, nullptr, d.leaf_state, nb, d.nn_policy, d.nn_value, s, ns);
     }
-    int rc = az_launch_encode(d.leaf_state, ns, mc->d_x, s); if (rc) return rc;
-    return az_nn_forward_dev(mc->nn, mc->d_x, ns, d.nn_policy, d.nn_value, AZ_NN_FP32, s);
+    int rc = az_launch_encode(d.leaf_state, ns, mc->d_x, s); if (rc) return rc;      // (encodes every slot: the stride of the SoA input is ns)
+    return az_nn_forward_dev(mc->nn, mc->d_x, nb, d.nn_policy, d.nn_value, AZ_NN_FP32, s);
 }
 
 // one AlphaZeroMCTS::simulate (alphazero_mcts.cpp:255-287) for every game, then the move choice
@@ -754,11 +757,11 @@ static int search_once(az_mcts* mc, int extra_all, int pick_mode, int apply_move
     k_mcts_begin<<<grid, MCTS_WARPS * 32, 0, s>>>(d, extra_all);
     k_mcts_sim<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, -1, 1);             // setRootState
     AZ_CUDA(cudaGetLastError());
-    int rc = evaluate_leaves(mc, s); if (rc) return rc;
+    int rc = evaluate_leaves(mc, s, 1); if (rc) return rc;
     for (int i = 0; i < sims / d.K; ++i) {               // rounds of K descents per tree
         k_mcts_sim<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, i, 1);
         AZ_CUDA(cudaGetLastError());
-        rc = evaluate_leaves(mc, s); if (rc) return rc;
+        rc = evaluate_leaves(mc, s, d.K); if (rc) return rc;
     }
     k_mcts_finish<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, pick_mode, apply_move, auto_reset);
     AZ_CUDA(cudaGetLastError());

@@ -53,8 +53,10 @@ void az_nn_train_release(az_nn* nn);        // az_nn_train.cu
 // bf16 tensor-core path (az_nn_tc.cu)
 int az_nn_tc_prepare(az_nn* nn);            // fold BN, pack bf16 weight tiles; called by finalize
 void az_nn_tc_release(az_nn* nn);
-// x: fp32 [n][7][6][13] (or NULL when env_state is given: encode fused into the stem)
-int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, int n, float* d_policy, float* d_value, cudaStream_t s);
+// x: fp32 [n][7][6][13] (or NULL when env_state is given: encode fused into the stem; env_state = SoA words with stride
+// state_stride >= n between words, 0 = n)
+int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, int n, float* d_policy, float* d_value, cudaStream_t s,
+                     int state_stride = 0);
 
 // raw 3x3 convolution of the training step on the tower kernel (az_nn_tc.cu): fp32 [n * 42][256] in, fp32 HWIO device weights
 // [9][256][256] (flip = 1: the data gradient's kernel), fp32 [n * 42][256] out; bf16 operands, fp32 accumulation

@@ -565,14 +565,15 @@ __global__ void __launch_bounds__(256) k_nn_pack_input_tc(const float* __restric
 // (alphazero_nn_data.cpp:165-196, alphazero_nn.cpp:31-67) as k_env_encode computes them (az_env.cu — same expressions, same
 // roundings), rounded to bf16 and written in the layout above without the fp32 [n][42][13] round trip through HBM.
 // One warp per position; lane l packs board cells l and l + 32.
-__global__ void __launch_bounds__(128) k_nn_pack_state_tc(const uint32_t* __restrict__ st, int n, __nv_bfloat16* __restrict__ out, int r_alloc,
-                                                           size_t var_stride)
+// (st = SoA game states, word w of position i at st[w * st_stride + i]; st_stride >= n lets a caller evaluate the first n of more slots)
+__global__ void __launch_bounds__(128) k_nn_pack_state_tc(const uint32_t* __restrict__ st, int n, int st_stride, __nv_bfloat16* __restrict__ out,
+                                                           int r_alloc, size_t var_stride)
 {
     __shared__ uint32_t s_words[4][16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gi = blockIdx.x * 4 + warp;
     if (gi >= n) return;
-    if (lane < 14) s_words[warp][lane] = st[(size_t)lane * n + gi];
+    if (lane < 14) s_words[warp][lane] = st[(size_t)lane * st_stride + gi];
     __syncwarp();
     const uint8_t* land = (const uint8_t*)s_words[warp];
     AzGame g;
@@ -1209,8 +1210,10 @@ static int tc_reserve(AzTcState* tc, int n)
     return AZ_OK;
 }
 
-int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, int n, float* d_policy, float* d_value, cudaStream_t s)
+int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, int n, float* d_policy, float* d_value, cudaStream_t s,
+                     int state_stride)
 {
+    if (state_stride < n) state_stride = n;
     AzTcState* tc = nn->tc;
     if (!tc || !tc->d_wpacked) { az_set_error("network not finalized"); return AZ_ERR_NOT_READY; }
     int rc = tc_reserve(tc, n); if (rc) return rc;
@@ -1223,7 +1226,7 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
     const int grid = tiles < tc->n_sm ? tiles : tc->n_sm;
     const int layers = 2 * nn->blocks;
     int cur = 0, tmp = 1, nxt = 2;
-    if (from_state) k_nn_pack_state_tc<<<(n + 3) / 4, 128, 0, s>>>(d_env_state, n, tc->d_in, tc->r_alloc, tc->in_var_stride);
+    if (from_state) k_nn_pack_state_tc<<<(n + 3) / 4, 128, 0, s>>>(d_env_state, n, state_stride, tc->d_in, tc->r_alloc, tc->in_var_stride);
     else k_nn_pack_input_tc<<<(n * 42 + 255) / 256, 256, 0, s>>>(d_x, n, tc->d_in, tc->r_alloc, tc->in_var_stride);
     AZ_CUDA(cudaGetLastError());
     AZ_CUDA((launch_conv<2, true, 3>(grid, s, tc->d_in, tc->d_wpacked, tc->d_scale + layers * 256, tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n,

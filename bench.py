@@ -333,7 +333,7 @@ def run_selfplay(args, api, torch, dist, azd, rank, world, local, barrier, shape
     if rank != 0:
         return None
     _, tf_peak, src = measured_peaks()
-    nn_launch_positions = n * K * (sims // K + 1) * moves_per_step * steps    # positions pushed through the tower per rank (every descent slot)
+    nn_launch_positions = n * (K * (sims // K) + 1) * moves_per_step * steps  # positions pushed through the tower per rank: n per root round, n * K per simulation round
     achieved_tf = nn_launch_positions * nn_flops_per_position(blocks) / (dev_ms * 1e-3) / 1e12
     return dict(metric="mcts_sims_per_sec", value=tot_sims / (dev_ms * 1e-3), unit="sims/s", ms_per_step=dev_ms / steps, steps=steps,
                 nn_evals_per_sec=tot_evals / (dev_ms * 1e-3), selfplay_env_steps_per_sec=tot_steps / (dev_ms * 1e-3),
@@ -345,9 +345,9 @@ def run_selfplay(args, api, torch, dist, azd, rank, world, local, barrier, shape
                             "games_per_gpu": n, "sims_per_move": sims, "blocks": blocks, "concurrent_descents": K},
                 roofline={"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
                           **ncu_traffic("k_nn_conv_tc3"), "peak_source": src + " (sustained cuBLAS bf16)",
-                          "executed_frac": achieved_tf * 49.0 / 42.0 / tf_peak,
+                          "executed_frac": achieved_tf * 48.0 / 42.0 / tf_peak,
                           "note": "conventional FLOPs/position (0.4981 G for 5 blocks) x positions pushed through the tower / whole-step device "
-                                  "time (tree kernels, encode and heads included in the time); the 49-row board layout executes 49/42 of "
+                                  "time (tree kernels, encode and heads included in the time); the 48-row board layout (42 cells + 6 zero rows per board) executes 48/42 of "
                                   "that (executed_frac); the forward runs at the board's 1 kW power cap (clocks.reasons: sw_power_cap), "
                                   "like the cuBLAS run the peak comes from; traffic = DRAM bytes of one tower-layer launch (ncu)"},
                 clocks=sp_clocks,
