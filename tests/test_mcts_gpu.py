@@ -25,14 +25,15 @@ def bits(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
 
-def run_lockstep(api, n, first, sims, T, play_mode, max_moves, evaluator="pseudo", net=None, oracle_eval=None, K=1, rules_kw=None):
+def run_lockstep(api, n, first, sims, T, play_mode, max_moves, evaluator="pseudo", net=None, oracle_eval=None, K=1, rules_kw=None,
+                 precision=None):
     rules_kw = rules_kw or {}
     rules_o = po.default_rules(mcts_simulations=sims, threads_per_mcts=T, **rules_kw)
     rules_d = api.default_rules(mcts_simulations=sims, threads_per_mcts=T, concurrent_descents=K, **rules_kw)
     env = api.Env(n, rules=rules_d, first_game_id=first)
     env.reset(SEED)
     ev = {"pseudo": api.EVAL_PSEUDO, "uniform": api.EVAL_UNIFORM, "nn": api.EVAL_NN}[evaluator]
-    mc = api.Mcts(env, net=net, evaluator=ev)
+    mc = api.Mcts(env, net=net, evaluator=ev, precision=api.FP32 if precision is None else precision)
     assert mc.simulations() == sims - sims % T
     games = [po.OracleGame(rules_o) for _ in range(n)]
     trees = []
@@ -166,24 +167,25 @@ def test_reference_golden_search_traces(api, golden_dir, name):
     mc.close(); env.close()
 
 
-@pytest.mark.parametrize("K", [1, 3])
-def test_search_with_network_matches_oracle_given_same_outputs(api, K):
-    """evaluator = the fp32 network.  The oracle search calls the SAME network (batch of one, the
-    kernels are batch-invariant) for its leaf evaluations, so both sides see identical outputs."""
+@pytest.mark.parametrize("K,prec", [(1, "fp32"), (3, "fp32"), (2, "bf16"), (4, "bf16")])
+def test_search_with_network_matches_oracle_given_same_outputs(api, K, prec):
+    """evaluator = the network (fp32 path, or the bf16 tcgen05 tower).  The oracle search calls the SAME network (batch of one, the
+    kernels are batch-invariant) for its leaf evaluations, so both sides see identical outputs.  K > 1 with the tensor-core path
+    also covers the root round, which evaluates one descent slot per game out of the K-slot leaf arrays."""
     net = api.Net(blocks=2, seed=1234)
     L = po.oracle_lib()
+    precision = api.FP32 if prec == "fp32" else api.BF16
 
     @C.CFUNCTYPE(None, C.POINTER(po.RoState), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p)
     def evaluator(sp, policy, value, user):
         x = np.zeros(po.INPUT_FLOATS, np.float32)
         L.ro_encode(sp, x)
-        p, v = net.forward(x.reshape(1, -1), api.FP32)
-        for i in range(43):
-            policy[i] = float(p[0, i])
+        p, v = net.forward(x.reshape(1, -1), precision)
+        C.memmove(policy, p.ctypes.data, 43 * 4)
         value[0] = float(v[0])
 
     assert run_lockstep(api, n=5, first=4242, sims=12, T=1, play_mode=False, max_moves=70, evaluator="nn", net=net,
-                        oracle_eval=evaluator, K=K) > 300
+                        oracle_eval=evaluator, K=K, precision=precision) > 300
     net.close()
 
 
