@@ -41,6 +41,10 @@ class AzCounters(C.Structure):
                     path_nodes=int(self.path_nodes))
 
 
+class AzCounters6(C.Structure):
+    _fields_ = [("steps", C.c_uint64), ("games", C.c_uint64), ("draws", C.c_uint64), ("wins", C.c_uint64 * 6)]
+
+
 _lib = None
 
 
@@ -125,6 +129,16 @@ def lib():
         L.az_arena_play.argtypes = [vp, C.c_uint64, C.c_uint64, C.POINTER(AzArenaResults), vp]
         L.az_selfplay_samples.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), vp]
         L.az_samples_write_file.argtypes = [C.c_char_p, vp, C.c_size_t]
+        L.az_env6_create.argtypes = [C.c_int, C.POINTER(AzRules), C.c_int, C.c_uint32, C.POINTER(vp)]
+        L.az_env6_destroy.argtypes = [vp]
+        L.az_env6_reset.argtypes = [vp, C.c_uint64, vp]
+        L.az_env6_rollout.argtypes = [vp, C.c_int, vp]
+        L.az_env6_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.az_env6_step.argtypes = [vp, vp, vp, vp]
+        L.az_env6_query.argtypes = [vp, vp, vp, vp]
+        L.az_env6_export.argtypes = [vp, vp, vp]
+        L.az_env6_import.argtypes = [vp, vp, vp]
+        L.az_env6_counters.argtypes = [vp, C.POINTER(AzCounters6), C.c_int, vp]
         L.az_dist_nccl_version.argtypes = [C.POINTER(C.c_int)]
         L.az_dist_init.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
         L.az_dist_unique_id.argtypes = [vp]
@@ -648,3 +662,63 @@ class Dist:
 
     def barrier(self):
         check(self.L.az_dist_barrier(self.h))
+
+
+ENV6_IMAGE_BYTES = 108
+
+
+class Env6:
+    """n lockstep SIX-PLAYER games (az_env6_*): the configs[3] extension, rules = SIXPLAYER.md, no reference parity"""
+
+    def __init__(self, n_games, rules=None, device=0, first_game_id=0):
+        self.L = lib()
+        self.n = int(n_games)
+        self.rules = rules if rules is not None else default_rules()
+        h = C.c_void_p()
+        check(self.L.az_env6_create(self.n, C.byref(self.rules), device, first_game_id, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.az_env6_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def reset(self, seed, stream=None):
+        check(self.L.az_env6_reset(self.h, int(seed), stream))
+
+    def rollout(self, n_steps, stream=None):
+        check(self.L.az_env6_rollout(self.h, int(n_steps), stream))
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        check(self.L.az_env6_last_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def step(self, action, stream=None):
+        act = np.ascontiguousarray(action, np.uint8)
+        assert act.shape == (self.n,)
+        st = np.empty(self.n, np.int8)
+        check(self.L.az_env6_step(self.h, _ptr(act), _ptr(st), stream))
+        return st
+
+    def query(self, stream=None):
+        v, st = np.empty(self.n, np.uint64), np.empty(self.n, np.int8)
+        check(self.L.az_env6_query(self.h, _ptr(v), _ptr(st), stream))
+        return v, st
+
+    def export(self, stream=None):
+        a = np.empty((self.n, ENV6_IMAGE_BYTES), np.uint8)
+        check(self.L.az_env6_export(self.h, _ptr(a), stream))
+        return a
+
+    def import_images(self, images, stream=None):
+        a = np.ascontiguousarray(images, np.uint8)
+        assert a.shape == (self.n, ENV6_IMAGE_BYTES)
+        check(self.L.az_env6_import(self.h, _ptr(a), stream))
+
+    def counters(self, reset=False, stream=None):
+        c = AzCounters6()
+        check(self.L.az_env6_counters(self.h, C.byref(c), int(reset), stream))
+        return dict(steps=int(c.steps), games=int(c.games), draws=int(c.draws), wins=[int(c.wins[i]) for i in range(6)])

@@ -26,6 +26,7 @@ UNITS = {
     "az_tc_gemm.cu": [],
     "az_nn_train.cu": ["-fmad=false"],   # training step: plain fp32, same roundings whatever the compiler would contract
     "az_ckpt.cpp": [],       # host only: TensorFlow V2 checkpoint bundles
+    "az_env6.cu": ["-fmad=false"],   # six-player extension of the environment (SIXPLAYER.md), integer only
     "az_dist.cu": [],        # NCCL weight broadcast + statistics gather (NCCL itself is dlopen'ed at run time)
 }
 

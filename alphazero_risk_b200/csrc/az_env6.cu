@@ -1,0 +1,594 @@
+// az_env6.cu — the SIX-PLAYER extension of the lockstep Risk environment (BASELINE.json configs[3]) and its az_env6_* C ABI.
+//
+// The reference has no six-player game (PLAYER_COUNT = 2, /root/reference/src/risk_game/state/state.h:13), so this is a
+// throughput-only extension with NO reference parity: its rules are SIXPLAYER.md, its only checker is oracle/risk6_oracle.c
+// (tests/test_env6_gpu.py compares bit for bit).  Everything that has a two-player counterpart follows that counterpart's
+// arithmetic (az_game.cuh) and shares its map tables, neighbour-union lookup, fortify-source search and Philox contract.  The
+// two-player path (az_env_*) is untouched.
+//
+// Layout: one thread per game; 28 words per game in HBM as a structure of arrays (word w of game g at state[w * n + g]):
+//   words 0..10   army bytes of the 42 lands            words 11..21  owner bytes (seat 0..5)
+//   word 22       cards of seats 0..3 (a byte each)     word 23       cards of seats 4, 5 | set-up pools of the six seats (4 bits each) << 16
+//   word 24       round | cur << 16 | card_sets << 24   word 25       reinf | phase << 8 | mob_from << 16 | mob_to << 24
+//   word 26       allow_draw | attacks << 8             word 27       ply
+// Inside a kernel the land bytes sit in shared-memory columns (bank = lane), six ownership masks + army > 1 + army == 32 in registers.
+#include <cstring>
+#include <new>
+
+#include "az_common.cuh"
+#include "az_game.cuh"
+
+#define E6_BLOCK 256
+#define E6_WORDS 28
+#define E6_IMG 108                      // sizeof(r6_state), oracle/risk6_oracle.h: the host image of one game
+#define E6_PLAYERS 6
+
+struct AzGame6 {
+    uint64_t own[E6_PLAYERS];           // only ever indexed with compile-time constants (see e6_own): stays in registers
+    uint64_t gt1, full;
+    uint32_t round, cur, card_sets, reinf, phase, mob_from, mob_to, allow_draw, attacks;
+    uint32_t cards_lo, cards_hi, pools; // a byte per seat (0..3 | 4, 5), four bits per seat
+};
+
+__device__ __forceinline__ uint64_t e6_own(const AzGame6& g, uint32_t p)
+{
+    uint64_t v = g.own[0];
+#pragma unroll
+    for (int k = 1; k < E6_PLAYERS; ++k) v = p == (uint32_t)k ? g.own[k] : v;
+    return v;
+}
+__device__ __forceinline__ void e6_move_land(AzGame6& g, uint32_t from_p, uint32_t to_p, uint64_t m)
+{
+#pragma unroll
+    for (int k = 0; k < E6_PLAYERS; ++k) {
+        if (from_p == (uint32_t)k) g.own[k] &= ~m;
+        if (to_p == (uint32_t)k) g.own[k] |= m;
+    }
+}
+__device__ __forceinline__ uint32_t e6_cards(const AzGame6& g, uint32_t p) { return p < 4 ? (g.cards_lo >> (8 * p)) & 0xffu : (g.cards_hi >> (8 * (p - 4))) & 0xffu; }
+__device__ __forceinline__ void e6_set_cards(AzGame6& g, uint32_t p, uint32_t v)
+{
+    v &= 0xffu;
+    if (p < 4) g.cards_lo = (g.cards_lo & ~(0xffu << (8 * p))) | (v << (8 * p));
+    else g.cards_hi = (g.cards_hi & ~(0xffu << (8 * (p - 4)))) | (v << (8 * (p - 4)));
+}
+__device__ __forceinline__ uint32_t e6_pool(const AzGame6& g, uint32_t p) { return (g.pools >> (4 * p)) & 0xfu; }
+
+struct E6Smem {
+    uint64_t tab[AZ_TABLE_U64];
+    uint32_t col[33 * E6_BLOCK];        // 11 army words + 11 owner words + 11 fortify-DFS parent words per thread
+};
+struct E6Ctx {
+    AzGame6 g;
+    AzLandColumn army, owner, scratch;
+    uint32_t ply;
+};
+
+__device__ __forceinline__ void e6_bind(E6Ctx& c, E6Smem& sm)
+{
+    c.army.base = (uint8_t*)(sm.col) + 4 * threadIdx.x; c.army.stride_bytes = 4 * E6_BLOCK;
+    c.owner.base = (uint8_t*)(sm.col + 11 * E6_BLOCK) + 4 * threadIdx.x; c.owner.stride_bytes = 4 * E6_BLOCK;
+    c.scratch.base = (uint8_t*)(sm.col + 22 * E6_BLOCK) + 4 * threadIdx.x; c.scratch.stride_bytes = 4 * E6_BLOCK;
+}
+__device__ __forceinline__ void e6_masks(E6Ctx& c)
+{
+#pragma unroll
+    for (int k = 0; k < E6_PLAYERS; ++k) c.g.own[k] = 0;
+    c.g.gt1 = c.g.full = 0;
+    for (int i = 0; i < AZ_LANDS; ++i) {
+        const uint32_t a = c.army.get(i), o = c.owner.get(i);
+        const uint64_t m = 1ull << i;
+#pragma unroll
+        for (int k = 0; k < E6_PLAYERS; ++k) if (o == (uint32_t)k) c.g.own[k] |= m;
+        if (a > 1) c.g.gt1 |= m;
+        if (a == AZ_ARMY_MAX) c.g.full |= m;
+    }
+}
+__device__ __forceinline__ void e6_unpack(AzGame6& g, uint32_t w22, uint32_t w23, uint32_t w24, uint32_t w25, uint32_t w26)
+{
+    g.cards_lo = w22; g.cards_hi = w23 & 0xffffu; g.pools = w23 >> 16;
+    g.round = w24 & 0xffffu; g.cur = (w24 >> 16) & 0xffu; g.card_sets = (w24 >> 24) & 0xffu;
+    g.reinf = w25 & 0xffu; g.phase = (w25 >> 8) & 0xffu; g.mob_from = (w25 >> 16) & 0xffu; g.mob_to = (w25 >> 24) & 0xffu;
+    g.allow_draw = w26 & 0xffu; g.attacks = (w26 >> 8) & 0xffu;
+}
+__device__ __forceinline__ void e6_load(E6Ctx& c, E6Smem& sm, const uint32_t* __restrict__ st, int n, int gi)
+{
+    e6_bind(c, sm);
+    for (int w = 0; w < 22; ++w) sm.col[w * E6_BLOCK + threadIdx.x] = st[(size_t)w * n + gi];
+    e6_masks(c);
+    e6_unpack(c.g, st[(size_t)22 * n + gi], st[(size_t)23 * n + gi], st[(size_t)24 * n + gi], st[(size_t)25 * n + gi], st[(size_t)26 * n + gi]);
+    c.ply = st[(size_t)27 * n + gi];
+}
+__device__ __forceinline__ void e6_store(const E6Ctx& c, E6Smem& sm, uint32_t* __restrict__ st, int n, int gi)
+{
+    for (int w = 0; w < 22; ++w) st[(size_t)w * n + gi] = sm.col[w * E6_BLOCK + threadIdx.x];
+    const AzGame6& g = c.g;
+    st[(size_t)22 * n + gi] = g.cards_lo;
+    st[(size_t)23 * n + gi] = (g.cards_hi & 0xffffu) | (g.pools << 16);
+    st[(size_t)24 * n + gi] = (g.round & 0xffffu) | (g.cur << 16) | (g.card_sets << 24);
+    st[(size_t)25 * n + gi] = (g.reinf & 0xffu) | (g.phase << 8) | (g.mob_from << 16) | (g.mob_to << 24);
+    st[(size_t)26 * n + gi] = (g.allow_draw & 0xffu) | ((g.attacks & 0xffu) << 8);
+    st[(size_t)27 * n + gi] = c.ply;
+}
+
+// ---------------------------------------------------------------- rules (SIXPLAYER.md; oracle/risk6_oracle.c states the same)
+__device__ __forceinline__ void e6_set_army(E6Ctx& c, int i, uint32_t army)
+{
+    c.army.set(i, army);
+    const uint64_t m = 1ull << i;
+    c.g.gt1 = army > 1 ? (c.g.gt1 | m) : (c.g.gt1 & ~m);
+    c.g.full = army == AZ_ARMY_MAX ? (c.g.full | m) : (c.g.full & ~m);
+}
+
+// winner seat 0..5, AZ_STATUS_DRAW, AZ_STATUS_RUNNING (State::gameStatus, state/state.cpp:518-565, for six seats)
+__device__ __forceinline__ int e6_status(const AzGame6& g, const AzRulesDev& r)
+{
+    int alive = 0, last = -1, best = -1, best_n = -1, tie = 0;
+#pragma unroll
+    for (int p = 0; p < E6_PLAYERS; ++p) {
+        const int n = __popcll(g.own[p]);
+        if (n > 0) { alive++; last = p; }
+        if (n > best_n) { best_n = n; best = p; tie = 0; } else if (n == best_n) tie = 1;
+    }
+    if (alive == 1) return last;
+    if (r.allow_yield && best_n >= 30) return best;
+    if ((int)g.round > r.max_game_rounds) return tie ? AZ_STATUS_DRAW : best;
+    return AZ_STATUS_RUNNING;
+}
+
+__device__ __forceinline__ uint64_t e6_attack_army(const AzGame6& g, const AzTables& T, uint64_t oc) { return az_nbr_union(T, oc & g.gt1) & ~oc; }
+
+// UtilityNN::getValidMoves (alphazero_moves.cpp:3-70): "the enemy" = every other seat
+__device__ __forceinline__ uint64_t e6_valid(const AzGame6& g, const AzTables& T, const AzRulesDev& r)
+{
+    const uint64_t oc = e6_own(g, g.cur);
+    if (g.phase == AZ_PH_MOBILIZATION) return (1ull << (g.mob_from & 63u)) | (1ull << (g.mob_to & 63u));
+    if (g.phase == AZ_PH_ATTACK) {
+        const uint64_t aa = e6_attack_army(g, T, oc);
+        return r.limit_attack ? (aa ? aa : AZ_SKIP_MASK) : (aa | AZ_SKIP_MASK);
+    }
+    const uint64_t border = az_nbr_union(T, AZ_ALL_LANDS & ~oc);
+    if (g.phase == AZ_PH_FORTIFY) return (r.limit_reinforcement ? (oc & border) : oc) | AZ_SKIP_MASK;
+    const uint64_t o = oc & ~g.full;                              // SETUP / REINFORCEMENT
+    if (o == 0) return AZ_SKIP_MASK;
+    return (r.limit_reinforcement && (o & border)) ? (o & border) : o;
+}
+
+__device__ __forceinline__ void e6_goto_attack(AzGame6& g, const AzTables& T)
+{
+    g.phase = AZ_PH_ATTACK; g.mob_from = AZ_NONE; g.mob_to = AZ_NONE; g.reinf = 0;
+    if (e6_attack_army(g, T, e6_own(g, g.cur)) == 0) g.phase = AZ_PH_FORTIFY;
+}
+
+// State::nextPlayerGameTurn (state.cpp:748-766): next seat that still owns a land; the round advances when the order wraps
+__device__ __forceinline__ void e6_end_turn(AzGame6& g)
+{
+    if (g.allow_draw) { e6_set_cards(g, g.cur, e6_cards(g, g.cur) + 1); g.allow_draw = 0; }
+    uint32_t next = g.cur;
+    for (int k = 0; k < E6_PLAYERS; ++k) {
+        next = next + 1 == E6_PLAYERS ? 0u : next + 1;
+        if (next == 0) g.round = (g.round + 1) & 0xffffu;
+        if (e6_own(g, next)) break;
+    }
+    g.cur = next; g.attacks = 0; g.phase = AZ_PH_REINFORCEMENT;
+    g.reinf = (uint32_t)az_reinforcement_value(e6_own(g, next));
+}
+
+// UtilityNN::makeMove (alphazero_moves.cpp:72-233) for a LEGAL action; dice = the base-6 digits of word 0 of the real-move block
+__device__ __forceinline__ void e6_move(E6Ctx& c, const AzTables& T, const AzRulesDev& r, int action, uint32_t dice_word)
+{
+    AzGame6& g = c.g;
+    const uint32_t cur = g.cur;
+    if (action == AZ_SKIP) {
+        if (g.phase == AZ_PH_REINFORCEMENT) e6_goto_attack(g, T);
+        else if (g.phase == AZ_PH_ATTACK) g.phase = AZ_PH_FORTIFY;
+        else if (g.phase == AZ_PH_FORTIFY) e6_end_turn(g);
+        return;
+    }
+    const int li = action;
+    const int at = (int)c.army.get(li);
+    if (g.phase == AZ_PH_SETUP) {
+        e6_set_army(c, li, (uint32_t)(at + 1));
+        g.pools -= 1u << (4 * cur);
+        g.cur = cur + 1 == E6_PLAYERS ? 0u : cur + 1;
+        if (g.cur == 0) g.round = (g.round + 1) & 0xffffu;
+        if (e6_pool(g, g.cur) == 0) { g.phase = AZ_PH_REINFORCEMENT; g.reinf = (uint32_t)az_reinforcement_value(e6_own(g, g.cur)); }
+    } else if (g.phase == AZ_PH_REINFORCEMENT) {
+        uint32_t cards = e6_cards(g, cur);
+        if (cards >= 3) {
+            e6_set_cards(g, cur, cards - 3);
+            g.card_sets = (g.card_sets + 1) & 0xffu;
+            const int cs = (int)g.card_sets;
+            g.reinf = (g.reinf + (uint32_t)(cs <= 5 ? 2 + 2 * cs : 15 + (cs - 6) * 5)) & 0xffu;
+        }
+        int rf = (int)g.reinf / 2;
+        if (rf < r.min_unit_move) rf = r.min_unit_move < (int)g.reinf ? r.min_unit_move : (int)g.reinf;
+        const int space = AZ_ARMY_MAX - at;
+        if (space < rf) rf = space;
+        g.reinf = (g.reinf - (uint32_t)rf) & 0xffu;
+        e6_set_army(c, li, (uint32_t)(at + rf));
+        if (g.reinf == 0) e6_goto_attack(g, T);
+    } else if (g.phase == AZ_PH_ATTACK) {
+        const uint64_t oc = e6_own(g, cur), cand = oc & g.gt1;
+        int best = 0, from = li;
+        uint64_t lst = T.list6[li];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int n = (int)(lst & 63u); lst >>= 6;
+            const bool ok = n != 63 && ((cand >> n) & 1ull);
+            const int v = ok ? (int)c.army.get(ok ? n : li) - 1 : 0;
+            if (v > best) { best = v; from = n; }
+        }
+        g.attacks = (g.attacks + 1) & 0xffu;
+        int a = best + 1, d = at, units;
+        const uint32_t defender = c.owner.get(li);
+        {
+            const int na = a >= 4 ? 3 : (a == 3 ? 2 : 1), nd = d >= 2 ? 2 : 1;
+            units = na;
+            uint32_t w = dice_word;
+            uint64_t p;
+            p = (uint64_t)w * 6u; w = (uint32_t)p; const int a0 = (int)(p >> 32) + 1;
+            int a1 = 0, a2 = 0, d1 = 0;
+            if (na > 1) { p = (uint64_t)w * 6u; w = (uint32_t)p; a1 = (int)(p >> 32) + 1; }
+            if (na > 2) { p = (uint64_t)w * 6u; w = (uint32_t)p; a2 = (int)(p >> 32) + 1; }
+            p = (uint64_t)w * 6u; w = (uint32_t)p; const int d0 = (int)(p >> 32) + 1;
+            if (nd > 1) { p = (uint64_t)w * 6u; w = (uint32_t)p; d1 = (int)(p >> 32) + 1; }
+            const int hi = max(a0, max(a1, a2));
+            int lo = min(a0, max(a1, a2)); lo = max(lo, min(a1, a2));
+            const int dh = max(d0, d1), dl = min(d0, d1);
+            if (hi > dh) d--; else { a--; units--; }
+            if (na >= 2 && nd == 2) { if (lo > dl) d--; else { a--; units--; } }
+        }
+        if (d == 0) {
+            a -= units;
+            if (a > 1) { g.phase = AZ_PH_MOBILIZATION; g.mob_from = (uint32_t)from; g.mob_to = (uint32_t)li; }
+            g.allow_draw = 1;
+            e6_set_army(c, from, (uint32_t)a); e6_set_army(c, li, (uint32_t)units);
+            c.owner.set(li, cur);
+            e6_move_land(g, defender, cur, 1ull << li);
+            if (e6_own(g, defender) == 0) {                       // elimination: the eliminator takes the cards
+                e6_set_cards(g, cur, e6_cards(g, cur) + e6_cards(g, defender));
+                e6_set_cards(g, defender, 0);
+            }
+        } else { e6_set_army(c, from, (uint32_t)a); e6_set_army(c, li, (uint32_t)d); }
+        if (g.phase == AZ_PH_ATTACK && e6_attack_army(g, T, e6_own(g, cur)) == 0) g.phase = AZ_PH_FORTIFY;
+    } else if (g.phase == AZ_PH_MOBILIZATION) {
+        if ((uint32_t)li == g.mob_from) e6_goto_attack(g, T);
+        else {
+            const int from = (int)g.mob_from;
+            const int af = (int)c.army.get(from), v = af - 1;
+            int rf = v / 2;
+            if (rf < r.min_unit_move) rf = r.min_unit_move < v ? r.min_unit_move : v;
+            e6_set_army(c, from, (uint32_t)(af - rf)); e6_set_army(c, li, (uint32_t)(at + rf));
+            if (af - rf == 1) e6_goto_attack(g, T);
+        }
+    } else {                                                      // FORTIFY
+        if (at != AZ_ARMY_MAX) {
+            AzGame t; t.cur = 0; t.own0 = e6_own(g, cur); t.own1 = 0; t.gt1 = g.gt1; t.full = g.full;   // the two-player search on the mover's lands
+            int from, amount;
+            az_fortify_source(t, c.army, c.scratch, T, li, from, amount);
+            if (from >= 0) {
+                const int space = AZ_ARMY_MAX - at, mv = space < amount ? space : amount;
+                const int af = (int)c.army.get(from);
+                e6_set_army(c, from, (uint32_t)(af - mv)); e6_set_army(c, li, (uint32_t)(at + mv));
+            }
+        }
+        e6_end_turn(g);
+    }
+}
+
+// State::newGame for six seats: the 42 draws of the deal stream go to seats 0..5 in turn, one army each; 13 armies to place per seat
+__device__ __forceinline__ void e6_new_game(E6Ctx& c, uint64_t seed, uint32_t game, uint32_t ply)
+{
+    AzGame6& g = c.g;
+#pragma unroll
+    for (int k = 0; k < E6_PLAYERS; ++k) g.own[k] = 0;
+    g.gt1 = g.full = 0;
+    g.round = 1; g.cur = 0; g.card_sets = 0; g.reinf = 0; g.phase = AZ_PH_SETUP; g.mob_from = AZ_NONE; g.mob_to = AZ_NONE;
+    g.allow_draw = 0; g.attacks = 0; g.cards_lo = g.cards_hi = 0; g.pools = 0xDDDDDDu;                 // 13 per seat
+    uint64_t avail = AZ_ALL_LANDS;
+    az_u32x4 blk;
+    for (uint32_t i = 0; i < 42; ++i) {
+        if ((i & 3u) == 0) blk = az_rng_block(seed, game, ply, AZ_STREAM_DEAL, i >> 2);
+        const uint32_t k = az_mulhi32(az_u32x4_word(blk, (int)(i & 3u)), 42u - i);
+        const int l = az_nth_set_bit(avail, k);
+        avail &= ~(1ull << l);
+        const uint32_t seat = i % E6_PLAYERS;
+        c.army.set(l, 1u); c.owner.set(l, seat);
+#pragma unroll
+        for (int s = 0; s < E6_PLAYERS; ++s) if (seat == (uint32_t)s) g.own[s] |= 1ull << l;
+    }
+}
+
+// ---------------------------------------------------------------- kernels
+__device__ __forceinline__ AzTables e6_stage(E6Smem& sm, const uint64_t* __restrict__ g_tab)
+{
+    for (int i = threadIdx.x; i < AZ_TABLE_U64; i += blockDim.x) sm.tab[i] = g_tab[i];
+    __syncthreads();
+    return az_tables_from_smem(sm.tab);
+}
+
+__global__ void __launch_bounds__(E6_BLOCK) k_env6_reset(uint32_t* __restrict__ st, int n, uint64_t seed, uint32_t first_game)
+{
+    __shared__ E6Smem sm;
+    const int gi = blockIdx.x * E6_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    E6Ctx c; e6_bind(c, sm);
+    for (int w = 0; w < 22; ++w) sm.col[w * E6_BLOCK + threadIdx.x] = 0;
+    e6_new_game(c, seed, first_game + (uint32_t)gi, 0);
+    c.ply = 0;
+    e6_store(c, sm, st, n, gi);
+}
+
+// n_steps uniform-random legal moves per game (action = k-th set bit of the mask, k = mulhi(word 1 of the real-move block,
+// popcount); dice = word 0), finished games re-dealt in place: the six-player form of az_env_rollout.  counters: steps, games,
+// draws, wins of seats 0..5
+__global__ void __launch_bounds__(E6_BLOCK) k_env6_rollout(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab, int n_steps,
+                                                          uint64_t seed, uint32_t first_game, AzRulesDev rules,
+                                                          unsigned long long* __restrict__ counters)
+{
+    __shared__ E6Smem sm;
+    const AzTables T = e6_stage(sm, g_tab);
+    const int gi = blockIdx.x * E6_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    E6Ctx c; e6_load(c, sm, st, n, gi);
+    const uint32_t game = first_game + (uint32_t)gi;
+    unsigned games = 0, draws = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        const int stt = e6_status(c.g, rules);
+        if (stt != AZ_STATUS_RUNNING) {
+            games++;
+            if (stt == AZ_STATUS_DRAW) draws++; else atomicAdd(&counters[3 + stt], 1ull);
+            e6_new_game(c, seed, game, c.ply);
+        }
+        const uint64_t valid = e6_valid(c.g, T, rules);
+        const az_u32x4 blk = az_rng_block(seed, game, c.ply, AZ_STREAM_REAL, 0);
+        const int action = az_nth_set_bit(valid, az_mulhi32(blk.y, (uint32_t)__popcll(valid)));
+        e6_move(c, T, rules, action, blk.x);
+        c.ply++;
+    }
+    e6_store(c, sm, st, n, gi);
+    atomicAdd(&counters[0], (unsigned long long)n_steps);
+    if (games) atomicAdd(&counters[1], (unsigned long long)games);
+    if (draws) atomicAdd(&counters[2], (unsigned long long)draws);
+}
+
+// one host-chosen action per game (the lockstep tests): status byte = AZ_STATUS_ILLEGAL / AZ_STATUS_OVER (state untouched) or the
+// game status after the move
+__global__ void __launch_bounds__(E6_BLOCK) k_env6_step(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
+                                                       const uint8_t* __restrict__ action, uint64_t seed, uint32_t first_game,
+                                                       AzRulesDev rules, int8_t* __restrict__ status)
+{
+    __shared__ E6Smem sm;
+    const AzTables T = e6_stage(sm, g_tab);
+    const int gi = blockIdx.x * E6_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    E6Ctx c; e6_load(c, sm, st, n, gi);
+    if (e6_status(c.g, rules) != AZ_STATUS_RUNNING) { status[gi] = AZ_STATUS_OVER; return; }
+    const int a = action[gi];
+    const uint64_t valid = e6_valid(c.g, T, rules);
+    if (a > AZ_SKIP || !((valid >> a) & 1ull)) { status[gi] = AZ_STATUS_ILLEGAL; return; }
+    const az_u32x4 blk = az_rng_block(seed, first_game + (uint32_t)gi, c.ply, AZ_STREAM_REAL, 0);
+    e6_move(c, T, rules, a, blk.x);
+    c.ply++;
+    e6_store(c, sm, st, n, gi);
+    status[gi] = (int8_t)e6_status(c.g, rules);
+}
+
+__global__ void __launch_bounds__(E6_BLOCK) k_env6_query(const uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
+                                                        AzRulesDev rules, uint64_t* __restrict__ valid, int8_t* __restrict__ status)
+{
+    __shared__ E6Smem sm;
+    const AzTables T = e6_stage(sm, g_tab);
+    const int gi = blockIdx.x * E6_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    E6Ctx c; e6_load(c, sm, st, n, gi);
+    if (valid) valid[gi] = e6_valid(c.g, T, rules);
+    if (status) status[gi] = (int8_t)e6_status(c.g, rules);
+}
+
+// 108-byte host image (== r6_state of the oracle): army[42], owner[42], cards[6], pool[6], round u16, cur, card_sets, reinf,
+// phase, mob_from, mob_to, allow_draw, attacks, 2 pad bytes
+__global__ void __launch_bounds__(E6_BLOCK) k_env6_export(const uint32_t* __restrict__ st, int n, uint8_t* __restrict__ img)
+{
+    __shared__ E6Smem sm;
+    const int gi = blockIdx.x * E6_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    E6Ctx c; e6_load(c, sm, st, n, gi);
+    uint8_t* d = img + (size_t)gi * E6_IMG;
+    for (int i = 0; i < AZ_LANDS; ++i) { d[i] = (uint8_t)c.army.get(i); d[42 + i] = (uint8_t)c.owner.get(i); }
+    for (uint32_t p = 0; p < E6_PLAYERS; ++p) { d[84 + p] = (uint8_t)e6_cards(c.g, p); d[90 + p] = (uint8_t)e6_pool(c.g, p); }
+    d[96] = (uint8_t)(c.g.round & 0xffu); d[97] = (uint8_t)(c.g.round >> 8);
+    d[98] = (uint8_t)c.g.cur; d[99] = (uint8_t)c.g.card_sets; d[100] = (uint8_t)c.g.reinf; d[101] = (uint8_t)c.g.phase;
+    d[102] = (uint8_t)c.g.mob_from; d[103] = (uint8_t)c.g.mob_to; d[104] = (uint8_t)c.g.allow_draw; d[105] = (uint8_t)c.g.attacks;
+    d[106] = 0; d[107] = 0;
+}
+__global__ void __launch_bounds__(E6_BLOCK) k_env6_import(uint32_t* __restrict__ st, int n, const uint8_t* __restrict__ img, int* __restrict__ bad)
+{
+    __shared__ E6Smem sm;
+    const int gi = blockIdx.x * E6_BLOCK + threadIdx.x;
+    if (gi >= n) return;
+    const uint8_t* d = img + (size_t)gi * E6_IMG;
+    E6Ctx c; e6_bind(c, sm);
+    for (int w = 0; w < 22; ++w) sm.col[w * E6_BLOCK + threadIdx.x] = 0;
+    bool ok = true;
+    for (int i = 0; i < AZ_LANDS; ++i) {
+        ok = ok && d[i] >= 1 && d[i] <= AZ_ARMY_MAX && d[42 + i] < E6_PLAYERS;
+        c.army.set(i, d[i]); c.owner.set(i, d[42 + i]);
+    }
+    e6_masks(c);
+    AzGame6& g = c.g;
+    g.cards_lo = g.cards_hi = 0; g.pools = 0;
+    for (uint32_t p = 0; p < E6_PLAYERS; ++p) { e6_set_cards(g, p, d[84 + p]); g.pools |= (uint32_t)(d[90 + p] & 0xfu) << (4 * p); ok = ok && d[90 + p] <= 13; }
+    g.round = (uint32_t)d[96] | ((uint32_t)d[97] << 8); g.cur = d[98]; g.card_sets = d[99]; g.reinf = d[100]; g.phase = d[101];
+    g.mob_from = d[102]; g.mob_to = d[103]; g.allow_draw = d[104]; g.attacks = d[105];
+    ok = ok && g.cur < E6_PLAYERS && g.phase <= AZ_PH_FORTIFY && g.phase != AZ_PH_SETUP_NEUTRAL;
+    if (!ok) { atomicAdd(bad, 1); return; }
+    c.ply = st[(size_t)27 * n + gi];                              // the slot's move counter is not part of the image
+    e6_store(c, sm, st, n, gi);
+}
+
+// ---------------------------------------------------------------- C ABI
+struct az_env6 {
+    int n = 0, device = 0;
+    uint32_t first_game = 0;
+    uint64_t seed = 0;
+    az_rules rules;
+    uint32_t* d_state = nullptr;
+    unsigned long long* d_counters = nullptr;   // steps, games, draws, wins[6]
+    uint8_t* d_img = nullptr; uint8_t* d_action = nullptr; int8_t* d_status = nullptr; uint64_t* d_valid = nullptr; int* d_bad = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+};
+
+static AzRulesDev e6_rules(const az_rules& r)
+{
+    AzRulesDev d; d.allow_yield = r.allow_yield; d.limit_reinforcement = r.limit_reinforcement; d.limit_attack = r.limit_attack;
+    d.max_game_rounds = r.max_game_rounds; d.min_unit_move = r.min_unit_move; return d;
+}
+static inline int e6_grid(int n) { return (n + E6_BLOCK - 1) / E6_BLOCK; }
+
+extern "C" int az_env6_create(int n_games, const az_rules* rules, int device, uint32_t first_game_id, az_env6** out)
+{
+    AZ_REQUIRE(out != nullptr, "out is NULL");
+    AZ_REQUIRE(n_games > 0, "n_games must be positive");
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have == 0) { az_set_error("no CUDA device: libaz_b200 has no CPU fallback"); return AZ_ERR_NO_DEVICE; }
+    AZ_REQUIRE(device >= 0 && device < have, "device index out of range");
+    AzDeviceGuard guard(device);
+    int rc = az_upload_tables(); if (rc) return rc;
+    az_env6* e = new (std::nothrow) az_env6();
+    AZ_REQUIRE(e != nullptr, "out of host memory");
+    e->n = n_games; e->device = device; e->first_game = first_game_id;
+    if (rules) e->rules = *rules; else az_default_rules(&e->rules);
+    const size_t n = (size_t)n_games;
+    cudaError_t ce = cudaMalloc(&e->d_state, sizeof(uint32_t) * E6_WORDS * n);
+    if (ce == cudaSuccess) ce = cudaMemset(e->d_state, 0, sizeof(uint32_t) * E6_WORDS * n);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_counters, sizeof(unsigned long long) * 16);
+    if (ce == cudaSuccess) ce = cudaMemset(e->d_counters, 0, sizeof(unsigned long long) * 16);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_img, n * E6_IMG);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_action, n);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_status, n);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_valid, sizeof(uint64_t) * n);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_bad, sizeof(int));
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e->ev1);
+    if (ce != cudaSuccess) { az_set_error("az_env6_create: %s", cudaGetErrorString(ce)); az_env6_destroy(e); return AZ_ERR_CUDA; }
+    *out = e;
+    return AZ_OK;
+}
+
+extern "C" int az_env6_destroy(az_env6* e)
+{
+    if (!e) return AZ_OK;
+    AzDeviceGuard guard(e->device);
+    cudaFree(e->d_state); cudaFree(e->d_counters); cudaFree(e->d_img); cudaFree(e->d_action); cudaFree(e->d_status); cudaFree(e->d_valid); cudaFree(e->d_bad);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    delete e;
+    return AZ_OK;
+}
+
+extern "C" int az_env6_reset(az_env6* e, uint64_t seed, void* stream)
+{
+    AZ_REQUIRE(e != nullptr, "env is NULL");
+    AzDeviceGuard guard(e->device);
+    e->seed = seed;
+    k_env6_reset<<<e6_grid(e->n), E6_BLOCK, 0, (cudaStream_t)stream>>>(e->d_state, e->n, seed, e->first_game);
+    AZ_CUDA(cudaGetLastError());
+    return AZ_OK;
+}
+
+extern "C" int az_env6_rollout(az_env6* e, int n_steps, void* stream)
+{
+    AZ_REQUIRE(e != nullptr, "env is NULL");
+    AZ_REQUIRE(n_steps >= 0, "n_steps must be >= 0");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AZ_CUDA(cudaEventRecord(e->ev0, s));
+    k_env6_rollout<<<e6_grid(e->n), E6_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game, e6_rules(e->rules),
+                                                     e->d_counters);
+    AZ_CUDA(cudaGetLastError());
+    AZ_CUDA(cudaEventRecord(e->ev1, s));
+    e->timed = true;
+    return AZ_OK;
+}
+
+extern "C" int az_env6_last_kernel_ms(az_env6* e, float* ms)
+{
+    AZ_REQUIRE(e && ms, "NULL argument");
+    AZ_REQUIRE(e->timed, "no timed launch yet");
+    AzDeviceGuard guard(e->device);
+    AZ_CUDA(cudaEventSynchronize(e->ev1));
+    AZ_CUDA(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return AZ_OK;
+}
+
+extern "C" int az_env6_step(az_env6* e, const uint8_t* h_action, int8_t* h_status, void* stream)
+{
+    AZ_REQUIRE(e && h_action && h_status, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AZ_CUDA(cudaMemcpyAsync(e->d_action, h_action, (size_t)e->n, cudaMemcpyHostToDevice, s));
+    k_env6_step<<<e6_grid(e->n), E6_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), e->d_action, e->seed, e->first_game, e6_rules(e->rules), e->d_status);
+    AZ_CUDA(cudaGetLastError());
+    AZ_CUDA(cudaMemcpyAsync(h_status, e->d_status, (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+extern "C" int az_env6_query(az_env6* e, uint64_t* h_valid, int8_t* h_status, void* stream)
+{
+    AZ_REQUIRE(e && (h_valid || h_status), "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    k_env6_query<<<e6_grid(e->n), E6_BLOCK, 0, s>>>(e->d_state, e->n, az_device_tables(), e6_rules(e->rules), h_valid ? e->d_valid : nullptr,
+                                                   h_status ? e->d_status : nullptr);
+    AZ_CUDA(cudaGetLastError());
+    if (h_valid) AZ_CUDA(cudaMemcpyAsync(h_valid, e->d_valid, sizeof(uint64_t) * (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    if (h_status) AZ_CUDA(cudaMemcpyAsync(h_status, e->d_status, (size_t)e->n, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+extern "C" int az_env6_export(az_env6* e, uint8_t* h_images, void* stream)
+{
+    AZ_REQUIRE(e && h_images, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    k_env6_export<<<e6_grid(e->n), E6_BLOCK, 0, s>>>(e->d_state, e->n, e->d_img);
+    AZ_CUDA(cudaGetLastError());
+    AZ_CUDA(cudaMemcpyAsync(h_images, e->d_img, (size_t)e->n * E6_IMG, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return AZ_OK;
+}
+
+extern "C" int az_env6_import(az_env6* e, const uint8_t* h_images, void* stream)
+{
+    AZ_REQUIRE(e && h_images, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    AZ_CUDA(cudaMemcpyAsync(e->d_img, h_images, (size_t)e->n * E6_IMG, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaMemsetAsync(e->d_bad, 0, sizeof(int), s));
+    k_env6_import<<<e6_grid(e->n), E6_BLOCK, 0, s>>>(e->d_state, e->n, e->d_img, e->d_bad);
+    AZ_CUDA(cudaGetLastError());
+    int bad = 0;
+    AZ_CUDA(cudaMemcpyAsync(&bad, e->d_bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    if (bad) { az_set_error("az_env6_import: %d malformed game image(s)", bad); return AZ_ERR_BAD_STATE; }
+    return AZ_OK;
+}
+
+extern "C" int az_env6_counters(az_env6* e, az_counters6* h_out, int reset, void* stream)
+{
+    AZ_REQUIRE(e && h_out, "NULL argument");
+    AzDeviceGuard guard(e->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long h[16];
+    AZ_CUDA(cudaMemcpyAsync(h, e->d_counters, sizeof h, cudaMemcpyDeviceToHost, s));
+    if (reset) AZ_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof h, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    h_out->steps = h[0]; h_out->games = h[1]; h_out->draws = h[2];
+    for (int p = 0; p < E6_PLAYERS; ++p) h_out->wins[p] = h[3 + p];
+    return AZ_OK;
+}

@@ -391,6 +391,42 @@ def run_play(args, api, torch, rank, local):
                                     % (games, args.blocks, slots)})
 
 
+def run_env6(args, api, torch, rank, local):
+    """BASELINE configs[3]'s game: the SIX-PLAYER extension (SIXPLAYER.md; no reference semantics, checker = oracle/risk6_oracle.c).
+    Environment only — 16384 lockstep six-player games, uniform-random legal moves, finished games re-dealt; the six-player search
+    is specified and not built."""
+    n, S = args.env6_games, args.lockstep
+    stream = torch.cuda.current_stream(); sptr = stream.cuda_stream
+    env = api.Env6(n, device=local, first_game_id=rank * n)
+    env.reset(SEED, stream=sptr)
+    for _ in range(3):
+        env.rollout(S, stream=sptr)
+    torch.cuda.synchronize()
+    env.counters(reset=True, stream=sptr)
+    steps = 5
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        ev[i][0].record(stream)
+        env.rollout(S, stream=sptr)
+        ev[i][1].record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    cnt = env.counters(stream=sptr)
+    env.close()
+    hbm_peak, _, src = measured_peaks()
+    bytes_per_step = 2 * 108 + 8 + 1 + 1                  # the 108-byte state image in and out + mask + action + status
+    achieved = bytes_per_step * n * S / (ms * 1e-3) / 1e9
+    return dict(metric="env6_steps_per_sec", value=n * S / (ms * 1e-3), unit="steps/s", ms_per_step=ms, steps=steps,
+                config={"workload": "configs[3] game (six-player EXTENSION, SIXPLAYER.md: no reference semantics, parity unpinned; environment "
+                                    "only): %d lockstep six-player games per GPU, uniform-random legal moves, %d moves per launch, finished "
+                                    "games re-dealt in place" % (n, S), "games_per_gpu": n},
+                roofline={"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                          "peak_source": src, "note": "algorithmic %d B/step (state image in + out, mask, action, status); like the "
+                                                      "two-player rollout the kernel keeps the state on chip and is issue / latency bound; a "
+                                                      "straightforward thread-per-game kernel, not tuned" % bytes_per_step},
+                results={"games_finished": cnt["games"], "draws": cnt["draws"], "wins": cnt["wins"]}, gpu_launches=steps)
+
+
 def run_train(args, api, torch, local):
     """SURVEY §8f N4: one optimizer step (AlphaZeroNN::train inner loop) on a batch of SETTINGS.BATCH_SIZE = 512 synthetic samples"""
     import numpy as np
@@ -583,6 +619,9 @@ def run_ours(args):
     train_line = None
     if args.train_batch >= 2 and rank == 0 and world == 1:
         train_line = run_train(args, api, torch, local)
+    env6_line = None
+    if args.env6_games > 0 and rank == 0:
+        env6_line = run_env6(args, api, torch, rank, local)
 
     if rank == 0:
         hbm_peak, _, src = measured_peaks()
@@ -632,6 +671,9 @@ def run_ours(args):
             line["play"] = play_line
         if train_line is not None:
             line["train"] = train_line
+        if env6_line is not None:
+            line["env6"] = env6_line
+            line["gpu_launches"] += env6_line["gpu_launches"]
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_env_baseline(12.0)
             line["cpu_baseline"] = cb
@@ -664,6 +706,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=5)
     ap.add_argument("--cfg5-games", type=int, default=16384, help="games per GPU of the configs[4] sub-line (0 skips it)")
     ap.add_argument("--cfg5-sims", type=int, default=800)
+    ap.add_argument("--env6-games", type=int, default=16384, help="games of the six-player environment sub-line (configs[3]'s game; 0 skips it)")
     ap.add_argument("--no-blocks20", dest="blocks20", action="store_false", help="skip the 20-block (CMake default graph) sub-line")
     ap.add_argument("--train-batch", type=int, default=512, help="training-step measurement batch (SETTINGS.BATCH_SIZE); 0 skips it")
     ap.add_argument("--play-games", type=int, default=1000, help="configs[0] match size (--cg); 0 skips it")

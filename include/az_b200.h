@@ -306,6 +306,29 @@ AZ_API int az_arena_destroy(az_arena* arena);
 /* plays 2 * floor(n_games / 2) games (pairs, like the reference) over the env's slots; seed fixes the Philox contract */
 AZ_API int az_arena_play(az_arena* arena, uint64_t n_games, uint64_t seed, az_arena_results* h_out, void* stream);
 
+/* ---------------------------------------------------------------- six-player extension (BASELINE.json configs[3]) — NO reference parity
+   The reference is a two-player game (PLAYER_COUNT = 2, state/state.h:13; owner = 2 bits with 2 = neutral, state.h:24-41): there
+   is no six-player interface to replace.  az_env6_* is a throughput-only extension whose rules are SIXPLAYER.md (six seats, no
+   neutral army, 7 lands + 13 set-up armies each, seats eliminated when they lose their last land, the eliminator takes the cards,
+   simple-card trade-ins as in the reference's default STATE_SIMPLE_CARDS mode) and whose only checker is oracle/risk6_oracle.c.
+   Same action space (42 lands + skip), status byte (winner seat 0..5, AZ_STATUS_DRAW, AZ_STATUS_RUNNING / _ILLEGAL / _OVER),
+   az_rules fields and Philox contract as az_env_*.  State image = AZ_ENV6_IMAGE_BYTES per game: army[42], owner[42], cards[6],
+   pool[6], round u16, cur, card_sets, reinf, phase, mob_from, mob_to, allow_draw, attacks, 2 pad bytes.  The search (az_mcts_*) and
+   the network encoding are two-player only; a six-player search is specified in SIXPLAYER.md and not built. */
+typedef struct az_env6 az_env6;
+#define AZ_ENV6_IMAGE_BYTES 108
+typedef struct az_counters6 { uint64_t steps, games, draws, wins[6]; } az_counters6;
+AZ_API int az_env6_create(int n_games, const az_rules* rules, int device, uint32_t first_game_id, az_env6** out);
+AZ_API int az_env6_destroy(az_env6* env);
+AZ_API int az_env6_reset(az_env6* env, uint64_t seed, void* stream);
+AZ_API int az_env6_rollout(az_env6* env, int n_steps, void* stream);          /* uniform-random legal play, finished games re-dealt */
+AZ_API int az_env6_last_kernel_ms(az_env6* env, float* ms);
+AZ_API int az_env6_step(az_env6* env, const uint8_t* h_action, int8_t* h_status, void* stream);
+AZ_API int az_env6_query(az_env6* env, uint64_t* h_valid, int8_t* h_status, void* stream);
+AZ_API int az_env6_export(az_env6* env, uint8_t* h_images, void* stream);
+AZ_API int az_env6_import(az_env6* env, const uint8_t* h_images, void* stream);
+AZ_API int az_env6_counters(az_env6* env, az_counters6* h_out, int reset, void* stream);
+
 /* ---------------------------------------------------------------- multi-GPU: NCCL over NVLink / NVSwitch, never inside a search
    Games shard over GPUs by contiguous global id (first_game_id of az_env_create) and never migrate; every GPU holds a full copy of
    the network.  The only exchanges are the two below.  NCCL is loaded at run time (libnccl.so.2); without it az_dist_init* fail

@@ -481,3 +481,50 @@ def ref_save_samples(path, players, nn_inputs, policies, status, rounds):
                                     np.ascontiguousarray(policies, np.float32).reshape(-1), int(status), int(rounds))
     if rc != 0:
         raise RuntimeError(ref_lib().ref_last_error().decode())
+
+
+# --------------------------------------------------------------------------- six-player extension (oracle/risk6_oracle.c)
+R6_STATE_BYTES, R6_PLAYERS = 108, 6
+
+
+class R6State(C.Structure):
+    _fields_ = [("army", C.c_uint8 * 42), ("owner", C.c_uint8 * 42), ("cards", C.c_uint8 * 6), ("pool", C.c_uint8 * 6),
+                ("round", C.c_uint16), ("cur", C.c_uint8), ("card_sets", C.c_uint8), ("reinf", C.c_uint8), ("phase", C.c_uint8),
+                ("mob_from", C.c_uint8), ("mob_to", C.c_uint8), ("allow_draw", C.c_uint8), ("attacks", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
+class Oracle6Game:
+    """one six-player game (SIXPLAYER.md) driven through the C statement of the extension; parity unpinned (no reference semantics)"""
+
+    def __init__(self, rules=None):
+        self.L = oracle_lib()
+        self.L.r6_new_game.argtypes = [C.POINTER(R6State), C.c_uint64, C.c_uint32, C.c_uint32]
+        self.L.r6_valid_moves.argtypes = [C.POINTER(R6State), C.POINTER(RoRules)]
+        self.L.r6_valid_moves.restype = C.c_uint64
+        self.L.r6_game_status.argtypes = [C.POINTER(R6State), C.POINTER(RoRules)]
+        self.L.r6_make_move.argtypes = [C.POINTER(R6State), C.c_int, C.POINTER(RoRules), C.c_uint64, C.c_uint32, C.c_uint32]
+        self.L.r6_random_action.argtypes = [C.POINTER(R6State), C.POINTER(RoRules), C.c_uint64, C.c_uint32, C.c_uint32]
+        self.s = R6State()
+        self.rules = rules if rules is not None else default_rules()
+        assert C.sizeof(R6State) == R6_STATE_BYTES
+
+    def new_game(self, seed, game, ply=0):
+        self.L.r6_new_game(C.byref(self.s), seed, game, ply)
+
+    def valid(self):
+        return int(self.L.r6_valid_moves(C.byref(self.s), C.byref(self.rules)))
+
+    def status(self):
+        return int(self.L.r6_game_status(C.byref(self.s), C.byref(self.rules)))
+
+    def random_action(self, seed, game, ply):
+        return int(self.L.r6_random_action(C.byref(self.s), C.byref(self.rules), seed, game, ply))
+
+    def move(self, action, seed, game, ply):
+        return int(self.L.r6_make_move(C.byref(self.s), int(action), C.byref(self.rules), seed, game, ply))
+
+    def image(self):
+        return np.frombuffer(bytes(self.s), np.uint8).copy()
+
+    def set_image(self, img):
+        C.memmove(C.byref(self.s), np.ascontiguousarray(img, np.uint8).ctypes.data, R6_STATE_BYTES)
