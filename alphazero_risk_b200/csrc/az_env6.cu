@@ -8,9 +8,9 @@
 //
 // Layout: one thread per game; 28 words per game in HBM as a structure of arrays (word w of game g at state[w * n + g]):
 //   words 0..10   army bytes of the 42 lands            words 11..21  owner bytes (seat 0..5)
-//   word 22       cards of seats 0..3 (a byte each)     word 23       cards of seats 4, 5 | set-up pools of the six seats (4 bits each) << 16
+//   word 22       cards of seats 0..3 (a byte each)     word 23       cards of seats 4, 5 | allow_draw << 16 | attacks << 24
 //   word 24       round | cur << 16 | card_sets << 24   word 25       reinf | phase << 8 | mob_from << 16 | mob_to << 24
-//   word 26       allow_draw | attacks << 8             word 27       ply
+//   word 26       set-up pools of the six seats (4 bits each)          word 27       ply
 // Inside a kernel the land bytes sit in shared-memory columns (bank = lane), six ownership masks + army > 1 + army == 32 in registers.
 #include <cstring>
 #include <new>
@@ -18,7 +18,7 @@
 #include "az_common.cuh"
 #include "az_game.cuh"
 
-#define E6_BLOCK 256
+#define E6_BLOCK 128                    // configs[3] has 16384 games per GPU: 128 blocks = four warps on 128 of the 148 SMs (256: 64 SMs)
 #define E6_WORDS 28
 #define E6_IMG 108                      // sizeof(r6_state), oracle/risk6_oracle.h: the host image of one game
 #define E6_PLAYERS 6
@@ -86,10 +86,10 @@ __device__ __forceinline__ void e6_masks(E6Ctx& c)
 }
 __device__ __forceinline__ void e6_unpack(AzGame6& g, uint32_t w22, uint32_t w23, uint32_t w24, uint32_t w25, uint32_t w26)
 {
-    g.cards_lo = w22; g.cards_hi = w23 & 0xffffu; g.pools = w23 >> 16;
+    g.cards_lo = w22; g.cards_hi = w23 & 0xffffu; g.allow_draw = (w23 >> 16) & 0xffu; g.attacks = (w23 >> 24) & 0xffu;
     g.round = w24 & 0xffffu; g.cur = (w24 >> 16) & 0xffu; g.card_sets = (w24 >> 24) & 0xffu;
     g.reinf = w25 & 0xffu; g.phase = (w25 >> 8) & 0xffu; g.mob_from = (w25 >> 16) & 0xffu; g.mob_to = (w25 >> 24) & 0xffu;
-    g.allow_draw = w26 & 0xffu; g.attacks = (w26 >> 8) & 0xffu;
+    g.pools = w26 & 0xffffffu;
 }
 __device__ __forceinline__ void e6_load(E6Ctx& c, E6Smem& sm, const uint32_t* __restrict__ st, int n, int gi)
 {
@@ -104,10 +104,10 @@ __device__ __forceinline__ void e6_store(const E6Ctx& c, E6Smem& sm, uint32_t* _
     for (int w = 0; w < 22; ++w) st[(size_t)w * n + gi] = sm.col[w * E6_BLOCK + threadIdx.x];
     const AzGame6& g = c.g;
     st[(size_t)22 * n + gi] = g.cards_lo;
-    st[(size_t)23 * n + gi] = (g.cards_hi & 0xffffu) | (g.pools << 16);
+    st[(size_t)23 * n + gi] = (g.cards_hi & 0xffffu) | ((g.allow_draw & 0xffu) << 16) | ((g.attacks & 0xffu) << 24);
     st[(size_t)24 * n + gi] = (g.round & 0xffffu) | (g.cur << 16) | (g.card_sets << 24);
     st[(size_t)25 * n + gi] = (g.reinf & 0xffu) | (g.phase << 8) | (g.mob_from << 16) | (g.mob_to << 24);
-    st[(size_t)26 * n + gi] = (g.allow_draw & 0xffu) | ((g.attacks & 0xffu) << 8);
+    st[(size_t)26 * n + gi] = g.pools & 0xffffffu;
     st[(size_t)27 * n + gi] = c.ply;
 }
 

@@ -72,7 +72,7 @@ def test_deal_matches_oracle(api, n, first):
 def test_lockstep_play_vs_oracle(api, kw):
     """host-chosen legal actions (the oracle's random rule), dice from the Philox contract on the device: legal masks, status bytes
     and every byte of the state compared as the games go, through eliminations, trade-ins and game ends"""
-    n, steps, first = 96, 1500, 700
+    n, steps, first = 64, 2900, 700
     env = api.Env6(n, rules=api.default_rules(**kw), first_game_id=first)
     env.reset(SEED)
     games = [po.Oracle6Game(po.default_rules(**kw)) for _ in range(n)]
