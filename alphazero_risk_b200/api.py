@@ -139,6 +139,13 @@ def lib():
         L.az_env6_export.argtypes = [vp, vp, vp]
         L.az_env6_import.argtypes = [vp, vp, vp]
         L.az_env6_counters.argtypes = [vp, C.POINTER(AzCounters6), C.c_int, vp]
+        L.az_env6_encode.argtypes = [vp, vp, vp]
+        L.az_mcts6_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+        L.az_mcts6_destroy.argtypes = [vp]
+        L.az_mcts6_search.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+        L.az_mcts6_root_stats.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.az_selfplay6_run.argtypes = [vp, C.c_int, vp]
+        L.az_mcts6_counters.argtypes = [vp, C.POINTER(AzCounters6), u64, u64, u64, C.c_int, vp]
         L.az_dist_nccl_version.argtypes = [C.POINTER(C.c_int)]
         L.az_dist_init.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
         L.az_dist_unique_id.argtypes = [vp]
@@ -722,3 +729,48 @@ class Env6:
         c = AzCounters6()
         check(self.L.az_env6_counters(self.h, C.byref(c), int(reset), stream))
         return dict(steps=int(c.steps), games=int(c.games), draws=int(c.draws), wins=[int(c.wins[i]) for i in range(6)])
+
+    def encode(self, stream=None):
+        a = np.empty((self.n, 7, 6, 13), np.float32)
+        check(self.L.az_env6_encode(self.h, _ptr(a), stream))
+        return a
+
+
+class Mcts6:
+    """one search tree per six-player game of `env` (az_mcts6_*, SIXPLAYER.md); hyper-parameters come from env.rules"""
+
+    def __init__(self, env, net=None, evaluator=0, precision=0):
+        self.L, self.env, self.net, self.n = lib(), env, net, env.n
+        h = C.c_void_p()
+        check(self.L.az_mcts6_create(env.h, net.h if net is not None else None, evaluator, precision, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.az_mcts6_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def search(self, pick_mode=0, apply_move=False, stream=None):
+        n = self.n
+        N, pi = np.empty((n, MOVES), np.uint32), np.empty((n, MOVES), np.float32)
+        mv, st = np.empty(n, np.uint8), np.empty(n, np.int8)
+        check(self.L.az_mcts6_search(self.h, pick_mode, int(apply_move), _ptr(N), _ptr(pi), _ptr(mv), _ptr(st), stream))
+        return dict(N=N, pi=pi, move=mv, status=st)
+
+    def root_stats(self, stream=None):
+        n = self.n
+        q, p = np.empty((n, MOVES), np.float32), np.empty((n, MOVES), np.float32)
+        sumn, tab = np.empty(n, np.uint32), np.empty(n, np.int32)
+        check(self.L.az_mcts6_root_stats(self.h, _ptr(q), _ptr(p), _ptr(sumn), _ptr(tab), stream))
+        return dict(Q=q, P=p, sumN=sumn, table=tab)
+
+    def selfplay(self, n_moves, stream=None):
+        check(self.L.az_selfplay6_run(self.h, int(n_moves), stream))
+
+    def counters(self, reset=False, stream=None):
+        c, sims, evals, errs = AzCounters6(), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(self.L.az_mcts6_counters(self.h, C.byref(c), C.byref(sims), C.byref(evals), C.byref(errs), int(reset), stream))
+        return dict(steps=int(c.steps), games=int(c.games), draws=int(c.draws), wins=[int(c.wins[i]) for i in range(6)], sims=int(sims.value),
+                    evals=int(evals.value), errors=int(errs.value))

@@ -27,6 +27,7 @@ UNITS = {
     "az_nn_train.cu": ["-fmad=false"],   # training step: plain fp32, same roundings whatever the compiler would contract
     "az_ckpt.cpp": [],       # host only: TensorFlow V2 checkpoint bundles
     "az_env6.cu": ["-fmad=false"],   # six-player extension of the environment (SIXPLAYER.md), integer only
+    "az_mcts6.cu": ["-fmad=false"],  # six-player search: reference roundings (no FMA contraction), like az_mcts.cu
     "az_dist.cu": [],        # NCCL weight broadcast + statistics gather (NCCL itself is dlopen'ed at run time)
 }
 

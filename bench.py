@@ -427,6 +427,71 @@ def run_env6(args, api, torch, rank, local):
                 results={"games_finished": cnt["games"], "draws": cnt["draws"], "wins": cnt["wins"]}, gpu_launches=steps)
 
 
+def run_selfplay6(args, api, torch, dist, azd, rank, world, local, barrier):
+    """BASELINE configs[3] as written: six-player self-play, 16384 games x 200 simulations per move, trade-ins on — the EXTENSION of
+    SIXPLAYER.md (no reference semantics, parity unpinned; checker = oracle/risk6_oracle.c).  Same tower, same bf16 tcgen05 forward;
+    one move after one warm-up move."""
+    from alphazero_risk_b200 import dist as azdist
+    n, sims, blocks = args.cfg4_games, args.cfg4_sims, args.blocks
+    stream = torch.cuda.current_stream(); sptr = stream.cuda_stream
+    rules = api.default_rules(mcts_simulations=sims, threads_per_mcts=1)
+    env = api.Env6(n, rules=rules, device=local, first_game_id=rank * n)
+    env.reset(SEED, stream=sptr)
+    env.rollout(80, stream=sptr)                          # past the 78 set-up plies: attacks, trade-ins and eliminations are live
+    net = api.Net(blocks=blocks, device=local)
+    if rank == 0:
+        net.init_random(1234)
+    if azd is not None:
+        azd.broadcast_weights([net], 0)
+    net.finalize()
+    mc = api.Mcts6(env, net=net, evaluator=api.EVAL_NN, precision=api.BF16)
+    mc.selfplay(1, stream=sptr)
+    torch.cuda.synchronize()
+    mc.counters(reset=True, stream=sptr)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    mc.selfplay(1, stream=sptr)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = e0.elapsed_time(e1)
+    cnt = mc.counters(stream=sptr)
+    # e2e: one az_mcts6_search through the host-buffer ABI (state images in, visit counts / pi / moves / status out)
+    h_img = env.export(stream=sptr)
+    barrier()
+    t0 = time.perf_counter()
+    env.import_images(h_img, stream=sptr)
+    mc.search(pick_mode=api.PICK_SELFPLAY, apply_move=True, stream=sptr)
+    env.export(stream=sptr)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    tot = [float(cnt["sims"]), float(cnt["evals"]), float(cnt["errors"])]
+    if dist is not None:
+        dev_ms, e2e_ms = azdist.max_over_ranks([dev_ms, e2e_ms], dist)
+        tot = [float(v) for v in azd.gather_stats([[int(t) for t in tot]])[0]]
+    mc.close(); net.close(); env.close()
+    if rank != 0:
+        return None
+    _, tf_peak, src = measured_peaks()
+    achieved_tf = n * (sims + 1) * nn_flops_per_position(blocks) / (dev_ms * 1e-3) / 1e12
+    return dict(metric="mcts6_sims_per_sec", value=tot[0] / (dev_ms * 1e-3), unit="sims/s", ms_per_step=dev_ms, steps=1,
+                nn_evals_per_sec=tot[1] / (dev_ms * 1e-3),
+                config={"workload": "configs[3]: SIX-PLAYER self-play (extension, SIXPLAYER.md: no reference semantics, parity unpinned), %d games x "
+                                    "%d MCTS sims/move per GPU, simple-card trade-ins, %d-block graph, random-init weights, bf16 tcgen05 forward, "
+                                    "one move" % (n, sims, blocks), "games_per_gpu": n, "sims_per_move": sims, "blocks": blocks},
+                roofline={"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved_tf / tf_peak,
+                          **ncu_traffic("k_nn_conv_tc3"), "peak_source": src + " (sustained cuBLAS bf16)",
+                          "executed_frac": achieved_tf * 48.0 / 42.0 / tf_peak,
+                          "note": "as mcts.roofline; the six-player tree kernels (one warp per game, game logic on lane 0) are inside the time"},
+                clocks=clocks, e2e={"value": n * sims * world / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": n * 108,
+                                    "d2h_bytes_per_step": n * (43 * 8 + 2 + 108), "steps": 1},
+                gpu_launches=2 + (sims + 1) * (1 + 1 + 1 + 1 + 2 * blocks + 1), dtype="bf16 tower / fp32 tree", results={"table_errors": tot[2]})
+
+
 def run_train(args, api, torch, local):
     """SURVEY §8f N4: one optimizer step (AlphaZeroNN::train inner loop) on a batch of SETTINGS.BATCH_SIZE = 512 synthetic samples"""
     import numpy as np
@@ -622,6 +687,9 @@ def run_ours(args):
     env6_line = None
     if args.env6_games > 0 and rank == 0:
         env6_line = run_env6(args, api, torch, rank, local)
+    cfg4_line = None
+    if not args.no_selfplay and args.cfg4_games > 0:
+        cfg4_line = run_selfplay6(args, api, torch, dist, azd, rank, world, local, barrier)
 
     if rank == 0:
         hbm_peak, _, src = measured_peaks()
@@ -663,7 +731,7 @@ def run_ours(args):
         if mcts_line is not None:
             line["mcts"] = mcts_line
             line["gpu_launches"] += mcts_line["gpu_launches"]
-        for key, sub in (("cfg5", cfg5_line), ("blocks20", blocks20_line)):
+        for key, sub in (("cfg5", cfg5_line), ("blocks20", blocks20_line), ("cfg4", cfg4_line)):
             if sub is not None:
                 line[key] = sub
                 line["gpu_launches"] += sub["gpu_launches"]
@@ -706,6 +774,8 @@ def main():
     ap.add_argument("--blocks", type=int, default=5)
     ap.add_argument("--cfg5-games", type=int, default=16384, help="games per GPU of the configs[4] sub-line (0 skips it)")
     ap.add_argument("--cfg5-sims", type=int, default=800)
+    ap.add_argument("--cfg4-games", type=int, default=16384, help="games per GPU of the six-player self-play sub-line (configs[3]; 0 skips it)")
+    ap.add_argument("--cfg4-sims", type=int, default=200)
     ap.add_argument("--env6-games", type=int, default=16384, help="games of the six-player environment sub-line (configs[3]'s game; 0 skips it)")
     ap.add_argument("--no-blocks20", dest="blocks20", action="store_false", help="skip the 20-block (CMake default graph) sub-line")
     ap.add_argument("--train-batch", type=int, default=512, help="training-step measurement batch (SETTINGS.BATCH_SIZE); 0 skips it")

@@ -313,8 +313,7 @@ AZ_API int az_arena_play(az_arena* arena, uint64_t n_games, uint64_t seed, az_ar
    simple-card trade-ins as in the reference's default STATE_SIMPLE_CARDS mode) and whose only checker is oracle/risk6_oracle.c.
    Same action space (42 lands + skip), status byte (winner seat 0..5, AZ_STATUS_DRAW, AZ_STATUS_RUNNING / _ILLEGAL / _OVER),
    az_rules fields and Philox contract as az_env_*.  State image = AZ_ENV6_IMAGE_BYTES per game: army[42], owner[42], cards[6],
-   pool[6], round u16, cur, card_sets, reinf, phase, mob_from, mob_to, allow_draw, attacks, 2 pad bytes.  The search (az_mcts_*) and
-   the network encoding are two-player only; a six-player search is specified in SIXPLAYER.md and not built. */
+   pool[6], round u16, cur, card_sets, reinf, phase, mob_from, mob_to, allow_draw, attacks, 2 pad bytes. */
 typedef struct az_env6 az_env6;
 #define AZ_ENV6_IMAGE_BYTES 108
 typedef struct az_counters6 { uint64_t steps, games, draws, wins[6]; } az_counters6;
@@ -328,6 +327,19 @@ AZ_API int az_env6_query(az_env6* env, uint64_t* h_valid, int8_t* h_status, void
 AZ_API int az_env6_export(az_env6* env, uint8_t* h_images, void* stream);
 AZ_API int az_env6_import(az_env6* env, const uint8_t* h_images, void* stream);
 AZ_API int az_env6_counters(az_env6* env, az_counters6* h_out, int reset, void* stream);
+/* the six-seat network input: the reference's [n][7][6][13] tensor with "enemy" = the seat that moves next, "neutral" = every other
+   seat (SIXPLAYER.md), so the same tower evaluates it */
+AZ_API int az_env6_encode(az_env6* env, float* h_x, void* stream);
+/* the six-player SEARCH of SIXPLAYER.md: the reference's MCTS with the table cleared before every search and the six-seat value rule
+   (a leaf's value belongs to the seat to move there: +v for that seat's nodes on the path, -v / 5 for the others); one descent per tree
+   per leaf batch (THREADS_PER_MCTS = 1 semantics), hyper-parameters from the env's az_rules, evaluators and precisions as az_mcts_create */
+typedef struct az_mcts6 az_mcts6;
+AZ_API int az_mcts6_create(az_env6* env, az_nn* nn, int evaluator, int precision, az_mcts6** out);
+AZ_API int az_mcts6_destroy(az_mcts6* mcts);
+AZ_API int az_mcts6_search(az_mcts6* mcts, int pick_mode, int apply_move, uint32_t* h_visits, float* h_pi, uint8_t* h_move, int8_t* h_status, void* stream);
+AZ_API int az_mcts6_root_stats(az_mcts6* mcts, float* h_q, float* h_p, uint32_t* h_sumn, int32_t* h_table, void* stream);
+AZ_API int az_selfplay6_run(az_mcts6* mcts, int n_moves, void* stream);      /* n_moves moves of every game, finished games re-dealt */
+AZ_API int az_mcts6_counters(az_mcts6* mcts, az_counters6* h_out, uint64_t* h_sims, uint64_t* h_evals, uint64_t* h_errors, int reset, void* stream);
 
 /* ---------------------------------------------------------------- multi-GPU: NCCL over NVLink / NVSwitch, never inside a search
    Games shard over GPUs by contiguous global id (first_game_id of az_env_create) and never migrate; every GPU holds a full copy of

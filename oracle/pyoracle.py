@@ -528,3 +528,44 @@ class Oracle6Game:
 
     def set_image(self, img):
         C.memmove(C.byref(self.s), np.ascontiguousarray(img, np.uint8).ctypes.data, R6_STATE_BYTES)
+
+
+class Oracle6Mcts:
+    """the six-player search of SIXPLAYER.md on the oracle (table cleared per search, pseudo evaluator unless `eval_fn` is given)"""
+
+    def __init__(self, rules=None, eval_fn=None):
+        self.L = oracle_lib()
+        self.rules = rules if rules is not None else default_rules()
+        f32 = np.ctypeslib.ndpointer(np.float32, flags="C")
+        self.L.r6_mcts_new.restype = C.c_void_p
+        self.L.r6_mcts_new.argtypes = [C.c_void_p, C.c_void_p]
+        self.L.r6_mcts_free.argtypes = [C.c_void_p]
+        self.L.r6_mcts_table_size.argtypes = [C.c_void_p]
+        self.L.r6_mcts_search.argtypes = [C.c_void_p, C.POINTER(R6State), C.POINTER(RoRules), C.c_uint64, C.c_uint32, C.c_uint32,
+                                          np.ctypeslib.ndpointer(np.uint32, flags="C"), f32, f32, f32, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]
+        self.L.r6_encode.argtypes = [C.POINTER(R6State), f32]
+        self.h = self.L.r6_mcts_new(C.cast(eval_fn, C.c_void_p) if eval_fn is not None else None, None)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.r6_mcts_free(self.h)
+            self.h = None
+
+    def table_size(self):
+        return int(self.L.r6_mcts_table_size(self.h))
+
+    def search(self, game_obj, seed, game, ply):
+        N = np.zeros(MOVES, np.uint32)
+        Q, P, pi = np.zeros(MOVES, np.float32), np.zeros(MOVES, np.float32), np.zeros(MOVES, np.float32)
+        sumN, val = C.c_uint32(0), C.c_float(0)
+        rc = self.L.r6_mcts_search(self.h, C.byref(game_obj.s), C.byref(self.rules), seed, game, ply, N, Q, P, pi, C.byref(sumN), C.byref(val))
+        assert rc == 0, rc
+        return dict(N=N, Q=Q, P=P, pi=pi, sumN=int(sumN.value), value=float(val.value))
+
+    def pick(self, pi, sample, seed, game, ply):
+        return int(self.L.ro_pick_move(np.ascontiguousarray(pi, np.float32), int(sample), seed, game, ply))
+
+    def encode(self, game_obj):
+        x = np.zeros(INPUT_FLOATS, np.float32)
+        self.L.r6_encode(C.byref(game_obj.s), x)
+        return x

@@ -36,4 +36,16 @@ uint64_t r6_valid_moves(const r6_state* s, const ro_rules* r);
 int r6_game_status(const r6_state* s, const ro_rules* r);          /* winner seat 0..5, R6_DRAW, R6_NOT_ENDED */
 int r6_make_move(r6_state* s, int action, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply);
 int r6_random_action(const r6_state* s, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply);
+void r6_encode(const r6_state* s, float x[RO_INPUT_FLOATS]);
+
+/* search: the reference's MCTS with the table cleared per search and the six-seat value rule of SIXPLAYER.md; one descent at a
+   time; move choice = ro_pick_move (argmax / temperature sampling) as in the two-player game */
+typedef void (*r6_eval_fn)(const r6_state* s, float policy[RO_MOVES], float* value, void* user);
+typedef struct r6_mcts r6_mcts;
+void r6_eval_pseudo(const r6_state* s, float policy[RO_MOVES], float* value, void* user);
+r6_mcts* r6_mcts_new(r6_eval_fn eval, void* user);
+void r6_mcts_free(r6_mcts* m);
+int r6_mcts_table_size(const r6_mcts* m);
+int r6_mcts_search(r6_mcts* m, const r6_state* root, const ro_rules* r, uint64_t seed, uint32_t game, uint32_t ply,
+                   uint32_t N[RO_MOVES], float Q[RO_MOVES], float P[RO_MOVES], float pi[RO_MOVES], uint32_t* sumN, float* root_value);
 #endif

@@ -4,7 +4,7 @@
 # _selfplay), then tools/traffic_from_ncu.py --sha gpurun_out/<tag>_source_sha.json ... -> profiles/traffic.json
 set -x
 TAG=${1:-r2}
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --sp-moves 1 --sp-steps 2 --play-games 0 --train-batch 0 --cfg5-games 0 --no-blocks20 --env6-games 0"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --sp-moves 1 --sp-steps 2 --play-games 0 --train-batch 0 --cfg5-games 0 --no-blocks20 --env6-games 0 --cfg4-games 0"
 python tools/source_sha.py > gpurun_out/${TAG}_source_sha.json
 $CMD > gpurun_out/${TAG}_prof_plain.json 2> gpurun_out/${TAG}_prof_plain.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_prof_ncu1.log 2>&1
