@@ -112,6 +112,7 @@ def lib():
         L.az_mcts_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
         L.az_mcts_destroy.argtypes = [vp]
         L.az_mcts_simulations.argtypes = [vp]
+        L.az_mcts_set_cohorts.argtypes = [vp, C.c_int]
         L.az_mcts_clear.argtypes = [vp, vp]
         L.az_mcts_search.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
         L.az_mcts_root_stats.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -536,6 +537,10 @@ class Mcts:
 
     def clear(self, stream=None):
         check(self.L.az_mcts_clear(self.h, stream))
+
+    def set_cohorts(self, cohorts):
+        """0 = automatic, 1 = one stream, 2 = two game cohorts on two streams wherever possible (az_mcts_set_cohorts)"""
+        check(self.L.az_mcts_set_cohorts(self.h, int(cohorts)))
 
     def search(self, pick_mode=PICK_ARGMAX, apply_move=False, extra_trim=None, stream=None):
         n = self.n

@@ -46,6 +46,7 @@ enum { CNT_SIMS = 0, CNT_EVALS = 1, CNT_POOL_OVERFLOW = 2, CNT_DEPTH_OVERFLOW = 
 
 struct MctsDev {
     int n, cap, H, dmax;
+    int g0, gcount;         // the games this launch of k_mcts_sim works on: [g0, g0 + gcount) (a cohort; the whole range otherwise)
     int K;                  // descents per tree that select before any backs up (az_rules.concurrent_descents); slot = j * n + game
     uint32_t* nodes;        // [n][2][cap][NODE_WORDS]
     uint32_t* index;        // [n][2][H]     0 = empty, else tag16 << 16 | (node + 1)
@@ -426,8 +427,8 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_sim(MctsDev m, const u
     __syncthreads();
     AzTables T = az_tables_from_smem(s_tab);
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int gi = blockIdx.x * MCTS_WARPS + warp;
-    if (gi >= m.n) return;
+    int gi = m.g0 + blockIdx.x * MCTS_WARPS + warp;
+    if (gi >= m.g0 + m.gcount) return;
     if (m.side_sel && m.side_sel[gi] != (uint8_t)m.side) return;
     WG w; wg_bind(w, s_w, warp);
     const uint32_t cur = m.epoch[gi] & 1u;
@@ -621,6 +622,12 @@ struct az_mcts {
     const int32_t* eval_games = nullptr;   // device list of the participating games, ascending
     int eval_count = 0;                    // its length; 0 = every slot is evaluated
     uint32_t* d_leaf_c = nullptr; float* d_pol_c = nullptr; float* d_val_c = nullptr;   // compacted leaf batch [16][m], [m][43], [m]
+    // two game cohorts on two streams (az_mcts_set_cohorts): while one cohort's leaf batch is in the tower, the other cohort's tree
+    // kernel, state packing, stem and head tail run, and the pairs of SMs a tower layer's last wave leaves idle go to the other
+    // cohort's layer.  Games are independent, so the results do not depend on the cohort count.
+    int cohorts = 0;                       // 0 = automatic (two cohorts when every condition of use_cohorts() holds), 1 = off, 2 = on where possible
+    cudaStream_t cohort_stream[2] = { nullptr, nullptr };
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = { nullptr, nullptr };
     std::vector<void*> allocs;
 };
 
@@ -655,6 +662,7 @@ extern "C" int az_mcts_create(az_env* env, az_nn* nn, int evaluator, int precisi
     MctsDev& d = mc->d;
     memset(&d, 0, sizeof d);
     d.n = az_env_n(env); d.K = K;
+    d.g0 = 0; d.gcount = d.n;
     d.cap = 3 * (sims + 1) + 64; if (d.cap > 65000) d.cap = 65000;
     d.H = next_pow2(2 * d.cap);
     d.dmax = 192;
@@ -692,7 +700,17 @@ extern "C" int az_mcts_destroy(az_mcts* mc)
     if (!mc) return AZ_OK;
     AzDeviceGuard guard(mc->device);
     for (void* p : mc->allocs) cudaFree(p);
+    for (int c = 0; c < 2; ++c) { if (mc->cohort_stream[c]) cudaStreamDestroy(mc->cohort_stream[c]); if (mc->ev_join[c]) cudaEventDestroy(mc->ev_join[c]); }
+    if (mc->ev_fork) cudaEventDestroy(mc->ev_fork);
     delete mc;
+    return AZ_OK;
+}
+
+extern "C" int az_mcts_set_cohorts(az_mcts* mc, int cohorts)
+{
+    AZ_REQUIRE(mc != nullptr, "mcts is NULL");
+    AZ_REQUIRE(cohorts >= 0 && cohorts <= 2, "cohorts: 0 = automatic, 1 = one stream, 2 = two game cohorts on two streams");
+    mc->cohorts = cohorts;
     return AZ_OK;
 }
 
@@ -715,6 +733,14 @@ extern "C" int az_mcts_clear(az_mcts* mc, void* stream)
 
 // k_used = descents per tree whose leaves this batch holds: K for a simulation round, 1 for the root round (setRootState uses
 // descent slot 0 only, so the other K - 1 slots of every game would be evaluated for nothing)
+// the leaf batch of ONE cohort (games [g0, g0 + gcount), one descent per tree): the cohort's slice of the SoA leaf arrays goes
+// through the tower with the cohort's own set of work buffers, on the cohort's stream
+static int evaluate_cohort(az_mcts* mc, cudaStream_t s, int cohort, int g0, int gcount)
+{
+    MctsDev& d = mc->d;
+    return az_nn_tc_forward(mc->nn, nullptr, d.leaf_state + g0, gcount, d.nn_policy + (size_t)g0 * AZ_MOVES, d.nn_value + g0, s, d.n * d.K, cohort, true);
+}
+
 static int evaluate_leaves(az_mcts* mc, cudaStream_t s, int k_used)
 {
     if (mc->evaluator != EVAL_NN) return AZ_OK;
@@ -745,6 +771,18 @@ static int evaluate_leaves(az_mcts* mc, cudaStream_t s, int k_used)
     return az_nn_forward_dev(mc->nn, mc->d_x, nb, d.nn_policy, d.nn_value, AZ_NN_FP32, s);
 }
 
+// Two cohorts pay when the tower dominates and a half batch still fills the device: tensor-core evaluator, one descent per tree (a
+// cohort's leaves are then one contiguous slice), every game searching (no arena compaction / side selection), and at least 2048
+// games (1024 per cohort = 192 tile pairs = 2.6 waves per layer; the other cohort's layer fills the tail)
+static bool use_cohorts(const az_mcts* mc)
+{
+    if (mc->cohorts == 1) return false;
+    const MctsDev& d = mc->d;
+    const bool possible = mc->evaluator == EVAL_NN && mc->precision == AZ_NN_BF16 && d.K == 1 && mc->eval_count == 0 && d.side_sel == nullptr && d.n >= 8;
+    if (mc->cohorts == 2) return possible;
+    return possible && d.n >= 2048;
+}
+
 // one AlphaZeroMCTS::simulate (alphazero_mcts.cpp:255-287) for every game, then the move choice
 static int search_once(az_mcts* mc, int extra_all, int pick_mode, int apply_move, int auto_reset, cudaStream_t s)
 {
@@ -752,16 +790,45 @@ static int search_once(az_mcts* mc, int extra_all, int pick_mode, int apply_move
     // the network may have been trained, restored or overwritten since the last search: fold + pack the current weights first
     if (mc->evaluator == EVAL_NN && !mc->nn->finalized) { int frc = az_nn_finalize(mc->nn); if (frc) return frc; }
     d.seed = az_env_seed(mc->env); d.first_game = az_env_first_game(mc->env);
+    d.g0 = 0; d.gcount = d.n;
     const uint64_t* tab = az_device_tables();
     int grid = (d.n + MCTS_WARPS - 1) / MCTS_WARPS, sims = az_mcts_simulations(mc);
     k_mcts_begin<<<grid, MCTS_WARPS * 32, 0, s>>>(d, extra_all);
-    k_mcts_sim<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, -1, 1);             // setRootState
     AZ_CUDA(cudaGetLastError());
-    int rc = evaluate_leaves(mc, s, 1); if (rc) return rc;
-    for (int i = 0; i < sims / d.K; ++i) {               // rounds of K descents per tree
-        k_mcts_sim<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, i, 1);
+    if (use_cohorts(mc)) {
+        if (!mc->ev_fork) {
+            AZ_CUDA(cudaEventCreateWithFlags(&mc->ev_fork, cudaEventDisableTiming));
+            for (int c = 0; c < 2; ++c) {
+                AZ_CUDA(cudaStreamCreateWithFlags(&mc->cohort_stream[c], cudaStreamNonBlocking));
+                AZ_CUDA(cudaEventCreateWithFlags(&mc->ev_join[c], cudaEventDisableTiming));
+            }
+        }
+        int rc = az_nn_reserve(mc->nn, d.n); if (rc) return rc;
+        const int split = (d.n / 2 + MCTS_WARPS - 1) / MCTS_WARPS * MCTS_WARPS;      // cohort 0 = games [0, split), cohort 1 = the rest
+        const int g0[2] = { 0, split }, gc[2] = { split, d.n - split };
+        AZ_CUDA(cudaEventRecord(mc->ev_fork, s));
+        for (int c = 0; c < 2; ++c) AZ_CUDA(cudaStreamWaitEvent(mc->cohort_stream[c], mc->ev_fork, 0));
+        for (int i = -1; i < sims; ++i) {                 // round -1 = setRootState; the cohorts' launches alternate so both streams stay fed
+            for (int c = 0; c < 2; ++c) {
+                MctsDev dc = d; dc.g0 = g0[c]; dc.gcount = gc[c];
+                k_mcts_sim<<<(gc[c] + MCTS_WARPS - 1) / MCTS_WARPS, MCTS_WARPS * 32, 0, mc->cohort_stream[c]>>>(dc, tab, i, 1);
+                AZ_CUDA(cudaGetLastError());
+                rc = evaluate_cohort(mc, mc->cohort_stream[c], c, g0[c], gc[c]); if (rc) return rc;
+            }
+        }
+        for (int c = 0; c < 2; ++c) {
+            AZ_CUDA(cudaEventRecord(mc->ev_join[c], mc->cohort_stream[c]));
+            AZ_CUDA(cudaStreamWaitEvent(s, mc->ev_join[c], 0));
+        }
+    } else {
+        k_mcts_sim<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, -1, 1);             // setRootState
         AZ_CUDA(cudaGetLastError());
-        rc = evaluate_leaves(mc, s, d.K); if (rc) return rc;
+        int rc = evaluate_leaves(mc, s, 1); if (rc) return rc;
+        for (int i = 0; i < sims / d.K; ++i) {               // rounds of K descents per tree
+            k_mcts_sim<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, i, 1);
+            AZ_CUDA(cudaGetLastError());
+            rc = evaluate_leaves(mc, s, d.K); if (rc) return rc;
+        }
     }
     k_mcts_finish<<<grid, MCTS_WARPS * 32, 0, s>>>(d, tab, pick_mode, apply_move, auto_reset);
     AZ_CUDA(cudaGetLastError());

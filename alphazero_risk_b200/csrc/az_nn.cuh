@@ -55,8 +55,10 @@ int az_nn_tc_prepare(az_nn* nn);            // fold BN, pack bf16 weight tiles; 
 void az_nn_tc_release(az_nn* nn);
 // x: fp32 [n][7][6][13] (or NULL when env_state is given: encode fused into the stem; env_state = SoA words with stride
 // state_stride >= n between words, 0 = n)
+// scratch_set: which of the two sets of work buffers to use (two forwards of one network may be in flight on two streams);
+// shared_device: another forward shares the device right now (no programmatic dependent launch between the layers, see az_nn_tc.cu)
 int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, int n, float* d_policy, float* d_value, cudaStream_t s,
-                     int state_stride = 0);
+                     int state_stride = 0, int scratch_set = 0, bool shared_device = false);
 
 // raw 3x3 convolution of the training step on the tower kernel (az_nn_tc.cu): fp32 [n * 42][256] in, fp32 HWIO device weights
 // [9][256][256] (flip = 1: the data gradient's kernel), fp32 [n * 42][256] out; bf16 operands, fp32 accumulation

@@ -56,17 +56,25 @@ template <int KCH> struct TcShape {
     static constexpr int smem_bytes(int nv) { return 2 * nv * A_BYTES + TC_STAGES * STAGE_BYTES + 2 * 256 * 4 + 32 * 8 + 16; }
 };
 
-struct AzTcState {
-    int cap_boards = 0, n_tiles = 0, r_alloc = 0, n_sm = 148;
+// work buffers of one forward in flight.  Two sets exist so that two forwards of the same network (the two game cohorts of a
+// search, az_mcts.cu) can be in flight on two streams at once; everything else in AzTcState is read-only during a forward.
+struct AzTcScratch {
+    int cap_boards = 0, n_tiles = 0, r_alloc = 0;
     __nv_bfloat16* d_act[3] = { nullptr, nullptr, nullptr };   // [32][r_alloc][8]
-    __nv_bfloat16* d_in = nullptr;                             // [2][r_alloc][8]: encoded input, 13 channels padded to 16
-    uint8_t* d_wpacked = nullptr;                              // [2*blocks] x 1.18 MB tower weights, then the 72 KB stem weights
+    __nv_bfloat16* d_in = nullptr;                             // [3][2][r_alloc][8]: encoded input, 13 channels padded to 16, three copies
+    size_t in_var_stride = 0;                                  // elements between the three copies of the encoded input
+    float4* d_head_z = nullptr;                                // [cap_boards * 42] (pi0, pi1, v, -) per board cell, written by the last tower layer
+};
+#define AZ_TC_SCRATCH_SETS 2
+
+struct AzTcState {
+    int n_sm = 148;
+    AzTcScratch scratch[AZ_TC_SCRATCH_SETS];
+    uint8_t* d_wpacked = nullptr;                              // the 72 KB stem weight stages
     int max_pairs = 74;                                        // CTA pairs of k_nn_conv_tc3 the device holds at once
     uint8_t* d_wpacked3 = nullptr;                             // tower weights for k_nn_conv_tc3: [K group][tap][half]
-    size_t in_var_stride = 0;                                  // elements between the three copies of the encoded input (three-copy layout)
     float* d_scale = nullptr; float* d_shift = nullptr;        // [2*blocks][256] folded BN, then [256] (7 used) for the stem's row BN
     float4* d_head_w = nullptr;                                // [256] (pi0, pi1, v, 0): the heads' 1x1 convolutions, per input channel
-    float4* d_head_z = nullptr;                                // [cap_boards * 42] (pi0, pi1, v, -) per board cell, written by the last tower layer
 };
 
 #include "az_tc_ptx.cuh"
@@ -740,7 +748,7 @@ static void pack_conv_pair(const float* w, __nv_bfloat16* dst, bool kb_outer = t
 // heads != NULL: the last layer — no activation out, per-cell head sums to head_z instead (T3_HEADS)
 static cudaError_t launch_conv_pair3(int grid, cudaStream_t s, const __nv_bfloat16* in, const uint8_t* w3, const float* scale, const float* shift,
                                      const __nv_bfloat16* skip, __nv_bfloat16* out, int n_boards, int r_alloc, int n_tiles,
-                                     const float4* head_w = nullptr, float4* head_z = nullptr)
+                                     const float4* head_w = nullptr, float4* head_z = nullptr, bool pdl = true)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(T3_THREADS); cfg.stream = s;
@@ -751,7 +759,9 @@ static cudaError_t launch_conv_pair3(int grid, cudaStream_t s, const __nv_bfloat
     // programmatic dependent launch between consecutive layers: the next layer's barrier / TMEM set-up overlaps this layer's last wave
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 2;
+    // (off when two forwards share the device: a successor parked on an SM pair in griddepcontrol.wait would keep the other
+    // forward's layer from filling the pairs this layer's last wave leaves idle)
+    cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
     if (head_w)
         return cudaLaunchKernelEx(&cfg, k_nn_conv_tc3<T3_HEADS>, in, w3, scale, shift, skip, out, n_boards, r_alloc, n_tiles,
                                   reinterpret_cast<float*>(head_z), head_w);
@@ -1180,14 +1190,17 @@ void az_nn_tc_release(az_nn* nn)
 {
     if (!nn->tc) return;
     AzTcState* tc = nn->tc;
-    for (int i = 0; i < 3; ++i) cudaFree(tc->d_act[i]);
-    cudaFree(tc->d_in); cudaFree(tc->d_wpacked); cudaFree(tc->d_wpacked3); cudaFree(tc->d_scale); cudaFree(tc->d_shift);
-    cudaFree(tc->d_head_w); cudaFree(tc->d_head_z);
+    for (AzTcScratch& sc : tc->scratch) {
+        for (int i = 0; i < 3; ++i) cudaFree(sc.d_act[i]);
+        cudaFree(sc.d_in); cudaFree(sc.d_head_z);
+    }
+    cudaFree(tc->d_wpacked); cudaFree(tc->d_wpacked3); cudaFree(tc->d_scale); cudaFree(tc->d_shift);
+    cudaFree(tc->d_head_w);
     delete tc;
     nn->tc = nullptr;
 }
 
-static int tc_reserve(AzTcState* tc, int n)
+static int tc_reserve(AzTcScratch* tc, int n)
 {
     if (n <= tc->cap_boards) return AZ_OK;
     for (int i = 0; i < 3; ++i) { cudaFree(tc->d_act[i]); tc->d_act[i] = nullptr; }
@@ -1211,11 +1224,13 @@ static int tc_reserve(AzTcState* tc, int n)
 }
 
 int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, int n, float* d_policy, float* d_value, cudaStream_t s,
-                     int state_stride)
+                     int state_stride, int scratch_set, bool shared_device)
 {
     if (state_stride < n) state_stride = n;
-    AzTcState* tc = nn->tc;
-    if (!tc || !tc->d_wpacked) { az_set_error("network not finalized"); return AZ_ERR_NOT_READY; }
+    AzTcState* st = nn->tc;
+    if (!st || !st->d_wpacked) { az_set_error("network not finalized"); return AZ_ERR_NOT_READY; }
+    if (scratch_set < 0 || scratch_set >= AZ_TC_SCRATCH_SETS) { az_set_error("scratch set out of range"); return AZ_ERR_INVALID_ARG; }
+    AzTcScratch* tc = &st->scratch[scratch_set];
     int rc = tc_reserve(tc, n); if (rc) return rc;
     // from game states (d_x == NULL): one kernel packs the stem's bf16 input straight from the states; from an fp32 tensor:
     // k_nn_pack_input_tc.  Same expressions and roundings on both routes (tests/test_mcts_gpu.py compares a search fed by the
@@ -1223,16 +1238,16 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
     const bool from_state = d_x == nullptr;
     // buffers are sized for cap_boards; only the tiles that hold boards of this call are computed
     const int tiles = (n * TC_RPB + TC_TILE_ROWS - 1) / TC_TILE_ROWS;
-    const int grid = tiles < tc->n_sm ? tiles : tc->n_sm;
+    const int grid = tiles < st->n_sm ? tiles : st->n_sm;
     const int layers = 2 * nn->blocks;
     int cur = 0, tmp = 1, nxt = 2;
     if (from_state) k_nn_pack_state_tc<<<(n + 3) / 4, 128, 0, s>>>(d_env_state, n, state_stride, tc->d_in, tc->r_alloc, tc->in_var_stride);
     else k_nn_pack_input_tc<<<(n * 42 + 255) / 256, 256, 0, s>>>(d_x, n, tc->d_in, tc->r_alloc, tc->in_var_stride);
     AZ_CUDA(cudaGetLastError());
-    AZ_CUDA((launch_conv<2, true, 3>(grid, s, tc->d_in, tc->d_wpacked, tc->d_scale + layers * 256, tc->d_shift + layers * 256, nullptr, tc->d_act[cur], n,
+    AZ_CUDA((launch_conv<2, true, 3>(grid, s, tc->d_in, st->d_wpacked, st->d_scale + layers * 256, st->d_shift + layers * 256, nullptr, tc->d_act[cur], n,
                                      tc->r_alloc, tiles, tc->in_var_stride * 2)));
     const int pitems = (tiles + 1) / 2;
-    const int pgrid = 2 * (pitems < tc->max_pairs ? pitems : tc->max_pairs);
+    const int pgrid = 2 * (pitems < st->max_pairs ? pitems : st->max_pairs);
     for (int i = 0; i < nn->blocks; ++i) {
         for (int h = 0; h < 2; ++h) {                        // branch2a: cur -> tmp; branch2b: tmp (+ cur as the residual) -> nxt
             const int L = 2 * i + h;
@@ -1240,8 +1255,8 @@ int az_nn_tc_forward(az_nn* nn, const float* d_x, const uint32_t* d_env_state, i
             const __nv_bfloat16* res = h ? tc->d_act[cur] : nullptr;
             __nv_bfloat16* dst = h ? tc->d_act[nxt] : tc->d_act[tmp];
             const bool last = L == layers - 1;              // the last layer feeds the heads directly: no activation store
-            AZ_CUDA(launch_conv_pair3(pgrid, s, src, tc->d_wpacked3 + (size_t)L * TC_LAYER_BYTES, tc->d_scale + L * 256, tc->d_shift + L * 256, res, dst, n,
-                                      tc->r_alloc, tiles, last ? tc->d_head_w : nullptr, last ? tc->d_head_z : nullptr));
+            AZ_CUDA(launch_conv_pair3(pgrid, s, src, st->d_wpacked3 + (size_t)L * TC_LAYER_BYTES, st->d_scale + L * 256, st->d_shift + L * 256, res, dst, n,
+                                      tc->r_alloc, tiles, last ? st->d_head_w : nullptr, last ? tc->d_head_z : nullptr, !shared_device));
         }
         int o = cur; cur = nxt; nxt = o;
     }

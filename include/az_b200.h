@@ -242,6 +242,11 @@ typedef struct az_mcts az_mcts;
    Replaces AlphaZeroMCTS (player/alpha_zero/alphazero_mcts.h:75-94) with THREADS_PER_MCTS = 1 semantics. */
 AZ_API int az_mcts_create(az_env* env, az_nn* nn, int evaluator, int precision, az_mcts** out);
 AZ_API int az_mcts_destroy(az_mcts* mcts);
+/* Two game cohorts on two CUDA streams inside a search: while one cohort's leaf batch is in the tower the other cohort's tree kernel,
+   state packing, stem and head tail run, and the SM pairs a tower layer's last wave leaves idle go to the other cohort's layer.
+   Games are independent, so results do not depend on the setting.  0 = automatic (tensor-core evaluator, one descent per tree,
+   every game searching, >= 2048 games), 1 = one stream, 2 = two cohorts wherever the conditions other than the game count hold */
+AZ_API int az_mcts_set_cohorts(az_mcts* mcts, int cohorts);
 AZ_API int az_mcts_simulations(const az_mcts* mcts);
 /* StateSimulationsStorage::clearNodes for every game (AlphaZeroPlayer::newGame, alphazero_player.cpp:31-34) */
 AZ_API int az_mcts_clear(az_mcts* mcts, void* stream);

@@ -334,3 +334,34 @@ def test_fused_state_packing_matches_the_tensor_route(api):
             assert move[g] == mv and o.move(mv, SEED, first + g, start + k) == 0
         assert (final[g] == o.data()).all(), g
     mc.close(); env.close(); net.close()
+
+
+@pytest.mark.parametrize("n", [70, 2500])
+def test_two_cohorts_change_nothing(api, n):
+    """az_mcts_set_cohorts: the games of a search split into two cohorts on two CUDA streams (one cohort's tree kernel / packing /
+    stem under the other's tower, each with its own set of tower work buffers).  Games are independent: visit counts, pi, moves,
+    counters and final states must equal the one-stream search bit for bit.  70 games force the cohort path below its automatic
+    threshold (ragged halves, less than one tile pair each); 2500 games take it automatically."""
+    sims = 10
+    rules = api.default_rules(mcts_simulations=sims, threads_per_mcts=1)
+    net = api.Net(blocks=2, seed=31)
+    out = {}
+    for mode in (1, 2 if n < 2048 else 0):
+        env = api.Env(n, rules=rules, first_game_id=5000)
+        env.reset(SEED)
+        env.rollout(120)
+        mc = api.Mcts(env, net=net, evaluator=api.EVAL_NN, precision=api.BF16)
+        mc.set_cohorts(mode)
+        res = []
+        for _ in range(3):
+            r = mc.search(pick_mode=api.PICK_SELFPLAY, apply_move=True)
+            res.append((r["N"].copy(), r["pi"].copy(), r["move"].copy()))
+        mc.selfplay(2)
+        out[mode] = (res, mc.counters(), env.export_aos().copy())
+        assert out[mode][1]["errors"] == 0
+        mc.close(); env.close()
+    (a, ca, fa), (b, cb, fb) = out.values()
+    for (n1, p1, m1), (n2, p2, m2) in zip(a, b):
+        assert (n1 == n2).all() and (bits(p1) == bits(p2)).all() and (m1 == m2).all()
+    assert ca == cb and (fa == fb).all()
+    net.close()
