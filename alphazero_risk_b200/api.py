@@ -113,6 +113,7 @@ def lib():
         L.az_mcts_destroy.argtypes = [vp]
         L.az_mcts_simulations.argtypes = [vp]
         L.az_mcts_set_cohorts.argtypes = [vp, C.c_int]
+        L.az_mcts_pool_stats.argtypes = [vp, u64, u64, u64, vp]
         L.az_mcts_clear.argtypes = [vp, vp]
         L.az_mcts_search.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
         L.az_mcts_root_stats.argtypes = [vp, vp, vp, vp, vp, vp, vp]
@@ -537,6 +538,12 @@ class Mcts:
 
     def clear(self, stream=None):
         check(self.L.az_mcts_clear(self.h, stream))
+
+    def pool_stats(self, stream=None):
+        """(peak nodes in any game's pool, nodes per pool, table bytes per game)"""
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(self.L.az_mcts_pool_stats(self.h, C.byref(a), C.byref(b), C.byref(c), stream))
+        return int(a.value), int(b.value), int(c.value)
 
     def set_cohorts(self, cohorts):
         """0 = automatic, 1 = one stream, 2 = two game cohorts on two streams wherever possible (az_mcts_set_cohorts)"""

@@ -42,7 +42,7 @@
 
 enum { EVAL_NN = 0, EVAL_PSEUDO = 1, EVAL_UNIFORM = 2 };
 #define REC_BYTES AZ_SAMPLE_BYTES
-enum { CNT_SIMS = 0, CNT_EVALS = 1, CNT_POOL_OVERFLOW = 2, CNT_DEPTH_OVERFLOW = 3, CNT_STEPS = 4, CNT_GAMES = 5, CNT_W0 = 6, CNT_W1 = 7, CNT_DRAW = 8, CNT_ILLEGAL = 9, CNT_PATH = 10, CNT_N = 12 };
+enum { CNT_SIMS = 0, CNT_EVALS = 1, CNT_POOL_OVERFLOW = 2, CNT_DEPTH_OVERFLOW = 3, CNT_STEPS = 4, CNT_GAMES = 5, CNT_W0 = 6, CNT_W1 = 7, CNT_DRAW = 8, CNT_ILLEGAL = 9, CNT_PATH = 10, CNT_POOL_PEAK = 11, CNT_N = 12 };
 
 struct MctsDev {
     int n, cap, H, dmax;
@@ -507,6 +507,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) k_mcts_finish(MctsDev m, cons
             if (lane == 0) {
                 m.out_move[gi] = (uint8_t)move; m.out_value[gi] = value; m.out_sumn[gi] = sumn;
                 m.out_table[gi] = (int32_t)(m.count[gi * 2 + cur] + m.count[gi * 2 + (cur ^ 1u)] - m.migrated[gi]);
+                atomicMax(&m.counters[CNT_POOL_PEAK], (unsigned long long)m.count[gi * 2 + cur]);     // fullest pool so far (az_mcts_pool_stats)
             }
         }
         if (apply_move && m.rec_out) {
@@ -958,6 +959,23 @@ extern "C" int az_mcts_counters(az_mcts* mc, az_counters* h_out, uint64_t* h_err
     h_out->sims = h[CNT_SIMS]; h_out->evals = h[CNT_EVALS]; h_out->steps = h[CNT_STEPS]; h_out->games = h[CNT_GAMES];
     h_out->wins[0] = h[CNT_W0]; h_out->wins[1] = h[CNT_W1]; h_out->draws = h[CNT_DRAW]; h_out->illegal = h[CNT_ILLEGAL]; h_out->path_nodes = h[CNT_PATH];
     if (h_errors) *h_errors = h[CNT_POOL_OVERFLOW] + h[CNT_DEPTH_OVERFLOW];
+    return AZ_OK;
+}
+
+// How full the node pools get: peak = the largest number of nodes any game's current pool held at the end of a search since the
+// counters were last reset, capacity = nodes per pool (3 x (simulations + 1) + 64; a pool that would overflow is counted in
+// az_mcts_counters' h_errors).  The pools are sized for the worst case; this is the measured occupancy next to it.
+extern "C" int az_mcts_pool_stats(az_mcts* mc, uint64_t* h_peak_nodes, uint64_t* h_capacity_nodes, uint64_t* h_bytes_per_game, void* stream)
+{
+    AZ_REQUIRE(mc != nullptr, "mcts is NULL");
+    AzDeviceGuard guard(mc->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long peak = 0;
+    AZ_CUDA(cudaMemcpyAsync(&peak, mc->d.counters + CNT_POOL_PEAK, sizeof peak, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    if (h_peak_nodes) *h_peak_nodes = peak;
+    if (h_capacity_nodes) *h_capacity_nodes = (uint64_t)mc->d.cap;
+    if (h_bytes_per_game) *h_bytes_per_game = 2ull * (uint64_t)mc->d.cap * NODE_WORDS * 4ull + 2ull * (uint64_t)mc->d.H * 4ull;
     return AZ_OK;
 }
 

@@ -278,6 +278,7 @@ def run_selfplay(args, api, torch, dist, azd, rank, world, local, barrier, shape
     sp_clocks = sampler.stop() if rank == 0 else None
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     cnt = mc.counters(stream=sptr)
+    pool_peak, pool_cap, pool_bytes = mc.pool_stats(stream=sptr)
     # e2e: the call a host-side game loop makes per move — State images in from pinned host memory (az_env_import_aos), one
     # az_mcts_search through the host-buffer ABI (visit counts, pi, moves, status copied back), images out again; as many moves as
     # the device-timed region above
@@ -354,7 +355,9 @@ def run_selfplay(args, api, torch, dist, azd, rank, world, local, barrier, shape
                 e2e={"value": n * sims * e2e_moves * world / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": n * 160,
                      "d2h_bytes_per_step": n * (43 * 8 + 2 + 160), "steps": e2e_moves},
                 gpu_launches=steps * moves_per_step * (2 + (sims // K + 1) * (1 + 1 + 1 + 2 * blocks + 1)),   # begin, finish; per round: tree, pack, stem, tower, heads
-                dtype="bf16 tower / fp32 tree", results={"games_finished": tot_games, "table_errors": errors}, tree=tree)
+                dtype="bf16 tower / fp32 tree", results={"games_finished": tot_games, "table_errors": errors}, tree=tree,
+                node_pools={"peak_nodes": pool_peak, "capacity_nodes": pool_cap, "bytes_per_game": pool_bytes,
+                            "note": "rank 0; fullest pool of any game at the end of a search / nodes per pool (worst-case sizing, overflow = table_errors)"})
 
 
 def run_play(args, api, torch, rank, local):

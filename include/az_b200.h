@@ -242,6 +242,10 @@ typedef struct az_mcts az_mcts;
    Replaces AlphaZeroMCTS (player/alpha_zero/alphazero_mcts.h:75-94) with THREADS_PER_MCTS = 1 semantics. */
 AZ_API int az_mcts_create(az_env* env, az_nn* nn, int evaluator, int precision, az_mcts** out);
 AZ_API int az_mcts_destroy(az_mcts* mcts);
+/* node-pool occupancy: the fullest pool any game had at the end of a search since the counters were reset, the capacity of a pool
+   (3 x (simulations + 1) + 64 nodes, worst-case sizing; overflows are counted in az_mcts_counters' h_errors) and the table bytes
+   held per game (two pools + two hash indices) */
+AZ_API int az_mcts_pool_stats(az_mcts* mcts, uint64_t* h_peak_nodes, uint64_t* h_capacity_nodes, uint64_t* h_bytes_per_game, void* stream);
 /* Two game cohorts on two CUDA streams inside a search: while one cohort's leaf batch is in the tower the other cohort's tree kernel,
    state packing, stem and head tail run, and the SM pairs a tower layer's last wave leaves idle go to the other cohort's layer.
    Games are independent, so results do not depend on the setting.  0 = automatic (tensor-core evaluator, one descent per tree,

@@ -103,6 +103,8 @@ def test_800_simulations_fit_the_node_pools(api):
     for _ in range(3):
         res = mc.search(pick_mode=api.PICK_SELFPLAY, apply_move=True)
     assert mc.counters()["errors"] == 0
+    peak, cap, per_game = mc.pool_stats()                     # measured occupancy next to the worst-case sizing
+    assert cap == 3 * (sims + 1) + 64 and sims < peak <= cap and per_game >= 2 * cap * 640
     rs = mc.root_stats()
     assert (res["N"].sum(axis=1) == rs["sumN"]).all() and (rs["sumN"] >= sims).all()
     # one game replayed on the oracle
