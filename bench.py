@@ -565,13 +565,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist, azd = None, None
     if world > 1:
-        # several ranks share the host: keep this rank's threads (and the pinned buffers they allocate) on the CPUs next to its GPU
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
-        except Exception as e:      # noqa: BLE001 - affinity is an optimisation only
-            sys.stderr.write("bench.py: GPU CPU-affinity not set (%s)\n" % e)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         # the product's own multi-GPU entry points (az_dist_*, NCCL): rank 0's communicator id travels over the launcher's channel
