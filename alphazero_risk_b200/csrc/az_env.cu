@@ -88,8 +88,10 @@ const uint64_t* az_device_tables()
 #ifndef ENV_BLOCK
 // The rollout kernel is bound by the latency of each warp's dependent instructions, so what matters is how many warps share an SM's
 // schedulers.  65536 games are 13.8 warps per SM: 448-thread blocks make 147 blocks = one per SM = 14 warps on every SM, where
-// 256-thread blocks put two blocks (16 warps) on 108 SMs and one on 40.  Swept on B200 (tools/env_block.sh, G steps/s):
-// 32..128: 13.7-13.8 (before the wide tables), 224: 15.3, 256: 15.1, 320: 13.0, 448: 15.85.  Static shared memory stays under 48 KB.
+// 256-thread blocks put two blocks (16 warps) on 108 SMs and one on 40.  Swept on B200 with the lane-per-game rollout (G steps/s):
+// 32..128: 13.7-13.8 (before the wide tables), 224: 15.3, 256: 15.1, 320: 13.0, 448: 15.85; the pooled rollout keeps 448 games per
+// block and gains nothing from more warps than that (512 / 576 / 640 threads: +0.5 / -0.5 / -1.3 %).  Static shared memory of the
+// other kernels stays under 48 KB.
 #define ENV_BLOCK 448
 #endif
 #define ENV_COL_WORDS 22     // 11 land words + 11 fortify-DFS parent words per thread
@@ -225,67 +227,237 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_query(const uint32_t* __restr
     if (status) status[gi] = (int8_t)az_game_status(c.g, rules);
 }
 
-// BASELINE config 2: n_steps uniform-random legal moves per game inside one launch; the state stays in registers /
-// shared memory between moves, finished games are re-dealt in place.  Structured around what ncu showed of the first version
-// (every lane running az_valid_moves / az_make_move as written for the single-step kernel; profiles/README.md): ~60 % of its
-// instructions were the fortify component search and the re-deal executing with 1-2 active lanes.  Here
-//   * the common work of a move (status, legal mask with ONE neighbour union, Philox block, action pick, land writes,
-//     attack-army check) is one instruction stream for all lanes (az_valid_moves_flat / az_move_flat);
-//   * a lane whose move needs the component search, or whose game ended, PARKS; parked lanes are served together once
-//     `park_f` / `park_r` of them have accumulated (or nothing else in the warp can run), so the long serial paths run
-//     with many lanes active instead of one.  A parked lane simply finishes its n_steps a little later: games are
-//     independent and their random streams are keyed by (game, ply), so the interleaving does not change any result.
-__global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
-                                                            int n_steps, uint64_t seed, uint32_t first_game, AzRulesDev rules,
-                                                            unsigned long long* __restrict__ counters, int park_f, int park_r)
+// ---------------------------------------------------------------- the rollout as a pool of games per block
+// BASELINE config 2: n_steps uniform-random legal moves per game inside one launch; the state stays in shared memory between
+// moves, finished games are re-dealt in place.  The common work of a move (legal mask with ONE neighbour union, Philox block,
+// action pick, land writes, attack-army check) is one instruction stream for all phases (az_valid_moves_flat / az_move_flat).
+// ncu on the lane-per-game kernel (round 1 / first half of round 2: every lane owns one game for the whole launch, lanes that need
+// a re-deal or the fortify component search park until a few of them have accumulated in their warp): 12.8 of 32 lanes active per
+// issued instruction — 42 % of the issue slots went to the parked-lane services running with <= 7 lanes and to phase-specific code.
+// Here a block's games are not tied to a lane.  Their contexts (land bytes, masks, scalars, ply, moves done: 28 words) live in shared
+// memory, there is one queue of game slots per CATEGORY — ATTACK, the other five round phases, "needs a re-deal", "needs the
+// component search" — and every warp repeatedly takes up to 32 games of ONE category, loads their contexts into its lanes (land
+// bytes into the lane's private column, so the rules code is the same thread code as everywhere else and stays free of bank
+// conflicts), makes one move per game, stores the contexts and appends each game to the queue of its new category.  Re-deals and
+// component searches of the whole block are thus served in batches of 16+ while nobody waits for them.  No block-wide barrier
+// (round 1's sorted kernel lost to its three __syncthreads per move): warps meet only in the queues' shared-memory atomics.  A
+// game finishes its n_steps whenever it gets there; games are independent and their random streams are keyed by (game, ply), so
+// the order does not change any result.  Measured (profiles/README.md): 26 games per warp-step, 20-23 active lanes per issued
+// instruction, +18 % steps/s over the lane-per-game kernel; grouping all six phases in one queue or one queue per phase both lose.
+#define ENV_POOL_SLOTS ENV_BLOCK                 // games per block (the grid is env_grid(n), as for every other env kernel)
+#define ENV_POOL_CTX_Q 7                         // uint4 per game context (28 words, 25 used)
+#define ENV_POOL_NCAT 4
+#define ENV_CAT_OTHER 0
+#define ENV_CAT_ATTACK 1
+#define ENV_CAT_REDEAL 2
+#define ENV_CAT_FORTIFY 3
+#define ENV_CAT_NONE 4
+#define ENV_POOL_NSUB 8                          // rings per category: slot % 8 (see the comment at the struct)
+#define ENV_POOL_QSUB 64                         // ring entries: more than the ENV_POOL_SLOTS / ENV_POOL_NSUB games that can ever be in one
+#define ENV_POOL_MIN_BATCH 16                    // re-deals / component searches are served once this many wait (swept 8..32 on B200)
+
+// A category's queue is EIGHT rings, one per slot % 8, and lane l of a taking warp is served from ring l % 8.  The eight lanes of a
+// quarter-warp then hold slots with eight different residues, so their 16-byte context accesses (112-byte stride: residues 0..7
+// map to the eight 16-byte bank groups) are free of bank conflicts — with one ring per category the random slots of a batch cost
+// ~2.2 wavefronts per ideal one and the shared-memory pipe sat at 60 % (ncu), which every other latency of the kernel then paid for.
+// It also spreads the queue atomics over eight words per category and lets every lane append its own game without any warp-level
+// grouping.
+struct EnvSmemPool {                             // starts like EnvSmemWide / EnvSmem: the per-thread helpers above work on it unchanged
+    uint64_t tab[AZ_TABLE_U64];
+    uint32_t col[ENV_COL_WORDS * ENV_BLOCK];     // per LANE: the land words + DFS parents of the game the lane works on right now
+    uint64_t lut11[AZ_LUT11_U64];
+    uint4 ctx[ENV_POOL_SLOTS * ENV_POOL_CTX_Q];  // per GAME
+    uint16_t q[ENV_POOL_NCAT][ENV_POOL_NSUB][ENV_POOL_QSUB];    // slot + 1, 0 = not written yet
+    uint32_t head[ENV_POOL_NCAT][ENV_POOL_NSUB], tail[ENV_POOL_NCAT][ENV_POOL_NSUB];
+    int cnt[ENV_POOL_NCAT][ENV_POOL_NSUB];       // appended and not yet taken (briefly negative while a taker over-reserves)
+    uint32_t remaining;                          // games that still have moves to make
+};
+
+__device__ __forceinline__ void pool_load(EnvCtx& c, EnvSmem& sm, const uint4* __restrict__ ctx, int slot, int& done, int& park_li)
+{
+    const uint4* p = ctx + slot * ENV_POOL_CTX_Q;
+    const uint4 a = p[0], b = p[1], d = p[2], e = p[3], f = p[4], h = p[5], k = p[6];
+    uint32_t* col = sm.col + threadIdx.x;
+    col[0 * ENV_BLOCK] = a.x; col[1 * ENV_BLOCK] = a.y; col[2 * ENV_BLOCK] = a.z; col[3 * ENV_BLOCK] = a.w;
+    col[4 * ENV_BLOCK] = b.x; col[5 * ENV_BLOCK] = b.y; col[6 * ENV_BLOCK] = b.z; col[7 * ENV_BLOCK] = b.w;
+    col[8 * ENV_BLOCK] = d.x; col[9 * ENV_BLOCK] = d.y; col[10 * ENV_BLOCK] = d.z;
+    az_unpack_scalars(c.g, d.z, d.w, e.x, e.y);
+    c.ply = e.z; done = (int)e.w;
+    c.g.own0 = (uint64_t)f.x | ((uint64_t)f.y << 32); c.g.own1 = (uint64_t)f.z | ((uint64_t)f.w << 32);
+    c.g.gt1 = (uint64_t)h.x | ((uint64_t)h.y << 32); c.g.full = (uint64_t)h.z | ((uint64_t)h.w << 32);
+    park_li = (int)k.x;
+}
+
+__device__ __forceinline__ void pool_store(const EnvCtx& c, const EnvSmem& sm, uint4* __restrict__ ctx, int slot, int done, int park_li)
+{
+    const uint32_t* col = sm.col + threadIdx.x;
+    uint4* p = ctx + slot * ENV_POOL_CTX_Q;
+    p[0] = make_uint4(col[0 * ENV_BLOCK], col[1 * ENV_BLOCK], col[2 * ENV_BLOCK], col[3 * ENV_BLOCK]);
+    p[1] = make_uint4(col[4 * ENV_BLOCK], col[5 * ENV_BLOCK], col[6 * ENV_BLOCK], col[7 * ENV_BLOCK]);
+    const uint32_t w10 = (col[10 * ENV_BLOCK] & 0xffffu) | (c.g.cards0 << 16) | (c.g.cards1 << 24);
+    p[2] = make_uint4(col[8 * ENV_BLOCK], col[9 * ENV_BLOCK], w10, az_pack_w11(c.g));
+    p[3] = make_uint4(az_pack_w12(c.g), az_pack_w13(c.g), c.ply, (uint32_t)done);
+    p[4] = make_uint4((uint32_t)c.g.own0, (uint32_t)(c.g.own0 >> 32), (uint32_t)c.g.own1, (uint32_t)(c.g.own1 >> 32));
+    p[5] = make_uint4((uint32_t)c.g.gt1, (uint32_t)(c.g.gt1 >> 32), (uint32_t)c.g.full, (uint32_t)(c.g.full >> 32));
+    p[6] = make_uint4((uint32_t)park_li, 0u, 0u, 0u);
+}
+
+// where a game goes next: nowhere once its n_steps are done, to the re-deal queue when it has ended (its result is counted
+// here, once), else to the queue of its round phase
+__device__ __forceinline__ int pool_phase_cat(uint32_t ph) { return ph == AZ_PH_ATTACK ? ENV_CAT_ATTACK : ENV_CAT_OTHER; }
+
+// where a game goes next: nowhere once its n_steps are done, to the re-deal queue when it has ended (its result is counted
+// here, once), else to the queue of its round phase
+__device__ __forceinline__ int pool_classify(const AzGame& g, int done, int n_steps, const AzRulesDev& rules,
+                                             unsigned& games, unsigned& w0, unsigned& w1, unsigned& dr)
+{
+    if (done >= n_steps) return ENV_CAT_NONE;
+    const int stt = az_game_status(g, rules);
+    if (stt != AZ_STATUS_RUNNING) { games++; w0 += stt == 0; w1 += stt == 1; dr += stt == AZ_STATUS_DRAW; return ENV_CAT_REDEAL; }
+    return pool_phase_cat(g.phase);
+}
+
+// appends the lane's game to the queue of its new category (newcat < 0 or ENV_CAT_NONE: nothing to append)
+__device__ __forceinline__ void pool_push(EnvSmemPool& sp, int newcat, int slot)
+{
+    if (newcat >= 0 && newcat < ENV_POOL_NCAT) {
+        const int r = slot & (ENV_POOL_NSUB - 1);
+        const uint32_t pos = atomicAdd(&sp.tail[newcat][r], 1u);
+        sp.q[newcat][r][pos & (ENV_POOL_QSUB - 1)] = (uint16_t)(slot + 1);
+        atomicAdd(&sp.cnt[newcat][r], 1);                               // a taker that gets ahead of the entry's store spins on the entry
+    }
+}
+
+// which category the warp serves next.  Lane l looks at ring l % 8 of category l / 8 (a warp can take up to 4 games from each ring);
+// a re-deal / component-search batch once ENV_POOL_MIN_BATCH of them wait, else the fuller of the two move queues (ties alternate),
+// else whatever is left.  Returns (priority << 2) | rotated category, 0 = every queue is empty.
+__device__ __forceinline__ uint32_t pool_choose(const EnvSmemPool& sp, int lane, unsigned rot)
+{
+    const int grp = lane >> 3, sub = lane & 7;
+    int a = *reinterpret_cast<const volatile int*>(&sp.cnt[grp][sub]);
+    a = a < 0 ? 0 : (a > 4 ? 4 : a);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    const uint32_t pr = grp >= ENV_CAT_REDEAL ? (a >= ENV_POOL_MIN_BATCH ? 64u + (uint32_t)a : (a ? 1u : 0u)) : (a ? 8u + (uint32_t)a : 0u);
+    const uint32_t score = sub == 0 ? (pr << 2) | (((uint32_t)grp + rot) & 3u) : 0u;
+    return __reduce_max_sync(0xffffffffu, score);
+}
+
+__global__ void __launch_bounds__(ENV_BLOCK, 1) k_env_rollout(uint32_t* __restrict__ st, int n, const uint64_t* __restrict__ g_tab,
+                                                               int n_steps, uint64_t seed, uint32_t first_game, AzRulesDev rules,
+                                                               unsigned long long* __restrict__ counters)
 {
     extern __shared__ __align__(16) unsigned char env_dyn_smem[];
+    EnvSmemPool& sp = *reinterpret_cast<EnvSmemPool*>(env_dyn_smem);
     EnvSmemWide& smw = *reinterpret_cast<EnvSmemWide*>(env_dyn_smem);
     EnvSmem& sm = *reinterpret_cast<EnvSmem*>(env_dyn_smem);
-    const AzTablesWide T = env_stage_tables_wide(smw, g_tab);
-    const int gi = blockIdx.x * ENV_BLOCK + threadIdx.x;
+    for (int i = threadIdx.x; i < ENV_POOL_NCAT * ENV_POOL_NSUB * ENV_POOL_QSUB; i += ENV_BLOCK) (&sp.q[0][0][0])[i] = 0;
+    if (threadIdx.x < ENV_POOL_NCAT * ENV_POOL_NSUB) { (&sp.head[0][0])[threadIdx.x] = 0; (&sp.tail[0][0])[threadIdx.x] = 0; (&sp.cnt[0][0])[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) sp.remaining = 0;
+    const AzTablesWide T = env_stage_tables_wide(smw, g_tab);              // __syncthreads inside
+    const int lane = threadIdx.x & 31;
+    const int gi0 = blockIdx.x * ENV_POOL_SLOTS, gi = gi0 + (int)threadIdx.x;
     const bool live = gi < n;
     unsigned games = 0, w0 = 0, w1 = 0, dr = 0;
-    int done = 0;
     EnvCtx c;
-    if (live) env_load(c, sm, st, n, gi); else { env_bind(c, sm); c.g = AzGame(); c.ply = 0; }
-    const uint32_t game = first_game + (uint32_t)gi;
-    int parked = 0, park_li = 0;                       // 0 = running, 1 = waiting for a re-deal, 2 = waiting for the component search
+    {
+        // every thread brings its own game in and queues it
+        int cat = -1;
+        if (live) {
+            env_load(c, sm, st, n, gi);
+            cat = pool_classify(c.g, 0, n_steps, rules, games, w0, w1, dr);
+            pool_store(c, sm, sp.ctx, (int)threadIdx.x, 0, 0);
+        } else env_bind(c, sm);
+        const int nq = __popc(__ballot_sync(0xffffffffu, cat >= 0 && cat < ENV_POOL_NCAT));
+        if (lane == 0 && nq) atomicAdd(&sp.remaining, (uint32_t)nq);
+        __threadfence_block();
+        pool_push(sp, cat, (int)threadIdx.x);
+    }
+    __syncthreads();
+    unsigned rot = threadIdx.x >> 5;
+    const int sub = lane & (ENV_POOL_NSUB - 1), grp = lane >> 3;           // ring this lane is served from; its place in the ring's batch of 4
+    uint32_t best = pool_choose(sp, lane, rot);
     for (;;) {
-        const bool active = live && done < n_steps;
-        const unsigned m_active = __ballot_sync(0xffffffffu, active);
-        if (!m_active) break;
-        const unsigned m_r = __ballot_sync(0xffffffffu, active && parked == 1);
-        const unsigned m_f = __ballot_sync(0xffffffffu, active && parked == 2);
-        const bool nobody_runs = (m_active & ~(m_r | m_f)) == 0;
-        if (m_r && (__popc(m_r) >= park_r || nobody_runs)) {
-            if (active && parked == 1) { az_new_game(c.g, c.land, seed, game, c.ply); parked = 0; }
+        if ((best >> 2) == 0) {
+            if (*reinterpret_cast<volatile uint32_t*>(&sp.remaining) == 0) break;
+            __nanosleep(64);
+            best = pool_choose(sp, lane, rot);
+            continue;
         }
-        if (m_f && (__popc(m_f) >= park_f || nobody_runs)) {
-            if (active && parked == 2) { az_fortify_finish(c.g, c.land, c.scratch, T, park_li); parked = 0; c.ply++; done++; }
+        const int cat = (int)(((best & 3u) - rot) & 3u);
+        // lanes 0..7 each take up to 4 games from one ring: reserve 4 at once and give back what was not there
+        int kq = 0; uint32_t hq = 0;
+        if (lane < ENV_POOL_NSUB) {
+            const int old = atomicSub(&sp.cnt[cat][lane], 4);
+            kq = old >= 4 ? 4 : (old > 0 ? old : 0);
+            if (kq < 4) atomicAdd(&sp.cnt[cat][lane], 4 - kq);
+            if (kq) hq = atomicAdd(&sp.head[cat][lane], (uint32_t)kq);
         }
-        if (live && done < n_steps && parked == 0) {
-            const int stt = az_game_status(c.g, rules);
-            if (stt != AZ_STATUS_RUNNING) {
-                games++; w0 += stt == 0; w1 += stt == 1; dr += stt == AZ_STATUS_DRAW;
-                parked = 1;
-            } else {
+        kq = __shfl_sync(0xffffffffu, kq, sub); hq = __shfl_sync(0xffffffffu, hq, sub);
+        const bool has = grp < kq;
+        if (!__any_sync(0xffffffffu, has)) { best = pool_choose(sp, lane, rot); continue; }
+        ++rot;
+        int slot = -1;
+        if (has) {
+            volatile uint16_t* e = &sp.q[cat][sub][(hq + (uint32_t)grp) & (ENV_POOL_QSUB - 1)];
+            uint16_t v;
+            while ((v = *e) == 0) { }
+            *e = 0;
+            slot = (int)v - 1;
+        }
+        __threadfence_block();
+        int newcat = -1, done = 0, park_li = 0;
+        if (slot >= 0) {
+            pool_load(c, sm, sp.ctx, slot, done, park_li);
+            const uint32_t game = first_game + (uint32_t)(gi0 + slot);
+            if (cat == ENV_CAT_REDEAL) {
+                az_new_game(c.g, c.land, seed, game, c.ply);
+                newcat = pool_phase_cat(c.g.phase);
+            } else if (cat == ENV_CAT_FORTIFY) {
+                az_fortify_finish(c.g, c.land, c.scratch, T, park_li);
+                c.ply++; done++;
+                newcat = pool_classify(c.g, done, n_steps, rules, games, w0, w1, dr);
+            } else if (cat == ENV_CAT_ATTACK) {
+                // the batch's phase is known here: the compiler drops the other phases' selects and branches from this copy
+                __builtin_assume(c.g.phase == AZ_PH_ATTACK);
                 const uint64_t valid = az_valid_moves_flat(c.g, T, rules);
                 const az_u32x4 blk = az_rng_block(seed, game, c.ply, AZ_STREAM_REAL, 0);
                 const int action = az_nth_set_bit(valid, az_mulhi32(blk.y, (uint32_t)__popcll(valid)));
-                if (az_move_flat(c.g, c.land, T, rules, action, blk.x)) { parked = 2; park_li = action; }
-                else { c.ply++; done++; }
+                az_move_flat(c.g, c.land, T, rules, action, blk.x);
+                c.ply++; done++;
+                newcat = pool_classify(c.g, done, n_steps, rules, games, w0, w1, dr);
+            } else {
+                __builtin_assume(c.g.phase != AZ_PH_ATTACK);
+                const uint64_t valid = az_valid_moves_flat(c.g, T, rules);
+                const az_u32x4 blk = az_rng_block(seed, game, c.ply, AZ_STREAM_REAL, 0);
+                const int action = az_nth_set_bit(valid, az_mulhi32(blk.y, (uint32_t)__popcll(valid)));
+                if (az_move_flat(c.g, c.land, T, rules, action, blk.x)) { newcat = ENV_CAT_FORTIFY; park_li = action; }
+                else { c.ply++; done++; newcat = pool_classify(c.g, done, n_steps, rules, games, w0, w1, dr); }
             }
         }
+        // the next choice is made BEFORE this batch goes back (it may miss the warp's own games, which is harmless): its
+        // load -> shuffle -> reduce chain then overlaps the context stores below instead of standing alone between two steps
+        best = pool_choose(sp, lane, rot);
+        if (slot >= 0) pool_store(c, sm, sp.ctx, slot, done, park_li);
+        __threadfence_block();
+        pool_push(sp, newcat, slot);
+        const int nfin = __popc(__ballot_sync(0xffffffffu, newcat == ENV_CAT_NONE));
+        if (lane == 0 && nfin) atomicSub(&sp.remaining, (uint32_t)nfin);
     }
-    if (live) env_store(c, sm, st, n, gi);
-    unsigned steps = live ? (unsigned)done : 0u;
+    __syncthreads();
+    unsigned steps = 0;
+    if (live) {
+        int done, park_li;
+        pool_load(c, sm, sp.ctx, (int)threadIdx.x, done, park_li);
+        env_store(c, sm, st, n, gi);
+        steps = (unsigned)done;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         steps += __shfl_xor_sync(0xffffffffu, steps, o); games += __shfl_xor_sync(0xffffffffu, games, o);
         w0 += __shfl_xor_sync(0xffffffffu, w0, o); w1 += __shfl_xor_sync(0xffffffffu, w1, o); dr += __shfl_xor_sync(0xffffffffu, dr, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         atomicAdd(&counters[0], (unsigned long long)steps);
         if (games) atomicAdd(&counters[1], (unsigned long long)games);
         if (w0) atomicAdd(&counters[2], (unsigned long long)w0);
@@ -293,8 +465,6 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_rollout(uint32_t* __restrict_
         if (dr) atomicAdd(&counters[4], (unsigned long long)dr);
     }
 }
-
-
 
 // staging of the samples scripted / random turns emit (Player::addTrainingSample), per game; st == NULL: not recording
 struct TurnRecDev {
@@ -941,16 +1111,13 @@ extern "C" int az_env_rollout(az_env* e, int n_steps, void* stream)
     AzDeviceGuard guard(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     AZ_CUDA(cudaEventRecord(e->ev0, s));
-    // how many parked lanes a warp collects before it runs the component search / the re-deal for them: swept on B200
-    // (park_f 4..12 x park_r 1..8, profiles/README.md) -> 8 / 3
-    constexpr int park_f = 8, park_r = 3;
-    static bool smem_set[64] = { false };                      // 64 KB of wide tables + columns: above the 48 KB default
+    static bool smem_set[64] = { false };                      // wide tables + lane columns + game contexts: above the 48 KB default
     if (!smem_set[e->device & 63]) {
-        AZ_CUDA(cudaFuncSetAttribute(k_env_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmemWide)));
+        AZ_CUDA(cudaFuncSetAttribute(k_env_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnvSmemPool)));
         smem_set[e->device & 63] = true;
     }
-    k_env_rollout<<<env_grid(e->n), ENV_BLOCK, sizeof(EnvSmemWide), s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
-                                                                        dev_rules(e->rules), e->d_counters, park_f, park_r);
+    k_env_rollout<<<env_grid(e->n), ENV_BLOCK, sizeof(EnvSmemPool), s>>>(e->d_state, e->n, az_device_tables(), n_steps, e->seed, e->first_game,
+                                                                        dev_rules(e->rules), e->d_counters);
     AZ_CUDA(cudaGetLastError());
     AZ_CUDA(cudaEventRecord(e->ev1, s));
     e->timed = true;

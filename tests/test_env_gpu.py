@@ -165,6 +165,35 @@ def test_rollout_matches_oracle_including_redeals(api, kw):
     env.close()
 
 
+@pytest.mark.parametrize("n,launches", [(1, (0, 1, 250)), (7, (3, 200)), (33, (150, 1, 0, 60)), (449, (90, 40)), (1000, (64, 65))])
+def test_rollout_pool_sizes_and_launch_lengths(api, n, launches):
+    """the pooled rollout (games queued per category inside a block) with block fills it is not tuned for — one game, fewer games than a
+    warp, one game over a block (448 slots), a partly filled last block — and with launches of 0 / 1 / few moves: every game makes
+    exactly the requested number of moves, in its own (game, ply) stream"""
+    first = 4000
+    env = api.Env(n, first_game_id=first)
+    env.reset(SEED)
+    for k in launches:
+        env.rollout(k)
+    steps = sum(launches)
+    dev = env.export_aos()
+    cnt = env.counters()
+    games = 0
+    o = po.OracleGame(po.default_rules())
+    for g in range(n):
+        o.new_game(SEED, first + g, 0)
+        ply = 0
+        for _ in range(steps):
+            if o.status() != -1:
+                games += 1
+                o.new_game(SEED, first + g, ply)
+            assert o.move(o.random_action(SEED, first + g, ply), SEED, first + g, ply) == 0
+            ply += 1
+        assert (dev[g] == o.data()).all(), g
+    assert cnt["steps"] == n * steps and cnt["games"] == games
+    env.close()
+
+
 def test_full_size_rollout_properties(api):
     """BASELINE config 2 size: 65536 games; size-independent properties instead of a CPU replay"""
     n, steps = 65536, 1000
