@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_query(const uint32_t* __restr
 #define ENV_CAT_FORTIFY 3
 #define ENV_CAT_NONE 4
 #define ENV_POOL_NSUB 8                          // rings per category: slot % 8 (see the comment at the struct)
-#define ENV_POOL_QSUB 64                         // ring entries: more than the ENV_POOL_SLOTS / ENV_POOL_NSUB games that can ever be in one
+#define ENV_POOL_QSUB 64                         // ring cells: more than the ENV_POOL_SLOTS / ENV_POOL_NSUB games that can ever be in one
 static_assert(ENV_POOL_SLOTS / ENV_POOL_NSUB < ENV_POOL_QSUB && ENV_POOL_SLOTS % 32 == 0 && ENV_POOL_NCAT * ENV_POOL_NSUB == 32, "ring sizing");
 #define ENV_POOL_MIN_BATCH 16                    // re-deals / component searches are served once this many wait (swept 8..32 on B200)
 
@@ -268,7 +268,10 @@ struct EnvSmemPool {                             // starts like EnvSmemWide / En
     uint32_t col[ENV_COL_WORDS * ENV_BLOCK];     // per LANE: the land words + DFS parents of the game the lane works on right now
     uint64_t lut11[AZ_LUT11_U64];
     uint4 ctx[ENV_POOL_SLOTS * ENV_POOL_CTX_Q];  // per GAME
-    uint16_t q[ENV_POOL_NCAT][ENV_POOL_NSUB][ENV_POOL_QSUB];    // slot + 1, 0 = not written yet
+    // ring cell = (sequence << 16) | slot.  Position p (a 32-bit counter, cell p % QSUB) may be written when the cell's sequence is
+    // p (mod 2^16), holds its game when it is p + 1, and is handed to position p + QSUB by its taker: a bounded multi-producer /
+    // multi-consumer queue that stays correct however long a warp stalls between reserving a position and using it
+    uint32_t q[ENV_POOL_NCAT][ENV_POOL_NSUB][ENV_POOL_QSUB];
     uint32_t head[ENV_POOL_NCAT][ENV_POOL_NSUB], tail[ENV_POOL_NCAT][ENV_POOL_NSUB];
     int cnt[ENV_POOL_NCAT][ENV_POOL_NSUB];       // appended and not yet taken (briefly negative while a taker over-reserves)
     uint32_t remaining;                          // games that still have moves to make
@@ -324,8 +327,10 @@ __device__ __forceinline__ void pool_push(EnvSmemPool& sp, int newcat, int slot)
     if (newcat >= 0 && newcat < ENV_POOL_NCAT) {
         const int r = slot & (ENV_POOL_NSUB - 1);
         const uint32_t pos = atomicAdd(&sp.tail[newcat][r], 1u);
-        sp.q[newcat][r][pos & (ENV_POOL_QSUB - 1)] = (uint16_t)(slot + 1);
-        atomicAdd(&sp.cnt[newcat][r], 1);                               // a taker that gets ahead of the entry's store spins on the entry
+        volatile uint32_t* e = &sp.q[newcat][r][pos & (ENV_POOL_QSUB - 1)];
+        while ((*e >> 16) != (pos & 0xffffu)) { }                        // the cell's previous lap has been taken (it has, unless a warp stalled for a whole lap)
+        *e = (((pos + 1u) & 0xffffu) << 16) | (uint32_t)slot;
+        atomicAdd(&sp.cnt[newcat][r], 1);                               // a taker that gets ahead of the cell's store spins on the cell
     }
 }
 
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(ENV_BLOCK, 1) k_env_rollout(uint32_t* __restri
     EnvSmemPool& sp = *reinterpret_cast<EnvSmemPool*>(env_dyn_smem);
     EnvSmemWide& smw = *reinterpret_cast<EnvSmemWide*>(env_dyn_smem);
     EnvSmem& sm = *reinterpret_cast<EnvSmem*>(env_dyn_smem);
-    for (int i = threadIdx.x; i < ENV_POOL_NCAT * ENV_POOL_NSUB * ENV_POOL_QSUB; i += ENV_BLOCK) (&sp.q[0][0][0])[i] = 0;
+    for (int i = threadIdx.x; i < ENV_POOL_NCAT * ENV_POOL_NSUB * ENV_POOL_QSUB; i += ENV_BLOCK) (&sp.q[0][0][0])[i] = (uint32_t)(i & (ENV_POOL_QSUB - 1)) << 16;
     if (threadIdx.x < ENV_POOL_NCAT * ENV_POOL_NSUB) { (&sp.head[0][0])[threadIdx.x] = 0; (&sp.tail[0][0])[threadIdx.x] = 0; (&sp.cnt[0][0])[threadIdx.x] = 0; }
     if (threadIdx.x == 0) sp.remaining = 0;
     const AzTablesWide T = env_stage_tables_wide(smw, g_tab);              // __syncthreads inside
@@ -400,11 +405,12 @@ __global__ void __launch_bounds__(ENV_BLOCK, 1) k_env_rollout(uint32_t* __restri
         ++rot;
         int slot = -1;
         if (has) {
-            volatile uint16_t* e = &sp.q[cat][sub][(hq + (uint32_t)grp) & (ENV_POOL_QSUB - 1)];
-            uint16_t v;
-            while ((v = *e) == 0) { }
-            *e = 0;
-            slot = (int)v - 1;
+            const uint32_t pos = hq + (uint32_t)grp;
+            volatile uint32_t* e = &sp.q[cat][sub][pos & (ENV_POOL_QSUB - 1)];
+            uint32_t v;
+            while (((v = *e) >> 16) != ((pos + 1u) & 0xffffu)) { }
+            *e = ((pos + ENV_POOL_QSUB) & 0xffffu) << 16;
+            slot = (int)(v & 0xffffu);
         }
         __threadfence_block();
         int newcat = -1, done = 0, park_li = 0;
