@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_env_query(const uint32_t* __restr
 // component searches of the whole block are thus served in batches of 16+ while nobody waits for them.  No block-wide barrier
 // (round 1's sorted kernel lost to its three __syncthreads per move): warps meet only in the queues' shared-memory atomics.  A
 // game finishes its n_steps whenever it gets there; games are independent and their random streams are keyed by (game, ply), so
-// the order does not change any result.  Measured (profiles/README.md): 26 games per warp-step, 20-23 active lanes per issued
-// instruction, +18 % steps/s over the lane-per-game kernel; grouping all six phases in one queue or one queue per phase both lose.
+// the order does not change any result.  Measured (profiles/README.md): 26 games per warp-step, 20 active lanes per issued
+// instruction, +22 % steps/s over the lane-per-game kernel; grouping all six phases in one queue or one queue per phase both lose.
 #define ENV_POOL_SLOTS ENV_BLOCK                 // games per block (the grid is env_grid(n), as for every other env kernel)
 #define ENV_POOL_CTX_Q 7                         // uint4 per game context (28 words, 25 used)
 #define ENV_POOL_NCAT 4

@@ -722,8 +722,7 @@ def run_ours(args):
                                    "note": "achieved = ALGORITHMIC bytes (330 B/step x games x moves per launch, SURVEY 8d) / CUDA-event time of "
                                            "k_env_rollout, as the metric contract asks; it is NOT the kernel's DRAM rate: the state stays on chip "
                                            "for the moves of a launch (traffic = ncu DRAM bytes of one launch, dram_achieved = traffic / time), "
-                                           "so the kernel is bound by instruction issue / latency — see issue_roofline; for the same reason frac is not capped at 1 "
-                                           "(the pooled rollout passes the rate a kernel that streamed 330 B per step through HBM could reach)"},
+                                           "so the kernel is bound by instruction issue / latency — see issue_roofline; for the same reason frac is not capped at 1"},
                                   **env_traffic),
                     issue_roofline=env_issue,
                     e2e={"value": e2e_games * S * e2e_steps * world / (e2e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": e2e_games * 160,
